@@ -1,0 +1,56 @@
+// Internal declarations shared by the translation units of libgadm.so (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/gadm.h"
+
+namespace gadm {
+
+// error plumbing (gadm_api.cu)
+int set_cuda_error(cudaError_t e);           // records text, returns GADM_ERR_CUDA
+int check_launch();                          // cudaGetLastError() -> GADM_OK / GADM_ERR_CUDA
+bool initialised();
+
+// 3-D bf16 tensor map {inner = K, rows, batch}, box {box_k, box_rows, 1}, SWIZZLE_128B (gadm_api.cu)
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t batch,
+                      uint32_t box_k, uint32_t box_rows);
+
+// match_sm100.cu
+int match_configure();
+int match_launch(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols, const float* aux,
+                 const uint8_t* mask, const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma,
+                 int pad_mode, int mode, int64_t* idx, float* max_sim, float* weight, float* soft_xyz,
+                 cudaStream_t stream);
+
+// prep.cu
+int prep_rows_launch(const float* feat, int B, int d, int N, int operand_mode, int pad_mode, void* rows, float* rinv,
+                     float* pad_sim, cudaStream_t stream);
+int prep_model_launch(const float* mesh, const float* model_xyz, int n_obj, int d, int M, int operand_mode, void* cols,
+                      float* aux, cudaStream_t stream);
+int kabsch_moments_launch(const int64_t* idx, const uint8_t* mask, const float* cloud, const float* aux,
+                          const int32_t* obj_id, int B, int N, int M, int n_obj, double* out, cudaStream_t stream);
+
+// knn3d.cu
+int knn3d_configure();
+size_t knn3d_workspace_bytes(const gadm_knn_job* jobs, int n_jobs, int algo);
+int knn3d_launch(const float* support, const float* query, const gadm_knn_job* jobs, int n_jobs, int algo,
+                 int32_t* idx, float* dist2, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+// knn_feat.cu
+int knn_feat_configure();
+int knn_feat_launch(const float* x, int B, int C, int N, int kdim, int k, int64_t* idx, cudaStream_t stream);
+
+// gather.cu
+int graph_feature_launch(const float* x, const int64_t* idx, int B, int C, int N, int k, float* out,
+                         cudaStream_t stream);
+int group_fwd_launch(const float* features, const int32_t* idx, int b, int c, int n, int m, int s, float* out,
+                     cudaStream_t stream);
+int group_bwd_launch(const float* grad_out, const int32_t* idx, int b, int c, int n, int m, int s,
+                     float* grad_features, cudaStream_t stream);
+int gather_neighbour_launch(const float* pc, const int64_t* idx, int B, int N, int C, int M, int K, float* out,
+                            cudaStream_t stream);
+
+}  // namespace gadm

@@ -1,0 +1,329 @@
+// Fused matching head for sm_100a: descriptor similarity (tcgen05 UMMA, bf16 in / fp32 accumulate in TMEM,
+// operands staged by TMA) + row-wise argmax / online softmax / soft model coordinates in the epilogue.
+// The [N, M] score matrix never leaves TMEM/registers.
+//
+// Replaces (reference tree): evaluator.py:89-93 (normalize, normalize, matmul, torch.max) and the padded
+// variants utils/pvn3d_eval_utils_kpls.py:436-444 / models/geoMatch_DGCNN.py:92-99.  The softmax weight
+// and soft coordinates are the extension defined in oracle/match_oracle.py.
+//
+// Work decomposition
+//   CTA  = one 128-row tile of one frame (grid = ceil(N/128) x B), 6 warps:
+//     warp 0      TMA producer: the 128 x K' row tile once, then model tiles (256 verts x 64 k, 32 KB) through
+//                 an S-stage mbarrier ring, plus the per-tile aux table ({x,y,z,1/|m|} or 1/|m| only)
+//     warp 1      UMMA issuer: 128x256x16 tcgen05.mma, accumulators double-buffered in TMEM (2 x 256 columns)
+//     warps 2..5  epilogue: thread = row; tcgen05.ld 32 columns at a time; score = acc * (1/|m_j|); running
+//                 max / first argmax; (soft) online softmax in base 2 with the row scale gamma*log2e/|f_i| folded
+//                 into one FFMA, sum of weights and weight * xyz accumulated in fp32.
+#include "gadm_internal.h"
+#include "ptx.cuh"
+
+namespace gadm {
+
+namespace {
+
+constexpr int BM = 128;               // rows (scene points) per CTA == UMMA M
+constexpr int BN = 256;               // model vertices per accumulator tile == UMMA N
+constexpr int BK = 64;                // bf16 elements per 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_BLK_BYTES = BM * BK * 2;     // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
+constexpr int AUX_BYTES = BN * 16;           // 4 KB (float4 per vertex; argmax mode uses the first 1 KB)
+constexpr int AUX_SLOTS = 4;                // aux ring is decoupled from the 2 accumulators so TMA can run ahead
+constexpr int MAX_STAGES = 6;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+
+struct Barriers {
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
+  uint64_t a_full;
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint64_t aux_full[AUX_SLOTS];
+  uint64_t aux_empty[AUX_SLOTS];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+struct MatchParams {
+  const float* rinv_rows;  // [B, N]
+  const float* pad_sim;    // [B, N] or null
+  const float* aux;        // [n_obj, M, 4] then [n_obj, M]
+  const uint8_t* mask;     // [B, N] or null
+  const int32_t* obj_id;   // [B] or null
+  int64_t* idx;
+  float* max_sim;
+  float* weight;
+  float* soft_xyz;
+  int B, N, M, KB, n_obj, stages;
+  int pad_mode;
+  float gamma_log2e;
+};
+
+__device__ __forceinline__ int frame_object(const MatchParams& p, int b) {
+  if (p.obj_id) return p.obj_id[b];
+  return p.n_obj == p.B ? b : 0;
+}
+
+template <bool kSoft>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
+             const MatchParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B atoms need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + p.KB * A_BLK_BYTES;
+  uint8_t* smem_aux = smem_b + p.stages * B_STAGE_BYTES;
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_aux + AUX_SLOTS * AUX_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int row0 = blockIdx.x * BM;
+  const int obj = frame_object(p, b);
+  const int num_tiles = (p.M + BN - 1) / BN;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_rows);
+    ptx::prefetch_tensormap(&tmap_cols);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&bars->full[s], 1);
+      ptx::mbar_init(&bars->empty[s], 1);
+    }
+    ptx::mbar_init(&bars->a_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&bars->tmem_full[a], 1);
+      ptx::mbar_init(&bars->tmem_empty[a], 4);  // one arrive per epilogue warp
+    }
+    for (int a = 0; a < AUX_SLOTS; ++a) {
+      ptx::mbar_init(&bars->aux_full[a], 1);
+      ptx::mbar_init(&bars->aux_empty[a], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&bars->tmem_base, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(&bars->a_full, p.KB * A_BLK_BYTES);
+      for (int kb = 0; kb < p.KB; ++kb)
+        ptx::tma_load_3d(smem_a + kb * A_BLK_BYTES, &tmap_rows, &bars->a_full, kb * BK, row0, b);
+      int stage = 0;
+      uint32_t phase = 0;
+      const float* aux_tab = kSoft ? p.aux + size_t(obj) * p.M * 4
+                                   : p.aux + size_t(p.n_obj) * p.M * 4 + size_t(obj) * p.M;
+      const uint32_t aux_elt = kSoft ? 16u : 4u;
+      for (int t = 0; t < num_tiles; ++t) {
+        const int slot = t % AUX_SLOTS;
+        const uint32_t use = uint32_t(t) / AUX_SLOTS;
+        ptx::mbar_wait(&bars->aux_empty[slot], (use & 1) ^ 1);
+        const int nvalid = min(BN, p.M - t * BN);
+        ptx::mbar_arrive_expect_tx(&bars->aux_full[slot], nvalid * aux_elt);
+        ptx::bulk_load_1d(smem_aux + slot * AUX_BYTES,
+                          reinterpret_cast<const uint8_t*>(aux_tab) + size_t(t) * BN * aux_elt, nvalid * aux_elt,
+                          &bars->aux_full[slot]);
+        for (int kb = 0; kb < p.KB; ++kb) {
+          ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&bars->full[stage], B_STAGE_BYTES);
+          ptx::tma_load_3d(smem_b + stage * B_STAGE_BYTES, &tmap_cols, &bars->full[stage], kb * BK, t * BN, obj);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== UMMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(BM, BN);
+      ptx::mbar_wait(&bars->a_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < num_tiles; ++t) {
+        const int acc = t & 1;
+        const uint32_t use = uint32_t(t) >> 1;
+        ptx::mbar_wait(&bars->tmem_empty[acc], (use & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.KB; ++kb) {
+          ptx::mbar_wait(&bars->full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem_a + kb * A_BLK_BYTES);
+          const uint32_t b_addr = ptx::smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            ptx::umma_bf16_ss(d_tmem, ptx::umma_desc_sw128_kmajor(a_addr + k * UMMA_K * 2),
+                              ptx::umma_desc_sw128_kmajor(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0);
+          }
+          ptx::umma_commit(&bars->empty[stage]);  // frees the smem stage once these MMAs have read it
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&bars->tmem_full[acc]);  // accumulator tile complete
+      }
+    }
+  } else {
+    // ============================== epilogue (4 warps, thread == row) ==============================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = row0 + q * 32 + lane;
+    const bool row_ok = row < p.N;
+    const size_t grow = size_t(b) * p.N + (row_ok ? row : 0);
+    const float rs = row_ok ? p.rinv_rows[grow] : 0.f;
+    const float g = p.gamma_log2e * rs;  // exponent scale: t = score_colscaled * g  (log2 units)
+
+    float vmax = -INFINITY;
+    int vidx = 0;
+    float mrun = -INFINITY, lsum = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+
+    for (int t = 0; t < num_tiles; ++t) {
+      const int acc = t & 1;
+      const uint32_t use = uint32_t(t) >> 1;
+      const int slot = t % AUX_SLOTS;
+      ptx::mbar_wait(&bars->aux_full[slot], (uint32_t(t) / AUX_SLOTS) & 1);
+      ptx::mbar_wait(&bars->tmem_full[acc], use & 1);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+      const int ncols = min(BN, p.M - t * BN);
+      const float4* aux4 = reinterpret_cast<const float4*>(smem_aux + slot * AUX_BYTES);
+      const float* aux1 = reinterpret_cast<const float*>(smem_aux + slot * AUX_BYTES);
+
+      for (int c = 0; c < BN / 32; ++c) {
+        if (c * 32 >= ncols) break;  // uniform
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(taddr + c * 32, r);
+        ptx::tmem_ld_wait();
+        float v[32];
+        float cmx = -INFINITY;
+        if (kSoft) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * aux4[c * 32 + j].w;
+        } else {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 cm = reinterpret_cast<const float4*>(aux1)[c * 8 + j4];
+            v[j4 * 4 + 0] = __uint_as_float(r[j4 * 4 + 0]) * cm.x;
+            v[j4 * 4 + 1] = __uint_as_float(r[j4 * 4 + 1]) * cm.y;
+            v[j4 * 4 + 2] = __uint_as_float(r[j4 * 4 + 2]) * cm.z;
+            v[j4 * 4 + 3] = __uint_as_float(r[j4 * 4 + 3]) * cm.w;
+          }
+        }
+        if (c * 32 + 32 > ncols) {  // ragged last tile: columns >= M are zero-filled by TMA, exclude them
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j >= ncols) v[j] = -INFINITY;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) cmx = fmaxf(cmx, v[j]);
+        if (cmx > vmax) {  // strict: an equal value in a later chunk never displaces the first maximal index
+          vmax = cmx;
+          int jj = 31;
+#pragma unroll
+          for (int j = 30; j >= 0; --j)
+            if (v[j] == cmx) jj = j;
+          vidx = t * BN + c * 32 + jj;
+        }
+        if (kSoft) {
+          const float tnew = fmaxf(mrun, cmx * g);
+          const float sc = ptx::ex2_approx(mrun - tnew);
+          lsum *= sc; ax *= sc; ay *= sc; az *= sc;
+          mrun = tnew;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float4 m = aux4[c * 32 + j];
+            const float pj = ptx::ex2_approx(fmaf(v[j], g, -tnew));
+            lsum += pj;
+            ax = fmaf(pj, m.x, ax);
+            ay = fmaf(pj, m.y, ay);
+            az = fmaf(pj, m.z, az);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(&bars->tmem_empty[acc]);
+        ptx::mbar_arrive(&bars->aux_empty[slot]);
+      }
+    }
+
+    if (row_ok) {
+      const bool keep = p.mask == nullptr || p.mask[grow] != 0;
+      float best = vmax * rs;
+      int64_t best_idx = vidx;
+      if (p.pad_mode != GADM_PAD_NONE) {
+        const float ps = p.pad_sim[grow];
+        if (ps > best) { best = ps; best_idx = p.M; }  // pad column is the last one: wins only if strictly larger
+      }
+      p.idx[grow] = keep ? best_idx : int64_t(-1);
+      p.max_sim[grow] = keep ? best : 0.f;
+      if (kSoft) {
+        const float inv = 1.f / lsum;
+        p.weight[grow] = keep ? inv : 0.f;  // softmax value at the (real-column) maximum: exp2(0)/lsum
+        p.soft_xyz[grow * 3 + 0] = keep ? ax * inv : 0.f;
+        p.soft_xyz[grow * 3 + 1] = keep ? ay * inv : 0.f;
+        p.soft_xyz[grow * 3 + 2] = keep ? az * inv : 0.f;
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+size_t match_smem_bytes(int KB, int stages) {
+  return size_t(KB) * A_BLK_BYTES + size_t(stages) * B_STAGE_BYTES + AUX_SLOTS * AUX_BYTES + sizeof(Barriers) + 1024;
+}
+
+}  // namespace
+
+int match_configure() {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(match_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(match_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  return GADM_OK;
+}
+
+int match_launch(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols, const float* aux,
+                 const uint8_t* mask, const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma,
+                 int pad_mode, int mode, int64_t* idx, float* max_sim, float* weight, float* soft_xyz,
+                 cudaStream_t stream) {
+  const int KB = Kp / BK;
+  // pick the deepest ring that fits in 227 KB
+  int stages = MAX_STAGES;
+  while (stages > 2 && match_smem_bytes(KB, stages) > 227 * 1024) --stages;
+  if (match_smem_bytes(KB, stages) > 227 * 1024) return GADM_ERR_UNSUPPORTED;
+
+  CUtensorMap tmap_rows, tmap_cols;
+  int rc = make_tmap_bf16_3d(&tmap_rows, rows, uint64_t(Kp), uint64_t(N), uint64_t(B), BK, BM);
+  if (rc != GADM_OK) return rc;
+  rc = make_tmap_bf16_3d(&tmap_cols, cols, uint64_t(Kp), uint64_t(M), uint64_t(n_obj), BK, BN);
+  if (rc != GADM_OK) return rc;
+
+  MatchParams p;
+  p.rinv_rows = rinv_rows; p.pad_sim = pad_sim; p.aux = aux; p.mask = mask; p.obj_id = obj_id;
+  p.idx = idx; p.max_sim = max_sim; p.weight = weight; p.soft_xyz = soft_xyz;
+  p.B = B; p.N = N; p.M = M; p.KB = KB; p.n_obj = n_obj; p.stages = stages; p.pad_mode = pad_mode;
+  p.gamma_log2e = gamma * 1.4426950408889634f;
+
+  dim3 grid((N + BM - 1) / BM, B);
+  const size_t smem = match_smem_bytes(KB, stages);
+  if (mode == GADM_MATCH_SOFT)
+    match_kernel<true><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+  else
+    match_kernel<false><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+  return check_launch();
+}
+
+}  // namespace gadm

@@ -1,0 +1,164 @@
+// Operand preparation for the fused matcher (one pass each, HBM-bound):
+//   channel-major fp32 descriptors [G, d, P]  ->  point-major bf16 operands [G, P, K'] (TMA/UMMA K-major),
+//   fp32 inverse L2 norms (F.normalize eps = 1e-12, evaluator.py:89-90), the pad-column similarity
+//   (geoMatch.py:117-119 / geoMatch_DGCNN.py:95-98) on the scene side, and the {x,y,z,1/|m|} aux table on the
+//   model side.  Also the Kabsch moment reduction that follows the matcher
+//   (utils/pvn3d_eval_utils_kpls.py:57-63).
+#include <cuda_bf16.h>
+
+#include "gadm_internal.h"
+
+namespace gadm {
+
+namespace {
+
+constexpr int PTS = 32;  // points per CTA (one 128-byte line of every channel row)
+
+// side: 0 = scene rows ([hi|hi|lo] in x3 mode), 1 = model columns ([hi|lo|hi] in x3 mode)
+template <int kSide>
+__global__ void __launch_bounds__(256)
+prep_kernel(const float* __restrict__ src, const float* __restrict__ xyz, int d, int P, int x3, int pad_mode,
+            __nv_bfloat16* __restrict__ dst, float* __restrict__ rinv, float* __restrict__ pad_sim,
+            float* __restrict__ aux4, float* __restrict__ aux1) {
+  extern __shared__ float tile[];  // [d][PTS + 1]
+  const int g = blockIdx.y;
+  const int p0 = blockIdx.x * PTS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Kp = x3 ? 3 * d : d;
+
+  const float* s = src + size_t(g) * d * P;
+  for (int c = warp; c < d; c += 8) {
+    const int p = p0 + lane;
+    tile[c * (PTS + 1) + lane] = p < P ? s[size_t(c) * P + p] : 0.f;  // coalesced along points
+  }
+  __syncthreads();
+
+  for (int pl = warp; pl < PTS; pl += 8) {  // one warp per point
+    const int p = p0 + pl;
+    if (p >= P) break;  // warp-uniform
+    float ss = 0.f, sum = 0.f;
+    __nv_bfloat16* out = dst + (size_t(g) * P + p) * Kp;
+    for (int c = lane * 2; c < d; c += 64) {
+      const float v0 = tile[c * (PTS + 1) + pl], v1 = tile[(c + 1) * (PTS + 1) + pl];
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+      const float f0 = __bfloat162float(h0), f1 = __bfloat162float(h1);
+      __nv_bfloat162 hi;
+      hi.x = h0; hi.y = h1;
+      if (x3) {
+        __nv_bfloat162 lo;
+        lo.x = __float2bfloat16_rn(v0 - f0);
+        lo.y = __float2bfloat16_rn(v1 - f1);
+        // the operand the tensor core effectively sees is hi + lo
+        const float e0 = f0 + __bfloat162float(lo.x), e1 = f1 + __bfloat162float(lo.y);
+        ss += e0 * e0 + e1 * e1;
+        sum += e0 + e1;
+        *reinterpret_cast<__nv_bfloat162*>(out + c) = hi;
+        *reinterpret_cast<__nv_bfloat162*>(out + d + c) = kSide == 0 ? hi : lo;
+        *reinterpret_cast<__nv_bfloat162*>(out + 2 * d + c) = kSide == 0 ? lo : hi;
+      } else {
+        ss += f0 * f0 + f1 * f1;
+        sum += f0 + f1;
+        *reinterpret_cast<__nv_bfloat162*>(out + c) = hi;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if (lane == 0) {
+      const float r = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+      const size_t gp = size_t(g) * P + p;
+      if (kSide == 0) {
+        rinv[gp] = r;
+        if (pad_mode == GADM_PAD_MINUS_ONE) {
+          pad_sim[gp] = -sum * r * rsqrtf(float(d));
+        } else if (pad_mode == GADM_PAD_E0) {
+          const float v0 = tile[pl];
+          float e0 = __bfloat162float(__float2bfloat16_rn(v0));
+          if (x3) e0 += __bfloat162float(__float2bfloat16_rn(v0 - e0));
+          pad_sim[gp] = e0 * r;
+        }
+      } else {
+        float4 a;
+        a.x = xyz ? xyz[gp * 3 + 0] : 0.f;
+        a.y = xyz ? xyz[gp * 3 + 1] : 0.f;
+        a.z = xyz ? xyz[gp * 3 + 2] : 0.f;
+        a.w = r;
+        reinterpret_cast<float4*>(aux4)[gp] = a;
+        aux1[gp] = r;
+      }
+    }
+  }
+}
+
+// One CTA per frame: fp64 accumulation of n, sum A, sum B, sum A B^T over matched rows.
+__global__ void __launch_bounds__(256)
+kabsch_moments_kernel(const int64_t* __restrict__ idx, const uint8_t* __restrict__ mask,
+                      const float* __restrict__ cloud, const float* __restrict__ aux,
+                      const int32_t* __restrict__ obj_id, int B, int N, int M, int n_obj, double* __restrict__ out) {
+  const int b = blockIdx.x;
+  const int obj = obj_id ? obj_id[b] : (n_obj == B ? b : 0);
+  const float4* tab = reinterpret_cast<const float4*>(aux) + size_t(obj) * M;
+  double acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const size_t gn = size_t(b) * N + n;
+    const int64_t j = idx[gn];
+    if (j < 0 || j >= M) continue;
+    if (mask && !mask[gn]) continue;
+    const float4 a = tab[j];
+    const float bx = cloud[gn * 3 + 0], by = cloud[gn * 3 + 1], bz = cloud[gn * 3 + 2];
+    acc[0] += 1.0;
+    acc[1] += a.x; acc[2] += a.y; acc[3] += a.z;
+    acc[4] += bx; acc[5] += by; acc[6] += bz;
+    acc[7] += double(a.x) * bx;  acc[8] += double(a.x) * by;  acc[9] += double(a.x) * bz;
+    acc[10] += double(a.y) * bx; acc[11] += double(a.y) * by; acc[12] += double(a.y) * bz;
+    acc[13] += double(a.z) * bx; acc[14] += double(a.z) * by; acc[15] += double(a.z) * bz;
+  }
+  __shared__ double red[8][16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];  // fixed order: deterministic
+    out[size_t(b) * 16 + threadIdx.x] = v;
+  }
+}
+
+}  // namespace
+
+int prep_rows_launch(const float* feat, int B, int d, int N, int operand_mode, int pad_mode, void* rows, float* rinv,
+                     float* pad_sim, cudaStream_t stream) {
+  dim3 grid((N + PTS - 1) / PTS, B);
+  const size_t smem = size_t(d) * (PTS + 1) * sizeof(float);
+  prep_kernel<0><<<grid, 256, smem, stream>>>(feat, nullptr, d, N, operand_mode == GADM_OPERAND_BF16X3, pad_mode,
+                                              static_cast<__nv_bfloat16*>(rows), rinv, pad_sim, nullptr, nullptr);
+  return check_launch();
+}
+
+int prep_model_launch(const float* mesh, const float* model_xyz, int n_obj, int d, int M, int operand_mode, void* cols,
+                      float* aux, cudaStream_t stream) {
+  dim3 grid((M + PTS - 1) / PTS, n_obj);
+  const size_t smem = size_t(d) * (PTS + 1) * sizeof(float);
+  prep_kernel<1><<<grid, 256, smem, stream>>>(mesh, model_xyz, d, M, operand_mode == GADM_OPERAND_BF16X3, 0,
+                                              static_cast<__nv_bfloat16*>(cols), nullptr, nullptr, aux,
+                                              aux + size_t(n_obj) * M * 4);
+  return check_launch();
+}
+
+int kabsch_moments_launch(const int64_t* idx, const uint8_t* mask, const float* cloud, const float* aux,
+                          const int32_t* obj_id, int B, int N, int M, int n_obj, double* out, cudaStream_t stream) {
+  kabsch_moments_kernel<<<B, 256, 0, stream>>>(idx, mask, cloud, aux, obj_id, B, N, M, n_obj, out);
+  return check_launch();
+}
+
+}  // namespace gadm

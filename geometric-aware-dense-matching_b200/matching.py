@@ -1,0 +1,169 @@
+"""Host side of the geoMatch matching head, mirroring the reference interfaces.
+
+  match(...)              the fused matcher (new entry point)
+  ModelBank               per-object descriptors + xyz prepared once (the reference keeps `models_3d` and
+                          mesh features per class id: evaluator.py:28-58, train_lm.py:331-340)
+  cal_frame_poses(item)   drop-in for evaluator.cal_frame_poses (evaluator.py:60-102): same item tuple,
+                          same early-outs and sentinel pose, returns the [3,4] pose
+  best_fit_transform      Kabsch from GPU-accumulated moments (utils/pvn3d_eval_utils_kpls.py:43-76)
+  GeoMatch                nn.Module with the reference's forward signature and end_points keys
+                          (models/geoMatch.py:159-200) around pluggable embedding networks
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import MATCH_MODES, OPERAND_MODES, PAD_MODES
+
+
+class ModelBank:
+    """Model-side operands for n_obj objects: bf16 descriptors [n_obj, M, K'] + aux {x,y,z,1/|m|}."""
+
+    def __init__(self, mesh_features, model_xyz, operand_mode="bf16"):
+        if mesh_features.dim() == 2:
+            mesh_features = mesh_features.unsqueeze(0)
+        if model_xyz.dim() == 2:
+            model_xyz = model_xyz.unsqueeze(0)
+        self.n_obj, self.d, self.M = mesh_features.shape
+        self.operand_mode = operand_mode
+        self.model_xyz = model_xyz.contiguous().float()
+        self.cols, self.aux = ops.prep_model(mesh_features.contiguous().float(), self.model_xyz,
+                                             OPERAND_MODES[operand_mode])
+
+    @property
+    def device(self):
+        return self.cols.device
+
+
+def match(rgbd, mesh, model_xyz=None, obj_id=None, mask=None, gamma=16.0, pad_mode="none",
+          operand_mode="bf16", mode="soft"):
+    """Dense scene-to-model correspondence.
+
+    rgbd [B, d, N] fp32 (end_points['rgbd']); mesh: ModelBank, or [n_obj | 1, d, M] fp32 (end_points['mesh'])
+    with model_xyz [n_obj, M, 3]; obj_id int [B] selects the object per frame; mask [B, N] (bool/uint8)
+    marks rows to match (others get idx = -1).
+    Returns (idx int64 [B,N], max_sim f32 [B,N], weight f32 [B,N], soft_xyz f32 [B,N,3]); with
+    mode="argmax" weight/soft_xyz are None (the reference's hard-argmax path, evaluator.py:89-93).
+    idx == M means the pad column won (pad_mode "minus_one" / "e0")."""
+    if rgbd.dim() == 2:
+        rgbd = rgbd.unsqueeze(0)
+    bank = mesh if isinstance(mesh, ModelBank) else ModelBank(
+        mesh, model_xyz if model_xyz is not None else
+        torch.zeros((mesh.shape[0] if mesh.dim() == 3 else 1, mesh.shape[-1], 3), device=mesh.device),
+        operand_mode)
+    if bank.operand_mode != operand_mode:
+        raise ValueError(f"bank was prepared with operand_mode={bank.operand_mode!r}")
+    B, d, N = rgbd.shape
+    if d != bank.d:
+        raise ValueError(f"descriptor dim mismatch: scene {d} vs model {bank.d}")
+    pm = PAD_MODES[pad_mode]
+    rows, rinv, pad_sim = ops.prep_rows(rgbd.contiguous().float(), OPERAND_MODES[operand_mode], pm)
+    if mask is not None:
+        mask = mask.to(torch.uint8).contiguous()
+    if obj_id is not None:
+        obj_id = torch.as_tensor(obj_id, device=rgbd.device).to(torch.int32).contiguous()
+    idx, max_sim, weight, soft_xyz = ops.match_fwd(rows, rinv, pad_sim, bank.cols, bank.aux, mask, obj_id,
+                                                   float(gamma), pm, MATCH_MODES[mode])
+    if mode == "argmax":
+        return idx, max_sim, None, None
+    return idx, max_sim, weight, soft_xyz
+
+
+def rt_from_moments(mom):
+    """best_fit_transform (utils/pvn3d_eval_utils_kpls.py:43-76) from {n, sum A, sum B, sum A B^T}.
+    mom: float64 [16] (numpy).  H = AA^T BB = sum(A B^T) - n cA cB^T."""
+    n = mom[0]
+    ca, cb = mom[1:4] / n, mom[4:7] / n
+    H = mom[7:16].reshape(3, 3) - n * np.outer(ca, cb)
+    U, S, Vt = np.linalg.svd(H)
+    R = Vt.T @ U.T
+    if np.linalg.det(R) < 0:
+        Vt[2, :] *= -1
+        R = Vt.T @ U.T
+    T = np.zeros((3, 4))
+    T[:, :3] = R
+    T[:, 3] = cb - R @ ca
+    return T
+
+
+def sentinel_pose():
+    """evaluator.py:69-71: identity rotation, t_z = -1000."""
+    rt = np.eye(4, dtype=np.float32)
+    rt[2, 3] = -1000
+    return rt[:3, :]
+
+
+def frame_poses(cld, seg, rgbd, bank, obj_id=None, det=None, min_pts=5):
+    """Batched evaluator.cal_frame_poses: cld [B,>=3,N], seg [B,2,N], rgbd [B,d,N] -> list of [3,4] poses.
+    One matcher launch + one moment launch + ONE device->host copy for the whole batch (the reference
+    syncs per frame at evaluator.py:83, :87, :99)."""
+    B, _, N = rgbd.shape
+    mask = (torch.argmax(seg, dim=1) == 1)                                   # evaluator.py:78,82
+    idx, _, _, _ = match(rgbd, bank, obj_id=obj_id, mask=mask, mode="argmax", operand_mode=bank.operand_mode)
+    cloud = cld[:, :3, :].transpose(1, 2).contiguous().float()               # evaluator.py:85
+    oid = None if obj_id is None else torch.as_tensor(obj_id, device=rgbd.device).to(torch.int32)
+    mom = ops.kabsch_moments(idx, mask.to(torch.uint8), cloud, bank.aux, oid, bank.M, bank.n_obj).cpu().numpy()
+    poses = []
+    for b in range(B):
+        n_sel = mom[b, 0]
+        if (det is not None and not bool(det[b])) or n_sel <= 1 or n_sel < min_pts:  # :72, :83, :96
+            poses.append(sentinel_pose())
+        else:
+            poses.append(rt_from_moments(mom[b]).astype(np.float32))
+    return poses
+
+
+def cal_frame_poses(item, bank):
+    """Drop-in for evaluator.cal_frame_poses(item) (evaluator.py:60-102); item =
+    (cld [>=3,N], seg_features [2,N], mesh_features (unused: the bank holds them), rgbd_features [d,N],
+     cls_id, det).  `bank` is indexed by obj_id = cls_id when it holds more than one object."""
+    cld, seg_features, _mesh, rgbd_features, cls_id, det = item
+    if not det:
+        return sentinel_pose()
+    oid = None if bank.n_obj == 1 else [int(cls_id)]
+    return frame_poses(cld[None], seg_features[None], rgbd_features[None], bank, obj_id=oid, det=[det])[0]
+
+
+class GeoMatch(nn.Module):
+    """The reference's GeoMatch forward contract (models/geoMatch.py:159-200, geoMatch_DGCNN.py:138-183) around
+    pluggable embedding networks (the FFB6D / SplineCNN / DGCNN backbones are out of scope).
+
+    pcd_emb(inputs) -> [B, C_emb, N]; model_emb() -> [d, M].  Heads keep the reference's layer names
+    (seg_layer, feature_encoding_layer, normalize_feature_layer) so checkpoints load unchanged when the
+    same head modules are supplied.  forward(inputs, end_points=None) returns end_points with
+    'seg' [B,2,N], 'mesh' [1,d,M], 'rgbd' [B,d,N]; in eval mode with match_in_forward=True it adds
+    'match_idx', 'match_sim', 'match_weight', 'match_xyz' from the fused kernel."""
+
+    def __init__(self, pcd_emb, model_emb, feature_encoding_layer, seg_layer, normalize_feature_layer=None,
+                 model_xyz=None, match_in_forward=False, gamma=16.0, operand_mode="bf16"):
+        super().__init__()
+        self.pcd_emb, self.model_emb = pcd_emb, model_emb
+        self.feature_encoding_layer, self.seg_layer = feature_encoding_layer, seg_layer
+        self.normalize_feature_layer = normalize_feature_layer
+        self.match_in_forward, self.gamma, self.operand_mode = match_in_forward, gamma, operand_mode
+        if model_xyz is not None:
+            self.register_buffer("xyz", model_xyz.float())
+        else:
+            self.xyz = None
+
+    def forward(self, inputs, end_points=None):
+        if not end_points:
+            end_points = {}
+        rgbd_emb = self.pcd_emb(inputs)                                   # geoMatch.py:178
+        mesh_features = self.model_emb()                                  # :179
+        rgbd_features = self.feature_encoding_layer(rgbd_emb)             # :180
+        if self.normalize_feature_layer is not None:
+            rgbd_emb = rgbd_emb + self.normalize_feature_layer(rgbd_features)   # :181-182
+        seg_features = self.seg_layer(rgbd_emb)                           # :183
+        mesh_features = mesh_features.unsqueeze(0)                        # :184
+        end_points['seg'] = seg_features
+        end_points['mesh'] = mesh_features
+        end_points['rgbd'] = rgbd_features
+        if self.match_in_forward and not self.training:
+            xyz = self.xyz if self.xyz is not None else None
+            mask = torch.argmax(seg_features, dim=1) == 1
+            idx, sim, w, sxyz = match(rgbd_features.detach(), mesh_features.detach(), xyz, mask=mask,
+                                      gamma=self.gamma, operand_mode=self.operand_mode)
+            end_points.update(match_idx=idx, match_sim=sim, match_weight=w, match_xyz=sxyz)
+        return end_points

@@ -1,0 +1,287 @@
+"""PyTorch custom ops (`torch.ops.gadm.*`) over the C ABI.  CUDA only; shape inference via register_fake.
+
+Tensors are validated here (dtype / contiguity / device); the C side validates sizes and alignment and
+returns error codes that become GadmError.  All ops enqueue on torch's current stream."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import KnnJob, PAD_MODES, OPERAND_MODES, MATCH_MODES, KNN_ALGOS  # noqa: F401
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need(t, dtype, name):
+    if not t.is_cuda:
+        raise _lib.GadmError(f"{name}: expected a CUDA tensor (libgadm has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: must be contiguous")
+
+
+def _lib_for(t):
+    return _lib.ensure_init(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+# --------------------------------------------------------------------------------------------- matching
+@torch.library.custom_op("gadm::prep_rows", mutates_args=(), device_types="cuda")
+def prep_rows(feat: torch.Tensor, operand_mode: int, pad_mode: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    _need(feat, torch.float32, "feat")
+    B, d, N = feat.shape
+    lib = _lib_for(feat)
+    kp = lib.gadm_operand_k(d, operand_mode)
+    _lib.check(min(kp, 0), "gadm_operand_k")
+    rows = torch.empty((B, N, kp), dtype=torch.bfloat16, device=feat.device)
+    rinv = torch.empty((B, N), dtype=torch.float32, device=feat.device)
+    pad_sim = torch.empty((B, N) if pad_mode else (0,), dtype=torch.float32, device=feat.device)
+    with torch.cuda.device(feat.device):
+        _lib.check(lib.gadm_prep_rows(_ptr(feat), B, d, N, operand_mode, pad_mode, _ptr(rows), _ptr(rinv),
+                                      _ptr(pad_sim) if pad_mode else None, _stream()), "gadm_prep_rows")
+    return rows, rinv, pad_sim
+
+
+@prep_rows.register_fake
+def _(feat, operand_mode, pad_mode):
+    B, d, N = feat.shape
+    kp = d * (3 if operand_mode == 1 else 1)
+    return (feat.new_empty((B, N, kp), dtype=torch.bfloat16), feat.new_empty((B, N)),
+            feat.new_empty((B, N) if pad_mode else (0,)))
+
+
+@torch.library.custom_op("gadm::prep_model", mutates_args=(), device_types="cuda")
+def prep_model(mesh: torch.Tensor, model_xyz: torch.Tensor, operand_mode: int) -> tuple[torch.Tensor, torch.Tensor]:
+    _need(mesh, torch.float32, "mesh")
+    _need(model_xyz, torch.float32, "model_xyz")
+    n_obj, d, M = mesh.shape
+    if tuple(model_xyz.shape) != (n_obj, M, 3):
+        raise ValueError(f"model_xyz must be [{n_obj}, {M}, 3], got {tuple(model_xyz.shape)}")
+    lib = _lib_for(mesh)
+    kp = lib.gadm_operand_k(d, operand_mode)
+    _lib.check(min(kp, 0), "gadm_operand_k")
+    cols = torch.empty((n_obj, M, kp), dtype=torch.bfloat16, device=mesh.device)
+    aux = torch.empty((n_obj * M * 5,), dtype=torch.float32, device=mesh.device)
+    with torch.cuda.device(mesh.device):
+        _lib.check(lib.gadm_prep_model(_ptr(mesh), _ptr(model_xyz), n_obj, d, M, operand_mode, _ptr(cols), _ptr(aux),
+                                       _stream()), "gadm_prep_model")
+    return cols, aux
+
+
+@prep_model.register_fake
+def _(mesh, model_xyz, operand_mode):
+    n_obj, d, M = mesh.shape
+    kp = d * (3 if operand_mode == 1 else 1)
+    return mesh.new_empty((n_obj, M, kp), dtype=torch.bfloat16), mesh.new_empty((n_obj * M * 5,))
+
+
+@torch.library.custom_op("gadm::match_fwd", mutates_args=(), device_types="cuda")
+def match_fwd(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tensor, cols: torch.Tensor, aux: torch.Tensor,
+              mask: torch.Tensor | None, obj_id: torch.Tensor | None, gamma: float, pad_mode: int,
+              mode: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    _need(rows, torch.bfloat16, "rows"); _need(cols, torch.bfloat16, "cols")
+    _need(rinv, torch.float32, "rinv"); _need(aux, torch.float32, "aux")
+    B, N, kp = rows.shape
+    n_obj, M, kp2 = cols.shape
+    if kp != kp2:
+        raise ValueError(f"operand K mismatch: rows {kp} vs cols {kp2}")
+    if mask is not None:
+        _need(mask, torch.uint8, "mask")
+        if tuple(mask.shape) != (B, N):
+            raise ValueError("mask must be [B, N]")
+    if obj_id is not None:
+        _need(obj_id, torch.int32, "obj_id")
+        if tuple(obj_id.shape) != (B,):
+            raise ValueError("obj_id must be [B]")
+    dev = rows.device
+    idx = torch.empty((B, N), dtype=torch.int64, device=dev)
+    max_sim = torch.empty((B, N), dtype=torch.float32, device=dev)
+    soft = mode == 1
+    weight = torch.empty((B, N) if soft else (0,), dtype=torch.float32, device=dev)
+    soft_xyz = torch.empty((B, N, 3) if soft else (0,), dtype=torch.float32, device=dev)
+    lib = _lib_for(rows)
+    with torch.cuda.device(dev):
+        _lib.check(lib.gadm_match_fwd(_ptr(rows), _ptr(rinv), _ptr(pad_sim) if pad_mode else None, _ptr(cols),
+                                      _ptr(aux), _ptr(mask), _ptr(obj_id), B, N, M, kp, n_obj, float(gamma),
+                                      pad_mode, mode, _ptr(idx), _ptr(max_sim), _ptr(weight) if soft else None,
+                                      _ptr(soft_xyz) if soft else None, _stream()), "gadm_match_fwd")
+    return idx, max_sim, weight, soft_xyz
+
+
+@match_fwd.register_fake
+def _(rows, rinv, pad_sim, cols, aux, mask, obj_id, gamma, pad_mode, mode):
+    B, N, _ = rows.shape
+    soft = mode == 1
+    return (rows.new_empty((B, N), dtype=torch.int64), rows.new_empty((B, N), dtype=torch.float32),
+            rows.new_empty((B, N) if soft else (0,), dtype=torch.float32),
+            rows.new_empty((B, N, 3) if soft else (0,), dtype=torch.float32))
+
+
+@torch.library.custom_op("gadm::kabsch_moments", mutates_args=(), device_types="cuda")
+def kabsch_moments(idx: torch.Tensor, mask: torch.Tensor | None, cloud: torch.Tensor, aux: torch.Tensor,
+                   obj_id: torch.Tensor | None, M: int, n_obj: int) -> torch.Tensor:
+    _need(idx, torch.int64, "idx"); _need(cloud, torch.float32, "cloud"); _need(aux, torch.float32, "aux")
+    B, N = idx.shape
+    if tuple(cloud.shape) != (B, N, 3):
+        raise ValueError("cloud must be [B, N, 3]")
+    out = torch.empty((B, 16), dtype=torch.float64, device=idx.device)
+    lib = _lib_for(idx)
+    with torch.cuda.device(idx.device):
+        _lib.check(lib.gadm_kabsch_moments(_ptr(idx), _ptr(mask), _ptr(cloud), _ptr(aux), _ptr(obj_id), B, N, M,
+                                           n_obj, _ptr(out), _stream()), "gadm_kabsch_moments")
+    return out
+
+
+@kabsch_moments.register_fake
+def _(idx, mask, cloud, aux, obj_id, M, n_obj):
+    return idx.new_empty((idx.shape[0], 16), dtype=torch.float64)
+
+
+# --------------------------------------------------------------------------------------------- kNN 3-D
+def make_jobs(job_list):
+    """[(support_off, query_off, out_off, s_bstride, q_bstride, o_bstride, n_support, n_query, k, batch)]."""
+    arr = (KnnJob * len(job_list))()
+    for a, j in zip(arr, job_list):
+        (a.support_off, a.query_off, a.out_off, a.support_bstride, a.query_bstride, a.out_bstride,
+         a.n_support, a.n_query, a.k, a.batch) = j
+    return arr
+
+
+def knn3d_jobs(support, query, jobs, out_elems, algo="auto", return_dist=False, workspace=None):
+    """Run a job table over flat point buffers.  support/query: [P, 3] fp32 CUDA; returns int32 [out_elems]."""
+    _need(support, torch.float32, "support"); _need(query, torch.float32, "query")
+    lib = _lib_for(support)
+    a = KNN_ALGOS[algo] if isinstance(algo, str) else int(algo)
+    need = lib.gadm_knn3d_workspace_bytes(jobs, len(jobs), a)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty((max(need, 16),), dtype=torch.uint8, device=support.device)
+    idx = torch.empty((out_elems,), dtype=torch.int32, device=support.device)
+    d2 = torch.empty((out_elems,), dtype=torch.float32, device=support.device) if return_dist else None
+    with torch.cuda.device(support.device):
+        _lib.check(lib.gadm_knn3d(_ptr(support), _ptr(query), jobs, len(jobs), a, _ptr(idx), _ptr(d2),
+                                  _ptr(workspace), workspace.numel(), _stream()), "gadm_knn3d")
+    return (idx, d2) if return_dist else idx
+
+
+@torch.library.custom_op("gadm::knn3d", mutates_args=(), device_types="cuda")
+def knn3d(support: torch.Tensor, query: torch.Tensor, k: int, algo: int) -> torch.Tensor:
+    """support [B, N1, 3], query [B, N2, 3] -> int32 [B, N2, k]."""
+    B, n1, _ = support.shape
+    n2 = query.shape[1]
+    jobs = make_jobs([(0, 0, 0, n1, n2, n2 * k, n1, n2, k, B)])
+    return knn3d_jobs(support.view(-1, 3), query.view(-1, 3), jobs, B * n2 * k, algo).view(B, n2, k)
+
+
+@knn3d.register_fake
+def _(support, query, k, algo):
+    return support.new_empty((support.shape[0], query.shape[1], k), dtype=torch.int32)
+
+
+# --------------------------------------------------------------------------------------------- DGCNN
+@torch.library.custom_op("gadm::knn_feat", mutates_args=(), device_types="cuda")
+def knn_feat(x: torch.Tensor, k: int, kdim: int) -> torch.Tensor:
+    _need(x, torch.float32, "x")
+    B, C, N = x.shape
+    idx = torch.empty((B, N, k), dtype=torch.int64, device=x.device)
+    lib = _lib_for(x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.gadm_knn_feat(_ptr(x), B, C, N, kdim, k, _ptr(idx), _stream()), "gadm_knn_feat")
+    return idx
+
+
+@knn_feat.register_fake
+def _(x, k, kdim):
+    return x.new_empty((x.shape[0], x.shape[2], k), dtype=torch.int64)
+
+
+@torch.library.custom_op("gadm::graph_feature", mutates_args=(), device_types="cuda")
+def graph_feature(x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    _need(x, torch.float32, "x"); _need(idx, torch.int64, "idx")
+    B, C, N = x.shape
+    k = idx.shape[2]
+    out = torch.empty((B, 2 * C, N, k), dtype=torch.float32, device=x.device)
+    lib = _lib_for(x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.gadm_graph_feature(_ptr(x), _ptr(idx), B, C, N, k, _ptr(out), _stream()),
+                   "gadm_graph_feature")
+    return out
+
+
+@graph_feature.register_fake
+def _(x, idx):
+    B, C, N = x.shape
+    return x.new_empty((B, 2 * C, N, idx.shape[2]))
+
+
+# --------------------------------------------------------------------------------------------- grouping
+@torch.library.custom_op("gadm::group_fwd", mutates_args=(), device_types="cuda")
+def group_fwd(features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    _need(features, torch.float32, "features"); _need(idx, torch.int32, "idx")
+    b, c, n = features.shape
+    _, m, s = idx.shape
+    out = torch.empty((b, c, m, s), dtype=torch.float32, device=features.device)
+    lib = _lib_for(features)
+    with torch.cuda.device(features.device):
+        _lib.check(lib.gadm_group_fwd(_ptr(features), _ptr(idx), b, c, n, m, s, _ptr(out), _stream()),
+                   "gadm_group_fwd")
+    return out
+
+
+@group_fwd.register_fake
+def _(features, idx):
+    return features.new_empty((features.shape[0], features.shape[1], idx.shape[1], idx.shape[2]))
+
+
+@torch.library.custom_op("gadm::group_bwd", mutates_args=(), device_types="cuda")
+def group_bwd(grad_out: torch.Tensor, idx: torch.Tensor, n: int) -> torch.Tensor:
+    _need(grad_out, torch.float32, "grad_out"); _need(idx, torch.int32, "idx")
+    b, c, m, s = grad_out.shape
+    gf = torch.empty((b, c, n), dtype=torch.float32, device=grad_out.device)
+    lib = _lib_for(grad_out)
+    with torch.cuda.device(grad_out.device):
+        _lib.check(lib.gadm_group_bwd(_ptr(grad_out), _ptr(idx), b, c, n, m, s, _ptr(gf), _stream()),
+                   "gadm_group_bwd")
+    return gf
+
+
+@group_bwd.register_fake
+def _(grad_out, idx, n):
+    return grad_out.new_empty((grad_out.shape[0], grad_out.shape[1], n))
+
+
+def _group_setup(ctx, inputs, output):
+    features, idx = inputs
+    ctx.save_for_backward(idx)
+    ctx.n = features.shape[2]
+
+
+def _group_backward(ctx, grad):
+    (idx,) = ctx.saved_tensors
+    return group_bwd(grad.contiguous(), idx, ctx.n), None
+
+
+group_fwd.register_autograd(_group_backward, setup_context=_group_setup)
+
+
+@torch.library.custom_op("gadm::gather_neighbour", mutates_args=(), device_types="cuda")
+def gather_neighbour(pc: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    _need(pc, torch.float32, "pc"); _need(idx, torch.int64, "idx")
+    B, N, C = pc.shape
+    _, M, K = idx.shape
+    out = torch.empty((B, M, K, C), dtype=torch.float32, device=pc.device)
+    lib = _lib_for(pc)
+    with torch.cuda.device(pc.device):
+        _lib.check(lib.gadm_gather_neighbour(_ptr(pc), _ptr(idx), B, N, C, M, K, _ptr(out), _stream()),
+                   "gadm_gather_neighbour")
+    return out
+
+
+@gather_neighbour.register_fake
+def _(pc, idx):
+    return pc.new_empty((pc.shape[0], idx.shape[1], idx.shape[2], pc.shape[2]))

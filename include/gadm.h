@@ -1,0 +1,160 @@
+/*
+ * gadm.h -- C ABI of libgadm.so: the B200 (sm_100a) implementation of the scene-to-model dense
+ * correspondence path of Ray0089/geometric-aware-dense-matching (geoMatch matching head + geometric kNN).
+ *
+ * Every entry point below replaces one reference interface (file:line relative to the reference tree):
+ *
+ *   gadm_prep_rows / gadm_prep_model / gadm_match_fwd
+ *       evaluator.py:77-93            cal_frame_poses: normalize rows, normalize columns, matmul, torch.max
+ *       utils/pvn3d_eval_utils_kpls.py:436-444, models/geoMatch.py:117-119   "-1" pad column variant
+ *       models/geoMatch_DGCNN.py:92-99                                       "e0" pad column variant
+ *       (+ the soft-correspondence extension: softmax weights and soft model coordinates)
+ *   gadm_kabsch
+ *       utils/pvn3d_eval_utils_kpls.py:43-76   best_fit_transform (moments here; 3x3 SVD on the host side)
+ *   gadm_knn3d
+ *       models/RandLA/utils/nearest_neighbors/knn_.h:11-17 / knn_.cxx:71-135   cpp_knn_batch(_omp)
+ *       models/RandLA/helper_tool.py:161-170                                   DataProcessing.knn_search
+ *       lib/pointops/functions/pointops.py:435-493                             knnquery / knnquery_heap
+ *   gadm_knn_feat
+ *       models/dgcnn.py:21-27         knn (feature-space dynamic-graph kNN)
+ *   gadm_graph_feature
+ *       models/dgcnn.py:30-56         get_graph_feature (gather + cat(nbr - x, x))
+ *   gadm_group_fwd / gadm_group_bwd
+ *       lib/pointops/functions/pointops.py:149-178   Grouping.forward / backward
+ *   gadm_gather_neighbour
+ *       models/RandLA/RandLANet.py:729-738           Building_block.gather_neighbour
+ *
+ * Conventions
+ *   - All tensor pointers are DEVICE pointers unless a parameter says HOST.  The caller owns all memory,
+ *     including workspaces; the library never allocates or frees device memory and never synchronises.
+ *   - Every call enqueues work on `stream` and returns 0 (GADM_OK) or a negative gadm_status.  No exceptions.
+ *   - Re-entrant: no mutable global state after gadm_init().
+ *   - The cubin is sm_100a only.  gadm_init() fails with GADM_ERR_ARCH elsewhere; there is no fallback.
+ */
+#ifndef GADM_H_
+#define GADM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* gadm_stream_t; /* == cudaStream_t */
+
+typedef enum {
+  GADM_OK = 0,
+  GADM_ERR_BAD_ARG = -1,     /* null pointer, non-positive size, inconsistent shapes            */
+  GADM_ERR_UNSUPPORTED = -2, /* d not a multiple of 64 / too large, k > 32, unknown mode ...    */
+  GADM_ERR_ALIGN = -3,       /* pointer not aligned as documented                               */
+  GADM_ERR_WORKSPACE = -4,   /* workspace too small                                             */
+  GADM_ERR_CUDA = -5,        /* a CUDA runtime / driver call or the launch failed               */
+  GADM_ERR_ARCH = -6,        /* device is not compute capability 10.x                           */
+  GADM_ERR_NOT_INIT = -7     /* gadm_init() has not succeeded on this process                   */
+} gadm_status;
+
+const char* gadm_strerror(int status);
+int gadm_abi_version(void);
+/* Checks the device (cc 10.x), resolves cuTensorMapEncodeTiled, raises the kernels' shared-memory limits. */
+int gadm_init(int device);
+/* cudaGetLastError text of the most recent GADM_ERR_CUDA on this thread ("" if none). */
+const char* gadm_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Matching head
+ * ------------------------------------------------------------------------------------------------ */
+enum { GADM_PAD_NONE = 0, GADM_PAD_MINUS_ONE = 1, GADM_PAD_E0 = 2 };
+/* operand_mode: how fp32 descriptors become bf16 tensor-core operands.
+ *   BF16   : round once to bf16 (exact if the inputs are bf16-representable); K' = d
+ *   BF16X3 : hi/lo split, operands [hi|hi|lo] x [hi|lo|hi]; K' = 3d; ~fp32-faithful (error ~1e-6)  */
+enum { GADM_OPERAND_BF16 = 0, GADM_OPERAND_BF16X3 = 1 };
+/* outputs: ARGMAX = idx + max_sim only (the reference's path); SOFT adds weight + soft_xyz. */
+enum { GADM_MATCH_ARGMAX = 0, GADM_MATCH_SOFT = 1 };
+
+/* K' for a given d / operand_mode (d for BF16, 3d for BF16X3). */
+int gadm_operand_k(int d, int operand_mode);
+
+/* Scene side.  feat [B, d, N] fp32 channel-major (end_points['rgbd'], models/geoMatch.py:199).
+ *   rows  [B, N, K'] bf16   point-major operand (16-byte aligned)
+ *   rinv  [B, N] fp32       1 / max(||f||, 1e-12)  (F.normalize eps, evaluator.py:89)
+ *   pad_sim [B, N] fp32 or NULL: similarity of each row with the pad column (pad_mode != NONE)       */
+int gadm_prep_rows(const float* feat, int B, int d, int N, int operand_mode, int pad_mode, void* rows,
+                   float* rinv, float* pad_sim, gadm_stream_t stream);
+
+/* Model side (once per object bank).  mesh [n_obj, d, M] fp32 channel-major (end_points['mesh']);
+ * model_xyz [n_obj, M, 3] fp32 or NULL.
+ *   cols [n_obj, M, K'] bf16 ; aux [n_obj, M, 4] fp32 = {x, y, z, 1/max(||m||,1e-12)} (16-byte aligned) */
+int gadm_prep_model(const float* mesh, const float* model_xyz, int n_obj, int d, int M, int operand_mode,
+                    void* cols, float* aux, gadm_stream_t stream);
+
+/* Fused similarity + row-wise argmax / online softmax / soft coordinates.  The [N, M] score matrix never
+ * exists in HBM.  For frame b the model is obj_id[b] (NULL: b if n_obj == B, else 0).
+ *   mask [B, N] uint8 or NULL: rows with mask == 0 get idx = -1 and zeros.
+ *   idx [B, N] int64 (M means "pad column won"), max_sim [B, N] fp32,
+ *   weight [B, N] fp32 and soft_xyz [B, N, 3] fp32 (may be NULL when mode == GADM_MATCH_ARGMAX).
+ * Kp = K' from gadm_operand_k(); must be a multiple of 64 and <= 768.                                 */
+int gadm_match_fwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
+                   const float* aux, const uint8_t* mask, const int32_t* obj_id, int B, int N, int M, int Kp,
+                   int n_obj, float gamma, int pad_mode, int mode, int64_t* idx, float* max_sim, float* weight,
+                   float* soft_xyz, gadm_stream_t stream);
+
+/* Moments for the least-squares pose fit that follows the matcher (best_fit_transform): per frame, over rows
+ * with idx in [0, M) (and mask != 0):  n, sum A, sum B, sum A B^T  with A = model xyz[idx], B = cloud point.
+ *   cloud [B, N, 3] fp32; out [B, 16] fp64 = {n, sA[3], sB[3], sAB[9]}  (zeroed by the callee)           */
+int gadm_kabsch_moments(const int64_t* idx, const uint8_t* mask, const float* cloud, const float* aux,
+                        const int32_t* obj_id, int B, int N, int M, int n_obj, double* out,
+                        gadm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Exact 3-D kNN (RandLA nearest_neighbors / pointops knnquery)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t support_off; /* in points, relative to `support`                                       */
+  int64_t query_off;   /* in points, relative to `query`                                         */
+  int64_t out_off;     /* in elements, relative to `idx` / `dist2`                               */
+  int64_t support_bstride, query_bstride, out_bstride; /* per batch item (points / elements)     */
+  int32_t n_support, n_query, k, batch;
+} gadm_knn_job;
+
+enum { GADM_KNN_BRUTE = 0, GADM_KNN_GRID = 1, GADM_KNN_AUTO = 2 };
+
+/* Device workspace needed by gadm_knn3d for these jobs (0 for GADM_KNN_BRUTE). */
+size_t gadm_knn3d_workspace_bytes(const gadm_knn_job* jobs_host, int n_jobs, int algo);
+
+/* For every job and batch item: the k nearest support points of each query, ascending squared distance
+ * d2 = ((dx*dx) + (dy*dy)) + (dz*dz) in fp32 without FMA contraction (nanoflann.hpp:343-346); equal
+ * distances ordered by ascending index.  Requires 1 <= k <= min(32, n_support).
+ *   support, query: [.., 3] fp32 ; idx: int32 [.., n_query, k] ; dist2: fp32 same shape or NULL.
+ *   jobs_host: HOST array (read before the call returns).                                            */
+int gadm_knn3d(const float* support, const float* query, const gadm_knn_job* jobs_host, int n_jobs, int algo,
+               int32_t* idx, float* dist2, void* workspace, size_t workspace_bytes, gadm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DGCNN dynamic-graph kNN + edge features
+ * ------------------------------------------------------------------------------------------------ */
+/* x [B, C, N] fp32; ranks by  -|xi|^2 + 2 xi.xj - |xj|^2  over the first `kdim` channels (kdim = C, or 3
+ * for dim9=True, models/dgcnn.py:38); idx int64 [B, N, k], nearest first, ties by ascending index. k <= 32 */
+int gadm_knn_feat(const float* x, int B, int C, int N, int kdim, int k, int64_t* idx, gadm_stream_t stream);
+
+/* out [B, 2C, N, k] fp32: out[b, c, n, j] = x[b, c, idx[b,n,j]] - x[b, c, n];  out[b, C+c, n, j] = x[b, c, n] */
+int gadm_graph_feature(const float* x, const int64_t* idx, int B, int C, int N, int k, float* out,
+                       gadm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Grouping (pointops) and neighbour gather (RandLA)
+ * ------------------------------------------------------------------------------------------------ */
+/* features (b, c, n) fp32, idx (b, m, s) int32 -> out (b, c, m, s): out[b,c,m,s] = features[b,c,idx[b,m,s]] */
+int gadm_group_fwd(const float* features, const int32_t* idx, int b, int c, int n, int m, int s, float* out,
+                   gadm_stream_t stream);
+/* grad_out (b, c, m, s) -> grad_features (b, c, n), scatter-add; grad_features is zeroed by the callee. */
+int gadm_group_bwd(const float* grad_out, const int32_t* idx, int b, int c, int n, int m, int s,
+                   float* grad_features, gadm_stream_t stream);
+/* pc (B, N, C) fp32, idx (B, M, K) int64 -> out (B, M, K, C): out[b,m,k,:] = pc[b, idx[b,m,k], :] */
+int gadm_gather_neighbour(const float* pc, const int64_t* idx, int B, int N, int C, int M, int K, float* out,
+                          gadm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GADM_H_ */

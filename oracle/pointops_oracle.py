@@ -1,0 +1,36 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the two pointops entry points the path names.
+
+PARITY UNPINNED: the CUDA sources of lib/pointops are absent from the reference
+(lib/pointops/pointops.egg-info/SOURCES.txt:6-24) and nothing imports the package.  Semantics come from
+  * KNNQueryNaive.forward   /root/reference/lib/pointops/functions/pointops.py:405-426  (pure torch)
+  * Grouping.forward/backward docstrings and shapes   .../pointops.py:149-178
+torch.sort is not stable across equal keys by contract; ties are canonicalised by (dist, index) here.
+"""
+import torch
+
+
+def knnquery_naive(nsample, xyz, new_xyz=None):
+    """xyz (b,n,3), new_xyz (b,m,3) -> idx int32 (b,m,nsample); pointops.py:405-424.
+    dist = (new - xyz)^2 summed over the coordinate axis (torch reduction order: x, y, z)."""
+    if new_xyz is None:
+        new_xyz = xyz
+    diff = new_xyz[:, :, None, :] - xyz[:, None, :, :]
+    dist = diff.pow(2).sum(dim=3)
+    idxs = torch.sort(dist, dim=2, stable=True)[1]      # stable => ties by ascending index
+    return idxs[:, :, :nsample].int(), torch.sort(dist, dim=2, stable=True)[0][:, :, :nsample]
+
+
+def grouping(features, idx):
+    """features (b,c,n), idx (b,m,s) int -> (b,c,m,s): out[b,c,m,s] = features[b,c,idx[b,m,s]]."""
+    b, c, n = features.shape
+    _, m, s = idx.shape
+    gather_idx = idx.long().view(b, 1, m * s).expand(b, c, m * s)
+    return torch.gather(features, 2, gather_idx).view(b, c, m, s)
+
+
+def grouping_backward(grad_out, idx, n):
+    """grad_out (b,c,m,s) -> grad_features (b,c,n): scatter-add (pointops.py:166-176)."""
+    b, c, m, s = grad_out.shape
+    g = torch.zeros(b, c, n, dtype=grad_out.dtype)
+    gather_idx = idx.long().view(b, 1, m * s).expand(b, c, m * s)
+    return g.scatter_add_(2, gather_idx, grad_out.reshape(b, c, m * s))

@@ -1,0 +1,174 @@
+"""-m gpu: fused matcher (C ABI) vs oracle/match_oracle.py on the same bf16-representable inputs.
+
+Gates (north star / SURVEY.md 8(c)):
+  argmax index   exact on every row whose oracle top-1 margin exceeds 1e-3 (mismatch rate reported below it)
+  max_sim        |err| <= 1e-3 (absolute on a cosine in [-1, 1])
+  weight         relative error <= 1e-3
+  soft_xyz       |err| <= 1e-3 * model diameter
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import match_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+def _check(out, ref, M, diameter, soft=True, rows=None):
+    idx, max_sim, weight, soft_xyz = [None if o is None else o.cpu() for o in out]
+    sel = slice(None) if rows is None else rows
+    idx, max_sim = idx[sel], max_sim[sel]
+    decided = ref["margin"] > TOL
+    assert decided.float().mean() > 0.5
+    assert torch.equal(idx[decided], ref["idx"][decided]), "argmax must be exact where margin > 1e-3"
+    assert (max_sim - ref["max_sim"]).abs().max() <= TOL
+    # below the margin the kernel may pick the runner-up, but its value must still be the max within tolerance
+    if soft:
+        weight, soft_xyz = weight[sel], soft_xyz[sel]
+        rel = ((weight - ref["weight"]).abs() / ref["weight"]).max()
+        assert rel <= TOL, f"weight rel err {rel}"
+        err = (soft_xyz - ref["soft_xyz"]).abs().max()
+        assert err <= TOL * diameter, f"soft_xyz err {err}"
+
+
+@pytest.mark.parametrize("regime", ["random", "planted"])
+@pytest.mark.parametrize("N,M,d", [(1000, 1024, 128), (777, 520, 64), (300, 8192, 128), (257, 768, 256)])
+def test_match_soft_vs_oracle(cuda, regime, N, M, d):
+    from gadm_b200 import matching, synth
+    rgbd, mesh, _ = synth.descriptors(2, N, M, d, n_obj=1, regime=regime, seed=2000 + N)
+    diam = 0.2
+    xyz = synth.fibonacci_sphere(M, diam)
+    out = matching.match(rgbd.to(cuda), mesh.to(cuda), xyz[None].to(cuda), gamma=16.0, mode="soft")
+    torch.cuda.synchronize()
+    for b in range(2):
+        ref = mo.match_soft(rgbd[b], mesh[0], xyz, gamma=16.0)
+        _check([o[b] for o in out], ref, M, diam)
+
+
+def test_match_argmax_mode_and_bank(cuda):
+    """mode='argmax' (the reference's path, evaluator.py:89-93) with a 3-object bank and per-frame obj_id."""
+    from gadm_b200 import matching, synth
+    B, N, M, d = 4, 640, 1024, 128
+    rgbd, mesh, _ = synth.descriptors(B, N, M, d, n_obj=3, regime="planted", seed=5)
+    xyz = synth.model_bank_xyz(3, M)
+    bank = matching.ModelBank(mesh.to(cuda), xyz.to(cuda))
+    obj = [2, 0, 1, 2]
+    idx, sim, w, sx = matching.match(rgbd.to(cuda), bank, obj_id=obj, mode="argmax")
+    assert w is None and sx is None
+    for b in range(B):
+        ridx, rsim, margin = mo.match_hard(rgbd[b], mesh[obj[b]])
+        ok = margin > TOL
+        assert torch.equal(idx[b].cpu()[ok], ridx[ok])
+        assert (sim[b].cpu() - rsim).abs().max() <= TOL
+
+
+@pytest.mark.parametrize("pad_mode", ["minus_one", "e0"])
+def test_match_pad_modes(cuda, pad_mode):
+    """Padded variants: pvn3d_eval_utils_kpls.py:436-444 (-1 column), geoMatch_DGCNN.py:92-99 (e0 column)."""
+    from gadm_b200 import matching, synth
+    N, M, d = 900, 512, 128
+    rgbd, mesh, _ = synth.descriptors(1, N, M, d, regime="random", seed=77)
+    if pad_mode == "minus_one":       # make the pad column win on some rows: rows with all-negative descriptors
+        rgbd[0, :, :100] = -rgbd[0, :, :100].abs()
+    else:
+        rgbd[0, 0, :100] = 30.0
+    xyz = synth.fibonacci_sphere(M, 0.2)
+    idx, sim, _, _ = matching.match(rgbd.to(cuda), mesh.to(cuda), xyz[None].to(cuda), pad_mode=pad_mode,
+                                    mode="argmax")
+    ridx, rsim, margin = mo.match_hard(rgbd[0], mesh[0], pad_mode=pad_mode)
+    ok = margin > TOL
+    assert (ridx == M).sum() >= 50, "test must exercise the pad column"
+    assert torch.equal(idx[0].cpu()[ok], ridx[ok])
+    assert (sim[0].cpu() - rsim).abs().max() <= TOL
+
+
+def test_match_mask_rows(cuda):
+    """Rows outside the seg mask get idx = -1 (evaluator.py:78-88 selects rows; we keep positions)."""
+    from gadm_b200 import matching, synth
+    N, M, d = 500, 256, 64
+    rgbd, mesh, _ = synth.descriptors(1, N, M, d, regime="planted", seed=9)
+    g = torch.Generator().manual_seed(1)
+    seg = torch.randn((2, N), generator=g)
+    mask = mo.seg_mask(seg)
+    xyz = synth.fibonacci_sphere(M, 0.1)
+    out = matching.match(rgbd.to(cuda), mesh.to(cuda), xyz[None].to(cuda), mask=mask[None].to(cuda))
+    idx = out[0][0].cpu()
+    assert torch.all(idx[~mask] == -1)
+    ref = mo.match_soft(rgbd[0], mesh[0], xyz, row_mask=mask)
+    _check([o[0] for o in out], ref, M, 0.1, rows=mask)
+
+
+def test_match_bf16x3_fp32_inputs(cuda):
+    """operand_mode='bf16x3': arbitrary fp32 descriptors, ~fp32-faithful similarities (error ~1e-6)."""
+    from gadm_b200 import matching, synth
+    N, M, d = 512, 1024, 128
+    g = torch.Generator().manual_seed(3)
+    rgbd, mesh = torch.randn((1, d, N), generator=g), torch.randn((1, d, M), generator=g)
+    xyz = synth.fibonacci_sphere(M, 0.2)
+    out = matching.match(rgbd.to(cuda), mesh.to(cuda), xyz[None].to(cuda), operand_mode="bf16x3")
+    ref = mo.match_soft(rgbd[0], mesh[0], xyz)
+    assert (out[1][0].cpu() - ref["max_sim"]).abs().max() < 2e-5
+    decided = ref["margin"] > 1e-4
+    assert torch.equal(out[0][0].cpu()[decided], ref["idx"][decided])
+    _check([o[0] for o in out], ref, M, 0.2)
+
+
+def test_match_full_size_properties(cuda):
+    """BASELINE shape 12800 x 8192 x 128: planted correspondences are recovered, weights in (0, 1],
+    soft_xyz inside the model's bounding sphere, argmax mode == soft mode indices, and a 2048-row sample
+    agrees with the oracle."""
+    from gadm_b200 import matching, synth
+    N, M, d = 12800, 8192, 128
+    rgbd, mesh, corr = synth.descriptors(1, N, M, d, regime="planted", seed=2000, sigma=0.5)
+    diam = 0.2
+    xyz = synth.fibonacci_sphere(M, diam)
+    bank = matching.ModelBank(mesh.to(cuda), xyz[None].to(cuda))
+    idx, sim, w, sx = matching.match(rgbd.to(cuda), bank)
+    idx2, sim2, _, _ = matching.match(rgbd.to(cuda), bank, mode="argmax")
+    assert torch.equal(idx, idx2) and torch.equal(sim, sim2)
+    assert (idx[0].cpu() == corr[0]).float().mean() > 0.99
+    assert torch.all((w > 0) & (w <= 1 + 1e-6))
+    assert torch.all(sx.norm(dim=-1) <= diam / 2 * (1 + 1e-4))
+    rows = torch.arange(0, N, N // 2048)[:2048]
+    ref = mo.match_soft(rgbd[0][:, rows], mesh[0], xyz)
+    _check([idx[0][rows], sim[0][rows], w[0][rows], sx[0][rows]], ref, M, diam)
+
+
+def test_match_errors(cuda):
+    from gadm_b200 import matching, _lib
+    with pytest.raises(_lib.GadmError):      # d not a multiple of 64
+        matching.match(torch.randn(1, 96, 64, device=cuda), torch.randn(1, 96, 64, device=cuda),
+                       torch.zeros(1, 64, 3, device=cuda))
+    with pytest.raises(_lib.GadmError):      # CPU tensors: no fallback
+        matching.match(torch.randn(1, 128, 64), torch.randn(1, 128, 64), torch.zeros(1, 64, 3))
+
+
+def test_frame_poses_recovers_pose(cuda):
+    """cal_frame_poses drop-in: planted correspondences + a known rigid transform -> Kabsch recovers it
+    (evaluator.py:60-102 + best_fit_transform)."""
+    from gadm_b200 import matching, synth
+    N, M, d = 2048, 1024, 128
+    rgbd, mesh, corr = synth.descriptors(1, N, M, d, regime="planted", seed=31, sigma=0.3)
+    xyz = synth.fibonacci_sphere(M, 0.2)
+    ang = 0.7
+    R = torch.tensor([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]], dtype=torch.float32)
+    t = torch.tensor([0.1, -0.05, 0.8])
+    cld = (xyz[corr[0]] @ R.T + t).T.contiguous()              # [3, N]
+    seg = torch.stack([torch.zeros(N), torch.ones(N)])          # all foreground
+    seg[0, ::7] = 2.0                                           # every 7th point background
+    bank = matching.ModelBank(mesh.to(cuda), xyz[None].to(cuda))
+    item = (cld.to(cuda), seg.to(cuda), None, rgbd[0].to(cuda), 0, True)
+    RT = matching.cal_frame_poses(item, bank)
+    assert RT.shape == (3, 4)
+    assert np.abs(RT[:, :3] - R.numpy()).max() < 1e-3 and np.abs(RT[:, 3] - t.numpy()).max() < 1e-3
+    # oracle Kabsch on the oracle matcher's output
+    mask = mo.seg_mask(seg)
+    ridx, _, _ = mo.match_hard(rgbd[0], mesh[0], row_mask=mask)
+    RT_ref = mo.best_fit_transform(xyz[ridx], cld.T[mask]).numpy()
+    assert np.abs(RT - RT_ref).max() < 1e-4
+    # early-outs: not detected -> sentinel pose (evaluator.py:69-73)
+    RT0 = matching.cal_frame_poses((cld.to(cuda), seg.to(cuda), None, rgbd[0].to(cuda), 0, False), bank)
+    assert RT0[2, 3] == -1000
