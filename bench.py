@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the scene-to-model dense correspondence path (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): an LM-O-shaped batch of 8 frames, one object each (8-object model bank):
+per frame 12800 scene points x 8192 model vertices, d = 128, FULL matching (normalise + similarity + argmax +
+softmax weight + soft coordinates) + the 22-call kNN pyramid of the reference's data layer
+(datasets/lm/linemod_pbr.py:534-569; 128x128 crop).  A step = one such batch.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]         our arm (CUDA, libgadm.so)
+  python bench.py --impl reference ...                        the reference's CPU path on the host cores
+For N > 1 launch with torchrun (one rank per GPU); frames are sharded by rank (weak scaling: 8 frames per rank
+per step), the only collective is the all_gather of the matcher outputs, overlapped on a side stream.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAMES = 8            # frames per rank per step
+N_PTS, M_VERTS, D = 12800, 8192, 128
+IN_SIZE = 128
+N_OBJ = 8
+GAMMA = 16.0
+ROT = 4               # distinct resident input batches rotated through the timed steps (> L2)
+WORKLOAD = "lmo_batch8: 8 frames x 1 object, 12800 pts x 8192 verts, d=128, full matching (soft) + 22-call kNN pyramid"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            j = json.load(f)
+        return j, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_frames(n_frames, seed, with_soft=False):
+    """The reference's own CPU path for n_frames frames: torch-CPU matching head (evaluator.py:89-93 restated in
+    oracle/match_oracle.py) with all host threads + the 22-call nanoflann schedule (compiled reference when
+    present, else the C port), one frame per worker thread like the reference's DataLoader workers.
+    Returns (seconds, kind, cores)."""
+    import numpy as np
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    sys.path.insert(0, ROOT)
+    import gadm_b200  # noqa: F401  (synthetic generators only; no CUDA is touched on this path)
+    from gadm_b200 import synth
+    from oracle import knn_oracle as ko, match_oracle as mo
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kind = "reference" if ko.have_reference() else "port"
+    knn_fn = ko.knn_search_ref if kind == "reference" else (lambda s, q, k: ko.knn_port(s, q, k).astype(np.int32))
+    rgbd, mesh, _ = synth.descriptors(n_frames, N_PTS, M_VERTS, D, n_obj=min(N_OBJ, n_frames), regime="planted",
+                                      seed=seed)
+    xyz = synth.model_bank_xyz(min(N_OBJ, n_frames), M_VERTS)
+    clouds = [synth.depth_cloud(IN_SIZE, N_PTS, seed + b) for b in range(n_frames)]
+
+    def knn_frame(b):
+        cld, sr = clouds[b]
+        return [knn_fn(s[None], q[None], k) for _, s, q, k in ko.schedule(cld, sr)]
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=min(cores, n_frames)) as ex:
+        futs = [ex.submit(knn_frame, b) for b in range(n_frames)]
+        for b in range(n_frames):
+            o = b % mesh.shape[0]
+            if with_soft:
+                mo.match_soft(rgbd[b], mesh[o], xyz[o], gamma=GAMMA)
+            else:
+                mo.match_hard(rgbd[b], mesh[o])
+        for f in futs:
+            f.result()
+    return time.perf_counter() - t0, kind, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames_per_step = FRAMES
+    for _ in range(args.warmup):
+        cpu_reference_frames(frames_per_step, 1000)
+    t = 0.0
+    kind, cores = "port", 1
+    for s in range(args.steps):
+        dt, kind, cores = cpu_reference_frames(frames_per_step, 1000 + s)
+        t += dt
+    value = frames_per_step * args.steps / t
+    sample = (f"{frames_per_step} frames/step: torch-CPU fp32 matching head (normalize, normalize, matmul, max; "
+              f"evaluator.py:89-93) on {cores} threads + 22-call nanoflann kNN schedule per frame "
+              f"({'compiled reference knn_.cxx' if kind == 'reference' else 'C port'}, one frame per worker thread)")
+    line = {"impl": "reference", "metric": "frames/s", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": frames_per_step},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import gadm_b200  # noqa: F401
+    from gadm_b200 import matching, ops, synth
+    from gadm_b200._lib import MATCH_MODES, OPERAND_MODES, PAD_MODES
+    from gadm_b200.knn import KnnPyramid
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk, pk_kind = peaks()
+
+    # ---- synthetic inputs: ROT distinct batches, host-pinned and device-resident copies
+    host, res = [], []
+    for r in range(ROT):
+        seed = 2000 + 97 * r + 1000 * rank
+        rgbd, mesh, _ = synth.descriptors(FRAMES, N_PTS, M_VERTS, D, n_obj=N_OBJ, regime="planted", seed=seed)
+        cld, sr = synth.frame_batch(FRAMES, IN_SIZE, N_PTS, seed=seed)
+        h = {"rgbd": rgbd.pin_memory(), "cld": cld.pin_memory(), "sr": {s: sr[s].pin_memory() for s in (2, 4, 8)}}
+        host.append(h)
+        res.append({"rgbd": rgbd.to(dev), "mesh": mesh.to(dev), "cld": cld.to(dev),
+                    "sr": {s: sr[s].to(dev) for s in (2, 4, 8)}})
+    xyz = synth.model_bank_xyz(N_OBJ, M_VERTS).to(dev)
+    obj_id = torch.arange(FRAMES, dtype=torch.int32, device=dev) % N_OBJ
+    pyr = KnnPyramid(N_PTS, {s: (IN_SIZE // s) ** 2 for s in (2, 4, 8)}, FRAMES)
+    ws_bytes = ops._lib.load().gadm_knn3d_workspace_bytes(pyr.jobs, len(pyr.jobs), ops.KNN_ALGOS["auto"])
+    pyr.workspace = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
+    for r in res:
+        r["pts"] = pyr.pack(r["cld"], r["sr"])
+    om, pm, mm = OPERAND_MODES["bf16"], PAD_MODES["none"], MATCH_MODES["soft"]
+    side = torch.cuda.Stream(device=dev)
+    gathered = None
+
+    def step(inp, ev=None):
+        """One pass of the hot path over one resident batch.  Returns the outputs."""
+        cols, aux = ops.prep_model(inp["mesh"], xyz, om)                      # model side (evaluator.py:90)
+        rows, rinv, pad = ops.prep_rows(inp["rgbd"], om, pm)                  # scene side (evaluator.py:89)
+        if ev:
+            ev[0].record()
+        out = ops.match_fwd(rows, rinv, pad, cols, aux, None, obj_id, GAMMA, pm, mm)   # evaluator.py:91-93 + ext.
+        if ev:
+            ev[1].record()
+        knn_idx = pyr.run_packed(inp["pts"])                                  # linemod_pbr.py:534-569
+        if ev:
+            ev[2].record()
+        return out, knn_idx
+
+    def gather(out):
+        """N > 1: all_gather of the fixed-stride matcher outputs on a side stream (overlaps the next step)."""
+        nonlocal gathered
+        if world == 1:
+            return
+        packed = torch.cat([out[0].view(FRAMES, -1).to(torch.float32), out[1].view(FRAMES, -1),
+                            out[2].view(FRAMES, -1), out[3].view(FRAMES, -1)], dim=1)
+        done = torch.cuda.Event()
+        done.record()
+        with torch.cuda.stream(side):
+            side.wait_event(done)
+            packed.record_stream(side)
+            if gathered is None:
+                gathered = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=dev)
+            dist.all_gather_into_tensor(gathered, packed)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`)
+    for w in range(args.warmup):
+        gather(step(res[w % ROT])[0])
+    sync_all()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    sync_all()
+    e0.record()
+    for s in range(args.steps):
+        gather(step(res[s % ROT], evs[s])[0])
+    e1.record()
+    torch.cuda.current_stream().wait_stream(side)
+    sync_all()
+    ms_total = e0.elapsed_time(e1)
+    match_ms = statistics.mean(ev[0].elapsed_time(ev[1]) for ev in evs)
+    knn_ms = statistics.mean(ev[1].elapsed_time(ev[2]) for ev in evs)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
+    def e2e_step(h, mesh_dev):
+        rgbd = h["rgbd"].to(dev, non_blocking=True)
+        cld = h["cld"].to(dev, non_blocking=True)
+        sr = {s: h["sr"][s].to(dev, non_blocking=True) for s in (2, 4, 8)}
+        bank = matching.ModelBank(mesh_dev, xyz)
+        idx, sim, w, sxyz = matching.match(rgbd, bank, obj_id=obj_id, gamma=GAMMA, mode="soft")
+        knn = pyr(cld, sr)
+        outs = [idx.cpu(), sim.cpu(), w.cpu(), sxyz.cpu()] + [knn[nm].cpu() for nm, _, _, _ in pyr.names]
+        return outs
+
+    for w in range(max(1, args.warmup // 2)):
+        outs = e2e_step(host[w % ROT], res[w % ROT]["mesh"])
+    h2d = sum(t.numel() * t.element_size() for t in [host[0]["rgbd"], host[0]["cld"]] + list(host[0]["sr"].values()))
+    d2h = sum(t.numel() * t.element_size() for t in outs)
+    sync_all()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for s in range(e2e_steps):
+        e2e_step(host[s % ROT], res[s % ROT]["mesh"])
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- max over ranks
+    if world > 1:
+        t = torch.tensor([ms_total, e2e_s, match_ms, knn_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_s, match_ms, knn_ms = [float(x) for x in t.tolist()]
+
+    if rank == 0:
+        frames = FRAMES * world * args.steps
+        value = frames / (ms_total * 1e-3)
+        flop_per_launch = 2.0 * N_PTS * M_VERTS * D * FRAMES
+        achieved = flop_per_launch / (match_ms * 1e-3) / 1e12
+        peak = pk.get("bf16_tflops", 1590.0)
+        launches = 3 + pyr_launches(pyr)
+        line = {
+            "metric": "frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": FRAMES, "n_obj": N_OBJ, "gamma": GAMMA,
+                       "operand_mode": "bf16 operands, fp32 accumulate", "parallelism": f"frames sharded x{world}",
+                       "l2": f"rotating {ROT} resident input batches (~{ROT * 85} MB > 126 MB L2)",
+                       "collective": "all_gather of matcher outputs on a side stream" if world > 1 else "none"},
+            "breakdown_ms": {"match_kernel": match_ms, "knn_pyramid": knn_ms,
+                             "prep_and_other": ms_total / args.steps - match_ms - knn_ms},
+            "roofline": {"kernel": "match_kernel<soft> (tcgen05 fused similarity+softmax+argmax)", "bound": "tensor",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_kind": f"{pk_kind} bf16 burst", "flop_per_launch": flop_per_launch,
+                         "traffic": None},
+            "knn": {"algorithmic_bytes_per_step": pyr.algorithmic_bytes * FRAMES,
+                    "achieved_gbs": pyr.algorithmic_bytes * FRAMES / (knn_ms * 1e-3) / 1e9,
+                    "hbm_peak_gbs": pk.get("hbm_gbs"), "queries_per_step": pyr.n_queries * FRAMES},
+            "e2e": {"value": FRAMES * world * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": launches * args.steps,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            n = 2
+            dt, kind, cores = cpu_reference_frames(n, 1000)      # warm
+            dt, kind, cores = cpu_reference_frames(n, 1001)
+            dts, _, _ = cpu_reference_frames(n, 1001, with_soft=True)
+            line["cpu_baseline"] = {
+                "value": n / dt, "unit": "frames/s", "cores": cores, "kind": kind,
+                "value_with_soft_extension": n / dts,
+                "sample": (f"{n} frames of the same workload: torch-CPU fp32 matching head (evaluator.py:89-93) on "
+                           f"{cores} threads + the 22-call nanoflann schedule per frame (one frame per worker thread)")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def pyr_launches(pyr):
+    any_grid = any(j.n_support >= 2048 for j in pyr.jobs)
+    any_brute = any(j.n_support < 2048 for j in pyr.jobs)
+    return (4 + 1 if any_grid else 0) + (1 if any_brute else 0)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gadm", choices=["gadm", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "gadm" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -142,7 +142,7 @@ def test_match_errors(cuda):
     with pytest.raises(_lib.GadmError):      # d not a multiple of 64
         matching.match(torch.randn(1, 96, 64, device=cuda), torch.randn(1, 96, 64, device=cuda),
                        torch.zeros(1, 64, 3, device=cuda))
-    with pytest.raises(_lib.GadmError):      # CPU tensors: no fallback
+    with pytest.raises((_lib.GadmError, NotImplementedError)):      # CPU tensors: no fallback, no CPU kernel registered
         matching.match(torch.randn(1, 128, 64), torch.randn(1, 128, 64), torch.zeros(1, 64, 3))
 
 
