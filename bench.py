@@ -254,6 +254,19 @@ def run_gpu(args):
     knn_ms = statistics.mean(ev[1].elapsed_time(ev[2]) for ev in evs)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- variant: the reference's own path (hard argmax only, evaluator.py:93), same operands
+    cols, aux = ops.prep_model(res[0]["mesh"], xyz, om)
+    rows, rinv, pad = ops.prep_rows(res[0]["rgbd"], om, pm)
+    va, vb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        ops.match_fwd(rows, rinv, pad, cols, aux, None, obj_id, GAMMA, pm, MATCH_MODES["argmax"])
+    va.record()
+    for _ in range(10):
+        ops.match_fwd(rows, rinv, pad, cols, aux, None, obj_id, GAMMA, pm, MATCH_MODES["argmax"])
+    vb.record()
+    torch.cuda.synchronize()
+    argmax_ms = va.elapsed_time(vb) / 10
+
     # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
     def e2e_step(h, mesh_dev):
         rgbd = h["rgbd"].to(dev, non_blocking=True)
@@ -304,6 +317,8 @@ def run_gpu(args):
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_kind": f"{pk_kind} bf16 burst", "flop_per_launch": flop_per_launch,
                          "traffic": None},
+            "variants": {"match_kernel_argmax_only_ms": argmax_ms,
+                         "match_kernel_argmax_only_frac": flop_per_launch / (argmax_ms * 1e-3) / 1e12 / peak},
             "knn": {"algorithmic_bytes_per_step": pyr.algorithmic_bytes * FRAMES,
                     "achieved_gbs": pyr.algorithmic_bytes * FRAMES / (knn_ms * 1e-3) / 1e9,
                     "hbm_peak_gbs": pk.get("hbm_gbs"), "queries_per_step": pyr.n_queries * FRAMES},

@@ -7,13 +7,17 @@
 // and soft coordinates are the extension defined in oracle/match_oracle.py.
 //
 // Work decomposition
-//   CTA  = one 128-row tile of one frame (grid = ceil(N/128) x B), 6 warps:
+//   CTA  = one 128-row tile of one frame (grid = ceil(N/128) x B), 10 warps:
 //     warp 0      TMA producer: the 128 x K' row tile once, then model tiles (256 verts x 64 k, 32 KB) through
 //                 an S-stage mbarrier ring, plus the per-tile aux table ({x,y,z,1/|m|} or 1/|m| only)
 //     warp 1      UMMA issuer: 128x256x16 tcgen05.mma, accumulators double-buffered in TMEM (2 x 256 columns)
-//     warps 2..5  epilogue: thread = row; tcgen05.ld 32 columns at a time; score = acc * (1/|m_j|); running
-//                 max / first argmax; (soft) online softmax in base 2 with the row scale gamma*log2e/|f_i| folded
-//                 into one FFMA, sum of weights and weight * xyz accumulated in fp32.
+//     warps 2..9  epilogue: thread = row (two threads per row, one per 128-column half of the tile);
+//                 tcgen05.ld 32 columns at a time, software-pipelined; score = acc * (1/|m_j|); running max /
+//                 first argmax; (soft) single-pass online softmax in base 2 against a lagged reference
+//                 exponent, row scale gamma*log2e/|f_i| folded into one FFMA, sum of weights and weight * xyz
+//                 accumulated in fp32; the halves are merged through shared memory at the end.
+#include <float.h>
+
 #include "gadm_internal.h"
 #include "ptx.cuh"
 
@@ -30,7 +34,8 @@ constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
 constexpr int AUX_BYTES = BN * 16;           // 4 KB (float4 per vertex; argmax mode uses the first 1 KB)
 constexpr int AUX_SLOTS = 4;                // aux ring is decoupled from the 2 accumulators so TMA can run ahead
 constexpr int MAX_STAGES = 6;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;          // TMA warp, MMA warp, 8 epilogue warps
+constexpr int XCH_BYTES = BM * 8 * 4;      // per-row state exchange between the two column halves
 constexpr int TMEM_COLS = 512;
 
 struct Barriers {
@@ -75,7 +80,8 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + p.KB * A_BLK_BYTES;
   uint8_t* smem_aux = smem_b + p.stages * B_STAGE_BYTES;
-  Barriers* bars = reinterpret_cast<Barriers*>(smem_aux + AUX_SLOTS * AUX_BYTES);
+  uint8_t* smem_xch = smem_aux + AUX_SLOTS * AUX_BYTES;
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_xch + XCH_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -94,11 +100,11 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
     ptx::mbar_init(&bars->a_full, 1);
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&bars->tmem_full[a], 1);
-      ptx::mbar_init(&bars->tmem_empty[a], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&bars->tmem_empty[a], 8);  // one arrive per epilogue warp
     }
     for (int a = 0; a < AUX_SLOTS; ++a) {
       ptx::mbar_init(&bars->aux_full[a], 1);
-      ptx::mbar_init(&bars->aux_empty[a], 4);
+      ptx::mbar_init(&bars->aux_empty[a], 8);
     }
     ptx::fence_mbar_init();
   }
@@ -169,17 +175,24 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
       }
     }
   } else {
-    // ============================== epilogue (4 warps, thread == row) ==============================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = row0 + q * 32 + lane;
+    // ============================== epilogue (8 warps; thread == row, two threads per row) ==============================
+    // warp w may only touch TMEM lanes [32*(w%4), +32); the two warps sharing a lane quarter split every
+    // 256-column tile into halves [0,128) and [128,256) and merge their per-row state at the end.
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    const int row_in_tile = q * 32 + lane;
+    const int row = row0 + row_in_tile;
     const bool row_ok = row < p.N;
     const size_t grow = size_t(b) * p.N + (row_ok ? row : 0);
     const float rs = row_ok ? p.rinv_rows[grow] : 0.f;
-    const float g = p.gamma_log2e * rs;  // exponent scale: t = score_colscaled * g  (log2 units)
+    const float g = p.gamma_log2e * rs;  // exponent scale: t = (acc * 1/|m_j|) * g   (log2 units)
 
     float vmax = -INFINITY;
     int vidx = 0;
-    float mrun = -INFINITY, lsum = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+    float mrun = -INFINITY, lsum = 0.f, ax = 0.f, ay = 0.f, az = 0.f;  // mrun is set from the first chunk before any exp
+    constexpr int HC = BN / 2;          // columns per half
+    constexpr int NCH = HC / 32;        // 32-column chunks per half tile
 
     for (int t = 0; t < num_tiles; ++t) {
       const int acc = t & 1;
@@ -188,60 +201,85 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
       ptx::mbar_wait(&bars->aux_full[slot], (uint32_t(t) / AUX_SLOTS) & 1);
       ptx::mbar_wait(&bars->tmem_full[acc], use & 1);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-      const int ncols = min(BN, p.M - t * BN);
-      const float4* aux4 = reinterpret_cast<const float4*>(smem_aux + slot * AUX_BYTES);
-      const float* aux1 = reinterpret_cast<const float*>(smem_aux + slot * AUX_BYTES);
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + half * HC;
+      const int ncols = min(BN, p.M - t * BN) - half * HC;  // valid columns in this half (may be <= 0)
+      const float4* aux4 = reinterpret_cast<const float4*>(smem_aux + slot * AUX_BYTES) + half * HC;
+      const float4* aux1 = reinterpret_cast<const float4*>(smem_aux + slot * AUX_BYTES) + half * (HC / 4);
 
-      for (int c = 0; c < BN / 32; ++c) {
-        if (c * 32 >= ncols) break;  // uniform
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(taddr + c * 32, r);
+      uint32_t ra[32], rb[32];
+      if (kSoft && t == 0 && ncols > 0) {
+        // reference exponent for the lagged online softmax: the first chunk's maximum
+        ptx::tmem_ld_32x32(taddr, ra);
         ptx::tmem_ld_wait();
-        float v[32];
-        float cmx = -INFINITY;
+        float c0 = -FLT_MAX;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) c0 = fmaxf(c0, __uint_as_float(ra[j]) * aux4[j].w);
+        mrun = c0 * g;
+      }
+      if (ncols > 0) ptx::tmem_ld_32x32(taddr, ra);
+
+      auto process = [&](uint32_t (&r)[32], int c) {
+        const int cbase = c * 32;
+        float cmx = -FLT_MAX;
         if (kSoft) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * aux4[c * 32 + j].w;
-        } else {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 cm = reinterpret_cast<const float4*>(aux1)[c * 8 + j4];
-            v[j4 * 4 + 0] = __uint_as_float(r[j4 * 4 + 0]) * cm.x;
-            v[j4 * 4 + 1] = __uint_as_float(r[j4 * 4 + 1]) * cm.y;
-            v[j4 * 4 + 2] = __uint_as_float(r[j4 * 4 + 2]) * cm.z;
-            v[j4 * 4 + 3] = __uint_as_float(r[j4 * 4 + 3]) * cm.w;
-          }
-        }
-        if (c * 32 + 32 > ncols) {  // ragged last tile: columns >= M are zero-filled by TMA, exclude them
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c * 32 + j >= ncols) v[j] = -INFINITY;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) cmx = fmaxf(cmx, v[j]);
-        if (cmx > vmax) {  // strict: an equal value in a later chunk never displaces the first maximal index
-          vmax = cmx;
-          int jj = 31;
-#pragma unroll
-          for (int j = 30; j >= 0; --j)
-            if (v[j] == cmx) jj = j;
-          vidx = t * BN + c * 32 + jj;
-        }
-        if (kSoft) {
-          const float tnew = fmaxf(mrun, cmx * g);
-          const float sc = ptx::ex2_approx(mrun - tnew);
-          lsum *= sc; ax *= sc; ay *= sc; az *= sc;
-          mrun = tnew;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float4 m = aux4[c * 32 + j];
-            const float pj = ptx::ex2_approx(fmaf(v[j], g, -tnew));
+            const float4 m = aux4[cbase + j];
+            float v = __uint_as_float(r[j]) * m.w;
+            if (cbase + 32 > ncols && cbase + j >= ncols) v = -FLT_MAX;  // ragged last tile (TMA zero-fills)
+            r[j] = __float_as_uint(v);
+            cmx = fmaxf(cmx, v);
+            const float pj = ptx::ex2_approx(fmaf(v, g, -mrun));
             lsum += pj;
             ax = fmaf(pj, m.x, ax);
             ay = fmaf(pj, m.y, ay);
             az = fmaf(pj, m.z, az);
           }
+        } else {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 cm = aux1[c * 8 + j4];
+            const float w[4] = {cm.x, cm.y, cm.z, cm.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int j = j4 * 4 + u;
+              float v = __uint_as_float(r[j]) * w[u];
+              if (cbase + 32 > ncols && cbase + j >= ncols) v = -FLT_MAX;
+              r[j] = __float_as_uint(v);
+              cmx = fmaxf(cmx, v);
+            }
+          }
+        }
+        if (cmx > vmax) {  // strict: an equal value in a later chunk never displaces the first maximal index
+          vmax = cmx;
+          int jj = 31;
+#pragma unroll
+          for (int j = 30; j >= 0; --j)
+            if (__uint_as_float(r[j]) == cmx) jj = j;
+          vidx = t * BN + half * HC + cbase + jj;
+        }
+        if (kSoft) {
+          const float tnew = cmx * g;
+          if (tnew > mrun) {  // rescale the running sums to the new reference exponent
+            const float sc = ptx::ex2_approx(mrun - tnew);
+            lsum *= sc; ax *= sc; ay *= sc; az *= sc;
+            mrun = tnew;
+          }
+        }
+      };
+
+#pragma unroll
+      for (int c = 0; c < NCH; c += 2) {
+        if (c * 32 < ncols) {
+          ptx::tmem_ld_wait();
+          if ((c + 1) * 32 < ncols) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
+          process(ra, c);
+        }
+        if ((c + 1) * 32 < ncols) {
+          ptx::tmem_ld_wait();
+          if ((c + 2) * 32 < ncols && c + 2 < NCH) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+          process(rb, c + 1);
         }
       }
       ptx::tc_fence_before();
@@ -252,7 +290,17 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
       }
     }
 
-    if (row_ok) {
+    // merge the two halves of every row: half 1 publishes, half 0 combines and writes the outputs
+    float* xch = reinterpret_cast<float*>(smem_xch) + row_in_tile * 8;
+    if (half == 1) {
+      xch[0] = vmax; xch[1] = __int_as_float(vidx); xch[2] = mrun; xch[3] = lsum;
+      xch[4] = ax; xch[5] = ay; xch[6] = az;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (half == 0 && row_ok) {
+      const float v1 = xch[0];
+      const int i1 = __float_as_int(xch[1]);
+      if (v1 > vmax || (v1 == vmax && i1 < vidx)) { vmax = v1; vidx = i1; }
       const bool keep = p.mask == nullptr || p.mask[grow] != 0;
       float best = vmax * rs;
       int64_t best_idx = vidx;
@@ -263,11 +311,15 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
       p.idx[grow] = keep ? best_idx : int64_t(-1);
       p.max_sim[grow] = keep ? best : 0.f;
       if (kSoft) {
-        const float inv = 1.f / lsum;
-        p.weight[grow] = keep ? inv : 0.f;  // softmax value at the (real-column) maximum: exp2(0)/lsum
-        p.soft_xyz[grow * 3 + 0] = keep ? ax * inv : 0.f;
-        p.soft_xyz[grow * 3 + 1] = keep ? ay * inv : 0.f;
-        p.soft_xyz[grow * 3 + 2] = keep ? az * inv : 0.f;
+        const float m1 = xch[2];
+        const float mm = fmaxf(mrun, m1);
+        const float s0 = ptx::ex2_approx(mrun - mm), s1 = ptx::ex2_approx(m1 - mm);
+        const float l = lsum * s0 + xch[3] * s1;
+        const float inv = 1.f / l;
+        p.weight[grow] = keep ? ptx::ex2_approx(fmaf(vmax, g, -mm)) * inv : 0.f;  // softmax value at the maximum
+        p.soft_xyz[grow * 3 + 0] = keep ? (ax * s0 + xch[4] * s1) * inv : 0.f;
+        p.soft_xyz[grow * 3 + 1] = keep ? (ay * s0 + xch[5] * s1) * inv : 0.f;
+        p.soft_xyz[grow * 3 + 2] = keep ? (az * s0 + xch[6] * s1) * inv : 0.f;
       }
     }
   }
@@ -281,7 +333,7 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
 }
 
 size_t match_smem_bytes(int KB, int stages) {
-  return size_t(KB) * A_BLK_BYTES + size_t(stages) * B_STAGE_BYTES + AUX_SLOTS * AUX_BYTES + sizeof(Barriers) + 1024;
+  return size_t(KB) * A_BLK_BYTES + size_t(stages) * B_STAGE_BYTES + AUX_SLOTS * AUX_BYTES + XCH_BYTES + sizeof(Barriers) + 1024;
 }
 
 }  // namespace

@@ -1,0 +1,29 @@
+"""Profiling driver: a few launches of each hot kernel at the BASELINE shapes (for ncu; not a benchmark)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import gadm_b200  # noqa
+from gadm_b200 import ops, synth
+from gadm_b200._lib import MATCH_MODES
+from gadm_b200.knn import KnnPyramid
+
+dev = torch.device("cuda", 0)
+B, N, M, D = 8, 12800, 8192, 128
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+rgbd, mesh, _ = synth.descriptors(B, N, M, D, n_obj=8, regime="planted", seed=2000)
+xyz = synth.model_bank_xyz(8, M).to(dev)
+obj = torch.arange(B, dtype=torch.int32, device=dev)
+cols, aux = ops.prep_model(mesh.to(dev), xyz, 0)
+rows, rinv, pad = ops.prep_rows(rgbd.to(dev), 0, 0)
+cld, sr = synth.frame_batch(B, 128, N, seed=2000)
+pyr = KnnPyramid(N, {s: (128 // s) ** 2 for s in (2, 4, 8)}, B)
+pts = pyr.pack(cld.to(dev), {s: v.to(dev) for s, v in sr.items()})
+for _ in range(reps):
+    if what in ("all", "match"):
+        ops.match_fwd(rows, rinv, pad, cols, aux, None, obj, 16.0, 0, MATCH_MODES["argmax"])
+        ops.match_fwd(rows, rinv, pad, cols, aux, None, obj, 16.0, 0, MATCH_MODES["soft"])
+    if what in ("all", "knn"):
+        pyr.run_packed(pts)
+torch.cuda.synchronize()
+print("done")
