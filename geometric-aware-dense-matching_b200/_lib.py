@@ -28,6 +28,7 @@ SIGNATURES = {
     "gadm_init": (c_int, [c_int]),
     "gadm_last_cuda_error": (ctypes.c_char_p, []),
     "gadm_operand_k": (c_int, [c_int, c_int]),
+    "gadm_aux_floats": (c_size_t, [c_int, c_int]),
     "gadm_prep_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gadm_prep_model": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "gadm_match_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

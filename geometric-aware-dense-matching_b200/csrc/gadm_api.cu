@@ -108,6 +108,11 @@ int gadm_operand_k(int d, int operand_mode) {
   return GADM_ERR_UNSUPPORTED;
 }
 
+size_t gadm_aux_floats(int n_obj, int M) {
+  if (n_obj <= 0 || M <= 0) return 0;
+  return size_t(n_obj) * size_t((M + 255) / 256) * 1024;
+}
+
 int gadm_prep_rows(const float* feat, int B, int d, int N, int operand_mode, int pad_mode, void* rows, float* rinv,
                    float* pad_sim, gadm_stream_t stream) {
   GADM_REQUIRE_INIT();

@@ -125,17 +125,15 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
         ptx::tma_load_3d(smem_a + kb * A_BLK_BYTES, &tmap_rows, &bars->a_full, kb * BK, row0, b);
       int stage = 0;
       uint32_t phase = 0;
-      const float* aux_tab = kSoft ? p.aux + size_t(obj) * p.M * 4
-                                   : p.aux + size_t(p.n_obj) * p.M * 4 + size_t(obj) * p.M;
-      const uint32_t aux_elt = kSoft ? 16u : 4u;
+      // aux: per object, per 256-vertex tile, 1024 floats = [1/|m| x256 | x x256 | y x256 | z x256]
+      const float* aux_tab = p.aux + size_t(obj) * num_tiles * (4 * BN);
+      const uint32_t aux_bytes = kSoft ? uint32_t(AUX_BYTES) : uint32_t(BN * 4);  // ARGMAX needs only 1/|m|
       for (int t = 0; t < num_tiles; ++t) {
         const int slot = t % AUX_SLOTS;
         const uint32_t use = uint32_t(t) / AUX_SLOTS;
         ptx::mbar_wait(&bars->aux_empty[slot], (use & 1) ^ 1);
-        const int nvalid = min(BN, p.M - t * BN);
-        ptx::mbar_arrive_expect_tx(&bars->aux_full[slot], nvalid * aux_elt);
-        ptx::bulk_load_1d(smem_aux + slot * AUX_BYTES,
-                          reinterpret_cast<const uint8_t*>(aux_tab) + size_t(t) * BN * aux_elt, nvalid * aux_elt,
+        ptx::mbar_arrive_expect_tx(&bars->aux_full[slot], aux_bytes);
+        ptx::bulk_load_1d(smem_aux + slot * AUX_BYTES, aux_tab + size_t(t) * (4 * BN), aux_bytes,
                           &bars->aux_full[slot]);
         for (int kb = 0; kb < p.KB; ++kb) {
           ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
@@ -190,7 +188,8 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
 
     float vmax = -INFINITY;
     int vidx = 0;
-    float mrun = -INFINITY, lsum = 0.f, ax = 0.f, ay = 0.f, az = 0.f;  // mrun is set from the first chunk before any exp
+    float mrun = -INFINITY;  // set from the first chunk before any exp
+    uint64_t l2 = 0, ax2 = 0, ay2 = 0, az2 = 0;  // packed (even-column | odd-column) partial sums, +0.0f bit patterns
     constexpr int HC = BN / 2;          // columns per half
     constexpr int NCH = HC / 32;        // 32-column chunks per half tile
 
@@ -203,8 +202,8 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + half * HC;
       const int ncols = min(BN, p.M - t * BN) - half * HC;  // valid columns in this half (may be <= 0)
-      const float4* aux4 = reinterpret_cast<const float4*>(smem_aux + slot * AUX_BYTES) + half * HC;
-      const float4* aux1 = reinterpret_cast<const float4*>(smem_aux + slot * AUX_BYTES) + half * (HC / 4);
+      // this half's slice of the aux slot: 1/|m| at [0,256), x at [256,512), y, z
+      const uint32_t auxs = ptx::smem_u32(smem_aux + slot * AUX_BYTES) + half * HC * 4;  // shared-space address
 
       uint32_t ra[32], rb[32];
       if (kSoft && t == 0 && ncols > 0) {
@@ -214,43 +213,31 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
         float c0 = -FLT_MAX;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (j < ncols) c0 = fmaxf(c0, __uint_as_float(ra[j]) * aux4[j].w);
+          if (j < ncols) c0 = fmaxf(c0, __uint_as_float(ra[j]) * ptx::lds32(auxs + j * 4));
         mrun = c0 * g;
       }
       if (ncols > 0) ptx::tmem_ld_32x32(taddr, ra);
 
       auto process = [&](uint32_t (&r)[32], int c) {
         const int cbase = c * 32;
-        float cmx = -FLT_MAX;
-        if (kSoft) {
+        const uint32_t cmp = auxs + cbase * 4;
+        // ---- scores: v = acc * 1/|m_j| (packed f32x2), kept in r[] for the argmax search
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float4 m = aux4[cbase + j];
-            float v = __uint_as_float(r[j]) * m.w;
-            if (cbase + 32 > ncols && cbase + j >= ncols) v = -FLT_MAX;  // ragged last tile (TMA zero-fills)
-            r[j] = __float_as_uint(v);
-            cmx = fmaxf(cmx, v);
-            const float pj = ptx::ex2_approx(fmaf(v, g, -mrun));
-            lsum += pj;
-            ax = fmaf(pj, m.x, ax);
-            ay = fmaf(pj, m.y, ay);
-            az = fmaf(pj, m.z, az);
-          }
-        } else {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 cm = aux1[c * 8 + j4];
-            const float w[4] = {cm.x, cm.y, cm.z, cm.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int j = j4 * 4 + u;
-              float v = __uint_as_float(r[j]) * w[u];
-              if (cbase + 32 > ncols && cbase + j >= ncols) v = -FLT_MAX;
-              r[j] = __float_as_uint(v);
-              cmx = fmaxf(cmx, v);
-            }
-          }
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 cm = ptx::lds128(cmp + j4 * 16);
+          const uint64_t v01 = ptx::fmul2(ptx::pack2(r[j4 * 4 + 0], r[j4 * 4 + 1]), ptx::pack2f(cm.x, cm.y));
+          const uint64_t v23 = ptx::fmul2(ptx::pack2(r[j4 * 4 + 2], r[j4 * 4 + 3]), ptx::pack2f(cm.z, cm.w));
+          ptx::unpack2(v01, r[j4 * 4 + 0], r[j4 * 4 + 1]);
+          ptx::unpack2(v23, r[j4 * 4 + 2], r[j4 * 4 + 3]);
         }
+        if (cbase + 32 > ncols) {  // ragged last tile only (warp-uniform): TMA zero-fills columns >= M
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (cbase + j >= ncols) r[j] = __float_as_uint(-FLT_MAX);
+        }
+        float cmx = __uint_as_float(r[0]);
+#pragma unroll
+        for (int j = 1; j < 32; ++j) cmx = fmaxf(cmx, __uint_as_float(r[j]));
         if (cmx > vmax) {  // strict: an equal value in a later chunk never displaces the first maximal index
           vmax = cmx;
           int jj = 31;
@@ -260,10 +247,32 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
           vidx = t * BN + half * HC + cbase + jj;
         }
         if (kSoft) {
+          // ---- p = 2^(v*g - m_run) against the lagged reference exponent; sums in packed f32x2 (even | odd column)
+          const uint64_t g2 = ptx::pack2f(g, g), nm2 = ptx::pack2f(-mrun, -mrun);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 X = ptx::lds128(cmp + BN * 4 + j4 * 16);
+            const float4 Y = ptx::lds128(cmp + 2 * BN * 4 + j4 * 16);
+            const float4 Z = ptx::lds128(cmp + 3 * BN * 4 + j4 * 16);
+            float t0, t1, t2, t3;
+            ptx::unpack2f(ptx::ffma2(ptx::pack2(r[j4 * 4 + 0], r[j4 * 4 + 1]), g2, nm2), t0, t1);
+            ptx::unpack2f(ptx::ffma2(ptx::pack2(r[j4 * 4 + 2], r[j4 * 4 + 3]), g2, nm2), t2, t3);
+            const uint64_t p01 = ptx::pack2f(ptx::ex2_approx(t0), ptx::ex2_approx(t1));
+            const uint64_t p23 = ptx::pack2f(ptx::ex2_approx(t2), ptx::ex2_approx(t3));
+            l2 = ptx::fadd2(l2, p01);
+            l2 = ptx::fadd2(l2, p23);
+            ax2 = ptx::ffma2(p01, ptx::pack2f(X.x, X.y), ax2);
+            ax2 = ptx::ffma2(p23, ptx::pack2f(X.z, X.w), ax2);
+            ay2 = ptx::ffma2(p01, ptx::pack2f(Y.x, Y.y), ay2);
+            ay2 = ptx::ffma2(p23, ptx::pack2f(Y.z, Y.w), ay2);
+            az2 = ptx::ffma2(p01, ptx::pack2f(Z.x, Z.y), az2);
+            az2 = ptx::ffma2(p23, ptx::pack2f(Z.z, Z.w), az2);
+          }
           const float tnew = cmx * g;
           if (tnew > mrun) {  // rescale the running sums to the new reference exponent
             const float sc = ptx::ex2_approx(mrun - tnew);
-            lsum *= sc; ax *= sc; ay *= sc; az *= sc;
+            const uint64_t sc2 = ptx::pack2f(sc, sc);
+            l2 = ptx::fmul2(l2, sc2); ax2 = ptx::fmul2(ax2, sc2); ay2 = ptx::fmul2(ay2, sc2); az2 = ptx::fmul2(az2, sc2);
             mrun = tnew;
           }
         }
@@ -292,6 +301,14 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
 
     // merge the two halves of every row: half 1 publishes, half 0 combines and writes the outputs
     float* xch = reinterpret_cast<float*>(smem_xch) + row_in_tile * 8;
+    float lsum, ax, ay, az;
+    {
+      float e, o;
+      ptx::unpack2f(l2, e, o); lsum = e + o;
+      ptx::unpack2f(ax2, e, o); ax = e + o;
+      ptx::unpack2f(ay2, e, o); ay = e + o;
+      ptx::unpack2f(az2, e, o); az = e + o;
+    }
     if (half == 1) {
       xch[0] = vmax; xch[1] = __int_as_float(vidx); xch[2] = mrun; xch[3] = lsum;
       xch[4] = ax; xch[5] = ay; xch[6] = az;

@@ -80,13 +80,13 @@ prep_kernel(const float* __restrict__ src, const float* __restrict__ xyz, int d,
           pad_sim[gp] = e0 * r;
         }
       } else {
-        float4 a;
-        a.x = xyz ? xyz[gp * 3 + 0] : 0.f;
-        a.y = xyz ? xyz[gp * 3 + 1] : 0.f;
-        a.z = xyz ? xyz[gp * 3 + 2] : 0.f;
-        a.w = r;
-        reinterpret_cast<float4*>(aux4)[gp] = a;
-        aux1[gp] = r;
+        // aux: per object, per 256-vertex tile: [1/|m| x256 | x x256 | y x256 | z x256]
+        const int tiles = (P + 255) / 256;
+        float* a = aux4 + (size_t(g) * tiles + p / 256) * 1024 + (p & 255);
+        a[0] = r;
+        a[256] = xyz ? xyz[gp * 3 + 0] : 0.f;
+        a[512] = xyz ? xyz[gp * 3 + 1] : 0.f;
+        a[768] = xyz ? xyz[gp * 3 + 2] : 0.f;
       }
     }
   }
@@ -99,7 +99,7 @@ kabsch_moments_kernel(const int64_t* __restrict__ idx, const uint8_t* __restrict
                       const int32_t* __restrict__ obj_id, int B, int N, int M, int n_obj, double* __restrict__ out) {
   const int b = blockIdx.x;
   const int obj = obj_id ? obj_id[b] : (n_obj == B ? b : 0);
-  const float4* tab = reinterpret_cast<const float4*>(aux) + size_t(obj) * M;
+  const float* tab = aux + size_t(obj) * ((M + 255) / 256) * 1024;
   double acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.0;
@@ -108,7 +108,9 @@ kabsch_moments_kernel(const int64_t* __restrict__ idx, const uint8_t* __restrict
     const int64_t j = idx[gn];
     if (j < 0 || j >= M) continue;
     if (mask && !mask[gn]) continue;
-    const float4 a = tab[j];
+    const float* e = tab + (j >> 8) * 1024 + (j & 255);
+    float4 a;
+    a.x = e[256]; a.y = e[512]; a.z = e[768];
     const float bx = cloud[gn * 3 + 0], by = cloud[gn * 3 + 1], bz = cloud[gn * 3 + 2];
     acc[0] += 1.0;
     acc[1] += a.x; acc[2] += a.y; acc[3] += a.z;
@@ -149,9 +151,11 @@ int prep_model_launch(const float* mesh, const float* model_xyz, int n_obj, int 
                       float* aux, cudaStream_t stream) {
   dim3 grid((M + PTS - 1) / PTS, n_obj);
   const size_t smem = size_t(d) * (PTS + 1) * sizeof(float);
+  // the pad columns of the last tile must be finite (they are multiplied by an exact 0 weight in the kernel)
+  cudaError_t e = cudaMemsetAsync(aux, 0, size_t(n_obj) * ((M + 255) / 256) * 1024 * sizeof(float), stream);
+  if (e != cudaSuccess) return set_cuda_error(e);
   prep_kernel<1><<<grid, 256, smem, stream>>>(mesh, model_xyz, d, M, operand_mode == GADM_OPERAND_BF16X3, 0,
-                                              static_cast<__nv_bfloat16*>(cols), nullptr, nullptr, aux,
-                                              aux + size_t(n_obj) * M * 4);
+                                              static_cast<__nv_bfloat16*>(cols), nullptr, nullptr, aux, nullptr);
   return check_launch();
 }
 

@@ -67,7 +67,7 @@ def prep_model(mesh: torch.Tensor, model_xyz: torch.Tensor, operand_mode: int) -
     kp = lib.gadm_operand_k(d, operand_mode)
     _lib.check(min(kp, 0), "gadm_operand_k")
     cols = torch.empty((n_obj, M, kp), dtype=torch.bfloat16, device=mesh.device)
-    aux = torch.empty((n_obj * M * 5,), dtype=torch.float32, device=mesh.device)
+    aux = torch.empty((n_obj * ((M + 255) // 256) * 1024,), dtype=torch.float32, device=mesh.device)
     with torch.cuda.device(mesh.device):
         _lib.check(lib.gadm_prep_model(_ptr(mesh), _ptr(model_xyz), n_obj, d, M, operand_mode, _ptr(cols), _ptr(aux),
                                        _stream()), "gadm_prep_model")
@@ -78,7 +78,8 @@ def prep_model(mesh: torch.Tensor, model_xyz: torch.Tensor, operand_mode: int) -
 def _(mesh, model_xyz, operand_mode):
     n_obj, d, M = mesh.shape
     kp = d * (3 if operand_mode == 1 else 1)
-    return mesh.new_empty((n_obj, M, kp), dtype=torch.bfloat16), mesh.new_empty((n_obj * M * 5,))
+    return (mesh.new_empty((n_obj, M, kp), dtype=torch.bfloat16),
+            mesh.new_empty((n_obj * ((M + 255) // 256) * 1024,)))
 
 
 @torch.library.custom_op("gadm::match_fwd", mutates_args=(), device_types="cuda")

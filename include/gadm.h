@@ -84,7 +84,10 @@ int gadm_prep_rows(const float* feat, int B, int d, int N, int operand_mode, int
 
 /* Model side (once per object bank).  mesh [n_obj, d, M] fp32 channel-major (end_points['mesh']);
  * model_xyz [n_obj, M, 3] fp32 or NULL.
- *   cols [n_obj, M, K'] bf16 ; aux [n_obj, M, 4] fp32 = {x, y, z, 1/max(||m||,1e-12)} (16-byte aligned) */
+ *   cols [n_obj, M, K'] bf16 (16-byte aligned)
+ *   aux  [n_obj, ceil(M/256), 4, 256] fp32 (16-byte aligned): per 256-vertex tile the rows
+ *        {1/max(||m||,1e-12), x, y, z}; pad columns of the last tile are zero.  gadm_aux_floats() sizes it. */
+size_t gadm_aux_floats(int n_obj, int M);
 int gadm_prep_model(const float* mesh, const float* model_xyz, int n_obj, int d, int M, int operand_mode,
                     void* cols, float* aux, gadm_stream_t stream);
 
