@@ -198,11 +198,16 @@ int gadm_knn_feat(const float* x, int B, int C, int N, int kdim, int k, int64_t*
   return knn_feat_launch(x, B, C, N, kdim, k, idx, (cudaStream_t)stream);
 }
 
-int gadm_graph_feature(const float* x, const int64_t* idx, int B, int C, int N, int k, float* out,
-                       gadm_stream_t stream) {
+size_t gadm_graph_feature_workspace_bytes(int B, int C, int N) {
+  if (B <= 0 || C <= 0 || N <= 0 || C % 4 != 0) return 0;
+  return size_t(B) * C * N * sizeof(float);
+}
+
+int gadm_graph_feature(const float* x, const int64_t* idx, int B, int C, int N, int k, float* out, void* workspace,
+                       size_t workspace_bytes, gadm_stream_t stream) {
   GADM_REQUIRE_INIT();
   if (!x || !idx || !out || B <= 0 || C <= 0 || N <= 0 || k <= 0) return GADM_ERR_BAD_ARG;
-  return graph_feature_launch(x, idx, B, C, N, k, out, (cudaStream_t)stream);
+  return graph_feature_launch(x, idx, B, C, N, k, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int gadm_group_fwd(const float* features, const int32_t* idx, int b, int c, int n, int m, int s, float* out,

@@ -45,7 +45,7 @@ int knn_feat_launch(const float* x, int B, int C, int N, int kdim, int k, int64_
 
 // gather.cu
 int graph_feature_launch(const float* x, const int64_t* idx, int B, int C, int N, int k, float* out,
-                         cudaStream_t stream);
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int group_fwd_launch(const float* features, const int32_t* idx, int b, int c, int n, int m, int s, float* out,
                      cudaStream_t stream);
 int group_bwd_launch(const float* grad_out, const int32_t* idx, int b, int c, int n, int m, int s,

@@ -31,6 +31,57 @@ graph_feature_kernel(const float* __restrict__ x, const int64_t* __restrict__ id
   }
 }
 
+// [B, C, N] -> [B, N, C] (32x32 shared-memory tiles, both sides coalesced)
+__global__ void __launch_bounds__(256)
+transpose_cn_kernel(const float* __restrict__ x, int C, int N, float* __restrict__ xt) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* xb = x + (size_t)b * C * N;
+  float* tb = xt + (size_t)b * C * N;
+  for (int r = ty; r < 32; r += 8)
+    tile[r][tx] = (c0 + r < C && n0 + tx < N) ? xb[(size_t)(c0 + r) * N + n0 + tx] : 0.f;
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (n0 + r < N && c0 + tx < C) tb[(size_t)(n0 + r) * C + c0 + tx] = tile[tx][r];
+}
+
+// thread = one (n, j) pair; reads the neighbour's and the centre's channel vectors from the point-major copy
+// (64 contiguous bytes at a time: every fetched sector is fully used -- the direct gather uses 4 of every 32
+// bytes), writes channel-major with coalesced streaming stores.
+__global__ void __launch_bounds__(256)
+graph_feature_t_kernel(const float* __restrict__ xt, const int64_t* __restrict__ idx, int C, int N, int k,
+                       float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // n * k + j
+  const long long NK = (long long)N * k;
+  if (e >= NK) return;
+  const int n = int(e / k);
+  const int nb = int(idx[(size_t)b * NK + e]);
+  const float4* pn = reinterpret_cast<const float4*>(xt + ((size_t)b * N + nb) * C);
+  const float4* pc = reinterpret_cast<const float4*>(xt + ((size_t)b * N + n) * C);
+  float* ob = out + (size_t)b * 2 * C * NK + e;
+  for (int c4 = 0; c4 < C / 4; c4 += 4) {
+    float4 vn[4], vc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (c4 + u < C / 4) { vn[u] = __ldg(pn + c4 + u); vc[u] = __ldg(pc + c4 + u); }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (c4 + u < C / 4) {
+        const int c = (c4 + u) * 4;
+        __stcs(ob + (size_t)(c + 0) * NK, vn[u].x - vc[u].x);
+        __stcs(ob + (size_t)(c + 1) * NK, vn[u].y - vc[u].y);
+        __stcs(ob + (size_t)(c + 2) * NK, vn[u].z - vc[u].z);
+        __stcs(ob + (size_t)(c + 3) * NK, vn[u].w - vc[u].w);
+        __stcs(ob + (size_t)(C + c + 0) * NK, vc[u].x);
+        __stcs(ob + (size_t)(C + c + 1) * NK, vc[u].y);
+        __stcs(ob + (size_t)(C + c + 2) * NK, vc[u].z);
+        __stcs(ob + (size_t)(C + c + 3) * NK, vc[u].w);
+      }
+  }
+}
+
 // thread = one (m, s) pair; loops over channels
 __global__ void __launch_bounds__(256)
 group_fwd_kernel(const float* __restrict__ f, const int32_t* __restrict__ idx, int c, int n, int ms,
@@ -72,9 +123,18 @@ gather_neighbour_kernel(const float* __restrict__ pc, const int64_t* __restrict_
 }  // namespace
 
 int graph_feature_launch(const float* x, const int64_t* idx, int B, int C, int N, int k, float* out,
-                         cudaStream_t stream) {
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (B > 65535) return GADM_ERR_UNSUPPORTED;
   const long long NK = (long long)N * k;
+  if (C % 4 == 0 && workspace != nullptr && workspace_bytes >= size_t(B) * C * N * sizeof(float) &&
+      (reinterpret_cast<uintptr_t>(workspace) & 15) == 0) {
+    float* xt = static_cast<float*>(workspace);
+    dim3 tg((N + 31) / 32, (C + 31) / 32, B);
+    transpose_cn_kernel<<<tg, 256, 0, stream>>>(x, C, N, xt);
+    dim3 grid((unsigned)((NK + 255) / 256), B);
+    graph_feature_t_kernel<<<grid, 256, 0, stream>>>(xt, idx, C, N, k, out);
+    return check_launch();
+  }
   dim3 grid((unsigned)((NK + 255) / 256), B);
   graph_feature_kernel<<<grid, 256, 0, stream>>>(x, idx, C, N, k, out);
   return check_launch();

@@ -208,8 +208,10 @@ def graph_feature(x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     k = idx.shape[2]
     out = torch.empty((B, 2 * C, N, k), dtype=torch.float32, device=x.device)
     lib = _lib_for(x)
+    ws_bytes = lib.gadm_graph_feature_workspace_bytes(B, C, N)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device) if ws_bytes else None
     with torch.cuda.device(x.device):
-        _lib.check(lib.gadm_graph_feature(_ptr(x), _ptr(idx), B, C, N, k, _ptr(out), _stream()),
+        _lib.check(lib.gadm_graph_feature(_ptr(x), _ptr(idx), B, C, N, k, _ptr(out), _ptr(ws), ws_bytes, _stream()),
                    "gadm_graph_feature")
     return out
 

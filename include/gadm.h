@@ -140,9 +140,12 @@ int gadm_knn3d(const float* support, const float* query, const gadm_knn_job* job
  * for dim9=True, models/dgcnn.py:38); idx int64 [B, N, k], nearest first, ties by ascending index. k <= 32 */
 int gadm_knn_feat(const float* x, int B, int C, int N, int kdim, int k, int64_t* idx, gadm_stream_t stream);
 
-/* out [B, 2C, N, k] fp32: out[b, c, n, j] = x[b, c, idx[b,n,j]] - x[b, c, n];  out[b, C+c, n, j] = x[b, c, n] */
-int gadm_graph_feature(const float* x, const int64_t* idx, int B, int C, int N, int k, float* out,
-                       gadm_stream_t stream);
+/* out [B, 2C, N, k] fp32: out[b, c, n, j] = x[b, c, idx[b,n,j]] - x[b, c, n];  out[b, C+c, n, j] = x[b, c, n]
+ * workspace (optional, 16-byte aligned, gadm_graph_feature_workspace_bytes): a point-major copy of x that makes
+ * the neighbour gathers sector-efficient; without it a slower direct-gather kernel runs (same result).      */
+size_t gadm_graph_feature_workspace_bytes(int B, int C, int N);
+int gadm_graph_feature(const float* x, const int64_t* idx, int B, int C, int N, int k, float* out, void* workspace,
+                       size_t workspace_bytes, gadm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Grouping (pointops) and neighbour gather (RandLA)

@@ -1,0 +1,46 @@
+"""Secondary measurement (BASELINE.json configs[4]): the geoMatch_DGCNN graph path --
+feature-space kNN k=20 on 4096 pts, batch 64, 1 x (C=3 via dim9) + 3 x (C=64) layers, + get_graph_feature.
+Prints one JSON line with per-kernel times and roofline fractions (CUDA events, 3 warm-ups, inputs > L2)."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import gadm_b200  # noqa
+from gadm_b200 import ops
+
+dev = torch.device("cuda", 0)
+B, C, N, k = 64, 64, 4096, 20
+g = torch.Generator().manual_seed(5000)
+x = torch.randn((B, C, N), generator=g).to(dev)
+x9 = torch.randn((B, 9, N), generator=g).to(dev)
+peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))) \
+    if os.path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0}
+
+
+def timed(fn, reps=5):
+    t_end = time.time() + 0.4          # ramp the clocks: the box idles at ~120 MHz
+    while time.time() < t_end:
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        out = fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps, out
+
+
+t_knn64, idx = timed(lambda: ops.knn_feat(x, k, C))
+t_knn3, idx3 = timed(lambda: ops.knn_feat(x9, k, 3))
+t_gf, out = timed(lambda: ops.graph_feature(x, idx))
+gf_bytes = 4 * B * C * N + 8 * B * N * k + 4 * B * 2 * C * N * k
+line = {
+    "workload": "dgcnn_graph: B=64, N=4096, k=20; knn C=64, knn C=3 (dim9), get_graph_feature C=64",
+    "knn_feat_c64_ms": t_knn64, "knn_feat_c64_tflops_fp32": 2.0 * B * N * N * C / (t_knn64 * 1e-3) / 1e12,
+    "knn_feat_c3_ms": t_knn3,
+    "graph_feature_ms": t_gf, "graph_feature_gbs": gf_bytes / (t_gf * 1e-3) / 1e9,
+    "graph_feature_frac_of_hbm_peak": gf_bytes / (t_gf * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0),
+    "layer_stack_ms (1x dim9 + 3x C=64 knn+graph)": t_knn3 + 3 * t_knn64 + 4 * t_gf,
+}
+print(json.dumps(line))
