@@ -30,7 +30,9 @@ constexpr int WARPS = 8;
 constexpr int QPB = QPW * WARPS;  // queries per CTA
 constexpr int TS = 1024;          // support points per shared-memory tile (12 KB)
 constexpr int GRID_MIN_SUPPORT = 2048;  // AUTO: smaller clouds are scanned by BRUTE
-constexpr int R_MAX = 3;          // shells visited before the whole-cloud fallback
+constexpr int R_MAX = 4;          // block radius (in cells) visited before the whole-cloud fallback
+constexpr int GRID_E = 4;         // pending candidates per lane between extractions (grid kernel)
+constexpr int BRUTE_E = 2;        // same, brute kernel (4 queries per warp: register budget)
 constexpr float PTS_PER_CELL = 6.f;
 
 struct JobDev {
@@ -72,34 +74,82 @@ __device__ __forceinline__ float dist2_ref(float qx, float qy, float qz, float p
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-__device__ __forceinline__ bool lex_less(float d, int i, float kd, int ki) { return d < kd || (d == kd && i < ki); }
+// ---------------------------------------------------------------------------------------------------
+// Warp-cooperative exact top-k selection (k <= 32) over a stream of (d2, index) candidates, one per lane per
+// offer.  Keys are compared lexicographically on (bits(d2), index); d2 >= 0 so its IEEE bits are monotone.
+//   * every lane keeps a short SORTED list of its own pending candidates (E entries, registers);
+//   * a candidate is admitted only if it beats the current k-th best (kd, ki), known after the first extraction;
+//   * when some lane's list is full (or at flush) the warp EXTRACTS the k smallest keys: k rounds of two
+//     hardware warp reductions (redux.sync.min.u32 on the distance bits, then on the index among the lanes
+//     that hold that distance); the winner pops its list head.  Rank r lands in lane r, which then holds it as
+//     the single entry of its list, so an extraction is also the compaction step.
+// Cost per query is ~16 issue slots per extracted rank instead of a serial ballot/shuffle insertion per
+// admitted candidate (profiles/: the r1 kernels spent ~2400 issue slots per k=16 query on that path).
+constexpr uint32_t D_EMPTY = 0xffffffffu;   // sorts after every real distance (inf = 0x7f800000)
+constexpr int I_EMPTY = 0x7fffffff;
 
-// Warp-level sorted list: lane l holds entry l.  Inserts (d, i), which the caller has checked beats entry k-1.
-__device__ __forceinline__ void warp_insert(float& ld, int& li, float d, int i, int lane) {
-  const bool before = lex_less(ld, li, d, i);  // my entry stays in front of the candidate (a prefix of lanes)
-  const int pos = __popc(__ballot_sync(0xffffffffu, before));
-  const float up_d = __shfl_up_sync(0xffffffffu, ld, 1);
-  const int up_i = __shfl_up_sync(0xffffffffu, li, 1);
-  if (lane > pos) { ld = up_d; li = up_i; }
-  else if (lane == pos) { ld = d; li = i; }
-}
+template <int E>
+struct WarpSelect {
+  uint32_t ed[E];
+  int ei[E];
+  uint32_t kd;   // k-th best so far (D_EMPTY / I_EMPTY until k candidates have been extracted)
+  int ki;
+  bool dirty;    // warp-uniform: something was admitted since the last extraction
 
-// Offer one candidate per lane (valid lanes only) to the list of one query.
-__device__ __forceinline__ void warp_offer(float& ld, int& li, float& kd, int& ki, float d, int i, bool valid, int k,
-                                           int lane) {
-  unsigned m = __ballot_sync(0xffffffffu, valid && lex_less(d, i, kd, ki));
-  while (m) {
-    const int src = __ffs(m) - 1;
-    m &= m - 1;
-    const float dc = __shfl_sync(0xffffffffu, d, src);
-    const int ic = __shfl_sync(0xffffffffu, i, src);
-    if (lex_less(dc, ic, kd, ki)) {  // warp-uniform; the bound may have tightened since the ballot
-      warp_insert(ld, li, dc, ic, lane);
-      kd = __shfl_sync(0xffffffffu, ld, k - 1);
-      ki = __shfl_sync(0xffffffffu, li, k - 1);
-    }
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int s = 0; s < E; ++s) { ed[s] = D_EMPTY; ei[s] = I_EMPTY; }
+    kd = D_EMPTY; ki = I_EMPTY; dirty = false;
   }
-}
+  static __device__ __forceinline__ bool key_less(uint32_t d, int i, uint32_t d2, int i2) {
+    return d < d2 || (d == d2 && i < i2);
+  }
+  // k smallest keys of everything pending -> lane r holds rank r (r < k); (kd, ki) = rank k-1
+  __device__ __forceinline__ void extract(int k, int lane) {
+    uint32_t od = D_EMPTY;
+    int oi = I_EMPTY;
+    for (int r = 0; r < k; ++r) {
+      const uint32_t dmin = __reduce_min_sync(0xffffffffu, ed[0]);
+      const uint32_t cand = ed[0] == dmin ? uint32_t(ei[0]) : uint32_t(I_EMPTY);
+      const uint32_t imin = __reduce_min_sync(0xffffffffu, cand);
+      if (lane == r) { od = dmin; oi = int(imin); }
+      if (cand == imin) {  // the owner pops its head (all lanes pop an EMPTY head once the stream is exhausted)
+#pragma unroll
+        for (int s = 0; s + 1 < E; ++s) { ed[s] = ed[s + 1]; ei[s] = ei[s + 1]; }
+        ed[E - 1] = D_EMPTY; ei[E - 1] = I_EMPTY;
+      }
+    }
+    ed[0] = od; ei[0] = oi;
+#pragma unroll
+    for (int s = 1; s < E; ++s) { ed[s] = D_EMPTY; ei[s] = I_EMPTY; }
+    kd = __shfl_sync(0xffffffffu, od, k - 1);
+    ki = __shfl_sync(0xffffffffu, oi, k - 1);
+    dirty = false;
+  }
+  // one candidate per lane (valid lanes only)
+  __device__ __forceinline__ void offer(float d, int i, bool valid, int k, int lane) {
+    const uint32_t db = __float_as_uint(d);
+    const bool acc = valid && key_less(db, i, kd, ki);
+    if (!__any_sync(0xffffffffu, acc)) return;
+    // bubble the newcomer through the sorted list; rejected lanes carry the EMPTY key, which never swaps
+    uint32_t cd = acc ? db : D_EMPTY;
+    int ci = acc ? i : I_EMPTY;
+#pragma unroll
+    for (int s = 0; s < E; ++s) {
+      const bool sw = key_less(cd, ci, ed[s], ei[s]);
+      const uint32_t td = sw ? ed[s] : cd;
+      const int ti = sw ? ei[s] : ci;
+      ed[s] = sw ? cd : ed[s];
+      ei[s] = sw ? ci : ei[s];
+      cd = td; ci = ti;
+    }
+    dirty = true;
+    if (__any_sync(0xffffffffu, ed[E - 1] != D_EMPTY)) extract(k, lane);
+  }
+  __device__ __forceinline__ void flush(int k, int lane) {
+    if (dirty) extract(k, lane);
+  }
+};
 
 __device__ __forceinline__ const JobDev& find_job(const LaunchJobs& L, int tile, int& item, int& qtile) {
   int j = 0;
@@ -126,15 +176,14 @@ knn_brute_kernel(const float* __restrict__ support, const float* __restrict__ qu
   const long long obase = job.out_off + item * job.out_bstride;
 
   const int q0 = qtile * QPB + warp * QPW;
-  float qx[QPW], qy[QPW], qz[QPW], ld[QPW], kd[QPW];
-  int li[QPW], ki[QPW];
+  float qx[QPW], qy[QPW], qz[QPW];
+  WarpSelect<BRUTE_E> sel[QPW];
 #pragma unroll
   for (int t = 0; t < QPW; ++t) {
     const int qi = min(q0 + t, job.n_query - 1);
     qx[t] = Q[qi * 3 + 0]; qy[t] = Q[qi * 3 + 1]; qz[t] = Q[qi * 3 + 2];
-    ld[t] = FLT_MAX; li[t] = INT_MAX; kd[t] = FLT_MAX; ki[t] = INT_MAX;
+    sel[t].reset();
   }
-  // FLT_MAX sentinels: a real candidate at d2 == FLT_MAX with any index still beats (FLT_MAX, INT_MAX)
 
   for (int s0 = 0; s0 < job.n_support; s0 += TS) {
     const int tn = min(TS, job.n_support - s0);
@@ -150,16 +199,17 @@ knn_brute_kernel(const float* __restrict__ support, const float* __restrict__ qu
 #pragma unroll
       for (int t = 0; t < QPW; ++t) {
         const float d = dist2_ref(qx[t], qy[t], qz[t], px, py, pz);
-        warp_offer(ld[t], li[t], kd[t], ki[t], d, gi, valid, k, lane);
+        sel[t].offer(d, gi, valid, k, lane);
       }
     }
   }
 #pragma unroll
   for (int t = 0; t < QPW; ++t) {
+    sel[t].flush(k, lane);
     const int qi = q0 + t;
     if (qi < job.n_query && lane < k) {
-      idx[obase + (long long)qi * k + lane] = li[t];
-      if (dist2) dist2[obase + (long long)qi * k + lane] = ld[t];
+      idx[obase + (long long)qi * k + lane] = sel[t].ei[0];
+      if (dist2) dist2[obase + (long long)qi * k + lane] = __uint_as_float(sel[t].ed[0]);
     }
   }
 }
@@ -325,7 +375,40 @@ grid_scatter_kernel(const float* __restrict__ support, uint8_t* __restrict__ ws,
 }
 
 // --------------------------------------------------------------------------------------------- GRID query
-// one warp per query, QPW queries per warp in sequence
+// One warp per query, QPW queries per warp in sequence.  Phase 0 visits the 3x3x3 block of cells around the
+// query's cell, phase r >= 1 the Chebyshev shell of radius r + 1.  Within a phase every lane owns one cell-row
+// range [rb, re) of the sorted point array; the ranges are FLATTENED (warp prefix sum + per-lane binary search
+// through shuffles) so that each offer carries 32 real candidates however short the individual ranges are.
+__device__ __forceinline__ void grid_offer_ranges(WarpSelect<GRID_E>& sel, const float4* __restrict__ pts, int rb,
+                                                  int re, float qx, float qy, float qz, int k, int lane) {
+  const int len = re - rb;
+  int incl = len;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  const int excl = incl - len;
+  for (int t0 = 0; t0 < total; t0 += 32) {
+    const int t = t0 + lane;
+    const bool valid = t < total;
+    // owner range of flat position t = number of lanes whose inclusive prefix is <= t
+    int pos = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int v = __shfl_sync(0xffffffffu, incl, pos + step - 1);
+      if (v <= t) pos += step;
+    }
+    const int src = min(pos, 31);
+    const int b0 = __shfl_sync(0xffffffffu, rb, src);
+    const int x0 = __shfl_sync(0xffffffffu, excl, src);
+    const float4 p = pts[valid ? b0 + (t - x0) : 0];
+    const float d = dist2_ref(qx, qy, qz, p.x, p.y, p.z);
+    sel.offer(d, __float_as_int(p.w), valid, k, lane);
+  }
+}
+
 __global__ void __launch_bounds__(WARPS * 32)
 knn_grid_kernel(const float* __restrict__ query, int32_t* __restrict__ idx, float* __restrict__ dist2,
                 uint8_t* __restrict__ ws, const __grid_constant__ LaunchJobs L) {
@@ -348,27 +431,28 @@ knn_grid_kernel(const float* __restrict__ query, int32_t* __restrict__ idx, floa
     const int cx = cell_coord(qx, g.ox, g.inv_h, g.dx);
     const int cy = cell_coord(qy, g.oy, g.inv_h, g.dy);
     const int cz = cell_coord(qz, g.oz, g.inv_h, g.dz);
-    float ld = FLT_MAX, kd = FLT_MAX;
-    int li = INT_MAX, ki = INT_MAX;
+    WarpSelect<GRID_E> sel;
+    sel.reset();
     bool done = false;
 
-    for (int rho = 0; rho <= R_MAX && !done; ++rho) {
-      // range slots of shell rho: rows (dz, dy) in [-rho, rho]^2, two slots per row
+    for (int rho = 1; rho <= R_MAX && !done; ++rho) {
+      // rho == 1: the whole 3x3x3 block, one range per (dz, dy) row.
+      // rho >= 2: the shell of radius rho: rows (dz, dy) in [-rho, rho]^2, two range slots per row
+      //           (rim rows: the full x span | nothing; inner rows: the cell at -rho | the cell at +rho).
       const int side = 2 * rho + 1;
-      const int nslots = 2 * side * side;
+      const int nslots = rho == 1 ? side * side : 2 * side * side;
       for (int s0 = 0; s0 < nslots; s0 += 32) {
         const int s = s0 + lane;
         int rb = 0, re = 0;
         if (s < nslots) {
-          const int row = s >> 1, second = s & 1;
+          const int row = rho == 1 ? s : s >> 1, second = rho == 1 ? 0 : s & 1;
           const int dz = row / side - rho, dy = row % side - rho;
           const int z = cz + dz, y = cy + dy;
           if (z >= 0 && z < g.dz && y >= 0 && y < g.dy) {
-            const bool rim = max(abs(dz), abs(dy)) == rho;
+            const bool rim = rho == 1 || max(abs(dz), abs(dy)) == rho;
             int x_lo, x_hi;
             if (rim) { x_lo = cx - rho; x_hi = second ? x_lo - 1 : cx + rho; }
             else     { x_lo = second ? cx + rho : cx - rho; x_hi = x_lo; }
-            if (rho == 0 && second) x_hi = x_lo - 1;
             x_lo = max(x_lo, 0); x_hi = min(x_hi, g.dx - 1);
             if (x_lo <= x_hi) {
               const int rowbase = (z * g.dy + y) * g.dx;
@@ -377,20 +461,9 @@ knn_grid_kernel(const float* __restrict__ query, int32_t* __restrict__ idx, floa
             }
           }
         }
-        unsigned nonempty = __ballot_sync(0xffffffffu, re > rb);
-        while (nonempty) {
-          const int src = __ffs(nonempty) - 1;
-          nonempty &= nonempty - 1;
-          const int b0 = __shfl_sync(0xffffffffu, rb, src), e0 = __shfl_sync(0xffffffffu, re, src);
-          for (int j0 = b0; j0 < e0; j0 += 32) {
-            const int j = j0 + lane;
-            const bool valid = j < e0;
-            const float4 p = pts[valid ? j : e0 - 1];
-            const float d = dist2_ref(qx, qy, qz, p.x, p.y, p.z);
-            warp_offer(ld, li, kd, ki, d, __float_as_int(p.w), valid, k, lane);
-          }
-        }
+        grid_offer_ranges(sel, pts, rb, re, qx, qy, qz, k, lane);
       }
+      sel.flush(k, lane);
       // distance from q to the nearest face of the visited block behind which unvisited cells exist
       float bound = FLT_MAX;
       if (cx - rho > 0) bound = fminf(bound, qx - (g.ox + float(cx - rho) * g.h));
@@ -403,22 +476,24 @@ knn_grid_kernel(const float* __restrict__ query, int32_t* __restrict__ idx, floa
         done = true;  // the block covers the whole grid
       } else {
         bound -= g.slack;
-        done = bound > 0.f && kd < bound * bound;  // strict: an unvisited point at exactly kd could win the index tie
+        // strict: an unvisited point at exactly the k-th distance could still win the index tie
+        done = bound > 0.f && sel.kd != D_EMPTY && __uint_as_float(sel.kd) < bound * bound;
       }
     }
     if (!done) {  // pathological query (far outside / sparse region): scan the whole cloud
-      ld = FLT_MAX; li = INT_MAX; kd = FLT_MAX; ki = INT_MAX;
+      sel.reset();
       for (int j0 = 0; j0 < job.n_support; j0 += 32) {
         const int j = j0 + lane;
         const bool valid = j < job.n_support;
         const float4 p = pts[valid ? j : job.n_support - 1];
         const float d = dist2_ref(qx, qy, qz, p.x, p.y, p.z);
-        warp_offer(ld, li, kd, ki, d, __float_as_int(p.w), valid, k, lane);
+        sel.offer(d, __float_as_int(p.w), valid, k, lane);
       }
+      sel.flush(k, lane);
     }
     if (lane < k) {
-      idx[obase + (long long)qi * k + lane] = li;
-      if (dist2) dist2[obase + (long long)qi * k + lane] = ld;
+      idx[obase + (long long)qi * k + lane] = sel.ei[0];
+      if (dist2) dist2[obase + (long long)qi * k + lane] = __uint_as_float(sel.ed[0]);
     }
   }
 }
