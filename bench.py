@@ -344,9 +344,9 @@ def run_gpu(args):
 
 def pyr_launches(pyr):
     """Kernel launches of one gadm_knn3d call (knn3d.cu): 4 grid-build kernels when any job uses the grid
-    (AUTO: n_support >= 2048), then one query kernel per algorithm present."""
-    any_grid = any(j.n_support >= 2048 for j in pyr.jobs)
-    any_brute = any(j.n_support < 2048 for j in pyr.jobs)
+    (AUTO: n_support >= 512), then one query kernel per algorithm present."""
+    any_grid = any(j.n_support >= 512 for j in pyr.jobs)
+    any_brute = any(j.n_support < 512 for j in pyr.jobs)
     return (4 + 1 if any_grid else 0) + (1 if any_brute else 0)
 
 

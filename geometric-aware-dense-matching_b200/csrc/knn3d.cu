@@ -17,6 +17,7 @@
 //          the distance to the unvisited region (conservative by a rounding slack), else falls back to a scan of
 //          the whole cloud.  Selection is the same lexicographic insertion, so results are identical to BRUTE.
 #include <float.h>
+#include <stdlib.h>
 
 #include "gadm_internal.h"
 
@@ -29,11 +30,9 @@ constexpr int QPW = 4;            // queries per warp (brute)
 constexpr int WARPS = 8;
 constexpr int QPB = QPW * WARPS;  // queries per CTA
 constexpr int TS = 1024;          // support points per shared-memory tile (12 KB)
-constexpr int GRID_MIN_SUPPORT = 2048;  // AUTO: smaller clouds are scanned by BRUTE
 constexpr int R_MAX = 4;          // block radius (in cells) visited before the whole-cloud fallback
 constexpr int GRID_E = 4;         // pending candidates per lane between extractions (grid kernel)
 constexpr int BRUTE_E = 2;        // same, brute kernel (4 queries per warp: register budget)
-constexpr float PTS_PER_CELL = 6.f;
 
 struct JobDev {
   long long support_off, query_off, out_off, support_bstride, query_bstride, out_bstride;
@@ -48,10 +47,14 @@ struct LaunchJobs {
 };
 
 struct GridHeader {  // 64 bytes at the start of each item's workspace
-  float ox, oy, oz, h, inv_h, slack;
+  float ox, oy, oz;      // bounding-box origin
+  float hx, hy, hz;      // cell size per axis (the thinnest axis may get fewer, taller cells: 2.5-D surfaces)
+  float ihx, ihy, ihz;   // 1 / cell size
+  float slack;           // rounding slack of the cell assignment, subtracted from every face distance
   int dx, dy, dz, n_cells;
-  int pad[6];
+  int pad[2];
 };
+static_assert(sizeof(GridHeader) == 64, "GridHeader is the 64-byte workspace prefix");
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 __host__ __device__ inline size_t grid_item_bytes(int n_support, int n_cells_max) {
@@ -237,22 +240,28 @@ __device__ __forceinline__ int cell_coord(float p, float o, float inv_h, int dim
 }
 
 // one CTA per cloud item: bounding box -> grid geometry; zero the counters
-__global__ void __launch_bounds__(256)
-grid_setup_kernel(const float* __restrict__ support, uint8_t* __restrict__ ws, const __grid_constant__ LaunchClouds C) {
+// Geometry: cells of side h = sqrt(ppc * a * b / n) along the two largest bounding-box extents a >= b (depth
+// clouds are 2.5-D surfaces: ~ppc points per occupied column); the thinnest axis gets int(c / h) + 1 layers
+// only as far as the cell budget allows (down to a single layer), so the table stays O(n) cells.
+__global__ void __launch_bounds__(1024)
+grid_setup_kernel(const float* __restrict__ support, uint8_t* __restrict__ ws, const __grid_constant__ LaunchClouds C,
+                  float ppc) {
   int item;
   const CloudDev& cl = find_cloud(C, blockIdx.x, item);
   const float* S = support + (cl.support_off + item * cl.support_bstride) * 3;
   uint8_t* base = ws + cl.ws_off + item * cl.ws_item_bytes;
+  // flat coalesced sweep over the 3n floats; element e belongs to axis e % 3
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  for (int i = threadIdx.x; i < cl.n_support; i += blockDim.x) {
+  const int n3 = cl.n_support * 3;
+  int ax = threadIdx.x % 3;
+  for (int e = threadIdx.x; e < n3; e += 1024) {  // 1024 % 3 == 1: the axis advances by one per iteration
+    const float v = S[e];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const float v = S[size_t(i) * 3 + a];
-      lo[a] = fminf(lo[a], v);
-      hi[a] = fmaxf(hi[a], v);
-    }
+    for (int a = 0; a < 3; ++a)
+      if (a == ax) { lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+    ax = ax == 2 ? 0 : ax + 1;
   }
-  __shared__ float red[6][8];
+  __shared__ float red[6][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
@@ -265,32 +274,51 @@ grid_setup_kernel(const float* __restrict__ support, uint8_t* __restrict__ ws, c
   }
   __syncthreads();
   __shared__ GridHeader hdr;
-  if (threadIdx.x == 0) {
-    for (int a = 0; a < 3; ++a)
-      for (int w = 1; w < 8; ++w) {
-        red[a][0] = fminf(red[a][0], red[a][w]);
-        red[3 + a][0] = fmaxf(red[3 + a][0], red[3 + a][w]);
+  if (warp == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float l = red[a][lane], h = red[3 + a][lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
+        h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
       }
-    float e[3] = {red[3][0] - red[0][0], red[4][0] - red[1][0], red[5][0] - red[2][0]};
-    // two largest extents span the (assumed 2.5-D) surface
-    float a = fmaxf(e[0], fmaxf(e[1], e[2]));
-    float c = fminf(e[0], fminf(e[1], e[2]));
-    float b = e[0] + e[1] + e[2] - a - c;
-    float h = sqrtf(PTS_PER_CELL * fmaxf(a * b, 1e-30f) / float(cl.n_support));
-    if (!(h > 0.f) || !isfinite(h)) h = 1.f;
-    h = fmaxf(h, a * 1e-4f + 1e-30f);
-    int dx, dy, dz;
-    for (;;) {
-      dx = int(e[0] / h) + 1; dy = int(e[1] / h) + 1; dz = int(e[2] / h) + 1;
-      if ((long long)dx * dy * dz <= cl.n_cells_max) break;
-      h *= 1.25f;
+      lo[a] = l; hi[a] = h;
     }
-    hdr.ox = red[0][0]; hdr.oy = red[1][0]; hdr.oz = red[2][0];
-    hdr.h = h; hdr.inv_h = 1.f / h;
-    const float scale = fmaxf(a, fmaxf(fabsf(red[0][0]), fmaxf(fabsf(red[1][0]), fabsf(red[2][0])))) + a;
-    hdr.slack = scale * 3.8e-6f;  // 2^-18: >> fp32 rounding of (p - o) * inv_h, << h
-    hdr.dx = dx; hdr.dy = dy; hdr.dz = dz; hdr.n_cells = dx * dy * dz;
-    *reinterpret_cast<GridHeader*>(base) = hdr;
+    if (lane == 0) {
+      const float e[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+      int thin = 0;  // axis of the smallest extent
+      if (e[1] < e[thin]) thin = 1;
+      if (e[2] < e[thin]) thin = 2;
+      const float a = fmaxf(e[0], fmaxf(e[1], e[2]));
+      const float b = e[0] + e[1] + e[2] - a - e[thin];
+      float h = sqrtf(ppc * fmaxf(a * b, 1e-30f) / float(cl.n_support));
+      if (!(h > 0.f) || !isfinite(h)) h = 1.f;
+      h = fmaxf(h, a * 1e-4f + 1e-30f);
+      int d[3];
+      for (;;) {
+        for (int x = 0; x < 3; ++x) d[x] = int(e[x] / h) + 1;
+        long long plane = 1;
+        for (int x = 0; x < 3; ++x) if (x != thin) plane *= d[x];
+        if (plane <= cl.n_cells_max) {
+          const long long layers = cl.n_cells_max / plane;
+          if (d[thin] > layers) d[thin] = int(layers);
+          break;
+        }
+        h *= 1.25f;
+      }
+      float hs[3];
+      for (int x = 0; x < 3; ++x) hs[x] = h;
+      if (d[thin] != int(e[thin] / h) + 1) hs[thin] = fmaxf(e[thin] / float(d[thin]) * 1.00001f, h);
+      hdr.ox = lo[0]; hdr.oy = lo[1]; hdr.oz = lo[2];
+      hdr.hx = hs[0]; hdr.hy = hs[1]; hdr.hz = hs[2];
+      hdr.ihx = 1.f / hs[0]; hdr.ihy = 1.f / hs[1]; hdr.ihz = 1.f / hs[2];
+      const float scale = fmaxf(a, fmaxf(fabsf(lo[0]), fmaxf(fabsf(lo[1]), fabsf(lo[2])))) + a;
+      hdr.slack = scale * 3.8e-6f;  // 2^-18: >> fp32 rounding of (p - o) * inv_h, << h
+      hdr.dx = d[0]; hdr.dy = d[1]; hdr.dz = d[2]; hdr.n_cells = d[0] * d[1] * d[2];
+      hdr.pad[0] = hdr.pad[1] = 0;
+      *reinterpret_cast<GridHeader*>(base) = hdr;
+    }
   }
   __syncthreads();
   int* cursor = grid_cursor(base, cl.n_cells_max);
@@ -307,9 +335,9 @@ grid_count_kernel(const float* __restrict__ support, uint8_t* __restrict__ ws, c
   const float* S = support + (cl.support_off + item * cl.support_bstride) * 3;
   uint8_t* base = ws + cl.ws_off + item * cl.ws_item_bytes;
   const GridHeader* g = reinterpret_cast<const GridHeader*>(base);
-  const int cx = cell_coord(S[size_t(i) * 3 + 0], g->ox, g->inv_h, g->dx);
-  const int cy = cell_coord(S[size_t(i) * 3 + 1], g->oy, g->inv_h, g->dy);
-  const int cz = cell_coord(S[size_t(i) * 3 + 2], g->oz, g->inv_h, g->dz);
+  const int cx = cell_coord(S[size_t(i) * 3 + 0], g->ox, g->ihx, g->dx);
+  const int cy = cell_coord(S[size_t(i) * 3 + 1], g->oy, g->ihy, g->dy);
+  const int cz = cell_coord(S[size_t(i) * 3 + 2], g->oz, g->ihz, g->dz);
   const int cell = (cz * g->dy + cy) * g->dx + cx;
   grid_cell_of(base, cl.n_cells_max, cl.n_support)[i] = cell;
   atomicAdd(&grid_cursor(base, cl.n_cells_max)[cell], 1);
@@ -329,10 +357,13 @@ grid_scan_kernel(uint8_t* __restrict__ ws, const __grid_constant__ LaunchClouds 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  for (int c0 = 0; c0 < n; c0 += 1024) {
-    const int i = c0 + threadIdx.x;
-    const int v = i < n ? cursor[i] : 0;
-    int x = v;
+  constexpr int PER = 4;  // consecutive cells per thread
+  for (int c0 = 0; c0 < n; c0 += 1024 * PER) {
+    const int i0 = c0 + threadIdx.x * PER;
+    int v[PER], tsum = 0;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) { v[u] = i0 + u < n ? cursor[i0 + u] : 0; tsum += v[u]; }
+    int x = tsum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int y = __shfl_up_sync(0xffffffffu, x, o);
@@ -350,10 +381,14 @@ grid_scan_kernel(uint8_t* __restrict__ ws, const __grid_constant__ LaunchClouds 
       warp_sums[lane] = w;  // inclusive
     }
     __syncthreads();
-    const int excl = carry + (warp ? warp_sums[warp - 1] : 0) + x - v;
-    if (i < n) { start[i] = excl; cursor[i] = excl; }
+    int excl = carry + (warp ? warp_sums[warp - 1] : 0) + x - tsum;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      if (i0 + u < n) { start[i0 + u] = excl; cursor[i0 + u] = excl; }
+      excl += v[u];
+    }
     __syncthreads();
-    if (threadIdx.x == 1023) carry = excl + v;
+    if (threadIdx.x == 1023) carry = excl;
     __syncthreads();
   }
   if (threadIdx.x == 0) start[n] = carry;
@@ -428,9 +463,9 @@ knn_grid_kernel(const float* __restrict__ query, int32_t* __restrict__ idx, floa
     const int qi = qtile * QPB + warp * QPW + t;
     if (qi >= job.n_query) break;  // warp-uniform
     const float qx = Q[qi * 3 + 0], qy = Q[qi * 3 + 1], qz = Q[qi * 3 + 2];
-    const int cx = cell_coord(qx, g.ox, g.inv_h, g.dx);
-    const int cy = cell_coord(qy, g.oy, g.inv_h, g.dy);
-    const int cz = cell_coord(qz, g.oz, g.inv_h, g.dz);
+    const int cx = cell_coord(qx, g.ox, g.ihx, g.dx);
+    const int cy = cell_coord(qy, g.oy, g.ihy, g.dy);
+    const int cz = cell_coord(qz, g.oz, g.ihz, g.dz);
     WarpSelect<GRID_E> sel;
     sel.reset();
     bool done = false;
@@ -466,12 +501,12 @@ knn_grid_kernel(const float* __restrict__ query, int32_t* __restrict__ idx, floa
       sel.flush(k, lane);
       // distance from q to the nearest face of the visited block behind which unvisited cells exist
       float bound = FLT_MAX;
-      if (cx - rho > 0) bound = fminf(bound, qx - (g.ox + float(cx - rho) * g.h));
-      if (cx + rho < g.dx - 1) bound = fminf(bound, (g.ox + float(cx + rho + 1) * g.h) - qx);
-      if (cy - rho > 0) bound = fminf(bound, qy - (g.oy + float(cy - rho) * g.h));
-      if (cy + rho < g.dy - 1) bound = fminf(bound, (g.oy + float(cy + rho + 1) * g.h) - qy);
-      if (cz - rho > 0) bound = fminf(bound, qz - (g.oz + float(cz - rho) * g.h));
-      if (cz + rho < g.dz - 1) bound = fminf(bound, (g.oz + float(cz + rho + 1) * g.h) - qz);
+      if (cx - rho > 0) bound = fminf(bound, qx - (g.ox + float(cx - rho) * g.hx));
+      if (cx + rho < g.dx - 1) bound = fminf(bound, (g.ox + float(cx + rho + 1) * g.hx) - qx);
+      if (cy - rho > 0) bound = fminf(bound, qy - (g.oy + float(cy - rho) * g.hy));
+      if (cy + rho < g.dy - 1) bound = fminf(bound, (g.oy + float(cy + rho + 1) * g.hy) - qy);
+      if (cz - rho > 0) bound = fminf(bound, qz - (g.oz + float(cz - rho) * g.hz));
+      if (cz + rho < g.dz - 1) bound = fminf(bound, (g.oz + float(cz + rho + 1) * g.hz) - qz);
       if (bound == FLT_MAX) {
         done = true;  // the block covers the whole grid
       } else {
@@ -498,17 +533,21 @@ knn_grid_kernel(const float* __restrict__ query, int32_t* __restrict__ idx, floa
   }
 }
 
+// cell budget of a cloud: O(n) so that the histogram scan stays cheap (grid_setup_kernel sizes the cells to fit)
 int cells_for(int n_support) {
-  long long c = 8LL * n_support;
-  if (c < 4096) c = 4096;
+  long long c = n_support / 2;
+  if (c < 1024) c = 1024;
   if (c > (1 << 18)) c = 1 << 18;
   return int(c);
 }
 
+float g_ppc = 8.f;            // target points per occupied cell column
+int g_grid_min_support = 512; // AUTO: smaller clouds are scanned by BRUTE
+
 bool job_uses_grid(const gadm_knn_job& j, int algo) {
   if (algo == GADM_KNN_BRUTE) return false;
   if (algo == GADM_KNN_GRID) return true;
-  return j.n_support >= GRID_MIN_SUPPORT;
+  return j.n_support >= g_grid_min_support;
 }
 
 bool same_cloud(const gadm_knn_job& a, const gadm_knn_job& b) {
@@ -518,7 +557,12 @@ bool same_cloud(const gadm_knn_job& a, const gadm_knn_job& b) {
 
 }  // namespace
 
-int knn3d_configure() { return GADM_OK; }
+int knn3d_configure() {
+  // tuning knobs for experiments (results are identical for every setting)
+  if (const char* s = getenv("GADM_KNN_PPC")) { const float v = float(atof(s)); if (v >= 1.f && v <= 64.f) g_ppc = v; }
+  if (const char* s = getenv("GADM_KNN_GRID_MIN")) { const int v = atoi(s); if (v >= 1) g_grid_min_support = v; }
+  return GADM_OK;
+}
 
 size_t knn3d_workspace_bytes(const gadm_knn_job* jobs, int n_jobs, int algo) {
   size_t total = 0;
@@ -565,7 +609,7 @@ int knn3d_launch(const float* support, const float* query, const gadm_knn_job* j
     auto flush = [&]() {
       if (C.n_clouds == 0) return;
       uint8_t* ws = static_cast<uint8_t*>(workspace);
-      grid_setup_kernel<<<C.total_items, 256, 0, stream>>>(support, ws, C);
+      grid_setup_kernel<<<C.total_items, 1024, 0, stream>>>(support, ws, C, g_ppc);
       dim3 gpts((max_pts + 255) / 256, C.total_items);
       grid_count_kernel<<<gpts, 256, 0, stream>>>(support, ws, C);
       grid_scan_kernel<<<C.total_items, 1024, 0, stream>>>(ws, C);
