@@ -27,14 +27,14 @@ int check_launch() {
 }
 bool initialised() { return g_init; }
 
-int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t batch,
-                      uint32_t box_k, uint32_t box_rows) {
+int make_tmap_2b_3d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t batch,
+                    uint32_t box_k, uint32_t box_rows, int dtype) {
   if (!g_encode) return GADM_ERR_NOT_INIT;
   cuuint64_t dims[3] = {k, rows, batch};
   cuuint64_t strides[2] = {k * 2, k * rows * 2};  // bytes, dims 1 and 2
   cuuint32_t box[3] = {box_k, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = g_encode(out, dtype ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -110,7 +110,7 @@ int gadm_operand_k(int d, int operand_mode) {
 
 size_t gadm_aux_floats(int n_obj, int M) {
   if (n_obj <= 0 || M <= 0) return 0;
-  return size_t(n_obj) * size_t((M + 255) / 256) * 1024;
+  return aux_total_floats(n_obj, M);
 }
 
 int gadm_prep_rows(const float* feat, int B, int d, int N, int operand_mode, int pad_mode, void* rows, float* rinv,

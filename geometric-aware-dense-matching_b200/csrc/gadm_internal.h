@@ -14,9 +14,19 @@ int set_cuda_error(cudaError_t e);           // records text, returns GADM_ERR_C
 int check_launch();                          // cudaGetLastError() -> GADM_OK / GADM_ERR_CUDA
 bool initialised();
 
-// 3-D bf16 tensor map {inner = K, rows, batch}, box {box_k, box_rows, 1}, SWIZZLE_128B (gadm_api.cu)
-int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t batch,
-                      uint32_t box_k, uint32_t box_rows);
+// 3-D tensor map of 2-byte elements {inner = K, rows, batch}, box {box_k, box_rows, 1}, SWIZZLE_128B (gadm_api.cu)
+// dtype: 0 = bf16, 1 = fp16
+int make_tmap_2b_3d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t batch,
+                    uint32_t box_k, uint32_t box_rows, int dtype);
+
+// Layout of the model-side `aux` buffer (gadm_prep_model), in floats, n = n_obj * M:
+//   [0, n)        1 / max(|m_j|, 1e-12)                column scales of the matcher epilogue
+//   [n, 4n)       model xyz, [n_obj, M, 3] fp32        (Kabsch moments)
+//   [4n, 7n)      x, y, z planes, [3, n_obj, M] fp32   (SOFT epilogue: one bulk copy per plane and tile)
+__host__ __device__ inline size_t aux_total_floats(int n_obj, int M) { return size_t(n_obj) * M * 7; }
+__host__ __device__ inline const float* aux_scales(const float* aux, int, int) { return aux; }
+__host__ __device__ inline const float* aux_xyz(const float* aux, int n_obj, int M) { return aux + size_t(n_obj) * M; }
+__host__ __device__ inline const float* aux_planes(const float* aux, int n_obj, int M) { return aux + size_t(n_obj) * M * 4; }
 
 // match_sm100.cu
 int match_configure();

@@ -5,6 +5,7 @@
 //   model side.  Also the Kabsch moment reduction that follows the matcher
 //   (utils/pvn3d_eval_utils_kpls.py:57-63).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "gadm_internal.h"
 
@@ -19,7 +20,7 @@ template <int kSide>
 __global__ void __launch_bounds__(256)
 prep_kernel(const float* __restrict__ src, const float* __restrict__ xyz, int d, int P, int x3, int pad_mode,
             __nv_bfloat16* __restrict__ dst, float* __restrict__ rinv, float* __restrict__ pad_sim,
-            float* __restrict__ aux4, float* __restrict__ aux1) {
+            float* __restrict__ aux_scale, float* __restrict__ aux_xyz, float* __restrict__ aux_planes, size_t plane) {
   extern __shared__ float tile[];  // [d][PTS + 1]
   const int g = blockIdx.y;
   const int p0 = blockIdx.x * PTS;
@@ -80,14 +81,18 @@ prep_kernel(const float* __restrict__ src, const float* __restrict__ xyz, int d,
           pad_sim[gp] = e0 * r;
         }
       } else {
-        // aux: per object, per 256-vertex tile: [1/|m| x256 | x x256 | y x256 | z x256]
-        const int tiles = (P + 255) / 256;
-        float* a = aux4 + (size_t(g) * tiles + p / 256) * 1024 + (p & 255);
-        a[0] = r;
-        a[256] = xyz ? xyz[gp * 3 + 0] : 0.f;
-        a[512] = xyz ? xyz[gp * 3 + 1] : 0.f;
-        a[768] = xyz ? xyz[gp * 3 + 2] : 0.f;
+        aux_scale[gp] = r;   // column scale of the matcher epilogue
       }
+    }
+  }
+  if (kSide == 1) {
+    // model coordinates: fp32 copy (Kabsch) and the x / y / z planes of the SOFT epilogue
+    for (int e = threadIdx.x; e < 3 * PTS; e += blockDim.x) {
+      const int pl = e / 3, c = e - 3 * pl, p = p0 + pl;
+      if (p >= P) continue;
+      const float v = xyz ? xyz[(size_t(g) * P + p0) * 3 + e] : 0.f;
+      aux_xyz[(size_t(g) * P + p0) * 3 + e] = v;
+      aux_planes[c * plane + size_t(g) * P + p] = v;
     }
   }
 }
@@ -99,7 +104,7 @@ kabsch_moments_kernel(const int64_t* __restrict__ idx, const uint8_t* __restrict
                       const int32_t* __restrict__ obj_id, int B, int N, int M, int n_obj, double* __restrict__ out) {
   const int b = blockIdx.x;
   const int obj = obj_id ? obj_id[b] : (n_obj == B ? b : 0);
-  const float* tab = aux + size_t(obj) * ((M + 255) / 256) * 1024;
+  const float* tab = aux_xyz(aux, n_obj, M) + size_t(obj) * M * 3;
   double acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.0;
@@ -108,9 +113,9 @@ kabsch_moments_kernel(const int64_t* __restrict__ idx, const uint8_t* __restrict
     const int64_t j = idx[gn];
     if (j < 0 || j >= M) continue;
     if (mask && !mask[gn]) continue;
-    const float* e = tab + (j >> 8) * 1024 + (j & 255);
+    const float* e = tab + j * 3;
     float4 a;
-    a.x = e[256]; a.y = e[512]; a.z = e[768];
+    a.x = e[0]; a.y = e[1]; a.z = e[2];
     const float bx = cloud[gn * 3 + 0], by = cloud[gn * 3 + 1], bz = cloud[gn * 3 + 2];
     acc[0] += 1.0;
     acc[1] += a.x; acc[2] += a.y; acc[3] += a.z;
@@ -143,7 +148,7 @@ int prep_rows_launch(const float* feat, int B, int d, int N, int operand_mode, i
   dim3 grid((N + PTS - 1) / PTS, B);
   const size_t smem = size_t(d) * (PTS + 1) * sizeof(float);
   prep_kernel<0><<<grid, 256, smem, stream>>>(feat, nullptr, d, N, operand_mode == GADM_OPERAND_BF16X3, pad_mode,
-                                              static_cast<__nv_bfloat16*>(rows), rinv, pad_sim, nullptr, nullptr);
+                                              static_cast<__nv_bfloat16*>(rows), rinv, pad_sim, nullptr, nullptr, nullptr, 0);
   return check_launch();
 }
 
@@ -151,11 +156,11 @@ int prep_model_launch(const float* mesh, const float* model_xyz, int n_obj, int 
                       float* aux, cudaStream_t stream) {
   dim3 grid((M + PTS - 1) / PTS, n_obj);
   const size_t smem = size_t(d) * (PTS + 1) * sizeof(float);
-  // the pad columns of the last tile must be finite (they are multiplied by an exact 0 weight in the kernel)
-  cudaError_t e = cudaMemsetAsync(aux, 0, size_t(n_obj) * ((M + 255) / 256) * 1024 * sizeof(float), stream);
-  if (e != cudaSuccess) return set_cuda_error(e);
+  const size_t plane = size_t(n_obj) * M;
+  float* a_xyz = aux + plane;
+  float* a_planes = aux + plane * 4;
   prep_kernel<1><<<grid, 256, smem, stream>>>(mesh, model_xyz, d, M, operand_mode == GADM_OPERAND_BF16X3, 0,
-                                              static_cast<__nv_bfloat16*>(cols), nullptr, nullptr, aux, nullptr);
+                                              static_cast<__nv_bfloat16*>(cols), nullptr, nullptr, aux, a_xyz, a_planes, plane);
   return check_launch();
 }
 

@@ -67,7 +67,7 @@ def prep_model(mesh: torch.Tensor, model_xyz: torch.Tensor, operand_mode: int) -
     kp = lib.gadm_operand_k(d, operand_mode)
     _lib.check(min(kp, 0), "gadm_operand_k")
     cols = torch.empty((n_obj, M, kp), dtype=torch.bfloat16, device=mesh.device)
-    aux = torch.empty((n_obj * ((M + 255) // 256) * 1024,), dtype=torch.float32, device=mesh.device)
+    aux = torch.empty((lib.gadm_aux_floats(n_obj, M),), dtype=torch.float32, device=mesh.device)
     with torch.cuda.device(mesh.device):
         _lib.check(lib.gadm_prep_model(_ptr(mesh), _ptr(model_xyz), n_obj, d, M, operand_mode, _ptr(cols), _ptr(aux),
                                        _stream()), "gadm_prep_model")
