@@ -189,17 +189,17 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
     // ============================== UMMA issuer ==============================
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(BM, BN);
-      ptx::mbar_wait_sleep(&bars->a_full, 0);
+      ptx::mbar_wait(&bars->a_full, 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < num_tiles; ++t) {
         const int acc = t & 1;
         const uint32_t use = uint32_t(t) >> 1;
-        ptx::mbar_wait_sleep(&bars->s_free[acc], (use & 1) ^ 1);
+        ptx::mbar_wait(&bars->s_free[acc], (use & 1) ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < p.KB; ++kb) {
-          ptx::mbar_wait_sleep(&bars->full[stage], phase);
+          ptx::mbar_wait(&bars->full[stage], phase);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(smem_a + kb * A_BLK_BYTES);
           const uint32_t b_addr = ptx::smem_u32(smem_b + stage * B_STAGE_BYTES);
