@@ -7,20 +7,34 @@
 // and soft coordinates are the extension defined in oracle/match_oracle.py.
 //
 // Work decomposition
-//   CTA  = one 128-row tile of one frame (grid = ceil(N/128) x B), 18 warps:
-//     warp 16     TMA producer: the 128 x K' row tile once, then model tiles (256 vertices x 64 k, 32 KB) through an
-//                 S-stage mbarrier ring, plus per tile the column scales 1/|m_j| and (SOFT) the x / y / z planes
-//     warp 17     UMMA issuer: 128x256x16 tcgen05.mma, accumulators double-buffered in TMEM (2 x 256 columns)
-//     warps 0..15 epilogue, thread = row: warp w owns TMEM lanes 32*(w%4).. and the 64-column slice w/4 of EVERY
-//                 tile, so a tile is drained in the time one warp needs for two 32-column chunks -- the accumulator
-//                 must be free again within one tile time of the tensor pipe, latency matters more than throughput.
-//                 Per chunk: tcgen05.ld, score = acc * 1/|m_j| (packed f32x2), 3-input max tree, first-maximal-
-//                 index search only when the chunk beats the running maximum; SOFT adds p = 2^(score*g - m_ref)
-//                 against a LAZY reference exponent (raised, with a rescale of the sums, only when exceeded by
-//                 more than 8), and fp32 sums of p and p * xyz.  The four slices of a row merge through shared
-//                 memory at the end.
-//   (A tensor-core P.V product for the coordinate sums was built and measured this round: a 128x16x16
-//   tcgen05.mma costs ~120 cycles whatever its N, so 16 of them per tile cost more than the similarity GEMM.)
+//   CTA  = RT row tiles of 128 scene points of one frame (grid = ceil(N / (128 RT)) x B), 18 warps.
+//          ARGMAX uses RT = 2 whenever the operands allow it (K' <= 128): every model tile that TMA brings in from
+//          L2 feeds TWO 128x256 accumulators, which halves the L2 -> SM operand traffic (1.3 GB per 8-frame launch
+//          with RT = 1) and binds each accumulator to its own 8 epilogue warps.
+//     warp 16     TMA producer: the (128 RT) x K' row tile once, then model tiles (256 vertices x 64 k, 32 KB) through
+//                 an S-stage mbarrier ring, plus per tile the column scales 1/|m_j| and (SOFT) the x / y / z planes
+//     warp 17     UMMA issuer: 128x256x16 tcgen05.mma into two 256-column TMEM accumulators.  RT = 1: the two
+//                 accumulators alternate between consecutive model tiles; RT = 2: accumulator r belongs to row tile r
+//                 and the MMAs of (tile t, r = 0), (t, 1), (t+1, 0) ... alternate, so either way the epilogue of one
+//                 accumulator overlaps the MMAs into the other.
+//     warps 0..15 epilogue, thread = row.  RT = 1: warp w owns TMEM lanes 32 (w % 4).. and the 64-column slice w / 4
+//                 of every tile; RT = 2: row tile (w / 4) % 2, 128-column slice w / 8.
+//                 Per 32-column chunk: tcgen05.ld, score = acc * 1/|m_j| (packed f32x2), 3-input max tree per 8
+//                 columns.  The position of the maximum inside its 8-column group is NOT searched in the loop (a
+//                 search is ~70 warp-divergent instructions and some lane of a warp needs one in most chunks): a
+//                 thread whose running maximum rises stores the group's 8 scores to a private shared-memory stash
+//                 with two predicated STS.128, and the first maximal index is looked up there once, after the last
+//                 tile.  SOFT adds p = 2^(score*g - m_ref) against a LAZY reference exponent (raised, with a rescale
+//                 of the sums, only when exceeded by more than 8), and fp32 sums of p and p * xyz.  The column slices
+//                 of a row merge through shared memory at the end.
+//   What bounds it (tools/epilogue_probe.cu, tools/tmem_probe.cu, tools/umma_probe.cu; profiles/SUMMARY_r1.md): not the
+//   tensor pipe, not TMEM bandwidth and not MUFU (2^x issues every ~2 cycles per scheduler), but the SM's single
+//   MIO / shared-memory pipe.  A broadcast LDS.128 costs ~5 of its cycles, the per-column scales alone are 256 of
+//   them per tile (~1400 cycles against 1024 cycles of MMA), SOFT adds 768 for the coordinate planes, and every
+//   tcgen05.ld queues behind the other warps' LDS / MUFU traffic.  A variant that moves the coordinate sums onto the
+//   tensor core (P rounded to fp16 and stored back over the scores in TMEM, sixteen 128x16x16 tcgen05.mma per tile
+//   against [hi(xyz) | lo(xyz) | 1]) passed parity but its extra TMEM round trips cost what the saved LDS gained;
+//   it is kept under tools/experiments/ with the measurements.
 #include <cuda_fp16.h>
 #include <float.h>
 #include <stdio.h>
@@ -35,7 +49,7 @@ namespace gadm {
 
 namespace {
 
-constexpr int BM = 128;               // rows (scene points) per CTA == UMMA M
+constexpr int BM = 128;               // rows (scene points) per row tile == UMMA M
 constexpr int BK = 64;                // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_BLK_BYTES = BM * BK * 2;     // 16 KB
@@ -44,12 +58,12 @@ constexpr int BN = 256;               // model vertices per accumulator tile == 
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
 constexpr int AUX_SLOTS = 4;                 // per-tile {1/|m|, x, y, z} ring, decoupled from the two accumulators
 constexpr int PLANE_BYTES = BN * 4;          // one fp32 plane of a tile
-constexpr int EPI_SUB = 4;                   // column slices per tile (epilogue warps per TMEM lane quarter)
-constexpr int EPI_WARPS = 4 * EPI_SUB;
-constexpr int CS = BN / EPI_SUB;             // columns per slice (64)
+constexpr int EPI_WARPS = 16;
 constexpr int NUM_THREADS = (EPI_WARPS + 2) * 32;   // warps 0-15 epilogue, 16 TMA, 17 UMMA
-constexpr int XCH_BYTES = (EPI_SUB - 1) * BM * 8 * 4;  // per-row state exchange between the column slices
-constexpr int BOUND_BYTES = BM * EPI_SUB * 4;          // running maxima of the four slices of every row
+constexpr int GRP = 8;                                 // columns per argmax group (stash granularity)
+constexpr int STASH_BYTES = EPI_WARPS * 32 * GRP * 4;  // per epilogue thread: the 8 scores of its best group
+constexpr int STASH_PLANE = EPI_WARPS * 32 * 16;       // float4 k of thread t lives at k * STASH_PLANE + t * 16
+static_assert(STASH_PLANE == 8192, "ptx::sts_stash8 hard-codes the plane stride");
 constexpr int TMEM_COLS = 512;
 constexpr float LAZY_TAU = 8.f;              // reference exponent is raised only when exceeded by more than this
 
@@ -57,8 +71,8 @@ struct Barriers {
   uint64_t full[MAX_STAGES];
   uint64_t empty[MAX_STAGES];
   uint64_t a_full;
-  uint64_t s_full[2];    // S accumulator of parity p complete (UMMA commit)
-  uint64_t s_free[2];    // S accumulator of parity p drained by all epilogue warps
+  uint64_t s_full[2];    // accumulator a complete (UMMA commit)
+  uint64_t s_free[2];    // accumulator a drained by all of its epilogue warps
   uint64_t aux_full[AUX_SLOTS];
   uint64_t aux_empty[AUX_SLOTS];
   uint32_t tmem_base;
@@ -86,41 +100,28 @@ __device__ __forceinline__ int frame_object(const MatchParams& p, int b) {
   return p.n_obj == p.B ? b : 0;
 }
 
-// first j with v[j] == m (m is the maximum of v, so one exists); W = 16 or 32
-template <int W>
-__device__ __forceinline__ int first_equal(const uint32_t (&v)[W], float m) {
-  int j_a = W, j_b = W, j_c = W, j_d = W - 1;  // four independent select chains, W = no hit
-  constexpr int Q = W / 4;
-#pragma unroll
-  for (int j = Q - 1; j >= 0; --j) {
-    if (__uint_as_float(v[j]) == m) j_a = j;
-    if (__uint_as_float(v[j + Q]) == m) j_b = j + Q;
-    if (__uint_as_float(v[j + 2 * Q]) == m) j_c = j + 2 * Q;
-    if (j < Q - 1 && __uint_as_float(v[j + 3 * Q]) == m) j_d = j + 3 * Q;
-  }
-  return min(min(j_a, j_b), min(j_c, j_d));
-}
-
-template <bool kSoft>
+template <bool kSoft, int RT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
              const MatchParams p) {
   constexpr int AUX_BYTES = kSoft ? 4 * PLANE_BYTES : PLANE_BYTES;
+  constexpr int SL = 4 / RT;                 // column slices per row (epilogue threads that share a row)
+  constexpr int CS = BN / SL;                // columns per slice: 64 (RT = 1) or 128 (RT = 2)
+  constexpr int ACC_WARPS = EPI_WARPS / RT;  // epilogue warps per accumulator (RT = 1: all of them, either one)
 
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem_a + p.KB * A_BLK_BYTES;
+  uint8_t* smem_a = smem;                                    // [RT][KB] blocks of 128 rows x 64 k
+  uint8_t* smem_b = smem_a + RT * p.KB * A_BLK_BYTES;
   uint8_t* smem_aux = smem_b + p.stages * B_STAGE_BYTES;   // per slot: [1/|m| x256 | x x256 | y x256 | z x256]
-  uint8_t* smem_xch = smem_aux + AUX_SLOTS * AUX_BYTES;
-  float* smem_bound = reinterpret_cast<float*>(smem_xch + XCH_BYTES);
-  Barriers* bars = reinterpret_cast<Barriers*>(smem_xch + XCH_BYTES + BOUND_BYTES);
+  uint8_t* smem_stash = smem_aux + AUX_SLOTS * AUX_BYTES;
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_stash + STASH_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.y;
-  const int row0 = blockIdx.x * BM;
+  const int row0 = blockIdx.x * (BM * RT);
   const int obj = frame_object(p, b);
   const int num_tiles = (p.M + BN - 1) / BN;
 
@@ -134,7 +135,7 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
     ptx::mbar_init(&bars->a_full, 1);
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&bars->s_full[a], 1);
-      ptx::mbar_init(&bars->s_free[a], EPI_WARPS);  // one arrive per epilogue warp
+      ptx::mbar_init(&bars->s_free[a], ACC_WARPS);  // one arrive per epilogue warp of the accumulator
     }
     for (int a = 0; a < AUX_SLOTS; ++a) {
       ptx::mbar_init(&bars->aux_full[a], 1);
@@ -146,7 +147,6 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
     ptx::tmem_alloc(&bars->tmem_base, TMEM_COLS);
     ptx::tmem_relinquish();
   }
-  if (threadIdx.x < BM * EPI_SUB) smem_bound[threadIdx.x] = -INFINITY;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -155,9 +155,11 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
   if (warp == EPI_WARPS) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(&bars->a_full, p.KB * A_BLK_BYTES);
-      for (int kb = 0; kb < p.KB; ++kb)
-        ptx::tma_load_3d(smem_a + kb * A_BLK_BYTES, &tmap_rows, &bars->a_full, kb * BK, row0, b);
+      ptx::mbar_arrive_expect_tx(&bars->a_full, RT * p.KB * A_BLK_BYTES);
+      for (int r = 0; r < RT; ++r)
+        for (int kb = 0; kb < p.KB; ++kb)
+          ptx::tma_load_3d(smem_a + (r * p.KB + kb) * A_BLK_BYTES, &tmap_rows, &bars->a_full, kb * BK,
+                           row0 + r * BM, b);   // rows >= N are zero-filled by TMA
       int stage = 0;
       uint32_t phase = 0;
       const size_t plane = size_t(p.n_obj) * p.M;
@@ -187,65 +189,92 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
     }
   } else if (warp == EPI_WARPS + 1) {
     // ============================== UMMA issuer ==============================
+    // (waits with a suspend-time hint: a busy poll competes for the MIO pipe the epilogue warps depend on)
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(BM, BN);
       ptx::mbar_wait(&bars->a_full, 0);
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage0 = 0;            // ring position of the tile's first K block
+      uint32_t phase0 = 0;
+#ifdef GADM_MATCH_TRACE
+      long long tr_free = 0, tr_full = 0, tr_t0 = clock64();
+#endif
       for (int t = 0; t < num_tiles; ++t) {
-        const int acc = t & 1;
-        const uint32_t use = uint32_t(t) >> 1;
-        ptx::mbar_wait(&bars->s_free[acc], (use & 1) ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.KB; ++kb) {
-          ptx::mbar_wait(&bars->full[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(smem_a + kb * A_BLK_BYTES);
-          const uint32_t b_addr = ptx::smem_u32(smem_b + stage * B_STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            ptx::umma_bf16_ss(d_tmem, ptx::umma_desc_sw128_kmajor(a_addr + k * UMMA_K * 2),
-                              ptx::umma_desc_sw128_kmajor(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0);
+        for (int r = 0; r < RT; ++r) {
+          const int acc = RT == 1 ? (t & 1) : r;
+          const uint32_t use = RT == 1 ? uint32_t(t) >> 1 : uint32_t(t);
+#ifdef GADM_MATCH_TRACE
+          const long long c0 = clock64();
+#endif
+          ptx::mbar_wait_sleep(&bars->s_free[acc], (use & 1) ^ 1);
+#ifdef GADM_MATCH_TRACE
+          tr_free += clock64() - c0;
+#endif
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          int stage = stage0;
+          uint32_t phase = phase0;
+          for (int kb = 0; kb < p.KB; ++kb) {
+            if (r == 0) {      // the stages of this tile stay resident until the last row tile has used them
+#ifdef GADM_MATCH_TRACE
+              const long long c1 = clock64();
+#endif
+              ptx::mbar_wait_sleep(&bars->full[stage], phase);
+#ifdef GADM_MATCH_TRACE
+              tr_full += clock64() - c1;
+#endif
+              ptx::tc_fence_after();
+            }
+            const uint32_t a_addr = ptx::smem_u32(smem_a + (r * p.KB + kb) * A_BLK_BYTES);
+            const uint32_t b_addr = ptx::smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              ptx::umma_bf16_ss(d_tmem, ptx::umma_desc_sw128_kmajor(a_addr + k * UMMA_K * 2),
+                                ptx::umma_desc_sw128_kmajor(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0);
+            }
+            if (r == RT - 1) ptx::umma_commit(&bars->empty[stage]);  // frees the stage once these MMAs have read it
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          ptx::umma_commit(&bars->empty[stage]);  // frees the smem stage once these MMAs have read it
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          ptx::umma_commit(&bars->s_full[acc]);     // accumulator tile complete
+          if (r == RT - 1) { stage0 = stage; phase0 = phase; }
         }
-        ptx::umma_commit(&bars->s_full[acc]);     // accumulator tile complete
       }
+#ifdef GADM_MATCH_TRACE
+      if ((blockIdx.x == 3 || blockIdx.x == 40) && blockIdx.y == 0)
+        printf("cta %d umma thread: %lld cycles for %d tiles x %d row tiles; waiting for a free accumulator %lld, "
+               "for operands %lld\n", blockIdx.x, clock64() - tr_t0, num_tiles, RT, tr_free, tr_full);
+#endif
     }
   } else {
-    // ============================== epilogue warps (thread == row, four column slices per row) ==============
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access (warp id % 4)
-    const int sub = warp >> 2;              // 64-column slice of every tile
+    // ============================== epilogue warps (thread == row, SL column slices per row) ==============
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access (warp id % 4)
+    const int rt = RT == 1 ? 0 : (warp >> 2) & 1;    // row tile
+    const int sub = RT == 1 ? warp >> 2 : warp >> 3; // column slice of every tile
     const int row_in_tile = q * 32 + lane;
-    const int row = row0 + row_in_tile;
+    const int row = row0 + rt * BM + row_in_tile;
     const bool row_ok = row < p.N;
     const size_t grow = size_t(b) * p.N + (row_ok ? row : 0);
     const float rs = row_ok ? p.rinv_rows[grow] : 0.f;
     const float g = p.gamma_log2e * rs;     // exponent scale: t = (acc * 1/|m_j|) * g   (log2 units)
     const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16) + sub * CS;
+    const uint32_t stash_addr = ptx::smem_u32(smem_stash) + threadIdx.x * 16;
 
-    // The running maximum of each slice is published per tile; a chunk below the best value any slice of the row
-    // has seen cannot hold the row's argmax, so the (warp-divergent) index search is skipped for it.  Stale
-    // values are still valid lower bounds, no synchronisation is needed.
-    const uint32_t bound_addr = ptx::smem_u32(smem_bound + row_in_tile * EPI_SUB);
-    float vmax = -INFINITY, thr = -INFINITY;
-    int vidx = 0;
+    float vmax = -INFINITY;                 // running maximum of this thread's slice of the row
+    int vgrp = 0;                           // first column of the 8-column group that first reached it
     float mref = 0.f;
     bool have_ref = false;
     // packed (even | odd column) partial sums, two independent chains each
     uint64_t l2a = 0, l2b = 0, ax2a = 0, ax2b = 0, ay2a = 0, ay2b = 0, az2a = 0, az2b = 0;
 
 #ifdef GADM_MATCH_TRACE
-    long long tr[4][4];
+    long long tr_wait = 0, tr_t0 = clock64();
 #endif
     for (int t = 0; t < num_tiles; ++t) {
-      const int acc = t & 1;
-      const uint32_t use = uint32_t(t) >> 1;
+      const int acc = RT == 1 ? (t & 1) : rt;
+      const uint32_t use = RT == 1 ? uint32_t(t) >> 1 : uint32_t(t);
       const int slot = t % AUX_SLOTS;
 #ifdef GADM_MATCH_TRACE
-      if (t >= 8 && t < 12) tr[t - 8][0] = clock64();
+      const long long c0 = clock64();
 #endif
       // both barriers are polled back to back so that their check latencies overlap
       if (!(ptx::mbar_try_wait(&bars->aux_full[slot], (uint32_t(t) / AUX_SLOTS) & 1) &
@@ -255,48 +284,58 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
       }
       ptx::tc_fence_after();
 #ifdef GADM_MATCH_TRACE
-      if (t >= 8 && t < 12) tr[t - 8][1] = clock64();
+      tr_wait += clock64() - c0;
 #endif
       const int ncols = min(BN, p.M - t * BN) - sub * CS;   // valid columns of this slice (may be <= 0)
       const uint32_t s_tmem = lane_base + acc * BN;
       const uint32_t sc_addr = ptx::smem_u32(smem_aux + slot * AUX_BYTES) + sub * CS * 4;
+      const int col_base = t * BN + sub * CS;
 
-      // One chunk of W (32 or 16) columns starting at slice column col0: scores, running (max, first argmax);
-      // SOFT: exponentials, sums of p and p * xyz.  kGuard (ragged last tile only) masks columns >= ncols.
-      auto process = [&](auto& r, int col0, auto guard_tag) {
-        constexpr int W = int(sizeof(r) / sizeof(r[0]));
+      // One chunk of 32 columns starting at slice column col0 (at least one of them valid).  r[] holds the raw
+      // accumulators on entry.  Scores (scaled by 1/|m_j|) stay packed in pairs; per 8-column group: 3-input max
+      // tree, and -- predicated, no branch -- the group's scores go to the stash when they raise the thread's
+      // running maximum.  SOFT: exponentials, sums of p and p * xyz.  kGuard (ragged last tile only) masks
+      // columns >= ncols.
+      auto process = [&](uint32_t (&r)[32], int col0, auto guard_tag) {
+        constexpr int W = 32;
+        constexpr int NG = W / GRP;
         constexpr bool kGuard = decltype(guard_tag)::value;
         const uint32_t sc = sc_addr + col0 * 4;
+        uint64_t v[W / 2];
 #pragma unroll
         for (int j4 = 0; j4 < W / 4; ++j4) {
           const float4 cm = ptx::lds128(sc + j4 * 16);
-          const uint64_t v01 = ptx::fmul2(ptx::pack2(r[j4 * 4 + 0], r[j4 * 4 + 1]), ptx::pack2f(cm.x, cm.y));
-          const uint64_t v23 = ptx::fmul2(ptx::pack2(r[j4 * 4 + 2], r[j4 * 4 + 3]), ptx::pack2f(cm.z, cm.w));
-          ptx::unpack2(v01, r[j4 * 4 + 0], r[j4 * 4 + 1]);
-          ptx::unpack2(v23, r[j4 * 4 + 2], r[j4 * 4 + 3]);
+          v[j4 * 2 + 0] = ptx::fmul2(ptx::pack2(r[j4 * 4 + 0], r[j4 * 4 + 1]), ptx::pack2f(cm.x, cm.y));
+          v[j4 * 2 + 1] = ptx::fmul2(ptx::pack2(r[j4 * 4 + 2], r[j4 * 4 + 3]), ptx::pack2f(cm.z, cm.w));
         }
         if (kGuard) {  // TMA zero-fills columns >= M and the stale scales behind them are meaningless
 #pragma unroll
-          for (int j = 0; j < W; ++j)
-            if (col0 + j >= ncols) r[j] = __float_as_uint(-INFINITY);
+          for (int j = 0; j < W / 2; ++j) {
+            float lo, hi;
+            ptx::unpack2f(v[j], lo, hi);
+            if (col0 + 2 * j >= ncols) lo = -INFINITY;
+            if (col0 + 2 * j + 1 >= ncols) hi = -INFINITY;
+            v[j] = ptx::pack2f(lo, hi);
+          }
         }
-        // 3-input max tree
-        float m4[W / 4];
+        float cmx = -INFINITY;
 #pragma unroll
-        for (int u = 0; u < W / 4; ++u)
-          m4[u] = ptx::fmax3(__uint_as_float(r[u * 4]), __uint_as_float(r[u * 4 + 1]),
-                             fmaxf(__uint_as_float(r[u * 4 + 2]), __uint_as_float(r[u * 4 + 3])));
-        float cmx = fmaxf(ptx::fmax3(m4[0], m4[1], m4[2]), m4[3]);
-        if (W == 32) cmx = ptx::fmax3(cmx, ptx::fmax3(m4[W / 4 - 4], m4[W / 4 - 3], m4[W / 4 - 2]), m4[W / 4 - 1]);
-        // strict against the own maximum (an equal value in a later chunk never displaces the first maximal
-        // index), non-strict against the other slices (an equal value there may sit at a higher index)
-        if (cmx > vmax && cmx >= thr) {
-          vmax = cmx;
-          vidx = t * BN + sub * CS + col0 + first_equal(r, cmx);
+        for (int h = 0; h < NG; ++h) {
+          float f[GRP];
+#pragma unroll
+          for (int j = 0; j < GRP / 2; ++j) ptx::unpack2f(v[h * 4 + j], f[2 * j], f[2 * j + 1]);
+          const float a0 = ptx::fmax3(f[0], f[1], f[2]), a1 = ptx::fmax3(f[3], f[4], f[5]);
+          const float gm = ptx::fmax3(a0, a1, fmaxf(f[6], f[7]));
+          // strict: an equal value in a later group never displaces the first maximal index
+          const bool up = gm > vmax;
+          ptx::sts_stash8(up, stash_addr, v[h * 4 + 0], v[h * 4 + 1], v[h * 4 + 2], v[h * 4 + 3]);
+          vgrp = up ? col_base + col0 + h * GRP : vgrp;
+          vmax = up ? gm : vmax;
+          if (kSoft) cmx = h == 0 ? gm : fmaxf(cmx, gm);
         }
         if (kSoft) {
           const float tnew = cmx * g;
-          if (!have_ref) { mref = tnew; have_ref = true; }   // warp-uniform: first chunk of the first tile
+          if (!have_ref) { mref = tnew; have_ref = true; }   // warp-uniform: first valid chunk of the slice
           if (__any_sync(0xffffffffu, tnew > mref + LAZY_TAU)) {
             // rare: raise the reference exponent and rescale the running sums
             const bool need = tnew > mref + LAZY_TAU;
@@ -315,8 +354,8 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
             const float4 X = ptx::lds128(sc + PLANE_BYTES + j4 * 16);
             const float4 Y = ptx::lds128(sc + 2 * PLANE_BYTES + j4 * 16);
             const float4 Z = ptx::lds128(sc + 3 * PLANE_BYTES + j4 * 16);
-            const uint64_t p01 = ptx::ex2_2(ptx::ffma2(ptx::pack2(r[j4 * 4 + 0], r[j4 * 4 + 1]), g2, nm2));
-            const uint64_t p23 = ptx::ex2_2(ptx::ffma2(ptx::pack2(r[j4 * 4 + 2], r[j4 * 4 + 3]), g2, nm2));
+            const uint64_t p01 = ptx::ex2_2(ptx::ffma2(v[j4 * 2 + 0], g2, nm2));
+            const uint64_t p23 = ptx::ex2_2(ptx::ffma2(v[j4 * 2 + 1], g2, nm2));
             l2a = ptx::fadd2(l2a, p01);
             l2b = ptx::fadd2(l2b, p23);
             ax2a = ptx::ffma2(p01, ptx::pack2f(X.x, X.y), ax2a);
@@ -331,51 +370,57 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
       using guard_off = std::integral_constant<bool, false>;
       using guard_on = std::integral_constant<bool, true>;
 
-      {
-        const float4 bd = ptx::lds128(bound_addr);
-        thr = fmaxf(fmaxf(bd.x, bd.y), fmaxf(bd.z, bd.w));
-      }
-      if (ncols >= CS) {
-        // full slice: both 32-column chunks are requested up front
+#pragma unroll
+      for (int c2 = 0; c2 < CS / 64; ++c2) {
+        const int nv = ncols - c2 * 64;      // valid columns of this pair of chunks
+        if (nv <= 0) break;
+        // ARGMAX keeps two 32-column chunks in flight (registers allow it), SOFT one
         uint32_t ra[32], rb[32];
-        ptx::tmem_ld_32x32(s_tmem, ra);
-        ptx::tmem_ld_32x32(s_tmem + 32, rb);
+        ptx::tmem_ld_32x32(s_tmem + c2 * 64, ra);
+        if (!kSoft) ptx::tmem_ld_32x32(s_tmem + c2 * 64 + 32, rb);
         ptx::tmem_ld_wait();
-#ifdef GADM_MATCH_TRACE
-        if (t >= 8 && t < 12) tr[t - 8][2] = clock64();
-#endif
-        process(ra, 0, guard_off{});
-        process(rb, 32, guard_off{});
-      } else if (ncols > 0) {
-        // ragged last tile: 16-column chunks, masked
-        uint32_t rc[16];
-        const int n16 = (ncols + 15) / 16;
-#pragma unroll 1
-        for (int c = 0; c < n16; ++c) {
-          ptx::tmem_ld_32x16(s_tmem + c * 16, rc);
-          ptx::tmem_ld_wait();
-          process(rc, c * 16, guard_on{});
+        if (nv >= 32) process(ra, c2 * 64, guard_off{});
+        else process(ra, c2 * 64, guard_on{});         // ragged last tile
+        if (nv > 32) {
+          if (kSoft) {
+            ptx::tmem_ld_32x32(s_tmem + c2 * 64 + 32, rb);
+            ptx::tmem_ld_wait();
+          }
+          if (nv >= 64) process(rb, c2 * 64 + 32, guard_off{});
+          else process(rb, c2 * 64 + 32, guard_on{});
         }
       }
-      ptx::sts32(bound_addr + sub * 4, vmax);
       ptx::tc_fence_before();
       __syncwarp();
-#ifdef GADM_MATCH_TRACE
-      if (t >= 8 && t < 12) tr[t - 8][3] = clock64();
-#endif
       if (lane == 0) {
         ptx::mbar_arrive(&bars->s_free[acc]);
         ptx::mbar_arrive(&bars->aux_empty[slot]);
       }
     }
 #ifdef GADM_MATCH_TRACE
-    if (blockIdx.x == 3 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == 13))
-      for (int i = 0; i < 4; ++i)
-        printf("warp %d tile %d: start %lld  wait %lld  ldtm %lld  process %lld\n", warp, 8 + i, tr[i][0] - tr[0][0],
-               tr[i][1] - tr[i][0], tr[i][2] - tr[i][1], tr[i][3] - tr[i][2]);
+    if ((blockIdx.x == 3 || blockIdx.x == 40) && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == 13))
+      printf("cta %d epilogue warp %d: %lld cycles, of which waiting for accumulator/aux %lld\n", blockIdx.x, warp,
+             clock64() - tr_t0, tr_wait);
 #endif
 
-    // ---- merge the four column slices of every row: slices 1..3 publish, slice 0 combines and writes the outputs
+    // ---- first maximal index of this slice: look it up in the stashed group (own writes, no barrier needed)
+    int vidx = 0;
+    if (vmax > -INFINITY) {
+      int j_first = GRP - 1;
+#pragma unroll
+      for (int k = GRP / 4 - 1; k >= 0; --k) {
+        const float4 sv = ptx::lds128(stash_addr + k * STASH_PLANE);
+        if (sv.w == vmax) j_first = 4 * k + 3;
+        if (sv.z == vmax) j_first = 4 * k + 2;
+        if (sv.y == vmax) j_first = 4 * k + 1;
+        if (sv.x == vmax) j_first = 4 * k + 0;
+      }
+      vidx = vgrp + j_first;
+    }
+
+    // ---- merge the column slices of every row: slices 1.. publish, slice 0 combines and writes the outputs.
+    // The exchange buffer reuses the row tile's own A blocks: every MMA that reads them has completed (this warp
+    // has seen the last s_full of its accumulator).
     float lsum = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
     if (kSoft) {
       float e, o;
@@ -385,7 +430,7 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
       ptx::unpack2f(ptx::fadd2(az2a, az2b), e, o); az = e + o;
       if (!have_ref) mref = -INFINITY;
     }
-    float* xch = reinterpret_cast<float*>(smem_xch);
+    float* xch = reinterpret_cast<float*>(smem_a + rt * p.KB * A_BLK_BYTES);   // (SL - 1) * 128 * 32 B <= 16 KB
     if (sub > 0) {
       float* x = xch + ((sub - 1) * BM + row_in_tile) * 8;
       x[0] = vmax; x[1] = __int_as_float(vidx); x[2] = mref; x[3] = lsum;
@@ -395,7 +440,7 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
     if (sub == 0 && row_ok) {
       float mm = mref;
 #pragma unroll
-      for (int s2 = 0; s2 < EPI_SUB - 1; ++s2) {
+      for (int s2 = 0; s2 < SL - 1; ++s2) {
         const float* x = xch + (s2 * BM + row_in_tile) * 8;
         const float v1 = x[0];
         const int i1 = __float_as_int(x[1]);
@@ -415,7 +460,7 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
         const float s0 = ptx::ex2_approx(mref - mm);  // exp2(-inf) = 0 for a slice that saw no column
         float l = lsum * s0, sx = ax * s0, sy = ay * s0, sz = az * s0;
 #pragma unroll
-        for (int s2 = 0; s2 < EPI_SUB - 1; ++s2) {
+        for (int s2 = 0; s2 < SL - 1; ++s2) {
           const float* x = xch + (s2 * BM + row_in_tile) * 8;
           const float s1 = ptx::ex2_approx(x[2] - mm);
           l = fmaf(x[3], s1, l); sx = fmaf(x[4], s1, sx); sy = fmaf(x[5], s1, sy); sz = fmaf(x[6], s1, sz);
@@ -438,18 +483,30 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
 }
 
 template <bool kSoft>
-size_t match_smem_bytes(int KB, int stages) {
-  return size_t(KB) * A_BLK_BYTES + size_t(stages) * B_STAGE_BYTES + AUX_SLOTS * (kSoft ? 4 : 1) * PLANE_BYTES +
-         XCH_BYTES + BOUND_BYTES + sizeof(Barriers) + 1024;
+size_t match_smem_bytes(int RT, int KB, int stages) {
+  return size_t(RT) * KB * A_BLK_BYTES + size_t(stages) * B_STAGE_BYTES + AUX_SLOTS * (kSoft ? 4 : 1) * PLANE_BYTES +
+         STASH_BYTES + sizeof(Barriers) + 1024;
+}
+
+// the deepest model-tile ring that fits in 227 KB next to the row tiles (0: does not fit)
+template <bool kSoft>
+int match_stages(int RT, int KB) {
+  int stages = MAX_STAGES;
+  while (stages > 0 && match_smem_bytes<kSoft>(RT, KB, stages) > 227 * 1024) --stages;
+  return stages;
 }
 
 }  // namespace
 
 int match_configure() {
   cudaError_t e;
-  e = cudaFuncSetAttribute(match_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(match_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
-  e = cudaFuncSetAttribute(match_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(match_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(match_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(match_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
   return GADM_OK;
 }
@@ -457,9 +514,18 @@ int match_configure() {
 template <bool kSoft>
 static int match_launch_t(const void* rows, const void* cols, MatchParams p, int Kp, cudaStream_t stream) {
   const int KB = Kp / BK;
-  int stages = MAX_STAGES;  // the deepest ring that fits in 227 KB
-  while (stages > 2 && match_smem_bytes<kSoft>(KB, stages) > 227 * 1024) --stages;
-  if (match_smem_bytes<kSoft>(KB, stages) > 227 * 1024) return GADM_ERR_UNSUPPORTED;
+  // Two row tiles per CTA when a ring of at least 2 KB stages (one tile resident, one in flight) fits beside them
+  // and the frame has more than one row tile; otherwise one row tile with the deepest ring.  Measured at the
+  // BASELINE shape: ARGMAX 0.204 ms (RT = 2) against 0.222 ms; SOFT 0.43 ms (RT = 2) against 0.41 ms -- SOFT is
+  // bound by the epilogue's shared-memory traffic, not by operand traffic, and prefers 16 warps per accumulator.
+  int RT = kSoft ? 1 : 2;
+  if (const char* f = getenv("GADM_MATCH_RT")) RT = atoi(f) == 1 ? 1 : 2;   // profiling aid
+  int stages = match_stages<kSoft>(2, KB);
+  if (RT == 2 && (stages < 2 * KB || p.N <= BM)) RT = 1;
+  if (RT == 1) {
+    stages = match_stages<kSoft>(1, KB);
+    if (stages < 2) return GADM_ERR_UNSUPPORTED;
+  }
   p.KB = KB; p.stages = stages;
 
   CUtensorMap tmap_rows, tmap_cols;
@@ -468,8 +534,12 @@ static int match_launch_t(const void* rows, const void* cols, MatchParams p, int
   rc = make_tmap_2b_3d(&tmap_cols, cols, uint64_t(Kp), uint64_t(p.M), uint64_t(p.n_obj), BK, BN, 0);
   if (rc != GADM_OK) return rc;
 
-  dim3 grid((p.N + BM - 1) / BM, p.B);
-  match_kernel<kSoft><<<grid, NUM_THREADS, match_smem_bytes<kSoft>(KB, stages), stream>>>(tmap_rows, tmap_cols, p);
+  dim3 grid((p.N + BM * RT - 1) / (BM * RT), p.B);
+  const size_t smem = match_smem_bytes<kSoft>(RT, KB, stages);
+  if (RT == 2)
+    match_kernel<kSoft, 2><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+  else
+    match_kernel<kSoft, 1><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
   return check_launch();
 }
 

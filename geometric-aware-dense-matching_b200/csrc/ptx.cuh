@@ -284,6 +284,18 @@ __device__ __forceinline__ uint64_t ex2_2(uint64_t t) {
 __device__ __forceinline__ void sts32(uint32_t saddr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
 }
+// predicated (branch-free) store of four packed pairs = 8 floats: float4 k goes to saddr + k * 8192
+// (the stash of the matcher epilogue: plane-major so that a full warp stores without bank conflicts)
+__device__ __forceinline__ void sts_stash8(bool pred, uint32_t saddr, uint64_t v0, uint64_t v1, uint64_t v2,
+                                           uint64_t v3) {
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "setp.ne.b32 P, %0, 0;\n\t"
+      "@P st.shared.v2.b64 [%1], {%2, %3};\n\t"
+      "@P st.shared.v2.b64 [%1 + 8192], {%4, %5};\n\t}\n"
+      ::"r"(uint32_t(pred)), "r"(saddr), "l"(v0), "l"(v1), "l"(v2), "l"(v3)
+      : "memory");
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }  // -> FMNMX3
 // {hi, lo} fp32 -> packed f16x2 (round to nearest even); `lo` lands in the low half
 __device__ __forceinline__ uint32_t cvt_f16x2(float hi, float lo) {
@@ -298,6 +310,12 @@ __device__ __forceinline__ uint32_t hmul2(uint32_t a, uint32_t b) {
   return d;
 }
 
+// clock read that is ordered after the producer of `dep` (profiling builds only)
+__device__ __forceinline__ long long clock_after(uint32_t dep) {
+  long long t;
+  asm volatile("{\n\t.reg .b32 z;\n\tand.b32 z, %1, 0;\n\tmov.u64 %0, %%clock64;\n\t}" : "=l"(t) : "r"(dep) : "memory");
+  return t;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
