@@ -33,6 +33,7 @@ constexpr int TS = 1024;          // support points per shared-memory tile (12 K
 constexpr int R_MAX = 4;          // block radius (in cells) visited before the whole-cloud fallback
 constexpr int GRID_E = 4;         // pending candidates per lane between extractions (grid kernel)
 constexpr int BRUTE_E = 2;        // same, brute kernel (4 queries per warp: register budget)
+constexpr int HALF_BLOCK_K = 4;   // grid queries with k <= this try the 2x2x2 half-cell block first
 
 struct JobDev {
   long long support_off, query_off, out_off, support_bstride, query_bstride, out_bstride;
@@ -165,7 +166,10 @@ __device__ __forceinline__ const JobDev& find_job(const LaunchJobs& L, int tile,
 }
 
 // --------------------------------------------------------------------------------------------- BRUTE
-__global__ void __launch_bounds__(WARPS * 32)
+#ifndef GADM_KNN_BRUTE_MINB
+#define GADM_KNN_BRUTE_MINB 4
+#endif
+__global__ void __launch_bounds__(WARPS * 32, GADM_KNN_BRUTE_MINB)
 knn_brute_kernel(const float* __restrict__ support, const float* __restrict__ query, int32_t* __restrict__ idx,
                  float* __restrict__ dist2, const __grid_constant__ LaunchJobs L) {
   __shared__ float sm[TS * 3];
@@ -444,7 +448,10 @@ __device__ __forceinline__ void grid_offer_ranges(WarpSelect<GRID_E>& sel, const
   }
 }
 
-__global__ void __launch_bounds__(WARPS * 32)
+#ifndef GADM_KNN_MINB
+#define GADM_KNN_MINB 6
+#endif
+__global__ void __launch_bounds__(WARPS * 32, GADM_KNN_MINB)
 knn_grid_kernel(const float* __restrict__ query, int32_t* __restrict__ idx, float* __restrict__ dist2,
                 uint8_t* __restrict__ ws, const __grid_constant__ LaunchJobs L) {
   int item, qtile;
@@ -469,6 +476,43 @@ knn_grid_kernel(const float* __restrict__ query, int32_t* __restrict__ idx, floa
     WarpSelect<GRID_E> sel;
     sel.reset();
     bool done = false;
+
+    if (k <= HALF_BLOCK_K) {
+      // Few neighbours wanted (the 1-NN interpolation jobs are half of all queries): look at the 2x2x2 block of
+      // cells nearest to the query first -- per axis the query's own cell and the neighbour on the side of the
+      // cell half the query lies in.  Every unvisited point is then at least half a cell away; with ~16 points
+      // per cell column that almost always proves the result, at 4/9 of the candidates of the 3x3x3 block.
+      const float fx = (qx - g.ox) * g.ihx - float(cx), fy = (qy - g.oy) * g.ihy - float(cy),
+                  fz = (qz - g.oz) * g.ihz - float(cz);
+      const int x0 = max(fx < 0.5f ? cx - 1 : cx, 0), x1 = min(fx < 0.5f ? cx : cx + 1, g.dx - 1);
+      const int y0 = max(fy < 0.5f ? cy - 1 : cy, 0), y1 = min(fy < 0.5f ? cy : cy + 1, g.dy - 1);
+      const int z0 = max(fz < 0.5f ? cz - 1 : cz, 0), z1 = min(fz < 0.5f ? cz : cz + 1, g.dz - 1);
+      int rb = 0, re = 0;
+      if (lane < 4) {
+        const int z = z0 + (lane >> 1), y = y0 + (lane & 1);
+        if (z <= z1 && y <= y1) {
+          const int rowbase = (z * g.dy + y) * g.dx;
+          rb = start[rowbase + x0];
+          re = start[rowbase + x1 + 1];
+        }
+      }
+      grid_offer_ranges(sel, pts, rb, re, qx, qy, qz, k, lane);
+      sel.flush(k, lane);
+      float bound = FLT_MAX;
+      if (x0 > 0) bound = fminf(bound, qx - (g.ox + float(x0) * g.hx));
+      if (x1 < g.dx - 1) bound = fminf(bound, (g.ox + float(x1 + 1) * g.hx) - qx);
+      if (y0 > 0) bound = fminf(bound, qy - (g.oy + float(y0) * g.hy));
+      if (y1 < g.dy - 1) bound = fminf(bound, (g.oy + float(y1 + 1) * g.hy) - qy);
+      if (z0 > 0) bound = fminf(bound, qz - (g.oz + float(z0) * g.hz));
+      if (z1 < g.dz - 1) bound = fminf(bound, (g.oz + float(z1 + 1) * g.hz) - qz);
+      if (bound == FLT_MAX) {
+        done = true;
+      } else {
+        bound -= g.slack;
+        done = bound > 0.f && sel.kd != D_EMPTY && __uint_as_float(sel.kd) < bound * bound;
+      }
+      if (!done) sel.reset();   // the 3x3x3 block below contains these cells again
+    }
 
     for (int rho = 1; rho <= R_MAX && !done; ++rho) {
       // rho == 1: the whole 3x3x3 block, one range per (dz, dy) row.
@@ -541,8 +585,8 @@ int cells_for(int n_support) {
   return int(c);
 }
 
-float g_ppc = 8.f;            // target points per occupied cell column
-int g_grid_min_support = 512; // AUTO: smaller clouds are scanned by BRUTE
+float g_ppc = 16.f;           // target points per occupied cell column
+int g_grid_min_support = 128; // AUTO: smaller clouds are scanned by BRUTE
 
 bool job_uses_grid(const gadm_knn_job& j, int algo) {
   if (algo == GADM_KNN_BRUTE) return false;
