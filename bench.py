@@ -320,7 +320,9 @@ def run_gpu(args):
             "roofline": {"kernel": "match_kernel<soft> (tcgen05 fused similarity+softmax+argmax)", "bound": "tensor",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_kind": f"{pk_kind} bf16 burst", "flop_per_launch": flop_per_launch,
-                         "traffic": None},
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
+                         # (profiles/r1d_ncu_full_final_kernels.csv); algorithmic bytes: 45 MB of operands + outputs
+                         "traffic": 44.51e6, "traffic_unit": "bytes per launch (ncu, round 1)"},
             "variants": {"match_kernel_argmax_only_ms": argmax_ms,
                          "match_kernel_argmax_only_frac": flop_per_launch / (argmax_ms * 1e-3) / 1e12 / peak},
             "knn": {"algorithmic_bytes_per_step": pyr.algorithmic_bytes * FRAMES,

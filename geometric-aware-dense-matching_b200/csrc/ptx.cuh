@@ -231,6 +231,19 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
 }
+// Same load WITHOUT `volatile`: the compiler may schedule it freely (hoist it over the predicated stash stores and
+// the other volatile asm of the epilogue).  The caller pins it below the mbarrier wait that publishes the data by
+// deriving `saddr` from a value laundered with opaque() after that wait.
+__device__ __forceinline__ float4 lds128_free(uint32_t saddr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+// makes `v` opaque to the optimiser at this point of the volatile-asm order (a scheduling pin, no instruction)
+__device__ __forceinline__ uint32_t opaque(uint32_t v) {
+  asm volatile("" : "+r"(v) :: "memory");
+  return v;
+}
 __device__ __forceinline__ float lds32(uint32_t saddr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));

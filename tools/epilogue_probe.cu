@@ -36,17 +36,25 @@ __global__ void __launch_bounds__(576, 1) probe(long long* out, float* sink_out,
   float vmax = -1e30f; int vgrp = 0;
   uint64_t l2a = 0, l2b = 0;
   uint32_t acc = 0;
+  uint32_t rn[32];
+  if (MODE & 256) ptx::tmem_ld_32x32(tbase, rn);
   const long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
-    if (MODE & 64) {           // fresh accumulators from TMEM, as in the real kernel
+    if ((MODE & 64) && !(MODE & 256)) {           // fresh accumulators from TMEM, as in the real kernel
       ptx::tmem_ld_32x32(tbase + (it & 1) * 256 + ((it >> 1) & 1) * 32, r);
       ptx::tmem_ld_wait();
+    }
+    if (MODE & 256) {          // software-pipelined: wait for the chunk requested one iteration ago, request the next
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = rn[i];
+      ptx::tmem_ld_32x32(tbase + (it & 1) * 256 + ((it >> 1) & 1) * 32, rn);
     }
     uint64_t v[16];
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
       float4 cm;
-      if (MODE & 4) cm = ptx::lds128(sc + j4 * 16); else cm = make_float4(g, g, g, g);
+      if (MODE & 512) cm = ptx::lds128_free(sc + j4 * 16); else if (MODE & 4) cm = ptx::lds128(sc + j4 * 16); else cm = make_float4(g, g, g, g);
       v[j4 * 2 + 0] = ptx::fmul2(ptx::pack2(r[j4 * 4 + 0], r[j4 * 4 + 1]), ptx::pack2f(cm.x, cm.y));
       v[j4 * 2 + 1] = ptx::fmul2(ptx::pack2(r[j4 * 4 + 2], r[j4 * 4 + 3]), ptx::pack2f(cm.z, cm.w));
     }
@@ -120,6 +128,13 @@ int main() {
   run<13 + 128>(out, sink, "no stash + tcgen05.st x16 per chunk");
   run<13 + 64 + 128>(out, sink, "no stash + tcgen05.ld + tcgen05.st");
   run<64>(out, sink, "ffma/fadd only + tcgen05.ld");
+  run<13 + 64 + 256>(out, sink, "no stash + PREFETCHED tcgen05.ld");
+  run<13 + 64 + 128 + 256>(out, sink, "no stash + PREFETCHED tcgen05.ld + tcgen05.st");
+  run<15 + 64 + 128 + 256>(out, sink, "everything + PREFETCHED ld + st");
+  run<15 + 64 + 128>(out, sink, "everything + ld + st");
+  run<15 + 512>(out, sink, "everything, non-volatile scale LDS");
+  run<15 + 64 + 128 + 512>(out, sink, "everything + ld + st, non-volatile scale LDS");
+  run<13 + 64 + 512>(out, sink, "no stash + ld, non-volatile scale LDS");
   run<15>(out, sink, "everything, p ~ 2^-20 (fp16 subnormal)", 20.f);
   run<15>(out, sink, "everything, p ~ 2^-40 (fp16 zero)", 40.f);
   run<7>(out, sink, "no fp16 pack, p ~ 2^-20", 20.f);
