@@ -7,11 +7,11 @@ All compute goes through libgadm.so (C ABI: include/gadm.h).  No CPU fallback ex
 from ._lib import GadmError, LIB_PATH, load as load_library  # noqa: F401
 
 __all__ = ["GadmError", "LIB_PATH", "load_library", "matching", "knn", "dgcnn", "pointops", "sharding", "synth",
-           "ops", "pipeline"]
+           "ops", "pipeline", "randla"]
 
 
 def __getattr__(name):  # lazy: importing the package must not need CUDA (CPU-side tests import synth/sharding)
-    if name in ("matching", "knn", "dgcnn", "pointops", "sharding", "synth", "ops", "pipeline"):
+    if name in ("matching", "knn", "dgcnn", "pointops", "sharding", "synth", "ops", "pipeline", "randla"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

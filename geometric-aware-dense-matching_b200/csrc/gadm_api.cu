@@ -231,4 +231,19 @@ int gadm_gather_neighbour(const float* pc, const int64_t* idx, int B, int N, int
   return gather_neighbour_launch(pc, idx, B, N, C, M, K, out, (cudaStream_t)stream);
 }
 
+int gadm_gather_max(const float* feature, const int64_t* idx, int B, int C, int N, int M, int K, float* out,
+                    gadm_stream_t stream) {
+  GADM_REQUIRE_INIT();
+  if (!feature || !idx || !out || B <= 0 || C <= 0 || N <= 0 || M <= 0 || K <= 0) return GADM_ERR_BAD_ARG;
+  return gather_max_launch(feature, idx, B, C, N, M, K, out, static_cast<cudaStream_t>(stream));
+}
+
+int gadm_relative_pos_encoding(const float* xyz, const int64_t* idx, int B, int N, int K, float* out,
+                               gadm_stream_t stream) {
+  GADM_REQUIRE_INIT();
+  if (!xyz || !idx || !out || B <= 0 || N <= 0 || K <= 0) return GADM_ERR_BAD_ARG;
+  if (reinterpret_cast<uintptr_t>(out) & 7) return GADM_ERR_ALIGN;
+  return relative_pos_encoding_launch(xyz, idx, B, N, K, out, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

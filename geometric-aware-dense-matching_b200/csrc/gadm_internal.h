@@ -62,5 +62,9 @@ int group_bwd_launch(const float* grad_out, const int32_t* idx, int b, int c, in
                      float* grad_features, cudaStream_t stream);
 int gather_neighbour_launch(const float* pc, const int64_t* idx, int B, int N, int C, int M, int K, float* out,
                             cudaStream_t stream);
+int gather_max_launch(const float* feature, const int64_t* idx, int B, int C, int N, int M, int K, float* out,
+                      cudaStream_t stream);
+int relative_pos_encoding_launch(const float* xyz, const int64_t* idx, int B, int N, int K, float* out,
+                                 cudaStream_t stream);
 
 }  // namespace gadm

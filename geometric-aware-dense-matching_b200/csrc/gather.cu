@@ -120,7 +120,75 @@ gather_neighbour_kernel(const float* __restrict__ pc, const int64_t* __restrict_
   for (int c = lane; c < C; c += 32) dst[c] = src[c];
 }
 
+// thread = one output point m of one batch item (consecutive lanes = consecutive m: coalesced stores along M);
+// the K indices of the point are read once and reused for every channel of the thread's channel block.
+template <int KMAX>
+__global__ void __launch_bounds__(256)
+gather_max_kernel(const float* __restrict__ f, const int64_t* __restrict__ idx, int C, int N, int M, int K,
+                  int c_per_block, float* __restrict__ out) {
+  const int b = blockIdx.z;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  int nb[KMAX];
+  const int64_t* ip = idx + ((size_t)b * M + m) * K;
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) nb[j] = j < K ? int(ip[j]) : 0;
+  const int c0 = blockIdx.y * c_per_block;
+  const int c1 = min(C, c0 + c_per_block);
+  for (int c = c0; c < c1; ++c) {
+    const float* row = f + ((size_t)b * C + c) * N;
+    float v = row[nb[0]];
+#pragma unroll
+    for (int j = 1; j < KMAX; ++j)
+      if (j < K) v = fmaxf(v, row[nb[j]]);
+    out[((size_t)b * C + c) * M + m] = v;
+  }
+}
+
+// thread = one (n, k) pair: 10 floats = five float2 stores (40-byte rows are 8-byte aligned)
+__global__ void __launch_bounds__(256)
+relative_pos_encoding_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ idx, int N, long long NK,
+                             int K, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // n * K + k
+  if (e >= NK) return;
+  const int n = int(e / K);
+  const int q = int(idx[(size_t)b * NK + e]);
+  const float* xb = xyz + (size_t)b * N * 3;
+  const float px = xb[n * 3 + 0], py = xb[n * 3 + 1], pz = xb[n * 3 + 2];
+  const float qx = xb[q * 3 + 0], qy = xb[q * 3 + 1], qz = xb[q * 3 + 2];
+  const float dx = px - qx, dy = py - qy, dz = pz - qz;
+  const float dis = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+  float2* o = reinterpret_cast<float2*>(out + ((size_t)b * NK + e) * 10);
+  __stcs(o + 0, make_float2(dis, dx));
+  __stcs(o + 1, make_float2(dy, dz));
+  __stcs(o + 2, make_float2(px, py));
+  __stcs(o + 3, make_float2(pz, qx));
+  __stcs(o + 4, make_float2(qy, qz));
+}
+
 }  // namespace
+
+int gather_max_launch(const float* feature, const int64_t* idx, int B, int C, int N, int M, int K, float* out,
+                      cudaStream_t stream) {
+  if (B > 65535 || K > 32) return GADM_ERR_UNSUPPORTED;
+  const int c_per_block = 8;
+  dim3 grid((M + 255) / 256, (C + c_per_block - 1) / c_per_block, B);
+  if (grid.y > 65535) return GADM_ERR_UNSUPPORTED;
+  if (K == 1) gather_max_kernel<1><<<grid, 256, 0, stream>>>(feature, idx, C, N, M, K, c_per_block, out);
+  else if (K <= 16) gather_max_kernel<16><<<grid, 256, 0, stream>>>(feature, idx, C, N, M, K, c_per_block, out);
+  else gather_max_kernel<32><<<grid, 256, 0, stream>>>(feature, idx, C, N, M, K, c_per_block, out);
+  return check_launch();
+}
+
+int relative_pos_encoding_launch(const float* xyz, const int64_t* idx, int B, int N, int K, float* out,
+                                 cudaStream_t stream) {
+  if (B > 65535) return GADM_ERR_UNSUPPORTED;
+  const long long NK = (long long)N * K;
+  dim3 grid((unsigned)((NK + 255) / 256), B);
+  relative_pos_encoding_kernel<<<grid, 256, 0, stream>>>(xyz, idx, N, NK, K, out);
+  return check_launch();
+}
 
 int graph_feature_launch(const float* x, const int64_t* idx, int B, int C, int N, int k, float* out,
                          void* workspace, size_t workspace_bytes, cudaStream_t stream) {

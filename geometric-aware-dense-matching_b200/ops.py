@@ -288,3 +288,42 @@ def gather_neighbour(pc: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 @gather_neighbour.register_fake
 def _(pc, idx):
     return pc.new_empty((pc.shape[0], idx.shape[1], idx.shape[2], pc.shape[2]))
+
+
+# --------------------------------------------------------------------------------------------- RandLA consumers
+@torch.library.custom_op("gadm::gather_max", mutates_args=(), device_types="cuda")
+def gather_max(feature: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """feature [B, C, N] fp32, idx [B, M, K] int64 -> [B, C, M] = max_k feature[b, c, idx[b, m, k]]."""
+    _need(feature, torch.float32, "feature"); _need(idx, torch.int64, "idx")
+    B, C, N = feature.shape
+    _, M, K = idx.shape
+    out = torch.empty((B, C, M), dtype=torch.float32, device=feature.device)
+    lib = _lib_for(feature)
+    with torch.cuda.device(feature.device):
+        _lib.check(lib.gadm_gather_max(_ptr(feature), _ptr(idx), B, C, N, M, K, _ptr(out), _stream()),
+                   "gadm_gather_max")
+    return out
+
+
+@gather_max.register_fake
+def _(feature, idx):
+    return feature.new_empty((feature.shape[0], feature.shape[1], idx.shape[1]))
+
+
+@torch.library.custom_op("gadm::relative_pos_encoding", mutates_args=(), device_types="cuda")
+def relative_pos_encoding(xyz: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """xyz [B, N, 3] fp32, idx [B, N, K] int64 -> [B, N, K, 10] = [|p-q|, p-q, p, q]."""
+    _need(xyz, torch.float32, "xyz"); _need(idx, torch.int64, "idx")
+    B, N, _ = xyz.shape
+    K = idx.shape[2]
+    out = torch.empty((B, N, K, 10), dtype=torch.float32, device=xyz.device)
+    lib = _lib_for(xyz)
+    with torch.cuda.device(xyz.device):
+        _lib.check(lib.gadm_relative_pos_encoding(_ptr(xyz), _ptr(idx), B, N, K, _ptr(out), _stream()),
+                   "gadm_relative_pos_encoding")
+    return out
+
+
+@relative_pos_encoding.register_fake
+def _(xyz, idx):
+    return xyz.new_empty((xyz.shape[0], xyz.shape[1], idx.shape[2], 10))

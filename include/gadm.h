@@ -160,6 +160,17 @@ int gadm_group_bwd(const float* grad_out, const int32_t* idx, int b, int c, int 
 int gadm_gather_neighbour(const float* pc, const int64_t* idx, int B, int N, int C, int M, int K, float* out,
                           gadm_stream_t stream);
 
+/* RandLA pooling / interpolation (models/RandLA/RandLANet.py:90-105 random_sample, :107-120 nearest_interpolation):
+ * feature (B, C, N) fp32, idx (B, M, K) int64 -> out (B, C, M): out[b,c,m] = max_k feature[b, c, idx[b,m,k]]
+ * (K = 1: a plain gather).  The reference materialises the (B, C, M*K) gather first. */
+int gadm_gather_max(const float* feature, const int64_t* idx, int B, int C, int N, int M, int K, float* out,
+                    gadm_stream_t stream);
+/* RandLA relative position encoding (models/RandLA/RandLANet.py:720-727): xyz (B, N, 3) fp32, idx (B, N, K) int64
+ * -> out (B, N, K, 10) = [ |p - q|, p - q, p, q ] with p = xyz[b,n], q = xyz[b, idx[b,n,k]]; the distance is
+ * sqrt((dx*dx + dy*dy) + dz*dz) in fp32. */
+int gadm_relative_pos_encoding(const float* xyz, const int64_t* idx, int B, int N, int K, float* out,
+                               gadm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

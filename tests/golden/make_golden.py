@@ -6,6 +6,8 @@
   match_golden.npz   outputs of the reference's matcher lines, EXECUTED from the reference source text
                      (evaluator.py:89-93 and utils/pvn3d_eval_utils_kpls.py:437-441) on seeded descriptors
   dgcnn_golden.npz   outputs of models/dgcnn.py knn() / get_graph_feature() imported from /root/reference
+  randla_golden.npz  outputs of RandLANet.py random_sample / nearest_interpolation / relative_pos_encoding /
+                     gather_neighbour, EXECUTED from the reference source text
 Nothing from the reference is copied into the repo: only inputs and numeric outputs are stored."""
 import os
 import sys
@@ -102,9 +104,40 @@ def make_dgcnn():
     np.savez_compressed(os.path.join(HERE, "dgcnn_golden.npz"), **out)
 
 
+def make_randla():
+    """models/RandLA/RandLANet.py is not importable here (it imports the compiled nearest_neighbors extension), so
+    the four functions are EXECUTED from the reference's source text: random_sample :90-105,
+    nearest_interpolation :108-120, relative_pos_encoding :720-727, gather_neighbour :730-738."""
+    ns = {"torch": torch}
+    exec(ref_lines("models/RandLA/RandLANet.py", 90, 105), ns)
+    exec(ref_lines("models/RandLA/RandLANet.py", 108, 120), ns)
+    exec(ref_lines("models/RandLA/RandLANet.py", 720, 727), ns)
+    exec(ref_lines("models/RandLA/RandLANet.py", 730, 738), ns)
+
+    class _Block:                                            # relative_pos_encoding calls self.gather_neighbour
+        gather_neighbour = staticmethod(ns["gather_neighbour"])
+    g = torch.Generator().manual_seed(21)
+    B, C, N, M, K = 2, 12, 160, 40, 16
+    feature = torch.randn((B, C, N, 1), generator=g)
+    pool_idx = torch.randint(0, N, (B, M, K), generator=g)
+    interp_idx = torch.randint(0, N, (B, 3 * M, 1), generator=g)
+    xyz = torch.rand((B, N, 3), generator=g)
+    neigh_idx = torch.randint(0, N, (B, N, K), generator=g)
+    out = {"feature": feature.numpy(), "pool_idx": pool_idx.numpy(), "interp_idx": interp_idx.numpy(),
+           "xyz": xyz.numpy(), "neigh_idx": neigh_idx.numpy()}
+    out["random_sample"] = ns["random_sample"](feature, pool_idx).numpy()
+    out["nearest_interpolation"] = ns["nearest_interpolation"](feature, interp_idx).numpy()
+    out["relative_pos_encoding"] = ns["relative_pos_encoding"](_Block(), xyz, neigh_idx).numpy()
+    out["gather_neighbour"] = ns["gather_neighbour"](xyz, neigh_idx).numpy()
+    np.savez_compressed(os.path.join(HERE, "randla_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "needs the reference tree"
     assert ko.have_reference()
-    make_knn(); make_match(); make_dgcnn()
+    if len(sys.argv) > 1 and sys.argv[1] == "randla":        # add one fixture without regenerating the others
+        make_randla()
+    else:
+        make_knn(); make_match(); make_dgcnn(); make_randla()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -84,3 +84,38 @@ def test_gather_neighbour(cuda):
     out = pointops.gather_neighbour(pc.to(cuda), idx.to(cuda)).cpu()
     ref = torch.gather(pc, 1, idx.reshape(B, -1).unsqueeze(-1).repeat(1, 1, C)).reshape(B, N, K, C)
     assert torch.equal(out, ref)
+
+
+def test_randla_consumers_vs_golden_and_oracle(cuda):
+    """random_sample / nearest_interpolation / relative_pos_encoding (RandLANet.py:90-120, 720-727)
+    against the fixture produced by executing the reference's own function bodies, and against the oracle at a
+    larger ragged shape.  Gathers and maxima are exact; the distance is sqrt of an fp32 sum of squares whose
+    reduction order torch does not pin, so it gets 2 ulp."""
+    import os
+    from gadm_b200 import randla
+    from oracle import randla_oracle as ro
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "randla_golden.npz"))
+    t = lambda k: torch.from_numpy(z[k])
+    out = randla.random_sample(t("feature").to(cuda), t("pool_idx").to(cuda)).cpu()
+    assert torch.equal(out, t("random_sample"))
+    out = randla.nearest_interpolation(t("feature").to(cuda), t("interp_idx").to(cuda)).cpu()
+    assert torch.equal(out, t("nearest_interpolation"))
+    rpe = randla.relative_pos_encoding(t("xyz").to(cuda), t("neigh_idx").to(cuda)).cpu()
+    ref = t("relative_pos_encoding")
+    assert torch.equal(rpe[..., 1:], ref[..., 1:])
+    assert torch.allclose(rpe[..., 0], ref[..., 0], rtol=3e-7, atol=0)
+
+    g = torch.Generator().manual_seed(9)
+    B, C, N, M, K = 3, 37, 1000, 333, 16
+    feat = torch.randn((B, C, N, 1), generator=g)
+    pool = torch.randint(0, N, (B, M, K), generator=g)
+    assert torch.equal(randla.random_sample(feat.to(cuda), pool.to(cuda)).cpu(), ro.random_sample(feat, pool))
+    up = torch.randint(0, N, (B, 2500, 1), generator=g)
+    assert torch.equal(randla.nearest_interpolation(feat.to(cuda), up.to(cuda)).cpu(),
+                       ro.nearest_interpolation(feat, up))
+    pool20 = torch.randint(0, N, (B, M, 20), generator=g)          # k > 16 path
+    assert torch.equal(randla.random_sample(feat.to(cuda), pool20.to(cuda)).cpu(), ro.random_sample(feat, pool20))
+    xyz = torch.rand((B, N, 3), generator=g)
+    nei = torch.randint(0, N, (B, N, K), generator=g)
+    got, want = randla.relative_pos_encoding(xyz.to(cuda), nei.to(cuda)).cpu(), ro.relative_pos_encoding(xyz, nei)
+    assert torch.equal(got[..., 1:], want[..., 1:]) and torch.allclose(got[..., 0], want[..., 0], rtol=3e-7, atol=0)

@@ -146,3 +146,14 @@ def test_pointops_oracle_semantics():
     f2 = f.clone().requires_grad_(True)
     po.grouping(f2, idx).backward(go)
     assert torch.allclose(gf, f2.grad)
+
+
+def test_randla_oracle_vs_reference_source():
+    """oracle/randla_oracle.py against the outputs of the reference's own function bodies (randla_golden.npz)."""
+    from oracle import randla_oracle as ro
+    z = np.load(os.path.join(G, "randla_golden.npz"))
+    t = lambda k: torch.from_numpy(z[k])
+    assert torch.equal(ro.random_sample(t("feature"), t("pool_idx")), t("random_sample"))
+    assert torch.equal(ro.nearest_interpolation(t("feature"), t("interp_idx")), t("nearest_interpolation"))
+    assert torch.equal(ro.gather_neighbour(t("xyz"), t("neigh_idx")), t("gather_neighbour"))
+    assert torch.equal(ro.relative_pos_encoding(t("xyz"), t("neigh_idx")), t("relative_pos_encoding"))

@@ -115,6 +115,104 @@ __global__ void __launch_bounds__(576, 1) probe(long long* out, float* sink_out,
   if (threadIdx.x < 32) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_slot, 512); }
 }
 
+// Paired rows: every thread owns the same lane of TWO row tiles; one broadcast LDS.128 of a per-column constant now
+// serves 2 x 4 scores.  W = columns per step (32 or 16).
+template <int SOFT, int W>
+__global__ void __launch_bounds__(576, 1) probe_pair(long long* out, float* sink_out, int iters, float g, float mref) {
+  __shared__ __align__(16) float aux[4 * 256];
+  __shared__ __align__(16) float stash[2 * 512 * 8];
+  __shared__ uint32_t tmem_slot;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) aux[i] = 1.0f + (i & 255) * 1e-3f;
+  if (threadIdx.x < 32) { ptx::tmem_alloc(&tmem_slot, 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (threadIdx.x >= 512) return;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t tbase = tmem_slot + (uint32_t((warp & 3) * 32) << 16) + (warp >> 2) * 32;
+  const uint32_t sc0 = ptx::smem_u32(aux) + ((warp >> 2) * 32) * 4;
+  const uint32_t stash_addr = ptx::smem_u32(stash) + threadIdx.x * 16;
+  float vmax[2] = {-1e30f, -1e30f}; int vgrp[2] = {0, 0};
+  uint64_t l2[2] = {0, 0}, ax2[2] = {0, 0}, ay2[2] = {0, 0}, az2[2] = {0, 0};
+  constexpr int NCH = 32 / W;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; it += 2) {      // one step = 2 rows x 32 columns = 64 scores per thread (as above)
+    const uint32_t s_tmem = tbase + (it & 2) * 128;
+    const uint32_t sc = ptx::opaque(sc0);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      uint32_t r0[W], r1[W];
+      if (W == 32) { ptx::tmem_ld_32x32(s_tmem, reinterpret_cast<uint32_t(&)[32]>(r0)); ptx::tmem_ld_32x32(s_tmem + 128, reinterpret_cast<uint32_t(&)[32]>(r1)); }
+      else { ptx::tmem_ld_32x16(s_tmem + c * 16, reinterpret_cast<uint32_t(&)[16]>(r0)); ptx::tmem_ld_32x16(s_tmem + 128 + c * 16, reinterpret_cast<uint32_t(&)[16]>(r1)); }
+      ptx::tmem_ld_wait();
+      uint64_t v0[W / 2], v1[W / 2];
+#pragma unroll
+      for (int j4 = 0; j4 < W / 4; ++j4) {
+        const float4 cm = ptx::lds128(sc + c * W * 4 + j4 * 16);
+        const uint64_t c01 = ptx::pack2f(cm.x, cm.y), c23 = ptx::pack2f(cm.z, cm.w);
+        v0[j4 * 2 + 0] = ptx::fmul2(ptx::pack2(r0[j4 * 4 + 0], r0[j4 * 4 + 1]), c01);
+        v0[j4 * 2 + 1] = ptx::fmul2(ptx::pack2(r0[j4 * 4 + 2], r0[j4 * 4 + 3]), c23);
+        v1[j4 * 2 + 0] = ptx::fmul2(ptx::pack2(r1[j4 * 4 + 0], r1[j4 * 4 + 1]), c01);
+        v1[j4 * 2 + 1] = ptx::fmul2(ptx::pack2(r1[j4 * 4 + 2], r1[j4 * 4 + 3]), c23);
+      }
+      float cmx[2] = {-1e30f, -1e30f};
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        uint64_t* v = rr ? v1 : v0;
+#pragma unroll
+        for (int h = 0; h < W / 8; ++h) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ptx::unpack2f(v[h * 4 + j], f[2 * j], f[2 * j + 1]);
+          const float a0 = ptx::fmax3(f[0], f[1], f[2]), a1 = ptx::fmax3(f[3], f[4], f[5]);
+          const float gm = ptx::fmax3(a0, a1, fmaxf(f[6], f[7]));
+          const bool up = gm > vmax[rr];
+          ptx::sts_stash8(up, stash_addr + rr * 16384, v[h * 4 + 0], v[h * 4 + 1], v[h * 4 + 2], v[h * 4 + 3]);
+          vgrp[rr] = up ? it * 32 + h * 8 : vgrp[rr];
+          vmax[rr] = up ? gm : vmax[rr];
+          cmx[rr] = fmaxf(cmx[rr], gm);
+        }
+      }
+      if (SOFT) {
+        const float m0 = mref + cmx[0] * 1e-9f, m1 = mref + cmx[1] * 1e-9f;
+        const uint64_t g2 = ptx::pack2f(g, g), nm0 = ptx::pack2f(-m0, -m0), nm1 = ptx::pack2f(-m1, -m1);
+#pragma unroll
+        for (int j4 = 0; j4 < W / 4; ++j4) {
+          const uint32_t a = sc + c * W * 4 + j4 * 16;
+          const float4 X = ptx::lds128(a + 1024), Y = ptx::lds128(a + 2048), Z = ptx::lds128(a + 3072);
+          const uint64_t X01 = ptx::pack2f(X.x, X.y), X23 = ptx::pack2f(X.z, X.w), Y01 = ptx::pack2f(Y.x, Y.y),
+                         Y23 = ptx::pack2f(Y.z, Y.w), Z01 = ptx::pack2f(Z.x, Z.y), Z23 = ptx::pack2f(Z.z, Z.w);
+          const uint64_t p0a = ptx::ex2_2(ptx::ffma2(v0[j4 * 2 + 0], g2, nm0)), p0b = ptx::ex2_2(ptx::ffma2(v0[j4 * 2 + 1], g2, nm0));
+          const uint64_t p1a = ptx::ex2_2(ptx::ffma2(v1[j4 * 2 + 0], g2, nm1)), p1b = ptx::ex2_2(ptx::ffma2(v1[j4 * 2 + 1], g2, nm1));
+          l2[0] = ptx::fadd2(l2[0], ptx::fadd2(p0a, p0b)); l2[1] = ptx::fadd2(l2[1], ptx::fadd2(p1a, p1b));
+          ax2[0] = ptx::ffma2(p0b, X23, ptx::ffma2(p0a, X01, ax2[0])); ax2[1] = ptx::ffma2(p1b, X23, ptx::ffma2(p1a, X01, ax2[1]));
+          ay2[0] = ptx::ffma2(p0b, Y23, ptx::ffma2(p0a, Y01, ay2[0])); ay2[1] = ptx::ffma2(p1b, Y23, ptx::ffma2(p1a, Y01, ay2[1]));
+          az2[0] = ptx::ffma2(p0b, Z23, ptx::ffma2(p0a, Z01, az2[0])); az2[1] = ptx::ffma2(p1b, Z23, ptx::ffma2(p1a, Z01, az2[1]));
+        }
+      }
+    }
+  }
+  const long long t1 = clock64();
+  float e, o;
+  ptx::unpack2f(ptx::fadd2(ptx::fadd2(l2[0], l2[1]), ptx::fadd2(ptx::fadd2(ax2[0], ax2[1]), ptx::fadd2(ptx::fadd2(ay2[0], ay2[1]), ptx::fadd2(az2[0], az2[1])))), e, o);
+  sink_out[blockIdx.x * 512 + threadIdx.x] = e + o + vmax[0] + vmax[1] + float(vgrp[0] + vgrp[1]);
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+  ptx::tc_fence_before();
+  asm volatile("bar.sync 1, 512;" ::: "memory");
+  if (threadIdx.x < 32) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_slot, 512); }
+}
+
+template <int SOFT, int W>
+void run_pair(long long* out, float* sink, const char* name) {
+  const int iters = 4000;
+  for (int rep = 0; rep < 2; ++rep) {
+    probe_pair<SOFT, W><<<148, 576>>>(out, sink, iters, 0.7f, 0.1f);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); exit(1); }
+  }
+  printf("%-64s %7.1f cycles per 128 x 256 scores (16 warps)\n", name, 2.0 * double(out[0]) / iters);
+}
+
 template <int SOFT, int FREE, int EARLY, int BOTH>
 void run(long long* out, float* sink, const char* name) {
   const int iters = 4000;
@@ -134,6 +232,10 @@ int main() {
   run<1, 1, 0, 0>(out, sink, "SOFT non-volatile LDS");
   run<1, 1, 1, 0>(out, sink, "SOFT non-volatile LDS, scales before the ld wait");
   run<1, 1, 1, 1>(out, sink, "SOFT non-volatile LDS, scales early, both chunks per wait");
+  run_pair<1, 32>(out, sink, "SOFT paired rows (2 rows per thread), 32 columns per step");
+  run_pair<1, 16>(out, sink, "SOFT paired rows, 16 columns per step");
+  run_pair<0, 32>(out, sink, "ARGMAX paired rows, 32 columns per step");
+  run_pair<0, 16>(out, sink, "ARGMAX paired rows, 16 columns per step");
   run<0, 0, 0, 1>(out, sink, "ARGMAX as shipped (volatile LDS, both chunks per wait)");
   run<0, 1, 0, 1>(out, sink, "ARGMAX non-volatile LDS");
   run<0, 1, 1, 1>(out, sink, "ARGMAX non-volatile LDS, scales before the ld wait");

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out, int reps) {
       const long long t0 = clock64();
       for (int r = 0; r < reps; ++r) {
         const uint32_t d_big = tm + (r & 1) * 0;   // same accumulator: dependent chain like the real kernel's k loop
-        if (variant == 0 || variant >= 4) {
+        if (variant == 0 || (variant >= 4 && variant < 10)) {
           for (int k = 0; k < 8; ++k)
             ptx::umma_bf16_ss(d_big, ptx::umma_desc_sw128_kmajor(a_addr + (k & 3) * 32),
                               ptx::umma_desc_sw128_kmajor(b_addr + (k & 3) * 32), id_big, k != 0);
@@ -68,6 +68,14 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out, int reps) {
         if (variant == 8)                          // 4 x TS N = 8 only (per-instruction latency vs throughput)
           for (int k = 0; k < 4; ++k)
             ptx::umma_f16_ts(tm + 480, tm + 256 + k * 8, ptx::umma_desc_sw128_kmajor(v_addr + (k & 3) * 32), id_n8, k != 0);
+        if (variant == 10 || variant == 11) {      // paired-row tile: 2 row tiles x 8 k-steps of 128x128x16
+          const uint32_t id_128 = ptx::umma_idesc_f16_f32(128, 128);
+          for (int k = 0; k < 8; ++k)
+            for (int rt = 0; rt < 2; ++rt)
+              ptx::umma_bf16_ss(tm + rt * 128, ptx::umma_desc_sw128_kmajor(a_addr + rt * 16384 + (k & 3) * 32),
+                                ptx::umma_desc_sw128_kmajor(b_addr + (k & 3) * 32), id_128, k != 0);
+          continue;
+        }
         if (variant == 9)                          // 16 x TS N = 8, independent accumulators (no D dependency)
           for (int k = 0; k < 16; ++k)
             ptx::umma_f16_ts(tm + 384 + k * 8, tm + 256 + k * 8, ptx::umma_desc_sw128_kmajor(v_addr + (k & 3) * 32), id_n8, 0);
@@ -77,7 +85,7 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out, int reps) {
       phase ^= 1;
       return clock64() - t0;
     };
-    for (int v = 0; v < 10; ++v) {
+    for (int v = 0; v < 12; ++v) {
       run(v);                                      // warm
       const long long c = run(v);
       if (blockIdx.x == 0) out[v] = c;
@@ -96,7 +104,7 @@ int main() {
   probe<<<148, 128, 100 * 1024>>>(out, reps);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
-  const char* names[10] = {"8 x SS 128x256x16 (one similarity tile, K=128)",
+  const char* names[12] = {"8 x SS 128x256x16 (one similarity tile, K=128)",
                            "16 x TS 128x8x16",
                            "16 x TS 128x16x16",
                            "16 x SS 128x8x16",
@@ -105,7 +113,9 @@ int main() {
                            "tile + 16 x SS N=8",
                            "16 x TS 128x32x16",
                            "4 x TS 128x8x16",
-                           "16 x TS 128x8x16 independent accumulators"};
-  for (int v = 0; v < 10; ++v) printf("%-48s %8.1f cycles per repetition\n", names[v], double(out[v]) / reps);
+                           "16 x TS 128x8x16 independent accumulators",
+                           "16 x SS 128x128x16 (two row tiles x K=128, B shared)",
+                           "16 x SS 128x128x16 (repeat)"};
+  for (int v = 0; v < 12; ++v) printf("%-48s %8.1f cycles per repetition\n", names[v], double(out[v]) / reps);
   return 0;
 }
