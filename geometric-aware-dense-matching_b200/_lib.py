@@ -48,6 +48,7 @@ SIGNATURES = {
     "gadm_gather_neighbour": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gadm_gather_max": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gadm_relative_pos_encoding": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "gadm_seg_mask": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
 }
 
 PAD_MODES = {"none": 0, "minus_one": 1, "e0": 2}

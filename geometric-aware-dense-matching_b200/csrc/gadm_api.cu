@@ -246,4 +246,10 @@ int gadm_relative_pos_encoding(const float* xyz, const int64_t* idx, int B, int 
   return relative_pos_encoding_launch(xyz, idx, B, N, K, out, static_cast<cudaStream_t>(stream));
 }
 
+int gadm_seg_mask(const float* seg, int B, int N, uint8_t* mask, gadm_stream_t stream) {
+  GADM_REQUIRE_INIT();
+  if (!seg || !mask || B <= 0 || N <= 0) return GADM_ERR_BAD_ARG;
+  return seg_mask_launch(seg, B, N, mask, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

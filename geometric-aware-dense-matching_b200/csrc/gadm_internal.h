@@ -40,6 +40,7 @@ int prep_rows_launch(const float* feat, int B, int d, int N, int operand_mode, i
                      float* pad_sim, cudaStream_t stream);
 int prep_model_launch(const float* mesh, const float* model_xyz, int n_obj, int d, int M, int operand_mode, void* cols,
                       float* aux, cudaStream_t stream);
+int seg_mask_launch(const float* seg, int B, int N, uint8_t* mask, cudaStream_t stream);
 int kabsch_moments_launch(const int64_t* idx, const uint8_t* mask, const float* cloud, const float* aux,
                           const int32_t* obj_id, int B, int N, int M, int n_obj, double* out, cudaStream_t stream);
 

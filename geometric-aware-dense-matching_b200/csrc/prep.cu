@@ -97,6 +97,16 @@ prep_kernel(const float* __restrict__ src, const float* __restrict__ xyz, int d,
   }
 }
 
+// evaluator.py:78,82 in one pass: mask = (argmax over the two seg channels == 1)
+__global__ void __launch_bounds__(256)
+seg_mask_kernel(const float* __restrict__ seg, int N, uint8_t* __restrict__ mask) {
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* s = seg + size_t(b) * 2 * N;
+  mask[size_t(b) * N + n] = s[N + n] > s[n] ? 1 : 0;
+}
+
 // One CTA per frame: fp64 accumulation of n, sum A, sum B, sum A B^T over matched rows.
 __global__ void __launch_bounds__(256)
 kabsch_moments_kernel(const int64_t* __restrict__ idx, const uint8_t* __restrict__ mask,
@@ -161,6 +171,12 @@ int prep_model_launch(const float* mesh, const float* model_xyz, int n_obj, int 
   float* a_planes = aux + plane * 4;
   prep_kernel<1><<<grid, 256, smem, stream>>>(mesh, model_xyz, d, M, operand_mode == GADM_OPERAND_BF16X3, 0,
                                               static_cast<__nv_bfloat16*>(cols), nullptr, nullptr, aux, a_xyz, a_planes, plane);
+  return check_launch();
+}
+
+int seg_mask_launch(const float* seg, int B, int N, uint8_t* mask, cudaStream_t stream) {
+  if (B > 65535) return GADM_ERR_UNSUPPORTED;
+  seg_mask_kernel<<<dim3((N + 255) / 256, B), 256, 0, stream>>>(seg, N, mask);
   return check_launch();
 }
 

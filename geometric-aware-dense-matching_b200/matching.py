@@ -99,11 +99,11 @@ def frame_poses(cld, seg, rgbd, bank, obj_id=None, det=None, min_pts=5):
     One matcher launch + one moment launch + ONE device->host copy for the whole batch (the reference
     syncs per frame at evaluator.py:83, :87, :99)."""
     B, _, N = rgbd.shape
-    mask = (torch.argmax(seg, dim=1) == 1)                                   # evaluator.py:78,82
+    mask = ops.seg_mask(seg.contiguous().float())                            # evaluator.py:78,82 (uint8 [B, N])
     idx, _, _, _ = match(rgbd, bank, obj_id=obj_id, mask=mask, mode="argmax", operand_mode=bank.operand_mode)
     cloud = cld[:, :3, :].transpose(1, 2).contiguous().float()               # evaluator.py:85
     oid = None if obj_id is None else torch.as_tensor(obj_id, device=rgbd.device).to(torch.int32)
-    mom = ops.kabsch_moments(idx, mask.to(torch.uint8), cloud, bank.aux, oid, bank.M, bank.n_obj).cpu().numpy()
+    mom = ops.kabsch_moments(idx, mask, cloud, bank.aux, oid, bank.M, bank.n_obj).cpu().numpy()
     poses = []
     for b in range(B):
         n_sel = mom[b, 0]
@@ -162,7 +162,7 @@ class GeoMatch(nn.Module):
         end_points['rgbd'] = rgbd_features
         if self.match_in_forward and not self.training:
             xyz = self.xyz if self.xyz is not None else None
-            mask = torch.argmax(seg_features, dim=1) == 1
+            mask = ops.seg_mask(seg_features.detach().contiguous().float())
             idx, sim, w, sxyz = match(rgbd_features.detach(), mesh_features.detach(), xyz, mask=mask,
                                       gamma=self.gamma, operand_mode=self.operand_mode)
             end_points.update(match_idx=idx, match_sim=sim, match_weight=w, match_xyz=sxyz)

@@ -327,3 +327,22 @@ def relative_pos_encoding(xyz: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 @relative_pos_encoding.register_fake
 def _(xyz, idx):
     return xyz.new_empty((xyz.shape[0], xyz.shape[1], idx.shape[2], 10))
+
+
+@torch.library.custom_op("gadm::seg_mask", mutates_args=(), device_types="cuda")
+def seg_mask(seg: torch.Tensor) -> torch.Tensor:
+    """seg [B, 2, N] fp32 -> uint8 [B, N] = (argmax over dim 1 == 1)   (evaluator.py:78,82)."""
+    _need(seg, torch.float32, "seg")
+    B, two, N = seg.shape
+    if two != 2:
+        raise ValueError("seg must be [B, 2, N]")
+    out = torch.empty((B, N), dtype=torch.uint8, device=seg.device)
+    lib = _lib_for(seg)
+    with torch.cuda.device(seg.device):
+        _lib.check(lib.gadm_seg_mask(_ptr(seg), B, N, _ptr(out), _stream()), "gadm_seg_mask")
+    return out
+
+
+@seg_mask.register_fake
+def _(seg):
+    return seg.new_empty((seg.shape[0], seg.shape[2]), dtype=torch.uint8)

@@ -102,6 +102,11 @@ int gadm_match_fwd(const void* rows, const float* rinv_rows, const float* pad_si
                    int n_obj, float gamma, int pad_mode, int mode, int64_t* idx, float* max_sim, float* weight,
                    float* soft_xyz, gadm_stream_t stream);
 
+/* Foreground mask of the matcher (evaluator.py:78,82: `seg_res = argmax(seg_features, dim=0); cls_msk = seg_res == 1`)
+ * without the argmax tensor: seg [B, 2, N] fp32 -> mask [B, N] uint8 = seg[b,1,n] > seg[b,0,n]  (torch.argmax returns
+ * the first maximal index, so a tie is background). */
+int gadm_seg_mask(const float* seg, int B, int N, uint8_t* mask, gadm_stream_t stream);
+
 /* Moments for the least-squares pose fit that follows the matcher (best_fit_transform): per frame, over rows
  * with idx in [0, M) (and mask != 0):  n, sum A, sum B, sum A B^T  with A = model xyz[idx], B = cloud point.
  *   cloud [B, N, 3] fp32; out [B, 16] fp64 = {n, sA[3], sB[3], sAB[9]}  (zeroed by the callee)           */

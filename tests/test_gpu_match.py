@@ -172,3 +172,15 @@ def test_frame_poses_recovers_pose(cuda):
     # early-outs: not detected -> sentinel pose (evaluator.py:69-73)
     RT0 = matching.cal_frame_poses((cld.to(cuda), seg.to(cuda), None, rgbd[0].to(cuda), 0, False), bank)
     assert RT0[2, 3] == -1000
+
+
+def test_seg_mask_matches_torch_argmax(cuda):
+    """the foreground mask of evaluator.py:78,82 in one kernel (ties -> background, as torch.argmax
+    returns the first maximal index)."""
+    from gadm_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    seg = torch.randn((3, 2, 1001), generator=g)
+    seg[:, 1, ::7] = seg[:, 0, ::7]                       # exact ties
+    got = ops.seg_mask(seg.to(cuda)).cpu()
+    assert got.dtype == torch.uint8 and got.shape == (3, 1001)
+    assert torch.equal(got.bool(), torch.argmax(seg, dim=1) == 1)
