@@ -7,11 +7,11 @@ from gadm_b200 import ops, synth
 from gadm_b200._lib import MATCH_MODES
 
 dev = torch.device("cuda", 0)
-B, N, M, D = 8, 12800, 8192, int(os.environ.get("D", "128"))
+B, N, M, D = int(os.environ.get("B", "8")), int(os.environ.get("N", "12800")), 8192, int(os.environ.get("D", "128"))
 regime = os.environ.get("REGIME", "planted")
 rgbd, mesh, _ = synth.descriptors(B, N, M, D, n_obj=8, regime=regime, seed=2000)
 xyz = synth.model_bank_xyz(8, M).to(dev)
-obj = torch.arange(B, dtype=torch.int32, device=dev)
+obj = torch.arange(B, dtype=torch.int32, device=dev) % 8
 cols, aux = ops.prep_model(mesh.to(dev), xyz, 0)
 rows, rinv, pad = ops.prep_rows(rgbd.to(dev), 0, 0)
 flop = 2.0 * N * M * D * B
@@ -25,4 +25,4 @@ for mode in ("argmax", "soft"):
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 20
-    print(f"{mode} d={D} {regime} dbg={os.environ.get('GADM_MATCH_DBG','0')}: {ms:.4f} ms  {flop/ms/1e9:.1f} TFLOP/s  frac {flop/ms/1e9/1658.8:.3f}", flush=True)
+    print(f"{mode} B={B} N={N} d={D} {regime} dbg={os.environ.get('GADM_MATCH_DBG','0')}: {ms:.4f} ms  {flop/ms/1e9:.1f} TFLOP/s  frac {flop/ms/1e9/1658.8:.3f}", flush=True)

@@ -10,7 +10,7 @@ using namespace gadm;
 
 // SOFT: 1 = soft, 0 = argmax.  FREE: non-volatile LDS.  EARLY: scale LDS issued before the tcgen05.ld wait.
 // BOTH: two chunks requested per wait (argmax style).  NOSTASHCLOB: stash stores without a "memory" clobber.
-template <int SOFT, int FREE, int EARLY, int BOTH>
+template <int SOFT, int FREE, int EARLY, int BOTH, int ABL = 0>
 __global__ void __launch_bounds__(576, 1) probe(long long* out, float* sink_out, int iters, float g, float mref) {
   __shared__ __align__(16) float aux[4 * 256];
   __shared__ __align__(16) float stash[512 * 8];
@@ -20,6 +20,29 @@ __global__ void __launch_bounds__(576, 1) probe(long long* out, float* sink_out,
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  extern __shared__ uint8_t dyn_raw[];
+  __shared__ volatile int stop_flag;
+  __shared__ uint64_t mbar;
+  if (ABL & 32) {
+    if (threadIdx.x == 0) { stop_flag = 0; ptx::mbar_init(&mbar, 1); ptx::fence_mbar_init(); }
+    uint8_t* dyn = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn_raw) + 1023) & ~uintptr_t(1023));
+    for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(dyn)[i] = 0x3c003c00u;
+    ptx::fence_proxy_async();
+    asm volatile("bar.sync 2, 576;" ::: "memory");
+    if (threadIdx.x == 544) {            // warp 17, lane 0: the UMMA issuer of the real kernel
+      const uint32_t a_addr = ptx::smem_u32(dyn), b_addr = ptx::smem_u32(dyn + 16 * 1024);
+      const uint32_t idesc = ptx::umma_idesc_f16_f32(128, 256);
+      uint32_t ph = 0; long long n = 0;
+      while (!stop_flag) {
+        for (int k = 0; k < 8; ++k)       // accumulate into columns 0..255 of lanes the probe does not read back
+          ptx::umma_bf16_ss(tmem_slot + 256 * ((n & 1) ^ 1) * 0 + 0, ptx::umma_desc_sw128_kmajor(a_addr + (k & 3) * 32),
+                            ptx::umma_desc_sw128_kmajor(b_addr + (k & 3) * 32), idesc, 1);
+        ptx::umma_commit(&mbar);
+        ptx::mbar_wait_sleep(&mbar, ph); ph ^= 1; ++n;
+      }
+      if (blockIdx.x == 0) out[2] = n;
+    }
+  }
   if (threadIdx.x >= 512) return;
   const int warp = threadIdx.x >> 5;
   const uint32_t tbase = tmem_slot + (uint32_t((warp & 3) * 32) << 16) + (warp >> 2) * 64;
@@ -45,7 +68,7 @@ __global__ void __launch_bounds__(576, 1) probe(long long* out, float* sink_out,
       const float a0 = ptx::fmax3(f[0], f[1], f[2]), a1 = ptx::fmax3(f[3], f[4], f[5]);
       const float gm = ptx::fmax3(a0, a1, fmaxf(f[6], f[7]));
       const bool up = gm > vmax;
-      ptx::sts_stash8(up, stash_addr, v[h * 4 + 0], v[h * 4 + 1], v[h * 4 + 2], v[h * 4 + 3]);
+      if (!(ABL & 8)) ptx::sts_stash8(up, stash_addr, v[h * 4 + 0], v[h * 4 + 1], v[h * 4 + 2], v[h * 4 + 3]);
       vgrp = up ? it * 32 + h * 8 : vgrp;
       vmax = up ? gm : vmax;
       cmx = fmaxf(cmx, gm);
@@ -55,13 +78,17 @@ __global__ void __launch_bounds__(576, 1) probe(long long* out, float* sink_out,
       const uint64_t g2 = ptx::pack2f(g, g), nm2 = ptx::pack2f(-m, -m);
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 X = lds(sc + 1024 + j4 * 16), Y = lds(sc + 2048 + j4 * 16), Z = lds(sc + 3072 + j4 * 16);
-        const uint64_t p01 = ptx::ex2_2(ptx::ffma2(v[j4 * 2 + 0], g2, nm2));
-        const uint64_t p23 = ptx::ex2_2(ptx::ffma2(v[j4 * 2 + 1], g2, nm2));
+        float4 X, Y, Z;
+        if (ABL & 1) { X = make_float4(g, m, g, m); Y = make_float4(m, g, m, g); Z = make_float4(g, g, m, m); }
+        else { X = lds(sc + 1024 + j4 * 16); Y = lds(sc + 2048 + j4 * 16); Z = lds(sc + 3072 + j4 * 16); }
+        uint64_t p01 = ptx::ffma2(v[j4 * 2 + 0], g2, nm2), p23 = ptx::ffma2(v[j4 * 2 + 1], g2, nm2);
+        if (!(ABL & 4)) { p01 = ptx::ex2_2(p01); p23 = ptx::ex2_2(p23); }
         l2a = ptx::fadd2(l2a, p01); l2b = ptx::fadd2(l2b, p23);
+        if (!(ABL & 2)) {
         ax2a = ptx::ffma2(p01, ptx::pack2f(X.x, X.y), ax2a); ax2b = ptx::ffma2(p23, ptx::pack2f(X.z, X.w), ax2b);
         ay2a = ptx::ffma2(p01, ptx::pack2f(Y.x, Y.y), ay2a); ay2b = ptx::ffma2(p23, ptx::pack2f(Y.z, Y.w), ay2b);
         az2a = ptx::ffma2(p01, ptx::pack2f(Z.x, Z.y), az2a); az2b = ptx::ffma2(p23, ptx::pack2f(Z.z, Z.w), az2b);
+        }
       }
     }
   };
@@ -85,7 +112,7 @@ __global__ void __launch_bounds__(576, 1) probe(long long* out, float* sink_out,
     ptx::tmem_ld_wait();
     if (!EARLY) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ca[j] = lds(sc + j * 16);
+      for (int j = 0; j < 8; ++j) ca[j] = (ABL & 16) ? make_float4(g, g, g, g) : lds(sc + j * 16);
     }
     process(ra, ca, sc, it);
     if (!BOTH) {
@@ -99,7 +126,7 @@ __global__ void __launch_bounds__(576, 1) probe(long long* out, float* sink_out,
     if (!EARLY || (false)) {
       if (!EARLY) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) cb[j] = lds(sc + 128 + j * 16);
+        for (int j = 0; j < 8; ++j) cb[j] = (ABL & 16) ? make_float4(g, g, g, g) : lds(sc + 128 + j * 16);
       }
     }
     process(rb, cb, sc + 128, it + 1);
@@ -112,6 +139,11 @@ __global__ void __launch_bounds__(576, 1) probe(long long* out, float* sink_out,
   if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
   ptx::tc_fence_before();
   asm volatile("bar.sync 1, 512;" ::: "memory");
+  if (ABL & 32) {
+    if (threadIdx.x == 0) stop_flag = 1;
+    // give the issuer time to see the flag and drain before TMEM goes away
+    __nanosleep(20000);
+  }
   if (threadIdx.x < 32) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_slot, 512); }
 }
 
@@ -213,11 +245,12 @@ void run_pair(long long* out, float* sink, const char* name) {
   printf("%-64s %7.1f cycles per 128 x 256 scores (16 warps)\n", name, 2.0 * double(out[0]) / iters);
 }
 
-template <int SOFT, int FREE, int EARLY, int BOTH>
+template <int SOFT, int FREE, int EARLY, int BOTH, int ABL = 0>
 void run(long long* out, float* sink, const char* name) {
   const int iters = 4000;
+  if (ABL & 32) cudaFuncSetAttribute(probe<SOFT, FREE, EARLY, BOTH, ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 50 * 1024);
   for (int rep = 0; rep < 2; ++rep) {
-    probe<SOFT, FREE, EARLY, BOTH><<<148, 576>>>(out, sink, iters, 0.7f, 0.1f);
+    probe<SOFT, FREE, EARLY, BOTH, ABL><<<148, 576, (ABL & 32) ? 50 * 1024 : 0>>>(out, sink, iters, 0.7f, 0.1f);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); exit(1); }
   }
@@ -229,6 +262,18 @@ int main() {
   cudaMallocManaged(&out, 64);
   cudaMalloc(&sink, 148 * 512 * 4);
   run<1, 0, 0, 0>(out, sink, "SOFT as shipped (volatile LDS, one chunk per wait)");
+  run<1, 0, 0, 0, 1>(out, sink, "SOFT, xyz constants from registers (no plane LDS)");
+  run<1, 0, 0, 0, 2>(out, sink, "SOFT, no p * xyz sums at all");
+  run<1, 0, 0, 0, 4>(out, sink, "SOFT, no MUFU");
+  run<1, 0, 0, 0, 8>(out, sink, "SOFT, no stash stores");
+  run<1, 0, 0, 0, 16>(out, sink, "SOFT, no scale LDS");
+  run<1, 0, 0, 0, 1 + 16>(out, sink, "SOFT, no LDS at all");
+  run<1, 0, 0, 0, 1 + 8 + 16>(out, sink, "SOFT, no LDS, no stash");
+  run<1, 0, 0, 0, 1 + 4 + 8 + 16>(out, sink, "SOFT, no LDS, no stash, no MUFU");
+  run<1, 0, 0, 0, 32>(out, sink, "SOFT as shipped + a UMMA issuer streaming 128x256x16 MMAs from smem");
+  printf("      (MMA tiles issued meanwhile: %lld)\n", out[2]);
+  run<0, 0, 0, 1, 32>(out, sink, "ARGMAX as shipped + the UMMA issuer");
+  printf("      (MMA tiles issued meanwhile: %lld)\n", out[2]);
   run<1, 1, 0, 0>(out, sink, "SOFT non-volatile LDS");
   run<1, 1, 1, 0>(out, sink, "SOFT non-volatile LDS, scales before the ld wait");
   run<1, 1, 1, 1>(out, sink, "SOFT non-volatile LDS, scales early, both chunks per wait");
