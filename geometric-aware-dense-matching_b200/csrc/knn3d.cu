@@ -155,6 +155,27 @@ struct WarpSelect {
   }
 };
 
+// k == 1 (the 1-NN interpolation jobs: half of all queries of the pyramid): no lists, every lane keeps the best key
+// it has seen, one pair of warp reductions at the end of a phase.  Same interface as WarpSelect.
+struct WarpMin {
+  uint32_t ed[1];
+  int ei[1];
+  uint32_t kd;
+  int ki;
+  __device__ __forceinline__ void reset() { ed[0] = D_EMPTY; ei[0] = I_EMPTY; kd = D_EMPTY; ki = I_EMPTY; }
+  __device__ __forceinline__ void offer(float d, int i, bool valid, int, int) {
+    const uint32_t db = __float_as_uint(d);
+    if (valid && (db < ed[0] || (db == ed[0] && i < ei[0]))) { ed[0] = db; ei[0] = i; }
+  }
+  __device__ __forceinline__ void flush(int, int) {
+    const uint32_t dmin = __reduce_min_sync(0xffffffffu, ed[0]);
+    const uint32_t cand = ed[0] == dmin ? uint32_t(ei[0]) : uint32_t(I_EMPTY);
+    const uint32_t imin = __reduce_min_sync(0xffffffffu, cand);
+    kd = dmin; ki = int(imin);
+    ed[0] = dmin; ei[0] = int(imin);     // every lane now holds the winner (lane 0 writes it out)
+  }
+};
+
 __device__ __forceinline__ const JobDev& find_job(const LaunchJobs& L, int tile, int& item, int& qtile) {
   int j = 0;
   while (j + 1 < L.n_jobs && tile >= L.jobs[j + 1].tile_begin) ++j;
@@ -418,7 +439,8 @@ grid_scatter_kernel(const float* __restrict__ support, uint8_t* __restrict__ ws,
 // query's cell, phase r >= 1 the Chebyshev shell of radius r + 1.  Within a phase every lane owns one cell-row
 // range [rb, re) of the sorted point array; the ranges are FLATTENED (warp prefix sum + per-lane binary search
 // through shuffles) so that each offer carries 32 real candidates however short the individual ranges are.
-__device__ __forceinline__ void grid_offer_ranges(WarpSelect<GRID_E>& sel, const float4* __restrict__ pts, int rb,
+template <class Sel>
+__device__ __forceinline__ void grid_offer_ranges(Sel& sel, const float4* __restrict__ pts, int rb,
                                                   int re, float qx, float qy, float qz, int k, int lane) {
   const int len = re - rb;
   int incl = len;
@@ -448,6 +470,119 @@ __device__ __forceinline__ void grid_offer_ranges(WarpSelect<GRID_E>& sel, const
   }
 }
 
+// one query, one warp (see knn_grid_kernel)
+template <class Sel>
+__device__ __forceinline__ void grid_query(const JobDev& job, const GridHeader& g, const int* __restrict__ start,
+                                           const float4* __restrict__ pts, float qx, float qy, float qz, int k,
+                                           int lane, int32_t* __restrict__ idx, float* __restrict__ dist2,
+                                           long long o) {
+  const int cx = cell_coord(qx, g.ox, g.ihx, g.dx);
+  const int cy = cell_coord(qy, g.oy, g.ihy, g.dy);
+  const int cz = cell_coord(qz, g.oz, g.ihz, g.dz);
+  Sel sel;
+  sel.reset();
+  bool done = false;
+
+  if (k <= HALF_BLOCK_K) {
+    // Few neighbours wanted (the 1-NN interpolation jobs are half of all queries): look at the 2x2x2 block of
+    // cells nearest to the query first -- per axis the query's own cell and the neighbour on the side of the
+    // cell half the query lies in.  Every unvisited point is then at least half a cell away; with ~16 points
+    // per cell column that almost always proves the result, at 4/9 of the candidates of the 3x3x3 block.
+    const float fx = (qx - g.ox) * g.ihx - float(cx), fy = (qy - g.oy) * g.ihy - float(cy),
+                fz = (qz - g.oz) * g.ihz - float(cz);
+    const int x0 = max(fx < 0.5f ? cx - 1 : cx, 0), x1 = min(fx < 0.5f ? cx : cx + 1, g.dx - 1);
+    const int y0 = max(fy < 0.5f ? cy - 1 : cy, 0), y1 = min(fy < 0.5f ? cy : cy + 1, g.dy - 1);
+    const int z0 = max(fz < 0.5f ? cz - 1 : cz, 0), z1 = min(fz < 0.5f ? cz : cz + 1, g.dz - 1);
+    int rb = 0, re = 0;
+    if (lane < 4) {
+      const int z = z0 + (lane >> 1), y = y0 + (lane & 1);
+      if (z <= z1 && y <= y1) {
+        const int rowbase = (z * g.dy + y) * g.dx;
+        rb = start[rowbase + x0];
+        re = start[rowbase + x1 + 1];
+      }
+    }
+    grid_offer_ranges(sel, pts, rb, re, qx, qy, qz, k, lane);
+    sel.flush(k, lane);
+    float bound = FLT_MAX;
+    if (x0 > 0) bound = fminf(bound, qx - (g.ox + float(x0) * g.hx));
+    if (x1 < g.dx - 1) bound = fminf(bound, (g.ox + float(x1 + 1) * g.hx) - qx);
+    if (y0 > 0) bound = fminf(bound, qy - (g.oy + float(y0) * g.hy));
+    if (y1 < g.dy - 1) bound = fminf(bound, (g.oy + float(y1 + 1) * g.hy) - qy);
+    if (z0 > 0) bound = fminf(bound, qz - (g.oz + float(z0) * g.hz));
+    if (z1 < g.dz - 1) bound = fminf(bound, (g.oz + float(z1 + 1) * g.hz) - qz);
+    if (bound == FLT_MAX) {
+      done = true;
+    } else {
+      bound -= g.slack;
+      done = bound > 0.f && sel.kd != D_EMPTY && __uint_as_float(sel.kd) < bound * bound;
+    }
+    if (!done) sel.reset();   // the 3x3x3 block below contains these cells again
+  }
+
+  for (int rho = 1; rho <= R_MAX && !done; ++rho) {
+    // rho == 1: the whole 3x3x3 block, one range per (dz, dy) row.
+    // rho >= 2: the shell of radius rho: rows (dz, dy) in [-rho, rho]^2, two range slots per row
+    //           (rim rows: the full x span | nothing; inner rows: the cell at -rho | the cell at +rho).
+    const int side = 2 * rho + 1;
+    const int nslots = rho == 1 ? side * side : 2 * side * side;
+    for (int s0 = 0; s0 < nslots; s0 += 32) {
+      const int s = s0 + lane;
+      int rb = 0, re = 0;
+      if (s < nslots) {
+        const int row = rho == 1 ? s : s >> 1, second = rho == 1 ? 0 : s & 1;
+        const int dz = row / side - rho, dy = row % side - rho;
+        const int z = cz + dz, y = cy + dy;
+        if (z >= 0 && z < g.dz && y >= 0 && y < g.dy) {
+          const bool rim = rho == 1 || max(abs(dz), abs(dy)) == rho;
+          int x_lo, x_hi;
+          if (rim) { x_lo = cx - rho; x_hi = second ? x_lo - 1 : cx + rho; }
+          else     { x_lo = second ? cx + rho : cx - rho; x_hi = x_lo; }
+          x_lo = max(x_lo, 0); x_hi = min(x_hi, g.dx - 1);
+          if (x_lo <= x_hi) {
+            const int rowbase = (z * g.dy + y) * g.dx;
+            rb = start[rowbase + x_lo];
+            re = start[rowbase + x_hi + 1];
+          }
+        }
+      }
+      grid_offer_ranges(sel, pts, rb, re, qx, qy, qz, k, lane);
+    }
+    sel.flush(k, lane);
+    // distance from q to the nearest face of the visited block behind which unvisited cells exist
+    float bound = FLT_MAX;
+    if (cx - rho > 0) bound = fminf(bound, qx - (g.ox + float(cx - rho) * g.hx));
+    if (cx + rho < g.dx - 1) bound = fminf(bound, (g.ox + float(cx + rho + 1) * g.hx) - qx);
+    if (cy - rho > 0) bound = fminf(bound, qy - (g.oy + float(cy - rho) * g.hy));
+    if (cy + rho < g.dy - 1) bound = fminf(bound, (g.oy + float(cy + rho + 1) * g.hy) - qy);
+    if (cz - rho > 0) bound = fminf(bound, qz - (g.oz + float(cz - rho) * g.hz));
+    if (cz + rho < g.dz - 1) bound = fminf(bound, (g.oz + float(cz + rho + 1) * g.hz) - qz);
+    if (bound == FLT_MAX) {
+      done = true;  // the block covers the whole grid
+    } else {
+      bound -= g.slack;
+      // strict: an unvisited point at exactly the k-th distance could still win the index tie
+      done = bound > 0.f && sel.kd != D_EMPTY && __uint_as_float(sel.kd) < bound * bound;
+    }
+  }
+  if (!done) {  // pathological query (far outside / sparse region): scan the whole cloud
+    sel.reset();
+    for (int j0 = 0; j0 < job.n_support; j0 += 32) {
+      const int j = j0 + lane;
+      const bool valid = j < job.n_support;
+      const float4 p = pts[valid ? j : job.n_support - 1];
+      const float d = dist2_ref(qx, qy, qz, p.x, p.y, p.z);
+      sel.offer(d, __float_as_int(p.w), valid, k, lane);
+    }
+    sel.flush(k, lane);
+  }
+  if (lane < k) {
+    idx[o + lane] = sel.ei[0];
+    if (dist2) dist2[o + lane] = __uint_as_float(sel.ed[0]);
+  }
+}
+
+
 #ifndef GADM_KNN_MINB
 #define GADM_KNN_MINB 6
 #endif
@@ -470,110 +605,9 @@ knn_grid_kernel(const float* __restrict__ query, int32_t* __restrict__ idx, floa
     const int qi = qtile * QPB + warp * QPW + t;
     if (qi >= job.n_query) break;  // warp-uniform
     const float qx = Q[qi * 3 + 0], qy = Q[qi * 3 + 1], qz = Q[qi * 3 + 2];
-    const int cx = cell_coord(qx, g.ox, g.ihx, g.dx);
-    const int cy = cell_coord(qy, g.oy, g.ihy, g.dy);
-    const int cz = cell_coord(qz, g.oz, g.ihz, g.dz);
-    WarpSelect<GRID_E> sel;
-    sel.reset();
-    bool done = false;
-
-    if (k <= HALF_BLOCK_K) {
-      // Few neighbours wanted (the 1-NN interpolation jobs are half of all queries): look at the 2x2x2 block of
-      // cells nearest to the query first -- per axis the query's own cell and the neighbour on the side of the
-      // cell half the query lies in.  Every unvisited point is then at least half a cell away; with ~16 points
-      // per cell column that almost always proves the result, at 4/9 of the candidates of the 3x3x3 block.
-      const float fx = (qx - g.ox) * g.ihx - float(cx), fy = (qy - g.oy) * g.ihy - float(cy),
-                  fz = (qz - g.oz) * g.ihz - float(cz);
-      const int x0 = max(fx < 0.5f ? cx - 1 : cx, 0), x1 = min(fx < 0.5f ? cx : cx + 1, g.dx - 1);
-      const int y0 = max(fy < 0.5f ? cy - 1 : cy, 0), y1 = min(fy < 0.5f ? cy : cy + 1, g.dy - 1);
-      const int z0 = max(fz < 0.5f ? cz - 1 : cz, 0), z1 = min(fz < 0.5f ? cz : cz + 1, g.dz - 1);
-      int rb = 0, re = 0;
-      if (lane < 4) {
-        const int z = z0 + (lane >> 1), y = y0 + (lane & 1);
-        if (z <= z1 && y <= y1) {
-          const int rowbase = (z * g.dy + y) * g.dx;
-          rb = start[rowbase + x0];
-          re = start[rowbase + x1 + 1];
-        }
-      }
-      grid_offer_ranges(sel, pts, rb, re, qx, qy, qz, k, lane);
-      sel.flush(k, lane);
-      float bound = FLT_MAX;
-      if (x0 > 0) bound = fminf(bound, qx - (g.ox + float(x0) * g.hx));
-      if (x1 < g.dx - 1) bound = fminf(bound, (g.ox + float(x1 + 1) * g.hx) - qx);
-      if (y0 > 0) bound = fminf(bound, qy - (g.oy + float(y0) * g.hy));
-      if (y1 < g.dy - 1) bound = fminf(bound, (g.oy + float(y1 + 1) * g.hy) - qy);
-      if (z0 > 0) bound = fminf(bound, qz - (g.oz + float(z0) * g.hz));
-      if (z1 < g.dz - 1) bound = fminf(bound, (g.oz + float(z1 + 1) * g.hz) - qz);
-      if (bound == FLT_MAX) {
-        done = true;
-      } else {
-        bound -= g.slack;
-        done = bound > 0.f && sel.kd != D_EMPTY && __uint_as_float(sel.kd) < bound * bound;
-      }
-      if (!done) sel.reset();   // the 3x3x3 block below contains these cells again
-    }
-
-    for (int rho = 1; rho <= R_MAX && !done; ++rho) {
-      // rho == 1: the whole 3x3x3 block, one range per (dz, dy) row.
-      // rho >= 2: the shell of radius rho: rows (dz, dy) in [-rho, rho]^2, two range slots per row
-      //           (rim rows: the full x span | nothing; inner rows: the cell at -rho | the cell at +rho).
-      const int side = 2 * rho + 1;
-      const int nslots = rho == 1 ? side * side : 2 * side * side;
-      for (int s0 = 0; s0 < nslots; s0 += 32) {
-        const int s = s0 + lane;
-        int rb = 0, re = 0;
-        if (s < nslots) {
-          const int row = rho == 1 ? s : s >> 1, second = rho == 1 ? 0 : s & 1;
-          const int dz = row / side - rho, dy = row % side - rho;
-          const int z = cz + dz, y = cy + dy;
-          if (z >= 0 && z < g.dz && y >= 0 && y < g.dy) {
-            const bool rim = rho == 1 || max(abs(dz), abs(dy)) == rho;
-            int x_lo, x_hi;
-            if (rim) { x_lo = cx - rho; x_hi = second ? x_lo - 1 : cx + rho; }
-            else     { x_lo = second ? cx + rho : cx - rho; x_hi = x_lo; }
-            x_lo = max(x_lo, 0); x_hi = min(x_hi, g.dx - 1);
-            if (x_lo <= x_hi) {
-              const int rowbase = (z * g.dy + y) * g.dx;
-              rb = start[rowbase + x_lo];
-              re = start[rowbase + x_hi + 1];
-            }
-          }
-        }
-        grid_offer_ranges(sel, pts, rb, re, qx, qy, qz, k, lane);
-      }
-      sel.flush(k, lane);
-      // distance from q to the nearest face of the visited block behind which unvisited cells exist
-      float bound = FLT_MAX;
-      if (cx - rho > 0) bound = fminf(bound, qx - (g.ox + float(cx - rho) * g.hx));
-      if (cx + rho < g.dx - 1) bound = fminf(bound, (g.ox + float(cx + rho + 1) * g.hx) - qx);
-      if (cy - rho > 0) bound = fminf(bound, qy - (g.oy + float(cy - rho) * g.hy));
-      if (cy + rho < g.dy - 1) bound = fminf(bound, (g.oy + float(cy + rho + 1) * g.hy) - qy);
-      if (cz - rho > 0) bound = fminf(bound, qz - (g.oz + float(cz - rho) * g.hz));
-      if (cz + rho < g.dz - 1) bound = fminf(bound, (g.oz + float(cz + rho + 1) * g.hz) - qz);
-      if (bound == FLT_MAX) {
-        done = true;  // the block covers the whole grid
-      } else {
-        bound -= g.slack;
-        // strict: an unvisited point at exactly the k-th distance could still win the index tie
-        done = bound > 0.f && sel.kd != D_EMPTY && __uint_as_float(sel.kd) < bound * bound;
-      }
-    }
-    if (!done) {  // pathological query (far outside / sparse region): scan the whole cloud
-      sel.reset();
-      for (int j0 = 0; j0 < job.n_support; j0 += 32) {
-        const int j = j0 + lane;
-        const bool valid = j < job.n_support;
-        const float4 p = pts[valid ? j : job.n_support - 1];
-        const float d = dist2_ref(qx, qy, qz, p.x, p.y, p.z);
-        sel.offer(d, __float_as_int(p.w), valid, k, lane);
-      }
-      sel.flush(k, lane);
-    }
-    if (lane < k) {
-      idx[obase + (long long)qi * k + lane] = sel.ei[0];
-      if (dist2) dist2[obase + (long long)qi * k + lane] = __uint_as_float(sel.ed[0]);
-    }
+    const long long o = obase + (long long)qi * k;
+    if (k == 1) grid_query<WarpMin>(job, g, start, pts, qx, qy, qz, k, lane, idx, dist2, o);
+    else grid_query<WarpSelect<GRID_E>>(job, g, start, pts, qx, qy, qz, k, lane, idx, dist2, o);
   }
 }
 

@@ -17,8 +17,8 @@ for (B, N, M, d) in [(2, 300, 520, 64), (1, 700, 1000, 128), (1, 130, 264, 256)]
             matching.match(rgbd.to(dev), mesh.to(dev), xyz, mask=mask, pad_mode=pad, mode=mode)
 rgbd, mesh, _ = synth.descriptors(1, 200, 264, 64, regime="random", seed=4)
 matching.match(rgbd.to(dev), mesh.to(dev), synth.model_bank_xyz(1, 264).to(dev), operand_mode="bf16x3")
-cld, sr = synth.frame_batch(2, 32, 800, seed=5)
-pyr = KnnPyramid(800, {s: (32 // s) ** 2 for s in (2, 4, 8)}, 2)
+cld, sr = synth.frame_batch(2, 64, 3200, seed=5)
+pyr = KnnPyramid(3200, {s: (64 // s) ** 2 for s in (2, 4, 8)}, 2)
 pyr(cld.to(dev), {s: v.to(dev) for s, v in sr.items()})
 x = torch.randn((2, 16, 300)).to(dev)
 dgcnn.get_graph_feature(x, k=8)
