@@ -31,7 +31,10 @@ constexpr int WARPS = 8;
 constexpr int QPB = QPW * WARPS;  // queries per CTA
 constexpr int TS = 1024;          // support points per shared-memory tile (12 KB)
 constexpr int R_MAX = 4;          // block radius (in cells) visited before the whole-cloud fallback
-constexpr int GRID_E = 4;         // pending candidates per lane between extractions (grid kernel)
+#ifndef GADM_KNN_GRID_E
+#define GADM_KNN_GRID_E 4
+#endif
+constexpr int GRID_E = GADM_KNN_GRID_E;   // pending candidates per lane between extractions (grid kernel)
 constexpr int BRUTE_E = 2;        // same, brute kernel (4 queries per warp: register budget)
 constexpr int HALF_BLOCK_K = 4;   // grid queries with k <= this try the 2x2x2 half-cell block first
 

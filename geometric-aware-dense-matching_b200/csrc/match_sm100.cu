@@ -496,6 +496,410 @@ int match_stages(int RT, int KB) {
   return stages;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Paired-row variant.  The epilogue's broadcast LDS of per-column constants share the SM's 128 B/clk shared-memory
+// port with the UMMA operand reads and the TMA writes, and in SOFT they are two thirds of that traffic (DESIGN.md
+// 3.1).  Here every epilogue thread owns the SAME lane of TWO row tiles, so a constant fetched from shared memory is
+// used for two scores: CTA = 256 rows, model tiles of 128 vertices, four 128-column accumulators
+// (2 buffers x 2 row tiles), 128x128x16 MMAs (same tensor rate, tools/umma_probe.cu).
+//   warp 16  TMA: the 256 x K' row tile once, model tiles (128 vertices x 64 k, 16 KB) + the tile's aux slice
+//   warp 17  UMMA: per K block the two row tiles back to back (the stage is read twice, then freed)
+//   warps 0..15  epilogue: warp w owns TMEM lanes 32 (w % 4).. of both row tiles and the 32-column slice w / 4
+constexpr int PBN = 128;                       // model vertices per tile
+constexpr int PB_STAGE_BYTES = PBN * BK * 2;   // 16 KB
+constexpr int P_MAX_STAGES = 8;
+constexpr int P_PLANE_BYTES = PBN * 4;
+constexpr int P_CS = PBN / 4;                  // 32 columns per warp slice
+constexpr int P_STASH_BYTES = 2 * STASH_BYTES; // two rows per thread
+
+struct PairBarriers {
+  uint64_t full[P_MAX_STAGES];
+  uint64_t empty[P_MAX_STAGES];
+  uint64_t a_full;
+  uint64_t s_full[2];
+  uint64_t s_free[2];
+  uint64_t aux_full[AUX_SLOTS];
+  uint64_t aux_empty[AUX_SLOTS];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+template <bool kSoft>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
+                  const MatchParams p) {
+  constexpr int AUX_BYTES = kSoft ? 4 * P_PLANE_BYTES : P_PLANE_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                                    // [2][KB] blocks of 128 rows x 64 k
+  uint8_t* smem_b = smem_a + 2 * p.KB * A_BLK_BYTES;
+  uint8_t* smem_aux = smem_b + p.stages * PB_STAGE_BYTES;  // per slot: [1/|m| x128 | x | y | z]
+  uint8_t* smem_stash = smem_aux + AUX_SLOTS * AUX_BYTES;
+  PairBarriers* bars = reinterpret_cast<PairBarriers*>(smem_stash + P_STASH_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int row0 = blockIdx.x * (2 * BM);
+  const int obj = frame_object(p, b);
+  const int num_tiles = (p.M + PBN - 1) / PBN;
+
+  if (warp == EPI_WARPS && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_rows);
+    ptx::prefetch_tensormap(&tmap_cols);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&bars->full[s], 1);
+      ptx::mbar_init(&bars->empty[s], 1);
+    }
+    ptx::mbar_init(&bars->a_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&bars->s_full[a], 1);
+      ptx::mbar_init(&bars->s_free[a], EPI_WARPS);
+    }
+    for (int a = 0; a < AUX_SLOTS; ++a) {
+      ptx::mbar_init(&bars->aux_full[a], 1);
+      ptx::mbar_init(&bars->aux_empty[a], EPI_WARPS);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == EPI_WARPS + 1) {
+    ptx::tmem_alloc(&bars->tmem_base, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == EPI_WARPS) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(&bars->a_full, 2 * p.KB * A_BLK_BYTES);
+      for (int r = 0; r < 2; ++r)
+        for (int kb = 0; kb < p.KB; ++kb)
+          ptx::tma_load_3d(smem_a + (r * p.KB + kb) * A_BLK_BYTES, &tmap_rows, &bars->a_full, kb * BK,
+                           row0 + r * BM, b);   // rows >= N are zero-filled by TMA
+      int stage = 0;
+      uint32_t phase = 0;
+      const size_t plane = size_t(p.n_obj) * p.M;
+      const float* sc_tab = p.scales + size_t(obj) * p.M;
+      const float* xyz_tab = p.planes + size_t(obj) * p.M;
+      for (int t = 0; t < num_tiles; ++t) {
+        const int slot = t % AUX_SLOTS;
+        const uint32_t use = uint32_t(t) / AUX_SLOTS;
+        const uint32_t bytes = uint32_t(min(PBN, p.M - t * PBN)) * 4;   // M % 8 == 0: a multiple of 16
+        ptx::mbar_wait_sleep(&bars->aux_empty[slot], (use & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&bars->aux_full[slot], kSoft ? 4 * bytes : bytes);
+        uint8_t* aux = smem_aux + slot * AUX_BYTES;
+        ptx::bulk_load_1d(aux, sc_tab + size_t(t) * PBN, bytes, &bars->aux_full[slot]);
+        if (kSoft) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            ptx::bulk_load_1d(aux + (c + 1) * P_PLANE_BYTES, xyz_tab + c * plane + size_t(t) * PBN, bytes,
+                              &bars->aux_full[slot]);
+        }
+        for (int kb = 0; kb < p.KB; ++kb) {
+          ptx::mbar_wait_sleep(&bars->empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&bars->full[stage], PB_STAGE_BYTES);
+          ptx::tma_load_3d(smem_b + stage * PB_STAGE_BYTES, &tmap_cols, &bars->full[stage], kb * BK, t * PBN, obj);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == EPI_WARPS + 1) {
+    // ============================== UMMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(BM, PBN);
+      ptx::mbar_wait(&bars->a_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < num_tiles; ++t) {
+        const int buf = t & 1;
+        ptx::mbar_wait_sleep(&bars->s_free[buf], ((uint32_t(t) >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        for (int kb = 0; kb < p.KB; ++kb) {
+          ptx::mbar_wait_sleep(&bars->full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t b_addr = ptx::smem_u32(smem_b + stage * PB_STAGE_BYTES);
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const uint32_t a_addr = ptx::smem_u32(smem_a + (r * p.KB + kb) * A_BLK_BYTES);
+            const uint32_t d_tmem = tmem_base + (buf * 2 + r) * PBN;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              ptx::umma_bf16_ss(d_tmem, ptx::umma_desc_sw128_kmajor(a_addr + k * UMMA_K * 2),
+                                ptx::umma_desc_sw128_kmajor(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0);
+          }
+          ptx::umma_commit(&bars->empty[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&bars->s_full[buf]);
+      }
+    }
+  } else {
+    // ============================== epilogue warps: thread == the same lane of both row tiles ==============
+    const int q = warp & 3;
+    const int sub = warp >> 2;              // 32-column slice of every tile
+    const int row_in_tile = q * 32 + lane;
+    int row[2];
+    bool row_ok[2];
+    size_t grow[2];
+    float rs[2], g[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      row[r] = row0 + r * BM + row_in_tile;
+      row_ok[r] = row[r] < p.N;
+      grow[r] = size_t(b) * p.N + (row_ok[r] ? row[r] : 0);
+      rs[r] = row_ok[r] ? p.rinv_rows[grow[r]] : 0.f;
+      g[r] = p.gamma_log2e * rs[r];
+    }
+    const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16) + sub * P_CS;
+    const uint32_t stash_addr = ptx::smem_u32(smem_stash) + threadIdx.x * 16;   // row r: + r * 2 * STASH_PLANE
+
+    float vmax[2] = {-INFINITY, -INFINITY};
+    int vgrp[2] = {0, 0};
+    float mref[2] = {0.f, 0.f};
+    bool have_ref = false;                  // both rows see their first valid chunk together
+    uint64_t l2[2] = {0, 0}, ax2[2] = {0, 0}, ay2[2] = {0, 0}, az2[2] = {0, 0};   // packed (even | odd column)
+
+    for (int t = 0; t < num_tiles; ++t) {
+      const int buf = t & 1;
+      const uint32_t use = uint32_t(t) >> 1;
+      const int slot = t % AUX_SLOTS;
+      if (!(ptx::mbar_try_wait(&bars->aux_full[slot], (uint32_t(t) / AUX_SLOTS) & 1) &
+            ptx::mbar_try_wait(&bars->s_full[buf], use & 1))) {
+        ptx::mbar_wait_sleep(&bars->aux_full[slot], (uint32_t(t) / AUX_SLOTS) & 1);
+        ptx::mbar_wait_sleep(&bars->s_full[buf], use & 1);
+      }
+      ptx::tc_fence_after();
+      const int ncols = min(PBN, p.M - t * PBN) - sub * P_CS;   // valid columns of this slice (may be <= 0)
+      const uint32_t s_tmem0 = lane_base + (buf * 2 + 0) * PBN, s_tmem1 = lane_base + (buf * 2 + 1) * PBN;
+      const uint32_t sc_addr = ptx::smem_u32(smem_aux + slot * AUX_BYTES) + sub * P_CS * 4;
+      const int col_base = t * PBN + sub * P_CS;
+
+      // W columns (slice columns col0 ..) of both rows: r0 / r1 hold the raw accumulators
+      auto process = [&](auto& r0, auto& r1, int col0, auto guard_tag) {
+        constexpr int W = int(sizeof(r0) / sizeof(r0[0]));
+        constexpr bool kGuard = decltype(guard_tag)::value;
+        const uint32_t sc = sc_addr + col0 * 4;
+        uint64_t v[2][W / 2];
+#pragma unroll
+        for (int j4 = 0; j4 < W / 4; ++j4) {
+          const float4 cm = ptx::lds128(sc + j4 * 16);
+          const uint64_t c01 = ptx::pack2f(cm.x, cm.y), c23 = ptx::pack2f(cm.z, cm.w);
+          v[0][j4 * 2 + 0] = ptx::fmul2(ptx::pack2(r0[j4 * 4 + 0], r0[j4 * 4 + 1]), c01);
+          v[0][j4 * 2 + 1] = ptx::fmul2(ptx::pack2(r0[j4 * 4 + 2], r0[j4 * 4 + 3]), c23);
+          v[1][j4 * 2 + 0] = ptx::fmul2(ptx::pack2(r1[j4 * 4 + 0], r1[j4 * 4 + 1]), c01);
+          v[1][j4 * 2 + 1] = ptx::fmul2(ptx::pack2(r1[j4 * 4 + 2], r1[j4 * 4 + 3]), c23);
+        }
+        if (kGuard) {
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+            for (int j = 0; j < W / 2; ++j) {
+              float lo, hi;
+              ptx::unpack2f(v[rr][j], lo, hi);
+              if (col0 + 2 * j >= ncols) lo = -INFINITY;
+              if (col0 + 2 * j + 1 >= ncols) hi = -INFINITY;
+              v[rr][j] = ptx::pack2f(lo, hi);
+            }
+        }
+        float cmx[2];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          cmx[rr] = -INFINITY;
+#pragma unroll
+          for (int h = 0; h < W / GRP; ++h) {
+            float f[GRP];
+#pragma unroll
+            for (int j = 0; j < GRP / 2; ++j) ptx::unpack2f(v[rr][h * 4 + j], f[2 * j], f[2 * j + 1]);
+            const float a0 = ptx::fmax3(f[0], f[1], f[2]), a1 = ptx::fmax3(f[3], f[4], f[5]);
+            const float gm = ptx::fmax3(a0, a1, fmaxf(f[6], f[7]));
+            const bool up = gm > vmax[rr];
+            ptx::sts_stash8(up, stash_addr + rr * 2 * STASH_PLANE, v[rr][h * 4 + 0], v[rr][h * 4 + 1],
+                            v[rr][h * 4 + 2], v[rr][h * 4 + 3]);
+            vgrp[rr] = up ? col_base + col0 + h * GRP : vgrp[rr];
+            vmax[rr] = up ? gm : vmax[rr];
+            if (kSoft) cmx[rr] = fmaxf(cmx[rr], gm);
+          }
+        }
+        if (kSoft) {
+          const float tn0 = cmx[0] * g[0], tn1 = cmx[1] * g[1];
+          if (!have_ref) { mref[0] = tn0; mref[1] = tn1; have_ref = true; }
+          if (__any_sync(0xffffffffu, tn0 > mref[0] + LAZY_TAU || tn1 > mref[1] + LAZY_TAU)) {
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              const float tn = rr ? tn1 : tn0;
+              const bool need = tn > mref[rr] + LAZY_TAU;
+              const float s = need ? ptx::ex2_approx(mref[rr] - tn) : 1.f;
+              const uint64_t s2 = ptx::pack2f(s, s);
+              l2[rr] = ptx::fmul2(l2[rr], s2); ax2[rr] = ptx::fmul2(ax2[rr], s2);
+              ay2[rr] = ptx::fmul2(ay2[rr], s2); az2[rr] = ptx::fmul2(az2[rr], s2);
+              mref[rr] = need ? tn : mref[rr];
+            }
+          }
+          const uint64_t g20 = ptx::pack2f(g[0], g[0]), g21 = ptx::pack2f(g[1], g[1]);
+          const uint64_t nm0 = ptx::pack2f(-mref[0], -mref[0]), nm1 = ptx::pack2f(-mref[1], -mref[1]);
+#pragma unroll
+          for (int j4 = 0; j4 < W / 4; ++j4) {
+            const float4 X = ptx::lds128(sc + P_PLANE_BYTES + j4 * 16);
+            const float4 Y = ptx::lds128(sc + 2 * P_PLANE_BYTES + j4 * 16);
+            const float4 Z = ptx::lds128(sc + 3 * P_PLANE_BYTES + j4 * 16);
+            const uint64_t X01 = ptx::pack2f(X.x, X.y), X23 = ptx::pack2f(X.z, X.w);
+            const uint64_t Y01 = ptx::pack2f(Y.x, Y.y), Y23 = ptx::pack2f(Y.z, Y.w);
+            const uint64_t Z01 = ptx::pack2f(Z.x, Z.y), Z23 = ptx::pack2f(Z.z, Z.w);
+            const uint64_t pa0 = ptx::ex2_2(ptx::ffma2(v[0][j4 * 2 + 0], g20, nm0));
+            const uint64_t pb0 = ptx::ex2_2(ptx::ffma2(v[0][j4 * 2 + 1], g20, nm0));
+            const uint64_t pa1 = ptx::ex2_2(ptx::ffma2(v[1][j4 * 2 + 0], g21, nm1));
+            const uint64_t pb1 = ptx::ex2_2(ptx::ffma2(v[1][j4 * 2 + 1], g21, nm1));
+            l2[0] = ptx::fadd2(l2[0], ptx::fadd2(pa0, pb0));
+            l2[1] = ptx::fadd2(l2[1], ptx::fadd2(pa1, pb1));
+            ax2[0] = ptx::ffma2(pb0, X23, ptx::ffma2(pa0, X01, ax2[0]));
+            ax2[1] = ptx::ffma2(pb1, X23, ptx::ffma2(pa1, X01, ax2[1]));
+            ay2[0] = ptx::ffma2(pb0, Y23, ptx::ffma2(pa0, Y01, ay2[0]));
+            ay2[1] = ptx::ffma2(pb1, Y23, ptx::ffma2(pa1, Y01, ay2[1]));
+            az2[0] = ptx::ffma2(pb0, Z23, ptx::ffma2(pa0, Z01, az2[0]));
+            az2[1] = ptx::ffma2(pb1, Z23, ptx::ffma2(pa1, Z01, az2[1]));
+          }
+        }
+      };
+      using guard_off = std::integral_constant<bool, false>;
+      using guard_on = std::integral_constant<bool, true>;
+
+      if (ncols > 0) {
+        if (!kSoft) {
+          uint32_t ra[32], rb[32];
+          ptx::tmem_ld_32x32(s_tmem0, ra);
+          ptx::tmem_ld_32x32(s_tmem1, rb);
+          ptx::tmem_ld_wait();
+          if (ncols >= P_CS) process(ra, rb, 0, guard_off{});
+          else process(ra, rb, 0, guard_on{});
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (ncols - h * 16 <= 0) break;
+            uint32_t ra[16], rb[16];
+            ptx::tmem_ld_32x16(s_tmem0 + h * 16, ra);
+            ptx::tmem_ld_32x16(s_tmem1 + h * 16, rb);
+            ptx::tmem_ld_wait();
+            if (ncols - h * 16 >= 16) process(ra, rb, h * 16, guard_off{});
+            else process(ra, rb, h * 16, guard_on{});
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(&bars->s_free[buf]);
+        ptx::mbar_arrive(&bars->aux_empty[slot]);
+      }
+    }
+
+    // ---- per row: first maximal index from the stash, merge of the four column slices, outputs
+    int vidx[2];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      vidx[rr] = 0;
+      if (vmax[rr] > -INFINITY) {
+        int j_first = GRP - 1;
+#pragma unroll
+        for (int k = GRP / 4 - 1; k >= 0; --k) {
+          const float4 sv = ptx::lds128(stash_addr + rr * 2 * STASH_PLANE + k * STASH_PLANE);
+          if (sv.w == vmax[rr]) j_first = 4 * k + 3;
+          if (sv.z == vmax[rr]) j_first = 4 * k + 2;
+          if (sv.y == vmax[rr]) j_first = 4 * k + 1;
+          if (sv.x == vmax[rr]) j_first = 4 * k + 0;
+        }
+        vidx[rr] = vgrp[rr] + j_first;
+      }
+    }
+    float lsum[2] = {0.f, 0.f}, ax[2] = {0.f, 0.f}, ay[2] = {0.f, 0.f}, az[2] = {0.f, 0.f};
+    if (kSoft) {
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        float e, o;
+        ptx::unpack2f(l2[rr], e, o); lsum[rr] = e + o;
+        ptx::unpack2f(ax2[rr], e, o); ax[rr] = e + o;
+        ptx::unpack2f(ay2[rr], e, o); ay[rr] = e + o;
+        ptx::unpack2f(az2[rr], e, o); az[rr] = e + o;
+        if (!have_ref) mref[rr] = -INFINITY;
+      }
+    }
+    // exchange buffers alias the row tiles' own A blocks (all MMAs have completed: the last s_full was seen)
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      float* xch = reinterpret_cast<float*>(smem_a + rr * p.KB * A_BLK_BYTES);   // 3 * 128 * 32 B = 12 KB <= 16 KB
+      if (sub > 0) {
+        float* x = xch + ((sub - 1) * BM + row_in_tile) * 8;
+        x[0] = vmax[rr]; x[1] = __int_as_float(vidx[rr]); x[2] = mref[rr]; x[3] = lsum[rr];
+        x[4] = ax[rr]; x[5] = ay[rr]; x[6] = az[rr];
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+    if (sub == 0) {
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        if (!row_ok[rr]) continue;
+        const float* xch = reinterpret_cast<const float*>(smem_a + rr * p.KB * A_BLK_BYTES);
+        float vm = vmax[rr], mm = mref[rr];
+        int vi = vidx[rr];
+#pragma unroll
+        for (int s2 = 0; s2 < 3; ++s2) {
+          const float* x = xch + (s2 * BM + row_in_tile) * 8;
+          const float v1 = x[0];
+          const int i1 = __float_as_int(x[1]);
+          if (v1 > vm || (v1 == vm && i1 < vi)) { vm = v1; vi = i1; }
+          mm = fmaxf(mm, x[2]);
+        }
+        const size_t gr = grow[rr];
+        const bool keep = p.mask == nullptr || p.mask[gr] != 0;
+        float best = vm * rs[rr];
+        int64_t best_idx = vi;
+        if (p.pad_mode != GADM_PAD_NONE) {
+          const float ps = p.pad_sim[gr];
+          if (ps > best) { best = ps; best_idx = p.M; }
+        }
+        p.idx[gr] = keep ? best_idx : int64_t(-1);
+        p.max_sim[gr] = keep ? best : 0.f;
+        if (kSoft) {
+          const float s0 = ptx::ex2_approx(mref[rr] - mm);
+          float l = lsum[rr] * s0, sx = ax[rr] * s0, sy = ay[rr] * s0, sz = az[rr] * s0;
+#pragma unroll
+          for (int s2 = 0; s2 < 3; ++s2) {
+            const float* x = xch + (s2 * BM + row_in_tile) * 8;
+            const float s1 = ptx::ex2_approx(x[2] - mm);
+            l = fmaf(x[3], s1, l); sx = fmaf(x[4], s1, sx); sy = fmaf(x[5], s1, sy); sz = fmaf(x[6], s1, sz);
+          }
+          const float inv = 1.f / l;
+          p.weight[gr] = keep ? ptx::ex2_approx(fmaf(vm, g[rr], -mm)) * inv : 0.f;
+          p.soft_xyz[gr * 3 + 0] = keep ? sx * inv : 0.f;
+          p.soft_xyz[gr * 3 + 1] = keep ? sy * inv : 0.f;
+          p.soft_xyz[gr * 3 + 2] = keep ? sz * inv : 0.f;
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS + 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <bool kSoft>
+size_t match_pair_smem_bytes(int KB, int stages) {
+  return size_t(2) * KB * A_BLK_BYTES + size_t(stages) * PB_STAGE_BYTES + AUX_SLOTS * (kSoft ? 4 : 1) * P_PLANE_BYTES +
+         P_STASH_BYTES + sizeof(PairBarriers) + 1024;
+}
+template <bool kSoft>
+int match_pair_stages(int KB) {
+  int stages = P_MAX_STAGES;
+  while (stages > 0 && match_pair_smem_bytes<kSoft>(KB, stages) > 227 * 1024) --stages;
+  return stages;
+}
+
 }  // namespace
 
 int match_configure() {
@@ -508,12 +912,36 @@ int match_configure() {
   if (e != cudaSuccess) return set_cuda_error(e);
   e = cudaFuncSetAttribute(match_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(match_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(match_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
   return GADM_OK;
 }
 
 template <bool kSoft>
 static int match_launch_t(const void* rows, const void* cols, MatchParams p, int Kp, cudaStream_t stream) {
   const int KB = Kp / BK;
+  {
+    // paired-row kernel (256 rows per CTA, every epilogue thread owns two rows).  Measured at the BASELINE shape:
+    // SOFT 0.384 ms against 0.400 ms (RT = 1), ARGMAX 0.241 ms against 0.211 ms (RT = 2) => default for SOFT only.
+    // GADM_MATCH_PAIR=1/0 forces / forbids it (profiling, tests).
+    bool pair = kSoft;
+    if (const char* f = getenv("GADM_MATCH_PAIR")) pair = atoi(f) != 0;
+    const int pstages = match_pair_stages<kSoft>(KB);
+    if (pair && pstages >= 2 * KB && p.N > BM) {
+      p.KB = KB; p.stages = pstages;
+      CUtensorMap tmap_rows, tmap_cols;
+      int rc = make_tmap_2b_3d(&tmap_rows, rows, uint64_t(Kp), uint64_t(p.N), uint64_t(p.B), BK, BM, 0);
+      if (rc != GADM_OK) return rc;
+      rc = make_tmap_2b_3d(&tmap_cols, cols, uint64_t(Kp), uint64_t(p.M), uint64_t(p.n_obj), BK, PBN, 0);
+      if (rc != GADM_OK) return rc;
+      dim3 grid((p.N + 2 * BM - 1) / (2 * BM), p.B);
+      match_pair_kernel<kSoft><<<grid, NUM_THREADS, match_pair_smem_bytes<kSoft>(KB, pstages), stream>>>(
+          tmap_rows, tmap_cols, p);
+      return check_launch();
+    }
+  }
   // Two row tiles per CTA when a ring of at least 2 KB stages (one tile resident, one in flight) fits beside them
   // and the frame has more than one row tile; otherwise one row tile with the deepest ring.  Measured at the
   // BASELINE shape: ARGMAX 0.204 ms (RT = 2) against 0.222 ms; SOFT 0.43 ms (RT = 2) against 0.41 ms -- SOFT is

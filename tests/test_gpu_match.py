@@ -184,3 +184,26 @@ def test_seg_mask_matches_torch_argmax(cuda):
     got = ops.seg_mask(seg.to(cuda)).cpu()
     assert got.dtype == torch.uint8 and got.shape == (3, 1001)
     assert torch.equal(got.bool(), torch.argmax(seg, dim=1) == 1)
+
+
+@pytest.mark.parametrize("env", [{"GADM_MATCH_PAIR": "0", "GADM_MATCH_RT": "1"}, {"GADM_MATCH_PAIR": "0", "GADM_MATCH_RT": "2"},
+                                 {"GADM_MATCH_PAIR": "1"}])
+def test_match_kernel_variants_agree(cuda, monkeypatch, env):
+    """The three tilings of the matcher (one row tile per CTA, two row tiles per CTA, paired rows per thread) are
+    selected per launch; every one of them must meet the same gates on a ragged shape, in both modes."""
+    from gadm_b200 import matching, synth
+    from oracle import match_oracle as mo
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    N, M, d = 1500, 2056, 128                  # ragged in rows (1500 = 5 * 256 + 220) and in model tiles (2056 = 8 * 256 + 8)
+    rgbd, mesh, _ = synth.descriptors(1, N, M, d, regime="planted", seed=77)
+    xyz = synth.fibonacci_sphere(M, 0.2)
+    ref = mo.match_soft(rgbd[0], mesh[0], xyz)
+    ok = ref["margin"] > 1e-3
+    for mode in ("soft", "argmax"):
+        idx, sim, w, sx = matching.match(rgbd.to(cuda), mesh.to(cuda), xyz[None].to(cuda), mode=mode)
+        assert torch.equal(idx[0].cpu()[ok], ref["idx"][ok])
+        assert (sim[0].cpu() - ref["max_sim"]).abs().max() <= 1e-3
+        if mode == "soft":
+            assert ((w[0].cpu() - ref["weight"]).abs() / ref["weight"]).max() <= 1e-3
+            assert (sx[0].cpu() - ref["soft_xyz"]).abs().max() <= 1e-3 * 0.2
