@@ -320,12 +320,12 @@ def run_gpu(args):
                        "collective": "all_gather of matcher outputs on a side stream" if world > 1 else "none"},
             "breakdown_ms": {"match_kernel": match_ms, "knn_pyramid": knn_ms,
                              "prep_and_other": ms_total / args.steps - match_ms - knn_ms},
-            "roofline": {"kernel": "match_kernel<soft> (tcgen05 fused similarity+softmax+argmax)", "bound": "tensor",
+            "roofline": {"kernel": "match_pair_kernel<soft> (tcgen05 fused similarity + softmax + argmax + soft coordinates)", "bound": "tensor",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_kind": f"{pk_kind} bf16 burst", "flop_per_launch": flop_per_launch,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
-                         # (profiles/r1d_ncu_full_final_kernels.csv); algorithmic bytes: 45 MB of operands + outputs
-                         "traffic": 44.51e6, "traffic_unit": "bytes per launch (ncu, round 1)"},
+                         # (profiles/r1e_ncu_full_final_kernels.csv); algorithmic bytes: 45 MB of operands + outputs
+                         "traffic": 44.63e6, "traffic_unit": "bytes per launch (ncu, round 1)"},
             "variants": {"match_kernel_argmax_only_ms": argmax_ms,
                          "match_kernel_argmax_only_frac": flop_per_launch / (argmax_ms * 1e-3) / 1e12 / peak},
             "knn": {"algorithmic_bytes_per_step": pyr.algorithmic_bytes * FRAMES,
