@@ -26,26 +26,37 @@ side = torch.cuda.Stream(device=dev, priority=0)
 main_hi = torch.cuda.Stream(device=dev, priority=-1) if prio else None
 
 
+mm_ev = []
+
+
 def step(i, mode):
     rgbd, mesh, _, _ = sets[i % 4]
     cur = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mm_ev.append((e0, e1))
     if mode == "serial":
         cols, aux = ops.prep_model(mesh, xyz, 0)
         rows, rinv, pad = ops.prep_rows(rgbd, 0, 0)
+        e0.record()
         out = ops.match_fwd(rows, rinv, pad, cols, aux, None, obj, 16.0, 0, MATCH_MODES["soft"])
+        e1.record()
         knn = pyr.run_packed(pts[i % 4])
         return out, knn
     cols, aux = ops.prep_model(mesh, xyz, 0)
     rows, rinv, pad = ops.prep_rows(rgbd, 0, 0)
     fork = torch.cuda.Event(); fork.record(cur)
     if mode == "match_first":
+        e0.record()
         out = ops.match_fwd(rows, rinv, pad, cols, aux, None, obj, 16.0, 0, MATCH_MODES["soft"])
+        e1.record()
     with torch.cuda.stream(side):
         side.wait_event(fork)
         knn = pyr.run_packed(pts[i % 4])
         join = torch.cuda.Event(); join.record(side)
     if mode == "knn_first":
+        e0.record()
         out = ops.match_fwd(rows, rinv, pad, cols, aux, None, obj, 16.0, 0, MATCH_MODES["soft"])
+        e1.record()
     cur.wait_event(join)
     return out, knn
 
@@ -58,9 +69,11 @@ for mode in ("serial", "match_first", "knn_first"):
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
+        mm_ev.clear()
         for i in range(20):
             step(i, mode)
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 20
-    print(f"{mode:12s} prio={int(prio)}: {ms:.4f} ms per step  {B / ms * 1e3:.0f} frames/s", flush=True)
+        mm = sum(x.elapsed_time(y) for x, y in mm_ev) / len(mm_ev)
+    print(f"{mode:12s} prio={int(prio)}: {ms:.4f} ms per step  {B / ms * 1e3:.0f} frames/s; match kernel {mm:.4f} ms", flush=True)

@@ -274,6 +274,14 @@ int main() {
   printf("      (MMA tiles issued meanwhile: %lld)\n", out[2]);
   run<0, 0, 0, 1, 32>(out, sink, "ARGMAX as shipped + the UMMA issuer");
   printf("      (MMA tiles issued meanwhile: %lld)\n", out[2]);
+  run<0, 0, 0, 1, 16>(out, sink, "ARGMAX, no scale LDS");
+  run<0, 0, 0, 1, 16 + 32>(out, sink, "ARGMAX, no scale LDS + the UMMA issuer");
+  printf("      (MMA tiles issued meanwhile: %lld)\n", out[2]);
+  run<0, 0, 0, 1, 8 + 16>(out, sink, "ARGMAX, no scale LDS, no stash");
+  run<0, 0, 0, 1, 8 + 16 + 32>(out, sink, "ARGMAX, no scale LDS, no stash + the UMMA issuer");
+  printf("      (MMA tiles issued meanwhile: %lld)\n", out[2]);
+  run<1, 0, 0, 0, 1 + 8 + 16 + 32>(out, sink, "SOFT, no LDS, no stash + the UMMA issuer");
+  printf("      (MMA tiles issued meanwhile: %lld)\n", out[2]);
   run<1, 1, 0, 0>(out, sink, "SOFT non-volatile LDS");
   run<1, 1, 1, 0>(out, sink, "SOFT non-volatile LDS, scales before the ld wait");
   run<1, 1, 1, 1>(out, sink, "SOFT non-volatile LDS, scales early, both chunks per wait");
