@@ -282,7 +282,19 @@ grid_setup_kernel(const float* __restrict__ support, uint8_t* __restrict__ ws, c
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   const int n3 = cl.n_support * 3;
   int ax = threadIdx.x % 3;
-  for (int e = threadIdx.x; e < n3; e += 1024) {  // 1024 % 3 == 1: the axis advances by one per iteration
+  // 1024 % 3 == 1: the axis advances by one per iteration, so three consecutive iterations touch x, y, z once each:
+  // issue the three loads together (the sweep is latency bound: one CTA per cloud)
+  int e = threadIdx.x;
+  for (; e + 2 * 1024 < n3; e += 3 * 1024) {
+    const float v0 = S[e], v1 = S[e + 1024], v2 = S[e + 2 * 1024];
+    const int a1 = ax == 2 ? 0 : ax + 1, a2 = a1 == 2 ? 0 : a1 + 1;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float v = a == ax ? v0 : (a == a1 ? v1 : v2);
+      lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v);
+    }
+  }
+  for (; e < n3; e += 1024) {
     const float v = S[e];
 #pragma unroll
     for (int a = 0; a < 3; ++a)
