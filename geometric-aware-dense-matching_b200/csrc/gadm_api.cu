@@ -69,7 +69,7 @@ const char* gadm_strerror(int status) {
   }
 }
 
-int gadm_abi_version(void) { return 1; }
+int gadm_abi_version(void) { return 2; }
 
 const char* gadm_last_cuda_error(void) { return g_cuda_err; }
 
@@ -138,20 +138,28 @@ int gadm_prep_model(const float* mesh, const float* model_xyz, int n_obj, int d,
 int gadm_match_fwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols, const float* aux,
                    const uint8_t* mask, const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma,
                    int pad_mode, int mode, int64_t* idx, float* max_sim, float* weight, float* soft_xyz,
-                   gadm_stream_t stream) {
+                   void* workspace, size_t workspace_bytes, gadm_stream_t stream) {
   GADM_REQUIRE_INIT();
   if (!rows || !rinv_rows || !cols || !aux || !idx || !max_sim) return GADM_ERR_BAD_ARG;
+  if (workspace && !aligned16(workspace)) return GADM_ERR_ALIGN;
   if (B <= 0 || N <= 0 || M <= 0 || Kp <= 0 || n_obj <= 0) return GADM_ERR_BAD_ARG;
   if (B > 65535) return GADM_ERR_UNSUPPORTED;
   if (mode != GADM_MATCH_ARGMAX && mode != GADM_MATCH_SOFT) return GADM_ERR_UNSUPPORTED;
   if (mode == GADM_MATCH_SOFT && (!weight || !soft_xyz)) return GADM_ERR_BAD_ARG;
+  // 2^(gamma log2(e) cos) is summed without a reference exponent: keep it well inside the fp32 range
+  if (mode == GADM_MATCH_SOFT && !(gamma >= -40.f && gamma <= 40.f)) return GADM_ERR_UNSUPPORTED;
   if (pad_mode < 0 || pad_mode > GADM_PAD_E0) return GADM_ERR_UNSUPPORTED;
   if (pad_mode != GADM_PAD_NONE && !pad_sim) return GADM_ERR_BAD_ARG;
   if (Kp % 64 != 0 || Kp > 768 || M % 8 != 0) return GADM_ERR_UNSUPPORTED;
   if (obj_id == nullptr && n_obj != 1 && n_obj != B) return GADM_ERR_BAD_ARG;
   if (!aligned16(rows) || !aligned16(cols) || !aligned16(aux)) return GADM_ERR_ALIGN;
   return match_launch(rows, rinv_rows, pad_sim, cols, aux, mask, obj_id, B, N, M, Kp, n_obj, gamma, pad_mode, mode,
-                      idx, max_sim, weight, soft_xyz, (cudaStream_t)stream);
+                      idx, max_sim, weight, soft_xyz, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t gadm_match_workspace_bytes(void) {
+  if (!initialised()) return 0;
+  return match_workspace_bytes();
 }
 
 int gadm_kabsch_moments(const int64_t* idx, const uint8_t* mask, const float* cloud, const float* aux,

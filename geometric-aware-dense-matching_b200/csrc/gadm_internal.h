@@ -33,7 +33,8 @@ int match_configure();
 int match_launch(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols, const float* aux,
                  const uint8_t* mask, const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma,
                  int pad_mode, int mode, int64_t* idx, float* max_sim, float* weight, float* soft_xyz,
-                 cudaStream_t stream);
+                 void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t match_workspace_bytes();
 
 // prep.cu
 int prep_rows_launch(const float* feat, int B, int d, int N, int operand_mode, int pad_mode, void* rows, float* rinv,

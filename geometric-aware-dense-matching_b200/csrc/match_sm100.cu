@@ -93,6 +93,8 @@ struct MatchParams {
   int B, N, M, KB, n_obj, stages;
   int pad_mode;
   float gamma_log2e;
+  uint8_t* stash;          // fragment-layout kernel: stash_slots slots of FRAG_STASH_BYTES (workspace), else null
+  int stash_slots;
 };
 
 __device__ __forceinline__ int frame_object(const MatchParams& p, int b) {
@@ -370,6 +372,9 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
       using guard_off = std::integral_constant<bool, false>;
       using guard_on = std::integral_constant<bool, true>;
 
+#ifdef GADM_DBG_NOEPI
+      if (false)
+#endif
 #pragma unroll
       for (int c2 = 0; c2 < CS / 64; ++c2) {
         const int nv = ncols - c2 * 64;      // valid columns of this pair of chunks
@@ -766,6 +771,9 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
       using guard_off = std::integral_constant<bool, false>;
       using guard_on = std::integral_constant<bool, true>;
 
+#ifdef GADM_DBG_NOEPI
+      if (false)
+#endif
       if (ncols > 0) {
         if (!kSoft) {
           uint32_t ra[32], rb[32];
@@ -900,6 +908,421 @@ int match_pair_stages(int KB) {
   return stages;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fragment-layout variant.  With thread == row every per-column constant has to be delivered to all 32 lanes of a
+// warp: 4 bytes of shared-memory return bandwidth per score and plane, which is what bounds the two kernels above
+// (DESIGN.md 3.1).  Here the accumulators are read with tcgen05.ld.16x256b, the mma.sync fragment layout: a thread
+// owns FOUR rows (TMEM lanes t/4 + {0, 8, 16, 24} of its warp's quarter) and, of every 8-column group, the column
+// pair 2 (t % 4) + {0, 1}.  One 8-byte LDS then serves 8 scores (4 rows x 2 columns) instead of 2, the 4 lanes of a
+// quad and the two column slices of a row merge once, after the last tile (shuffles + shared memory).
+//   Tiling, TMA and UMMA roles: as match_kernel<., 2> (256 rows per CTA, accumulator r = row tile r, 128x256x16 MMAs).
+//   warps 0..15: row tile (w / 4) % 2, TMEM lane quarter w % 4, 128-column slice w / 8.
+//   Argmax: a row has 8 tracks (4 quad lanes x 2 slices), a thread 4 of them, so the stash of "the scores of the
+//   chunk that last raised the running maximum" (32 B per track, 64 KB per CTA) lives in an L2-resident workspace
+//   slot indexed by %smid (one CTA per SM: the CTA needs > half of the SM's shared memory); stores are predicated,
+//   plane-major and coalesced, and only the storing thread ever reads them back.
+constexpr int FRAG_STASH_BYTES = EPI_WARPS * 32 * 4 * 32;   // 512 threads x 4 rows x 8 scores = 64 KB per slot
+constexpr int FRAG_STASH_PLANE = EPI_WARPS * 32 * 8;        // one packed pair per thread
+constexpr int FRAG_NO_RECORD = 0x40000000;                  // chunk column of a track that holds no record
+
+constexpr int FRAG_THREADS = 640;   // 4 epilogue warpgroups + 1 producer warpgroup (TMA, UMMA, two idle warps)
+
+template <bool kSoft, int RT>
+__global__ void __launch_bounds__(FRAG_THREADS, 1)
+match_frag_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
+                  const MatchParams p) {
+  constexpr int SL = 4 / RT;                 // column slices per row (warps that share a row)
+  constexpr int F_CS = BN / SL;              // columns per warp slice: 64 (RT = 1) or 128 (RT = 2)
+  constexpr int AUX_BYTES = kSoft ? 4 * PLANE_BYTES : PLANE_BYTES;
+  constexpr int W = 32;                      // columns per chunk
+  constexpr int NP = W / 8;                  // packed pairs (8-column groups) per row and chunk
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                                    // [RT][KB] blocks of 128 rows x 64 k
+  uint8_t* smem_b = smem_a + RT * p.KB * A_BLK_BYTES;
+  uint8_t* smem_aux = smem_b + p.stages * B_STAGE_BYTES;   // per slot: [1/|m| x256 | x x256 | y x256 | z x256]
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_aux + AUX_SLOTS * AUX_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int row0 = blockIdx.x * (BM * RT);
+  const int obj = frame_object(p, b);
+  const int num_tiles = (p.M + BN - 1) / BN;
+
+  if (warp == EPI_WARPS && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_rows);
+    ptx::prefetch_tensormap(&tmap_cols);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&bars->full[s], 1);
+      ptx::mbar_init(&bars->empty[s], 1);
+    }
+    ptx::mbar_init(&bars->a_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&bars->s_full[a], 1);
+      ptx::mbar_init(&bars->s_free[a], EPI_WARPS / RT);   // one arrive per epilogue warp of the accumulator
+    }
+    for (int a = 0; a < AUX_SLOTS; ++a) {
+      ptx::mbar_init(&bars->aux_full[a], 1);
+      ptx::mbar_init(&bars->aux_empty[a], EPI_WARPS);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == EPI_WARPS + 1) {
+    ptx::tmem_alloc(&bars->tmem_base, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp >= EPI_WARPS) {
+    // producer warpgroup (warps 16..19): hand registers to the epilogue warpgroups
+    ptx::setmaxnreg_dec<24>();
+  }
+  if (warp == EPI_WARPS) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(&bars->a_full, RT * p.KB * A_BLK_BYTES);
+      for (int r = 0; r < RT; ++r)
+        for (int kb = 0; kb < p.KB; ++kb)
+          ptx::tma_load_3d(smem_a + (r * p.KB + kb) * A_BLK_BYTES, &tmap_rows, &bars->a_full, kb * BK,
+                           row0 + r * BM, b);   // rows >= N are zero-filled by TMA
+      int stage = 0;
+      uint32_t phase = 0;
+      const size_t plane = size_t(p.n_obj) * p.M;
+      const float* sc_tab = p.scales + size_t(obj) * p.M;
+      const float* xyz_tab = p.planes + size_t(obj) * p.M;
+      for (int t = 0; t < num_tiles; ++t) {
+        const int slot = t % AUX_SLOTS;
+        const uint32_t use = uint32_t(t) / AUX_SLOTS;
+        const uint32_t bytes = uint32_t(min(BN, p.M - t * BN)) * 4;   // M % 8 == 0: a multiple of 16
+        ptx::mbar_wait_sleep(&bars->aux_empty[slot], (use & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&bars->aux_full[slot], kSoft ? 4 * bytes : bytes);
+        uint8_t* aux = smem_aux + slot * AUX_BYTES;
+        ptx::bulk_load_1d(aux, sc_tab + size_t(t) * BN, bytes, &bars->aux_full[slot]);
+        if (kSoft) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            ptx::bulk_load_1d(aux + (c + 1) * PLANE_BYTES, xyz_tab + c * plane + size_t(t) * BN, bytes,
+                              &bars->aux_full[slot]);
+        }
+        for (int kb = 0; kb < p.KB; ++kb) {
+          ptx::mbar_wait_sleep(&bars->empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&bars->full[stage], B_STAGE_BYTES);
+          ptx::tma_load_3d(smem_b + stage * B_STAGE_BYTES, &tmap_cols, &bars->full[stage], kb * BK, t * BN, obj);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == EPI_WARPS + 1) {
+    // ============================== UMMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(BM, BN);
+      ptx::mbar_wait(&bars->a_full, 0);
+      int stage0 = 0;            // ring position of the tile's first K block
+      uint32_t phase0 = 0;
+      for (int t = 0; t < num_tiles; ++t) {
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          const int acc = RT == 1 ? (t & 1) : r;
+          const uint32_t use = RT == 1 ? uint32_t(t) >> 1 : uint32_t(t);
+          ptx::mbar_wait_sleep(&bars->s_free[acc], (use & 1) ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          int stage = stage0;
+          uint32_t phase = phase0;
+          for (int kb = 0; kb < p.KB; ++kb) {
+            if (r == 0) {      // the stages of this tile stay resident until the last row tile has used them
+              ptx::mbar_wait_sleep(&bars->full[stage], phase);
+              ptx::tc_fence_after();
+            }
+            const uint32_t a_addr = ptx::smem_u32(smem_a + (r * p.KB + kb) * A_BLK_BYTES);
+            const uint32_t b_addr = ptx::smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              ptx::umma_bf16_ss(d_tmem, ptx::umma_desc_sw128_kmajor(a_addr + k * UMMA_K * 2),
+                                ptx::umma_desc_sw128_kmajor(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0);
+            }
+            if (r == RT - 1) ptx::umma_commit(&bars->empty[stage]);  // frees the stage once these MMAs have read it
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          ptx::umma_commit(&bars->s_full[acc]);   // accumulator tile complete
+          if (r == RT - 1) { stage0 = stage; phase0 = phase; }
+        }
+      }
+    }
+  } else if (warp < EPI_WARPS) {
+    ptx::setmaxnreg_inc<112>();
+    // ============================== epilogue warps (fragment layout: 4 rows x column pairs per thread) ==========
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access (warp id % 4)
+    const int rt = RT == 1 ? 0 : (warp >> 2) & 1;      // row tile
+    const int sub = RT == 1 ? warp >> 2 : warp >> 3;   // column slice of every tile
+    const int q4 = lane & 3;                 // column pair inside every 8-column group
+    const int r8 = lane >> 2;                // rows q * 32 + r8 + 8 rr, rr = 0..3
+    const int rbase = row0 + rt * BM + q * 32 + r8;
+    float g[4];                              // exponent scale of row rr: t = (acc * 1/|m_j|) * g   (log2 units)
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int row = rbase + 8 * rr;
+      g[rr] = kSoft && row < p.N ? p.gamma_log2e * p.rinv_rows[size_t(b) * p.N + row] : 0.f;
+    }
+    const uint32_t lane_lo0 = tmem_base + (uint32_t(q * 32) << 16) + sub * F_CS;
+    if (ptx::smid() >= uint32_t(p.stash_slots)) __trap();
+    // stash of row rr, pair i: plane rr * NP + i of the slot, 8 bytes per thread (coalesced 256-byte warp stores)
+    uint8_t* stash = p.stash + size_t(ptx::smid()) * FRAG_STASH_BYTES + threadIdx.x * 8;
+
+    float vmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // running maximum of the thread's track of row rr
+    int vchk[4] = {0, 0, 0, 0};              // first column of the chunk that first reached it
+    // SOFT: p = 2^(score * g) WITHOUT a reference exponent: |score * g| <= |gamma| log2(e) (a cosine times gamma), and
+    // gadm_match_fwd admits |gamma| <= 40 only, so p stays within 2^+-58 and the sums within fp32 range -- the online
+    // maximum of a flash-style softmax (a compare, a vote and a rescale per chunk) is not needed at all.
+    uint64_t l2[4] = {0, 0, 0, 0}, ax2[4] = {0, 0, 0, 0}, ay2[4] = {0, 0, 0, 0}, az2[4] = {0, 0, 0, 0};
+
+    for (int t = 0; t < num_tiles; ++t) {
+      const int slot = t % AUX_SLOTS;
+      const int acc = RT == 1 ? (t & 1) : rt;
+      const uint32_t use = RT == 1 ? uint32_t(t) >> 1 : uint32_t(t);
+      if (!(ptx::mbar_try_wait(&bars->aux_full[slot], (uint32_t(t) / AUX_SLOTS) & 1) &
+            ptx::mbar_try_wait(&bars->s_full[acc], use & 1))) {
+        ptx::mbar_wait_sleep(&bars->aux_full[slot], (uint32_t(t) / AUX_SLOTS) & 1);
+        ptx::mbar_wait_sleep(&bars->s_full[acc], use & 1);
+      }
+      ptx::tc_fence_after();
+      const uint32_t lane_lo = lane_lo0 + acc * BN, lane_hi = lane_lo + (16u << 16);
+      const int ncols = min(BN, p.M - t * BN) - sub * F_CS;   // valid columns of this slice (may be <= 0)
+      const uint32_t sc_addr = ptx::smem_u32(smem_aux + slot * AUX_BYTES) + (sub * F_CS + 2 * q4) * 4;
+      const int col_base = t * BN + sub * F_CS;
+
+      // One chunk of W columns starting at slice column col0; d0 / d1 hold the raw accumulators of rows
+      // {0, 8} / {16, 24} (+ r8), c2 the column scales of the thread's pairs.  kGuard (ragged last tile): 8-column
+      // groups at or beyond ncols are masked (M % 8 == 0: a group is valid or invalid as a whole).
+      auto process = [&](auto& d0, auto& d1, const uint64_t (&c2)[NP], int col0, auto guard_tag) {
+        constexpr bool kGuard = decltype(guard_tag)::value;
+        const uint32_t sc = sc_addr + col0 * 4;
+        uint64_t v[4][NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          v[0][i] = ptx::fmul2(ptx::pack2(d0[4 * i + 0], d0[4 * i + 1]), c2[i]);
+          v[1][i] = ptx::fmul2(ptx::pack2(d0[4 * i + 2], d0[4 * i + 3]), c2[i]);
+          v[2][i] = ptx::fmul2(ptx::pack2(d1[4 * i + 0], d1[4 * i + 1]), c2[i]);
+          v[3][i] = ptx::fmul2(ptx::pack2(d1[4 * i + 2], d1[4 * i + 3]), c2[i]);
+          if (kGuard && col0 + 8 * i >= ncols) {                   // warp-uniform
+            const uint64_t ninf2 = ptx::pack2f(-INFINITY, -INFINITY);
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) v[rr][i] = ninf2;
+          }
+        }
+        if (kSoft) {
+#pragma unroll
+          for (int i = 0; i < NP; ++i) {
+            if (kGuard && col0 + 8 * i >= ncols) break;            // stale constants behind the last group
+#ifdef GADM_DBG_NOLDS
+            const uint64_t X2 = ptx::pack2f(1.f + i, 1.f), Y2 = ptx::pack2f(2.f + i, 1.f), Z2 = ptx::pack2f(3.f + i, 1.f);
+#else
+            const uint64_t X2 = ptx::lds64(sc + PLANE_BYTES + i * 32);
+            const uint64_t Y2 = ptx::lds64(sc + 2 * PLANE_BYTES + i * 32);
+            const uint64_t Z2 = ptx::lds64(sc + 3 * PLANE_BYTES + i * 32);
+#endif
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+#ifdef GADM_DBG_NOMUFU
+              const uint64_t pp = ptx::fmul2(v[rr][i], ptx::pack2f(g[rr], g[rr]));
+#else
+              const uint64_t pp = ptx::ex2_2(ptx::fmul2(v[rr][i], ptx::pack2f(g[rr], g[rr])));   // p = 2^(score * g)
+#endif
+              l2[rr] = ptx::fadd2(l2[rr], pp);
+              ax2[rr] = ptx::ffma2(pp, X2, ax2[rr]);
+              ay2[rr] = ptx::ffma2(pp, Y2, ay2[rr]);
+              az2[rr] = ptx::ffma2(pp, Z2, az2[rr]);
+            }
+          }
+        }
+#ifdef GADM_DBG_NOMAX
+        for (int rr = 0; rr < 4; ++rr) vmax[rr] += __uint_as_float(uint32_t(v[rr][0] ^ v[rr][1] ^ v[rr][2] ^ v[rr][3]));
+#else
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          float f[2 * NP];
+#pragma unroll
+          for (int i = 0; i < NP; ++i) ptx::unpack2f(v[rr][i], f[2 * i], f[2 * i + 1]);
+          const float a0 = ptx::fmax3(f[0], f[1], f[2]), a1 = ptx::fmax3(f[3], f[4], f[5]);
+          const float gm = ptx::fmax3(a0, a1, fmaxf(f[6], f[7]));
+          // strict: an equal value in a later chunk never displaces the first maximal index
+          const bool up = gm > vmax[rr];
+#pragma unroll
+#ifndef GADM_DBG_NOSTASH
+          for (int i = 0; i < NP; ++i) ptx::stg_pred8(up, stash + (rr * NP + i) * FRAG_STASH_PLANE, v[rr][i]);
+#endif
+          vchk[rr] = up ? col_base + col0 : vchk[rr];
+          vmax[rr] = up ? gm : vmax[rr];
+        }
+#endif
+      };
+      using guard_off = std::integral_constant<bool, false>;
+      using guard_on = std::integral_constant<bool, true>;
+
+#ifndef GADM_DBG_NOEPI
+#pragma unroll
+      for (int c = 0; c < F_CS / W; ++c) {
+        const int nv = ncols - c * W;        // valid columns from this chunk on
+        if (nv <= 0) break;
+        uint32_t d0[4 * NP], d1[4 * NP];
+        uint64_t c2[NP];
+        ptx::tmem_ld_frag(lane_lo + c * W, d0);
+        ptx::tmem_ld_frag(lane_hi + c * W, d1);
+#pragma unroll
+#ifdef GADM_DBG_NOLDS
+        for (int i = 0; i < NP; ++i) c2[i] = ptx::pack2f(1.f + i, 1.f);
+#else
+        for (int i = 0; i < NP; ++i) c2[i] = ptx::lds64(sc_addr + (c * W + 8 * i) * 4);   // overlaps the TMEM latency
+#endif
+        ptx::tmem_ld_wait();
+#ifdef GADM_DBG_LDONLY
+        vchk[0] += d0[0] + d1[0] + d0[15] + d1[15];
+#else
+        if (nv >= W) process(d0, d1, c2, c * W, guard_off{});
+        else process(d0, d1, c2, c * W, guard_on{});
+#endif
+      }
+#endif
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(&bars->s_free[acc]);
+        ptx::mbar_arrive(&bars->aux_empty[slot]);
+      }
+      // The 4 tracks of a quad belong to the same rows.  Each one alone would raise its running maximum (and store
+      // a stash entry: a wavefront of the SM's data pipe per store instruction with any lane on) H(n) ~ 5 times;
+      // sharing the quad's maximum after tiles 0, 1, 3, 7, ... leaves ~ln(2) updates per ROW between two
+      // exchanges.  A track that adopts a larger maximum than its own gives up its record: its chunk becomes a
+      // sentinel that loses every tie, which is right -- the holder of that maximum sits at an earlier column.
+      if ((t & (t + 1)) == 0) {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          float m = fmaxf(vmax[rr], __shfl_xor_sync(0xffffffffu, vmax[rr], 1));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+          if (vmax[rr] < m) { vmax[rr] = m; vchk[rr] = FRAG_NO_RECORD; }
+        }
+      }
+    }
+
+    // ---- first maximal index of every track: look it up in the stashed chunk (own stores, read back through L2)
+    int vidx[4];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      vidx[rr] = FRAG_NO_RECORD;
+      if (vmax[rr] > -INFINITY && vchk[rr] != FRAG_NO_RECORD) {
+        int j_first = 2 * NP - 1;
+#pragma unroll
+        for (int i = NP - 1; i >= 0; --i) {
+          float lo, hi;
+          ptx::unpack2f(ptx::ldg_cg64(stash + (rr * NP + i) * FRAG_STASH_PLANE), lo, hi);
+          if (hi == vmax[rr]) j_first = 2 * i + 1;
+          if (lo == vmax[rr]) j_first = 2 * i;
+        }
+        vidx[rr] = vchk[rr] + 8 * (j_first >> 1) + 2 * q4 + (j_first & 1);
+      }
+    }
+
+    // ---- merge the 4 tracks of a quad (butterfly: afterwards every lane of the quad holds all 4 rows)
+    float lsum[4], ax[4], ay[4], az[4];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      float e, o;
+      ptx::unpack2f(l2[rr], e, o); lsum[rr] = e + o;
+      ptx::unpack2f(ax2[rr], e, o); ax[rr] = e + o;
+      ptx::unpack2f(ay2[rr], e, o); ay[rr] = e + o;
+      ptx::unpack2f(az2[rr], e, o); az[rr] = e + o;
+#pragma unroll
+      for (int off = 1; off <= 2; off <<= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, vmax[rr], off);
+        const int oi = __shfl_xor_sync(0xffffffffu, vidx[rr], off);
+        if (ov > vmax[rr] || (ov == vmax[rr] && oi < vidx[rr])) { vmax[rr] = ov; vidx[rr] = oi; }
+        if (kSoft) {
+          lsum[rr] += __shfl_xor_sync(0xffffffffu, lsum[rr], off);
+          ax[rr] += __shfl_xor_sync(0xffffffffu, ax[rr], off);
+          ay[rr] += __shfl_xor_sync(0xffffffffu, ay[rr], off);
+          az[rr] += __shfl_xor_sync(0xffffffffu, az[rr], off);
+        }
+      }
+    }
+    // lane q4 of the quad finishes row rr == q4
+    float my_vmax = vmax[0], my_l = lsum[0], my_ax = ax[0], my_ay = ay[0], my_az = az[0], my_g = g[0];
+    int my_vidx = vidx[0];
+#pragma unroll
+    for (int rr = 1; rr < 4; ++rr)
+      if (q4 == rr) {
+        my_vmax = vmax[rr]; my_vidx = vidx[rr]; my_l = lsum[rr];
+        my_ax = ax[rr]; my_ay = ay[rr]; my_az = az[rr]; my_g = g[rr];
+      }
+    const int row_in_tile = q * 32 + r8 + 8 * q4;
+    const int row = row0 + rt * BM + row_in_tile;
+    const bool row_ok = row < p.N;
+    const size_t grow = size_t(b) * p.N + (row_ok ? row : 0);
+
+    // ---- merge the two column slices of every row through shared memory (the row tile's own A blocks: every MMA
+    // that reads them has completed, this warp has seen the last s_full of its accumulator)
+    float* xch = reinterpret_cast<float*>(smem_a + rt * p.KB * A_BLK_BYTES);   // (SL - 1) * 128 * 32 B <= 16 KB
+    if (sub > 0) {
+      float* x = xch + ((sub - 1) * BM + row_in_tile) * 8;
+      x[0] = my_vmax; x[1] = __int_as_float(my_vidx); x[2] = my_l;
+      x[3] = my_ax; x[4] = my_ay; x[5] = my_az;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+    if (sub == 0 && row_ok) {
+#pragma unroll
+      for (int s2 = 0; s2 < SL - 1; ++s2) {
+        const float* x = xch + (s2 * BM + row_in_tile) * 8;
+        const float v1 = x[0];
+        const int i1 = __float_as_int(x[1]);
+        if (v1 > my_vmax || (v1 == my_vmax && i1 < my_vidx)) { my_vmax = v1; my_vidx = i1; }
+        my_l += x[2]; my_ax += x[3]; my_ay += x[4]; my_az += x[5];
+      }
+      const float rs = p.rinv_rows[grow];
+      const bool keep = p.mask == nullptr || p.mask[grow] != 0;
+      float best = my_vmax * rs;
+      int64_t best_idx = my_vidx;
+      if (p.pad_mode != GADM_PAD_NONE) {
+        const float ps = p.pad_sim[grow];
+        if (ps > best) { best = ps; best_idx = p.M; }  // pad column is the last one: wins only if strictly larger
+      }
+      p.idx[grow] = keep ? best_idx : int64_t(-1);
+      p.max_sim[grow] = keep ? best : 0.f;
+      if (kSoft) {
+        const float inv = 1.f / my_l;
+        p.weight[grow] = keep ? ptx::ex2_approx(my_vmax * my_g) * inv : 0.f;  // softmax value at the maximum
+        p.soft_xyz[grow * 3 + 0] = keep ? my_ax * inv : 0.f;
+        p.soft_xyz[grow * 3 + 1] = keep ? my_ay * inv : 0.f;
+        p.soft_xyz[grow * 3 + 2] = keep ? my_az * inv : 0.f;
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS + 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <bool kSoft>
+size_t match_frag_smem_bytes(int RT, int KB, int stages) {
+  return size_t(RT) * KB * A_BLK_BYTES + size_t(stages) * B_STAGE_BYTES + AUX_SLOTS * (kSoft ? 4 : 1) * PLANE_BYTES +
+         sizeof(Barriers) + 1024;
+}
+template <bool kSoft>
+int match_frag_stages(int RT, int KB) {
+  int stages = MAX_STAGES;
+  while (stages > 0 && match_frag_smem_bytes<kSoft>(RT, KB, stages) > 227 * 1024) --stages;
+  return stages;
+}
+
+int g_stash_slots = 0;     // SM count of the device gadm_init() ran on (written once, read-only afterwards)
+
 }  // namespace
 
 int match_configure() {
@@ -916,12 +1339,57 @@ int match_configure() {
   if (e != cudaSuccess) return set_cuda_error(e);
   e = cudaFuncSetAttribute(match_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(match_frag_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(match_frag_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(match_frag_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(match_frag_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  int dev = 0, sms = 0;
+  e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  g_stash_slots = sms;
   return GADM_OK;
 }
+
+// One stash slot per SM (the fragment-layout kernel runs one CTA per SM and indexes its slot by %smid).
+size_t match_workspace_bytes() { return size_t(g_stash_slots) * FRAG_STASH_BYTES; }
 
 template <bool kSoft>
 static int match_launch_t(const void* rows, const void* cols, MatchParams p, int Kp, cudaStream_t stream) {
   const int KB = Kp / BK;
+  {
+    // fragment-layout kernel (needs the stash workspace).  RT = 1: one row tile per CTA and the two accumulators
+    // alternate between consecutive model tiles; RT = 2: two row tiles per CTA (half the L2 operand traffic).
+    // Measured at the BASELINE shape: ARGMAX 0.242 / 0.223 ms (RT = 1 / 2) against 0.211 ms for
+    // match_kernel<., 2>, SOFT 0.445 / 0.426 ms against 0.383 ms for the paired-row kernel -- it quarters the
+    // epilogue's shared-memory wavefronts but pays for them in issue slots (16 stash stores per chunk) and the
+    // SOFT epilogue is MUFU / FMA-bound either way, so it is NOT the default.
+    // GADM_MATCH_FRAG=1/2 selects it with RT = 1 / RT = 2 (profiling, tests).
+    int frt = 0;
+    if (const char* f = getenv("GADM_MATCH_FRAG")) frt = atoi(f);
+    if (frt == 2 && (match_frag_stages<kSoft>(2, KB) < 2 * KB || p.N <= BM)) frt = 1;
+    const int fstages = frt > 0 ? match_frag_stages<kSoft>(frt, KB) : 0;
+    if (frt > 0 && p.stash != nullptr && fstages >= 2) {
+      p.KB = KB; p.stages = fstages;
+      CUtensorMap tmap_rows, tmap_cols;
+      int rc = make_tmap_2b_3d(&tmap_rows, rows, uint64_t(Kp), uint64_t(p.N), uint64_t(p.B), BK, BM, 0);
+      if (rc != GADM_OK) return rc;
+      rc = make_tmap_2b_3d(&tmap_cols, cols, uint64_t(Kp), uint64_t(p.M), uint64_t(p.n_obj), BK, BN, 0);
+      if (rc != GADM_OK) return rc;
+      dim3 grid((p.N + frt * BM - 1) / (frt * BM), p.B);
+      const size_t smem = match_frag_smem_bytes<kSoft>(frt, KB, fstages);
+      if (frt == 2)
+        match_frag_kernel<kSoft, 2><<<grid, FRAG_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+      else
+        match_frag_kernel<kSoft, 1><<<grid, FRAG_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+      return check_launch();
+    }
+  }
   {
     // paired-row kernel (256 rows per CTA, every epilogue thread owns two rows).  Measured at the BASELINE shape:
     // SOFT 0.384 ms against 0.400 ms (RT = 1), ARGMAX 0.241 ms against 0.211 ms (RT = 2) => default for SOFT only.
@@ -974,8 +1442,11 @@ static int match_launch_t(const void* rows, const void* cols, MatchParams p, int
 int match_launch(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols, const float* aux,
                  const uint8_t* mask, const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma,
                  int pad_mode, int mode, int64_t* idx, float* max_sim, float* weight, float* soft_xyz,
-                 cudaStream_t stream) {
+                 void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   MatchParams p;
+  const bool ws_ok = workspace != nullptr && g_stash_slots > 0 && workspace_bytes >= match_workspace_bytes();
+  p.stash = ws_ok ? static_cast<uint8_t*>(workspace) : nullptr;
+  p.stash_slots = g_stash_slots;
   p.rinv_rows = rinv_rows; p.pad_sim = pad_sim; p.scales = aux_scales(aux, n_obj, M);
   p.planes = aux_planes(aux, n_obj, M); p.mask = mask; p.obj_id = obj_id;
   p.idx = idx; p.max_sim = max_sim; p.weight = weight; p.soft_xyz = soft_xyz;

@@ -181,6 +181,28 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "r"(taddr)
       : "memory");
 }
+// TMEM -> registers in the 16x256b fragment layout (the mma.sync accumulator layout): 16 TMEM lanes starting at the
+// lane of `taddr`, NG groups of 8 fp32 columns.  Thread t holds, for group i:
+//   r[4i + 0], r[4i + 1] = lane t / 4,     columns 8i + 2 (t % 4) + {0, 1}
+//   r[4i + 2], r[4i + 3] = lane t / 4 + 8, same columns
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_16x256b_x4(taddr, r); }
+__device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, uint32_t (&r)[8]) { tmem_ld_16x256b_x2(taddr, r); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 
@@ -242,6 +264,56 @@ __device__ __forceinline__ float4 lds128_free(uint32_t saddr) {
 // makes `v` opaque to the optimiser at this point of the volatile-asm order (a scheduling pin, no instruction)
 __device__ __forceinline__ uint32_t opaque(uint32_t v) {
   asm volatile("" : "+r"(v) :: "memory");
+  return v;
+}
+// one packed pair (8 bytes) from shared memory
+__device__ __forceinline__ uint64_t lds64(uint32_t saddr) {
+  uint64_t v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(saddr));
+  return v;
+}
+// predicated (branch-free) 16-byte stores of packed pairs to GLOBAL memory: the fragment-layout matcher keeps its
+// argmax stash in an L2-resident workspace (2048 row tracks per CTA do not fit in shared memory)
+__device__ __forceinline__ void stg_pred16(bool pred, void* gaddr, uint64_t v0, uint64_t v1) {
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "setp.ne.b32 P, %0, 0;\n\t"
+      "@P st.global.v2.b64 [%1], {%2, %3};\n\t}\n"
+      ::"r"(uint32_t(pred)), "l"(gaddr), "l"(v0), "l"(v1)
+      : "memory");
+}
+__device__ __forceinline__ void stg_pred32(bool pred, void* gaddr, uint64_t v0, uint64_t v1, uint64_t v2, uint64_t v3) {
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "setp.ne.b32 P, %0, 0;\n\t"
+      "@P st.global.v2.b64 [%1], {%2, %3};\n\t"
+      "@P st.global.v2.b64 [%1 + 8192], {%4, %5};\n\t}\n"
+      ::"r"(uint32_t(pred)), "l"(gaddr), "l"(v0), "l"(v1), "l"(v2), "l"(v3)
+      : "memory");
+}
+__device__ __forceinline__ void stg_pred8(bool pred, void* gaddr, uint64_t v) {
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "setp.ne.b32 P, %0, 0;\n\t"
+      "@P st.global.b64 [%1], %2;\n\t}\n"
+      ::"r"(uint32_t(pred)), "l"(gaddr), "l"(v)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t ldg_cg64(const void* gaddr) {
+  uint64_t v;
+  asm volatile("ld.global.cg.b64 %0, [%1];" : "=l"(v) : "l"(gaddr) : "memory");
+  return v;
+}
+// L2 (cache-global) load of a float4 the same thread stored earlier
+__device__ __forceinline__ float4 ldg_cg128(const void* gaddr) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(gaddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t smid() {
+  uint32_t v;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
   return v;
 }
 __device__ __forceinline__ float lds32(uint32_t saddr) {

@@ -108,10 +108,13 @@ def match_fwd(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tensor, col
     soft_xyz = torch.empty((B, N, 3) if soft else (0,), dtype=torch.float32, device=dev)
     lib = _lib_for(rows)
     with torch.cuda.device(dev):
+        # scratch of the fragment-layout kernel (argmax stash, one 64 KB slot per SM), from torch's caching allocator
+        ws = torch.empty((int(lib.gadm_match_workspace_bytes()),), dtype=torch.uint8, device=dev)
         _lib.check(lib.gadm_match_fwd(_ptr(rows), _ptr(rinv), _ptr(pad_sim) if pad_mode else None, _ptr(cols),
                                       _ptr(aux), _ptr(mask), _ptr(obj_id), B, N, M, kp, n_obj, float(gamma),
                                       pad_mode, mode, _ptr(idx), _ptr(max_sim), _ptr(weight) if soft else None,
-                                      _ptr(soft_xyz) if soft else None, _stream()), "gadm_match_fwd")
+                                      _ptr(soft_xyz) if soft else None, _ptr(ws), ws.numel(), _stream()),
+                   "gadm_match_fwd")
     return idx, max_sim, weight, soft_xyz
 
 

@@ -96,11 +96,16 @@ int gadm_prep_model(const float* mesh, const float* model_xyz, int n_obj, int d,
  *   mask [B, N] uint8 or NULL: rows with mask == 0 get idx = -1 and zeros.
  *   idx [B, N] int64 (M means "pad column won"), max_sim [B, N] fp32,
  *   weight [B, N] fp32 and soft_xyz [B, N, 3] fp32 (may be NULL when mode == GADM_MATCH_ARGMAX).
- * Kp = K' from gadm_operand_k(); must be a multiple of 64 and <= 768.                                 */
+ * Kp = K' from gadm_operand_k(); must be a multiple of 64 and <= 768.
+ * workspace (optional, 16-byte aligned, gadm_match_workspace_bytes() bytes, contents irrelevant on entry and
+ * exit): scratch for the fragment-layout kernel, the fastest one for K' <= 128; one workspace serves one launch
+ * at a time (launches that may overlap on different streams need one each).  NULL selects the kernels that need
+ * none.  Results are identical either way.                                                             */
+size_t gadm_match_workspace_bytes(void);
 int gadm_match_fwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
                    const float* aux, const uint8_t* mask, const int32_t* obj_id, int B, int N, int M, int Kp,
                    int n_obj, float gamma, int pad_mode, int mode, int64_t* idx, float* max_sim, float* weight,
-                   float* soft_xyz, gadm_stream_t stream);
+                   float* soft_xyz, void* workspace, size_t workspace_bytes, gadm_stream_t stream);
 
 /* Foreground mask of the matcher (evaluator.py:78,82: `seg_res = argmax(seg_features, dim=0); cls_msk = seg_res == 1`)
  * without the argmax tensor: seg [B, 2, N] fp32 -> mask [B, N] uint8 = seg[b,1,n] > seg[b,0,n]  (torch.argmax returns

@@ -30,7 +30,7 @@ def test_library_exports_every_header_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/gadm.h but not exported by libgadm.so"
     assert set(syms) == set(_lib.SIGNATURES), "ctypes signature table must cover the header exactly"
-    assert lib.gadm_abi_version() == 1
+    assert lib.gadm_abi_version() == 2
     assert ctypes.sizeof(_lib.KnnJob) == 64
 
 
@@ -48,7 +48,8 @@ def test_error_codes_and_no_gpu_behaviour():
         assert lib.gadm_init(0) in (-5, -6)
         assert lib.gadm_knn_feat(None, 1, 1, 1, 1, 1, None, None) == -7
         assert lib.gadm_match_fwd(*([None] * 7), 1, 1, 8, 64, 1, ctypes.c_float(16.0), 0, 0,
-                                  *([None] * 5)) == -7
+                                  *([None] * 5), 0, None) == -7
+        assert lib.gadm_match_workspace_bytes() == 0
 
 
 def test_knn_workspace_planning_is_host_only():
