@@ -65,7 +65,6 @@ constexpr int STASH_BYTES = EPI_WARPS * 32 * GRP * 4;  // per epilogue thread: t
 constexpr int STASH_PLANE = EPI_WARPS * 32 * 16;       // float4 k of thread t lives at k * STASH_PLANE + t * 16
 static_assert(STASH_PLANE == 8192, "ptx::sts_stash8 hard-codes the plane stride");
 constexpr int TMEM_COLS = 512;
-constexpr float LAZY_TAU = 8.f;              // reference exponent is raised only when exceeded by more than this
 
 struct Barriers {
   uint64_t full[MAX_STAGES];
@@ -263,8 +262,6 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
 
     float vmax = -INFINITY;                 // running maximum of this thread's slice of the row
     int vgrp = 0;                           // first column of the 8-column group that first reached it
-    float mref = 0.f;
-    bool have_ref = false;
     // packed (even | odd column) partial sums, two independent chains each
     uint64_t l2a = 0, l2b = 0, ax2a = 0, ax2b = 0, ay2a = 0, ay2b = 0, az2a = 0, az2b = 0;
 
@@ -320,7 +317,6 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
             v[j] = ptx::pack2f(lo, hi);
           }
         }
-        float cmx = -INFINITY;
 #pragma unroll
         for (int h = 0; h < NG; ++h) {
           float f[GRP];
@@ -333,31 +329,18 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
           ptx::sts_stash8(up, stash_addr, v[h * 4 + 0], v[h * 4 + 1], v[h * 4 + 2], v[h * 4 + 3]);
           vgrp = up ? col_base + col0 + h * GRP : vgrp;
           vmax = up ? gm : vmax;
-          if (kSoft) cmx = h == 0 ? gm : fmaxf(cmx, gm);
         }
         if (kSoft) {
-          const float tnew = cmx * g;
-          if (!have_ref) { mref = tnew; have_ref = true; }   // warp-uniform: first valid chunk of the slice
-          if (__any_sync(0xffffffffu, tnew > mref + LAZY_TAU)) {
-            // rare: raise the reference exponent and rescale the running sums
-            const bool need = tnew > mref + LAZY_TAU;
-            const float s = need ? ptx::ex2_approx(mref - tnew) : 1.f;
-            const uint64_t s2 = ptx::pack2f(s, s);
-            l2a = ptx::fmul2(l2a, s2); l2b = ptx::fmul2(l2b, s2);
-            ax2a = ptx::fmul2(ax2a, s2); ax2b = ptx::fmul2(ax2b, s2);
-            ay2a = ptx::fmul2(ay2a, s2); ay2b = ptx::fmul2(ay2b, s2);
-            az2a = ptx::fmul2(az2a, s2); az2b = ptx::fmul2(az2b, s2);
-            mref = need ? tnew : mref;
-          }
-          // p = 2^(v*g - m_ref); sums in packed f32x2 (even | odd column)
-          const uint64_t g2 = ptx::pack2f(g, g), nm2 = ptx::pack2f(-mref, -mref);
+          // p = 2^(v*g), no reference exponent: |v*g| <= |gamma| log2(e) <= 58 (gadm_match_fwd admits |gamma| <= 40),
+          // so p and its sums stay inside the fp32 range; sums in packed f32x2 (even | odd column)
+          const uint64_t g2 = ptx::pack2f(g, g);
 #pragma unroll
           for (int j4 = 0; j4 < W / 4; ++j4) {
             const float4 X = ptx::lds128(sc + PLANE_BYTES + j4 * 16);
             const float4 Y = ptx::lds128(sc + 2 * PLANE_BYTES + j4 * 16);
             const float4 Z = ptx::lds128(sc + 3 * PLANE_BYTES + j4 * 16);
-            const uint64_t p01 = ptx::ex2_2(ptx::ffma2(v[j4 * 2 + 0], g2, nm2));
-            const uint64_t p23 = ptx::ex2_2(ptx::ffma2(v[j4 * 2 + 1], g2, nm2));
+            const uint64_t p01 = ptx::ex2_2(ptx::fmul2(v[j4 * 2 + 0], g2));
+            const uint64_t p23 = ptx::ex2_2(ptx::fmul2(v[j4 * 2 + 1], g2));
             l2a = ptx::fadd2(l2a, p01);
             l2b = ptx::fadd2(l2b, p23);
             ax2a = ptx::ffma2(p01, ptx::pack2f(X.x, X.y), ax2a);
@@ -433,24 +416,21 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
       ptx::unpack2f(ptx::fadd2(ax2a, ax2b), e, o); ax = e + o;
       ptx::unpack2f(ptx::fadd2(ay2a, ay2b), e, o); ay = e + o;
       ptx::unpack2f(ptx::fadd2(az2a, az2b), e, o); az = e + o;
-      if (!have_ref) mref = -INFINITY;
     }
     float* xch = reinterpret_cast<float*>(smem_a + rt * p.KB * A_BLK_BYTES);   // (SL - 1) * 128 * 32 B <= 16 KB
     if (sub > 0) {
       float* x = xch + ((sub - 1) * BM + row_in_tile) * 8;
-      x[0] = vmax; x[1] = __int_as_float(vidx); x[2] = mref; x[3] = lsum;
+      x[0] = vmax; x[1] = __int_as_float(vidx); x[3] = lsum;
       x[4] = ax; x[5] = ay; x[6] = az;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
     if (sub == 0 && row_ok) {
-      float mm = mref;
 #pragma unroll
       for (int s2 = 0; s2 < SL - 1; ++s2) {
         const float* x = xch + (s2 * BM + row_in_tile) * 8;
         const float v1 = x[0];
         const int i1 = __float_as_int(x[1]);
         if (v1 > vmax || (v1 == vmax && i1 < vidx)) { vmax = v1; vidx = i1; }
-        mm = fmaxf(mm, x[2]);
       }
       const bool keep = p.mask == nullptr || p.mask[grow] != 0;
       float best = vmax * rs;
@@ -462,16 +442,14 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
       p.idx[grow] = keep ? best_idx : int64_t(-1);
       p.max_sim[grow] = keep ? best : 0.f;
       if (kSoft) {
-        const float s0 = ptx::ex2_approx(mref - mm);  // exp2(-inf) = 0 for a slice that saw no column
-        float l = lsum * s0, sx = ax * s0, sy = ay * s0, sz = az * s0;
+        float l = lsum, sx = ax, sy = ay, sz = az;
 #pragma unroll
         for (int s2 = 0; s2 < SL - 1; ++s2) {
           const float* x = xch + (s2 * BM + row_in_tile) * 8;
-          const float s1 = ptx::ex2_approx(x[2] - mm);
-          l = fmaf(x[3], s1, l); sx = fmaf(x[4], s1, sx); sy = fmaf(x[5], s1, sy); sz = fmaf(x[6], s1, sz);
+          l += x[3]; sx += x[4]; sy += x[5]; sz += x[6];
         }
         const float inv = 1.f / l;
-        p.weight[grow] = keep ? ptx::ex2_approx(fmaf(vmax, g, -mm)) * inv : 0.f;  // softmax value at the maximum
+        p.weight[grow] = keep ? ptx::ex2_approx(vmax * g) * inv : 0.f;  // softmax value at the maximum
         p.soft_xyz[grow * 3 + 0] = keep ? sx * inv : 0.f;
         p.soft_xyz[grow * 3 + 1] = keep ? sy * inv : 0.f;
         p.soft_xyz[grow * 3 + 2] = keep ? sz * inv : 0.f;
@@ -663,8 +641,6 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
 
     float vmax[2] = {-INFINITY, -INFINITY};
     int vgrp[2] = {0, 0};
-    float mref[2] = {0.f, 0.f};
-    bool have_ref = false;                  // both rows see their first valid chunk together
     uint64_t l2[2] = {0, 0}, ax2[2] = {0, 0}, ay2[2] = {0, 0}, az2[2] = {0, 0};   // packed (even | odd column)
 
     for (int t = 0; t < num_tiles; ++t) {
@@ -709,10 +685,8 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
               v[rr][j] = ptx::pack2f(lo, hi);
             }
         }
-        float cmx[2];
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-          cmx[rr] = -INFINITY;
 #pragma unroll
           for (int h = 0; h < W / GRP; ++h) {
             float f[GRP];
@@ -725,26 +699,11 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
                             v[rr][h * 4 + 2], v[rr][h * 4 + 3]);
             vgrp[rr] = up ? col_base + col0 + h * GRP : vgrp[rr];
             vmax[rr] = up ? gm : vmax[rr];
-            if (kSoft) cmx[rr] = fmaxf(cmx[rr], gm);
           }
         }
         if (kSoft) {
-          const float tn0 = cmx[0] * g[0], tn1 = cmx[1] * g[1];
-          if (!have_ref) { mref[0] = tn0; mref[1] = tn1; have_ref = true; }
-          if (__any_sync(0xffffffffu, tn0 > mref[0] + LAZY_TAU || tn1 > mref[1] + LAZY_TAU)) {
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-              const float tn = rr ? tn1 : tn0;
-              const bool need = tn > mref[rr] + LAZY_TAU;
-              const float s = need ? ptx::ex2_approx(mref[rr] - tn) : 1.f;
-              const uint64_t s2 = ptx::pack2f(s, s);
-              l2[rr] = ptx::fmul2(l2[rr], s2); ax2[rr] = ptx::fmul2(ax2[rr], s2);
-              ay2[rr] = ptx::fmul2(ay2[rr], s2); az2[rr] = ptx::fmul2(az2[rr], s2);
-              mref[rr] = need ? tn : mref[rr];
-            }
-          }
+          // p = 2^(v*g), no reference exponent (see match_kernel)
           const uint64_t g20 = ptx::pack2f(g[0], g[0]), g21 = ptx::pack2f(g[1], g[1]);
-          const uint64_t nm0 = ptx::pack2f(-mref[0], -mref[0]), nm1 = ptx::pack2f(-mref[1], -mref[1]);
 #pragma unroll
           for (int j4 = 0; j4 < W / 4; ++j4) {
             const float4 X = ptx::lds128(sc + P_PLANE_BYTES + j4 * 16);
@@ -753,10 +712,10 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
             const uint64_t X01 = ptx::pack2f(X.x, X.y), X23 = ptx::pack2f(X.z, X.w);
             const uint64_t Y01 = ptx::pack2f(Y.x, Y.y), Y23 = ptx::pack2f(Y.z, Y.w);
             const uint64_t Z01 = ptx::pack2f(Z.x, Z.y), Z23 = ptx::pack2f(Z.z, Z.w);
-            const uint64_t pa0 = ptx::ex2_2(ptx::ffma2(v[0][j4 * 2 + 0], g20, nm0));
-            const uint64_t pb0 = ptx::ex2_2(ptx::ffma2(v[0][j4 * 2 + 1], g20, nm0));
-            const uint64_t pa1 = ptx::ex2_2(ptx::ffma2(v[1][j4 * 2 + 0], g21, nm1));
-            const uint64_t pb1 = ptx::ex2_2(ptx::ffma2(v[1][j4 * 2 + 1], g21, nm1));
+            const uint64_t pa0 = ptx::ex2_2(ptx::fmul2(v[0][j4 * 2 + 0], g20));
+            const uint64_t pb0 = ptx::ex2_2(ptx::fmul2(v[0][j4 * 2 + 1], g20));
+            const uint64_t pa1 = ptx::ex2_2(ptx::fmul2(v[1][j4 * 2 + 0], g21));
+            const uint64_t pb1 = ptx::ex2_2(ptx::fmul2(v[1][j4 * 2 + 1], g21));
             l2[0] = ptx::fadd2(l2[0], ptx::fadd2(pa0, pb0));
             l2[1] = ptx::fadd2(l2[1], ptx::fadd2(pa1, pb1));
             ax2[0] = ptx::ffma2(pb0, X23, ptx::ffma2(pa0, X01, ax2[0]));
@@ -830,7 +789,6 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
         ptx::unpack2f(ax2[rr], e, o); ax[rr] = e + o;
         ptx::unpack2f(ay2[rr], e, o); ay[rr] = e + o;
         ptx::unpack2f(az2[rr], e, o); az[rr] = e + o;
-        if (!have_ref) mref[rr] = -INFINITY;
       }
     }
     // exchange buffers alias the row tiles' own A blocks (all MMAs have completed: the last s_full was seen)
@@ -839,7 +797,7 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
       float* xch = reinterpret_cast<float*>(smem_a + rr * p.KB * A_BLK_BYTES);   // 3 * 128 * 32 B = 12 KB <= 16 KB
       if (sub > 0) {
         float* x = xch + ((sub - 1) * BM + row_in_tile) * 8;
-        x[0] = vmax[rr]; x[1] = __int_as_float(vidx[rr]); x[2] = mref[rr]; x[3] = lsum[rr];
+        x[0] = vmax[rr]; x[1] = __int_as_float(vidx[rr]); x[3] = lsum[rr];
         x[4] = ax[rr]; x[5] = ay[rr]; x[6] = az[rr];
       }
     }
@@ -849,7 +807,7 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
       for (int rr = 0; rr < 2; ++rr) {
         if (!row_ok[rr]) continue;
         const float* xch = reinterpret_cast<const float*>(smem_a + rr * p.KB * A_BLK_BYTES);
-        float vm = vmax[rr], mm = mref[rr];
+        float vm = vmax[rr];
         int vi = vidx[rr];
 #pragma unroll
         for (int s2 = 0; s2 < 3; ++s2) {
@@ -857,7 +815,6 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
           const float v1 = x[0];
           const int i1 = __float_as_int(x[1]);
           if (v1 > vm || (v1 == vm && i1 < vi)) { vm = v1; vi = i1; }
-          mm = fmaxf(mm, x[2]);
         }
         const size_t gr = grow[rr];
         const bool keep = p.mask == nullptr || p.mask[gr] != 0;
@@ -870,16 +827,14 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
         p.idx[gr] = keep ? best_idx : int64_t(-1);
         p.max_sim[gr] = keep ? best : 0.f;
         if (kSoft) {
-          const float s0 = ptx::ex2_approx(mref[rr] - mm);
-          float l = lsum[rr] * s0, sx = ax[rr] * s0, sy = ay[rr] * s0, sz = az[rr] * s0;
+          float l = lsum[rr], sx = ax[rr], sy = ay[rr], sz = az[rr];
 #pragma unroll
           for (int s2 = 0; s2 < 3; ++s2) {
             const float* x = xch + (s2 * BM + row_in_tile) * 8;
-            const float s1 = ptx::ex2_approx(x[2] - mm);
-            l = fmaf(x[3], s1, l); sx = fmaf(x[4], s1, sx); sy = fmaf(x[5], s1, sy); sz = fmaf(x[6], s1, sz);
+            l += x[3]; sx += x[4]; sy += x[5]; sz += x[6];
           }
           const float inv = 1.f / l;
-          p.weight[gr] = keep ? ptx::ex2_approx(fmaf(vm, g[rr], -mm)) * inv : 0.f;
+          p.weight[gr] = keep ? ptx::ex2_approx(vm * g[rr]) * inv : 0.f;
           p.soft_xyz[gr * 3 + 0] = keep ? sx * inv : 0.f;
           p.soft_xyz[gr * 3 + 1] = keep ? sy * inv : 0.f;
           p.soft_xyz[gr * 3 + 2] = keep ? sz * inv : 0.f;
@@ -1321,6 +1276,281 @@ int match_frag_stages(int RT, int KB) {
   return stages;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Alternating variant of match_kernel<ARGMAX, 2>.  There, accumulator r belongs to 8 fixed epilogue warps, so an
+// accumulator's MMAs wait for its own epilogue and its epilogue warps idle while it is refilled: the period of a
+// model tile is T_mma + E_8warps.  Here ALL 16 epilogue warps drain accumulator 0 (row tile 0) while the tensor
+// core fills accumulator 1 (row tile 1) with the same model tile, then swap: the period is 2 max(T_mma, E_16warps)
+// and the epilogue never idles -- the double buffering of RT = 1 with the halved L2 operand traffic of RT = 2.
+// A thread owns one row of each row tile (TMEM lane q * 32 + lane) and the 64-column slice w / 4 of every tile.
+// Two stash entries per thread (32 KB per CTA) do not fit beside the operands: the stash lives in the per-SM
+// workspace slot (predicated, coalesced STG.128; only the storing thread reads it back).
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
+                 const MatchParams p) {
+  constexpr int RT = 2;
+  constexpr int AUX_BYTES = PLANE_BYTES;
+  constexpr int SL = 4;                      // column slices per row
+  constexpr int CS = BN / SL;                // 64 columns per slice
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                                    // [RT][KB] blocks of 128 rows x 64 k
+  uint8_t* smem_b = smem_a + RT * p.KB * A_BLK_BYTES;
+  uint8_t* smem_aux = smem_b + p.stages * B_STAGE_BYTES;   // per slot: 1/|m| x256
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_aux + AUX_SLOTS * AUX_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int row0 = blockIdx.x * (BM * RT);
+  const int obj = frame_object(p, b);
+  const int num_tiles = (p.M + BN - 1) / BN;
+
+  if (warp == EPI_WARPS && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_rows);
+    ptx::prefetch_tensormap(&tmap_cols);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&bars->full[s], 1);
+      ptx::mbar_init(&bars->empty[s], 1);
+    }
+    ptx::mbar_init(&bars->a_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&bars->s_full[a], 1);
+      ptx::mbar_init(&bars->s_free[a], EPI_WARPS);   // every epilogue warp drains every accumulator
+    }
+    for (int a = 0; a < AUX_SLOTS; ++a) {
+      ptx::mbar_init(&bars->aux_full[a], 1);
+      ptx::mbar_init(&bars->aux_empty[a], EPI_WARPS);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == EPI_WARPS + 1) {
+    ptx::tmem_alloc(&bars->tmem_base, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == EPI_WARPS) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(&bars->a_full, RT * p.KB * A_BLK_BYTES);
+      for (int r = 0; r < RT; ++r)
+        for (int kb = 0; kb < p.KB; ++kb)
+          ptx::tma_load_3d(smem_a + (r * p.KB + kb) * A_BLK_BYTES, &tmap_rows, &bars->a_full, kb * BK,
+                           row0 + r * BM, b);   // rows >= N are zero-filled by TMA
+      int stage = 0;
+      uint32_t phase = 0;
+      const float* sc_tab = p.scales + size_t(obj) * p.M;
+      for (int t = 0; t < num_tiles; ++t) {
+        const int slot = t % AUX_SLOTS;
+        const uint32_t use = uint32_t(t) / AUX_SLOTS;
+        const uint32_t bytes = uint32_t(min(BN, p.M - t * BN)) * 4;   // M % 8 == 0: a multiple of 16
+        ptx::mbar_wait_sleep(&bars->aux_empty[slot], (use & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&bars->aux_full[slot], bytes);
+        ptx::bulk_load_1d(smem_aux + slot * AUX_BYTES, sc_tab + size_t(t) * BN, bytes, &bars->aux_full[slot]);
+        for (int kb = 0; kb < p.KB; ++kb) {
+          ptx::mbar_wait_sleep(&bars->empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&bars->full[stage], B_STAGE_BYTES);
+          ptx::tma_load_3d(smem_b + stage * B_STAGE_BYTES, &tmap_cols, &bars->full[stage], kb * BK, t * BN, obj);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == EPI_WARPS + 1) {
+    // ============================== UMMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(BM, BN);
+      ptx::mbar_wait(&bars->a_full, 0);
+      int stage0 = 0;            // ring position of the tile's first K block
+      uint32_t phase0 = 0;
+      for (int t = 0; t < num_tiles; ++t) {
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          ptx::mbar_wait_sleep(&bars->s_free[r], (uint32_t(t) & 1) ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + r * BN;
+          int stage = stage0;
+          uint32_t phase = phase0;
+          for (int kb = 0; kb < p.KB; ++kb) {
+            if (r == 0) {      // the stages of this tile stay resident until the last row tile has used them
+              ptx::mbar_wait_sleep(&bars->full[stage], phase);
+              ptx::tc_fence_after();
+            }
+            const uint32_t a_addr = ptx::smem_u32(smem_a + (r * p.KB + kb) * A_BLK_BYTES);
+            const uint32_t b_addr = ptx::smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              ptx::umma_bf16_ss(d_tmem, ptx::umma_desc_sw128_kmajor(a_addr + k * UMMA_K * 2),
+                                ptx::umma_desc_sw128_kmajor(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0);
+            }
+            if (r == RT - 1) ptx::umma_commit(&bars->empty[stage]);  // frees the stage once these MMAs have read it
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          ptx::umma_commit(&bars->s_full[r]);     // accumulator tile complete
+          if (r == RT - 1) { stage0 = stage; phase0 = phase; }
+        }
+      }
+    }
+  } else {
+    // ============================== epilogue warps (thread == one row of each row tile) ==============
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access (warp id % 4)
+    const int sub = warp >> 2;                       // 64-column slice of every tile
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16) + sub * CS;
+    if (ptx::smid() >= uint32_t(p.stash_slots)) __trap();
+    // stash entry of row tile r, float4 k: + (2 r + k) * 8192 (plane-major: coalesced 512-byte warp stores)
+    uint8_t* stash = p.stash + size_t(ptx::smid()) * FRAG_STASH_BYTES + threadIdx.x * 16;
+
+    float vmax[RT] = {-INFINITY, -INFINITY};   // running maximum of this thread's slice of its row of row tile r
+    int vgrp[RT] = {0, 0};                     // first column of the 8-column group that first reached it
+
+    for (int t = 0; t < num_tiles; ++t) {
+      const int slot = t % AUX_SLOTS;
+      const int ncols = min(BN, p.M - t * BN) - sub * CS;   // valid columns of this slice (may be <= 0)
+      const uint32_t sc_addr = ptx::smem_u32(smem_aux + slot * AUX_BYTES) + sub * CS * 4;
+      const int col_base = t * BN + sub * CS;
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        if (!((r > 0 || ptx::mbar_try_wait(&bars->aux_full[slot], (uint32_t(t) / AUX_SLOTS) & 1)) &
+              ptx::mbar_try_wait(&bars->s_full[r], uint32_t(t) & 1))) {
+          if (r == 0) ptx::mbar_wait_sleep(&bars->aux_full[slot], (uint32_t(t) / AUX_SLOTS) & 1);
+          ptx::mbar_wait_sleep(&bars->s_full[r], uint32_t(t) & 1);
+        }
+        ptx::tc_fence_after();
+        const uint32_t s_tmem = lane_base + r * BN;
+
+        // one chunk of 32 columns starting at slice column col0 (see match_kernel)
+        auto process = [&](uint32_t (&d)[32], int col0, auto guard_tag) {
+          constexpr bool kGuard = decltype(guard_tag)::value;
+          const uint32_t sc = sc_addr + col0 * 4;
+          uint64_t v[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 cm = ptx::lds128(sc + j4 * 16);
+            v[j4 * 2 + 0] = ptx::fmul2(ptx::pack2(d[j4 * 4 + 0], d[j4 * 4 + 1]), ptx::pack2f(cm.x, cm.y));
+            v[j4 * 2 + 1] = ptx::fmul2(ptx::pack2(d[j4 * 4 + 2], d[j4 * 4 + 3]), ptx::pack2f(cm.z, cm.w));
+          }
+          if (kGuard) {  // TMA zero-fills columns >= M and the stale scales behind them are meaningless
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float lo, hi;
+              ptx::unpack2f(v[j], lo, hi);
+              if (col0 + 2 * j >= ncols) lo = -INFINITY;
+              if (col0 + 2 * j + 1 >= ncols) hi = -INFINITY;
+              v[j] = ptx::pack2f(lo, hi);
+            }
+          }
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            float f[GRP];
+#pragma unroll
+            for (int j = 0; j < GRP / 2; ++j) ptx::unpack2f(v[h * 4 + j], f[2 * j], f[2 * j + 1]);
+            const float a0 = ptx::fmax3(f[0], f[1], f[2]), a1 = ptx::fmax3(f[3], f[4], f[5]);
+            const float gm = ptx::fmax3(a0, a1, fmaxf(f[6], f[7]));
+            // strict: an equal value in a later group never displaces the first maximal index
+            const bool up = gm > vmax[r];
+            ptx::stg_pred32(up, stash + r * 2 * 8192, v[h * 4 + 0], v[h * 4 + 1], v[h * 4 + 2], v[h * 4 + 3]);
+            vgrp[r] = up ? col_base + col0 + h * GRP : vgrp[r];
+            vmax[r] = up ? gm : vmax[r];
+          }
+        };
+        using guard_off = std::integral_constant<bool, false>;
+        using guard_on = std::integral_constant<bool, true>;
+
+        if (ncols > 0) {
+          uint32_t ra[32], rb[32];
+          ptx::tmem_ld_32x32(s_tmem, ra);
+          ptx::tmem_ld_32x32(s_tmem + 32, rb);
+          ptx::tmem_ld_wait();
+          if (ncols >= 32) process(ra, 0, guard_off{});
+          else process(ra, 0, guard_on{});         // ragged last tile
+          if (ncols > 32) {
+            if (ncols >= 64) process(rb, 32, guard_off{});
+            else process(rb, 32, guard_on{});
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(&bars->s_free[r]);
+          if (r == RT - 1) ptx::mbar_arrive(&bars->aux_empty[slot]);
+        }
+      }
+    }
+
+    // ---- per row tile: first maximal index of this slice from the stash (own stores, read back through L2), then
+    // the merge of the 4 column slices through shared memory (the row tile's own A blocks: all MMAs have completed)
+    int vidx[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      vidx[r] = 0;
+      if (vmax[r] > -INFINITY) {
+        int j_first = GRP - 1;
+#pragma unroll
+        for (int k = GRP / 4 - 1; k >= 0; --k) {
+          const float4 sv = ptx::ldg_cg128(stash + (r * 2 + k) * 8192);
+          if (sv.w == vmax[r]) j_first = 4 * k + 3;
+          if (sv.z == vmax[r]) j_first = 4 * k + 2;
+          if (sv.y == vmax[r]) j_first = 4 * k + 1;
+          if (sv.x == vmax[r]) j_first = 4 * k + 0;
+        }
+        vidx[r] = vgrp[r] + j_first;
+      }
+      if (sub > 0) {
+        float* x = reinterpret_cast<float*>(smem_a + r * p.KB * A_BLK_BYTES) + ((sub - 1) * BM + row_in_tile) * 2;
+        x[0] = vmax[r]; x[1] = __int_as_float(vidx[r]);
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+    if (sub == 0) {
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        const int row = row0 + r * BM + row_in_tile;
+        if (row >= p.N) continue;
+        const size_t grow = size_t(b) * p.N + row;
+        float vm = vmax[r];
+        int vi = vidx[r];
+#pragma unroll
+        for (int s2 = 0; s2 < SL - 1; ++s2) {
+          const float* x = reinterpret_cast<const float*>(smem_a + r * p.KB * A_BLK_BYTES) + (s2 * BM + row_in_tile) * 2;
+          const float v1 = x[0];
+          const int i1 = __float_as_int(x[1]);
+          if (v1 > vm || (v1 == vm && i1 < vi)) { vm = v1; vi = i1; }
+        }
+        const bool keep = p.mask == nullptr || p.mask[grow] != 0;
+        float best = vm * p.rinv_rows[grow];
+        int64_t best_idx = vi;
+        if (p.pad_mode != GADM_PAD_NONE) {
+          const float ps = p.pad_sim[grow];
+          if (ps > best) { best = ps; best_idx = p.M; }  // pad column is the last one: wins only if strictly larger
+        }
+        p.idx[grow] = keep ? best_idx : int64_t(-1);
+        p.max_sim[grow] = keep ? best : 0.f;
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS + 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+inline size_t match_alt_smem_bytes(int KB, int stages) {
+  return size_t(2) * KB * A_BLK_BYTES + size_t(stages) * B_STAGE_BYTES + AUX_SLOTS * PLANE_BYTES + sizeof(Barriers) + 1024;
+}
+inline int match_alt_stages(int KB) {
+  int stages = MAX_STAGES;
+  while (stages > 0 && match_alt_smem_bytes(KB, stages) > 227 * 1024) --stages;
+  return stages;
+}
+
 int g_stash_slots = 0;     // SM count of the device gadm_init() ran on (written once, read-only afterwards)
 
 }  // namespace
@@ -1338,6 +1568,8 @@ int match_configure() {
   e = cudaFuncSetAttribute(match_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
   e = cudaFuncSetAttribute(match_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(match_alt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
   e = cudaFuncSetAttribute(match_frag_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
@@ -1387,6 +1619,24 @@ static int match_launch_t(const void* rows, const void* cols, MatchParams p, int
         match_frag_kernel<kSoft, 2><<<grid, FRAG_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
       else
         match_frag_kernel<kSoft, 1><<<grid, FRAG_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+      return check_launch();
+    }
+  }
+  if (!kSoft) {
+    // alternating kernel (ARGMAX, needs the stash workspace, a ring of two resident model tiles and more than one
+    // row tile per frame).  GADM_MATCH_ALT=0 forbids it (profiling, tests).
+    bool alt = true;
+    if (const char* f = getenv("GADM_MATCH_ALT")) alt = atoi(f) != 0;
+    const int astages = match_alt_stages(KB);
+    if (alt && p.stash != nullptr && astages >= 2 * KB && p.N > BM) {
+      p.KB = KB; p.stages = astages;
+      CUtensorMap tmap_rows, tmap_cols;
+      int rc = make_tmap_2b_3d(&tmap_rows, rows, uint64_t(Kp), uint64_t(p.N), uint64_t(p.B), BK, BM, 0);
+      if (rc != GADM_OK) return rc;
+      rc = make_tmap_2b_3d(&tmap_cols, cols, uint64_t(Kp), uint64_t(p.M), uint64_t(p.n_obj), BK, BN, 0);
+      if (rc != GADM_OK) return rc;
+      dim3 grid((p.N + 2 * BM - 1) / (2 * BM), p.B);
+      match_alt_kernel<<<grid, NUM_THREADS, match_alt_smem_bytes(KB, astages), stream>>>(tmap_rows, tmap_cols, p);
       return check_launch();
     }
   }

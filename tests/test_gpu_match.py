@@ -186,13 +186,13 @@ def test_seg_mask_matches_torch_argmax(cuda):
     assert torch.equal(got.bool(), torch.argmax(seg, dim=1) == 1)
 
 
-@pytest.mark.parametrize("env", [{"GADM_MATCH_FRAG": "0", "GADM_MATCH_PAIR": "0", "GADM_MATCH_RT": "1"},
-                                 {"GADM_MATCH_FRAG": "0", "GADM_MATCH_PAIR": "0", "GADM_MATCH_RT": "2"},
-                                 {"GADM_MATCH_FRAG": "0", "GADM_MATCH_PAIR": "1"}, {"GADM_MATCH_FRAG": "1"},
-                                 {"GADM_MATCH_FRAG": "2"}])
+@pytest.mark.parametrize("env", [{"GADM_MATCH_ALT": "0", "GADM_MATCH_PAIR": "0", "GADM_MATCH_RT": "1"},
+                                 {"GADM_MATCH_ALT": "0", "GADM_MATCH_PAIR": "0", "GADM_MATCH_RT": "2"},
+                                 {"GADM_MATCH_ALT": "0", "GADM_MATCH_PAIR": "1"}, {"GADM_MATCH_ALT": "1"},
+                                 {"GADM_MATCH_FRAG": "1"}, {"GADM_MATCH_FRAG": "2"}])
 def test_match_kernel_variants_agree(cuda, monkeypatch, env):
-    """The kernels of the matcher (one row tile per CTA, two row tiles per CTA, paired rows per thread, fragment
-    layout with four rows per thread on one / two row tiles per CTA) are selected per launch; every one of them must meet the same gates
+    """The kernels of the matcher (one row tile per CTA, two row tiles per CTA, paired rows per thread, alternating
+    accumulators, fragment layout with four rows per thread on one / two row tiles per CTA) are selected per launch; every one of them must meet the same gates
     on a ragged shape, in both modes."""
     from gadm_b200 import matching, synth
     from oracle import match_oracle as mo
