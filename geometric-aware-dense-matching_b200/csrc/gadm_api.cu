@@ -103,7 +103,7 @@ int gadm_init(int device) {
 
 int gadm_operand_k(int d, int operand_mode) {
   if (d <= 0) return GADM_ERR_BAD_ARG;
-  if (operand_mode == GADM_OPERAND_BF16) return d;
+  if (operand_mode == GADM_OPERAND_BF16 || operand_mode == GADM_OPERAND_BF16N) return d;
   if (operand_mode == GADM_OPERAND_BF16X3) return 3 * d;
   return GADM_ERR_UNSUPPORTED;
 }
@@ -119,7 +119,7 @@ int gadm_prep_rows(const float* feat, int B, int d, int N, int operand_mode, int
   if (!feat || !rows || !rinv || B <= 0 || d <= 0 || N <= 0) return GADM_ERR_BAD_ARG;
   if (pad_mode != GADM_PAD_NONE && !pad_sim) return GADM_ERR_BAD_ARG;
   if (pad_mode < 0 || pad_mode > GADM_PAD_E0) return GADM_ERR_UNSUPPORTED;
-  if (operand_mode != GADM_OPERAND_BF16 && operand_mode != GADM_OPERAND_BF16X3) return GADM_ERR_UNSUPPORTED;
+  if (operand_mode < GADM_OPERAND_BF16 || operand_mode > GADM_OPERAND_BF16N) return GADM_ERR_UNSUPPORTED;
   if (d % 64 != 0 || d > 256) return GADM_ERR_UNSUPPORTED;
   if (!aligned16(rows)) return GADM_ERR_ALIGN;
   return prep_rows_launch(feat, B, d, N, operand_mode, pad_mode, rows, rinv, pad_sim, (cudaStream_t)stream);
@@ -129,7 +129,7 @@ int gadm_prep_model(const float* mesh, const float* model_xyz, int n_obj, int d,
                     float* aux, gadm_stream_t stream) {
   GADM_REQUIRE_INIT();
   if (!mesh || !cols || !aux || n_obj <= 0 || d <= 0 || M <= 0) return GADM_ERR_BAD_ARG;
-  if (operand_mode != GADM_OPERAND_BF16 && operand_mode != GADM_OPERAND_BF16X3) return GADM_ERR_UNSUPPORTED;
+  if (operand_mode < GADM_OPERAND_BF16 || operand_mode > GADM_OPERAND_BF16N) return GADM_ERR_UNSUPPORTED;
   if (d % 64 != 0 || d > 256 || M % 8 != 0) return GADM_ERR_UNSUPPORTED;
   if (!aligned16(cols) || !aligned16(aux)) return GADM_ERR_ALIGN;
   return prep_model_launch(mesh, model_xyz, n_obj, d, M, operand_mode, cols, aux, (cudaStream_t)stream);
@@ -144,7 +144,7 @@ int gadm_match_fwd(const void* rows, const float* rinv_rows, const float* pad_si
   if (workspace && !aligned16(workspace)) return GADM_ERR_ALIGN;
   if (B <= 0 || N <= 0 || M <= 0 || Kp <= 0 || n_obj <= 0) return GADM_ERR_BAD_ARG;
   if (B > 65535) return GADM_ERR_UNSUPPORTED;
-  if (mode != GADM_MATCH_ARGMAX && mode != GADM_MATCH_SOFT) return GADM_ERR_UNSUPPORTED;
+  if (mode < GADM_MATCH_ARGMAX || mode > GADM_MATCH_ARGMAX_UNIT) return GADM_ERR_UNSUPPORTED;
   if (mode == GADM_MATCH_SOFT && (!weight || !soft_xyz)) return GADM_ERR_BAD_ARG;
   // 2^(gamma log2(e) cos) is summed without a reference exponent: keep it well inside the fp32 range
   if (mode == GADM_MATCH_SOFT && !(gamma >= -40.f && gamma <= 40.f)) return GADM_ERR_UNSUPPORTED;

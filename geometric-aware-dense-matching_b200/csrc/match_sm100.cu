@@ -94,6 +94,7 @@ struct MatchParams {
   float gamma_log2e;
   uint8_t* stash;          // fragment-layout kernel: stash_slots slots of FRAG_STASH_BYTES (workspace), else null
   int stash_slots;
+  int unit_scales;         // GADM_MATCH_ARGMAX_UNIT: kernels that can, skip the column scales (the others apply them)
 };
 
 __device__ __forceinline__ int frame_object(const MatchParams& p, int b) {
@@ -1285,6 +1286,9 @@ int match_frag_stages(int RT, int KB) {
 // A thread owns one row of each row tile (TMEM lane q * 32 + lane) and the 64-column slice w / 4 of every tile.
 // Two stash entries per thread (32 KB per CTA) do not fit beside the operands: the stash lives in the per-SM
 // workspace slot (predicated, coalesced STG.128; only the storing thread reads it back).
+// kUnit (GADM_MATCH_ARGMAX_UNIT, operands from GADM_OPERAND_BF16N): the column norms are taken as 1, the epilogue
+// needs no per-column constant at all -- no aux ring, no LDS, no multiply.
+template <bool kUnit>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
                  const MatchParams p) {
@@ -1349,9 +1353,11 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
         const int slot = t % AUX_SLOTS;
         const uint32_t use = uint32_t(t) / AUX_SLOTS;
         const uint32_t bytes = uint32_t(min(BN, p.M - t * BN)) * 4;   // M % 8 == 0: a multiple of 16
-        ptx::mbar_wait_sleep(&bars->aux_empty[slot], (use & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(&bars->aux_full[slot], bytes);
-        ptx::bulk_load_1d(smem_aux + slot * AUX_BYTES, sc_tab + size_t(t) * BN, bytes, &bars->aux_full[slot]);
+        if (!kUnit) {
+          ptx::mbar_wait_sleep(&bars->aux_empty[slot], (use & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&bars->aux_full[slot], bytes);
+          ptx::bulk_load_1d(smem_aux + slot * AUX_BYTES, sc_tab + size_t(t) * BN, bytes, &bars->aux_full[slot]);
+        }
         for (int kb = 0; kb < p.KB; ++kb) {
           ptx::mbar_wait_sleep(&bars->empty[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&bars->full[stage], B_STAGE_BYTES);
@@ -1415,9 +1421,9 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
       const int col_base = t * BN + sub * CS;
 #pragma unroll
       for (int r = 0; r < RT; ++r) {
-        if (!((r > 0 || ptx::mbar_try_wait(&bars->aux_full[slot], (uint32_t(t) / AUX_SLOTS) & 1)) &
+        if (!((kUnit || r > 0 || ptx::mbar_try_wait(&bars->aux_full[slot], (uint32_t(t) / AUX_SLOTS) & 1)) &
               ptx::mbar_try_wait(&bars->s_full[r], uint32_t(t) & 1))) {
-          if (r == 0) ptx::mbar_wait_sleep(&bars->aux_full[slot], (uint32_t(t) / AUX_SLOTS) & 1);
+          if (!kUnit && r == 0) ptx::mbar_wait_sleep(&bars->aux_full[slot], (uint32_t(t) / AUX_SLOTS) & 1);
           ptx::mbar_wait_sleep(&bars->s_full[r], uint32_t(t) & 1);
         }
         ptx::tc_fence_after();
@@ -1430,9 +1436,14 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
           uint64_t v[16];
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 cm = ptx::lds128(sc + j4 * 16);
-            v[j4 * 2 + 0] = ptx::fmul2(ptx::pack2(d[j4 * 4 + 0], d[j4 * 4 + 1]), ptx::pack2f(cm.x, cm.y));
-            v[j4 * 2 + 1] = ptx::fmul2(ptx::pack2(d[j4 * 4 + 2], d[j4 * 4 + 3]), ptx::pack2f(cm.z, cm.w));
+            if (kUnit) {
+              v[j4 * 2 + 0] = ptx::pack2(d[j4 * 4 + 0], d[j4 * 4 + 1]);
+              v[j4 * 2 + 1] = ptx::pack2(d[j4 * 4 + 2], d[j4 * 4 + 3]);
+            } else {
+              const float4 cm = ptx::lds128(sc + j4 * 16);
+              v[j4 * 2 + 0] = ptx::fmul2(ptx::pack2(d[j4 * 4 + 0], d[j4 * 4 + 1]), ptx::pack2f(cm.x, cm.y));
+              v[j4 * 2 + 1] = ptx::fmul2(ptx::pack2(d[j4 * 4 + 2], d[j4 * 4 + 3]), ptx::pack2f(cm.z, cm.w));
+            }
           }
           if (kGuard) {  // TMA zero-fills columns >= M and the stale scales behind them are meaningless
 #pragma unroll
@@ -1477,7 +1488,7 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
         __syncwarp();
         if (lane == 0) {
           ptx::mbar_arrive(&bars->s_free[r]);
-          if (r == RT - 1) ptx::mbar_arrive(&bars->aux_empty[slot]);
+          if (!kUnit && r == RT - 1) ptx::mbar_arrive(&bars->aux_empty[slot]);
         }
       }
     }
@@ -1521,6 +1532,8 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
           const int i1 = __float_as_int(x[1]);
           if (v1 > vm || (v1 == vm && i1 < vi)) { vm = v1; vi = i1; }
         }
+        // kUnit searched with unit column norms; the winner's similarity is reported with its true scale
+        if (kUnit) vm *= p.scales[size_t(obj) * p.M + vi];
         const bool keep = p.mask == nullptr || p.mask[grow] != 0;
         float best = vm * p.rinv_rows[grow];
         int64_t best_idx = vi;
@@ -1569,7 +1582,9 @@ int match_configure() {
   if (e != cudaSuccess) return set_cuda_error(e);
   e = cudaFuncSetAttribute(match_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
-  e = cudaFuncSetAttribute(match_alt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(match_alt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(match_alt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
   e = cudaFuncSetAttribute(match_frag_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
@@ -1636,7 +1651,10 @@ static int match_launch_t(const void* rows, const void* cols, MatchParams p, int
       rc = make_tmap_2b_3d(&tmap_cols, cols, uint64_t(Kp), uint64_t(p.M), uint64_t(p.n_obj), BK, BN, 0);
       if (rc != GADM_OK) return rc;
       dim3 grid((p.N + 2 * BM - 1) / (2 * BM), p.B);
-      match_alt_kernel<<<grid, NUM_THREADS, match_alt_smem_bytes(KB, astages), stream>>>(tmap_rows, tmap_cols, p);
+      if (p.unit_scales)
+        match_alt_kernel<true><<<grid, NUM_THREADS, match_alt_smem_bytes(KB, astages), stream>>>(tmap_rows, tmap_cols, p);
+      else
+        match_alt_kernel<false><<<grid, NUM_THREADS, match_alt_smem_bytes(KB, astages), stream>>>(tmap_rows, tmap_cols, p);
       return check_launch();
     }
   }
@@ -1702,6 +1720,7 @@ int match_launch(const void* rows, const float* rinv_rows, const float* pad_sim,
   p.idx = idx; p.max_sim = max_sim; p.weight = weight; p.soft_xyz = soft_xyz;
   p.B = B; p.N = N; p.M = M; p.KB = 0; p.n_obj = n_obj; p.stages = 0; p.pad_mode = pad_mode;
   p.gamma_log2e = gamma * 1.4426950408889634f;
+  p.unit_scales = mode == GADM_MATCH_ARGMAX_UNIT;
   if (mode == GADM_MATCH_SOFT) return match_launch_t<true>(rows, cols, p, Kp, stream);
   return match_launch_t<false>(rows, cols, p, Kp, stream);
 }

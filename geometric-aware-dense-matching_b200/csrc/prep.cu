@@ -18,7 +18,7 @@ constexpr int PTS = 32;  // points per CTA (one 128-byte line of every channel r
 // side: 0 = scene rows ([hi|hi|lo] in x3 mode), 1 = model columns ([hi|lo|hi] in x3 mode)
 template <int kSide>
 __global__ void __launch_bounds__(256)
-prep_kernel(const float* __restrict__ src, const float* __restrict__ xyz, int d, int P, int x3, int pad_mode,
+prep_kernel(const float* __restrict__ src, const float* __restrict__ xyz, int d, int P, int x3, int prenorm, int pad_mode,
             __nv_bfloat16* __restrict__ dst, float* __restrict__ rinv, float* __restrict__ pad_sim,
             float* __restrict__ aux_scale, float* __restrict__ aux_xyz, float* __restrict__ aux_planes, size_t plane) {
   extern __shared__ float tile[];  // [d][PTS + 1]
@@ -39,8 +39,19 @@ prep_kernel(const float* __restrict__ src, const float* __restrict__ xyz, int d,
     if (p >= P) break;  // warp-uniform
     float ss = 0.f, sum = 0.f;
     __nv_bfloat16* out = dst + (size_t(g) * P + p) * Kp;
+    float pre = 1.f;
+    if (kSide == 1 && prenorm) {   // BF16N: F.normalize in fp32 first, then the one rounding to bf16
+      float s2 = 0.f;
+      for (int c = lane; c < d; c += 32) {
+        const float v = tile[c * (PTS + 1) + pl];
+        s2 = fmaf(v, v, s2);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      pre = 1.f / fmaxf(sqrtf(s2), 1e-12f);
+    }
     for (int c = lane * 2; c < d; c += 64) {
-      const float v0 = tile[c * (PTS + 1) + pl], v1 = tile[(c + 1) * (PTS + 1) + pl];
+      const float v0 = tile[c * (PTS + 1) + pl] * pre, v1 = tile[(c + 1) * (PTS + 1) + pl] * pre;
       const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
       const float f0 = __bfloat162float(h0), f1 = __bfloat162float(h1);
       __nv_bfloat162 hi;
@@ -157,7 +168,7 @@ int prep_rows_launch(const float* feat, int B, int d, int N, int operand_mode, i
                      float* pad_sim, cudaStream_t stream) {
   dim3 grid((N + PTS - 1) / PTS, B);
   const size_t smem = size_t(d) * (PTS + 1) * sizeof(float);
-  prep_kernel<0><<<grid, 256, smem, stream>>>(feat, nullptr, d, N, operand_mode == GADM_OPERAND_BF16X3, pad_mode,
+  prep_kernel<0><<<grid, 256, smem, stream>>>(feat, nullptr, d, N, operand_mode == GADM_OPERAND_BF16X3, 0, pad_mode,
                                               static_cast<__nv_bfloat16*>(rows), rinv, pad_sim, nullptr, nullptr, nullptr, 0);
   return check_launch();
 }
@@ -169,7 +180,8 @@ int prep_model_launch(const float* mesh, const float* model_xyz, int n_obj, int 
   const size_t plane = size_t(n_obj) * M;
   float* a_xyz = aux + plane;
   float* a_planes = aux + plane * 4;
-  prep_kernel<1><<<grid, 256, smem, stream>>>(mesh, model_xyz, d, M, operand_mode == GADM_OPERAND_BF16X3, 0,
+  prep_kernel<1><<<grid, 256, smem, stream>>>(mesh, model_xyz, d, M, operand_mode == GADM_OPERAND_BF16X3,
+                                              operand_mode == GADM_OPERAND_BF16N, 0,
                                               static_cast<__nv_bfloat16*>(cols), nullptr, nullptr, aux, a_xyz, a_planes, plane);
   return check_launch();
 }

@@ -67,12 +67,21 @@ const char* gadm_last_cuda_error(void);
 enum { GADM_PAD_NONE = 0, GADM_PAD_MINUS_ONE = 1, GADM_PAD_E0 = 2 };
 /* operand_mode: how fp32 descriptors become bf16 tensor-core operands.
  *   BF16   : round once to bf16 (exact if the inputs are bf16-representable); K' = d
- *   BF16X3 : hi/lo split, operands [hi|hi|lo] x [hi|lo|hi]; K' = 3d; ~fp32-faithful (error ~1e-6)  */
-enum { GADM_OPERAND_BF16 = 0, GADM_OPERAND_BF16X3 = 1 };
-/* outputs: ARGMAX = idx + max_sim only (the reference's path); SOFT adds weight + soft_xyz. */
-enum { GADM_MATCH_ARGMAX = 0, GADM_MATCH_SOFT = 1 };
+ *   BF16X3 : hi/lo split, operands [hi|hi|lo] x [hi|lo|hi]; K' = 3d; ~fp32-faithful (error ~1e-6)
+ *   BF16N  : model columns are L2-normalised in fp32 (F.normalize, evaluator.py:90) BEFORE the single rounding
+ *            to bf16; scene rows as BF16; K' = d.  The column scales in `aux` become 1/||bf16 column|| = 1 +- ~2e-4,
+ *            so every mode stays exact with respect to the rounded operands, and GADM_MATCH_ARGMAX_UNIT may
+ *            drop the scales altogether.                                                              */
+enum { GADM_OPERAND_BF16 = 0, GADM_OPERAND_BF16X3 = 1, GADM_OPERAND_BF16N = 2 };
+/* outputs: ARGMAX = idx + max_sim only (the reference's path); SOFT adds weight + soft_xyz.
+ * ARGMAX_UNIT = ARGMAX for operands prepared with GADM_OPERAND_BF16N, treating the column norms as exactly 1
+ * DURING THE SEARCH (no per-column constant in the epilogue: the fastest kernel); the winner's similarity is
+ * reported with its true scale.  The searched scores differ from ARGMAX's by the factor ||bf16 column|| =
+ * 1 +- 2^-8 at most (~3e-4 rms at d = 128), so the index can differ from ARGMAX's only on rows whose top-1
+ * margin is below |score| * 2^-7; falls back to ARGMAX when the unit kernel does not apply.                 */
+enum { GADM_MATCH_ARGMAX = 0, GADM_MATCH_SOFT = 1, GADM_MATCH_ARGMAX_UNIT = 2 };
 
-/* K' for a given d / operand_mode (d for BF16, 3d for BF16X3). */
+/* K' for a given d / operand_mode (d for BF16 and BF16N, 3d for BF16X3). */
 int gadm_operand_k(int d, int operand_mode);
 
 /* Scene side.  feat [B, d, N] fp32 channel-major (end_points['rgbd'], models/geoMatch.py:199).

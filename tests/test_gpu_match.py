@@ -210,3 +210,40 @@ def test_match_kernel_variants_agree(cuda, monkeypatch, env):
         if mode == "soft":
             assert ((w[0].cpu() - ref["weight"]).abs() / ref["weight"]).max() <= 1e-3
             assert (sx[0].cpu() - ref["soft_xyz"]).abs().max() <= 1e-3 * 0.2
+
+
+def test_match_bf16n_operands_and_unit_argmax(cuda):
+    """operand_mode='bf16n': model columns are normalised (F.normalize, evaluator.py:90) BEFORE the one rounding to
+    bf16.  (1) every mode stays exact with respect to the rounded operands: the oracle fed the rounded normalised
+    columns meets the usual gates; (2) mode='argmax_unit' (no per-column scale, the fastest kernel) meets the 1e-3
+    gates against the oracle on the ORIGINAL descriptors and agrees with mode='argmax' up to ||bf16 column|| - 1."""
+    import torch.nn.functional as F
+    from gadm_b200 import matching, synth
+    B, N, M, d = 2, 1500, 2056, 128            # ragged rows and model tiles
+    rgbd, mesh, _ = synth.descriptors(B, N, M, d, regime="planted", seed=91)
+    diam = 0.2
+    xyz = synth.fibonacci_sphere(M, diam)
+    bank = matching.ModelBank(mesh.to(cuda), xyz[None].to(cuda), operand_mode="bf16n")
+    mesh_n = bank.cols[0].float().cpu().T.contiguous()                 # what the tensor core sees, [d, M]
+    want = F.normalize(mesh[0], p=2, dim=0)
+    assert torch.all((mesh_n - want).abs() <= 2 ** -8 * want.abs() + 1e-30)  # one bf16 rounding of the normalised column
+    assert (mesh_n != synth.bf16_round(want)).float().mean() < 1e-3    # (the fp32 norm may differ in the last bit)
+    out = matching.match(rgbd.to(cuda), bank, operand_mode="bf16n")
+    hard = matching.match(rgbd.to(cuda), bank, operand_mode="bf16n", mode="argmax")
+    unit = matching.match(rgbd.to(cuda), bank, operand_mode="bf16n", mode="argmax_unit")
+    assert unit[2] is None and unit[3] is None
+    for b in range(B):
+        ref_n = mo.match_soft(rgbd[b], mesh_n, xyz)                    # (1) exact w.r.t. the rounded operands
+        _check([o[b] for o in out], ref_n, M, diam)
+        assert torch.equal(hard[0][b], out[0][b])
+        ref = mo.match_soft(rgbd[b], mesh[0], xyz)                     # (2) the reference on the original inputs
+        ok = ref["margin"] > TOL
+        assert torch.equal(unit[0][b].cpu()[ok], ref["idx"][ok])
+        assert (unit[1][b].cpu() - ref["max_sim"]).abs().max() <= TOL
+        assert (mesh_n.norm(dim=0) - 1).abs().max() < 2 ** -8          # the search ignores this factor ...
+        same = (unit[0][b] == hard[0][b]).cpu()
+        assert same.float().mean() > 0.999
+        # ... but the winner's similarity is reported with its true column scale
+        assert torch.allclose(unit[1][b].cpu()[same], hard[1][b].cpu()[same], atol=2e-6)
+    with pytest.raises(ValueError):                                    # unit scales need normalised columns
+        matching.match(rgbd.to(cuda), matching.ModelBank(mesh.to(cuda), xyz[None].to(cuda)), mode="argmax_unit")

@@ -15,7 +15,9 @@ obj = torch.arange(B, dtype=torch.int32, device=dev) % 8
 cols, aux = ops.prep_model(mesh.to(dev), xyz, 0)
 rows, rinv, pad = ops.prep_rows(rgbd.to(dev), 0, 0)
 flop = 2.0 * N * M * D * B
-for mode in ("argmax", "soft"):
+if os.environ.get("OPERAND", "bf16") == "bf16n":
+    cols, aux = ops.prep_model(mesh.to(dev), xyz, 2)
+for mode in (("argmax_unit",) if os.environ.get("OPERAND", "bf16") == "bf16n" else ()) + ("argmax", "soft"):
     for _ in range(3):
         ops.match_fwd(rows, rinv, pad, cols, aux, None, obj, 16.0, 0, MATCH_MODES[mode])
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
