@@ -1302,7 +1302,8 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
   uint8_t* smem_a = smem;                                    // [RT][KB] blocks of 128 rows x 64 k
   uint8_t* smem_b = smem_a + RT * p.KB * A_BLK_BYTES;
   uint8_t* smem_aux = smem_b + p.stages * B_STAGE_BYTES;   // per slot: 1/|m| x256
-  Barriers* bars = reinterpret_cast<Barriers*>(smem_aux + AUX_SLOTS * AUX_BYTES);
+  float* smem_xmax = reinterpret_cast<float*>(smem_aux + AUX_SLOTS * AUX_BYTES);   // [RT][SL][128] running maxima
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_xmax + RT * SL * BM);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1491,6 +1492,24 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
           if (!kUnit && r == RT - 1) ptx::mbar_arrive(&bars->aux_empty[slot]);
         }
       }
+      // A row has 4 tracks (one per column slice, in 4 different warps).  Alone, each raises its running maximum
+      // (two stash stores, wavefronts of the data pipe the MMAs saturate) ~H(n) times; after tiles 0, 1, 3, 7, 15
+      // the slices publish their maxima and adopt the row's: a track that adopts a larger maximum than its own
+      // gives up its record (its index becomes a sentinel that loses every tie -- the holder sits at an earlier
+      // column), and from then on only values above the ROW's maximum so far are recorded.
+      if ((t & (t + 1)) == 0 && t < 16 && t + 1 < num_tiles) {
+#pragma unroll
+        for (int r = 0; r < RT; ++r) smem_xmax[(r * SL + sub) * BM + row_in_tile] = vmax[r];
+        asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          float m = vmax[r];
+#pragma unroll
+          for (int s2 = 0; s2 < SL; ++s2) m = fmaxf(m, smem_xmax[(r * SL + s2) * BM + row_in_tile]);
+          if (vmax[r] < m) { vmax[r] = m; vgrp[r] = FRAG_NO_RECORD; }
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      }
     }
 
     // ---- per row tile: first maximal index of this slice from the stash (own stores, read back through L2), then
@@ -1498,8 +1517,8 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
     int vidx[RT];
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
-      vidx[r] = 0;
-      if (vmax[r] > -INFINITY) {
+      vidx[r] = FRAG_NO_RECORD;
+      if (vmax[r] > -INFINITY && vgrp[r] != FRAG_NO_RECORD) {
         int j_first = GRP - 1;
 #pragma unroll
         for (int k = GRP / 4 - 1; k >= 0; --k) {
@@ -1556,7 +1575,8 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
 }
 
 inline size_t match_alt_smem_bytes(int KB, int stages) {
-  return size_t(2) * KB * A_BLK_BYTES + size_t(stages) * B_STAGE_BYTES + AUX_SLOTS * PLANE_BYTES + sizeof(Barriers) + 1024;
+  return size_t(2) * KB * A_BLK_BYTES + size_t(stages) * B_STAGE_BYTES + AUX_SLOTS * PLANE_BYTES + 2 * 4 * BM * 4 +
+         sizeof(Barriers) + 1024;
 }
 inline int match_alt_stages(int KB) {
   int stages = MAX_STAGES;
