@@ -302,6 +302,17 @@ def run_gpu(args):
     vb.record()
     torch.cuda.synchronize()
     argmax_ms = va.elapsed_time(vb) / 10
+    # ---- variant: the same search on columns normalised BEFORE the bf16 rounding (operand mode bf16n), without the
+    # per-column scale in the epilogue (GADM_MATCH_ARGMAX_UNIT); the winner's similarity carries its true scale
+    cols_n, aux_n = ops.prep_model(res[0]["mesh"], xyz, OPERAND_MODES["bf16n"])
+    for _ in range(3):
+        ops.match_fwd(rows, rinv, pad, cols_n, aux_n, None, obj_id, GAMMA, pm, MATCH_MODES["argmax_unit"])
+    va.record()
+    for _ in range(10):
+        ops.match_fwd(rows, rinv, pad, cols_n, aux_n, None, obj_id, GAMMA, pm, MATCH_MODES["argmax_unit"])
+    vb.record()
+    torch.cuda.synchronize()
+    unit_ms = va.elapsed_time(vb) / 10
 
     # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
     # pipeline.FrameStream: pinned host inputs -> H2D -> prep + match + kNN -> D2H of every output into pinned host
@@ -367,7 +378,12 @@ def run_gpu(args):
                          # (profiles/r1e_ncu_full_final_kernels.csv); algorithmic bytes: 45 MB of operands + outputs
                          "traffic": 44.63e6, "traffic_unit": "bytes per launch (ncu, round 1)"},
             "variants": {"match_kernel_argmax_only_ms": argmax_ms,
-                         "match_kernel_argmax_only_frac": flop_per_launch / (argmax_ms * 1e-3) / 1e12 / peak},
+                         "match_kernel_argmax_only_frac": flop_per_launch / (argmax_ms * 1e-3) / 1e12 / peak,
+                         "match_kernel_argmax_unit_ms": unit_ms,
+                         "match_kernel_argmax_unit_frac": flop_per_launch / (unit_ms * 1e-3) / 1e12 / peak,
+                         "note": "argmax_only = evaluator.py:89-93 exactly (match_alt_kernel); argmax_unit = same search "
+                                 "on bf16n operands without column scales (index may differ only below a 2^-7 |score| "
+                                 "margin); the timed step above uses the SOFT kernel"},
             "knn": {"algorithmic_bytes_per_step": pyr.algorithmic_bytes * FRAMES,
                     "achieved_gbs": pyr.algorithmic_bytes * FRAMES / (knn_ms * 1e-3) / 1e9,
                     "hbm_peak_gbs": pk.get("hbm_gbs"), "queries_per_step": pyr.n_queries * FRAMES},

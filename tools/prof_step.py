@@ -15,6 +15,7 @@ rgbd, mesh, _ = synth.descriptors(B, N, M, D, n_obj=8, regime="planted", seed=20
 xyz = synth.model_bank_xyz(8, M).to(dev)
 obj = torch.arange(B, dtype=torch.int32, device=dev)
 cols, aux = ops.prep_model(mesh.to(dev), xyz, 0)
+cols_n, aux_n = ops.prep_model(mesh.to(dev), xyz, 2)          # bf16n: columns normalised before the rounding
 rows, rinv, pad = ops.prep_rows(rgbd.to(dev), 0, 0)
 cld, sr = synth.frame_batch(B, 128, N, seed=2000)
 pyr = KnnPyramid(N, {s: (128 // s) ** 2 for s in (2, 4, 8)}, B)
@@ -23,6 +24,7 @@ for _ in range(reps):
     if what in ("all", "match"):
         ops.match_fwd(rows, rinv, pad, cols, aux, None, obj, 16.0, 0, MATCH_MODES["argmax"])
         ops.match_fwd(rows, rinv, pad, cols, aux, None, obj, 16.0, 0, MATCH_MODES["soft"])
+        ops.match_fwd(rows, rinv, pad, cols_n, aux_n, None, obj, 16.0, 0, MATCH_MODES["argmax_unit"])
     if what in ("all", "knn"):
         pyr.run_packed(pts)
 torch.cuda.synchronize()
