@@ -82,6 +82,25 @@ def _(mesh, model_xyz, operand_mode):
             mesh.new_empty((n_obj * ((M + 255) // 256) * 1024,)))
 
 
+_MATCH_WS = {}
+
+
+def _match_workspace(lib, dev):
+    """Scratch of the alternating / fragment-layout match kernels (argmax stash, one 64 KB slot per SM): one
+    persistent buffer per (device, stream) -- launches on a stream are ordered, launches on different streams get
+    different buffers, and the timed loop never touches the allocator (a per-call torch.empty next to
+    record_stream()-held NCCL buffers made the caching allocator cudaMalloc inside the step)."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(dev).cuda_stream)
+    ws = _MATCH_WS.get(key)
+    if ws is None:
+        if len(_MATCH_WS) >= 64:          # streams come and go (pools, graphs): keep the cache bounded
+            _MATCH_WS.clear()
+        ws = torch.empty((int(lib.gadm_match_workspace_bytes()),), dtype=torch.uint8, device=dev)
+        _MATCH_WS[key] = ws
+    return ws
+
+
 @torch.library.custom_op("gadm::match_fwd", mutates_args=(), device_types="cuda")
 def match_fwd(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tensor, cols: torch.Tensor, aux: torch.Tensor,
               mask: torch.Tensor | None, obj_id: torch.Tensor | None, gamma: float, pad_mode: int,
@@ -108,8 +127,7 @@ def match_fwd(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tensor, col
     soft_xyz = torch.empty((B, N, 3) if soft else (0,), dtype=torch.float32, device=dev)
     lib = _lib_for(rows)
     with torch.cuda.device(dev):
-        # scratch of the fragment-layout kernel (argmax stash, one 64 KB slot per SM), from torch's caching allocator
-        ws = torch.empty((int(lib.gadm_match_workspace_bytes()),), dtype=torch.uint8, device=dev)
+        ws = _match_workspace(lib, dev)
         _lib.check(lib.gadm_match_fwd(_ptr(rows), _ptr(rinv), _ptr(pad_sim) if pad_mode else None, _ptr(cols),
                                       _ptr(aux), _ptr(mask), _ptr(obj_id), B, N, M, kp, n_obj, float(gamma),
                                       pad_mode, mode, _ptr(idx), _ptr(max_sim), _ptr(weight) if soft else None,
