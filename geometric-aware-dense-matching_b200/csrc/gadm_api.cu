@@ -157,6 +157,24 @@ int gadm_match_fwd(const void* rows, const float* rinv_rows, const float* pad_si
                       idx, max_sim, weight, soft_xyz, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int gadm_circle_loss_fwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
+                         const float* aux, const float* planes_frame, const int64_t* match_idx, const uint8_t* fg,
+                         const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma, float margin,
+                         float radius, float* loss, float* lse_p, float* lse_n, gadm_stream_t stream) {
+  GADM_REQUIRE_INIT();
+  if (!rows || !rinv_rows || !pad_sim || !cols || !aux || !planes_frame || !match_idx || !loss || !lse_p || !lse_n)
+    return GADM_ERR_BAD_ARG;
+  if (B <= 0 || N <= 0 || M <= 0 || Kp <= 0 || n_obj <= 0) return GADM_ERR_BAD_ARG;
+  if (B > 65535 || Kp % 64 != 0 || Kp > 768 || M % 8 != 0) return GADM_ERR_UNSUPPORTED;
+  if (obj_id == nullptr && n_obj != 1 && n_obj != B) return GADM_ERR_BAD_ARG;
+  if (!(margin >= 0.f && margin < 1.f) || !(radius > 0.f) || !(gamma > 0.f)) return GADM_ERR_BAD_ARG;
+  // 2^logit is summed without a running maximum: |logit| <= gamma (2 + m)(2 - m) must stay inside the fp32 range
+  if (gamma * (2.f + margin) * (2.f - margin) * 1.4426950408889634f > 120.f) return GADM_ERR_UNSUPPORTED;
+  if (!aligned16(rows) || !aligned16(cols) || !aligned16(aux) || !aligned16(planes_frame)) return GADM_ERR_ALIGN;
+  return circle_launch(rows, rinv_rows, pad_sim, cols, aux, planes_frame, match_idx, fg, obj_id, B, N, M, Kp, n_obj,
+                       gamma, margin, radius, loss, lse_p, lse_n, (cudaStream_t)stream);
+}
+
 size_t gadm_match_workspace_bytes(void) {
   if (!initialised()) return 0;
   return match_workspace_bytes();

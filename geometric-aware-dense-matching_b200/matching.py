@@ -74,6 +74,38 @@ def match(rgbd, mesh, model_xyz=None, obj_id=None, mask=None, gamma=16.0, pad_mo
     return idx, max_sim, weight, soft_xyz
 
 
+def circle_match_loss(rgbd, bank, labels, match_idx, visible_flag, positive_r, obj_id=None, gamma=16.0, margin=0.2,
+                      return_rows=False):
+    """The matching loss of GeoMatch.pointwise_feature_matching (models/geoMatch.py:102-157 + :55-83 +
+    CircleLoss.forward, models/loss.py:475-490) for a whole batch in one fused launch, forward only.
+
+    rgbd [B, d, N] fp32 (end_points['rgbd']); bank: ModelBank of the object(s) (operand_mode "bf16");
+    labels [B, N] (rows with label == 1 take part, x['labels']); match_idx [B, N] int (ground-truth vertex, M = off
+    the model, x['match_idx']); visible_flag [B, M] (x['visible_flag']); positive_r: metres (geoMatch.py:24).
+    Returns the scalar the reference returns: the mean over samples with >= 3 foreground rows of the mean row loss
+    (0 if there is none); return_rows=True adds the per-row (loss, lse_p, lse_n) tensors."""
+    if bank.operand_mode != "bf16":
+        raise ValueError("circle_match_loss expects a bank prepared with operand_mode='bf16'")
+    B, d, N = rgbd.shape
+    dev = rgbd.device
+    rows, rinv, pad_sim = ops.prep_rows(rgbd.contiguous().float(), OPERAND_MODES["bf16"], PAD_MODES["minus_one"])
+    oid = None if obj_id is None else torch.as_tensor(obj_id, device=dev).to(torch.int32).contiguous()
+    sel = oid.long() if oid is not None else (torch.arange(B, device=dev) if bank.n_obj == B
+                                              else torch.zeros(B, dtype=torch.long, device=dev))
+    vis = visible_flag.to(dev).bool()                                            # [B, M]
+    xyz_f = bank.model_xyz[sel]                                                  # [B, M, 3]
+    planes = torch.where(vis[None], xyz_f.permute(2, 0, 1), xyz_f.new_full((), 1e18)).contiguous()   # [3, B, M]
+    fg = (labels.to(dev) == 1).to(torch.uint8).contiguous()
+    loss, lse_p, lse_n = ops.circle_loss_fwd(rows, rinv, pad_sim, bank.cols, bank.aux, planes,
+                                             match_idx.to(dev).long().contiguous(), fg, oid, float(gamma),
+                                             float(margin), float(positive_r))
+    cnt = fg.sum(dim=1)
+    per_sample = loss.sum(dim=1) / cnt.clamp(min=1)                              # CircleLoss: .mean() over the rows
+    use = cnt >= 3                                                               # geoMatch.py:128-129
+    total = torch.where(use.any(), (per_sample * use).sum() / use.sum().clamp(min=1), per_sample.new_zeros(()))
+    return (total, loss, lse_p, lse_n) if return_rows else total
+
+
 def rt_from_moments(mom):
     """best_fit_transform (utils/pvn3d_eval_utils_kpls.py:43-76) from {n, sum A, sum B, sum A B^T}.
     mom: float64 [16] (numpy).  H = AA^T BB = sum(A B^T) - n cA cB^T."""

@@ -145,6 +145,49 @@ def _(rows, rinv, pad_sim, cols, aux, mask, obj_id, gamma, pad_mode, mode):
             rows.new_empty((B, N, 3) if soft else (0,), dtype=torch.float32))
 
 
+@torch.library.custom_op("gadm::circle_loss_fwd", mutates_args=(), device_types="cuda")
+def circle_loss_fwd(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tensor, cols: torch.Tensor,
+                    aux: torch.Tensor, planes_frame: torch.Tensor, match_idx: torch.Tensor,
+                    fg: torch.Tensor | None, obj_id: torch.Tensor | None, gamma: float, margin: float,
+                    radius: float) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Per-row CircleLoss of the similarity with the -1-padded model (gadm_circle_loss_fwd): (loss, lse_p, lse_n)."""
+    _need(rows, torch.bfloat16, "rows"); _need(cols, torch.bfloat16, "cols")
+    _need(rinv, torch.float32, "rinv"); _need(pad_sim, torch.float32, "pad_sim"); _need(aux, torch.float32, "aux")
+    _need(planes_frame, torch.float32, "planes_frame"); _need(match_idx, torch.int64, "match_idx")
+    B, N, kp = rows.shape
+    n_obj, M, kp2 = cols.shape
+    if kp != kp2:
+        raise ValueError(f"operand K mismatch: rows {kp} vs cols {kp2}")
+    if tuple(planes_frame.shape) != (3, B, M):
+        raise ValueError(f"planes_frame must be [3, {B}, {M}]")
+    if tuple(match_idx.shape) != (B, N) or tuple(pad_sim.shape) != (B, N):
+        raise ValueError("match_idx and pad_sim must be [B, N]")
+    if fg is not None:
+        _need(fg, torch.uint8, "fg")
+        if tuple(fg.shape) != (B, N):
+            raise ValueError("fg must be [B, N]")
+    if obj_id is not None:
+        _need(obj_id, torch.int32, "obj_id")
+    dev = rows.device
+    loss = torch.empty((B, N), dtype=torch.float32, device=dev)
+    lse_p = torch.empty((B, N), dtype=torch.float32, device=dev)
+    lse_n = torch.empty((B, N), dtype=torch.float32, device=dev)
+    lib = _lib_for(rows)
+    with torch.cuda.device(dev):
+        _lib.check(lib.gadm_circle_loss_fwd(_ptr(rows), _ptr(rinv), _ptr(pad_sim), _ptr(cols), _ptr(aux),
+                                            _ptr(planes_frame), _ptr(match_idx), _ptr(fg), _ptr(obj_id), B, N, M, kp,
+                                            n_obj, float(gamma), float(margin), float(radius), _ptr(loss), _ptr(lse_p),
+                                            _ptr(lse_n), _stream()), "gadm_circle_loss_fwd")
+    return loss, lse_p, lse_n
+
+
+@circle_loss_fwd.register_fake
+def _(rows, rinv, pad_sim, cols, aux, planes_frame, match_idx, fg, obj_id, gamma, margin, radius):
+    B, N, _ = rows.shape
+    return (rows.new_empty((B, N), dtype=torch.float32), rows.new_empty((B, N), dtype=torch.float32),
+            rows.new_empty((B, N), dtype=torch.float32))
+
+
 @torch.library.custom_op("gadm::kabsch_moments", mutates_args=(), device_types="cuda")
 def kabsch_moments(idx: torch.Tensor, mask: torch.Tensor | None, cloud: torch.Tensor, aux: torch.Tensor,
                    obj_id: torch.Tensor | None, M: int, n_obj: int) -> torch.Tensor:

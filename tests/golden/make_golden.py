@@ -8,6 +8,8 @@
   dgcnn_golden.npz   outputs of models/dgcnn.py knn() / get_graph_feature() imported from /root/reference
   randla_golden.npz  outputs of RandLANet.py random_sample / nearest_interpolation / relative_pos_encoding /
                      gather_neighbour, EXECUTED from the reference source text
+  circle_golden.npz  the training-side matching loss: CircleLoss imported from models/loss.py, GeoMatch.matching_loss /
+                     pointwise_feature_matching and pdist EXECUTED from the reference source text
 Nothing from the reference is copied into the repo: only inputs and numeric outputs are stored."""
 import os
 import sys
@@ -132,12 +134,73 @@ def make_randla():
     np.savez_compressed(os.path.join(HERE, "randla_golden.npz"), **out)
 
 
+def make_circle():
+    """The training-side matching loss, EXECUTED from the reference: CircleLoss is imported from models/loss.py (torch
+    only), GeoMatch.matching_loss (models/geoMatch.py:55-83), GeoMatch.pointwise_feature_matching (:102-157) and pdist
+    (utils/basic_utils.py:86-93) run from the source text; .cuda() is a no-op while they run."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_loss", os.path.join(REF, "models", "loss.py"))
+    ref_loss = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_loss)
+    ns = {"torch": torch, "F": F}
+    exec(ref_lines("utils/basic_utils.py", 86, 93), ns)                   # pdist
+    exec(ref_lines("models/geoMatch.py", 55, 83), ns)                     # matching_loss(self, ...)
+    exec(ref_lines("models/geoMatch.py", 102, 157), ns)                   # pointwise_feature_matching(self, ...)
+
+    g = torch.Generator().manual_seed(31)
+    B, d, N, M = 3, 64, 96, 64
+    bf = lambda t: t.to(torch.bfloat16).to(torch.float32)
+    mesh = bf(torch.randn((1, d, M), generator=g))
+    i = torch.arange(M, dtype=torch.float64) + 0.5                         # Fibonacci sphere, diameter 0.2 m
+    phi, theta = torch.acos(1 - 2 * i / M), np.pi * (1 + 5 ** 0.5) * i
+    xyz = (0.1 * torch.stack([torch.cos(theta) * torch.sin(phi), torch.sin(theta) * torch.sin(phi),
+                              torch.cos(phi)], dim=1)).float()
+    vis = (torch.rand((B, M), generator=g) < 0.6)
+    labels = (torch.rand((B, N), generator=g) < 0.45).long()
+    labels[2] = 0
+    labels[2, :2] = 1                                                      # < 3 foreground rows: the sample is skipped
+    match_idx = torch.full((B, N), M, dtype=torch.int32)
+    rgbd = bf(torch.randn((B, d, N), generator=g))
+    for b in range(B):
+        vis_ids = torch.where(vis[b])[0]
+        pick = vis_ids[torch.randint(0, len(vis_ids), (N,), generator=g)]
+        on = torch.rand((N,), generator=g) < 0.8                           # 20 % of the rows are off the model
+        match_idx[b] = torch.where(on, pick, torch.full_like(pick, M)).int()
+        near = on.nonzero()[:, 0][::2]                                     # half of the on-model rows look like their vertex
+        rgbd[b][:, near] = bf(mesh[0][:, match_idx[b][near].long()] + 0.5 * torch.randn((d, len(near)), generator=g))
+    positive_r = 0.045
+
+    class _Emb:
+        sys_corr_idx = None
+        _buffers = {"xyz": xyz}
+    stub = types.SimpleNamespace(feat_dim=d, positive_r=positive_r, circle_loss=ref_loss.CircleLoss(16), model_emb=_Emb())
+    stub.matching_loss = types.MethodType(ns["matching_loss"], stub)
+    x = {"labels": labels, "match_idx": match_idx, "RT": torch.zeros((B, 3, 4)), "visible_flag": vis.to(torch.uint8)}
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        total = ns["pointwise_feature_matching"](stub, rgbd.clone(), mesh.clone(), x)
+        per_sample = []
+        for b in range(2):
+            xb = {k: v[b:b + 1] for k, v in x.items()}
+            per_sample.append(float(ns["pointwise_feature_matching"](stub, rgbd[b:b + 1].clone(), mesh.clone(), xb)))
+    finally:
+        torch.Tensor.cuda = real_cuda
+    out = {"rgbd": rgbd.numpy(), "mesh": mesh.numpy(), "xyz": xyz.numpy(), "vis": vis.numpy().astype(np.uint8),
+           "labels": labels.numpy(), "match_idx": match_idx.numpy(), "positive_r": np.float32(positive_r),
+           "ref_total": np.float32(float(total)), "ref_per_sample": np.asarray(per_sample, dtype=np.float32)}
+    np.savez_compressed(os.path.join(HERE, "circle_golden.npz"), **out)
+    print("circle golden: total", float(total), "per sample", per_sample)
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "needs the reference tree"
     assert ko.have_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "randla":        # add one fixture without regenerating the others
         make_randla()
+    elif len(sys.argv) > 1 and sys.argv[1] == "circle":
+        make_circle()
     else:
-        make_knn(); make_match(); make_dgcnn(); make_randla()
+        make_knn(); make_match(); make_dgcnn(); make_randla(); make_circle()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -1,0 +1,86 @@
+"""-m gpu: fused CircleLoss forward (gadm_circle_loss_fwd) vs oracle/circle_oracle.py (which
+reproduces the reference's own loss to 1e-6 on the golden fixture) on the same bf16-representable inputs.
+Gate: fp32 path, 1e-3 relative on the scalar loss and on every row's loss (+1e-3 absolute for rows near 0)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import circle_oracle as co
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-3
+
+
+def _check(rgbd, mesh, labels, match_idx, xyz, vis, r, cuda, obj_id=None, bank=None):
+    from gadm_b200 import matching
+    if bank is None:
+        bank = matching.ModelBank(mesh.to(cuda), xyz.to(cuda))
+    total, rows, lse_p, lse_n = matching.circle_match_loss(rgbd.to(cuda), bank, labels.to(cuda), match_idx.to(cuda),
+                                                           vis.to(cuda), r, obj_id=obj_id, return_rows=True)
+    B = rgbd.shape[0]
+    per = []
+    for b in range(B):
+        o = 0 if obj_id is None else int(obj_id[b])
+        if int((labels[b] == 1).sum()) < 3:
+            continue
+        idxs, want, wp, wn = co.sample_rows(rgbd[b], mesh[o], labels[b], match_idx[b], xyz[o], vis[b], r)
+        got = rows[b].cpu()[idxs]
+        assert torch.all((got - want).abs() <= TOL * want.abs() + TOL), f"row loss, sample {b}"
+        fin = torch.isfinite(wp)
+        assert torch.all((lse_p[b].cpu()[idxs][fin] - wp[fin]).abs() <= TOL * wp[fin].abs() + TOL)
+        assert torch.all((lse_n[b].cpu()[idxs] - wn).abs() <= TOL * wn.abs() + TOL)
+        off = torch.ones(labels.shape[1], dtype=torch.bool)
+        off[idxs] = False
+        assert torch.all(rows[b].cpu()[off] == 0)          # rows outside the foreground take no part
+        per.append(want.mean())
+    want_total = torch.stack(per).mean() if per else torch.tensor(0.0)
+    assert abs(float(total) - float(want_total)) <= TOL * abs(float(want_total)) + 1e-6
+    return float(total)
+
+
+def test_circle_loss_golden_fixture(cuda):
+    g = np.load(os.path.join(GOLD, "circle_golden.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    total = _check(t("rgbd"), t("mesh"), t("labels"), t("match_idx").long(), t("xyz")[None], t("vis"),
+                   float(g["positive_r"]), cuda)
+    assert abs(total - float(g["ref_total"])) <= TOL * float(g["ref_total"])      # the reference's own number
+
+
+def test_circle_loss_ragged_bank(cuda):
+    """Ragged rows / model tiles (1500 rows, 2056 vertices), a 2-object bank with per-frame obj_id, planted matches,
+    per-frame visibility, 15 % of the rows off the model."""
+    from gadm_b200 import synth
+    B, N, M, d = 3, 1500, 2056, 128
+    g = torch.Generator().manual_seed(41)
+    mesh = synth.bf16_round(torch.randn((2, d, M), generator=g))
+    xyz = torch.stack([synth.fibonacci_sphere(M, 0.2), synth.fibonacci_sphere(M, 0.15)])
+    obj = [1, 0, 1]
+    vis = torch.rand((B, M), generator=g) < 0.5
+    labels = (torch.rand((B, N), generator=g) < 0.6).long()
+    match_idx = torch.full((B, N), M, dtype=torch.int64)
+    rgbd = synth.bf16_round(torch.randn((B, d, N), generator=g))
+    for b in range(B):
+        ids = torch.where(vis[b])[0]
+        pick = ids[torch.randint(0, len(ids), (N,), generator=g)]
+        on = torch.rand((N,), generator=g) < 0.85
+        match_idx[b] = torch.where(on, pick, torch.full_like(pick, M))
+        sel = on.nonzero()[:, 0]
+        rgbd[b][:, sel] = synth.bf16_round(mesh[obj[b]][:, match_idx[b][sel]] + 0.7 * torch.randn((d, len(sel)), generator=g))
+    total = _check(rgbd, mesh, labels, match_idx, xyz, vis, 0.012, cuda, obj_id=obj)
+    assert total > 0
+
+
+def test_circle_loss_errors(cuda):
+    from gadm_b200 import matching, synth, _lib
+    rgbd, mesh, _ = synth.descriptors(1, 256, 256, 64, seed=3)
+    xyz = synth.fibonacci_sphere(256, 0.2)
+    bank = matching.ModelBank(mesh.to(cuda), xyz[None].to(cuda))
+    args = (rgbd.to(cuda), bank, torch.ones((1, 256), dtype=torch.long), torch.zeros((1, 256), dtype=torch.long),
+            torch.ones((1, 256), dtype=torch.uint8))
+    with pytest.raises(_lib.GadmError):                      # 2^logit would leave the fp32 range
+        matching.circle_match_loss(*args, 0.01, gamma=40.0)
+    # no foreground sample with >= 3 rows: the reference returns 0 (geoMatch.py:151-152)
+    assert float(matching.circle_match_loss(args[0], bank, torch.zeros((1, 256), dtype=torch.long), args[3], args[4], 0.01)) == 0.0

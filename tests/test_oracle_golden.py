@@ -157,3 +157,27 @@ def test_randla_oracle_vs_reference_source():
     assert torch.equal(ro.nearest_interpolation(t("feature"), t("interp_idx")), t("nearest_interpolation"))
     assert torch.equal(ro.gather_neighbour(t("xyz"), t("neigh_idx")), t("gather_neighbour"))
     assert torch.equal(ro.relative_pos_encoding(t("xyz"), t("neigh_idx")), t("relative_pos_encoding"))
+
+
+def test_circle_oracle_reproduces_reference_loss():
+    """oracle/circle_oracle.py against the outputs of the reference's own CircleLoss / matching_loss /
+    pointwise_feature_matching (tests/golden/circle_golden.npz, generated by make_golden.py from /root/reference)."""
+    from oracle import circle_oracle as co
+    g = np.load(os.path.join(G, "circle_golden.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    r = float(g["positive_r"])
+    total = co.batch_loss(t("rgbd"), t("mesh")[0], t("labels"), t("match_idx"), t("xyz"), t("vis"), r)
+    assert abs(float(total) - float(g["ref_total"])) <= 1e-6 * abs(float(g["ref_total"]))
+    for b in range(2):                                       # sample 2 has < 3 foreground rows: skipped (geoMatch.py:128)
+        one = co.batch_loss(t("rgbd")[b:b + 1], t("mesh")[0], t("labels")[b:b + 1], t("match_idx")[b:b + 1],
+                            t("xyz"), t("vis")[b:b + 1], r)
+        assert abs(float(one) - float(g["ref_per_sample"][b])) <= 1e-6 * abs(float(g["ref_per_sample"][b]))
+    assert float(co.batch_loss(t("rgbd")[2:], t("mesh")[0], t("labels")[2:], t("match_idx")[2:], t("xyz"),
+                               t("vis")[2:], r)) == 0.0
+    # the mask the loss sees: every on-model row has its own (visible) ground-truth vertex as a positive, an
+    # off-model row has the pad column only
+    mi = t("match_idx")[0].long()
+    mask = co.positive_mask(mi, t("xyz"), t("vis")[0], r)
+    on = mi != 64
+    assert torch.all(mask[on, :64].gather(1, mi[on][:, None])) and not mask[on, 64].any()
+    assert torch.all(mask[~on, 64]) and not mask[~on, :64].any()
