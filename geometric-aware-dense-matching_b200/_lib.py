@@ -38,6 +38,9 @@ SIGNATURES = {
     "gadm_circle_loss_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gadm_circle_loss_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "gadm_kabsch_moments": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                     c_void_p, c_void_p]),
     "gadm_knn3d_workspace_bytes": (c_size_t, [ctypes.POINTER(KnnJob), c_int, c_int]),

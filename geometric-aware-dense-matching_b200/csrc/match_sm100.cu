@@ -1610,10 +1610,17 @@ struct CircleParams {
   float* loss;              // [B, N] softplus(LSE_p + LSE_n), 0 for rows outside fg
   float* lse_p;             // [B, N] natural-log LSE of the positive / negative logits (for a backward pass)
   float* lse_n;
+  const float* w;           // kGrad: [B, N] dL/dz of every row (0 for rows that take no part)
+  float* G;                 // kGrad: [B, N, Mp] dL/dsim, column M = pad column, columns M+1.. = 0
+  int Mp;
   int B, N, M, KB, n_obj, stages;
   float gamma_log2e, margin, r2;
 };
 
+// kGrad: the same pass, but instead of the two sums every score's gradient is written,
+//   dL/dsim_ij = w_i * (j positive ? softmax_p(j) * (-ap_ij gamma) : softmax_n(j) * (an_ij gamma)),
+// with ap / an constants (the reference detaches them, loss.py:479-480) and the row's two LSEs from the forward pass.
+template <bool kGrad>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
               const CircleParams p) {
@@ -1738,6 +1745,11 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
     const float m = p.margin, one_m = 1.f - p.margin, one_p = 1.f + p.margin, gl = p.gamma_log2e;
     const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16) + sub * CS;
     float sum_p = 0.f, sum_n = 0.f;
+    // kGrad: row constants (log2 units) and the row of G
+    const float Lp = kGrad && row_ok ? p.lse_p[grow] * 1.4426950408889634f : 0.f;
+    const float Ln = kGrad && row_ok ? p.lse_n[grow] * 1.4426950408889634f : 0.f;
+    const float wg = kGrad && row_ok ? p.w[grow] * (gl * 0.6931471805599453f) : 0.f;     // w_i * gamma
+    float* grow_g = kGrad ? p.G + grow * size_t(p.Mp) : nullptr;
 
     for (int t = 0; t < num_tiles; ++t) {
       const int acc = t & 1;
@@ -1755,6 +1767,7 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
         uint32_t d[16];
         ptx::tmem_ld_32x16(s_tmem + c * 16, d);
         ptx::tmem_ld_wait();
+        float gout[16];
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           const uint32_t a = sc_addr + (c * 16 + j4 * 4) * 4;
@@ -1773,10 +1786,23 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
             const float ap = fmaxf(one_p - s, 0.f), an = fmaxf(s + m, 0.f);             // loss.py:479-480
             const float lp = -ap * (s - one_m) * gl, ln = an * (s - m) * gl;            // loss.py:488-489 (log2 units)
             const bool valid = c * 16 + j4 * 4 + e < ncols;
-            const float ex = ptx::ex2_approx(pos ? lp : ln);
-            sum_p += (valid && pos) ? ex : 0.f;
-            sum_n += (valid && !pos) ? ex : 0.f;
+            if (kGrad) {
+              const float sm = ptx::ex2_approx(pos ? lp - Lp : ln - Ln);                // softmax weight inside its set
+              gout[j4 * 4 + e] = wg * sm * (pos ? -ap : an);
+            } else {
+              const float ex = ptx::ex2_approx(pos ? lp : ln);
+              sum_p += (valid && pos) ? ex : 0.f;
+              sum_n += (valid && !pos) ? ex : 0.f;
+            }
           }
+        }
+        if (kGrad && row_ok) {
+          float* dst = grow_g + t * BN + sub * CS + c * 16;
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4)
+            if (c * 16 + j4 * 4 < ncols)           // M % 8 == 0 and 16-byte groups: a float4 is valid or invalid as a whole
+              *reinterpret_cast<float4*>(dst + j4 * 4) =
+                  make_float4(gout[j4 * 4], gout[j4 * 4 + 1], gout[j4 * 4 + 2], gout[j4 * 4 + 3]);
         }
       }
       ptx::tc_fence_before();
@@ -1789,13 +1815,22 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
 
     // ---- merge the 4 column slices (exchange buffer aliases the A blocks: all MMAs have completed), add the pad
     // column (positive exactly for the rows that are off the model: geoMatch.py:78), softplus
+    if (kGrad) {
+      if (sub == 0 && row_ok) {       // the pad column and the zero padding of the row
+        const float s = p.pad_sim[grow];
+        const float ap = fmaxf(one_p - s, 0.f), an = fmaxf(s + m, 0.f);
+        const float gp = in_mesh ? wg * ptx::ex2_approx(an * (s - m) * gl - Ln) * an
+                                 : wg * ptx::ex2_approx(-ap * (s - one_m) * gl - Lp) * -ap;
+        for (int j = p.M; j < p.Mp; ++j) grow_g[j] = j == p.M ? gp : 0.f;
+      }
+    }
     float* xch = reinterpret_cast<float*>(smem_a);      // 3 * 128 * 8 B
-    if (sub > 0) {
+    if (!kGrad && sub > 0) {
       xch[((sub - 1) * BM + row_in_tile) * 2 + 0] = sum_p;
       xch[((sub - 1) * BM + row_in_tile) * 2 + 1] = sum_n;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-    if (sub == 0 && row_ok) {
+    if (!kGrad && sub == 0 && row_ok) {
 #pragma unroll
       for (int s2 = 0; s2 < SL - 1; ++s2) {
         sum_p += xch[(s2 * BM + row_in_tile) * 2 + 0];
@@ -1845,7 +1880,9 @@ int match_configure() {
   if (e != cudaSuccess) return set_cuda_error(e);
   e = cudaFuncSetAttribute(match_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
-  e = cudaFuncSetAttribute(circle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(circle_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(circle_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
   e = cudaFuncSetAttribute(match_alt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
@@ -1993,8 +2030,9 @@ int match_launch(const void* rows, const float* rinv_rows, const float* pad_sim,
 int circle_launch(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols, const float* aux,
                   const float* planes_frame, const int64_t* match_idx, const uint8_t* fg, const int32_t* obj_id, int B,
                   int N, int M, int Kp, int n_obj, float gamma, float margin, float radius, float* loss, float* lse_p,
-                  float* lse_n, cudaStream_t stream) {
+                  float* lse_n, const float* w, float* G, int Mp, cudaStream_t stream) {
   CircleParams p;
+  p.w = w; p.G = G; p.Mp = Mp;
   p.rinv_rows = rinv_rows; p.pad_sim = pad_sim; p.scales = aux_scales(aux, n_obj, M); p.planes = planes_frame;
   p.xyz = aux_xyz(aux, n_obj, M); p.match_idx = match_idx; p.fg = fg; p.obj_id = obj_id;
   p.loss = loss; p.lse_p = lse_p; p.lse_n = lse_n;
@@ -2011,7 +2049,10 @@ int circle_launch(const void* rows, const float* rinv_rows, const float* pad_sim
   rc = make_tmap_2b_3d(&tmap_cols, cols, uint64_t(Kp), uint64_t(M), uint64_t(n_obj), BK, BN, 0);
   if (rc != GADM_OK) return rc;
   dim3 grid((N + BM - 1) / BM, B);
-  circle_kernel<<<grid, NUM_THREADS, circle_smem_bytes(KB, stages), stream>>>(tmap_rows, tmap_cols, p);
+  if (G != nullptr)
+    circle_kernel<true><<<grid, NUM_THREADS, circle_smem_bytes(KB, stages), stream>>>(tmap_rows, tmap_cols, p);
+  else
+    circle_kernel<false><<<grid, NUM_THREADS, circle_smem_bytes(KB, stages), stream>>>(tmap_rows, tmap_cols, p);
   return check_launch();
 }
 

@@ -74,35 +74,94 @@ def match(rgbd, mesh, model_xyz=None, obj_id=None, mask=None, gamma=16.0, pad_mo
     return idx, max_sim, weight, soft_xyz
 
 
-def circle_match_loss(rgbd, bank, labels, match_idx, visible_flag, positive_r, obj_id=None, gamma=16.0, margin=0.2,
-                      return_rows=False):
-    """The matching loss of GeoMatch.pointwise_feature_matching (models/geoMatch.py:102-157 + :55-83 +
-    CircleLoss.forward, models/loss.py:475-490) for a whole batch in one fused launch, forward only.
+class _CircleMatchLoss(torch.autograd.Function):
+    """Forward: gadm_circle_loss_fwd on bf16 operands prepared from (rgbd, mesh).  Backward: dL/dsim recomputed by
+    gadm_circle_loss_bwd (nothing of size [N, M] is kept between the passes), two library GEMMs (G M^ and G^T F^) and
+    the backward of the two F.normalize calls; the bf16 rounding of the operands is straight-through."""
 
-    rgbd [B, d, N] fp32 (end_points['rgbd']); bank: ModelBank of the object(s) (operand_mode "bf16");
-    labels [B, N] (rows with label == 1 take part, x['labels']); match_idx [B, N] int (ground-truth vertex, M = off
-    the model, x['match_idx']); visible_flag [B, M] (x['visible_flag']); positive_r: metres (geoMatch.py:24).
+    @staticmethod
+    def forward(ctx, rgbd, mesh, model_xyz, labels, match_idx, visible_flag, sel, oid, positive_r, gamma, margin):
+        B, d, N = rgbd.shape
+        dev = rgbd.device
+        rows, rinv, pad_sim = ops.prep_rows(rgbd.contiguous().float(), OPERAND_MODES["bf16"], PAD_MODES["minus_one"])
+        cols, aux = ops.prep_model(mesh.contiguous().float(), model_xyz, OPERAND_MODES["bf16"])
+        vis = visible_flag.to(dev).bool()                                            # [B, M]
+        xyz_f = model_xyz[sel]                                                       # [B, M, 3]
+        planes = torch.where(vis[None], xyz_f.permute(2, 0, 1), xyz_f.new_full((), 1e18)).contiguous()   # [3, B, M]
+        fg = (labels.to(dev) == 1).to(torch.uint8).contiguous()
+        mi = match_idx.to(dev).long().contiguous()
+        loss, lse_p, lse_n = ops.circle_loss_fwd(rows, rinv, pad_sim, cols, aux, planes, mi, fg, oid, gamma, margin,
+                                                 positive_r)
+        cnt = fg.sum(dim=1)
+        use = cnt >= 3                                                               # geoMatch.py:128-129
+        n_use = use.sum().clamp(min=1)
+        row_w = (fg * use[:, None]).float() / (cnt.clamp(min=1)[:, None] * n_use)    # d total / d loss_row
+        total = (loss * row_w).sum()
+        ctx.save_for_backward(rows, rinv, pad_sim, cols, aux, planes, mi, sel, lse_p, lse_n, row_w)
+        ctx.oid, ctx.cfg, ctx.n_obj = oid, (gamma, margin, positive_r), mesh.shape[0]
+        ctx.mark_non_differentiable(loss, lse_p, lse_n)
+        return total, loss, lse_p, lse_n
+
+    @staticmethod
+    def backward(ctx, g_total, _g_loss, _g_p, _g_n):
+        rows, rinv, pad_sim, cols, aux, planes, mi, sel, lse_p, lse_n, row_w = ctx.saved_tensors
+        gamma, margin, positive_r = ctx.cfg
+        B, N, d = rows.shape
+        n_obj, M, _ = cols.shape
+        w = (torch.sigmoid(lse_p + lse_n) * row_w * g_total).contiguous()            # softplus' = sigmoid
+        G = ops.circle_loss_bwd(rows, rinv, pad_sim, cols, aux, planes, mi, ctx.oid, gamma, margin, positive_r,
+                                lse_p, lse_n, w)                                     # [B, N, M + 8]
+        f_hat = rows.float() * rinv[..., None]                                       # [B, N, d]
+        scale = aux[: n_obj * M].view(n_obj, M, 1)
+        m_hat = torch.zeros((n_obj, M + 8, d), dtype=torch.float32, device=rows.device)
+        m_hat[:, :M] = cols.float() * scale
+        m_hat[:, M] = -(d ** -0.5)                                                   # the normalised -1 pad column
+        d_fhat = torch.bmm(G, m_hat[sel])                                            # [B, N, d]
+        d_mhat_b = torch.bmm(G.transpose(1, 2), f_hat)[:, :M]                        # [B, M, d]
+        d_mhat = torch.zeros((n_obj, M, d), dtype=torch.float32, device=rows.device).index_add_(0, sel, d_mhat_b)
+        # backward of F.normalize: x^ = x / |x|  =>  dx = (dx^ - (dx^ . x^) x^) / |x|
+        d_f = (d_fhat - (d_fhat * f_hat).sum(-1, keepdim=True) * f_hat) * rinv[..., None]
+        mh = m_hat[:, :M]
+        d_m = (d_mhat - (d_mhat * mh).sum(-1, keepdim=True) * mh) * scale
+        return (d_f.transpose(1, 2).contiguous(), d_m.transpose(1, 2).contiguous(), None, None, None, None, None, None,
+                None, None, None)
+
+
+def circle_match_loss(rgbd, mesh, labels, match_idx, visible_flag, positive_r, model_xyz=None, obj_id=None,
+                      gamma=16.0, margin=0.2, return_rows=False):
+    """The matching loss of GeoMatch.pointwise_feature_matching (models/geoMatch.py:102-157 + :55-83 +
+    CircleLoss.forward, models/loss.py:475-490) for a whole batch in one fused launch, differentiable with respect
+    to rgbd and mesh.
+
+    rgbd [B, d, N] fp32 (end_points['rgbd']); mesh [n_obj | 1, d, M] fp32 (end_points['mesh']) with model_xyz
+    [n_obj, M, 3], or a ModelBank (no gradient to the model then); labels [B, N] (rows with label == 1 take part,
+    x['labels']); match_idx [B, N] int (ground-truth vertex, M = off the model, x['match_idx']); visible_flag [B, M]
+    (x['visible_flag']); positive_r: metres (geoMatch.py:24).
     Returns the scalar the reference returns: the mean over samples with >= 3 foreground rows of the mean row loss
     (0 if there is none); return_rows=True adds the per-row (loss, lse_p, lse_n) tensors."""
-    if bank.operand_mode != "bf16":
-        raise ValueError("circle_match_loss expects a bank prepared with operand_mode='bf16'")
-    B, d, N = rgbd.shape
+    if isinstance(mesh, ModelBank):
+        bank = mesh
+        if bank.operand_mode != "bf16":
+            raise ValueError("circle_match_loss expects a bank prepared with operand_mode='bf16'")
+        # a prepared bank holds only the rounded operands: rebuild channel-major fp32 descriptors from them (they are
+        # bf16-representable, so the forward pass is unchanged; no gradient reaches the caller's model features)
+        model_xyz = bank.model_xyz
+        mesh = bank.cols.float().transpose(1, 2).contiguous()
+    elif mesh.dim() == 2:
+        mesh = mesh.unsqueeze(0)
+    if model_xyz is None:
+        raise ValueError("model_xyz [n_obj, M, 3] is needed for the positive mask")
+    if model_xyz.dim() == 2:
+        model_xyz = model_xyz.unsqueeze(0)
+    B = rgbd.shape[0]
     dev = rgbd.device
-    rows, rinv, pad_sim = ops.prep_rows(rgbd.contiguous().float(), OPERAND_MODES["bf16"], PAD_MODES["minus_one"])
+    n_obj = mesh.shape[0]
     oid = None if obj_id is None else torch.as_tensor(obj_id, device=dev).to(torch.int32).contiguous()
-    sel = oid.long() if oid is not None else (torch.arange(B, device=dev) if bank.n_obj == B
+    sel = oid.long() if oid is not None else (torch.arange(B, device=dev) if n_obj == B
                                               else torch.zeros(B, dtype=torch.long, device=dev))
-    vis = visible_flag.to(dev).bool()                                            # [B, M]
-    xyz_f = bank.model_xyz[sel]                                                  # [B, M, 3]
-    planes = torch.where(vis[None], xyz_f.permute(2, 0, 1), xyz_f.new_full((), 1e18)).contiguous()   # [3, B, M]
-    fg = (labels.to(dev) == 1).to(torch.uint8).contiguous()
-    loss, lse_p, lse_n = ops.circle_loss_fwd(rows, rinv, pad_sim, bank.cols, bank.aux, planes,
-                                             match_idx.to(dev).long().contiguous(), fg, oid, float(gamma),
-                                             float(margin), float(positive_r))
-    cnt = fg.sum(dim=1)
-    per_sample = loss.sum(dim=1) / cnt.clamp(min=1)                              # CircleLoss: .mean() over the rows
-    use = cnt >= 3                                                               # geoMatch.py:128-129
-    total = torch.where(use.any(), (per_sample * use).sum() / use.sum().clamp(min=1), per_sample.new_zeros(()))
+    total, loss, lse_p, lse_n = _CircleMatchLoss.apply(rgbd, mesh, model_xyz.contiguous().float().to(dev), labels,
+                                                       match_idx, visible_flag, sel, oid, float(positive_r),
+                                                       float(gamma), float(margin))
     return (total, loss, lse_p, lse_n) if return_rows else total
 
 

@@ -188,6 +188,37 @@ def _(rows, rinv, pad_sim, cols, aux, planes_frame, match_idx, fg, obj_id, gamma
             rows.new_empty((B, N), dtype=torch.float32))
 
 
+@torch.library.custom_op("gadm::circle_loss_bwd", mutates_args=(), device_types="cuda")
+def circle_loss_bwd(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tensor, cols: torch.Tensor,
+                    aux: torch.Tensor, planes_frame: torch.Tensor, match_idx: torch.Tensor,
+                    obj_id: torch.Tensor | None, gamma: float, margin: float, radius: float, lse_p: torch.Tensor,
+                    lse_n: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """dL/dsim [B, N, M + 8] (column M = pad column, the rest of the padding 0) for per-row upstream gradients w
+    (gadm_circle_loss_bwd)."""
+    _need(rows, torch.bfloat16, "rows"); _need(cols, torch.bfloat16, "cols")
+    for t, n in ((rinv, "rinv"), (pad_sim, "pad_sim"), (aux, "aux"), (planes_frame, "planes_frame"), (lse_p, "lse_p"),
+                 (lse_n, "lse_n"), (w, "w")):
+        _need(t, torch.float32, n)
+    _need(match_idx, torch.int64, "match_idx")
+    B, N, kp = rows.shape
+    n_obj, M, _ = cols.shape
+    Mp = M + 8
+    G = torch.empty((B, N, Mp), dtype=torch.float32, device=rows.device)
+    lib = _lib_for(rows)
+    with torch.cuda.device(rows.device):
+        _lib.check(lib.gadm_circle_loss_bwd(_ptr(rows), _ptr(rinv), _ptr(pad_sim), _ptr(cols), _ptr(aux),
+                                            _ptr(planes_frame), _ptr(match_idx), _ptr(obj_id), B, N, M, kp, n_obj,
+                                            float(gamma), float(margin), float(radius), _ptr(lse_p), _ptr(lse_n),
+                                            _ptr(w), _ptr(G), Mp, _stream()), "gadm_circle_loss_bwd")
+    return G
+
+
+@circle_loss_bwd.register_fake
+def _(rows, rinv, pad_sim, cols, aux, planes_frame, match_idx, obj_id, gamma, margin, radius, lse_p, lse_n, w):
+    B, N, _ = rows.shape
+    return rows.new_empty((B, N, cols.shape[1] + 8), dtype=torch.float32)
+
+
 @torch.library.custom_op("gadm::kabsch_moments", mutates_args=(), device_types="cuda")
 def kabsch_moments(idx: torch.Tensor, mask: torch.Tensor | None, cloud: torch.Tensor, aux: torch.Tensor,
                    obj_id: torch.Tensor | None, M: int, n_obj: int) -> torch.Tensor:

@@ -133,6 +133,19 @@ int gadm_circle_loss_fwd(const void* rows, const float* rinv_rows, const float* 
                          const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma, float margin,
                          float radius, float* loss, float* lse_p, float* lse_n, gadm_stream_t stream);
 
+/* Backward companion: dL/dsim for the rows' upstream gradients, recomputed from the same operands (the forward
+ * pass keeps 8 bytes per row, not the similarity matrix).
+ *   lse_p / lse_n [B, N] from gadm_circle_loss_fwd;  w [B, N] = dL/d(LSE_p + LSE_n) of every row, i.e.
+ *   sigmoid(LSE_p + LSE_n) * dL/dloss_row (0 for rows that take no part)
+ *   G [B, N, Mp] fp32 (16-byte aligned, Mp >= M + 1, Mp % 4 == 0): G[b, i, j] = dL/dsim_ij for j < M, column M = the
+ *   pad column, columns M + 1 .. Mp - 1 = 0.  ap / an are constants as in the reference (detach, loss.py:479-480).
+ * The two gradient GEMMs that follow (G M^ and G^T F^) are plain library GEMMs on the caller's side.                */
+int gadm_circle_loss_bwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
+                         const float* aux, const float* planes_frame, const int64_t* match_idx,
+                         const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma, float margin,
+                         float radius, const float* lse_p, const float* lse_n, const float* w, float* G, int Mp,
+                         gadm_stream_t stream);
+
 /* Foreground mask of the matcher (evaluator.py:78,82: `seg_res = argmax(seg_features, dim=0); cls_msk = seg_res == 1`)
  * without the argmax tensor: seg [B, 2, N] fp32 -> mask [B, N] uint8 = seg[b,1,n] > seg[b,0,n]  (torch.argmax returns
  * the first maximal index, so a tie is background). */

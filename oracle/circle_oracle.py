@@ -41,8 +41,8 @@ def _masked_lse(logit, mask):
 
 def circle_rows(sim, mask, m=0.2, gamma=16.0):
     """loss.py:475-490 without the final mean: per-row softplus(LSE_p + LSE_n), and the two LSEs."""
-    ap = torch.clamp_min(-sim + 1 + m, min=0.0)                                  # :479 (masking = restricting the LSE)
-    an = torch.clamp_min(sim + m, min=0.0)                                       # :480
+    ap = torch.clamp_min(-sim.detach() + 1 + m, min=0.0)                         # :479 (masking = restricting the LSE)
+    an = torch.clamp_min(sim.detach() + m, min=0.0)                              # :480 (both detached, as there)
     logit_p = -ap * (sim - (1 - m)) * gamma                                      # :482, :488
     logit_n = an * (sim - m) * gamma                                             # :483, :489
     lse_p, lse_n = _masked_lse(logit_p, mask), _masked_lse(logit_n, ~mask)       # :491-492

@@ -20,6 +20,9 @@ def _check(rgbd, mesh, labels, match_idx, xyz, vis, r, cuda, obj_id=None, bank=N
         bank = matching.ModelBank(mesh.to(cuda), xyz.to(cuda))
     total, rows, lse_p, lse_n = matching.circle_match_loss(rgbd.to(cuda), bank, labels.to(cuda), match_idx.to(cuda),
                                                            vis.to(cuda), r, obj_id=obj_id, return_rows=True)
+    total2 = matching.circle_match_loss(rgbd.to(cuda), mesh.to(cuda), labels.to(cuda), match_idx.to(cuda), vis.to(cuda),
+                                        r, model_xyz=xyz.to(cuda), obj_id=obj_id)        # raw features instead of a bank
+    assert float(total2) == float(total)
     B = rgbd.shape[0]
     per = []
     for b in range(B):
@@ -73,6 +76,41 @@ def test_circle_loss_ragged_bank(cuda):
     assert total > 0
 
 
+def test_circle_loss_gradients_vs_autograd_of_the_reference_math(cuda):
+    """d loss / d rgbd and d loss / d mesh against torch autograd through the oracle (the reference's own formulas,
+    ap / an detached as at loss.py:479-480) on the CPU.  Gate: 1e-3 of the largest gradient entry."""
+    from gadm_b200 import matching, synth
+    B, N, M, d = 2, 300, 520, 64
+    g = torch.Generator().manual_seed(51)
+    mesh = synth.bf16_round(torch.randn((1, d, M), generator=g))
+    xyz = synth.fibonacci_sphere(M, 0.2)[None]
+    vis = torch.rand((B, M), generator=g) < 0.6
+    labels = (torch.rand((B, N), generator=g) < 0.5).long()
+    match_idx = torch.full((B, N), M, dtype=torch.int64)
+    rgbd = synth.bf16_round(torch.randn((B, d, N), generator=g))
+    for b in range(B):
+        ids = torch.where(vis[b])[0]
+        pick = ids[torch.randint(0, len(ids), (N,), generator=g)]
+        on = torch.rand((N,), generator=g) < 0.8
+        match_idx[b] = torch.where(on, pick, torch.full_like(pick, M))
+        sel = on.nonzero()[:, 0]
+        rgbd[b][:, sel] = synth.bf16_round(mesh[0][:, match_idx[b][sel]] + 0.8 * torch.randn((d, len(sel)), generator=g))
+    r = 0.03
+    a = rgbd.clone().requires_grad_(True)
+    m = mesh.clone().requires_grad_(True)
+    want = co.batch_loss(a, m[0], labels, match_idx, xyz[0], vis, r)
+    want.backward()
+    ad = rgbd.to(cuda).requires_grad_(True)
+    md = mesh.to(cuda).requires_grad_(True)
+    got = matching.circle_match_loss(ad, md, labels.to(cuda), match_idx.to(cuda), vis.to(cuda), r, model_xyz=xyz.to(cuda))
+    assert abs(float(got.detach()) - float(want.detach())) <= TOL * abs(float(want.detach()))
+    (2.0 * got).backward()                                   # upstream gradient 2: checks the chain through g_total
+    for name, gd, wd in (("rgbd", ad.grad.cpu() / 2, a.grad), ("mesh", md.grad.cpu() / 2, m.grad)):
+        err = (gd - wd).abs().max()
+        assert err <= TOL * wd.abs().max(), f"d loss / d {name}: max err {err} vs max |grad| {wd.abs().max()}"
+        assert wd.abs().max() > 0
+
+
 def test_circle_loss_errors(cuda):
     from gadm_b200 import matching, synth, _lib
     rgbd, mesh, _ = synth.descriptors(1, 256, 256, 64, seed=3)
@@ -82,5 +120,7 @@ def test_circle_loss_errors(cuda):
             torch.ones((1, 256), dtype=torch.uint8))
     with pytest.raises(_lib.GadmError):                      # 2^logit would leave the fp32 range
         matching.circle_match_loss(*args, 0.01, gamma=40.0)
+    with pytest.raises(ValueError):                          # raw features need the model coordinates
+        matching.circle_match_loss(args[0], mesh.to(cuda), args[2], args[3], args[4], 0.01)
     # no foreground sample with >= 3 rows: the reference returns 0 (geoMatch.py:151-152)
     assert float(matching.circle_match_loss(args[0], bank, torch.zeros((1, 256), dtype=torch.long), args[3], args[4], 0.01)) == 0.0
