@@ -228,11 +228,16 @@ class GeoMatch(nn.Module):
     (seg_layer, feature_encoding_layer, normalize_feature_layer) so checkpoints load unchanged when the
     same head modules are supplied.  forward(inputs, end_points=None) returns end_points with
     'seg' [B,2,N], 'mesh' [1,d,M], 'rgbd' [B,d,N]; in eval mode with match_in_forward=True it adds
-    'match_idx', 'match_sim', 'match_weight', 'match_xyz' from the fused kernel."""
+    'match_idx', 'match_sim', 'match_weight', 'match_xyz' from the fused kernel.  In training mode (geoMatch.py:188-195)
+    it adds 'match_loss' (the fused CircleLoss, circle_match_loss) when positive_r and model_xyz are given, and
+    'seg_loss' / 'loss' through the pluggable seg_loss_func(seg, labels) / awl(seg_loss, match_loss) (the reference's
+    FocalLoss and AutomaticWeightedLoss are outside the path); without awl, 'loss' is their plain sum."""
 
     def __init__(self, pcd_emb, model_emb, feature_encoding_layer, seg_layer, normalize_feature_layer=None,
-                 model_xyz=None, match_in_forward=False, gamma=16.0, operand_mode="bf16"):
+                 model_xyz=None, match_in_forward=False, gamma=16.0, operand_mode="bf16", positive_r=None,
+                 seg_loss_func=None, awl=None):
         super().__init__()
+        self.positive_r, self.seg_loss_func, self.awl = positive_r, seg_loss_func, awl
         self.pcd_emb, self.model_emb = pcd_emb, model_emb
         self.feature_encoding_layer, self.seg_layer = feature_encoding_layer, seg_layer
         self.normalize_feature_layer = normalize_feature_layer
@@ -252,6 +257,17 @@ class GeoMatch(nn.Module):
             rgbd_emb = rgbd_emb + self.normalize_feature_layer(rgbd_features)   # :181-182
         seg_features = self.seg_layer(rgbd_emb)                           # :183
         mesh_features = mesh_features.unsqueeze(0)                        # :184
+        if self.training and self.positive_r is not None and self.xyz is not None and 'match_idx' in inputs:
+            match_loss = circle_match_loss(rgbd_features, mesh_features, inputs['labels'], inputs['match_idx'],
+                                           inputs['visible_flag'], self.positive_r, model_xyz=self.xyz,
+                                           gamma=16.0, margin=0.2)        # :190 (CircleLoss(16), m = 0.2: :27, :81)
+            end_points['match_loss'] = match_loss
+            if self.seg_loss_func is not None:
+                seg_loss = self.seg_loss_func(seg_features, inputs['labels'])               # :191
+                end_points['seg_loss'] = seg_loss
+                end_points['loss'] = self.awl(seg_loss, match_loss) if self.awl is not None else seg_loss + match_loss
+            else:
+                end_points['loss'] = match_loss
         end_points['seg'] = seg_features
         end_points['mesh'] = mesh_features
         end_points['rgbd'] = rgbd_features

@@ -124,3 +124,59 @@ def test_circle_loss_errors(cuda):
         matching.circle_match_loss(args[0], mesh.to(cuda), args[2], args[3], args[4], 0.01)
     # no foreground sample with >= 3 rows: the reference returns 0 (geoMatch.py:151-152)
     assert float(matching.circle_match_loss(args[0], bank, torch.zeros((1, 256), dtype=torch.long), args[3], args[4], 0.01)) == 0.0
+
+
+def test_geomatch_module_forward_contract(cuda):
+    """gadm_b200.matching.GeoMatch keeps the reference's forward contract (models/geoMatch.py:159-200): end_points
+    keys and shapes; eval + match_in_forward adds the fused matcher's outputs; training adds 'match_loss' (fused
+    CircleLoss, equal to the oracle on the same features), 'seg_loss', 'loss', and gradients reach every head."""
+    import torch.nn as nn
+    from gadm_b200 import matching, synth
+    B, N, M, d, C = 2, 640, 512, 64, 32
+    torch.manual_seed(0)
+
+    class Pcd(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c = nn.Conv1d(9, C, 1)
+        def forward(self, inputs):
+            return self.c(inputs['cld_rgb_nrm'])
+
+    class Mesh(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.f = nn.Parameter(torch.randn(d, M))
+        def forward(self):
+            return self.f
+
+    xyz = synth.fibonacci_sphere(M, 0.2)
+    net = matching.GeoMatch(Pcd(), Mesh(), nn.Conv1d(C, d, 1), nn.Conv1d(C, 2, 1), nn.Conv1d(d, C, 1), model_xyz=xyz,
+                            match_in_forward=True, positive_r=0.03,
+                            seg_loss_func=lambda seg, lab: nn.functional.cross_entropy(seg, lab)).to(cuda)
+    g = torch.Generator().manual_seed(1)
+    vis = torch.rand((B, M), generator=g) < 0.7
+    labels = (torch.rand((B, N), generator=g) < 0.5).long()
+    match_idx = torch.full((B, N), M, dtype=torch.int32)
+    for b in range(B):
+        ids = torch.where(vis[b])[0]
+        pick = ids[torch.randint(0, len(ids), (N,), generator=g)]
+        match_idx[b] = torch.where(torch.rand((N,), generator=g) < 0.8, pick, torch.full_like(pick, M)).int()
+    inputs = {'cld_rgb_nrm': torch.randn((B, 9, N), generator=g).to(cuda), 'labels': labels.to(cuda),
+              'match_idx': match_idx.to(cuda), 'visible_flag': vis.to(torch.uint8).to(cuda)}
+    net.eval()
+    with torch.no_grad():
+        ep = net(inputs)
+    assert ep['seg'].shape == (B, 2, N) and ep['mesh'].shape == (1, d, M) and ep['rgbd'].shape == (B, d, N)
+    assert ep['match_idx'].shape == (B, N) and ep['match_xyz'].shape == (B, N, 3) and 'loss' not in ep
+    net.train()
+    ep = net(inputs)
+    assert {'loss', 'seg_loss', 'match_loss', 'seg', 'mesh', 'rgbd'} <= set(ep) and 'match_idx' not in ep
+    bf = synth.bf16_round                                       # the fused loss sees the features rounded to bf16
+    want = co.batch_loss(bf(ep['rgbd'].detach().cpu()), bf(ep['mesh'].detach().cpu()[0]), labels, match_idx.long(), xyz,
+                         vis, 0.03)
+    assert abs(float(ep['match_loss'].detach()) - float(want)) <= TOL * abs(float(want))
+    ep['loss'].backward()
+    for name, prm in net.named_parameters():
+        if name.startswith("normalize_feature_layer"):           # feeds the segmentation branch only
+            continue
+        assert prm.grad is not None and torch.isfinite(prm.grad).all() and prm.grad.abs().max() > 0, name
