@@ -160,25 +160,25 @@ int gadm_match_fwd(const void* rows, const float* rinv_rows, const float* pad_si
 int gadm_circle_loss_fwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
                          const float* aux, const float* planes_frame, const int64_t* match_idx, const uint8_t* fg,
                          const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma, float margin,
-                         float radius, float* loss, float* lse_p, float* lse_n, gadm_stream_t stream) {
+                         float* loss, float* lse_p, float* lse_n, gadm_stream_t stream) {
   GADM_REQUIRE_INIT();
   if (!rows || !rinv_rows || !pad_sim || !cols || !aux || !planes_frame || !match_idx || !loss || !lse_p || !lse_n)
     return GADM_ERR_BAD_ARG;
   if (B <= 0 || N <= 0 || M <= 0 || Kp <= 0 || n_obj <= 0) return GADM_ERR_BAD_ARG;
   if (B > 65535 || Kp % 64 != 0 || Kp > 768 || M % 8 != 0) return GADM_ERR_UNSUPPORTED;
   if (obj_id == nullptr && n_obj != 1 && n_obj != B) return GADM_ERR_BAD_ARG;
-  if (!(margin >= 0.f && margin < 1.f) || !(radius > 0.f) || !(gamma > 0.f)) return GADM_ERR_BAD_ARG;
+  if (!(margin >= 0.f && margin < 1.f) || !(gamma > 0.f)) return GADM_ERR_BAD_ARG;
   // 2^logit is summed without a running maximum: |logit| <= gamma (2 + m)(2 - m) must stay inside the fp32 range
   if (gamma * (2.f + margin) * (2.f - margin) * 1.4426950408889634f > 120.f) return GADM_ERR_UNSUPPORTED;
   if (!aligned16(rows) || !aligned16(cols) || !aligned16(aux) || !aligned16(planes_frame)) return GADM_ERR_ALIGN;
   return circle_launch(rows, rinv_rows, pad_sim, cols, aux, planes_frame, match_idx, fg, obj_id, B, N, M, Kp, n_obj,
-                       gamma, margin, radius, loss, lse_p, lse_n, nullptr, nullptr, 0, (cudaStream_t)stream);
+                       gamma, margin, loss, lse_p, lse_n, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
 
 int gadm_circle_loss_bwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
                          const float* aux, const float* planes_frame, const int64_t* match_idx,
                          const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma, float margin,
-                         float radius, const float* lse_p, const float* lse_n, const float* w, float* G, int Mp,
+                         const float* lse_p, const float* lse_n, const float* w, float* G, int Mp,
                          gadm_stream_t stream) {
   GADM_REQUIRE_INIT();
   if (!rows || !rinv_rows || !pad_sim || !cols || !aux || !planes_frame || !match_idx || !lse_p || !lse_n || !w || !G)
@@ -187,12 +187,12 @@ int gadm_circle_loss_bwd(const void* rows, const float* rinv_rows, const float* 
   if (B > 65535 || Kp % 64 != 0 || Kp > 768 || M % 8 != 0) return GADM_ERR_UNSUPPORTED;
   if (Mp < M + 1 || Mp % 4 != 0) return GADM_ERR_BAD_ARG;
   if (obj_id == nullptr && n_obj != 1 && n_obj != B) return GADM_ERR_BAD_ARG;
-  if (!(margin >= 0.f && margin < 1.f) || !(radius > 0.f) || !(gamma > 0.f)) return GADM_ERR_BAD_ARG;
+  if (!(margin >= 0.f && margin < 1.f) || !(gamma > 0.f)) return GADM_ERR_BAD_ARG;
   if (gamma * (2.f + margin) * (2.f - margin) * 1.4426950408889634f > 120.f) return GADM_ERR_UNSUPPORTED;
   if (!aligned16(rows) || !aligned16(cols) || !aligned16(aux) || !aligned16(planes_frame) || !aligned16(G))
     return GADM_ERR_ALIGN;
   return circle_launch(rows, rinv_rows, pad_sim, cols, aux, planes_frame, match_idx, nullptr, obj_id, B, N, M, Kp, n_obj,
-                       gamma, margin, radius, nullptr, const_cast<float*>(lse_p), const_cast<float*>(lse_n), w, G, Mp,
+                       gamma, margin, nullptr, const_cast<float*>(lse_p), const_cast<float*>(lse_n), w, G, Mp,
                        (cudaStream_t)stream);
 }
 

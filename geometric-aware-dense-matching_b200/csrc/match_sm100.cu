@@ -1602,7 +1602,7 @@ struct CircleParams {
   const float* rinv_rows;   // [B, N]
   const float* pad_sim;     // [B, N] similarity with the -1 pad column
   const float* scales;      // [n_obj, M]
-  const float* planes;      // [3, B, M] per-FRAME x / y / z planes, invisible vertices at 1e18
+  const float* planes;      // [4, B, M] per-FRAME x / y / z planes (invisible vertices at 1e18) + squared positive radius
   const float* xyz;         // [n_obj, M, 3] model coordinates (ground-truth vertex lookup)
   const int64_t* match_idx; // [B, N], M = not on the model
   const uint8_t* fg;        // [B, N] rows that take part (labels == 1)
@@ -1614,7 +1614,7 @@ struct CircleParams {
   float* G;                 // kGrad: [B, N, Mp] dL/dsim, column M = pad column, columns M+1.. = 0
   int Mp;
   int B, N, M, KB, n_obj, stages;
-  float gamma_log2e, margin, r2;
+  float gamma_log2e, margin;
 };
 
 // kGrad: the same pass, but instead of the two sums every score's gradient is written,
@@ -1624,13 +1624,13 @@ template <bool kGrad>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
               const CircleParams p) {
-  constexpr int AUX_BYTES = 4 * PLANE_BYTES;
+  constexpr int AUX_BYTES = 5 * PLANE_BYTES;
   constexpr int SL = 4, CS = BN / SL;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                    // [KB] blocks of 128 rows x 64 k
   uint8_t* smem_b = smem_a + p.KB * A_BLK_BYTES;
-  uint8_t* smem_aux = smem_b + p.stages * B_STAGE_BYTES;   // per slot: [1/|m| x256 | x x256 | y x256 | z x256]
+  uint8_t* smem_aux = smem_b + p.stages * B_STAGE_BYTES;   // per slot: [1/|m| x256 | x | y | z | r^2]
   Barriers* bars = reinterpret_cast<Barriers*>(smem_aux + AUX_SLOTS * AUX_BYTES);
 
   const int warp = threadIdx.x >> 5;
@@ -1683,11 +1683,11 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
         const uint32_t use = uint32_t(t) / AUX_SLOTS;
         const uint32_t bytes = uint32_t(min(BN, p.M - t * BN)) * 4;
         ptx::mbar_wait_sleep(&bars->aux_empty[slot], (use & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(&bars->aux_full[slot], 4 * bytes);
+        ptx::mbar_arrive_expect_tx(&bars->aux_full[slot], 5 * bytes);
         uint8_t* aux = smem_aux + slot * AUX_BYTES;
         ptx::bulk_load_1d(aux, sc_tab + size_t(t) * BN, bytes, &bars->aux_full[slot]);
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+        for (int c = 0; c < 4; ++c)
           ptx::bulk_load_1d(aux + (c + 1) * PLANE_BYTES, xyz_tab + c * plane + size_t(t) * BN, bytes,
                             &bars->aux_full[slot]);
         for (int kb = 0; kb < p.KB; ++kb) {
@@ -1773,16 +1773,16 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
           const uint32_t a = sc_addr + (c * 16 + j4 * 4) * 4;
           const float4 cm = ptx::lds128(a);
           const float4 X = ptx::lds128(a + PLANE_BYTES), Y = ptx::lds128(a + 2 * PLANE_BYTES),
-                       Z = ptx::lds128(a + 3 * PLANE_BYTES);
+                       Z = ptx::lds128(a + 3 * PLANE_BYTES), R = ptx::lds128(a + 4 * PLANE_BYTES);
           const float cs[4] = {cm.x, cm.y, cm.z, cm.w}, xs[4] = {X.x, X.y, X.z, X.w};
-          const float ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+          const float ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w}, r2s[4] = {R.x, R.y, R.z, R.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float s = (__uint_as_float(d[j4 * 4 + e]) * cs[e]) * rs;             // cosine similarity
             // (A - B).pow(2).sum(-1) as the reference evaluates it: no FMA, left to right (basic_utils.py:88)
             const float dx = __fsub_rn(gx, xs[e]), dy = __fsub_rn(gy, ys[e]), dz = __fsub_rn(gz, zs[e]);
             const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            const bool pos = __fadd_rn(d2, 1e-7f) < p.r2;                              // sqrt(D2 + 1e-7) < positive_r
+            const bool pos = __fadd_rn(d2, 1e-7f) < r2s[e];                            // sqrt(D2 + 1e-7) < positive_r[j]
             const float ap = fmaxf(one_p - s, 0.f), an = fmaxf(s + m, 0.f);             // loss.py:479-480
             const float lp = -ap * (s - one_m) * gl, ln = an * (s - m) * gl;            // loss.py:488-489 (log2 units)
             const bool valid = c * 16 + j4 * 4 + e < ncols;
@@ -1859,7 +1859,7 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
 }
 
 inline size_t circle_smem_bytes(int KB, int stages) {
-  return size_t(KB) * A_BLK_BYTES + size_t(stages) * B_STAGE_BYTES + AUX_SLOTS * 4 * PLANE_BYTES + sizeof(Barriers) + 1024;
+  return size_t(KB) * A_BLK_BYTES + size_t(stages) * B_STAGE_BYTES + AUX_SLOTS * 5 * PLANE_BYTES + sizeof(Barriers) + 1024;
 }
 
 int g_stash_slots = 0;     // SM count of the device gadm_init() ran on (written once, read-only afterwards)
@@ -2029,7 +2029,7 @@ int match_launch(const void* rows, const float* rinv_rows, const float* pad_sim,
 
 int circle_launch(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols, const float* aux,
                   const float* planes_frame, const int64_t* match_idx, const uint8_t* fg, const int32_t* obj_id, int B,
-                  int N, int M, int Kp, int n_obj, float gamma, float margin, float radius, float* loss, float* lse_p,
+                  int N, int M, int Kp, int n_obj, float gamma, float margin, float* loss, float* lse_p,
                   float* lse_n, const float* w, float* G, int Mp, cudaStream_t stream) {
   CircleParams p;
   p.w = w; p.G = G; p.Mp = Mp;
@@ -2037,7 +2037,7 @@ int circle_launch(const void* rows, const float* rinv_rows, const float* pad_sim
   p.xyz = aux_xyz(aux, n_obj, M); p.match_idx = match_idx; p.fg = fg; p.obj_id = obj_id;
   p.loss = loss; p.lse_p = lse_p; p.lse_n = lse_n;
   p.B = B; p.N = N; p.M = M; p.n_obj = n_obj;
-  p.gamma_log2e = gamma * 1.4426950408889634f; p.margin = margin; p.r2 = radius * radius;
+  p.gamma_log2e = gamma * 1.4426950408889634f; p.margin = margin;
   const int KB = Kp / BK;
   int stages = MAX_STAGES;
   while (stages > 0 && circle_smem_bytes(KB, stages) > 227 * 1024) --stages;

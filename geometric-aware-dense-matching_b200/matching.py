@@ -80,42 +80,46 @@ class _CircleMatchLoss(torch.autograd.Function):
     the backward of the two F.normalize calls; the bf16 rounding of the operands is straight-through."""
 
     @staticmethod
-    def forward(ctx, rgbd, mesh, model_xyz, labels, match_idx, visible_flag, sel, oid, positive_r, gamma, margin):
+    def forward(ctx, rgbd, mesh, model_xyz, labels, match_idx, visible_flag, sel, oid, radius, gamma, margin, pad_mode):
         B, d, N = rgbd.shape
         dev = rgbd.device
-        rows, rinv, pad_sim = ops.prep_rows(rgbd.contiguous().float(), OPERAND_MODES["bf16"], PAD_MODES["minus_one"])
+        rows, rinv, pad_sim = ops.prep_rows(rgbd.contiguous().float(), OPERAND_MODES["bf16"], PAD_MODES[pad_mode])
         cols, aux = ops.prep_model(mesh.contiguous().float(), model_xyz, OPERAND_MODES["bf16"])
         vis = visible_flag.to(dev).bool()                                            # [B, M]
         xyz_f = model_xyz[sel]                                                       # [B, M, 3]
-        planes = torch.where(vis[None], xyz_f.permute(2, 0, 1), xyz_f.new_full((), 1e18)).contiguous()   # [3, B, M]
+        planes = torch.empty((4, B, xyz_f.shape[1]), dtype=torch.float32, device=dev)
+        planes[:3] = torch.where(vis[None], xyz_f.permute(2, 0, 1), xyz_f.new_full((), 1e18))
+        planes[3] = radius * radius                                                  # [B, M] squared positive radius
         fg = (labels.to(dev) == 1).to(torch.uint8).contiguous()
         mi = match_idx.to(dev).long().contiguous()
-        loss, lse_p, lse_n = ops.circle_loss_fwd(rows, rinv, pad_sim, cols, aux, planes, mi, fg, oid, gamma, margin,
-                                                 positive_r)
+        loss, lse_p, lse_n = ops.circle_loss_fwd(rows, rinv, pad_sim, cols, aux, planes, mi, fg, oid, gamma, margin)
         cnt = fg.sum(dim=1)
         use = cnt >= 3                                                               # geoMatch.py:128-129
         n_use = use.sum().clamp(min=1)
         row_w = (fg * use[:, None]).float() / (cnt.clamp(min=1)[:, None] * n_use)    # d total / d loss_row
         total = (loss * row_w).sum()
         ctx.save_for_backward(rows, rinv, pad_sim, cols, aux, planes, mi, sel, lse_p, lse_n, row_w)
-        ctx.oid, ctx.cfg, ctx.n_obj = oid, (gamma, margin, positive_r), mesh.shape[0]
+        ctx.oid, ctx.cfg, ctx.n_obj = oid, (gamma, margin, pad_mode), mesh.shape[0]
         ctx.mark_non_differentiable(loss, lse_p, lse_n)
         return total, loss, lse_p, lse_n
 
     @staticmethod
     def backward(ctx, g_total, _g_loss, _g_p, _g_n):
         rows, rinv, pad_sim, cols, aux, planes, mi, sel, lse_p, lse_n, row_w = ctx.saved_tensors
-        gamma, margin, positive_r = ctx.cfg
+        gamma, margin, pad_mode = ctx.cfg
         B, N, d = rows.shape
         n_obj, M, _ = cols.shape
         w = (torch.sigmoid(lse_p + lse_n) * row_w * g_total).contiguous()            # softplus' = sigmoid
-        G = ops.circle_loss_bwd(rows, rinv, pad_sim, cols, aux, planes, mi, ctx.oid, gamma, margin, positive_r,
-                                lse_p, lse_n, w)                                     # [B, N, M + 8]
+        G = ops.circle_loss_bwd(rows, rinv, pad_sim, cols, aux, planes, mi, ctx.oid, gamma, margin, lse_p, lse_n,
+                                w)                                                   # [B, N, M + 8]
         f_hat = rows.float() * rinv[..., None]                                       # [B, N, d]
         scale = aux[: n_obj * M].view(n_obj, M, 1)
         m_hat = torch.zeros((n_obj, M + 8, d), dtype=torch.float32, device=rows.device)
         m_hat[:, :M] = cols.float() * scale
-        m_hat[:, M] = -(d ** -0.5)                                                   # the normalised -1 pad column
+        if pad_mode == "minus_one":
+            m_hat[:, M] = -(d ** -0.5)                                               # the normalised -1 pad column
+        else:
+            m_hat[:, M, 0] = 1.0                                                     # e0 (geoMatch_DGCNN.py:95-98)
         d_fhat = torch.bmm(G, m_hat[sel])                                            # [B, N, d]
         d_mhat_b = torch.bmm(G.transpose(1, 2), f_hat)[:, :M]                        # [B, M, d]
         d_mhat = torch.zeros((n_obj, M, d), dtype=torch.float32, device=rows.device).index_add_(0, sel, d_mhat_b)
@@ -124,11 +128,18 @@ class _CircleMatchLoss(torch.autograd.Function):
         mh = m_hat[:, :M]
         d_m = (d_mhat - (d_mhat * mh).sum(-1, keepdim=True) * mh) * scale
         return (d_f.transpose(1, 2).contiguous(), d_m.transpose(1, 2).contiguous(), None, None, None, None, None, None,
-                None, None, None)
+                None, None, None, None)
+
+
+def dgcnn_positive_radius(model_xyz, RT, positive_r):
+    """Per-vertex positive radius of the DGCNN variant (models/geoMatch_DGCNN.py:64-65):
+    positive_r / 1000 * the camera-space depth of every model vertex.  model_xyz [M, 3], RT [B, 3, 4] -> [B, M]."""
+    z = torch.matmul(model_xyz, RT[:, :, :3].transpose(1, 2))[..., 2] + RT[:, None, 2, 3]
+    return positive_r / 1000.0 * z
 
 
 def circle_match_loss(rgbd, mesh, labels, match_idx, visible_flag, positive_r, model_xyz=None, obj_id=None,
-                      gamma=16.0, margin=0.2, return_rows=False):
+                      gamma=16.0, margin=0.2, return_rows=False, pad_mode="minus_one"):
     """The matching loss of GeoMatch.pointwise_feature_matching (models/geoMatch.py:102-157 + :55-83 +
     CircleLoss.forward, models/loss.py:475-490) for a whole batch in one fused launch, differentiable with respect
     to rgbd and mesh.
@@ -136,7 +147,8 @@ def circle_match_loss(rgbd, mesh, labels, match_idx, visible_flag, positive_r, m
     rgbd [B, d, N] fp32 (end_points['rgbd']); mesh [n_obj | 1, d, M] fp32 (end_points['mesh']) with model_xyz
     [n_obj, M, 3], or a ModelBank (no gradient to the model then); labels [B, N] (rows with label == 1 take part,
     x['labels']); match_idx [B, N] int (ground-truth vertex, M = off the model, x['match_idx']); visible_flag [B, M]
-    (x['visible_flag']); positive_r: metres (geoMatch.py:24).
+    (x['visible_flag']); positive_r: metres (geoMatch.py:24), a scalar, or a [B, M] tensor of per-vertex radii
+    (dgcnn_positive_radius: the DGCNN variant, which also uses pad_mode="e0" and labels = x['origin_labels']).
     Returns the scalar the reference returns: the mean over samples with >= 3 foreground rows of the mean row loss
     (0 if there is none); return_rows=True adds the per-row (loss, lse_p, lse_n) tensors."""
     if isinstance(mesh, ModelBank):
@@ -159,9 +171,12 @@ def circle_match_loss(rgbd, mesh, labels, match_idx, visible_flag, positive_r, m
     oid = None if obj_id is None else torch.as_tensor(obj_id, device=dev).to(torch.int32).contiguous()
     sel = oid.long() if oid is not None else (torch.arange(B, device=dev) if n_obj == B
                                               else torch.zeros(B, dtype=torch.long, device=dev))
+    M = mesh.shape[-1]
+    radius = (positive_r.to(dev).float() if torch.is_tensor(positive_r) else
+              torch.full((1, 1), float(positive_r), device=dev)).expand(B, M)
     total, loss, lse_p, lse_n = _CircleMatchLoss.apply(rgbd, mesh, model_xyz.contiguous().float().to(dev), labels,
-                                                       match_idx, visible_flag, sel, oid, float(positive_r),
-                                                       float(gamma), float(margin))
+                                                       match_idx, visible_flag, sel, oid, radius, float(gamma),
+                                                       float(margin), pad_mode)
     return (total, loss, lse_p, lse_n) if return_rows else total
 
 

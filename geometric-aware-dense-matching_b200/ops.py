@@ -148,9 +148,10 @@ def _(rows, rinv, pad_sim, cols, aux, mask, obj_id, gamma, pad_mode, mode):
 @torch.library.custom_op("gadm::circle_loss_fwd", mutates_args=(), device_types="cuda")
 def circle_loss_fwd(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tensor, cols: torch.Tensor,
                     aux: torch.Tensor, planes_frame: torch.Tensor, match_idx: torch.Tensor,
-                    fg: torch.Tensor | None, obj_id: torch.Tensor | None, gamma: float, margin: float,
-                    radius: float) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """Per-row CircleLoss of the similarity with the -1-padded model (gadm_circle_loss_fwd): (loss, lse_p, lse_n)."""
+                    fg: torch.Tensor | None, obj_id: torch.Tensor | None, gamma: float,
+                    margin: float) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Per-row CircleLoss of the similarity with the padded model (gadm_circle_loss_fwd): (loss, lse_p, lse_n).
+    planes_frame [4, B, M]: x / y / z of the vertices (invisible ones at 1e18) and their squared positive radius."""
     _need(rows, torch.bfloat16, "rows"); _need(cols, torch.bfloat16, "cols")
     _need(rinv, torch.float32, "rinv"); _need(pad_sim, torch.float32, "pad_sim"); _need(aux, torch.float32, "aux")
     _need(planes_frame, torch.float32, "planes_frame"); _need(match_idx, torch.int64, "match_idx")
@@ -158,8 +159,8 @@ def circle_loss_fwd(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tenso
     n_obj, M, kp2 = cols.shape
     if kp != kp2:
         raise ValueError(f"operand K mismatch: rows {kp} vs cols {kp2}")
-    if tuple(planes_frame.shape) != (3, B, M):
-        raise ValueError(f"planes_frame must be [3, {B}, {M}]")
+    if tuple(planes_frame.shape) != (4, B, M):
+        raise ValueError(f"planes_frame must be [4, {B}, {M}]")
     if tuple(match_idx.shape) != (B, N) or tuple(pad_sim.shape) != (B, N):
         raise ValueError("match_idx and pad_sim must be [B, N]")
     if fg is not None:
@@ -176,13 +177,13 @@ def circle_loss_fwd(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tenso
     with torch.cuda.device(dev):
         _lib.check(lib.gadm_circle_loss_fwd(_ptr(rows), _ptr(rinv), _ptr(pad_sim), _ptr(cols), _ptr(aux),
                                             _ptr(planes_frame), _ptr(match_idx), _ptr(fg), _ptr(obj_id), B, N, M, kp,
-                                            n_obj, float(gamma), float(margin), float(radius), _ptr(loss), _ptr(lse_p),
+                                            n_obj, float(gamma), float(margin), _ptr(loss), _ptr(lse_p),
                                             _ptr(lse_n), _stream()), "gadm_circle_loss_fwd")
     return loss, lse_p, lse_n
 
 
 @circle_loss_fwd.register_fake
-def _(rows, rinv, pad_sim, cols, aux, planes_frame, match_idx, fg, obj_id, gamma, margin, radius):
+def _(rows, rinv, pad_sim, cols, aux, planes_frame, match_idx, fg, obj_id, gamma, margin):
     B, N, _ = rows.shape
     return (rows.new_empty((B, N), dtype=torch.float32), rows.new_empty((B, N), dtype=torch.float32),
             rows.new_empty((B, N), dtype=torch.float32))
@@ -191,7 +192,7 @@ def _(rows, rinv, pad_sim, cols, aux, planes_frame, match_idx, fg, obj_id, gamma
 @torch.library.custom_op("gadm::circle_loss_bwd", mutates_args=(), device_types="cuda")
 def circle_loss_bwd(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tensor, cols: torch.Tensor,
                     aux: torch.Tensor, planes_frame: torch.Tensor, match_idx: torch.Tensor,
-                    obj_id: torch.Tensor | None, gamma: float, margin: float, radius: float, lse_p: torch.Tensor,
+                    obj_id: torch.Tensor | None, gamma: float, margin: float, lse_p: torch.Tensor,
                     lse_n: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """dL/dsim [B, N, M + 8] (column M = pad column, the rest of the padding 0) for per-row upstream gradients w
     (gadm_circle_loss_bwd)."""
@@ -208,13 +209,13 @@ def circle_loss_bwd(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tenso
     with torch.cuda.device(rows.device):
         _lib.check(lib.gadm_circle_loss_bwd(_ptr(rows), _ptr(rinv), _ptr(pad_sim), _ptr(cols), _ptr(aux),
                                             _ptr(planes_frame), _ptr(match_idx), _ptr(obj_id), B, N, M, kp, n_obj,
-                                            float(gamma), float(margin), float(radius), _ptr(lse_p), _ptr(lse_n),
+                                            float(gamma), float(margin), _ptr(lse_p), _ptr(lse_n),
                                             _ptr(w), _ptr(G), Mp, _stream()), "gadm_circle_loss_bwd")
     return G
 
 
 @circle_loss_bwd.register_fake
-def _(rows, rinv, pad_sim, cols, aux, planes_frame, match_idx, obj_id, gamma, margin, radius, lse_p, lse_n, w):
+def _(rows, rinv, pad_sim, cols, aux, planes_frame, match_idx, obj_id, gamma, margin, lse_p, lse_n, w):
     B, N, _ = rows.shape
     return rows.new_empty((B, N, cols.shape[1] + 8), dtype=torch.float32)
 

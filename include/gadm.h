@@ -119,19 +119,22 @@ int gadm_match_fwd(const void* rows, const float* rinv_rows, const float* pad_si
 /* Flash-style CircleLoss forward, the training-side twin of the matcher.  Replaces, per batch,
  * models/geoMatch.py:102-157 (similarity of the foreground rows with the -1-padded, normalised model), :55-83
  * (positive mask) and models/loss.py:475-490 (CircleLoss.forward) without materialising sim [n_fg, M + 1]:
- *   rows / rinv_rows / pad_sim  from gadm_prep_rows(pad_mode = GADM_PAD_MINUS_ONE); cols / aux from gadm_prep_model
- *   planes_frame [3, B, M] fp32 (16-byte aligned): per-frame x / y / z planes of the model vertices in which the
- *                vertices with visible_flag == 0 are moved to 1e18 (they can then never be positives)
+ *   rows / rinv_rows / pad_sim  from gadm_prep_rows with the variant's pad column (GADM_PAD_MINUS_ONE for
+ *                models/geoMatch.py:117-119, GADM_PAD_E0 for models/geoMatch_DGCNN.py:95-98); cols / aux from gadm_prep_model
+ *   planes_frame [4, B, M] fp32 (16-byte aligned): per-frame x / y / z planes of the model vertices in which the
+ *                vertices with visible_flag == 0 are moved to 1e18 (they can then never be positives), and the
+ *                squared positive radius of every vertex (a constant for geoMatch.py:24,67; positive_r / 1000 * the
+ *                vertex's camera-space depth for geoMatch_DGCNN.py:64-65)
  *   match_idx [B, N] int64: ground-truth vertex of every row, M = off the model (pad column is its only positive)
  *   fg [B, N] uint8 or NULL: rows that take part (labels == 1); the others get 0
- *   positive j for row i: |xyz[match_idx[i]] - planes_frame[:, b, j]|^2 + 1e-7 < radius^2   (basic_utils.py:86-89)
+ *   positive j for row i: |xyz[match_idx[i]] - planes_frame[0:3, b, j]|^2 + 1e-7 < planes_frame[3, b, j]   (basic_utils.py:86-89)
  *   loss [B, N] = softplus(LSE_p + LSE_n) per row; lse_p / lse_n [B, N]: the two natural-log LSEs (what a backward
  *   pass needs).  The mean over rows / samples (geoMatch.py:150-156) is left to the caller.
  * gamma (2 + margin)(2 - margin) log2(e) must be <= 120 (gamma = 16, margin = 0.2: 91).                          */
 int gadm_circle_loss_fwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
                          const float* aux, const float* planes_frame, const int64_t* match_idx, const uint8_t* fg,
                          const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma, float margin,
-                         float radius, float* loss, float* lse_p, float* lse_n, gadm_stream_t stream);
+                         float* loss, float* lse_p, float* lse_n, gadm_stream_t stream);
 
 /* Backward companion: dL/dsim for the rows' upstream gradients, recomputed from the same operands (the forward
  * pass keeps 8 bytes per row, not the similarity matrix).
@@ -143,7 +146,7 @@ int gadm_circle_loss_fwd(const void* rows, const float* rinv_rows, const float* 
 int gadm_circle_loss_bwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
                          const float* aux, const float* planes_frame, const int64_t* match_idx,
                          const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma, float margin,
-                         float radius, const float* lse_p, const float* lse_n, const float* w, float* G, int Mp,
+                         const float* lse_p, const float* lse_n, const float* w, float* G, int Mp,
                          gadm_stream_t stream);
 
 /* Foreground mask of the matcher (evaluator.py:78,82: `seg_res = argmax(seg_features, dim=0); cls_msk = seg_res == 1`)

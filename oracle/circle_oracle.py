@@ -19,14 +19,17 @@ def pdist(A, B):
 
 
 def positive_mask(match_idx, mesh_xyz, vis_flag, positive_r):
-    """geoMatch.py:55-79.  match_idx [n] (M = off the model), mesh_xyz [M, 3], vis_flag [M] -> bool [n, M + 1]."""
+    """geoMatch.py:55-79.  match_idx [n] (M = off the model), mesh_xyz [M, 3], vis_flag [M] -> bool [n, M + 1].
+    positive_r: a scalar (geoMatch.py:67) or a per-vertex tensor [M] (geoMatch_DGCNN.py:64-65: positive_r / 1000 * the
+    camera-space depth of the vertex; only the entries of visible vertices are used)."""
     n_node = len(mesh_xyz)
     in_mesh = match_idx != n_node                                               # :59
     vis = vis_flag.to(torch.bool)
     mask = torch.zeros((len(match_idx), n_node), dtype=torch.bool)              # :72
     if in_mesh.any():
         gt_pt = mesh_xyz[match_idx[in_mesh]]                                    # :63
-        near = pdist(gt_pt, mesh_xyz[vis]) < positive_r                         # :65-66, :73
+        r = positive_r[vis] if torch.is_tensor(positive_r) and positive_r.dim() else positive_r
+        near = pdist(gt_pt, mesh_xyz[vis]) < r                                  # :65-66, :73
         sub = torch.zeros((int(in_mesh.sum()), n_node), dtype=torch.bool)
         sub[:, vis] = near                                                      # :74-75
         mask[in_mesh] = sub                                                     # :76
@@ -49,11 +52,23 @@ def circle_rows(sim, mask, m=0.2, gamma=16.0):
     return F.softplus(lse_p + lse_n), lse_p, lse_n                               # :494
 
 
-def sample_rows(rgbd_feature, mesh_feature, labels, match_idx, mesh_xyz, vis_flag, positive_r, m=0.2, gamma=16.0):
-    """One iteration of the loop at geoMatch.py:125-149.  rgbd_feature [d, N], mesh_feature [d, M], labels [N],
-    match_idx [N] -> (idxs, loss_rows, lse_p, lse_n) over the foreground rows."""
+def dgcnn_radius(mesh_xyz, RT, positive_r):
+    """geoMatch_DGCNN.py:64-65 for all vertices: positive_r / 1000 * (R x + t)_z.  RT [3, 4] -> [M]."""
+    proj = torch.matmul(mesh_xyz, RT[:, :3].t()) + RT[:, 3:].t()
+    return positive_r / 1000.0 * proj[:, 2]
+
+
+def sample_rows(rgbd_feature, mesh_feature, labels, match_idx, mesh_xyz, vis_flag, positive_r, m=0.2, gamma=16.0,
+                pad="minus_one"):
+    """One iteration of the loop at geoMatch.py:125-149 (pad "minus_one") or geoMatch_DGCNN.py:107-127 (pad "e0";
+    there all rows are normalised first, which is the same arithmetic per row).  rgbd_feature [d, N], mesh_feature
+    [d, M], labels [N], match_idx [N] -> (idxs, loss_rows, lse_p, lse_n) over the foreground rows."""
     d = rgbd_feature.shape[0]
-    mesh_padded = F.normalize(torch.cat([mesh_feature, -torch.ones((d, 1))], dim=1), p=2, dim=0)   # :117-119
+    padding = -torch.ones((d, 1))                                                # geoMatch.py:117
+    if pad == "e0":                                                              # geoMatch_DGCNN.py:95-96
+        padding = torch.zeros((d, 1))
+        padding[0] = 1
+    mesh_padded = F.normalize(torch.cat([mesh_feature, padding], dim=1), p=2, dim=0)   # :117-119 / DGCNN :97-98
     idxs = torch.where(labels == 1)[0]                                           # :127
     selected = F.normalize(rgbd_feature.transpose(0, 1).index_select(0, idxs), p=2, dim=1)         # :131, :134
     sim = torch.matmul(selected, mesh_padded)                                    # :136
@@ -61,13 +76,16 @@ def sample_rows(rgbd_feature, mesh_feature, labels, match_idx, mesh_xyz, vis_fla
     return (idxs,) + circle_rows(sim, mask, m, gamma)
 
 
-def batch_loss(rgbd, mesh_feature, labels, match_idx, mesh_xyz, vis_flags, positive_r, m=0.2, gamma=16.0):
-    """geoMatch.py:102-157: mean over the samples with >= 3 foreground rows of the mean row loss; 0 if none."""
+def batch_loss(rgbd, mesh_feature, labels, match_idx, mesh_xyz, vis_flags, positive_r, m=0.2, gamma=16.0,
+               pad="minus_one"):
+    """geoMatch.py:102-157 (geoMatch_DGCNN.py:80-136 with pad "e0" and positive_r a [B, M] tensor): mean over the
+    samples with >= 3 foreground rows of the mean row loss; 0 if none."""
     per = []
     for i in range(rgbd.shape[0]):
         if int((labels[i] == 1).sum()) < 3:                                      # :128-129
             continue
-        _, rows, _, _ = sample_rows(rgbd[i], mesh_feature, labels[i], match_idx[i], mesh_xyz, vis_flags[i],
-                                    positive_r, m, gamma)
+        r = positive_r[i] if torch.is_tensor(positive_r) and positive_r.dim() == 2 else positive_r
+        _, rows, _, _ = sample_rows(rgbd[i], mesh_feature, labels[i], match_idx[i], mesh_xyz, vis_flags[i], r, m, gamma,
+                                    pad)
         per.append(rows.mean())
     return torch.stack(per).mean() if per else torch.tensor(0.0)                 # :151-156

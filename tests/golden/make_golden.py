@@ -189,6 +189,31 @@ def make_circle():
     out = {"rgbd": rgbd.numpy(), "mesh": mesh.numpy(), "xyz": xyz.numpy(), "vis": vis.numpy().astype(np.uint8),
            "labels": labels.numpy(), "match_idx": match_idx.numpy(), "positive_r": np.float32(positive_r),
            "ref_total": np.float32(float(total)), "ref_per_sample": np.asarray(per_sample, dtype=np.float32)}
+
+    # the DGCNN variant (models/geoMatch_DGCNN.py:53-78 matching_loss with a per-vertex radius positive_r / 1000 * depth,
+    # :80-136 pointwise_feature_matching with the e0 pad column and x['origin_labels']), same inputs + poses
+    ns2 = {"torch": torch, "F": F, "pdist": ns["pdist"]}
+    exec(ref_lines("models/geoMatch_DGCNN.py", 53, 78), ns2)
+    exec(ref_lines("models/geoMatch_DGCNN.py", 80, 136), ns2)
+    RT = torch.zeros((B, 3, 4))
+    for b in range(B):
+        q, _ = torch.linalg.qr(torch.randn((3, 3), generator=g))
+        RT[b, :, :3] = q * torch.sign(torch.det(q))
+        RT[b, :, 3] = torch.tensor([0.05 * b, -0.02, 0.8 + 0.3 * b])
+    pos_r_dgcnn = 40.0                                                   # radius = 0.04 * depth (0.8 .. 1.5 m)
+
+    class _Emb2:
+        _buffers = {"mesh": torch.cat([xyz.t(), torch.zeros((3, M))], dim=0)[None]}     # [1, 6, M], xyz in channels 0..2
+    stub2 = types.SimpleNamespace(feat_dim=d, positive_r=pos_r_dgcnn, circle_loss=ref_loss.CircleLoss(16), model_emb=_Emb2())
+    stub2.matching_loss = types.MethodType(ns2["matching_loss"], stub2)
+    x2 = {"origin_labels": labels, "match_idx": match_idx, "RT": RT, "visible_flag": vis.to(torch.uint8)}
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        total2 = ns2["pointwise_feature_matching"](stub2, rgbd.clone(), mesh.clone(), x2)
+    finally:
+        torch.Tensor.cuda = real_cuda
+    out.update(RT=RT.numpy(), dgcnn_positive_r=np.float32(pos_r_dgcnn), dgcnn_ref_total=np.float32(float(total2)))
+    print("circle golden (DGCNN variant): total", float(total2))
     np.savez_compressed(os.path.join(HERE, "circle_golden.npz"), **out)
     print("circle golden: total", float(total), "per sample", per_sample)
 

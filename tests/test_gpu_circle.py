@@ -52,6 +52,25 @@ def test_circle_loss_golden_fixture(cuda):
     assert abs(total - float(g["ref_total"])) <= TOL * float(g["ref_total"])      # the reference's own number
 
 
+def test_circle_loss_dgcnn_variant_golden(cuda):
+    """models/geoMatch_DGCNN.py:53-78, :80-136: e0 pad column, per-vertex positive radius positive_r / 1000 * depth."""
+    from gadm_b200 import matching
+    g = np.load(os.path.join(GOLD, "circle_golden.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    xyz, RT, pr = t("xyz"), t("RT"), float(g["dgcnn_positive_r"])
+    rad = matching.dgcnn_positive_radius(xyz.to(cuda), RT.to(cuda), pr)
+    want_rad = torch.stack([co.dgcnn_radius(xyz, RT[b], pr) for b in range(3)])
+    assert torch.allclose(rad.cpu(), want_rad, rtol=1e-6, atol=1e-9)
+    total, rows, _, _ = matching.circle_match_loss(t("rgbd").to(cuda), t("mesh").to(cuda), t("labels").to(cuda),
+                                                   t("match_idx").to(cuda), t("vis").to(cuda), rad,
+                                                   model_xyz=xyz[None].to(cuda), pad_mode="e0", return_rows=True)
+    assert abs(float(total) - float(g["dgcnn_ref_total"])) <= TOL * float(g["dgcnn_ref_total"])
+    for b in range(2):
+        idxs, want, _, _ = co.sample_rows(t("rgbd")[b], t("mesh")[0], t("labels")[b], t("match_idx")[b].long(), xyz,
+                                          t("vis")[b], want_rad[b], pad="e0")
+        assert torch.all((rows[b].cpu()[idxs] - want).abs() <= TOL * want.abs() + TOL)
+
+
 def test_circle_loss_ragged_bank(cuda):
     """Ragged rows / model tiles (1500 rows, 2056 vertices), a 2-object bank with per-frame obj_id, planted matches,
     per-frame visibility, 15 % of the rows off the model."""

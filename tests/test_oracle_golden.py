@@ -174,6 +174,10 @@ def test_circle_oracle_reproduces_reference_loss():
         assert abs(float(one) - float(g["ref_per_sample"][b])) <= 1e-6 * abs(float(g["ref_per_sample"][b]))
     assert float(co.batch_loss(t("rgbd")[2:], t("mesh")[0], t("labels")[2:], t("match_idx")[2:], t("xyz"),
                                t("vis")[2:], r)) == 0.0
+    # the DGCNN variant (geoMatch_DGCNN.py:53-78, :80-136): e0 pad column, per-vertex radius positive_r / 1000 * depth
+    rad = torch.stack([co.dgcnn_radius(t("xyz"), t("RT")[b], float(g["dgcnn_positive_r"])) for b in range(3)])
+    tot2 = co.batch_loss(t("rgbd"), t("mesh")[0], t("labels"), t("match_idx"), t("xyz"), t("vis"), rad, pad="e0")
+    assert abs(float(tot2) - float(g["dgcnn_ref_total"])) <= 1e-6 * abs(float(g["dgcnn_ref_total"]))
     # the mask the loss sees: every on-model row has its own (visible) ground-truth vertex as a positive, an
     # off-model row has the pad column only
     mi = t("match_idx")[0].long()
