@@ -1862,7 +1862,13 @@ inline size_t circle_smem_bytes(int KB, int stages) {
   return size_t(KB) * A_BLK_BYTES + size_t(stages) * B_STAGE_BYTES + AUX_SLOTS * 5 * PLANE_BYTES + sizeof(Barriers) + 1024;
 }
 
-int g_stash_slots = 0;     // SM count of the device gadm_init() ran on (written once, read-only afterwards)
+int g_stash_slots = 0;     // %nsmid of the device gadm_init() ran on (written once, read-only afterwards)
+
+__global__ void nsmid_kernel(unsigned int* out) {
+  unsigned int v;
+  asm volatile("mov.u32 %0, %%nsmid;" : "=r"(v));
+  *out = v;
+}
 
 }  // namespace
 
@@ -1901,7 +1907,16 @@ int match_configure() {
   if (e != cudaSuccess) return set_cuda_error(e);
   e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return set_cuda_error(e);
-  g_stash_slots = sms;
+  // the stash slots are indexed by %smid, whose range is [0, %nsmid) -- read it once (init may synchronise)
+  unsigned int* d_n = nullptr;
+  unsigned int nsmid = 0;
+  e = cudaMalloc(&d_n, sizeof(unsigned int));
+  if (e != cudaSuccess) return set_cuda_error(e);
+  nsmid_kernel<<<1, 1>>>(d_n);
+  e = cudaMemcpy(&nsmid, d_n, sizeof(unsigned int), cudaMemcpyDeviceToHost);
+  cudaFree(d_n);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  g_stash_slots = sms > int(nsmid) ? sms : int(nsmid);
   return GADM_OK;
 }
 
