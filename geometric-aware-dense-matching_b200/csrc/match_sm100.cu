@@ -95,6 +95,7 @@ struct MatchParams {
   uint8_t* stash;          // fragment-layout kernel: stash_slots slots of FRAG_STASH_BYTES (workspace), else null
   int stash_slots;
   int unit_scales;         // GADM_MATCH_ARGMAX_UNIT: kernels that can, skip the column scales (the others apply them)
+  const void* rows_ptr;    // [B, N, K'] bf16 (match_ta_kernel loads its A operand from global memory)
 };
 
 __device__ __forceinline__ int frame_object(const MatchParams& p, int b) {
@@ -1585,6 +1586,337 @@ inline int match_alt_stages(int KB) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// TMEM-resident A.  With two row tiles per CTA the UMMA operand reads (A 4 KB + B 8 KB per 128x256x16 MMA) and the TMA
+// writes of the model tile already fill the SM's shared-memory data pipe.  Here the CTA's own 256 rows
+// are written into TENSOR MEMORY once (tcgen05.st by the epilogue warps, straight from global memory) and every MMA
+// takes its A operand from there (tcgen05.mma [d], [a], b-desc): the MMAs read only B from shared memory, A needs no
+// shared memory at all.  TMEM budget: 2 x K'/2 columns of A (K' <= 128) + two accumulators of 192 columns = 512, so
+// the model tile is 192 vertices (128x192x16 MMAs).  Everything else as match_alt_kernel.
+constexpr int TBN = 192;                        // model vertices per tile
+constexpr int TB_STAGE_BYTES = TBN * BK * 2;    // 24 KB
+constexpr int TA_COL0 = 2 * TBN;                // first TMEM column of the A operands
+
+template <bool kUnit>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+match_ta_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
+                 const MatchParams p) {
+  constexpr int RT = 2;
+  constexpr int AUX_BYTES = PLANE_BYTES;
+  constexpr int SL = 4;                      // column slices per row
+  constexpr int CS = TBN / SL;               // 48 columns per slice: a 32-column and a 16-column chunk
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_b = smem;
+  uint8_t* smem_aux = smem_b + p.stages * TB_STAGE_BYTES;  // per slot: 1/|m| x192
+  float* smem_xmax = reinterpret_cast<float*>(smem_aux + AUX_SLOTS * AUX_BYTES);   // [RT][SL][128] running maxima
+  float* smem_xch = smem_xmax + RT * SL * BM;                                      // [RT][SL - 1][128][2] slice merge
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_xch + RT * (SL - 1) * BM * 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int row0 = blockIdx.x * (BM * RT);
+  const int obj = frame_object(p, b);
+  const int num_tiles = (p.M + TBN - 1) / TBN;
+
+  if (warp == EPI_WARPS && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_rows);
+    ptx::prefetch_tensormap(&tmap_cols);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&bars->full[s], 1);
+      ptx::mbar_init(&bars->empty[s], 1);
+    }
+    ptx::mbar_init(&bars->a_full, EPI_WARPS);      // every epilogue warp writes its part of A into TMEM
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&bars->s_full[a], 1);
+      ptx::mbar_init(&bars->s_free[a], EPI_WARPS);   // every epilogue warp drains every accumulator
+    }
+    for (int a = 0; a < AUX_SLOTS; ++a) {
+      ptx::mbar_init(&bars->aux_full[a], 1);
+      ptx::mbar_init(&bars->aux_empty[a], EPI_WARPS);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == EPI_WARPS + 1) {
+    ptx::tmem_alloc(&bars->tmem_base, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == EPI_WARPS) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const float* sc_tab = p.scales + size_t(obj) * p.M;
+      for (int t = 0; t < num_tiles; ++t) {
+        const int slot = t % AUX_SLOTS;
+        const uint32_t use = uint32_t(t) / AUX_SLOTS;
+        const uint32_t bytes = uint32_t(min(TBN, p.M - t * TBN)) * 4;   // M % 8 == 0: a multiple of 16
+        if (!kUnit) {
+          ptx::mbar_wait_sleep(&bars->aux_empty[slot], (use & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&bars->aux_full[slot], bytes);
+          ptx::bulk_load_1d(smem_aux + slot * AUX_BYTES, sc_tab + size_t(t) * TBN, bytes, &bars->aux_full[slot]);
+        }
+        for (int kb = 0; kb < p.KB; ++kb) {
+          ptx::mbar_wait_sleep(&bars->empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&bars->full[stage], TB_STAGE_BYTES);
+          ptx::tma_load_3d(smem_b + stage * TB_STAGE_BYTES, &tmap_cols, &bars->full[stage], kb * BK, t * TBN, obj);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == EPI_WARPS + 1) {
+    // ============================== UMMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(BM, TBN);
+      ptx::mbar_wait(&bars->a_full, 0);
+      ptx::tc_fence_after();
+      int stage0 = 0;            // ring position of the tile's first K block
+      uint32_t phase0 = 0;
+      for (int t = 0; t < num_tiles; ++t) {
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          ptx::mbar_wait_sleep(&bars->s_free[r], (uint32_t(t) & 1) ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + r * TBN;
+          const uint32_t a_tmem = tmem_base + TA_COL0 + r * (p.KB * (BK / 2));   // K'/2 columns per row tile
+          int stage = stage0;
+          uint32_t phase = phase0;
+          for (int kb = 0; kb < p.KB; ++kb) {
+            if (r == 0) {      // the stages of this tile stay resident until the last row tile has used them
+              ptx::mbar_wait_sleep(&bars->full[stage], phase);
+              ptx::tc_fence_after();
+            }
+            const uint32_t b_addr = ptx::smem_u32(smem_b + stage * TB_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {     // 16 k = 8 TMEM columns of A
+              ptx::umma_f16_ts(d_tmem, a_tmem + (kb * (BK / UMMA_K) + k) * (UMMA_K / 2),
+                               ptx::umma_desc_sw128_kmajor(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0);
+            }
+            if (r == RT - 1) ptx::umma_commit(&bars->empty[stage]);  // frees the stage once these MMAs have read it
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          ptx::umma_commit(&bars->s_full[r]);     // accumulator tile complete
+          if (r == RT - 1) { stage0 = stage; phase0 = phase; }
+        }
+      }
+    }
+  } else {
+    // ============================== epilogue warps (thread == one row of each row tile) ==============
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access (warp id % 4)
+    const int sub = warp >> 2;                       // 48-column slice of every tile
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16) + sub * CS;
+    {
+      // A operand: this thread's row of both row tiles, K range [sub K'/4, (sub + 1) K'/4), from global memory into
+      // TMEM (lane = row, one 32-bit column = two consecutive k: the layout tcgen05.mma reads an A operand in)
+      const int kq = p.KB * (BK / 4);                // bf16 elements per thread and row tile: 16 (K' = 64) or 32
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        const int row = row0 + r * BM + row_in_tile;
+        const uint4* src = reinterpret_cast<const uint4*>(
+            static_cast<const uint8_t*>(p.rows_ptr) + ((size_t(b) * p.N + (row < p.N ? row : 0)) * (p.KB * BK) + sub * kq) * 2);
+        const uint32_t dst = tmem_base + (uint32_t(q * 32) << 16) + TA_COL0 + r * (p.KB * (BK / 2)) + sub * (kq / 2);
+        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
+        if (row < p.N) {
+          v0 = src[0]; v1 = src[1];
+          if (kq == 32) { v2 = src[2]; v3 = src[3]; }
+        }
+        if (kq == 32) {
+          const uint32_t w[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+          ptx::tmem_st_32x16(dst, w);
+        } else {
+          const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          ptx::tmem_st_32x8(dst, w);
+        }
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars->a_full);
+    }
+    if (ptx::smid() >= uint32_t(p.stash_slots)) __trap();
+    // stash entry of row tile r, float4 k: + (2 r + k) * 8192 (plane-major: coalesced 512-byte warp stores)
+    uint8_t* stash = p.stash + size_t(ptx::smid()) * FRAG_STASH_BYTES + threadIdx.x * 16;
+
+    float vmax[RT] = {-INFINITY, -INFINITY};   // running maximum of this thread's slice of its row of row tile r
+    int vgrp[RT] = {0, 0};                     // first column of the 8-column group that first reached it
+
+    for (int t = 0; t < num_tiles; ++t) {
+      const int slot = t % AUX_SLOTS;
+      const int ncols = min(TBN, p.M - t * TBN) - sub * CS;   // valid columns of this slice (may be <= 0)
+      const uint32_t sc_addr = ptx::smem_u32(smem_aux + slot * AUX_BYTES) + sub * CS * 4;
+      const int col_base = t * TBN + sub * CS;
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        if (!((kUnit || r > 0 || ptx::mbar_try_wait(&bars->aux_full[slot], (uint32_t(t) / AUX_SLOTS) & 1)) &
+              ptx::mbar_try_wait(&bars->s_full[r], uint32_t(t) & 1))) {
+          if (!kUnit && r == 0) ptx::mbar_wait_sleep(&bars->aux_full[slot], (uint32_t(t) / AUX_SLOTS) & 1);
+          ptx::mbar_wait_sleep(&bars->s_full[r], uint32_t(t) & 1);
+        }
+        ptx::tc_fence_after();
+        const uint32_t s_tmem = lane_base + r * TBN;
+
+        // one chunk of W = 32 or 16 columns starting at slice column col0 (see match_kernel)
+        auto process = [&](auto& d, int col0, auto guard_tag) {
+          constexpr int W = int(sizeof(d) / sizeof(d[0]));
+          constexpr bool kGuard = decltype(guard_tag)::value;
+          const uint32_t sc = sc_addr + col0 * 4;
+          uint64_t v[W / 2];
+#pragma unroll
+          for (int j4 = 0; j4 < W / 4; ++j4) {
+            if (kUnit) {
+              v[j4 * 2 + 0] = ptx::pack2(d[j4 * 4 + 0], d[j4 * 4 + 1]);
+              v[j4 * 2 + 1] = ptx::pack2(d[j4 * 4 + 2], d[j4 * 4 + 3]);
+            } else {
+              const float4 cm = ptx::lds128(sc + j4 * 16);
+              v[j4 * 2 + 0] = ptx::fmul2(ptx::pack2(d[j4 * 4 + 0], d[j4 * 4 + 1]), ptx::pack2f(cm.x, cm.y));
+              v[j4 * 2 + 1] = ptx::fmul2(ptx::pack2(d[j4 * 4 + 2], d[j4 * 4 + 3]), ptx::pack2f(cm.z, cm.w));
+            }
+          }
+          if (kGuard) {  // TMA zero-fills columns >= M and the stale scales behind them are meaningless
+#pragma unroll
+            for (int j = 0; j < W / 2; ++j) {
+              float lo, hi;
+              ptx::unpack2f(v[j], lo, hi);
+              if (col0 + 2 * j >= ncols) lo = -INFINITY;
+              if (col0 + 2 * j + 1 >= ncols) hi = -INFINITY;
+              v[j] = ptx::pack2f(lo, hi);
+            }
+          }
+#pragma unroll
+          for (int h = 0; h < W / GRP; ++h) {
+            float f[GRP];
+#pragma unroll
+            for (int j = 0; j < GRP / 2; ++j) ptx::unpack2f(v[h * 4 + j], f[2 * j], f[2 * j + 1]);
+            const float a0 = ptx::fmax3(f[0], f[1], f[2]), a1 = ptx::fmax3(f[3], f[4], f[5]);
+            const float gm = ptx::fmax3(a0, a1, fmaxf(f[6], f[7]));
+            // strict: an equal value in a later group never displaces the first maximal index
+            const bool up = gm > vmax[r];
+            ptx::stg_pred32(up, stash + r * 2 * 8192, v[h * 4 + 0], v[h * 4 + 1], v[h * 4 + 2], v[h * 4 + 3]);
+            vgrp[r] = up ? col_base + col0 + h * GRP : vgrp[r];
+            vmax[r] = up ? gm : vmax[r];
+          }
+        };
+        using guard_off = std::integral_constant<bool, false>;
+        using guard_on = std::integral_constant<bool, true>;
+
+#ifdef GADM_DBG_NOEPI
+        if (false)
+#endif
+        if (ncols > 0) {
+          uint32_t ra[32], rb[16];
+          ptx::tmem_ld_32x32(s_tmem, ra);
+          ptx::tmem_ld_32x16(s_tmem + 32, rb);
+          ptx::tmem_ld_wait();
+          if (ncols >= 32) process(ra, 0, guard_off{});
+          else process(ra, 0, guard_on{});         // ragged last tile
+          if (ncols > 32) {
+            if (ncols >= CS) process(rb, 32, guard_off{});
+            else process(rb, 32, guard_on{});
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(&bars->s_free[r]);
+          if (!kUnit && r == RT - 1) ptx::mbar_arrive(&bars->aux_empty[slot]);
+        }
+      }
+      // A row has 4 tracks (one per column slice, in 4 different warps).  Alone, each raises its running maximum
+      // (two stash stores, wavefronts of the data pipe the MMAs saturate) ~H(n) times; after tiles 0, 1, 3, 7, 15
+      // the slices publish their maxima and adopt the row's: a track that adopts a larger maximum than its own
+      // gives up its record (its index becomes a sentinel that loses every tie -- the holder sits at an earlier
+      // column), and from then on only values above the ROW's maximum so far are recorded.
+      if ((t & (t + 1)) == 0 && t < 16 && t + 1 < num_tiles) {
+#pragma unroll
+        for (int r = 0; r < RT; ++r) smem_xmax[(r * SL + sub) * BM + row_in_tile] = vmax[r];
+        asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          float m = vmax[r];
+#pragma unroll
+          for (int s2 = 0; s2 < SL; ++s2) m = fmaxf(m, smem_xmax[(r * SL + s2) * BM + row_in_tile]);
+          if (vmax[r] < m) { vmax[r] = m; vgrp[r] = FRAG_NO_RECORD; }
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      }
+    }
+
+    // ---- per row tile: first maximal index of this slice from the stash (own stores, read back through L2), then
+    // the merge of the 4 column slices through shared memory
+    int vidx[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      vidx[r] = FRAG_NO_RECORD;
+      if (vmax[r] > -INFINITY && vgrp[r] != FRAG_NO_RECORD) {
+        int j_first = GRP - 1;
+#pragma unroll
+        for (int k = GRP / 4 - 1; k >= 0; --k) {
+          const float4 sv = ptx::ldg_cg128(stash + (r * 2 + k) * 8192);
+          if (sv.w == vmax[r]) j_first = 4 * k + 3;
+          if (sv.z == vmax[r]) j_first = 4 * k + 2;
+          if (sv.y == vmax[r]) j_first = 4 * k + 1;
+          if (sv.x == vmax[r]) j_first = 4 * k + 0;
+        }
+        vidx[r] = vgrp[r] + j_first;
+      }
+      if (sub > 0) {
+        float* x = smem_xch + ((r * (SL - 1) + sub - 1) * BM + row_in_tile) * 2;
+        x[0] = vmax[r]; x[1] = __int_as_float(vidx[r]);
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+    if (sub == 0) {
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        const int row = row0 + r * BM + row_in_tile;
+        if (row >= p.N) continue;
+        const size_t grow = size_t(b) * p.N + row;
+        float vm = vmax[r];
+        int vi = vidx[r];
+#pragma unroll
+        for (int s2 = 0; s2 < SL - 1; ++s2) {
+          const float* x = smem_xch + ((r * (SL - 1) + s2) * BM + row_in_tile) * 2;
+          const float v1 = x[0];
+          const int i1 = __float_as_int(x[1]);
+          if (v1 > vm || (v1 == vm && i1 < vi)) { vm = v1; vi = i1; }
+        }
+        // kUnit searched with unit column norms; the winner's similarity is reported with its true scale
+        if (kUnit) vm *= p.scales[size_t(obj) * p.M + vi];
+        const bool keep = p.mask == nullptr || p.mask[grow] != 0;
+        float best = vm * p.rinv_rows[grow];
+        int64_t best_idx = vi;
+        if (p.pad_mode != GADM_PAD_NONE) {
+          const float ps = p.pad_sim[grow];
+          if (ps > best) { best = ps; best_idx = p.M; }  // pad column is the last one: wins only if strictly larger
+        }
+        p.idx[grow] = keep ? best_idx : int64_t(-1);
+        p.max_sim[grow] = keep ? best : 0.f;
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS + 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+
+inline size_t match_ta_smem_bytes(int stages) {
+  return size_t(stages) * TB_STAGE_BYTES + AUX_SLOTS * PLANE_BYTES + 2 * 4 * BM * 4 + 2 * 3 * BM * 8 + sizeof(Barriers) + 1024;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
 // Flash-style CircleLoss forward: the training-side twin of the matcher.
 // Reference: models/geoMatch.py:102-157 (per sample: foreground rows, normalise, sim = F^ M^_pad with the -1 pad
 // column), :55-83 (positive mask: model vertices that are visible AND within positive_r of the row's ground-truth
@@ -1890,6 +2222,10 @@ int match_configure() {
   if (e != cudaSuccess) return set_cuda_error(e);
   e = cudaFuncSetAttribute(circle_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(match_ta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(match_ta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
   e = cudaFuncSetAttribute(match_alt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
   e = cudaFuncSetAttribute(match_alt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1951,6 +2287,30 @@ static int match_launch_t(const void* rows, const void* cols, MatchParams p, int
         match_frag_kernel<kSoft, 2><<<grid, FRAG_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
       else
         match_frag_kernel<kSoft, 1><<<grid, FRAG_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+      return check_launch();
+    }
+  }
+  if (!kSoft) {
+    // TMEM-resident A (ARGMAX, K' <= 128, needs the stash workspace): opt-in with GADM_MATCH_TA=1 (profiling, tests).
+    // Parity-green but slower: A from TMEM leaves room for 192-column accumulators only, and a 128x192x16 MMA takes
+    // the time of a 128x256x16 one -- with the epilogue compiled out the pipeline reaches 77 % of the bf16 peak
+    // (99.7 % for match_alt_kernel's 128x256x16 MMAs from shared memory); ARGMAX 0.206 ms against 0.187-0.197 ms,
+    // ARGMAX_UNIT 0.190 ms against 0.156-0.164 ms.
+    bool ta = false;
+    if (const char* f = getenv("GADM_MATCH_TA")) ta = atoi(f) != 0;
+    if (ta && p.stash != nullptr && KB <= 2 && p.N > BM) {
+      p.KB = KB; p.stages = MAX_STAGES;
+      p.rows_ptr = rows;
+      CUtensorMap tmap_rows, tmap_cols;
+      int rc = make_tmap_2b_3d(&tmap_rows, rows, uint64_t(Kp), uint64_t(p.N), uint64_t(p.B), BK, BM, 0);
+      if (rc != GADM_OK) return rc;
+      rc = make_tmap_2b_3d(&tmap_cols, cols, uint64_t(Kp), uint64_t(p.M), uint64_t(p.n_obj), BK, TBN, 0);
+      if (rc != GADM_OK) return rc;
+      dim3 grid((p.N + 2 * BM - 1) / (2 * BM), p.B);
+      if (p.unit_scales)
+        match_ta_kernel<true><<<grid, NUM_THREADS, match_ta_smem_bytes(p.stages), stream>>>(tmap_rows, tmap_cols, p);
+      else
+        match_ta_kernel<false><<<grid, NUM_THREADS, match_ta_smem_bytes(p.stages), stream>>>(tmap_rows, tmap_cols, p);
       return check_launch();
     }
   }
@@ -2038,6 +2398,7 @@ int match_launch(const void* rows, const float* rinv_rows, const float* pad_sim,
   p.B = B; p.N = N; p.M = M; p.KB = 0; p.n_obj = n_obj; p.stages = 0; p.pad_mode = pad_mode;
   p.gamma_log2e = gamma * 1.4426950408889634f;
   p.unit_scales = mode == GADM_MATCH_ARGMAX_UNIT;
+  p.rows_ptr = rows;
   if (mode == GADM_MATCH_SOFT) return match_launch_t<true>(rows, cols, p, Kp, stream);
   return match_launch_t<false>(rows, cols, p, Kp, stream);
 }

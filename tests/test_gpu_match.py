@@ -188,11 +188,12 @@ def test_seg_mask_matches_torch_argmax(cuda):
 
 @pytest.mark.parametrize("env", [{"GADM_MATCH_ALT": "0", "GADM_MATCH_PAIR": "0", "GADM_MATCH_RT": "1"},
                                  {"GADM_MATCH_ALT": "0", "GADM_MATCH_PAIR": "0", "GADM_MATCH_RT": "2"},
-                                 {"GADM_MATCH_ALT": "0", "GADM_MATCH_PAIR": "1"}, {"GADM_MATCH_ALT": "1"},
+                                 {"GADM_MATCH_ALT": "0", "GADM_MATCH_PAIR": "1"},
+                                 {"GADM_MATCH_ALT": "1"}, {"GADM_MATCH_TA": "1"},
                                  {"GADM_MATCH_FRAG": "1"}, {"GADM_MATCH_FRAG": "2"}])
 def test_match_kernel_variants_agree(cuda, monkeypatch, env):
     """The kernels of the matcher (one row tile per CTA, two row tiles per CTA, paired rows per thread, alternating
-    accumulators, fragment layout with four rows per thread on one / two row tiles per CTA) are selected per launch; every one of them must meet the same gates
+    accumulators with A in shared memory / in tensor memory, fragment layout with four rows per thread on one / two row tiles per CTA) are selected per launch; every one of them must meet the same gates
     on a ragged shape, in both modes."""
     from gadm_b200 import matching, synth
     from oracle import match_oracle as mo
