@@ -246,21 +246,34 @@ def run_gpu(args):
         main.wait_event(join)
         return out, knn_idx
 
+    ring = {"k": 0, "buf": [None, None], "ev": [None, None]}
+
     def gather(out):
-        """N > 1: all_gather of the fixed-stride matcher outputs on a side stream (overlaps the next step)."""
+        """N > 1: all_gather of the fixed-stride matcher outputs on a side stream (overlaps the next step).  The packed
+        buffers are a persistent ring of two (no record_stream(): blocks released under a foreign stream return to
+        the caching allocator at unpredictable times and a step that finds none free pays a cudaMalloc)."""
         nonlocal gathered
         if world == 1:
             return
-        packed = torch.cat([out[0].view(FRAMES, -1).to(torch.float32), out[1].view(FRAMES, -1),
-                            out[2].view(FRAMES, -1), out[3].view(FRAMES, -1)], dim=1)
+        k = ring["k"] % 2
+        ring["k"] += 1
+        parts = [out[0].view(FRAMES, -1).to(torch.float32), out[1].view(FRAMES, -1), out[2].view(FRAMES, -1),
+                 out[3].view(FRAMES, -1)]
+        if ring["buf"][k] is None:
+            ring["buf"][k] = torch.empty((FRAMES, sum(p.shape[1] for p in parts)), dtype=torch.float32, device=dev)
+            ring["ev"][k] = torch.cuda.Event()
+            gathered = gathered if gathered is not None else torch.empty((world,) + tuple(ring["buf"][k].shape),
+                                                                         dtype=torch.float32, device=dev)
+        else:
+            torch.cuda.current_stream().wait_event(ring["ev"][k])    # the all_gather that read this buffer two steps ago
+        packed = ring["buf"][k]
+        torch.cat(parts, dim=1, out=packed)
         done = torch.cuda.Event()
         done.record()
         with torch.cuda.stream(side):
             side.wait_event(done)
-            packed.record_stream(side)
-            if gathered is None:
-                gathered = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=dev)
             dist.all_gather_into_tensor(gathered, packed)
+            ring["ev"][k].record(side)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -336,7 +349,7 @@ def run_gpu(args):
             check += int(out["idx"][0, 0]) + int(out["knn"][0])
         return check
 
-    e2e_run(max(2, args.warmup))
+    e2e_run(max(8, args.warmup))            # every slot of the 3-deep pipeline reused at least twice before timing
     sync_all()
     e2e_steps = max(3, args.steps)
     t0 = time.perf_counter()
