@@ -248,3 +248,53 @@ def test_match_bf16n_operands_and_unit_argmax(cuda):
         assert torch.allclose(unit[1][b].cpu()[same], hard[1][b].cpu()[same], atol=2e-6)
     with pytest.raises(ValueError):                                    # unit scales need normalised columns
         matching.match(rgbd.to(cuda), matching.ModelBank(mesh.to(cuda), xyz[None].to(cuda)), mode="argmax_unit")
+
+
+@pytest.mark.parametrize("env", [{}, {"GADM_MATCH_ALT": "0"}, {"GADM_MATCH_ALT": "0", "GADM_MATCH_RT": "1"},
+                                 {"GADM_MATCH_TA": "1"}, {"GADM_MATCH_FRAG": "1"}, {"GADM_MATCH_FRAG": "2"}])
+def test_match_exact_ties_first_index_wins(cuda, monkeypatch, env):
+    """torch.max returns the FIRST maximal index of the scores it is given (evaluator.py:93).  Model vertices duplicated bit for bit across
+    groups, chunks, column slices, model tiles and (alternating kernel) beyond the tiles after which the slices
+    exchange their running maxima: on every row whose best vertex has copies the smallest index must win -- the stash
+    look-up, the slice / quad merges and the 'no record' sentinel of the exchanges all have to break ties that way."""
+    from gadm_b200 import matching, synth
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    N, M, d = 777, 4608, 128                   # 18 model tiles of 256 (24 of 192), ragged rows
+    g = torch.Generator().manual_seed(5)
+    mesh = synth.bf16_round(torch.randn((1, d, M), generator=g))
+    src = torch.randperm(512, generator=g)[:200]                      # originals in the first two tiles
+    copies = {}
+    for i, c in enumerate(src.tolist()):
+        # a copy in the same 8-column group / chunk / slice / tile, and copies in later tiles (before and after
+        # the exchanges that follow tiles 0, 1, 3, 7, 15)
+        offs = [(c // 8) * 8 + (c + 3) % 8, c + 32 if c % 64 < 32 else c - 32, (c + 64) % 256 + (c // 256) * 256,
+                c + 256 * (1 + i % 3), c + 256 * (4 + i % 12)]
+        for o in offs:
+            if o != c and o not in copies and o not in src.tolist() and 0 <= o < M:
+                mesh[0][:, o] = mesh[0][:, c]
+                copies[o] = c
+    corr = torch.randint(0, M, (1, N), generator=g)                    # planted AFTER the duplication
+    rgbd = synth.bf16_round(mesh[0][:, corr[0]] + 0.3 * torch.randn((d, N), generator=g))[None]
+    # rows planted on a duplicated vertex (or on one of its copies) must report the smallest member of the set
+    groups = {}
+    for o, c in copies.items():
+        groups.setdefault(c, {c}).add(o)
+    want = corr[0].clone()
+    member = {}
+    for c, grp in groups.items():
+        for x in grp:
+            member[x] = min(grp)
+    hit = torch.tensor([int(c) in member for c in corr[0].tolist()])
+    assert hit.sum() > 30
+    for i in torch.where(hit)[0].tolist():
+        want[i] = member[int(corr[0][i])]
+    xyz = synth.fibonacci_sphere(M, 0.2)
+    # (the CPU reference is no arbiter here: its SGEMM sums different columns in different orders, so bit-identical
+    # vertices get scores that differ in the last bit and torch.max picks any of them; the tensor core accumulates
+    # identical operands identically, so the kernel's scores tie exactly and the contract "first index" is testable)
+    ref_idx, _, _ = mo.match_hard(rgbd[0], mesh[0])
+    assert all(member.get(int(a), int(a)) == int(b) for a, b in zip(ref_idx[hit].tolist(), want[hit].tolist()))
+    for mode in ("argmax", "soft"):
+        idx = matching.match(rgbd.to(cuda), mesh.to(cuda), xyz[None].to(cuda), mode=mode)[0][0].cpu()
+        assert torch.equal(idx[hit], want[hit]), f"{mode}: a later copy displaced the first maximal index"
