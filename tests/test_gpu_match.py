@@ -298,3 +298,30 @@ def test_match_exact_ties_first_index_wins(cuda, monkeypatch, env):
     for mode in ("argmax", "soft"):
         idx = matching.match(rgbd.to(cuda), mesh.to(cuda), xyz[None].to(cuda), mode=mode)[0][0].cpu()
         assert torch.equal(idx[hit], want[hit]), f"{mode}: a later copy displaced the first maximal index"
+
+
+@pytest.mark.parametrize("N,M,d", [(5, 8, 64), (129, 264, 128), (128, 256, 64), (257, 8, 128), (1, 8192, 128)])
+def test_match_tiny_and_boundary_shapes(cuda, N, M, d):
+    """Smallest legal sizes and tile boundaries (one scene point, 8 model vertices, exactly one row tile, one row past
+    it): every launch path (single-row-tile fallbacks included), both modes, with and without an all-zero mask."""
+    from gadm_b200 import matching, synth
+    rgbd, mesh, _ = synth.descriptors(2, N, M, d, regime="random", seed=700 + N + M)
+    diam = 0.2
+    xyz = synth.fibonacci_sphere(M, diam)
+    bank = matching.ModelBank(mesh.to(cuda), xyz[None].to(cuda))
+    soft = matching.match(rgbd.to(cuda), bank)
+    hard = matching.match(rgbd.to(cuda), bank, mode="argmax")
+    for b in range(2):
+        ref = mo.match_soft(rgbd[b], mesh[0], xyz)
+        ok = ref["margin"] > TOL
+        for out in (soft, hard):
+            assert torch.equal(out[0][b].cpu()[ok], ref["idx"][ok])
+            assert (out[1][b].cpu() - ref["max_sim"]).abs().max() <= TOL
+        assert ((soft[2][b].cpu() - ref["weight"]).abs() / ref["weight"]).max() <= TOL
+        assert (soft[3][b].cpu() - ref["soft_xyz"]).abs().max() <= TOL * diam
+    none = torch.zeros((2, N), dtype=torch.bool, device=cuda)
+    for mode in ("soft", "argmax"):
+        idx, sim, w, sx = matching.match(rgbd.to(cuda), bank, mask=none, mode=mode)
+        assert torch.all(idx == -1) and torch.all(sim == 0)
+        if mode == "soft":
+            assert torch.all(w == 0) and torch.all(sx == 0)
