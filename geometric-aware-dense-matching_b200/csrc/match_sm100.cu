@@ -1,40 +1,40 @@
 // Fused matching head for sm_100a: descriptor similarity (tcgen05 UMMA, bf16 in / fp32 accumulate in TMEM,
-// operands staged by TMA) + row-wise argmax / online softmax / soft model coordinates.
-// The [N, M] score matrix never leaves TMEM/registers.
+// operands staged by TMA) + row-wise argmax / softmax / soft model coordinates, and its training-side twin
+// (CircleLoss forward / dL/dsim).  The [N, M] score matrix never leaves TMEM / registers.
 //
 // Replaces (reference tree): evaluator.py:89-93 (normalize, normalize, matmul, torch.max) and the padded
-// variants utils/pvn3d_eval_utils_kpls.py:436-444 / models/geoMatch_DGCNN.py:92-99.  The softmax weight
-// and soft coordinates are the extension defined in oracle/match_oracle.py.
+// variants utils/pvn3d_eval_utils_kpls.py:436-444 / models/geoMatch_DGCNN.py:92-99; models/geoMatch.py:55-83,102-157 +
+// models/loss.py:475-490 (circle_kernel).  The softmax weight and soft coordinates are the extension defined in
+// oracle/match_oracle.py.
 //
-// Work decomposition
-//   CTA  = RT row tiles of 128 scene points of one frame (grid = ceil(N / (128 RT)) x B), 18 warps.
-//          ARGMAX uses RT = 2 whenever the operands allow it (K' <= 128): every model tile that TMA brings in from
-//          L2 feeds TWO 128x256 accumulators, which halves the L2 -> SM operand traffic (1.3 GB per 8-frame launch
-//          with RT = 1) and binds each accumulator to its own 8 epilogue warps.
-//     warp 16     TMA producer: the (128 RT) x K' row tile once, then model tiles (256 vertices x 64 k, 32 KB) through
-//                 an S-stage mbarrier ring, plus per tile the column scales 1/|m_j| and (SOFT) the x / y / z planes
-//     warp 17     UMMA issuer: 128x256x16 tcgen05.mma into two 256-column TMEM accumulators.  RT = 1: the two
-//                 accumulators alternate between consecutive model tiles; RT = 2: accumulator r belongs to row tile r
-//                 and the MMAs of (tile t, r = 0), (t, 1), (t+1, 0) ... alternate, so either way the epilogue of one
-//                 accumulator overlaps the MMAs into the other.
-//     warps 0..15 epilogue, thread = row.  RT = 1: warp w owns TMEM lanes 32 (w % 4).. and the 64-column slice w / 4
-//                 of every tile; RT = 2: row tile (w / 4) % 2, 128-column slice w / 8.
-//                 Per 32-column chunk: tcgen05.ld, score = acc * 1/|m_j| (packed f32x2), 3-input max tree per 8
-//                 columns.  The position of the maximum inside its 8-column group is NOT searched in the loop (a
+// Kernels (what runs when: match_launch_t; measurements and bounds: DESIGN.md 3.1, profiles/SUMMARY_r1.md)
+//   match_kernel<soft|argmax, RT>   thread = row; RT row tiles of 128 scene points per CTA.  RT = 1: the two TMEM
+//                                   accumulators alternate between model tiles; RT = 2: accumulator r = row tile r with
+//                                   8 fixed epilogue warps.  The no-workspace ARGMAX path and SOFT for K' > 128.
+//   match_pair_kernel<soft|argmax>  256 rows per CTA, 128-vertex model tiles, every epilogue thread owns the same lane
+//                                   of both row tiles (a per-column constant serves two scores).  Default for SOFT.
+//   match_alt_kernel<exact|unit>    ARGMAX default: two row tiles per CTA, ALL 16 epilogue warps drain one accumulator
+//                                   while the tensor core fills the other; stash in the per-SM workspace slot; running
+//                                   maxima shared across the column slices of a row.  unit: no per-column constant.
+//   match_ta_kernel, match_frag_kernel   opt-in experiments kept parity-green (A operand in tensor memory;
+//                                   tcgen05.ld.16x256b fragment layout): both measured slower, see DESIGN.md.
+//   circle_kernel<fwd|grad>         CircleLoss: masked exponential sums / dL/dsim in the epilogue.
+//
+// Common skeleton
+//     warp 16     TMA producer: the row tile(s) once, then model tiles (256 vertices x 64 k, 32 KB) through an S-stage
+//                 mbarrier ring, plus per tile the column scales 1/|m_j| and (SOFT / circle) the coordinate planes
+//     warp 17     UMMA issuer: 128x256x16 tcgen05.mma into two 256-column TMEM accumulators, tcgen05.commit
+//     warps 0..15 epilogue.  Per 32-column chunk: tcgen05.ld, score = acc * 1/|m_j| (packed f32x2), 3-input max tree
+//                 per 8 columns.  The position of the maximum inside its 8-column group is NOT searched in the loop (a
 //                 search is ~70 warp-divergent instructions and some lane of a warp needs one in most chunks): a
-//                 thread whose running maximum rises stores the group's 8 scores to a private shared-memory stash
-//                 with two predicated STS.128, and the first maximal index is looked up there once, after the last
-//                 tile.  SOFT adds p = 2^(score*g - m_ref) against a LAZY reference exponent (raised, with a rescale
-//                 of the sums, only when exceeded by more than 8), and fp32 sums of p and p * xyz.  The column slices
-//                 of a row merge through shared memory at the end.
-//   What bounds it (tools/epilogue_probe.cu, tools/tmem_probe.cu, tools/umma_probe.cu; profiles/SUMMARY_r1.md): not the
-//   tensor pipe, not TMEM bandwidth and not MUFU (2^x issues every ~2 cycles per scheduler), but the SM's single
-//   MIO / shared-memory pipe.  A broadcast LDS.128 costs ~5 of its cycles, the per-column scales alone are 256 of
-//   them per tile (~1400 cycles against 1024 cycles of MMA), SOFT adds 768 for the coordinate planes, and every
-//   tcgen05.ld queues behind the other warps' LDS / MUFU traffic.  A variant that moves the coordinate sums onto the
-//   tensor core (P rounded to fp16 and stored back over the scores in TMEM, sixteen 128x16x16 tcgen05.mma per tile
-//   against [hi(xyz) | lo(xyz) | 1]) passed parity but its extra TMEM round trips cost what the saved LDS gained;
-//   it is kept under tools/experiments/ with the measurements.
+//                 thread whose running maximum rises stores the group's 8 scores to a private stash with two
+//                 predicated 16-byte stores (shared memory or the L2-resident workspace), and the first maximal index
+//                 is looked up there once, after the last tile.  SOFT adds p = 2^(score * g) (no reference exponent:
+//                 |gamma| <= 40 keeps the sums inside the fp32 range) and fp32 sums of p and p * xyz.  The column
+//                 slices of a row merge through shared memory at the end.
+//   What bounds them: with two row tiles per CTA the UMMA operand reads + TMA writes alone fill the SM's shared-memory
+//   data pipe (1024 wavefronts per 1024-cycle tile), so every epilogue LDS / store wavefront lengthens the tile;
+//   SOFT is additionally capped by MUFU.EX2 (16/clk/SM: 2048 cycles per 128x256 tile).
 #include <cuda_fp16.h>
 #include <float.h>
 #include <stdio.h>

@@ -9,6 +9,11 @@
  *       utils/pvn3d_eval_utils_kpls.py:436-444, models/geoMatch.py:117-119   "-1" pad column variant
  *       models/geoMatch_DGCNN.py:92-99                                       "e0" pad column variant
  *       (+ the soft-correspondence extension: softmax weights and soft model coordinates)
+ *   gadm_circle_loss_fwd / gadm_circle_loss_bwd
+ *       models/geoMatch.py:55-83, 102-157 (geoMatch_DGCNN.py:53-78, 80-136) + models/loss.py:475-490
+ *       pointwise_feature_matching + matching_loss + CircleLoss.forward, and dL/dsim for its backward pass
+ *   gadm_seg_mask
+ *       evaluator.py:78,82            seg argmax -> foreground mask
  *   gadm_kabsch
  *       utils/pvn3d_eval_utils_kpls.py:43-76   best_fit_transform (moments here; 3x3 SVD on the host side)
  *   gadm_knn3d
