@@ -72,16 +72,26 @@ t = float(torch_materialised(False))
 print(f"loss fused {f:.6f}  torch {t:.6f}  rel diff {abs(f - t) / abs(t):.2e}")
 rows, rinv, pad_sim = ops.prep_rows(rgbd.to(dev), 0, 1)
 cols, aux = ops.prep_model(mesh.to(dev), xyz, 0)
-planes = torch.where(vis[None], xyz[0].t()[:, None, :].expand(3, B, M), xyz.new_full((), 1e18)).contiguous()
+planes = torch.empty((4, B, M), device=dev)
+planes[:3] = torch.where(vis[None], xyz[0].t()[:, None, :].expand(3, B, M), xyz.new_full((), 1e18))
+planes[3] = r * r
 fg = torch.ones((B, N), dtype=torch.uint8, device=dev)
-k_fwd = timed(lambda: ops.circle_loss_fwd(rows, rinv, pad_sim, cols, aux, planes, match_idx, fg, None, 16.0, 0.2, r))
-loss, lp_, ln_ = ops.circle_loss_fwd(rows, rinv, pad_sim, cols, aux, planes, match_idx, fg, None, 16.0, 0.2, r)
+k_fwd = timed(lambda: ops.circle_loss_fwd(rows, rinv, pad_sim, cols, aux, planes, match_idx, fg, None, 16.0, 0.2))
+loss, lp_, ln_ = ops.circle_loss_fwd(rows, rinv, pad_sim, cols, aux, planes, match_idx, fg, None, 16.0, 0.2)
 w = torch.full((B, N), 1.0 / (B * N), device=dev)
-k_bwd = timed(lambda: ops.circle_loss_bwd(rows, rinv, pad_sim, cols, aux, planes, match_idx, None, 16.0, 0.2, r, lp_, ln_, w))
+k_bwd = timed(lambda: ops.circle_loss_bwd(rows, rinv, pad_sim, cols, aux, planes, match_idx, None, 16.0, 0.2, lp_, ln_, w))
 flop = 2.0 * N * M * D * B
 print(f"circle_kernel<fwd>  {k_fwd:.3f} ms  ({flop / k_fwd / 1e9:.0f} TFLOP/s of similarity)   "
       f"circle_kernel<grad> {k_bwd:.3f} ms (writes {B * N * (M + 8) * 4 / 1e9:.2f} GB: {B * N * (M + 8) * 4 / k_bwd / 1e6:.0f} GB/s)")
 print(f"fused forward (prep + kernel + reduction)   {timed(fused_fwd):.3f} ms")
 print(f"fused forward + backward                    {timed(fused_fwd_bwd, 3):.3f} ms")
+
+
+def fused_fwd_bwd_tf32():
+    rg.grad = me.grad = None
+    matching.circle_match_loss(rg, me, labels, match_idx, vis, r, model_xyz=xyz, grad_gemm="tf32").backward()
+
+
+print(f"fused forward + backward (tf32 grad GEMMs)  {timed(fused_fwd_bwd_tf32, 3):.3f} ms")
 print(f"torch materialised forward                  {timed(lambda: torch_materialised(False), 3):.3f} ms")
 print(f"torch materialised forward + backward       {timed(lambda: torch_materialised(True), 3):.3f} ms")
