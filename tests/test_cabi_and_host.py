@@ -178,3 +178,16 @@ def test_gather_outputs_gloo_world2(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0 and "ok" in out, out
+
+
+def test_dgcnn_positive_radius_matches_reference_formula():
+    """matching.dgcnn_positive_radius (host logic, torch only) == models/geoMatch_DGCNN.py:64-65 as restated by the
+    oracle: positive_r / 1000 * camera-space depth of every model vertex."""
+    import numpy as np
+    from gadm_b200 import matching
+    from oracle import circle_oracle as co
+    g = np.load(os.path.join(ROOT, "tests", "golden", "circle_golden.npz"))
+    xyz, RT, pr = torch.from_numpy(g["xyz"]), torch.from_numpy(g["RT"]), float(g["dgcnn_positive_r"])
+    got = matching.dgcnn_positive_radius(xyz, RT, pr)
+    want = torch.stack([co.dgcnn_radius(xyz, RT[b], pr) for b in range(RT.shape[0])])
+    assert got.shape == (RT.shape[0], xyz.shape[0]) and torch.allclose(got, want, rtol=1e-6, atol=1e-9)
