@@ -326,6 +326,16 @@ def run_gpu(args):
     vb.record()
     torch.cuda.synchronize()
     unit_ms = va.elapsed_time(vb) / 10
+    # ---- variant: exact argmax on the same bf16n operands (bit-identical to ARGMAX; 32-column chunks that cannot beat a
+    # running maximum are skipped, which is safe because every column scale is <= 1 + 2^-8)
+    for _ in range(3):
+        ops.match_fwd(rows, rinv, pad, cols_n, aux_n, None, obj_id, GAMMA, pm, MATCH_MODES["argmax_bf16n"])
+    va.record()
+    for _ in range(10):
+        ops.match_fwd(rows, rinv, pad, cols_n, aux_n, None, obj_id, GAMMA, pm, MATCH_MODES["argmax_bf16n"])
+    vb.record()
+    torch.cuda.synchronize()
+    pruned_ms = va.elapsed_time(vb) / 10
 
     # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
     # pipeline.FrameStream: pinned host inputs -> H2D -> prep + match + kNN -> D2H of every output into pinned host
@@ -392,9 +402,12 @@ def run_gpu(args):
                          "traffic": 44.63e6, "traffic_unit": "bytes per launch (ncu, round 1)"},
             "variants": {"match_kernel_argmax_only_ms": argmax_ms,
                          "match_kernel_argmax_only_frac": flop_per_launch / (argmax_ms * 1e-3) / 1e12 / peak,
+                         "match_kernel_argmax_bf16n_ms": pruned_ms,
+                         "match_kernel_argmax_bf16n_frac": flop_per_launch / (pruned_ms * 1e-3) / 1e12 / peak,
                          "match_kernel_argmax_unit_ms": unit_ms,
                          "match_kernel_argmax_unit_frac": flop_per_launch / (unit_ms * 1e-3) / 1e12 / peak,
-                         "note": "argmax_only = evaluator.py:89-93 exactly (match_alt_kernel); argmax_unit = same search "
+                         "note": "argmax_only = evaluator.py:89-93 exactly (match_alt_kernel); argmax_bf16n = the same, exact, on columns "
+                                 "normalised before the bf16 rounding (chunk pruning); argmax_unit = same search "
                                  "on bf16n operands without column scales (index may differ only below a 2^-7 |score| "
                                  "margin); the timed step above uses the SOFT kernel"},
             "knn": {"algorithmic_bytes_per_step": pyr.algorithmic_bytes * FRAMES,

@@ -60,7 +60,7 @@ SIGNATURES = {
 
 PAD_MODES = {"none": 0, "minus_one": 1, "e0": 2}
 OPERAND_MODES = {"bf16": 0, "bf16x3": 1, "bf16n": 2}
-MATCH_MODES = {"argmax": 0, "soft": 1, "argmax_unit": 2}
+MATCH_MODES = {"argmax": 0, "soft": 1, "argmax_unit": 2, "argmax_bf16n": 3}
 KNN_ALGOS = {"brute": 0, "grid": 1, "auto": 2}
 
 _lib = None

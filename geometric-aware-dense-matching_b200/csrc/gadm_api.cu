@@ -144,7 +144,7 @@ int gadm_match_fwd(const void* rows, const float* rinv_rows, const float* pad_si
   if (workspace && !aligned16(workspace)) return GADM_ERR_ALIGN;
   if (B <= 0 || N <= 0 || M <= 0 || Kp <= 0 || n_obj <= 0) return GADM_ERR_BAD_ARG;
   if (B > 65535) return GADM_ERR_UNSUPPORTED;
-  if (mode < GADM_MATCH_ARGMAX || mode > GADM_MATCH_ARGMAX_UNIT) return GADM_ERR_UNSUPPORTED;
+  if (mode < GADM_MATCH_ARGMAX || mode > GADM_MATCH_ARGMAX_BF16N) return GADM_ERR_UNSUPPORTED;
   if (mode == GADM_MATCH_SOFT && (!weight || !soft_xyz)) return GADM_ERR_BAD_ARG;
   // 2^(gamma log2(e) cos) is summed without a reference exponent: keep it well inside the fp32 range
   if (mode == GADM_MATCH_SOFT && !(gamma >= -40.f && gamma <= 40.f)) return GADM_ERR_UNSUPPORTED;

@@ -94,7 +94,8 @@ struct MatchParams {
   float gamma_log2e;
   uint8_t* stash;          // fragment-layout kernel: stash_slots slots of FRAG_STASH_BYTES (workspace), else null
   int stash_slots;
-  int unit_scales;         // GADM_MATCH_ARGMAX_UNIT: kernels that can, skip the column scales (the others apply them)
+  int unit_scales;         // 1 = GADM_MATCH_ARGMAX_UNIT: kernels that can, skip the column scales (the others apply them);
+                           // 2 = GADM_MATCH_ARGMAX_BF16N: exact, scales known to be <= 1 + 2^-8 (chunk pruning)
   const void* rows_ptr;    // [B, N, K'] bf16 (match_ta_kernel loads its A operand from global memory)
 };
 
@@ -1289,7 +1290,10 @@ int match_frag_stages(int RT, int KB) {
 // workspace slot (predicated, coalesced STG.128; only the storing thread reads it back).
 // kUnit (GADM_MATCH_ARGMAX_UNIT, operands from GADM_OPERAND_BF16N): the column norms are taken as 1, the epilogue
 // needs no per-column constant at all -- no aux ring, no LDS, no multiply.
-template <bool kUnit>
+// kPrune (GADM_MATCH_ARGMAX_BF16N, same operands): exact scores, but a 32-column chunk is skipped -- no scale LDS, no
+// multiply, no stash -- when max(raw, 0) * (1 + 2^-8) cannot beat the running maximum of any row of the warp: every
+// column scale of BF16N operands is <= 1 / (1 - 2^-9), products round monotonically, so nothing is ever missed.
+template <bool kUnit, bool kPrune>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
                  const MatchParams p) {
@@ -1434,6 +1438,17 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
         // one chunk of 32 columns starting at slice column col0 (see match_kernel)
         auto process = [&](uint32_t (&d)[32], int col0, auto guard_tag) {
           constexpr bool kGuard = decltype(guard_tag)::value;
+          if (kPrune) {
+            float a[11];
+#pragma unroll
+            for (int j = 0; j < 10; ++j)
+              a[j] = ptx::fmax3(__uint_as_float(d[3 * j]), __uint_as_float(d[3 * j + 1]), __uint_as_float(d[3 * j + 2]));
+            a[10] = fmaxf(__uint_as_float(d[30]), __uint_as_float(d[31]));
+            const float b0 = ptx::fmax3(a[0], a[1], a[2]), b1 = ptx::fmax3(a[3], a[4], a[5]);
+            const float b2 = ptx::fmax3(a[6], a[7], a[8]), b3 = fmaxf(a[9], a[10]);
+            const float bound = fmaxf(ptx::fmax3(b0, b1, fmaxf(b2, b3)), 0.f) * 1.00390625f;   // * (1 + 2^-8)
+            if (!__any_sync(0xffffffffu, bound > vmax[r])) return;
+          }
           const uint32_t sc = sc_addr + col0 * 4;
           uint64_t v[16];
 #pragma unroll
@@ -2226,9 +2241,11 @@ int match_configure() {
   if (e != cudaSuccess) return set_cuda_error(e);
   e = cudaFuncSetAttribute(match_ta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
-  e = cudaFuncSetAttribute(match_alt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(match_alt_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
-  e = cudaFuncSetAttribute(match_alt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(match_alt_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(match_alt_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
   e = cudaFuncSetAttribute(match_frag_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
@@ -2307,7 +2324,7 @@ static int match_launch_t(const void* rows, const void* cols, MatchParams p, int
       rc = make_tmap_2b_3d(&tmap_cols, cols, uint64_t(Kp), uint64_t(p.M), uint64_t(p.n_obj), BK, TBN, 0);
       if (rc != GADM_OK) return rc;
       dim3 grid((p.N + 2 * BM - 1) / (2 * BM), p.B);
-      if (p.unit_scales)
+      if (p.unit_scales == 1)
         match_ta_kernel<true><<<grid, NUM_THREADS, match_ta_smem_bytes(p.stages), stream>>>(tmap_rows, tmap_cols, p);
       else
         match_ta_kernel<false><<<grid, NUM_THREADS, match_ta_smem_bytes(p.stages), stream>>>(tmap_rows, tmap_cols, p);
@@ -2328,10 +2345,12 @@ static int match_launch_t(const void* rows, const void* cols, MatchParams p, int
       rc = make_tmap_2b_3d(&tmap_cols, cols, uint64_t(Kp), uint64_t(p.M), uint64_t(p.n_obj), BK, BN, 0);
       if (rc != GADM_OK) return rc;
       dim3 grid((p.N + 2 * BM - 1) / (2 * BM), p.B);
-      if (p.unit_scales)
-        match_alt_kernel<true><<<grid, NUM_THREADS, match_alt_smem_bytes(KB, astages), stream>>>(tmap_rows, tmap_cols, p);
+      if (p.unit_scales == 1)
+        match_alt_kernel<true, false><<<grid, NUM_THREADS, match_alt_smem_bytes(KB, astages), stream>>>(tmap_rows, tmap_cols, p);
+      else if (p.unit_scales == 2)
+        match_alt_kernel<false, true><<<grid, NUM_THREADS, match_alt_smem_bytes(KB, astages), stream>>>(tmap_rows, tmap_cols, p);
       else
-        match_alt_kernel<false><<<grid, NUM_THREADS, match_alt_smem_bytes(KB, astages), stream>>>(tmap_rows, tmap_cols, p);
+        match_alt_kernel<false, false><<<grid, NUM_THREADS, match_alt_smem_bytes(KB, astages), stream>>>(tmap_rows, tmap_cols, p);
       return check_launch();
     }
   }
@@ -2397,7 +2416,7 @@ int match_launch(const void* rows, const float* rinv_rows, const float* pad_sim,
   p.idx = idx; p.max_sim = max_sim; p.weight = weight; p.soft_xyz = soft_xyz;
   p.B = B; p.N = N; p.M = M; p.KB = 0; p.n_obj = n_obj; p.stages = 0; p.pad_mode = pad_mode;
   p.gamma_log2e = gamma * 1.4426950408889634f;
-  p.unit_scales = mode == GADM_MATCH_ARGMAX_UNIT;
+  p.unit_scales = mode == GADM_MATCH_ARGMAX_UNIT ? 1 : mode == GADM_MATCH_ARGMAX_BF16N ? 2 : 0;
   p.rows_ptr = rows;
   if (mode == GADM_MATCH_SOFT) return match_launch_t<true>(rows, cols, p, Kp, stream);
   return match_launch_t<false>(rows, cols, p, Kp, stream);

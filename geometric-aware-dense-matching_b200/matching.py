@@ -67,8 +67,10 @@ def match(rgbd, mesh, model_xyz=None, obj_id=None, mask=None, gamma=16.0, pad_mo
         mask = mask.to(torch.uint8).contiguous()
     if obj_id is not None:
         obj_id = torch.as_tensor(obj_id, device=rgbd.device).to(torch.int32).contiguous()
+    # exact argmax on a bank whose columns were normalised before the rounding: same results, chunk pruning allowed
+    kmode = "argmax_bf16n" if mode == "argmax" and bank.operand_mode == "bf16n" else mode
     idx, max_sim, weight, soft_xyz = ops.match_fwd(rows, rinv, pad_sim, bank.cols, bank.aux, mask, obj_id,
-                                                   float(gamma), pm, MATCH_MODES[mode])
+                                                   float(gamma), pm, MATCH_MODES[kmode])
     if mode != "soft":
         return idx, max_sim, None, None
     return idx, max_sim, weight, soft_xyz

@@ -83,8 +83,11 @@ enum { GADM_OPERAND_BF16 = 0, GADM_OPERAND_BF16X3 = 1, GADM_OPERAND_BF16N = 2 };
  * DURING THE SEARCH (no per-column constant in the epilogue: the fastest kernel); the winner's similarity is
  * reported with its true scale.  The searched scores differ from ARGMAX's by the factor ||bf16 column|| =
  * 1 +- 2^-8 at most (~3e-4 rms at d = 128), so the index can differ from ARGMAX's only on rows whose top-1
- * margin is below |score| * 2^-7; falls back to ARGMAX when the unit kernel does not apply.                 */
-enum { GADM_MATCH_ARGMAX = 0, GADM_MATCH_SOFT = 1, GADM_MATCH_ARGMAX_UNIT = 2 };
+ * margin is below |score| * 2^-7; falls back to ARGMAX when the unit kernel does not apply.
+ * ARGMAX_BF16N = ARGMAX (same results, bit for bit) for operands prepared with GADM_OPERAND_BF16N: the caller asserts
+ * that every column scale is <= 1 + 2^-8, which lets the kernel skip whole 32-column chunks whose raw maximum cannot
+ * beat a running maximum (no scale loads, no multiplies for ~60 % of the chunks).                              */
+enum { GADM_MATCH_ARGMAX = 0, GADM_MATCH_SOFT = 1, GADM_MATCH_ARGMAX_UNIT = 2, GADM_MATCH_ARGMAX_BF16N = 3 };
 
 /* K' for a given d / operand_mode (d for BF16 and BF16N, 3d for BF16X3). */
 int gadm_operand_k(int d, int operand_mode);

@@ -233,6 +233,12 @@ def test_match_bf16n_operands_and_unit_argmax(cuda):
     hard = matching.match(rgbd.to(cuda), bank, operand_mode="bf16n", mode="argmax")
     unit = matching.match(rgbd.to(cuda), bank, operand_mode="bf16n", mode="argmax_unit")
     assert unit[2] is None and unit[3] is None
+    # mode="argmax" on a bf16n bank runs GADM_MATCH_ARGMAX_BF16N (chunk pruning): bit-identical to the unpruned kernel
+    from gadm_b200 import ops
+    from gadm_b200._lib import MATCH_MODES
+    rows, rinv, pad = ops.prep_rows(rgbd.to(cuda), 2, 0)
+    plain = ops.match_fwd(rows, rinv, pad, bank.cols, bank.aux, None, None, 16.0, 0, MATCH_MODES["argmax"])
+    assert torch.equal(plain[0], hard[0]) and torch.equal(plain[1], hard[1])
     for b in range(B):
         ref_n = mo.match_soft(rgbd[b], mesh_n, xyz)                    # (1) exact w.r.t. the rounded operands
         _check([o[b] for o in out], ref_n, M, diam)

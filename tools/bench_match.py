@@ -17,7 +17,7 @@ rows, rinv, pad = ops.prep_rows(rgbd.to(dev), 0, 0)
 flop = 2.0 * N * M * D * B
 if os.environ.get("OPERAND", "bf16") == "bf16n":
     cols, aux = ops.prep_model(mesh.to(dev), xyz, 2)
-for mode in (("argmax_unit",) if os.environ.get("OPERAND", "bf16") == "bf16n" else ()) + ("argmax", "soft"):
+for mode in (("argmax_unit", "argmax_bf16n") if os.environ.get("OPERAND", "bf16") == "bf16n" else ()) + ("argmax", "soft"):
     for _ in range(3):
         ops.match_fwd(rows, rinv, pad, cols, aux, None, obj, 16.0, 0, MATCH_MODES[mode])
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
