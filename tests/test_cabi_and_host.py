@@ -191,3 +191,24 @@ def test_dgcnn_positive_radius_matches_reference_formula():
     got = matching.dgcnn_positive_radius(xyz, RT, pr)
     want = torch.stack([co.dgcnn_radius(xyz, RT[b], pr) for b in range(RT.shape[0])])
     assert got.shape == (RT.shape[0], xyz.shape[0]) and torch.allclose(got, want, rtol=1e-6, atol=1e-9)
+
+
+def test_bf16n_column_scales_stay_below_the_pruning_bound():
+    """GADM_MATCH_ARGMAX_BF16N skips a chunk when max(raw, 0) * (1 + 2^-8) cannot beat a running maximum; that is exact
+    only if every column scale 1 / ||bf16(normalised column)|| is <= 1 + 2^-8.  Round-to-nearest bf16 has a relative
+    error <= 2^-9 per element, so ||.|| >= 1 - 2^-9: checked here on random, sparse, constant and worst-case columns
+    (every element just above a rounding midpoint) for d = 64 .. 256, emulating gadm_prep_model's BF16N path."""
+    import torch.nn.functional as F
+    bound = 1.0 + 2.0 ** -8
+    g = torch.Generator().manual_seed(9)
+    for d in (64, 128, 192, 256):
+        cols = [torch.randn((d, 4096), generator=g), torch.randn((d, 512), generator=g) * (torch.rand((d, 512), generator=g) < 0.05),
+                torch.ones((d, 8)), torch.eye(d)[:, :8]]
+        # worst case for the norm: every element rounds DOWN by almost half an ulp after the normalisation
+        w = torch.full((d, 8), 1.0) + 2.0 ** -8 * 0.999
+        cols.append(w * torch.tensor([1.0, 2.0, 0.5, 3.0, 7.0, 0.1, 11.0, 1e-3])[None])
+        for m in cols:
+            m = m[:, m.norm(dim=0) > 0]
+            mt = F.normalize(m.float(), p=2, dim=0).to(torch.bfloat16).float()
+            scale = 1.0 / mt.norm(dim=0).clamp_min(1e-12)
+            assert float(scale.max()) <= bound, (d, float(scale.max()))
