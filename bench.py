@@ -42,6 +42,52 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+class near_gpu:
+    """with near_gpu(torch, index): the calling THREAD runs on the CPUs of the NUMA node the GPU hangs off, so that the
+    pinned host buffers allocated inside land next to it (H2D over PCIe from the far socket is what makes the end-to-end
+    leg vary from run to run).  Only the calling thread is moved and its affinity is restored on exit: worker threads
+    (torch's CPU pool, created beforehand) and the CPU-baseline leg keep every core.  Best effort: .node is None when
+    the topology is not visible (containers often hide it)."""
+
+    def __init__(self, torch, index):
+        self.torch, self.index, self.node, self.saved = torch, index, None, None
+
+    def __enter__(self):
+        self.saved = os.sched_getaffinity(0)
+        self.node = bind_to_gpu_numa_node(self.torch, self.index)
+        return self
+
+    def __exit__(self, *exc):
+        try:
+            os.sched_setaffinity(0, self.saved)
+        except Exception:
+            pass
+        return False
+
+
+def bind_to_gpu_numa_node(torch, index):
+    try:
+        prop = torch.cuda.get_device_properties(index)
+        bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)              # never leave the cgroup's own set
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -170,6 +216,7 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    torch.randn(1 << 20).sum()                       # torch's CPU worker pool exists (with every core) from here on
     dev = torch.device("cuda", local)
     if world > 1:
         # NCCL prints its version to stdout when the communicator is created; stdout must carry the one JSON line only
@@ -192,7 +239,9 @@ def run_gpu(args):
         seed = 2000 + 97 * r + 1000 * rank
         rgbd, mesh, _ = synth.descriptors(FRAMES, N_PTS, M_VERTS, D, n_obj=N_OBJ, regime="planted", seed=seed)
         cld, sr = synth.frame_batch(FRAMES, IN_SIZE, N_PTS, seed=seed)
-        h = {"rgbd": rgbd.pin_memory(), "cld": cld.pin_memory(), "sr": {s: sr[s].pin_memory() for s in (2, 4, 8)}}
+        with near_gpu(torch, local) as ng:          # pinned pages next to the GPU
+            h = {"rgbd": rgbd.pin_memory(), "cld": cld.pin_memory(), "sr": {s: sr[s].pin_memory() for s in (2, 4, 8)}}
+        numa = ng.node
         host.append(h)
         res.append({"rgbd": rgbd.to(dev), "mesh": mesh.to(dev), "cld": cld.to(dev),
                     "sr": {s: sr[s].to(dev) for s in (2, 4, 8)}})
@@ -343,7 +392,8 @@ def run_gpu(args):
     # that the H2D copies, which bound this path (54 MB per step over PCIe), run back to back.
     from gadm_b200.pipeline import FrameStream
     bank = matching.ModelBank(res[0]["mesh"], xyz)
-    fs = FrameStream(bank, pyr, FRAMES, D, N_PTS, obj_id=obj_id, gamma=GAMMA, mode="soft", depth=3)
+    with near_gpu(torch, local):
+        fs = FrameStream(bank, pyr, FRAMES, D, N_PTS, obj_id=obj_id, gamma=GAMMA, mode="soft", depth=3)
     h2d, d2h = fs.h2d_bytes, fs.d2h_bytes
 
     def e2e_run(n):
@@ -389,7 +439,8 @@ def run_gpu(args):
                        "l2": f"rotating {ROT} resident input batches (~{ROT * 85} MB > 126 MB L2)",
                        "streams": "prep + match on the main stream, kNN pyramid on a second stream" if not args.no_overlap
                        else "one stream",
-                       "collective": "all_gather of matcher outputs on a side stream" if world > 1 else "none"},
+                       "collective": "all_gather of matcher outputs on a side stream" if world > 1 else "none",
+                       "numa_node": numa},
             "breakdown_ms": {"match_kernel": match_ms, "knn_pyramid": knn_ms,
                              "note": ("serial: prep, match, kNN" if args.no_overlap else
                                       "the kNN pyramid runs on a second stream under the matcher; "
