@@ -112,12 +112,14 @@ int gadm_prep_model(const float* mesh, const float* model_xyz, int n_obj, int d,
  * exists in HBM.  For frame b the model is obj_id[b] (NULL: b if n_obj == B, else 0).
  *   mask [B, N] uint8 or NULL: rows with mask == 0 get idx = -1 and zeros.
  *   idx [B, N] int64 (M means "pad column won"), max_sim [B, N] fp32,
- *   weight [B, N] fp32 and soft_xyz [B, N, 3] fp32 (may be NULL when mode == GADM_MATCH_ARGMAX).
+ *   weight [B, N] fp32 and soft_xyz [B, N, 3] fp32 (may be NULL unless mode == GADM_MATCH_SOFT).
  * Kp = K' from gadm_operand_k(); must be a multiple of 64 and <= 768.
- * workspace (optional, 16-byte aligned, gadm_match_workspace_bytes() bytes, contents irrelevant on entry and
- * exit): scratch for the fragment-layout kernel, the fastest one for K' <= 128; one workspace serves one launch
- * at a time (launches that may overlap on different streams need one each).  NULL selects the kernels that need
- * none.  Results are identical either way.                                                             */
+ * gamma (SOFT): softmax temperature, |gamma| <= 40 (the terms 2^(gamma log2(e) cos) are summed without a reference
+ * exponent; GADM_ERR_UNSUPPORTED beyond that).
+ * workspace (optional, 16-byte aligned, gadm_match_workspace_bytes() bytes = 64 KB per SM, contents irrelevant on
+ * entry and exit): argmax scratch of the alternating kernels, the fastest ARGMAX path for K' <= 128.  Give launches
+ * that may overlap on different streams one workspace each.  NULL selects the kernels that need none; results are
+ * identical either way.                                                                                  */
 size_t gadm_match_workspace_bytes(void);
 int gadm_match_fwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
                    const float* aux, const uint8_t* mask, const int32_t* obj_id, int B, int N, int M, int Kp,
