@@ -1,6 +1,12 @@
 #!/bin/bash
 # Timing experiments (NOT product builds; results of the variants are wrong by construction): libgadm.so variants with
 # one epilogue ingredient removed, to see what bounds the matcher.   build (here) / run (GPU box)
+#   VARS="BASE NOEPI NOSTASH NOLDS NOMUFU NOMAX LDONLY" tools/variants_match.sh build      (-DGADM_DBG_<name>)
+#   NOEPI   no epilogue at all: the TMA -> UMMA -> commit pipeline ceiling (match_kernel, pair, frag, TMEM-A kernels)
+#   NOSTASH / NOLDS / NOMUFU / NOMAX / LDONLY: fragment-layout kernel without stash stores / constant loads /
+#   exponentials / max tree + stash / everything but the TMEM loads.
+#   Select the kernel under test at run time with GADM_MATCH_FRAG / GADM_MATCH_TA / GADM_MATCH_ALT / GADM_MATCH_PAIR /
+#   GADM_MATCH_RT (see match_launch_t); results: profiles/SUMMARY_r1.md.
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 T=$ROOT/tools/_variants
