@@ -26,6 +26,7 @@ SIGNATURES = {
     "gadm_strerror": (ctypes.c_char_p, [c_int]),
     "gadm_abi_version": (c_int, []),
     "gadm_init": (c_int, [c_int]),
+    "gadm_config_set": (c_int, [ctypes.c_char_p, c_int]),
     "gadm_last_cuda_error": (ctypes.c_char_p, []),
     "gadm_operand_k": (c_int, [c_int, c_int]),
     "gadm_aux_floats": (c_size_t, [c_int, c_int]),
@@ -96,6 +97,11 @@ def check(rc, what):
         if rc == -5:
             msg += ": " + lib.gadm_last_cuda_error().decode()
         raise GadmError(f"{what} failed ({rc}): {msg}")
+
+
+def config_set(key: str, value: int):
+    """gadm_config_set: kernel-selection switches for profiling and tests (-1 = automatic)."""
+    check(load().gadm_config_set(key.encode(), int(value)), f"gadm_config_set({key})")
 
 
 def ensure_init(device_index):

@@ -69,7 +69,12 @@ const char* gadm_strerror(int status) {
   }
 }
 
-int gadm_abi_version(void) { return 2; }
+int gadm_abi_version(void) { return 3; }
+
+int gadm_config_set(const char* key, int value) {
+  if (!key) return GADM_ERR_BAD_ARG;
+  return match_config_set(key, value);
+}
 
 const char* gadm_last_cuda_error(void) { return g_cuda_err; }
 
@@ -91,7 +96,9 @@ int gadm_init(int device) {
     }
     g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
   }
-  int rc = match_configure();
+  int rc = match_configure(device);
+  if (rc != GADM_OK) return rc;
+  rc = circle_configure();
   if (rc != GADM_OK) return rc;
   rc = knn3d_configure();
   if (rc != GADM_OK) return rc;
@@ -143,7 +150,6 @@ int gadm_match_fwd(const void* rows, const float* rinv_rows, const float* pad_si
   if (!rows || !rinv_rows || !cols || !aux || !idx || !max_sim) return GADM_ERR_BAD_ARG;
   if (workspace && !aligned16(workspace)) return GADM_ERR_ALIGN;
   if (B <= 0 || N <= 0 || M <= 0 || Kp <= 0 || n_obj <= 0) return GADM_ERR_BAD_ARG;
-  if (B > 65535) return GADM_ERR_UNSUPPORTED;
   if (mode < GADM_MATCH_ARGMAX || mode > GADM_MATCH_ARGMAX_BF16N) return GADM_ERR_UNSUPPORTED;
   if (mode == GADM_MATCH_SOFT && (!weight || !soft_xyz)) return GADM_ERR_BAD_ARG;
   // 2^(gamma log2(e) cos) is summed without a reference exponent: keep it well inside the fp32 range

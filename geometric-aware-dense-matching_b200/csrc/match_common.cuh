@@ -1,0 +1,95 @@
+// Shared definitions of the tcgen05 matcher kernels (match_sm100.cu) and the CircleLoss kernel (circle_sm100.cu).
+#pragma once
+#include <cuda_fp16.h>
+#include <float.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <type_traits>
+
+#include "gadm_internal.h"
+#include "ptx.cuh"
+
+namespace gadm {
+namespace {
+
+constexpr int BM = 128;               // rows (scene points) per row tile == UMMA M
+constexpr int BK = 64;                // bf16 elements per 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_BLK_BYTES = BM * BK * 2;     // 16 KB
+constexpr int MAX_STAGES = 6;
+constexpr int BN = 256;               // model vertices per accumulator tile == UMMA N
+constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
+constexpr int AUX_SLOTS = 4;                 // per-tile {1/|m|, x, y, z} ring, decoupled from the two accumulators
+constexpr int PLANE_BYTES = BN * 4;          // one fp32 plane of a tile
+constexpr int EPI_WARPS = 16;
+constexpr int NUM_THREADS = (EPI_WARPS + 2) * 32;   // warps 0-15 epilogue, 16 TMA, 17 UMMA
+constexpr int GRP = 8;                                 // columns per argmax group (stash granularity)
+constexpr int STASH_BYTES = EPI_WARPS * 32 * GRP * 4;  // per epilogue thread: the 8 scores of its best group
+constexpr int STASH_PLANE = EPI_WARPS * 32 * 16;       // float4 k of thread t lives at k * STASH_PLANE + t * 16
+static_assert(STASH_PLANE == 8192, "ptx::sts_stash8 hard-codes the plane stride");
+constexpr int TMEM_COLS = 512;
+
+constexpr int STASH_SLOT_BYTES = EPI_WARPS * 32 * 4 * 32;   // per-SM argmax stash slot of the workspace (64 KB)
+constexpr int NO_RECORD = 0x40000000;                       // index of a track that holds no record (loses every tie)
+constexpr int PART_ROWS = 2 * BM;                           // rows of a row block (two row tiles)
+
+struct Barriers {
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
+  uint64_t a_full;
+  uint64_t a_free;       // persistent kernels: every MMA that reads the row tiles of the segment has completed
+  uint64_t s_full[2];    // accumulator a complete (UMMA commit)
+  uint64_t s_free[2];    // accumulator a drained by all of its epilogue warps
+  uint64_t aux_full[AUX_SLOTS];
+  uint64_t aux_empty[AUX_SLOTS];
+  uint32_t tmem_base;
+  int merge_lo, merge_hi;   // persistent kernels: CTA range whose partial results this CTA has to merge (lo < 0: none)
+  uint32_t pad;
+};
+
+struct MatchParams {
+  const float* rinv_rows;  // [B, N]
+  const float* pad_sim;    // [B, N] or null
+  const float* scales;     // [n_obj, M]  1/|m_j|
+  const float* planes;     // [3, n_obj, M] model x / y / z planes (SOFT)
+  const void* vt;          // [n_obj, 16, Mp] fp16 V^T of the tensor-core coordinate sums (match_fa_kernel)
+  const void* rows_ptr;    // [B, N, K'] bf16 rows (match_fa_kernel loads its A operand into tensor memory itself)
+  const uint8_t* mask;     // [B, N] or null
+  const int32_t* obj_id;   // [B] or null
+  int64_t* idx;
+  float* max_sim;
+  float* weight;
+  float* soft_xyz;
+  int B, N, M, KB, n_obj, stages;
+  int pad_mode;
+  float gamma_log2e;
+  uint8_t* stash;          // stash_slots slots of STASH_SLOT_BYTES (workspace, indexed by %smid), else null
+  int stash_slots;
+  // persistent kernels: the (frame, row block, model tile) units are dealt out evenly, in linear order, to the CTAs of
+  // the grid; a row block whose tiles end up in several CTAs is finished by the last of them to arrive
+  int T;                   // model tiles per row
+  int RB;                  // row blocks (PART_ROWS rows) per frame
+  long long total_units;   // B * RB * T
+  unsigned int* seg_count; // [grid] arrival counters (workspace, zeroed by the launcher)
+  float* partial;          // [grid][2][PART_ROWS][8] partial results (workspace)
+  int unit_scales;         // 1 = GADM_MATCH_ARGMAX_UNIT: kernels that can, skip the column scales (the others apply them);
+                           // 2 = GADM_MATCH_ARGMAX_BF16N: exact, scales known to be <= 1 + 2^-8 (chunk pruning)
+};
+
+// first unit of CTA c (c == gridDim.x: one past the last unit)
+__device__ __forceinline__ long long sched_begin(const MatchParams& p, int c) {
+  return (long long)c * p.total_units / (long long)gridDim.x;
+}
+// the CTA whose range holds unit u: the largest c with sched_begin(c) <= u
+__device__ __forceinline__ int sched_cta_of(const MatchParams& p, long long u) {
+  return int(((u + 1) * (long long)gridDim.x - 1) / p.total_units);
+}
+
+__device__ __forceinline__ int frame_object(const MatchParams& p, int b) {
+  if (p.obj_id) return p.obj_id[b];
+  return p.n_obj == p.B ? b : 0;
+}
+
+}  // namespace
+}  // namespace gadm

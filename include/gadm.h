@@ -14,8 +14,8 @@
  *       pointwise_feature_matching + matching_loss + CircleLoss.forward, and dL/dsim for its backward pass
  *   gadm_seg_mask
  *       evaluator.py:78,82            seg argmax -> foreground mask
- *   gadm_kabsch
- *       utils/pvn3d_eval_utils_kpls.py:43-76   best_fit_transform (moments here; 3x3 SVD on the host side)
+ *   gadm_kabsch_moments
+ *       utils/pvn3d_eval_utils_kpls.py:43-76   best_fit_transform (the moments of the two point sets)
  *   gadm_knn3d
  *       models/RandLA/utils/nearest_neighbors/knn_.h:11-17 / knn_.cxx:71-135   cpp_knn_batch(_omp)
  *       models/RandLA/helper_tool.py:161-170                                   DataProcessing.knn_search
@@ -31,9 +31,12 @@
  *
  * Conventions
  *   - All tensor pointers are DEVICE pointers unless a parameter says HOST.  The caller owns all memory,
- *     including workspaces; the library never allocates or frees device memory and never synchronises.
+ *     including workspaces; the library never allocates or frees device memory.  gadm_init() is the only call
+ *     that may synchronise the device; every other call only enqueues work.
  *   - Every call enqueues work on `stream` and returns 0 (GADM_OK) or a negative gadm_status.  No exceptions.
- *   - Re-entrant: no mutable global state after gadm_init().
+ *   - Re-entrant: after gadm_init() the only mutable global state is the set of switches of gadm_config_set()
+ *     (kernel selection for profiling and tests; read once per call, never from the environment).  gadm_init()
+ *     keeps what it learns about a device (SM count) per device: call it once for every device that is used.
  *   - The cubin is sm_100a only.  gadm_init() fails with GADM_ERR_ARCH elsewhere; there is no fallback.
  */
 #ifndef GADM_H_
@@ -61,8 +64,14 @@ typedef enum {
 
 const char* gadm_strerror(int status);
 int gadm_abi_version(void);
-/* Checks the device (cc 10.x), resolves cuTensorMapEncodeTiled, raises the kernels' shared-memory limits. */
+/* Checks the device (cc 10.x), resolves cuTensorMapEncodeTiled, raises the kernels' shared-memory limits and records
+ * the device's SM count (per device).  Makes `device` current. */
 int gadm_init(int device);
+/* Kernel-selection switches for profiling and tests; -1 restores the automatic choice.  Keys:
+ *   "match.alt"   0 forbids the alternating persistent ARGMAX kernel        "match.pair"  1 / 0 forces / forbids the paired-row kernel
+ *   "match.rt"    1 / 2 row tiles per CTA of the generic kernel             "match.ctas"  grid of the persistent kernels (<= SM count)
+ * Results do not depend on any of them.  GADM_ERR_BAD_ARG for an unknown key. */
+int gadm_config_set(const char* key, int value);
 /* cudaGetLastError text of the most recent GADM_ERR_CUDA on this thread ("" if none). */
 const char* gadm_last_cuda_error(void);
 
@@ -116,10 +125,11 @@ int gadm_prep_model(const float* mesh, const float* model_xyz, int n_obj, int d,
  * Kp = K' from gadm_operand_k(); must be a multiple of 64 and <= 768.
  * gamma (SOFT): softmax temperature, |gamma| <= 40 (the terms 2^(gamma log2(e) cos) are summed without a reference
  * exponent; GADM_ERR_UNSUPPORTED beyond that).
- * workspace (optional, 16-byte aligned, gadm_match_workspace_bytes() bytes = 64 KB per SM, contents irrelevant on
- * entry and exit): argmax scratch of the alternating kernels, the fastest ARGMAX path for K' <= 128.  Give launches
- * that may overlap on different streams one workspace each.  NULL selects the kernels that need none; results are
- * identical either way.                                                                                  */
+ * workspace (optional, 16-byte aligned, gadm_match_workspace_bytes() bytes on the current device -- about 80 KB per
+ * SM: argmax scratch, arrival counters and partial results of the persistent kernels; contents irrelevant on entry
+ * and exit).  The persistent kernels deal the (frame, 256-row block, model tile) units out evenly to one CTA per SM
+ * and need it.  Give launches that may overlap on different streams one workspace each.  NULL selects the kernels
+ * that need none; results are identical either way.                                                      */
 size_t gadm_match_workspace_bytes(void);
 int gadm_match_fwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
                    const float* aux, const uint8_t* mask, const int32_t* obj_id, int B, int N, int M, int Kp,

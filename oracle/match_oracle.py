@@ -47,6 +47,15 @@ def seg_mask(seg_features):
     return torch.argmax(seg_features, dim=0) == 1
 
 
+def match_ref(rgbd_features, mesh_features, row_mask=None, pad_mode=PAD_NONE):
+    """Exactly evaluator.py:89-93 and nothing else: normalize, normalize, matmul, torch.max -> (idx, max_sim).
+    This is what the CPU arms of bench.py time (match_hard below adds a top-2 for the parity margin, which the
+    reference does not run)."""
+    S = similarity(rgbd_features, mesh_features, row_mask, pad_mode)
+    max_sim, idx = torch.max(S, dim=1)                 # evaluator.py:93
+    return idx, max_sim
+
+
 def match_hard(rgbd_features, mesh_features, row_mask=None, pad_mode=PAD_NONE):
     """-> (idx int64 [n_sel], max_sim fp32 [n_sel], margin fp32 [n_sel]).  evaluator.py:93.
     margin = top1 - top2 of the row, used by the parity gate (exact where margin > 1e-3)."""

@@ -186,19 +186,33 @@ def test_seg_mask_matches_torch_argmax(cuda):
     assert torch.equal(got.bool(), torch.argmax(seg, dim=1) == 1)
 
 
-@pytest.mark.parametrize("env", [{"GADM_MATCH_ALT": "0", "GADM_MATCH_PAIR": "0", "GADM_MATCH_RT": "1"},
-                                 {"GADM_MATCH_ALT": "0", "GADM_MATCH_PAIR": "0", "GADM_MATCH_RT": "2"},
-                                 {"GADM_MATCH_ALT": "0", "GADM_MATCH_PAIR": "1"},
-                                 {"GADM_MATCH_ALT": "1"}, {"GADM_MATCH_TA": "1"},
-                                 {"GADM_MATCH_FRAG": "1"}, {"GADM_MATCH_FRAG": "2"}])
-def test_match_kernel_variants_agree(cuda, monkeypatch, env):
-    """The kernels of the matcher (one row tile per CTA, two row tiles per CTA, paired rows per thread, alternating
-    accumulators with A in shared memory / in tensor memory, fragment layout with four rows per thread on one / two row tiles per CTA) are selected per launch; every one of them must meet the same gates
-    on a ragged shape, in both modes."""
+@pytest.fixture
+def cfg():
+    """gadm_config_set switches for one test; restored to automatic afterwards."""
+    from gadm_b200 import _lib
+    used = []
+
+    def set_(switches):
+        for k, v in switches.items():
+            _lib.config_set(k, v)
+            used.append(k)
+    yield set_
+    for k in used:
+        _lib.config_set(k, -1)
+
+
+@pytest.mark.parametrize("env", [{"match.alt": 0, "match.pair": 0, "match.rt": 1},
+                                 {"match.alt": 0, "match.pair": 0, "match.rt": 2},
+                                 {"match.alt": 0, "match.pair": 1},
+                                 {"match.alt": 1}, {"match.ctas": 5}, {"match.ctas": 37}, {"match.ctas": 1}])
+def test_match_kernel_variants_agree(cuda, cfg, env):
+    """The kernels of the matcher (one row tile per CTA, two row tiles per CTA, paired rows per thread, the
+    persistent kernels with their units dealt out to 148 / 37 / 5 / 1 CTAs -- row blocks split over two or more
+    CTAs and merged by the last to arrive) are selected per launch; every one of them must meet the same gates on a
+    ragged shape, in both modes."""
     from gadm_b200 import matching, synth
     from oracle import match_oracle as mo
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
+    cfg(env)
     N, M, d = 1500, 2056, 128                  # ragged in rows (1500 = 5 * 256 + 220) and in model tiles (2056 = 8 * 256 + 8)
     rgbd, mesh, _ = synth.descriptors(1, N, M, d, regime="planted", seed=77)
     xyz = synth.fibonacci_sphere(M, 0.2)
@@ -256,16 +270,15 @@ def test_match_bf16n_operands_and_unit_argmax(cuda):
         matching.match(rgbd.to(cuda), matching.ModelBank(mesh.to(cuda), xyz[None].to(cuda)), mode="argmax_unit")
 
 
-@pytest.mark.parametrize("env", [{}, {"GADM_MATCH_ALT": "0"}, {"GADM_MATCH_ALT": "0", "GADM_MATCH_RT": "1"},
-                                 {"GADM_MATCH_TA": "1"}, {"GADM_MATCH_FRAG": "1"}, {"GADM_MATCH_FRAG": "2"}])
-def test_match_exact_ties_first_index_wins(cuda, monkeypatch, env):
+@pytest.mark.parametrize("env", [{}, {"match.alt": 0}, {"match.alt": 0, "match.rt": 1},
+                                 {"match.ctas": 3}, {"match.ctas": 11}, {"match.ctas": 50}])
+def test_match_exact_ties_first_index_wins(cuda, cfg, env):
     """torch.max returns the FIRST maximal index of the scores it is given (evaluator.py:93).  Model vertices duplicated bit for bit across
     groups, chunks, column slices, model tiles and (alternating kernel) beyond the tiles after which the slices
     exchange their running maxima: on every row whose best vertex has copies the smallest index must win -- the stash
     look-up, the slice / quad merges and the 'no record' sentinel of the exchanges all have to break ties that way."""
     from gadm_b200 import matching, synth
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
+    cfg(env)
     N, M, d = 777, 4608, 128                   # 18 model tiles of 256 (24 of 192), ragged rows
     g = torch.Generator().manual_seed(5)
     mesh = synth.bf16_round(torch.randn((1, d, M), generator=g))

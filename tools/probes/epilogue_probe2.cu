@@ -5,7 +5,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
-#include "../geometric-aware-dense-matching_b200/csrc/ptx.cuh"
+#include "../../geometric-aware-dense-matching_b200/csrc/ptx.cuh"
 using namespace gadm;
 
 // SOFT: 1 = soft, 0 = argmax.  FREE: non-volatile LDS.  EARLY: scale LDS issued before the tcgen05.ld wait.

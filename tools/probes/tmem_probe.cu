@@ -4,7 +4,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
-#include "../geometric-aware-dense-matching_b200/csrc/ptx.cuh"
+#include "../../geometric-aware-dense-matching_b200/csrc/ptx.cuh"
 
 using namespace gadm;
 
