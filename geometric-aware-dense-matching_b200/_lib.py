@@ -7,7 +7,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgadm.so")
+# GADM_LIB: load another build of the same library (the timing-trace variant of tools/); default = the product
+LIB_PATH = os.environ.get("GADM_LIB") or os.path.join(_HERE, "libgadm.so")
 
 c_void_p, c_int, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
 
@@ -31,6 +32,8 @@ SIGNATURES = {
     "gadm_operand_k": (c_int, [c_int, c_int]),
     "gadm_aux_floats": (c_size_t, [c_int, c_int]),
     "gadm_prep_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gadm_prep_rows_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gadm_pack_match_outputs": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p]),
     "gadm_prep_model": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "gadm_match_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,

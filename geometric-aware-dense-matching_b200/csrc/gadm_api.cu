@@ -129,7 +129,27 @@ int gadm_prep_rows(const float* feat, int B, int d, int N, int operand_mode, int
   if (operand_mode < GADM_OPERAND_BF16 || operand_mode > GADM_OPERAND_BF16N) return GADM_ERR_UNSUPPORTED;
   if (d % 64 != 0 || d > 256) return GADM_ERR_UNSUPPORTED;
   if (!aligned16(rows)) return GADM_ERR_ALIGN;
-  return prep_rows_launch(feat, B, d, N, operand_mode, pad_mode, rows, rinv, pad_sim, (cudaStream_t)stream);
+  return prep_rows_launch(feat, 0, B, d, N, operand_mode, pad_mode, rows, rinv, pad_sim, (cudaStream_t)stream);
+}
+
+int gadm_prep_rows_bf16(const void* feat_bf16, int B, int d, int N, int operand_mode, int pad_mode, void* rows,
+                        float* rinv, float* pad_sim, gadm_stream_t stream) {
+  GADM_REQUIRE_INIT();
+  if (!feat_bf16 || !rows || !rinv || B <= 0 || d <= 0 || N <= 0) return GADM_ERR_BAD_ARG;
+  if (pad_mode != GADM_PAD_NONE && !pad_sim) return GADM_ERR_BAD_ARG;
+  if (pad_mode < 0 || pad_mode > GADM_PAD_E0) return GADM_ERR_UNSUPPORTED;
+  // a bf16 source has no low part to split: BF16X3 would only triple the work
+  if (operand_mode != GADM_OPERAND_BF16 && operand_mode != GADM_OPERAND_BF16N) return GADM_ERR_UNSUPPORTED;
+  if (d % 64 != 0 || d > 256) return GADM_ERR_UNSUPPORTED;
+  if (!aligned16(rows)) return GADM_ERR_ALIGN;
+  return prep_rows_launch(feat_bf16, 1, B, d, N, operand_mode, pad_mode, rows, rinv, pad_sim, (cudaStream_t)stream);
+}
+
+int gadm_pack_match_outputs(const int64_t* idx, const float* max_sim, const float* weight, const float* soft_xyz,
+                            int64_t n, int32_t* out, gadm_stream_t stream) {
+  GADM_REQUIRE_INIT();
+  if (!idx || !max_sim || !out || n <= 0) return GADM_ERR_BAD_ARG;
+  return pack_outputs_launch(idx, max_sim, weight, soft_xyz, size_t(n), out, (cudaStream_t)stream);
 }
 
 int gadm_prep_model(const float* mesh, const float* model_xyz, int n_obj, int d, int M, int operand_mode, void* cols,

@@ -51,8 +51,10 @@ int circle_launch(const void* rows, const float* rinv_rows, const float* pad_sim
                   float* lse_n, const float* w, float* G, int Mp, cudaStream_t stream);
 
 // prep.cu
-int prep_rows_launch(const float* feat, int B, int d, int N, int operand_mode, int pad_mode, void* rows, float* rinv,
-                     float* pad_sim, cudaStream_t stream);
+int prep_rows_launch(const void* feat, int feat_bf16, int B, int d, int N, int operand_mode, int pad_mode, void* rows,
+                     float* rinv, float* pad_sim, cudaStream_t stream);
+int pack_outputs_launch(const int64_t* idx, const float* max_sim, const float* weight, const float* soft_xyz, size_t n,
+                        int32_t* out, cudaStream_t stream);
 int prep_model_launch(const float* mesh, const float* model_xyz, int n_obj, int d, int M, int operand_mode, void* cols,
                       float* aux, cudaStream_t stream);
 int seg_mask_launch(const float* seg, int B, int N, uint8_t* mask, cudaStream_t stream);

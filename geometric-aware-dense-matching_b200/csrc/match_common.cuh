@@ -68,6 +68,7 @@ struct MatchParams {
   int stash_slots;
   // persistent kernels: the (frame, row block, model tile) units are dealt out evenly, in linear order, to the CTAs of
   // the grid; a row block whose tiles end up in several CTAs is finished by the last of them to arrive
+  int dbg;                 // timing ablations (gadm_config_set "match.dbg"); 0 in production
   int T;                   // model tiles per row
   int RB;                  // row blocks (PART_ROWS rows) per frame
   long long total_units;   // B * RB * T

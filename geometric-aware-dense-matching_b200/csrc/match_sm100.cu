@@ -1196,20 +1196,22 @@ inline int match_alt_stages(int KB) {
 // match_fa_kernel: SOFT for K' <= 128 -- the fused softmax laid out the way flash attention lays it out on this
 // architecture.  The p * xyz / p sums of the other SOFT kernels are four FP32-pipe operations and three broadcast
 // LDS.128 per score next to one MUFU.EX2; here they are one more GEMM on the tensor core:
-//   S = F M^T           tcgen05.mma 128x128x16, A = the CTA's own rows from TENSOR MEMORY (written once per segment with
-//                       tcgen05.st, so the MMAs read only the model tile from shared memory), accumulator S[r] in TMEM
+//   S = F M^T           tcgen05.mma 128x128x16, A = the CTA's 128 rows from TENSOR MEMORY (written once per segment with
+//                       tcgen05.st, so the MMAs read only the model tile from shared memory), accumulators S[0], S[1]
+//                       alternate between model tiles: S(t+1) is computed while the epilogue works on S(t)
 //   epilogue warps      thread = row x 32-column slice: score = S * 1/|m_j| (exact argmax track as in
 //                       match_alt_kernel), p = 2^(score * g - off) with a LAZY per-thread reference exponent `off`
-//                       (raised, with a rescale of the thread's own O accumulator, only when exceeded by more than 8,
-//                       so p <= 2^8 fits fp16), p rounded to fp16 and stored back over the scores it came from
+//                       (raised, with a rescale of the thread's own O accumulator, only when exceeded by more than 14,
+//                       so p <= 2^14 fits fp16), p rounded to fp16 and stored back over the scores it came from
 //   O += P V            tcgen05.mma 128x16x16, A = P from TMEM, B = V^T tile from shared memory with rows
 //                       {x_hi, y_hi, z_hi, x_lo, y_lo, z_lo, 1}: the coordinate sums AND the sum of p, in fp32, from the
 //                       same rounded p -- the rounding cancels to second order in soft_xyz; weight = 2^(max - off) / sum
 //                       carries at most one fp16 rounding (2^-11) of the dominant term.
-// A thread never shares its reference exponent: each (row tile, column slice) has its own 16-column O accumulator.
-// TMEM: S[0], S[1] 128 columns each | A[0], A[1] 64 each | O[2][4] 16 each = 512.
-// Persistent: units (frame, 256-row block, 128-vertex tile) dealt out as in match_alt_kernel; the two row tiles of a
-// block alternate, all 16 epilogue warps work on one while the tensor core fills the other.
+// A thread never shares its reference exponent: each column slice has its own 16-column O accumulator.
+// TMEM: S[0], S[1] 128 columns each | A 64 | O[4] 16 each = 384 of 512.
+// Persistent: units (frame, 128-row tile, 128-vertex tile) dealt out evenly to the CTAs as in match_alt_kernel.
+// Issue: the whole UMMA warp runs the loop and one elected lane issues (ptx::umma_f16_ts_warp): 64-cycle MMAs do not
+// hide the scalar code of an `if (lane == 0)` issuer.
 constexpr int FBN = 128;                        // model vertices per tile == UMMA N of the similarity
 constexpr int FB_STAGE_BYTES = FBN * BK * 2;    // 16 KB
 constexpr int F_MAX_STAGES = 8;
@@ -1218,38 +1220,40 @@ constexpr int VT_BLK_BYTES = 16 * BK * 2;       // [16 rows x 64 vertices] fp16 
 constexpr int VT_TILE_BYTES = (FBN / BK) * VT_BLK_BYTES;
 constexpr int F_SC_BYTES = FBN * 4;
 constexpr int F_SLOTS = 4;                      // ring of {column scales, V^T} per tile
-constexpr int F_TM_A = 2 * FBN;                 // TMEM column of A[0]
-constexpr int F_TM_O = F_TM_A + 2 * 64;         // TMEM column of O[0][0]
-constexpr float F_LAZY = 8.f;                   // the reference exponent lags the running maximum by at most 2^8
+constexpr int F_TM_A = 2 * FBN;                 // TMEM column of A
+constexpr int F_TM_O = F_TM_A + 64;             // TMEM column of O[0]
+constexpr float F_LAZY = 14.f;                  // the reference exponent lags the running maximum by at most 2^14
+constexpr int FA_THREADS = 640;                 // 4 epilogue warpgroups + 1 producer warpgroup (TMA, UMMA, two idle warps)
+constexpr int F_STASH_BYTES = STASH_BYTES;      // one row per thread
 
 struct FaBarriers {
   uint64_t full[F_MAX_STAGES];
   uint64_t empty[F_MAX_STAGES];
   uint64_t aux_full[F_SLOTS];     // scales + V^T of the tile have landed
-  uint64_t sc_empty[F_SLOTS];     // scales read by every epilogue warp (both row tiles)
-  uint64_t vt_empty[F_SLOTS];     // V^T read by the P V MMAs of both row tiles (tcgen05.commit)
+  uint64_t sc_empty[F_SLOTS];     // scales read by every epilogue warp
+  uint64_t vt_empty[F_SLOTS];     // V^T read by the tile's P V MMAs (tcgen05.commit)
   uint64_t a_ready;               // the segment's rows are in tensor memory (all epilogue warps)
-  uint64_t s_full[2];             // S[r] complete (tcgen05.commit; covers every earlier MMA, the P V ones included)
-  uint64_t p_full[2];             // P[r] stored by every epilogue warp: P V may run, then S[r] may be overwritten
+  uint64_t s_full[2];             // S[buf] complete (tcgen05.commit)
+  uint64_t p_full[2];             // P[buf] stored by every epilogue warp: P V may run, then S[buf] may be overwritten
   uint64_t o_full;                // every P V MMA of the segment has completed
   uint32_t tmem_base;
   int merge_lo, merge_hi;
   uint32_t pad;
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(FA_THREADS, 1)
 match_fa_kernel(const __grid_constant__ CUtensorMap tmap_cols, const __grid_constant__ CUtensorMap tmap_vt,
                 const MatchParams p) {
-  constexpr int RT = 2, SL = 4;
+  constexpr int SL = 4;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_b = smem;                                        // model tile ring
   uint8_t* smem_vt = smem_b + p.stages * FB_STAGE_BYTES;         // V^T ring (1024-byte aligned atoms)
   uint8_t* smem_sc = smem_vt + F_SLOTS * VT_TILE_BYTES;          // column scale ring
-  uint8_t* smem_stash = smem_sc + F_SLOTS * F_SC_BYTES;          // two rows per thread
-  float* smem_xmax = reinterpret_cast<float*>(smem_stash + P_STASH_BYTES);     // [RT][SL][128]
-  float* smem_xch = smem_xmax + RT * SL * BM;                                  // [RT][SL - 1][128][8]
-  FaBarriers* bars = reinterpret_cast<FaBarriers*>(smem_xch + RT * (SL - 1) * BM * 8);
+  uint8_t* smem_stash = smem_sc + F_SLOTS * F_SC_BYTES;
+  float* smem_xmax = reinterpret_cast<float*>(smem_stash + F_STASH_BYTES);     // [SL][128]
+  float* smem_xch = smem_xmax + SL * BM;                                       // [SL - 1][128][8]
+  FaBarriers* bars = reinterpret_cast<FaBarriers*>(smem_xch + (SL - 1) * BM * 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1284,6 +1288,10 @@ match_fa_kernel(const __grid_constant__ CUtensorMap tmap_cols, const __grid_cons
   ptx::tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
+  // register reallocation (whole warpgroups): the producer warpgroup keeps 56 registers per thread (only what it frees
+  // can be re-allocated), the epilogue warpgroups get 104
+  if (warp >= EPI_WARPS) {
+  ptx::setmaxnreg_dec<56>();
   if (warp == EPI_WARPS) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
@@ -1298,6 +1306,13 @@ match_fa_kernel(const __grid_constant__ CUtensorMap tmap_cols, const __grid_cons
           const int slot = n % F_SLOTS;
           const uint32_t par = ((n / F_SLOTS) & 1) ^ 1;
           const uint32_t bytes = uint32_t(min(FBN, p.M - t * FBN)) * 4;   // M % 8 == 0: a multiple of 16
+          // the model tile first: the similarity of tile t + 1 is issued before the P V of tile t frees an aux slot
+          for (int kb = 0; kb < p.KB; ++kb) {
+            ptx::mbar_wait_sleep(&bars->empty[stage], phase ^ 1);
+            ptx::mbar_arrive_expect_tx(&bars->full[stage], FB_STAGE_BYTES);
+            ptx::tma_load_3d(smem_b + stage * FB_STAGE_BYTES, &tmap_cols, &bars->full[stage], kb * BK, t * FBN, obj);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
           ptx::mbar_wait_sleep(&bars->sc_empty[slot], par);
           ptx::mbar_wait_sleep(&bars->vt_empty[slot], par);
           ptx::mbar_arrive_expect_tx(&bars->aux_full[slot], bytes + VT_TILE_BYTES);
@@ -1306,85 +1321,68 @@ match_fa_kernel(const __grid_constant__ CUtensorMap tmap_cols, const __grid_cons
           for (int h = 0; h < FBN / BK; ++h)   // vertices >= M: zero rows of the table or zero-filled by TMA
             ptx::tma_load_3d(smem_vt + slot * VT_TILE_BYTES + h * VT_BLK_BYTES, &tmap_vt, &bars->aux_full[slot],
                              t * FBN + h * BK, 0, obj);
-          for (int kb = 0; kb < p.KB; ++kb) {
-            ptx::mbar_wait_sleep(&bars->empty[stage], phase ^ 1);
-            ptx::mbar_arrive_expect_tx(&bars->full[stage], FB_STAGE_BYTES);
-            ptx::tma_load_3d(smem_b + stage * FB_STAGE_BYTES, &tmap_cols, &bars->full[stage], kb * BK, t * FBN, obj);
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
-          }
         }
         u += tb - ta;
       }
     }
   } else if (warp == EPI_WARPS + 1) {
-    // ============================== UMMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16_f32(BM, FBN);
-      constexpr uint32_t idesc_pv = ptx::umma_idesc_f16_f32(BM, 16);
-      int stage0 = 0;
-      uint32_t phase0 = 0, n = 0, seg = 0;
-      uint32_t np[2] = {0, 0};                     // completed phases of p_full[r] consumed so far
-      // P V of tile (slot) for row tile r: 4 slices x 2 K steps, A = P over the first half of the slice's own scores
-      auto issue_pv = [&](int r, int slot, bool first_tile) {
-        ptx::mbar_wait_sleep(&bars->p_full[r], np[r] & 1);
-        ++np[r];
-        ptx::tc_fence_after();
-        const uint32_t vt_addr = ptx::smem_u32(smem_vt + slot * VT_TILE_BYTES);
+    // ============================== UMMA issuer (the whole warp runs the loop, one elected lane issues) ======
+    constexpr uint32_t idesc_s = ptx::umma_idesc_bf16_f32(BM, FBN);
+    constexpr uint32_t idesc_pv = ptx::umma_idesc_f16_f32(BM, 16);
+    int stage = 0;
+    uint32_t phase = 0, n = 0, seg = 0;
+    // P V of tile m (its P sits in S[m & 1]): 4 slices x 2 K steps, A = P over the first half of the slice's scores
+    auto issue_pv = [&](uint32_t m, bool first_tile) {
+      const uint32_t buf = m & 1;
+      ptx::mbar_wait_sleep(&bars->p_full[buf], (m >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t vt_addr = ptx::smem_u32(smem_vt + (m % F_SLOTS) * VT_TILE_BYTES);
+      if (!(p.dbg & 1)) {
 #pragma unroll
         for (int s = 0; s < SL; ++s)
 #pragma unroll
           for (int k = 0; k < 2; ++k)
-            ptx::umma_f16_ts(tmem_base + F_TM_O + (r * SL + s) * 16, tmem_base + r * FBN + s * F_CS + k * 8,
-                             ptx::umma_desc_sw128_kmajor(vt_addr + (s >> 1) * VT_BLK_BYTES + ((s & 1) * 2 + k) * 32),
-                             idesc_pv, !(first_tile && k == 0));
-      };
-      for (long long u = u_begin; u < u_end; ++seg) {
-        const int ntiles = int(min((long long)p.T - (u % p.T), u_end - u));
-        ptx::mbar_wait_sleep(&bars->a_ready, seg & 1);
-        ptx::tc_fence_after();
-        for (int t = 0; t < ntiles; ++t, ++n) {
-#pragma unroll
-          for (int r = 0; r < RT; ++r) {
-            if (t > 0) {
-              issue_pv(r, (n - 1) % F_SLOTS, t == 1);
-              if (r == RT - 1) ptx::umma_commit(&bars->vt_empty[(n - 1) % F_SLOTS]);
-            }
-            const uint32_t d_tmem = tmem_base + r * FBN;
-            const uint32_t a_tmem = tmem_base + F_TM_A + r * 64;
-            int stage = stage0;
-            uint32_t phase = phase0;
-            for (int kb = 0; kb < p.KB; ++kb) {
-              if (r == 0) {
-                ptx::mbar_wait_sleep(&bars->full[stage], phase);
-                ptx::tc_fence_after();
-              }
-              const uint32_t b_addr = ptx::smem_u32(smem_b + stage * FB_STAGE_BYTES);
-#pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k)
-                ptx::umma_f16_ts(d_tmem, a_tmem + (kb * (BK / UMMA_K) + k) * (UMMA_K / 2),
-                                 ptx::umma_desc_sw128_kmajor(b_addr + k * UMMA_K * 2), idesc_s, (kb | k) != 0);
-              if (r == RT - 1) ptx::umma_commit(&bars->empty[stage]);
-              if (++stage == p.stages) { stage = 0; phase ^= 1; }
-            }
-            ptx::umma_commit(&bars->s_full[r]);
-            if (r == RT - 1) { stage0 = stage; phase0 = phase; }
-          }
-        }
-        // the last tile's P V, then the segment's sums are final
-#pragma unroll
-        for (int r = 0; r < RT; ++r) issue_pv(r, (n - 1) % F_SLOTS, ntiles == 1);
-        ptx::umma_commit(&bars->vt_empty[(n - 1) % F_SLOTS]);
-        ptx::umma_commit(&bars->o_full);
-        u += ntiles;
+            ptx::umma_f16_ts_warp(tmem_base + F_TM_O + s * 16, tmem_base + buf * FBN + s * F_CS + k * 8,
+                                  ptx::umma_desc_sw128_kmajor(vt_addr + (s >> 1) * VT_BLK_BYTES + ((s & 1) * 2 + k) * 32),
+                                  idesc_pv, !(first_tile && k == 0));
       }
+      ptx::umma_commit_warp(&bars->vt_empty[m % F_SLOTS]);
+    };
+    for (long long u = u_begin; u < u_end; ++seg) {
+      const int ntiles = int(min((long long)p.T - (u % p.T), u_end - u));
+      ptx::mbar_wait_sleep(&bars->a_ready, seg & 1);
+      ptx::tc_fence_after();
+      for (int t = 0; t < ntiles; ++t, ++n) {
+        // S(n) into S[n & 1]: what that buffer held (P of tile n - 2) was read by P V MMAs issued before this point
+        const uint32_t d_tmem = tmem_base + (n & 1) * FBN;
+        for (int kb = 0; kb < p.KB; ++kb) {
+          ptx::mbar_wait_sleep(&bars->full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t b_addr = ptx::smem_u32(smem_b + stage * FB_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            ptx::umma_f16_ts_warp(d_tmem, tmem_base + F_TM_A + (kb * (BK / UMMA_K) + k) * (UMMA_K / 2),
+                                  ptx::umma_desc_sw128_kmajor(b_addr + k * UMMA_K * 2), idesc_s, (kb | k) != 0);
+          ptx::umma_commit_warp(&bars->empty[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit_warp(&bars->s_full[n & 1]);
+        if (t > 0) issue_pv(n - 1, t == 1);        // while the epilogue works on S(n)
+      }
+      issue_pv(n - 1, ntiles == 1);                // the last tile's P V, then the segment's sums are final
+      ptx::umma_commit_warp(&bars->o_full);
+      u += ntiles;
     }
+  }
   } else {
-    // ============================== epilogue warps (thread == one row of each row tile x one slice) ==============
+    ptx::setmaxnreg_inc<104>();
+    // ============================== epilogue warps (thread == one row x one 32-column slice) ==============
     const int q = warp & 3;
     const int sub = warp >> 2;                       // 32-column slice of every tile
     const int row_in_tile = q * 32 + lane;
     const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
-    const uint32_t stash_addr = ptx::smem_u32(smem_stash) + threadIdx.x * 16;   // row tile r: + r * 2 * STASH_PLANE
+    const uint32_t stash_addr = ptx::smem_u32(smem_stash) + threadIdx.x * 16;
+    const uint32_t o_tmem = lane_base + F_TM_O + sub * 16;
     const int rbg_first = int(u_begin / p.T);
     const int Kp = p.KB * BK;
 
@@ -1392,36 +1390,32 @@ match_fa_kernel(const __grid_constant__ CUtensorMap tmap_cols, const __grid_cons
     for (long long u = u_begin; u < u_end; ++seg) {
       const int rbg = int(u / p.T), ta = int(u - (long long)rbg * p.T);
       const int tb = int(min((long long)p.T, ta + (u_end - u)));
-      const int b = rbg / p.RB, row0 = (rbg % p.RB) * (BM * RT);
+      const int b = rbg / p.RB, row0 = (rbg % p.RB) * BM;
       u += tb - ta;
 
-      // ---- this thread's rows (K range [sub K'/4, (sub + 1) K'/4)) from global memory into tensor memory: lane = row,
+      // ---- this thread's row (K range [sub K'/4, (sub + 1) K'/4)) from global memory into tensor memory: lane = row,
       // one 32-bit column = two consecutive k, the layout tcgen05.mma reads an A operand in.  Every MMA of the previous
       // segment that read A has completed (its last s_full was seen) and its sums have been read (program order).
-      float g[RT];
+      const int row = row0 + row_in_tile;
+      const bool row_ok = row < p.N;
+      const size_t grow = size_t(b) * p.N + (row_ok ? row : 0);
+      const float g = row_ok ? p.gamma_log2e * p.rinv_rows[grow] : 0.f;   // exponent scale: t = score * g (log2), g >= 0
       {
-        const int kq = Kp / 4;                       // bf16 elements per thread and row tile: 16 (K' = 64) or 32
-#pragma unroll
-        for (int r = 0; r < RT; ++r) {
-          const int row = row0 + r * BM + row_in_tile;
-          const bool ok = row < p.N;
-          const size_t grow = size_t(b) * p.N + (ok ? row : 0);
-          g[r] = ok ? p.gamma_log2e * p.rinv_rows[grow] : 0.f;   // exponent scale: t = score * g (log2 units), g >= 0
-          const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.rows_ptr) +
-                                                            (grow * Kp + sub * kq) * 2);
-          const uint32_t dst = lane_base + F_TM_A + r * 64 + sub * (kq / 2);
-          uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
-          if (ok) {
-            v0 = src[0]; v1 = src[1];
-            if (kq == 32) { v2 = src[2]; v3 = src[3]; }
-          }
-          if (kq == 32) {
-            const uint32_t w[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
-            ptx::tmem_st_32x16(dst, w);
-          } else {
-            const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            ptx::tmem_st_32x8(dst, w);
-          }
+        const int kq = Kp / 4;                       // bf16 elements per thread: 16 (K' = 64) or 32
+        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.rows_ptr) +
+                                                          (grow * Kp + sub * kq) * 2);
+        const uint32_t dst = lane_base + F_TM_A + sub * (kq / 2);
+        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
+        if (row_ok) {
+          v0 = src[0]; v1 = src[1];
+          if (kq == 32) { v2 = src[2]; v3 = src[3]; }
+        }
+        if (kq == 32) {
+          const uint32_t w[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+          ptx::tmem_st_32x16(dst, w);
+        } else {
+          const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          ptx::tmem_st_32x8(dst, w);
         }
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
@@ -1429,38 +1423,38 @@ match_fa_kernel(const __grid_constant__ CUtensorMap tmap_cols, const __grid_cons
         if (lane == 0) ptx::mbar_arrive(&bars->a_ready);
       }
 
-      float vmax[RT] = {-INFINITY, -INFINITY};
-      int vgrp[RT] = {0, 0};
-      float off[RT] = {-INFINITY, -INFINITY};      // reference exponent of this thread's sums (log2 units)
+      float vmax = -INFINITY;
+      int vgrp = 0;
+      float off = -INFINITY;                         // reference exponent of this thread's sums (log2 units)
 
       for (int t = ta; t < tb; ++t, ++n) {
         const int slot = n % F_SLOTS;
+        const uint32_t buf = n & 1;
         const int ncols = min(FBN, p.M - t * FBN) - sub * F_CS;   // valid columns of this slice (may be <= 0)
         const uint32_t sc = ptx::smem_u32(smem_sc + slot * F_SC_BYTES) + sub * F_CS * 4;
         const int col_base = t * FBN + sub * F_CS;
-        const bool o_live = t > ta;                  // the O accumulators hold the sums of the segment's earlier tiles
-#pragma unroll
-        for (int r = 0; r < RT; ++r) {
-          if (!((r > 0 || ptx::mbar_try_wait(&bars->aux_full[slot], (n / F_SLOTS) & 1)) &
-                ptx::mbar_try_wait(&bars->s_full[r], n & 1))) {
-            if (r == 0) ptx::mbar_wait_sleep(&bars->aux_full[slot], (n / F_SLOTS) & 1);
-            ptx::mbar_wait_sleep(&bars->s_full[r], n & 1);
-          }
-          ptx::tc_fence_after();
-          const uint32_t s_tmem = lane_base + r * FBN + sub * F_CS;
-          const uint32_t o_tmem = lane_base + F_TM_O + (r * SL + sub) * 16;
-          uint32_t pk[16];
+        const bool o_live = t > ta;                  // the O accumulator holds the sums of the segment's earlier tiles
+        if (!(ptx::mbar_try_wait(&bars->aux_full[slot], (n / F_SLOTS) & 1) &
+              ptx::mbar_try_wait(&bars->s_full[buf], (n >> 1) & 1))) {
+          ptx::mbar_wait_sleep(&bars->aux_full[slot], (n / F_SLOTS) & 1);
+          ptx::mbar_wait_sleep(&bars->s_full[buf], (n >> 1) & 1);
+        }
+        ptx::tc_fence_after();
+        const uint32_t s_tmem = lane_base + buf * FBN + sub * F_CS;
+        uint32_t pk[16];
 
-          auto process = [&](uint32_t (&d)[32], auto guard_tag) {
-            constexpr bool kGuard = decltype(guard_tag)::value;
-            uint64_t v[16];
+        // One visit: this thread's 32 scores of the accumulator.  kGuard (ragged last tile only) masks columns >= M.
+        auto visit = [&](auto guard_tag) {
+          constexpr bool kGuard = decltype(guard_tag)::value;
+          // scaled scores of the chunk: score = S * 1/|m_j| (packed pairs, even column in the low half)
+          auto scaled = [&](const uint32_t (&d)[32], uint64_t (&v)[16]) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const float4 cm = ptx::lds128(sc + j4 * 16);
               v[j4 * 2 + 0] = ptx::fmul2(ptx::pack2(d[j4 * 4 + 0], d[j4 * 4 + 1]), ptx::pack2f(cm.x, cm.y));
               v[j4 * 2 + 1] = ptx::fmul2(ptx::pack2(d[j4 * 4 + 2], d[j4 * 4 + 3]), ptx::pack2f(cm.z, cm.w));
             }
-            if (kGuard) {
+            if (kGuard) {                            // columns >= M never win and weigh nothing
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 float lo, hi;
@@ -1470,83 +1464,109 @@ match_fa_kernel(const __grid_constant__ CUtensorMap tmap_cols, const __grid_cons
                 v[j] = ptx::pack2f(lo, hi);
               }
             }
-            float gm[4];
+          };
+          // p = 2^(score * g - off) of one packed pair, rounded to fp16 (a column >= M has score -inf: p = 0, but
+          // -inf * 0 = NaN when g == 0, hence the explicit zero)
+          auto exp_pair = [&](uint64_t v2, int j) -> uint32_t {
+            float lo, hi;
+            ptx::unpack2f(ptx::ex2_2(ptx::ffma2(v2, ptx::pack2f(g, g), ptx::pack2f(-off, -off))), lo, hi);
+            if (kGuard) {
+              if (2 * j >= ncols) lo = 0.f;
+              if (2 * j + 1 >= ncols) hi = 0.f;
+            }
+            return ptx::cvt_f16x2(hi, lo);
+          };
+          auto group_max = [&](const uint64_t* v4) -> float {
+            float f[GRP];
+#pragma unroll
+            for (int j = 0; j < GRP / 2; ++j) ptx::unpack2f(v4[j], f[2 * j], f[2 * j + 1]);
+            const float a0 = ptx::fmax3(f[0], f[1], f[2]), a1 = ptx::fmax3(f[3], f[4], f[5]);
+            return ptx::fmax3(a0, a1, fmaxf(f[6], f[7]));
+          };
+
+          float gm[4];
+          {
+            // ---- main pass.  The exponentials are SPECULATIVE, taken with the reference exponent as it stands, so
+            // the 32 MUFU.EX2 depend on nothing but the scores and overlap the maximum tree.
+            uint32_t d[32];
+            ptx::tmem_ld_32x32(s_tmem, d);
+            ptx::tmem_ld_wait();
+            uint64_t v[16];
+            scaled(d, v);
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-              float f[GRP];
 #pragma unroll
-              for (int j = 0; j < GRP / 2; ++j) ptx::unpack2f(v[h * 4 + j], f[2 * j], f[2 * j + 1]);
-              const float a0 = ptx::fmax3(f[0], f[1], f[2]), a1 = ptx::fmax3(f[3], f[4], f[5]);
-              gm[h] = ptx::fmax3(a0, a1, fmaxf(f[6], f[7]));
-              const bool up = gm[h] > vmax[r];      // strict: a later equal value never displaces the first index
-              ptx::sts_stash8(up, stash_addr + r * 2 * STASH_PLANE, v[h * 4 + 0], v[h * 4 + 1], v[h * 4 + 2], v[h * 4 + 3]);
-              vgrp[r] = up ? col_base + h * GRP : vgrp[r];
-              vmax[r] = up ? gm[h] : vmax[r];
+              for (int j = 0; j < 4; ++j) pk[h * 4 + j] = exp_pair(v[h * 4 + j], h * 4 + j);
+              gm[h] = group_max(&v[h * 4]);
             }
-            // lazy reference exponent: raise it (and rescale this thread's sums) only when the chunk exceeds it by > 2^8
-            const float tmx = ptx::fmax3(gm[0], gm[1], fmaxf(gm[2], gm[3])) * g[r];
-            const bool need = tmx > off[r] + F_LAZY;
-            if (__any_sync(0xffffffffu, need)) {
-              const float noff = need ? tmx : off[r];
+          }
+          const float cmax = ptx::fmax3(gm[0], gm[1], fmaxf(gm[2], gm[3]));
+          const float tmx = cmax * g;
+          const bool need = tmx > off + F_LAZY;             // the chunk exceeds the reference exponent by > 2^14
+          const bool any_up = __any_sync(0xffffffffu, cmax > vmax);
+          const bool any_need = __any_sync(0xffffffffu, need);
+          if (any_up | any_need) {
+            // ---- rare pass (after the first tiles): some row of the warp improves its maximum or outgrows its
+            // exponent.  The scores are still in tensor memory (P is stored below): read and scale them again.
+            uint32_t d[32];
+            ptx::tmem_ld_32x32(s_tmem, d);
+            ptx::tmem_ld_wait();
+            uint64_t v[16];
+            scaled(d, v);
+            if (any_up) {
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                const bool up = gm[h] > vmax;       // strict: a later equal value never displaces the first index
+                ptx::sts_stash8(up, stash_addr, v[h * 4 + 0], v[h * 4 + 1], v[h * 4 + 2], v[h * 4 + 3]);
+                vgrp = up ? col_base + h * GRP : vgrp;
+                vmax = up ? gm[h] : vmax;
+              }
+            }
+            if (any_need) {
+              // lazy reference exponent: raised to the chunk's maximum, this thread's sums rescaled, the chunk's
+              // exponentials redone
+              const float noff = need ? tmx : off;
               if (o_live) {
                 uint32_t o[8];
                 ptx::tmem_ld_32x8(o_tmem, o);
                 ptx::tmem_ld_wait();
-                const float f = need ? ptx::ex2_approx(off[r] - noff) : 1.f;
+                const float f = need ? ptx::ex2_approx(off - noff) : 1.f;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
                 ptx::tmem_st_32x8(o_tmem, o);
               }
-              off[r] = noff;
-            }
-            const uint64_t g2 = ptx::pack2f(g[r], g[r]), o2 = ptx::pack2f(-off[r], -off[r]);
+              off = noff;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float lo, hi;
-              ptx::unpack2f(ptx::ex2_2(ptx::ffma2(v[j], g2, o2)), lo, hi);
-              if (kGuard) {                          // (-inf * 0 = NaN when g == 0)
-                if (2 * j >= ncols) lo = 0.f;
-                if (2 * j + 1 >= ncols) hi = 0.f;
-              }
-              pk[j] = ptx::cvt_f16x2(hi, lo);
+              for (int j = 0; j < 16; ++j) pk[j] = exp_pair(v[j], j);
             }
-          };
-          using guard_off = std::integral_constant<bool, false>;
-          using guard_on = std::integral_constant<bool, true>;
-
-          if (ncols > 0) {
-            uint32_t d[32];
-            ptx::tmem_ld_32x32(s_tmem, d);
-            ptx::tmem_ld_wait();
-            if (ncols >= F_CS) process(d, guard_off{});
-            else process(d, guard_on{});
-          } else {
+          }
+        };
+        if (ncols >= F_CS && !(p.dbg & 8)) {
+          visit(std::integral_constant<bool, false>{});
+        } else if (ncols > 0 && !(p.dbg & 8)) {
+          visit(std::integral_constant<bool, true>{});
+        } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = 0u;   // the P V MMAs read this slice whatever it holds
-          }
-          ptx::tmem_st_32x16(s_tmem, pk);
-          ptx::tmem_st_wait();
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            ptx::mbar_arrive(&bars->p_full[r]);
-            if (r == RT - 1) ptx::mbar_arrive(&bars->sc_empty[slot]);
-          }
+          for (int j = 0; j < 16; ++j) pk[j] = 0u;   // the P V MMAs read this slice whatever it holds
+        }
+        ptx::tmem_st_32x16(s_tmem, pk);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(&bars->p_full[buf]);
+          ptx::mbar_arrive(&bars->sc_empty[slot]);
         }
         // running maxima shared across the four slices of a row after the segment's tiles 0, 1, 3, 7, 15, 31
-        // (see match_alt_kernel): fewer stash stores
+        // (see match_alt_kernel): fewer rare passes
         const int tl = t - ta;
         if ((tl & (tl + 1)) == 0 && tl < 32 && t + 1 < tb) {
-#pragma unroll
-          for (int r = 0; r < RT; ++r) smem_xmax[(r * SL + sub) * BM + row_in_tile] = vmax[r];
+          smem_xmax[sub * BM + row_in_tile] = vmax;
           asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+          float m = vmax;
 #pragma unroll
-          for (int r = 0; r < RT; ++r) {
-            float m = vmax[r];
-#pragma unroll
-            for (int s2 = 0; s2 < SL; ++s2) m = fmaxf(m, smem_xmax[(r * SL + s2) * BM + row_in_tile]);
-            if (vmax[r] < m) { vmax[r] = m; vgrp[r] = NO_RECORD; }
-          }
+          for (int s2 = 0; s2 < SL; ++s2) m = fmaxf(m, smem_xmax[s2 * BM + row_in_tile]);
+          if (vmax < m) { vmax = m; vgrp = NO_RECORD; }
           asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32) : "memory");
         }
       }
@@ -1554,36 +1574,35 @@ match_fa_kernel(const __grid_constant__ CUtensorMap tmap_cols, const __grid_cons
       // ---- end of the segment: this thread's sums (relative to its own reference exponent), its first maximal index
       ptx::mbar_wait_sleep(&bars->o_full, seg & 1);
       ptx::tc_fence_after();
-      float vm[RT], so[RT], sl[RT], sx[RT], sy[RT], sz[RT];
-      int vi[RT];
-#pragma unroll
-      for (int r = 0; r < RT; ++r) {
+      float vm, so, sl, sx, sy, sz;
+      int vi;
+      {
         uint32_t o[8];
-        ptx::tmem_ld_32x8(lane_base + F_TM_O + (r * SL + sub) * 16, o);
+        ptx::tmem_ld_32x8(o_tmem, o);
         ptx::tmem_ld_wait();
-        so[r] = off[r];
-        sx[r] = __uint_as_float(o[0]) + __uint_as_float(o[3]);
-        sy[r] = __uint_as_float(o[1]) + __uint_as_float(o[4]);
-        sz[r] = __uint_as_float(o[2]) + __uint_as_float(o[5]);
-        sl[r] = __uint_as_float(o[6]);
-        vm[r] = vmax[r];
-        vi[r] = NO_RECORD;
-        if (vmax[r] > -INFINITY && vgrp[r] != NO_RECORD) {
+        so = off;
+        sx = __uint_as_float(o[0]) + __uint_as_float(o[3]);
+        sy = __uint_as_float(o[1]) + __uint_as_float(o[4]);
+        sz = __uint_as_float(o[2]) + __uint_as_float(o[5]);
+        sl = __uint_as_float(o[6]);
+        vm = vmax;
+        vi = NO_RECORD;
+        if (vmax > -INFINITY && vgrp != NO_RECORD) {
           int j_first = GRP - 1;
 #pragma unroll
           for (int k = GRP / 4 - 1; k >= 0; --k) {
-            const float4 sv = ptx::lds128(stash_addr + r * 2 * STASH_PLANE + k * STASH_PLANE);
-            if (sv.w == vmax[r]) j_first = 4 * k + 3;
-            if (sv.z == vmax[r]) j_first = 4 * k + 2;
-            if (sv.y == vmax[r]) j_first = 4 * k + 1;
-            if (sv.x == vmax[r]) j_first = 4 * k + 0;
+            const float4 sv = ptx::lds128(stash_addr + k * STASH_PLANE);
+            if (sv.w == vmax) j_first = 4 * k + 3;
+            if (sv.z == vmax) j_first = 4 * k + 2;
+            if (sv.y == vmax) j_first = 4 * k + 1;
+            if (sv.x == vmax) j_first = 4 * k + 0;
           }
-          vi[r] = vgrp[r] + j_first;
+          vi = vgrp + j_first;
         }
         if (sub > 0) {
-          float4* x = reinterpret_cast<float4*>(smem_xch + ((r * (SL - 1) + sub - 1) * BM + row_in_tile) * 8);
-          x[0] = make_float4(vm[r], __int_as_float(vi[r]), so[r], sl[r]);
-          x[1] = make_float4(sx[r], sy[r], sz[r], 0.f);
+          float4* x = reinterpret_cast<float4*>(smem_xch + ((sub - 1) * BM + row_in_tile) * 8);
+          x[0] = make_float4(vm, __int_as_float(vi), so, sl);
+          x[1] = make_float4(sx, sy, sz, 0.f);
         }
       }
       ptx::tc_fence_before();
@@ -1591,31 +1610,26 @@ match_fa_kernel(const __grid_constant__ CUtensorMap tmap_cols, const __grid_cons
       if (sub == 0) {
         // one more partial result (v, i, o, l, x, y, z) folded into the row's: maximum with first-index ties, sums
         // brought to the larger reference exponent (2^-inf = 0 retires a slice that never saw a valid column)
-        auto fold = [&](int r, float v1, int i1, float o1, float l1, float x1, float y1, float z1) {
-          if (v1 > vm[r] || (v1 == vm[r] && i1 < vi[r])) { vm[r] = v1; vi[r] = i1; }
-          const float om = fmaxf(so[r], o1);
-          const float fa = ptx::ex2_approx(so[r] - om), fb = ptx::ex2_approx(o1 - om);
-          sl[r] = sl[r] * fa + l1 * fb; sx[r] = sx[r] * fa + x1 * fb;
-          sy[r] = sy[r] * fa + y1 * fb; sz[r] = sz[r] * fa + z1 * fb;
-          so[r] = om;
+        auto fold = [&](float v1, int i1, float o1, float l1, float x1, float y1, float z1) {
+          if (v1 > vm || (v1 == vm && i1 < vi)) { vm = v1; vi = i1; }
+          const float om = fmaxf(so, o1);
+          const float fa = ptx::ex2_approx(so - om), fb = ptx::ex2_approx(o1 - om);
+          sl = sl * fa + l1 * fb; sx = sx * fa + x1 * fb;
+          sy = sy * fa + y1 * fb; sz = sz * fa + z1 * fb;
+          so = om;
         };
 #pragma unroll
-        for (int r = 0; r < RT; ++r)
-#pragma unroll
-          for (int s2 = 0; s2 < SL - 1; ++s2) {
-            const float4* x = reinterpret_cast<const float4*>(smem_xch + ((r * (SL - 1) + s2) * BM + row_in_tile) * 8);
-            const float4 a = x[0], c = x[1];
-            fold(r, a.x, __float_as_int(a.y), a.z, a.w, c.x, c.y, c.z);
-          }
+        for (int s2 = 0; s2 < SL - 1; ++s2) {
+          const float4* x = reinterpret_cast<const float4*>(smem_xch + (s2 * BM + row_in_tile) * 8);
+          const float4 a = x[0], c = x[1];
+          fold(a.x, __float_as_int(a.y), a.z, a.w, c.x, c.y, c.z);
+        }
         bool finish = ta == 0 && tb == p.T;
         if (!finish) {
           float4* part = reinterpret_cast<float4*>(p.partial) +
                          (size_t(blockIdx.x) * 2 + (rbg == rbg_first ? 0 : 1)) * PART_ROWS * 2;
-#pragma unroll
-          for (int r = 0; r < RT; ++r) {
-            part[(r * BM + row_in_tile) * 2 + 0] = make_float4(vm[r], __int_as_float(vi[r]), so[r], sl[r]);
-            part[(r * BM + row_in_tile) * 2 + 1] = make_float4(sx[r], sy[r], sz[r], 0.f);
-          }
+          part[row_in_tile * 2 + 0] = make_float4(vm, __int_as_float(vi), so, sl);
+          part[row_in_tile * 2 + 1] = make_float4(sx, sy, sz, 0.f);
           __threadfence();
           asm volatile("bar.sync 3, 128;" ::: "memory");
           if (threadIdx.x == 0) {
@@ -1626,45 +1640,33 @@ match_fa_kernel(const __grid_constant__ CUtensorMap tmap_cols, const __grid_cons
           }
           asm volatile("bar.sync 3, 128;" ::: "memory");
           const int c_lo = bars->merge_lo, c_hi = bars->merge_hi;
-          if (c_lo >= 0) {                           // last to arrive: merge every segment of the row block
+          if (c_lo >= 0) {                           // last to arrive: merge every segment of the row tile
             __threadfence();
-#pragma unroll
-            for (int r = 0; r < RT; ++r) {
-              vm[r] = -INFINITY; vi[r] = NO_RECORD; so[r] = -INFINITY; sl[r] = sx[r] = sy[r] = sz[r] = 0.f;
-            }
+            vm = -INFINITY; vi = NO_RECORD; so = -INFINITY; sl = sx = sy = sz = 0.f;
             for (int c = c_lo; c <= c_hi; ++c) {     // ascending columns: on ties the earlier segment wins
               const float4* q4 = reinterpret_cast<const float4*>(p.partial) +
                                  (size_t(c) * 2 + (int(sched_begin(p, c) / p.T) == rbg ? 0 : 1)) * PART_ROWS * 2;
-#pragma unroll
-              for (int r = 0; r < RT; ++r) {
-                const float4 a = ptx::ldg_cg128(q4 + (r * BM + row_in_tile) * 2), cc = ptx::ldg_cg128(q4 + (r * BM + row_in_tile) * 2 + 1);
-                fold(r, a.x, __float_as_int(a.y), a.z, a.w, cc.x, cc.y, cc.z);
-              }
+              const float4 a = ptx::ldg_cg128(q4 + row_in_tile * 2), cc = ptx::ldg_cg128(q4 + row_in_tile * 2 + 1);
+              fold(a.x, __float_as_int(a.y), a.z, a.w, cc.x, cc.y, cc.z);
             }
             finish = true;
           }
         }
-        if (finish) {
-#pragma unroll
-          for (int r = 0; r < RT; ++r) {
-            const int row = row0 + r * BM + row_in_tile;
-            if (row >= p.N) continue;
-            const size_t grow = size_t(b) * p.N + row;
-            const bool keep = p.mask == nullptr || p.mask[grow] != 0;
-            float best = vm[r] * p.rinv_rows[grow];
-            int64_t best_idx = vi[r];
-            if (p.pad_mode != GADM_PAD_NONE) {
-              const float ps = p.pad_sim[grow];
-              if (ps > best) { best = ps; best_idx = p.M; }
-            }
-            p.idx[grow] = keep ? best_idx : int64_t(-1);
-            p.max_sim[grow] = keep ? best : 0.f;
-            const float inv = 1.f / sl[r];
-            p.weight[grow] = keep ? ptx::ex2_approx(vm[r] * g[r] - so[r]) * inv : 0.f;   // softmax value at the maximum
-            p.soft_xyz[grow * 3 + 0] = keep ? sx[r] * inv : 0.f;
-            p.soft_xyz[grow * 3 + 1] = keep ? sy[r] * inv : 0.f;
-            p.soft_xyz[grow * 3 + 2] = keep ? sz[r] * inv : 0.f;
+        if (finish && row_ok) {
+          const bool keep = p.mask == nullptr || p.mask[grow] != 0;
+          float best = vm * p.rinv_rows[grow];
+          int64_t best_idx = vi;
+          if (p.pad_mode != GADM_PAD_NONE) {
+            const float ps = p.pad_sim[grow];
+            if (ps > best) { best = ps; best_idx = p.M; }
           }
+          p.idx[grow] = keep ? best_idx : int64_t(-1);
+          p.max_sim[grow] = keep ? best : 0.f;
+          const float inv = 1.f / sl;
+          p.weight[grow] = keep ? ptx::ex2_approx(vm * g - so) * inv : 0.f;   // softmax value at the maximum
+          p.soft_xyz[grow * 3 + 0] = keep ? sx * inv : 0.f;
+          p.soft_xyz[grow * 3 + 1] = keep ? sy * inv : 0.f;
+          p.soft_xyz[grow * 3 + 2] = keep ? sz * inv : 0.f;
         }
       }
     }
@@ -1679,8 +1681,8 @@ match_fa_kernel(const __grid_constant__ CUtensorMap tmap_cols, const __grid_cons
 }
 
 inline size_t match_fa_smem_bytes(int stages) {
-  return size_t(stages) * FB_STAGE_BYTES + F_SLOTS * (VT_TILE_BYTES + F_SC_BYTES) + P_STASH_BYTES + 2 * 4 * BM * 4 +
-         2 * 3 * BM * 32 + sizeof(FaBarriers) + 1024;
+  return size_t(stages) * FB_STAGE_BYTES + F_SLOTS * (VT_TILE_BYTES + F_SC_BYTES) + F_STASH_BYTES + 4 * BM * 4 +
+         3 * BM * 32 + sizeof(FaBarriers) + 1024;
 }
 inline int match_fa_stages() {
   int stages = F_MAX_STAGES;
@@ -1711,6 +1713,8 @@ struct MatchConfig {
   int rt = -1;          // match.rt    1 / 2: row tiles per CTA of match_kernel
   int ctas = -1;        // match.ctas  grid of the persistent kernels (default: one CTA per SM)
   int fa = -1;          // match.fa    1 / 0: allow / forbid the tensor-core-sums SOFT kernel (match_fa_kernel)
+  int dbg = -1;         // match.dbg   timing ablations of match_fa_kernel (results are WRONG): 1 no P V MMAs, 2 no
+                        //             exponentials, 4 no argmax track, 8 no epilogue arithmetic at all
 };
 MatchConfig g_cfg;
 
@@ -1731,6 +1735,7 @@ int match_config_set(const char* key, int value) {
   if (!strcmp(key, "match.rt")) { g_cfg.rt = value; return GADM_OK; }
   if (!strcmp(key, "match.ctas")) { g_cfg.ctas = value; return GADM_OK; }
   if (!strcmp(key, "match.fa")) { g_cfg.fa = value; return GADM_OK; }
+  if (!strcmp(key, "match.dbg")) { g_cfg.dbg = value; return GADM_OK; }
   return GADM_ERR_BAD_ARG;
 }
 
@@ -1809,8 +1814,9 @@ static int match_launch_t(const void* rows, const void* cols, MatchParams p, int
     const int fstages = match_fa_stages();
     if (cfg.fa != 0 && p.stash != nullptr && KB <= 2 && fstages >= 2 * KB && p.N > BM && p.gamma_log2e >= 0.f) {
       p.KB = KB; p.stages = fstages;
+      p.dbg = cfg.dbg > 0 ? cfg.dbg : 0;
       p.T = (p.M + FBN - 1) / FBN;
-      p.RB = (p.N + PART_ROWS - 1) / PART_ROWS;
+      p.RB = (p.N + BM - 1) / BM;                    // this kernel's row block is one row tile
       p.total_units = (long long)p.B * p.RB * p.T;
       int grid = cfg.ctas > 0 ? min(cfg.ctas, sms) : sms;
       if ((long long)grid > p.total_units) grid = int(p.total_units);
@@ -1821,7 +1827,7 @@ static int match_launch_t(const void* rows, const void* cols, MatchParams p, int
       if (rc != GADM_OK) return rc;
       cudaError_t e = cudaMemsetAsync(p.seg_count, 0, size_t(grid) * sizeof(unsigned int), stream);
       if (e != cudaSuccess) return set_cuda_error(e);
-      match_fa_kernel<<<grid, NUM_THREADS, match_fa_smem_bytes(fstages), stream>>>(tmap_cols, tmap_vt, p);
+      match_fa_kernel<<<grid, FA_THREADS, match_fa_smem_bytes(fstages), stream>>>(tmap_cols, tmap_vt, p);
       return check_launch();
     }
   }
@@ -1888,7 +1894,7 @@ int match_launch(const void* rows, const float* rinv_rows, const float* pad_sim,
   p.stash_slots = slots;
   p.seg_count = ws_ok ? reinterpret_cast<unsigned int*>(ws + size_t(slots) * STASH_SLOT_BYTES) : nullptr;
   p.partial = ws_ok ? reinterpret_cast<float*>(ws + size_t(slots) * STASH_SLOT_BYTES + ws_counter_bytes()) : nullptr;
-  p.T = 0; p.RB = 0; p.total_units = 0;
+  p.T = 0; p.RB = 0; p.total_units = 0; p.dbg = 0;
   p.rinv_rows = rinv_rows; p.pad_sim = pad_sim; p.scales = aux_scales(aux, n_obj, M);
   p.planes = aux_planes(aux, n_obj, M); p.mask = mask; p.obj_id = obj_id;
   p.vt = aux_vt(aux, n_obj, M); p.rows_ptr = rows;

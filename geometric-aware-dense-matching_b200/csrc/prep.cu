@@ -16,9 +16,14 @@ namespace {
 constexpr int PTS = 32;  // points per CTA (one 128-byte line of every channel row)
 
 // side: 0 = scene rows ([hi|hi|lo] in x3 mode), 1 = model columns ([hi|lo|hi] in x3 mode)
-template <int kSide>
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// TIn: float, or __nv_bfloat16 for descriptors that arrive already rounded (exactly the values a float source holds
+// after the rounding this kernel would apply: same operands, half the bytes)
+template <int kSide, typename TIn>
 __global__ void __launch_bounds__(256)
-prep_kernel(const float* __restrict__ src, const float* __restrict__ xyz, int d, int P, int x3, int prenorm, int pad_mode,
+prep_kernel(const TIn* __restrict__ src, const float* __restrict__ xyz, int d, int P, int x3, int prenorm, int pad_mode,
             __nv_bfloat16* __restrict__ dst, float* __restrict__ rinv, float* __restrict__ pad_sim,
             float* __restrict__ aux_scale, float* __restrict__ aux_xyz, float* __restrict__ aux_planes, size_t plane,
             __half* __restrict__ vt, int vt_pitch) {
@@ -28,10 +33,10 @@ prep_kernel(const float* __restrict__ src, const float* __restrict__ xyz, int d,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Kp = x3 ? 3 * d : d;
 
-  const float* s = src + size_t(g) * d * P;
+  const TIn* s = src + size_t(g) * d * P;
   for (int c = warp; c < d; c += 8) {
     const int p = p0 + lane;
-    tile[c * (PTS + 1) + lane] = p < P ? s[size_t(c) * P + p] : 0.f;  // coalesced along points
+    tile[c * (PTS + 1) + lane] = p < P ? to_f32(s[size_t(c) * P + p]) : 0.f;  // coalesced along points
   }
   __syncthreads();
 
@@ -180,13 +185,40 @@ kabsch_moments_kernel(const int64_t* __restrict__ idx, const uint8_t* __restrict
 
 }  // namespace
 
-int prep_rows_launch(const float* feat, int B, int d, int N, int operand_mode, int pad_mode, void* rows, float* rinv,
-                     float* pad_sim, cudaStream_t stream) {
+int prep_rows_launch(const void* feat, int feat_bf16, int B, int d, int N, int operand_mode, int pad_mode, void* rows,
+                     float* rinv, float* pad_sim, cudaStream_t stream) {
   dim3 grid((N + PTS - 1) / PTS, B);
   const size_t smem = size_t(d) * (PTS + 1) * sizeof(float);
-  prep_kernel<0><<<grid, 256, smem, stream>>>(feat, nullptr, d, N, operand_mode == GADM_OPERAND_BF16X3, 0, pad_mode,
-                                              static_cast<__nv_bfloat16*>(rows), rinv, pad_sim, nullptr, nullptr, nullptr, 0,
-                                              nullptr, 0);
+  if (feat_bf16)
+    prep_kernel<0, __nv_bfloat16><<<grid, 256, smem, stream>>>(
+        static_cast<const __nv_bfloat16*>(feat), nullptr, d, N, operand_mode == GADM_OPERAND_BF16X3, 0, pad_mode,
+        static_cast<__nv_bfloat16*>(rows), rinv, pad_sim, nullptr, nullptr, nullptr, 0, nullptr, 0);
+  else
+    prep_kernel<0, float><<<grid, 256, smem, stream>>>(
+        static_cast<const float*>(feat), nullptr, d, N, operand_mode == GADM_OPERAND_BF16X3, 0, pad_mode,
+        static_cast<__nv_bfloat16*>(rows), rinv, pad_sim, nullptr, nullptr, nullptr, 0, nullptr, 0);
+  return check_launch();
+}
+
+// idx (int64 -> int32), max_sim, weight, soft_xyz -> one [n, 6] record of 32-bit words per scene point: a single
+// contiguous device-to-host copy carries every matcher output of a batch
+__global__ void __launch_bounds__(256)
+pack_outputs_kernel(const int64_t* __restrict__ idx, const float* __restrict__ max_sim, const float* __restrict__ weight,
+                    const float* __restrict__ soft_xyz, size_t n, int32_t* __restrict__ out) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t* o = out + i * 6;
+  o[0] = int32_t(idx[i]);
+  o[1] = __float_as_int(max_sim[i]);
+  o[2] = weight ? __float_as_int(weight[i]) : 0;
+  o[3] = soft_xyz ? __float_as_int(soft_xyz[i * 3 + 0]) : 0;
+  o[4] = soft_xyz ? __float_as_int(soft_xyz[i * 3 + 1]) : 0;
+  o[5] = soft_xyz ? __float_as_int(soft_xyz[i * 3 + 2]) : 0;
+}
+
+int pack_outputs_launch(const int64_t* idx, const float* max_sim, const float* weight, const float* soft_xyz, size_t n,
+                        int32_t* out, cudaStream_t stream) {
+  pack_outputs_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(idx, max_sim, weight, soft_xyz, n, out);
   return check_launch();
 }
 
@@ -197,7 +229,7 @@ int prep_model_launch(const float* mesh, const float* model_xyz, int n_obj, int 
   const size_t plane = size_t(n_obj) * M;
   float* a_xyz = aux + plane;
   float* a_planes = aux + plane * 4;
-  prep_kernel<1><<<grid, 256, smem, stream>>>(mesh, model_xyz, d, M, operand_mode == GADM_OPERAND_BF16X3,
+  prep_kernel<1, float><<<grid, 256, smem, stream>>>(mesh, model_xyz, d, M, operand_mode == GADM_OPERAND_BF16X3,
                                               operand_mode == GADM_OPERAND_BF16N, 0,
                                               static_cast<__nv_bfloat16*>(cols), nullptr, nullptr, aux, a_xyz, a_planes, plane,
                                               reinterpret_cast<__half*>(aux + plane * 7), aux_vt_pitch(M));

@@ -87,9 +87,9 @@ class KnnPyramid:
         parts = [cld] + [sr2dptxyz[s] for s in (2, 4, 8)]
         return torch.cat([p.float() for p in parts], dim=1).contiguous().view(-1, 3)
 
-    def run_packed(self, pts):
+    def run_packed(self, pts, out=None):
         lib_ws = self.workspace
-        idx = ops.knn3d_jobs(pts, pts, self.jobs, self.out_elems, self.algo, workspace=lib_ws)
+        idx = ops.knn3d_jobs(pts, pts, self.jobs, self.out_elems, self.algo, workspace=lib_ws, out=out)
         return idx
 
     def __call__(self, cld, sr2dptxyz):

@@ -34,7 +34,9 @@ def _lib_for(t):
 # --------------------------------------------------------------------------------------------- matching
 @torch.library.custom_op("gadm::prep_rows", mutates_args=(), device_types="cuda")
 def prep_rows(feat: torch.Tensor, operand_mode: int, pad_mode: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    _need(feat, torch.float32, "feat")
+    # fp32 descriptors (the reference's end_points['rgbd']) or descriptors that are already bf16 (same outputs as for
+    # the fp32 values they represent; half the bytes)
+    _need(feat, torch.bfloat16 if feat.dtype == torch.bfloat16 else torch.float32, "feat")
     B, d, N = feat.shape
     lib = _lib_for(feat)
     kp = lib.gadm_operand_k(d, operand_mode)
@@ -42,9 +44,11 @@ def prep_rows(feat: torch.Tensor, operand_mode: int, pad_mode: int) -> tuple[tor
     rows = torch.empty((B, N, kp), dtype=torch.bfloat16, device=feat.device)
     rinv = torch.empty((B, N), dtype=torch.float32, device=feat.device)
     pad_sim = torch.empty((B, N) if pad_mode else (0,), dtype=torch.float32, device=feat.device)
+    fn, name = ((lib.gadm_prep_rows_bf16, "gadm_prep_rows_bf16") if feat.dtype == torch.bfloat16
+                else (lib.gadm_prep_rows, "gadm_prep_rows"))
     with torch.cuda.device(feat.device):
-        _lib.check(lib.gadm_prep_rows(_ptr(feat), B, d, N, operand_mode, pad_mode, _ptr(rows), _ptr(rinv),
-                                      _ptr(pad_sim) if pad_mode else None, _stream()), "gadm_prep_rows")
+        _lib.check(fn(_ptr(feat), B, d, N, operand_mode, pad_mode, _ptr(rows), _ptr(rinv),
+                      _ptr(pad_sim) if pad_mode else None, _stream()), name)
     return rows, rinv, pad_sim
 
 
@@ -80,6 +84,24 @@ def _(mesh, model_xyz, operand_mode):
     kp = d * (3 if operand_mode == 1 else 1)
     return (mesh.new_empty((n_obj, M, kp), dtype=torch.bfloat16),
             mesh.new_empty((n_obj * (7 * M + 8 * ((M + 63) // 64 * 64)),)))     # gadm_aux_floats
+
+
+@torch.library.custom_op("gadm::pack_match_outputs", mutates_args=("out",), device_types="cuda")
+def pack_match_outputs(idx: torch.Tensor, max_sim: torch.Tensor, weight: torch.Tensor | None,
+                       soft_xyz: torch.Tensor | None, out: torch.Tensor) -> None:
+    """{int32 idx, max_sim, weight, x, y, z} records of every scene point into `out` (int32 [..., 6])."""
+    _need(idx, torch.int64, "idx"); _need(max_sim, torch.float32, "max_sim"); _need(out, torch.int32, "out")
+    n = idx.numel()
+    if out.numel() != 6 * n or max_sim.numel() != n:
+        raise ValueError("pack_match_outputs: out must hold 6 words per scene point")
+    if weight is not None and weight.numel() == 0:
+        weight = None
+    if soft_xyz is not None and soft_xyz.numel() == 0:
+        soft_xyz = None
+    lib = _lib_for(idx)
+    with torch.cuda.device(idx.device):
+        _lib.check(lib.gadm_pack_match_outputs(_ptr(idx), _ptr(max_sim), _ptr(weight), _ptr(soft_xyz), n, _ptr(out),
+                                               _stream()), "gadm_pack_match_outputs")
 
 
 _MATCH_WS = {}
@@ -250,15 +272,20 @@ def make_jobs(job_list):
     return arr
 
 
-def knn3d_jobs(support, query, jobs, out_elems, algo="auto", return_dist=False, workspace=None):
-    """Run a job table over flat point buffers.  support/query: [P, 3] fp32 CUDA; returns int32 [out_elems]."""
+def knn3d_jobs(support, query, jobs, out_elems, algo="auto", return_dist=False, workspace=None, out=None):
+    """Run a job table over flat point buffers.  support/query: [P, 3] fp32 CUDA; returns int32 [out_elems]
+    (`out`: write the indices there instead of allocating)."""
     _need(support, torch.float32, "support"); _need(query, torch.float32, "query")
     lib = _lib_for(support)
     a = KNN_ALGOS[algo] if isinstance(algo, str) else int(algo)
     need = lib.gadm_knn3d_workspace_bytes(jobs, len(jobs), a)
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty((max(need, 16),), dtype=torch.uint8, device=support.device)
-    idx = torch.empty((out_elems,), dtype=torch.int32, device=support.device)
+    if out is not None:
+        _need(out, torch.int32, "out")
+        if out.numel() != out_elems:
+            raise ValueError(f"out must hold {out_elems} int32")
+    idx = out if out is not None else torch.empty((out_elems,), dtype=torch.int32, device=support.device)
     d2 = torch.empty((out_elems,), dtype=torch.float32, device=support.device) if return_dist else None
     with torch.cuda.device(support.device):
         _lib.check(lib.gadm_knn3d(_ptr(support), _ptr(query), jobs, len(jobs), a, _ptr(idx), _ptr(d2),

@@ -107,6 +107,10 @@ int gadm_operand_k(int d, int operand_mode);
  *   pad_sim [B, N] fp32 or NULL: similarity of each row with the pad column (pad_mode != NONE)       */
 int gadm_prep_rows(const float* feat, int B, int d, int N, int operand_mode, int pad_mode, void* rows,
                    float* rinv, float* pad_sim, gadm_stream_t stream);
+/* The same for descriptors that are already bf16 ([B, d, N] bf16 channel-major): identical outputs to gadm_prep_rows
+ * on the fp32 values they represent, half the bytes to read (and to upload).  BF16 / BF16N operand modes only. */
+int gadm_prep_rows_bf16(const void* feat_bf16, int B, int d, int N, int operand_mode, int pad_mode, void* rows,
+                        float* rinv, float* pad_sim, gadm_stream_t stream);
 
 /* Model side (once per object bank).  mesh [n_obj, d, M] fp32 channel-major (end_points['mesh']);
  * model_xyz [n_obj, M, 3] fp32 or NULL.
@@ -135,6 +139,12 @@ int gadm_match_fwd(const void* rows, const float* rinv_rows, const float* pad_si
                    const float* aux, const uint8_t* mask, const int32_t* obj_id, int B, int N, int M, int Kp,
                    int n_obj, float gamma, int pad_mode, int mode, int64_t* idx, float* max_sim, float* weight,
                    float* soft_xyz, void* workspace, size_t workspace_bytes, gadm_stream_t stream);
+
+/* Packs the matcher outputs of n scene points into records of six 32-bit words {int32 idx, max_sim, weight, x, y, z}
+ * (weight / soft_xyz may be NULL: zeros), so that one contiguous copy carries them to the host -- the reference pulls
+ * idx and the cloud back tensor by tensor (evaluator.py:87,99).  idx must fit int32 (it is < M + 1). */
+int gadm_pack_match_outputs(const int64_t* idx, const float* max_sim, const float* weight, const float* soft_xyz,
+                            int64_t n, int32_t* out, gadm_stream_t stream);
 
 /* Flash-style CircleLoss forward, the training-side twin of the matcher.  Replaces, per batch,
  * models/geoMatch.py:102-157 (similarity of the foreground rows with the -1-padded, normalised model), :55-83

@@ -11,13 +11,20 @@
 
 using namespace gadm;
 
-__global__ void __launch_bounds__(128, 1) probe(long long* out, int reps) {
+// load: 0 = the other warps idle, 1 = they stream tcgen05.ld x32 over the S region, 2 = ld x32 + st x16 (the epilogue's
+// traffic pattern) while warp 0 issues the MMAs
+__global__ void __launch_bounds__(512, 1) probe(long long* out, int reps, int load) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
+  __shared__ uint64_t dummy[4];
   __shared__ uint32_t tmem_slot;
   for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
-  if (threadIdx.x == 0) { ptx::mbar_init(&bar, 1); ptx::fence_mbar_init(); }
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bar, 1);
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(&dummy[i], 1);
+    ptx::fence_mbar_init();
+  }
   if (threadIdx.x < 32) { ptx::tmem_alloc(&tmem_slot, 512); ptx::tmem_relinquish(); }
   ptx::fence_proxy_async();
   ptx::tc_fence_before();
@@ -27,14 +34,35 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out, int reps) {
   {
     uint32_t z[16];
     for (int i = 0; i < 16; ++i) z[i] = 0x3c003c00u;
-    const uint32_t lane_base = tm + (uint32_t((threadIdx.x >> 5) * 32) << 16);
-    for (int c = 0; c < 512; c += 16) ptx::tmem_st_32x16(lane_base + c, z);
+    const uint32_t lane_base = tm + (uint32_t(((threadIdx.x >> 5) & 3) * 32) << 16);
+    if (threadIdx.x < 128) for (int c = 0; c < 512; c += 16) ptx::tmem_st_32x16(lane_base + c, z);
     ptx::tmem_st_wait();
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
 
+  __shared__ volatile int stop_flag;
+  if (threadIdx.x == 0) stop_flag = 0;
+  __syncthreads();
+  if (threadIdx.x >= 128 && load > 0) {
+    // background TMEM traffic: 12 warps (lane quarter = warp % 4) read (and write) 32 / 16 columns of S[0] / S[1]
+    const uint32_t lane_base = tm + (uint32_t(((threadIdx.x >> 5) & 3) * 32) << 16);
+    uint32_t acc = 0;
+    while (!stop_flag) {
+      uint32_t d[32];
+      ptx::tmem_ld_32x32(lane_base + ((threadIdx.x >> 7) & 1) * 128 + 64, d);
+      ptx::tmem_ld_wait();
+      for (int i = 0; i < 32; ++i) acc += d[i];
+      if (load > 1) {
+        uint32_t z[16];
+        for (int i = 0; i < 16; ++i) z[i] = 0x3c003c00u;
+        ptx::tmem_st_32x16(lane_base + ((threadIdx.x >> 7) & 1) * 128 + 96, z);
+        ptx::tmem_st_wait();
+      }
+    }
+    if (acc == 0x12345678u) out[31] = acc;
+  }
   if (threadIdx.x == 0) {
     const uint32_t b_addr = ptx::smem_u32(smem);                  // B stages: 2 x 16 KB (128 vertices x 64 k)
     const uint32_t v_addr = ptx::smem_u32(smem + 64 * 1024);      // V tile: 2 blocks of [16 rows x 64 k] fp16
@@ -93,6 +121,23 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out, int reps) {
                 ptx::umma_f16_ts(O + (s >> 1) * 16, S + s * 32 + k * 8, ptx::umma_desc_sw128_kmajor(v_addr + (s >> 1) * 2048 + ((s & 1) * 2 + k) * 32), id_pv, 1);
             break;
           case 9: pv_mmas(id_pv64, 0); break;                       // N = 64 (timing only)
+          case 10: s_mmas(); ptx::umma_commit(&dummy[0]); break;    // S + one commit per unit (nobody waits on it)
+          case 11: s_mmas(); ptx::umma_commit(&dummy[0]); ptx::umma_commit(&dummy[1]); ptx::umma_commit(&dummy[2]); break;
+          case 12: pv_mmas(id_pv, 16); s_mmas(); ptx::umma_commit(&dummy[0]); ptx::umma_commit(&dummy[1]); break;
+          case 13:                                                  // 8 x SS 128x256x16 (the alt kernel's unit) + 2 commits
+            for (int k = 0; k < 8; ++k)
+              ptx::umma_bf16_ss(tm, ptx::umma_desc_sw128_kmajor(bss_a + (k >> 2) * 16384 + (k & 3) * 32),
+                                ptx::umma_desc_sw128_kmajor(b_addr + (k & 3) * 32), id_s256, k != 0);
+            ptx::umma_commit(&dummy[0]); ptx::umma_commit(&dummy[1]);
+            break;
+          case 14:                                                  // the same without commits
+            for (int k = 0; k < 8; ++k)
+              ptx::umma_bf16_ss(tm, ptx::umma_desc_sw128_kmajor(bss_a + (k >> 2) * 16384 + (k & 3) * 32),
+                                ptx::umma_desc_sw128_kmajor(b_addr + (k & 3) * 32), id_s256, k != 0);
+            break;
+          case 15: {                                                // S, commit, and WAIT for it every unit (full serialisation)
+            s_mmas(); ptx::umma_commit(&dummy[3]); ptx::mbar_wait(&dummy[3], rep & 1);
+          } break;
         }
       }
       ptx::umma_commit(&bar);
@@ -100,11 +145,14 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out, int reps) {
       phase ^= 1;
       return clock64() - t0;
     };
-    for (int v = 0; v < 10; ++v) {
-      run(v);                                      // warm
+    for (int v = 0; v < 16; ++v) {
+      if (v == 15) {                               // dummy[3]'s phase must restart at 0 for each run of variant 15
+        ptx::mbar_init(&dummy[3], 1); ptx::fence_mbar_init();
+      }
       const long long c = run(v);
       if (blockIdx.x == 0) out[v] = c;
     }
+    stop_flag = 1;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -113,13 +161,15 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out, int reps) {
 
 int main() {
   long long* out;
-  cudaMallocManaged(&out, 16 * sizeof(long long));
+  cudaMallocManaged(&out, 32 * sizeof(long long));
   const int reps = 256;
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  probe<<<148, 128, 100 * 1024>>>(out, reps);
+  for (int load = 0; load < 3; ++load) {
+  printf("---- background TMEM traffic from 12 warps: %s\n", load == 0 ? "none" : load == 1 ? "tcgen05.ld x32" : "tcgen05.ld x32 + st x16");
+  probe<<<148, 512, 100 * 1024>>>(out, reps, load);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
-  const char* names[10] = {"S: 8 x TS 128x128x16 (A in TMEM)",
+  const char* names[16] = {"S: 8 x TS 128x128x16 (A in TMEM)",
                            "PV: 8 x TS 128x16x16 into 4 accumulators",
                            "PV then S (kernel order)",
                            "PV: 8 x TS 128x16x16 into ONE accumulator",
@@ -128,7 +178,14 @@ int main() {
                            "PV: 8 x TS 128x32x16",
                            "8 x TS 128x256x16",
                            "PV: 8 x TS 128x16x16 into 2 accumulators",
-                           "PV: 8 x TS 128x64x16"};
-  for (int v = 0; v < 10; ++v) printf("%-48s %8.1f cycles per unit\n", names[v], double(out[v]) / reps);
+                           "PV: 8 x TS 128x64x16",
+                           "S + 1 commit per unit",
+                           "S + 3 commits per unit",
+                           "PV, S + 2 commits per unit",
+                           "8 x SS 128x256x16 + 2 commits per unit",
+                           "8 x SS 128x256x16, no commits",
+                           "S + commit + wait per unit"};
+  for (int v = 0; v < 16; ++v) printf("%-48s %8.1f cycles per unit\n", names[v], double(out[v]) / reps);
+  }
   return 0;
 }
