@@ -7,8 +7,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# GADM_LIB: load another build of the same library (the timing-trace variant of tools/); default = the product
-LIB_PATH = os.environ.get("GADM_LIB") or os.path.join(_HERE, "libgadm.so")
+LIB_PATH = os.path.join(_HERE, "libgadm.so")
 
 c_void_p, c_int, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
 

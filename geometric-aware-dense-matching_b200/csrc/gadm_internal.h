@@ -23,14 +23,7 @@ int make_tmap_2b_3d(CUtensorMap* out, const void* base, uint64_t k, uint64_t row
 //   [0, n)        1 / max(|m_j|, 1e-12)                column scales of the matcher epilogue
 //   [n, 4n)       model xyz, [n_obj, M, 3] fp32        (Kabsch moments)
 //   [4n, 7n)      x, y, z planes, [3, n_obj, M] fp32   (SOFT epilogue: one bulk copy per plane and tile)
-//   [7n, 7n + 8 n_obj Mp)   V^T, [n_obj, 16, Mp] fp16, Mp = M rounded up to 64: the B operand of the tensor-core
-//                 coordinate sums (match_fa_kernel).  Rows {x_hi, y_hi, z_hi, x_lo, y_lo, z_lo, 1, 0 ...} with
-//                 hi = fp16(x), lo = fp16(x - hi); vertices >= M are zero.
-__host__ __device__ inline int aux_vt_pitch(int M) { return (M + 63) / 64 * 64; }
-__host__ __device__ inline size_t aux_total_floats(int n_obj, int M) {
-  return size_t(n_obj) * M * 7 + size_t(n_obj) * 8 * aux_vt_pitch(M);
-}
-__host__ __device__ inline const float* aux_vt(const float* aux, int n_obj, int M) { return aux + size_t(n_obj) * M * 7; }
+__host__ __device__ inline size_t aux_total_floats(int n_obj, int M) { return size_t(n_obj) * M * 7; }
 __host__ __device__ inline const float* aux_scales(const float* aux, int, int) { return aux; }
 __host__ __device__ inline const float* aux_xyz(const float* aux, int n_obj, int M) { return aux + size_t(n_obj) * M; }
 __host__ __device__ inline const float* aux_planes(const float* aux, int n_obj, int M) { return aux + size_t(n_obj) * M * 4; }

@@ -53,8 +53,6 @@ struct MatchParams {
   const float* pad_sim;    // [B, N] or null
   const float* scales;     // [n_obj, M]  1/|m_j|
   const float* planes;     // [3, n_obj, M] model x / y / z planes (SOFT)
-  const void* vt;          // [n_obj, 16, Mp] fp16 V^T of the tensor-core coordinate sums (match_fa_kernel)
-  const void* rows_ptr;    // [B, N, K'] bf16 rows (match_fa_kernel loads its A operand into tensor memory itself)
   const uint8_t* mask;     // [B, N] or null
   const int32_t* obj_id;   // [B] or null
   int64_t* idx;
@@ -68,7 +66,6 @@ struct MatchParams {
   int stash_slots;
   // persistent kernels: the (frame, row block, model tile) units are dealt out evenly, in linear order, to the CTAs of
   // the grid; a row block whose tiles end up in several CTAs is finished by the last of them to arrive
-  int dbg;                 // timing ablations (gadm_config_set "match.dbg"); 0 in production
   int T;                   // model tiles per row
   int RB;                  // row blocks (PART_ROWS rows) per frame
   long long total_units;   // B * RB * T

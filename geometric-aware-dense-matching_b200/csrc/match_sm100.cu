@@ -531,6 +531,9 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
     }
   } else if (warp == EPI_WARPS + 1) {
     // ============================== UMMA issuer ==============================
+    // (one lane issues.  Issuing from the whole warp with an elected lane keeps the operands in uniform registers and
+    // shortens the scalar code between MMAs, but 32 polling lanes cost the epilogue warps of the same scheduler more
+    // than that saves: 0.403 ms against 0.381 ms at the BASELINE shape)
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(BM, PBN);
       ptx::mbar_wait(&bars->a_full, 0);
@@ -1193,504 +1196,6 @@ inline int match_alt_stages(int KB) {
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// match_fa_kernel: SOFT for K' <= 128 -- the fused softmax laid out the way flash attention lays it out on this
-// architecture.  The p * xyz / p sums of the other SOFT kernels are four FP32-pipe operations and three broadcast
-// LDS.128 per score next to one MUFU.EX2; here they are one more GEMM on the tensor core:
-//   S = F M^T           tcgen05.mma 128x128x16, A = the CTA's 128 rows from TENSOR MEMORY (written once per segment with
-//                       tcgen05.st, so the MMAs read only the model tile from shared memory), accumulators S[0], S[1]
-//                       alternate between model tiles: S(t+1) is computed while the epilogue works on S(t)
-//   epilogue warps      thread = row x 32-column slice: score = S * 1/|m_j| (exact argmax track as in
-//                       match_alt_kernel), p = 2^(score * g - off) with a LAZY per-thread reference exponent `off`
-//                       (raised, with a rescale of the thread's own O accumulator, only when exceeded by more than 14,
-//                       so p <= 2^14 fits fp16), p rounded to fp16 and stored back over the scores it came from
-//   O += P V            tcgen05.mma 128x16x16, A = P from TMEM, B = V^T tile from shared memory with rows
-//                       {x_hi, y_hi, z_hi, x_lo, y_lo, z_lo, 1}: the coordinate sums AND the sum of p, in fp32, from the
-//                       same rounded p -- the rounding cancels to second order in soft_xyz; weight = 2^(max - off) / sum
-//                       carries at most one fp16 rounding (2^-11) of the dominant term.
-// A thread never shares its reference exponent: each column slice has its own 16-column O accumulator.
-// TMEM: S[0], S[1] 128 columns each | A 64 | O[4] 16 each = 384 of 512.
-// Persistent: units (frame, 128-row tile, 128-vertex tile) dealt out evenly to the CTAs as in match_alt_kernel.
-// Issue: the whole UMMA warp runs the loop and one elected lane issues (ptx::umma_f16_ts_warp): 64-cycle MMAs do not
-// hide the scalar code of an `if (lane == 0)` issuer.
-constexpr int FBN = 128;                        // model vertices per tile == UMMA N of the similarity
-constexpr int FB_STAGE_BYTES = FBN * BK * 2;    // 16 KB
-constexpr int F_MAX_STAGES = 8;
-constexpr int F_CS = FBN / 4;                   // 32 columns per slice
-constexpr int VT_BLK_BYTES = 16 * BK * 2;       // [16 rows x 64 vertices] fp16 = 2 KB (two SWIZZLE_128B atoms)
-constexpr int VT_TILE_BYTES = (FBN / BK) * VT_BLK_BYTES;
-constexpr int F_SC_BYTES = FBN * 4;
-constexpr int F_SLOTS = 4;                      // ring of {column scales, V^T} per tile
-constexpr int F_TM_A = 2 * FBN;                 // TMEM column of A
-constexpr int F_TM_O = F_TM_A + 64;             // TMEM column of O[0]
-constexpr float F_LAZY = 14.f;                  // the reference exponent lags the running maximum by at most 2^14
-constexpr int FA_THREADS = 640;                 // 4 epilogue warpgroups + 1 producer warpgroup (TMA, UMMA, two idle warps)
-constexpr int F_STASH_BYTES = STASH_BYTES;      // one row per thread
-
-struct FaBarriers {
-  uint64_t full[F_MAX_STAGES];
-  uint64_t empty[F_MAX_STAGES];
-  uint64_t aux_full[F_SLOTS];     // scales + V^T of the tile have landed
-  uint64_t sc_empty[F_SLOTS];     // scales read by every epilogue warp
-  uint64_t vt_empty[F_SLOTS];     // V^T read by the tile's P V MMAs (tcgen05.commit)
-  uint64_t a_ready;               // the segment's rows are in tensor memory (all epilogue warps)
-  uint64_t s_full[2];             // S[buf] complete (tcgen05.commit)
-  uint64_t p_full[2];             // P[buf] stored by every epilogue warp: P V may run, then S[buf] may be overwritten
-  uint64_t o_full;                // every P V MMA of the segment has completed
-  uint32_t tmem_base;
-  int merge_lo, merge_hi;
-  uint32_t pad;
-};
-
-__global__ void __launch_bounds__(FA_THREADS, 1)
-match_fa_kernel(const __grid_constant__ CUtensorMap tmap_cols, const __grid_constant__ CUtensorMap tmap_vt,
-                const MatchParams p) {
-  constexpr int SL = 4;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_b = smem;                                        // model tile ring
-  uint8_t* smem_vt = smem_b + p.stages * FB_STAGE_BYTES;         // V^T ring (1024-byte aligned atoms)
-  uint8_t* smem_sc = smem_vt + F_SLOTS * VT_TILE_BYTES;          // column scale ring
-  uint8_t* smem_stash = smem_sc + F_SLOTS * F_SC_BYTES;
-  float* smem_xmax = reinterpret_cast<float*>(smem_stash + F_STASH_BYTES);     // [SL][128]
-  float* smem_xch = smem_xmax + SL * BM;                                       // [SL - 1][128][8]
-  FaBarriers* bars = reinterpret_cast<FaBarriers*>(smem_xch + (SL - 1) * BM * 8);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const long long u_begin = sched_begin(p, blockIdx.x), u_end = sched_begin(p, blockIdx.x + 1);
-
-  if (warp == EPI_WARPS && lane == 0) {
-    ptx::prefetch_tensormap(&tmap_cols);
-    ptx::prefetch_tensormap(&tmap_vt);
-    for (int s = 0; s < p.stages; ++s) {
-      ptx::mbar_init(&bars->full[s], 1);
-      ptx::mbar_init(&bars->empty[s], 1);
-    }
-    for (int a = 0; a < F_SLOTS; ++a) {
-      ptx::mbar_init(&bars->aux_full[a], 1);
-      ptx::mbar_init(&bars->sc_empty[a], EPI_WARPS);
-      ptx::mbar_init(&bars->vt_empty[a], 1);
-    }
-    ptx::mbar_init(&bars->a_ready, EPI_WARPS);
-    for (int a = 0; a < 2; ++a) {
-      ptx::mbar_init(&bars->s_full[a], 1);
-      ptx::mbar_init(&bars->p_full[a], EPI_WARPS);
-    }
-    ptx::mbar_init(&bars->o_full, 1);
-    ptx::fence_mbar_init();
-  }
-  if (warp == EPI_WARPS + 1) {
-    ptx::tmem_alloc(&bars->tmem_base, TMEM_COLS);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = bars->tmem_base;
-
-  // register reallocation (whole warpgroups): the producer warpgroup keeps 56 registers per thread (only what it frees
-  // can be re-allocated), the epilogue warpgroups get 104
-  if (warp >= EPI_WARPS) {
-  ptx::setmaxnreg_dec<56>();
-  if (warp == EPI_WARPS) {
-    // ============================== TMA producer ==============================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0, n = 0;
-      for (long long u = u_begin; u < u_end;) {
-        const int rbg = int(u / p.T), ta = int(u - (long long)rbg * p.T);
-        const int tb = int(min((long long)p.T, ta + (u_end - u)));
-        const int obj = frame_object(p, rbg / p.RB);
-        const float* sc_tab = p.scales + size_t(obj) * p.M;
-        for (int t = ta; t < tb; ++t, ++n) {
-          const int slot = n % F_SLOTS;
-          const uint32_t par = ((n / F_SLOTS) & 1) ^ 1;
-          const uint32_t bytes = uint32_t(min(FBN, p.M - t * FBN)) * 4;   // M % 8 == 0: a multiple of 16
-          // the model tile first: the similarity of tile t + 1 is issued before the P V of tile t frees an aux slot
-          for (int kb = 0; kb < p.KB; ++kb) {
-            ptx::mbar_wait_sleep(&bars->empty[stage], phase ^ 1);
-            ptx::mbar_arrive_expect_tx(&bars->full[stage], FB_STAGE_BYTES);
-            ptx::tma_load_3d(smem_b + stage * FB_STAGE_BYTES, &tmap_cols, &bars->full[stage], kb * BK, t * FBN, obj);
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
-          }
-          ptx::mbar_wait_sleep(&bars->sc_empty[slot], par);
-          ptx::mbar_wait_sleep(&bars->vt_empty[slot], par);
-          ptx::mbar_arrive_expect_tx(&bars->aux_full[slot], bytes + VT_TILE_BYTES);
-          ptx::bulk_load_1d(smem_sc + slot * F_SC_BYTES, sc_tab + size_t(t) * FBN, bytes, &bars->aux_full[slot]);
-#pragma unroll
-          for (int h = 0; h < FBN / BK; ++h)   // vertices >= M: zero rows of the table or zero-filled by TMA
-            ptx::tma_load_3d(smem_vt + slot * VT_TILE_BYTES + h * VT_BLK_BYTES, &tmap_vt, &bars->aux_full[slot],
-                             t * FBN + h * BK, 0, obj);
-        }
-        u += tb - ta;
-      }
-    }
-  } else if (warp == EPI_WARPS + 1) {
-    // ============================== UMMA issuer (the whole warp runs the loop, one elected lane issues) ======
-    constexpr uint32_t idesc_s = ptx::umma_idesc_bf16_f32(BM, FBN);
-    constexpr uint32_t idesc_pv = ptx::umma_idesc_f16_f32(BM, 16);
-    int stage = 0;
-    uint32_t phase = 0, n = 0, seg = 0;
-    // P V of tile m (its P sits in S[m & 1]): 4 slices x 2 K steps, A = P over the first half of the slice's scores
-    auto issue_pv = [&](uint32_t m, bool first_tile) {
-      const uint32_t buf = m & 1;
-      ptx::mbar_wait_sleep(&bars->p_full[buf], (m >> 1) & 1);
-      ptx::tc_fence_after();
-      const uint32_t vt_addr = ptx::smem_u32(smem_vt + (m % F_SLOTS) * VT_TILE_BYTES);
-      if (!(p.dbg & 1)) {
-#pragma unroll
-        for (int s = 0; s < SL; ++s)
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
-            ptx::umma_f16_ts_warp(tmem_base + F_TM_O + s * 16, tmem_base + buf * FBN + s * F_CS + k * 8,
-                                  ptx::umma_desc_sw128_kmajor(vt_addr + (s >> 1) * VT_BLK_BYTES + ((s & 1) * 2 + k) * 32),
-                                  idesc_pv, !(first_tile && k == 0));
-      }
-      ptx::umma_commit_warp(&bars->vt_empty[m % F_SLOTS]);
-    };
-    for (long long u = u_begin; u < u_end; ++seg) {
-      const int ntiles = int(min((long long)p.T - (u % p.T), u_end - u));
-      ptx::mbar_wait_sleep(&bars->a_ready, seg & 1);
-      ptx::tc_fence_after();
-      for (int t = 0; t < ntiles; ++t, ++n) {
-        // S(n) into S[n & 1]: what that buffer held (P of tile n - 2) was read by P V MMAs issued before this point
-        const uint32_t d_tmem = tmem_base + (n & 1) * FBN;
-        for (int kb = 0; kb < p.KB; ++kb) {
-          ptx::mbar_wait_sleep(&bars->full[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t b_addr = ptx::smem_u32(smem_b + stage * FB_STAGE_BYTES);
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            ptx::umma_f16_ts_warp(d_tmem, tmem_base + F_TM_A + (kb * (BK / UMMA_K) + k) * (UMMA_K / 2),
-                                  ptx::umma_desc_sw128_kmajor(b_addr + k * UMMA_K * 2), idesc_s, (kb | k) != 0);
-          ptx::umma_commit_warp(&bars->empty[stage]);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        }
-        ptx::umma_commit_warp(&bars->s_full[n & 1]);
-        if (t > 0) issue_pv(n - 1, t == 1);        // while the epilogue works on S(n)
-      }
-      issue_pv(n - 1, ntiles == 1);                // the last tile's P V, then the segment's sums are final
-      ptx::umma_commit_warp(&bars->o_full);
-      u += ntiles;
-    }
-  }
-  } else {
-    ptx::setmaxnreg_inc<104>();
-    // ============================== epilogue warps (thread == one row x one 32-column slice) ==============
-    const int q = warp & 3;
-    const int sub = warp >> 2;                       // 32-column slice of every tile
-    const int row_in_tile = q * 32 + lane;
-    const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
-    const uint32_t stash_addr = ptx::smem_u32(smem_stash) + threadIdx.x * 16;
-    const uint32_t o_tmem = lane_base + F_TM_O + sub * 16;
-    const int rbg_first = int(u_begin / p.T);
-    const int Kp = p.KB * BK;
-
-    uint32_t n = 0, seg = 0;
-    for (long long u = u_begin; u < u_end; ++seg) {
-      const int rbg = int(u / p.T), ta = int(u - (long long)rbg * p.T);
-      const int tb = int(min((long long)p.T, ta + (u_end - u)));
-      const int b = rbg / p.RB, row0 = (rbg % p.RB) * BM;
-      u += tb - ta;
-
-      // ---- this thread's row (K range [sub K'/4, (sub + 1) K'/4)) from global memory into tensor memory: lane = row,
-      // one 32-bit column = two consecutive k, the layout tcgen05.mma reads an A operand in.  Every MMA of the previous
-      // segment that read A has completed (its last s_full was seen) and its sums have been read (program order).
-      const int row = row0 + row_in_tile;
-      const bool row_ok = row < p.N;
-      const size_t grow = size_t(b) * p.N + (row_ok ? row : 0);
-      const float g = row_ok ? p.gamma_log2e * p.rinv_rows[grow] : 0.f;   // exponent scale: t = score * g (log2), g >= 0
-      {
-        const int kq = Kp / 4;                       // bf16 elements per thread: 16 (K' = 64) or 32
-        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.rows_ptr) +
-                                                          (grow * Kp + sub * kq) * 2);
-        const uint32_t dst = lane_base + F_TM_A + sub * (kq / 2);
-        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
-        if (row_ok) {
-          v0 = src[0]; v1 = src[1];
-          if (kq == 32) { v2 = src[2]; v3 = src[3]; }
-        }
-        if (kq == 32) {
-          const uint32_t w[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
-          ptx::tmem_st_32x16(dst, w);
-        } else {
-          const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-          ptx::tmem_st_32x8(dst, w);
-        }
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bars->a_ready);
-      }
-
-      float vmax = -INFINITY;
-      int vgrp = 0;
-      float off = -INFINITY;                         // reference exponent of this thread's sums (log2 units)
-
-      for (int t = ta; t < tb; ++t, ++n) {
-        const int slot = n % F_SLOTS;
-        const uint32_t buf = n & 1;
-        const int ncols = min(FBN, p.M - t * FBN) - sub * F_CS;   // valid columns of this slice (may be <= 0)
-        const uint32_t sc = ptx::smem_u32(smem_sc + slot * F_SC_BYTES) + sub * F_CS * 4;
-        const int col_base = t * FBN + sub * F_CS;
-        const bool o_live = t > ta;                  // the O accumulator holds the sums of the segment's earlier tiles
-        if (!(ptx::mbar_try_wait(&bars->aux_full[slot], (n / F_SLOTS) & 1) &
-              ptx::mbar_try_wait(&bars->s_full[buf], (n >> 1) & 1))) {
-          ptx::mbar_wait_sleep(&bars->aux_full[slot], (n / F_SLOTS) & 1);
-          ptx::mbar_wait_sleep(&bars->s_full[buf], (n >> 1) & 1);
-        }
-        ptx::tc_fence_after();
-        const uint32_t s_tmem = lane_base + buf * FBN + sub * F_CS;
-        uint32_t pk[16];
-
-        // One visit: this thread's 32 scores of the accumulator.  kGuard (ragged last tile only) masks columns >= M.
-        auto visit = [&](auto guard_tag) {
-          constexpr bool kGuard = decltype(guard_tag)::value;
-          // scaled scores of the chunk: score = S * 1/|m_j| (packed pairs, even column in the low half)
-          auto scaled = [&](const uint32_t (&d)[32], uint64_t (&v)[16]) {
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 cm = ptx::lds128(sc + j4 * 16);
-              v[j4 * 2 + 0] = ptx::fmul2(ptx::pack2(d[j4 * 4 + 0], d[j4 * 4 + 1]), ptx::pack2f(cm.x, cm.y));
-              v[j4 * 2 + 1] = ptx::fmul2(ptx::pack2(d[j4 * 4 + 2], d[j4 * 4 + 3]), ptx::pack2f(cm.z, cm.w));
-            }
-            if (kGuard) {                            // columns >= M never win and weigh nothing
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float lo, hi;
-                ptx::unpack2f(v[j], lo, hi);
-                if (2 * j >= ncols) lo = -INFINITY;
-                if (2 * j + 1 >= ncols) hi = -INFINITY;
-                v[j] = ptx::pack2f(lo, hi);
-              }
-            }
-          };
-          // p = 2^(score * g - off) of one packed pair, rounded to fp16 (a column >= M has score -inf: p = 0, but
-          // -inf * 0 = NaN when g == 0, hence the explicit zero)
-          auto exp_pair = [&](uint64_t v2, int j) -> uint32_t {
-            float lo, hi;
-            ptx::unpack2f(ptx::ex2_2(ptx::ffma2(v2, ptx::pack2f(g, g), ptx::pack2f(-off, -off))), lo, hi);
-            if (kGuard) {
-              if (2 * j >= ncols) lo = 0.f;
-              if (2 * j + 1 >= ncols) hi = 0.f;
-            }
-            return ptx::cvt_f16x2(hi, lo);
-          };
-          auto group_max = [&](const uint64_t* v4) -> float {
-            float f[GRP];
-#pragma unroll
-            for (int j = 0; j < GRP / 2; ++j) ptx::unpack2f(v4[j], f[2 * j], f[2 * j + 1]);
-            const float a0 = ptx::fmax3(f[0], f[1], f[2]), a1 = ptx::fmax3(f[3], f[4], f[5]);
-            return ptx::fmax3(a0, a1, fmaxf(f[6], f[7]));
-          };
-
-          float gm[4];
-          {
-            // ---- main pass.  The exponentials are SPECULATIVE, taken with the reference exponent as it stands, so
-            // the 32 MUFU.EX2 depend on nothing but the scores and overlap the maximum tree.
-            uint32_t d[32];
-            ptx::tmem_ld_32x32(s_tmem, d);
-            ptx::tmem_ld_wait();
-            uint64_t v[16];
-            scaled(d, v);
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) pk[h * 4 + j] = exp_pair(v[h * 4 + j], h * 4 + j);
-              gm[h] = group_max(&v[h * 4]);
-            }
-          }
-          const float cmax = ptx::fmax3(gm[0], gm[1], fmaxf(gm[2], gm[3]));
-          const float tmx = cmax * g;
-          const bool need = tmx > off + F_LAZY;             // the chunk exceeds the reference exponent by > 2^14
-          const bool any_up = __any_sync(0xffffffffu, cmax > vmax);
-          const bool any_need = __any_sync(0xffffffffu, need);
-          if (any_up | any_need) {
-            // ---- rare pass (after the first tiles): some row of the warp improves its maximum or outgrows its
-            // exponent.  The scores are still in tensor memory (P is stored below): read and scale them again.
-            uint32_t d[32];
-            ptx::tmem_ld_32x32(s_tmem, d);
-            ptx::tmem_ld_wait();
-            uint64_t v[16];
-            scaled(d, v);
-            if (any_up) {
-#pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                const bool up = gm[h] > vmax;       // strict: a later equal value never displaces the first index
-                ptx::sts_stash8(up, stash_addr, v[h * 4 + 0], v[h * 4 + 1], v[h * 4 + 2], v[h * 4 + 3]);
-                vgrp = up ? col_base + h * GRP : vgrp;
-                vmax = up ? gm[h] : vmax;
-              }
-            }
-            if (any_need) {
-              // lazy reference exponent: raised to the chunk's maximum, this thread's sums rescaled, the chunk's
-              // exponentials redone
-              const float noff = need ? tmx : off;
-              if (o_live) {
-                uint32_t o[8];
-                ptx::tmem_ld_32x8(o_tmem, o);
-                ptx::tmem_ld_wait();
-                const float f = need ? ptx::ex2_approx(off - noff) : 1.f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-                ptx::tmem_st_32x8(o_tmem, o);
-              }
-              off = noff;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) pk[j] = exp_pair(v[j], j);
-            }
-          }
-        };
-        if (ncols >= F_CS && !(p.dbg & 8)) {
-          visit(std::integral_constant<bool, false>{});
-        } else if (ncols > 0 && !(p.dbg & 8)) {
-          visit(std::integral_constant<bool, true>{});
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = 0u;   // the P V MMAs read this slice whatever it holds
-        }
-        ptx::tmem_st_32x16(s_tmem, pk);
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          ptx::mbar_arrive(&bars->p_full[buf]);
-          ptx::mbar_arrive(&bars->sc_empty[slot]);
-        }
-        // running maxima shared across the four slices of a row after the segment's tiles 0, 1, 3, 7, 15, 31
-        // (see match_alt_kernel): fewer rare passes
-        const int tl = t - ta;
-        if ((tl & (tl + 1)) == 0 && tl < 32 && t + 1 < tb) {
-          smem_xmax[sub * BM + row_in_tile] = vmax;
-          asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-          float m = vmax;
-#pragma unroll
-          for (int s2 = 0; s2 < SL; ++s2) m = fmaxf(m, smem_xmax[s2 * BM + row_in_tile]);
-          if (vmax < m) { vmax = m; vgrp = NO_RECORD; }
-          asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-        }
-      }
-
-      // ---- end of the segment: this thread's sums (relative to its own reference exponent), its first maximal index
-      ptx::mbar_wait_sleep(&bars->o_full, seg & 1);
-      ptx::tc_fence_after();
-      float vm, so, sl, sx, sy, sz;
-      int vi;
-      {
-        uint32_t o[8];
-        ptx::tmem_ld_32x8(o_tmem, o);
-        ptx::tmem_ld_wait();
-        so = off;
-        sx = __uint_as_float(o[0]) + __uint_as_float(o[3]);
-        sy = __uint_as_float(o[1]) + __uint_as_float(o[4]);
-        sz = __uint_as_float(o[2]) + __uint_as_float(o[5]);
-        sl = __uint_as_float(o[6]);
-        vm = vmax;
-        vi = NO_RECORD;
-        if (vmax > -INFINITY && vgrp != NO_RECORD) {
-          int j_first = GRP - 1;
-#pragma unroll
-          for (int k = GRP / 4 - 1; k >= 0; --k) {
-            const float4 sv = ptx::lds128(stash_addr + k * STASH_PLANE);
-            if (sv.w == vmax) j_first = 4 * k + 3;
-            if (sv.z == vmax) j_first = 4 * k + 2;
-            if (sv.y == vmax) j_first = 4 * k + 1;
-            if (sv.x == vmax) j_first = 4 * k + 0;
-          }
-          vi = vgrp + j_first;
-        }
-        if (sub > 0) {
-          float4* x = reinterpret_cast<float4*>(smem_xch + ((sub - 1) * BM + row_in_tile) * 8);
-          x[0] = make_float4(vm, __int_as_float(vi), so, sl);
-          x[1] = make_float4(sx, sy, sz, 0.f);
-        }
-      }
-      ptx::tc_fence_before();
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-      if (sub == 0) {
-        // one more partial result (v, i, o, l, x, y, z) folded into the row's: maximum with first-index ties, sums
-        // brought to the larger reference exponent (2^-inf = 0 retires a slice that never saw a valid column)
-        auto fold = [&](float v1, int i1, float o1, float l1, float x1, float y1, float z1) {
-          if (v1 > vm || (v1 == vm && i1 < vi)) { vm = v1; vi = i1; }
-          const float om = fmaxf(so, o1);
-          const float fa = ptx::ex2_approx(so - om), fb = ptx::ex2_approx(o1 - om);
-          sl = sl * fa + l1 * fb; sx = sx * fa + x1 * fb;
-          sy = sy * fa + y1 * fb; sz = sz * fa + z1 * fb;
-          so = om;
-        };
-#pragma unroll
-        for (int s2 = 0; s2 < SL - 1; ++s2) {
-          const float4* x = reinterpret_cast<const float4*>(smem_xch + (s2 * BM + row_in_tile) * 8);
-          const float4 a = x[0], c = x[1];
-          fold(a.x, __float_as_int(a.y), a.z, a.w, c.x, c.y, c.z);
-        }
-        bool finish = ta == 0 && tb == p.T;
-        if (!finish) {
-          float4* part = reinterpret_cast<float4*>(p.partial) +
-                         (size_t(blockIdx.x) * 2 + (rbg == rbg_first ? 0 : 1)) * PART_ROWS * 2;
-          part[row_in_tile * 2 + 0] = make_float4(vm, __int_as_float(vi), so, sl);
-          part[row_in_tile * 2 + 1] = make_float4(sx, sy, sz, 0.f);
-          __threadfence();
-          asm volatile("bar.sync 3, 128;" ::: "memory");
-          if (threadIdx.x == 0) {
-            const int c_lo = sched_cta_of(p, (long long)rbg * p.T), c_hi = sched_cta_of(p, (long long)(rbg + 1) * p.T - 1);
-            const unsigned int old = atomicAdd(&p.seg_count[c_lo], 1u);
-            bars->merge_lo = old == unsigned(c_hi - c_lo) ? c_lo : -1;
-            bars->merge_hi = c_hi;
-          }
-          asm volatile("bar.sync 3, 128;" ::: "memory");
-          const int c_lo = bars->merge_lo, c_hi = bars->merge_hi;
-          if (c_lo >= 0) {                           // last to arrive: merge every segment of the row tile
-            __threadfence();
-            vm = -INFINITY; vi = NO_RECORD; so = -INFINITY; sl = sx = sy = sz = 0.f;
-            for (int c = c_lo; c <= c_hi; ++c) {     // ascending columns: on ties the earlier segment wins
-              const float4* q4 = reinterpret_cast<const float4*>(p.partial) +
-                                 (size_t(c) * 2 + (int(sched_begin(p, c) / p.T) == rbg ? 0 : 1)) * PART_ROWS * 2;
-              const float4 a = ptx::ldg_cg128(q4 + row_in_tile * 2), cc = ptx::ldg_cg128(q4 + row_in_tile * 2 + 1);
-              fold(a.x, __float_as_int(a.y), a.z, a.w, cc.x, cc.y, cc.z);
-            }
-            finish = true;
-          }
-        }
-        if (finish && row_ok) {
-          const bool keep = p.mask == nullptr || p.mask[grow] != 0;
-          float best = vm * p.rinv_rows[grow];
-          int64_t best_idx = vi;
-          if (p.pad_mode != GADM_PAD_NONE) {
-            const float ps = p.pad_sim[grow];
-            if (ps > best) { best = ps; best_idx = p.M; }
-          }
-          p.idx[grow] = keep ? best_idx : int64_t(-1);
-          p.max_sim[grow] = keep ? best : 0.f;
-          const float inv = 1.f / sl;
-          p.weight[grow] = keep ? ptx::ex2_approx(vm * g - so) * inv : 0.f;   // softmax value at the maximum
-          p.soft_xyz[grow * 3 + 0] = keep ? sx * inv : 0.f;
-          p.soft_xyz[grow * 3 + 1] = keep ? sy * inv : 0.f;
-          p.soft_xyz[grow * 3 + 2] = keep ? sz * inv : 0.f;
-        }
-      }
-    }
-  }
-
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == EPI_WARPS + 1) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
-  }
-}
-
-inline size_t match_fa_smem_bytes(int stages) {
-  return size_t(stages) * FB_STAGE_BYTES + F_SLOTS * (VT_TILE_BYTES + F_SC_BYTES) + F_STASH_BYTES + 4 * BM * 4 +
-         3 * BM * 32 + sizeof(FaBarriers) + 1024;
-}
-inline int match_fa_stages() {
-  int stages = F_MAX_STAGES;
-  while (stages > 0 && match_fa_smem_bytes(stages) > 227 * 1024) --stages;
-  return stages;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // Host side: per-device facts read once by gadm_init(), kernel selection, launch.
 constexpr int MAX_DEVICES = 64;
 struct DeviceInfo {
@@ -1712,9 +1217,6 @@ struct MatchConfig {
   int pair = -1;        // match.pair  1 / 0: force / forbid the paired-row kernel
   int rt = -1;          // match.rt    1 / 2: row tiles per CTA of match_kernel
   int ctas = -1;        // match.ctas  grid of the persistent kernels (default: one CTA per SM)
-  int fa = -1;          // match.fa    1 / 0: allow / forbid the tensor-core-sums SOFT kernel (match_fa_kernel)
-  int dbg = -1;         // match.dbg   timing ablations of match_fa_kernel (results are WRONG): 1 no P V MMAs, 2 no
-                        //             exponentials, 4 no argmax track, 8 no epilogue arithmetic at all
 };
 MatchConfig g_cfg;
 
@@ -1734,8 +1236,6 @@ int match_config_set(const char* key, int value) {
   if (!strcmp(key, "match.pair")) { g_cfg.pair = value; return GADM_OK; }
   if (!strcmp(key, "match.rt")) { g_cfg.rt = value; return GADM_OK; }
   if (!strcmp(key, "match.ctas")) { g_cfg.ctas = value; return GADM_OK; }
-  if (!strcmp(key, "match.fa")) { g_cfg.fa = value; return GADM_OK; }
-  if (!strcmp(key, "match.dbg")) { g_cfg.dbg = value; return GADM_OK; }
   return GADM_ERR_BAD_ARG;
 }
 
@@ -1751,7 +1251,6 @@ int match_configure(int device) {
   if ((rc = set_smem_limit(match_alt_kernel<false, false>)) != GADM_OK) return rc;
   if ((rc = set_smem_limit(match_alt_kernel<true, false>)) != GADM_OK) return rc;
   if ((rc = set_smem_limit(match_alt_kernel<false, true>)) != GADM_OK) return rc;
-  if ((rc = set_smem_limit(match_fa_kernel)) != GADM_OK) return rc;
   int sms = 0;
   cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (e != cudaSuccess) return set_cuda_error(e);
@@ -1805,29 +1304,6 @@ static int match_launch_t(const void* rows, const void* cols, MatchParams p, int
         match_alt_kernel<false, true><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
       else
         match_alt_kernel<false, false><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
-      return check_launch();
-    }
-  }
-  if (kSoft) {
-    // tensor-core-sums persistent kernel (SOFT; K' <= 128, gamma >= 0, needs the workspace and more than one row tile
-    // per frame)
-    const int fstages = match_fa_stages();
-    if (cfg.fa != 0 && p.stash != nullptr && KB <= 2 && fstages >= 2 * KB && p.N > BM && p.gamma_log2e >= 0.f) {
-      p.KB = KB; p.stages = fstages;
-      p.dbg = cfg.dbg > 0 ? cfg.dbg : 0;
-      p.T = (p.M + FBN - 1) / FBN;
-      p.RB = (p.N + BM - 1) / BM;                    // this kernel's row block is one row tile
-      p.total_units = (long long)p.B * p.RB * p.T;
-      int grid = cfg.ctas > 0 ? min(cfg.ctas, sms) : sms;
-      if ((long long)grid > p.total_units) grid = int(p.total_units);
-      CUtensorMap tmap_cols, tmap_vt;
-      int rc = make_tmap_2b_3d(&tmap_cols, cols, uint64_t(Kp), uint64_t(p.M), uint64_t(p.n_obj), BK, FBN, 0);
-      if (rc != GADM_OK) return rc;
-      rc = make_tmap_2b_3d(&tmap_vt, p.vt, uint64_t(aux_vt_pitch(p.M)), 16, uint64_t(p.n_obj), BK, 16, 1);
-      if (rc != GADM_OK) return rc;
-      cudaError_t e = cudaMemsetAsync(p.seg_count, 0, size_t(grid) * sizeof(unsigned int), stream);
-      if (e != cudaSuccess) return set_cuda_error(e);
-      match_fa_kernel<<<grid, FA_THREADS, match_fa_smem_bytes(fstages), stream>>>(tmap_cols, tmap_vt, p);
       return check_launch();
     }
   }
@@ -1894,10 +1370,9 @@ int match_launch(const void* rows, const float* rinv_rows, const float* pad_sim,
   p.stash_slots = slots;
   p.seg_count = ws_ok ? reinterpret_cast<unsigned int*>(ws + size_t(slots) * STASH_SLOT_BYTES) : nullptr;
   p.partial = ws_ok ? reinterpret_cast<float*>(ws + size_t(slots) * STASH_SLOT_BYTES + ws_counter_bytes()) : nullptr;
-  p.T = 0; p.RB = 0; p.total_units = 0; p.dbg = 0;
+  p.T = 0; p.RB = 0; p.total_units = 0;
   p.rinv_rows = rinv_rows; p.pad_sim = pad_sim; p.scales = aux_scales(aux, n_obj, M);
   p.planes = aux_planes(aux, n_obj, M); p.mask = mask; p.obj_id = obj_id;
-  p.vt = aux_vt(aux, n_obj, M); p.rows_ptr = rows;
   p.idx = idx; p.max_sim = max_sim; p.weight = weight; p.soft_xyz = soft_xyz;
   p.B = B; p.N = N; p.M = M; p.KB = 0; p.n_obj = n_obj; p.stages = 0; p.pad_mode = pad_mode;
   p.gamma_log2e = gamma * 1.4426950408889634f;

@@ -25,8 +25,7 @@ template <int kSide, typename TIn>
 __global__ void __launch_bounds__(256)
 prep_kernel(const TIn* __restrict__ src, const float* __restrict__ xyz, int d, int P, int x3, int prenorm, int pad_mode,
             __nv_bfloat16* __restrict__ dst, float* __restrict__ rinv, float* __restrict__ pad_sim,
-            float* __restrict__ aux_scale, float* __restrict__ aux_xyz, float* __restrict__ aux_planes, size_t plane,
-            __half* __restrict__ vt, int vt_pitch) {
+            float* __restrict__ aux_scale, float* __restrict__ aux_xyz, float* __restrict__ aux_planes, size_t plane) {
   extern __shared__ float tile[];  // [d][PTS + 1]
   const int g = blockIdx.y;
   const int p0 = blockIdx.x * PTS;
@@ -110,21 +109,6 @@ prep_kernel(const TIn* __restrict__ src, const float* __restrict__ xyz, int d, i
       const float v = xyz ? xyz[(size_t(g) * P + p0) * 3 + e] : 0.f;
       aux_xyz[(size_t(g) * P + p0) * 3 + e] = v;
       aux_planes[c * plane + size_t(g) * P + p] = v;
-      // V^T rows c (hi) and 3 + c (lo): x = hi + lo to ~2^-22 relative
-      const __half hi = __float2half_rn(v);
-      __half* col = vt + size_t(g) * 16 * vt_pitch + p;
-      col[size_t(c) * vt_pitch] = hi;
-      col[size_t(3 + c) * vt_pitch] = __float2half_rn(v - __half2float(hi));
-    }
-    // row 6 = 1 (the sum of p), rows 7..15 = 0; the last CTA also zeroes the vertices [P, vt_pitch) of every row
-    for (int e = threadIdx.x; e < 10 * PTS; e += blockDim.x) {
-      const int r = 6 + e / PTS, p = p0 + e % PTS;
-      if (p < P) vt[(size_t(g) * 16 + r) * vt_pitch + p] = __float2half_rn(r == 6 ? 1.f : 0.f);
-    }
-    if (p0 + PTS >= P) {
-      const int npad = vt_pitch - P;
-      for (int e = threadIdx.x; e < 16 * npad; e += blockDim.x)
-        vt[(size_t(g) * 16 + e / npad) * vt_pitch + P + e % npad] = __float2half_rn(0.f);
     }
   }
 }
@@ -192,11 +176,11 @@ int prep_rows_launch(const void* feat, int feat_bf16, int B, int d, int N, int o
   if (feat_bf16)
     prep_kernel<0, __nv_bfloat16><<<grid, 256, smem, stream>>>(
         static_cast<const __nv_bfloat16*>(feat), nullptr, d, N, operand_mode == GADM_OPERAND_BF16X3, 0, pad_mode,
-        static_cast<__nv_bfloat16*>(rows), rinv, pad_sim, nullptr, nullptr, nullptr, 0, nullptr, 0);
+        static_cast<__nv_bfloat16*>(rows), rinv, pad_sim, nullptr, nullptr, nullptr, 0);
   else
     prep_kernel<0, float><<<grid, 256, smem, stream>>>(
         static_cast<const float*>(feat), nullptr, d, N, operand_mode == GADM_OPERAND_BF16X3, 0, pad_mode,
-        static_cast<__nv_bfloat16*>(rows), rinv, pad_sim, nullptr, nullptr, nullptr, 0, nullptr, 0);
+        static_cast<__nv_bfloat16*>(rows), rinv, pad_sim, nullptr, nullptr, nullptr, 0);
   return check_launch();
 }
 
@@ -231,8 +215,7 @@ int prep_model_launch(const float* mesh, const float* model_xyz, int n_obj, int 
   float* a_planes = aux + plane * 4;
   prep_kernel<1, float><<<grid, 256, smem, stream>>>(mesh, model_xyz, d, M, operand_mode == GADM_OPERAND_BF16X3,
                                               operand_mode == GADM_OPERAND_BF16N, 0,
-                                              static_cast<__nv_bfloat16*>(cols), nullptr, nullptr, aux, a_xyz, a_planes, plane,
-                                              reinterpret_cast<__half*>(aux + plane * 7), aux_vt_pitch(M));
+                                              static_cast<__nv_bfloat16*>(cols), nullptr, nullptr, aux, a_xyz, a_planes, plane);
   return check_launch();
 }
 

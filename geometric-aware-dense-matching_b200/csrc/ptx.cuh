@@ -247,29 +247,6 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       : "memory");
 }
 
-// ---- warp-wide issue: EVERY lane of a converged warp executes these with identical operands and one elected lane
-// issues.  The operands then live in uniform registers; an issuer confined to `if (lane == 0)` instead pays a
-// R2UR.BROADCAST waterfall and ~60 cycles of dependent scalar code per MMA, which the tensor pipe does not hide
-// behind 64-cycle (N <= 128) MMAs.
-__device__ __forceinline__ void umma_f16_ts_warp(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
-                                                 uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
-      ::"r"(smem_u32(bar))
-      : "memory");
-}
-
 // explicit shared-memory loads (a generic pointer makes the compiler emit LD instead of LDS)
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   float4 v;

@@ -83,7 +83,7 @@ def _(mesh, model_xyz, operand_mode):
     n_obj, d, M = mesh.shape
     kp = d * (3 if operand_mode == 1 else 1)
     return (mesh.new_empty((n_obj, M, kp), dtype=torch.bfloat16),
-            mesh.new_empty((n_obj * (7 * M + 8 * ((M + 63) // 64 * 64)),)))     # gadm_aux_floats
+            mesh.new_empty((n_obj * M * 7,)))     # gadm_aux_floats
 
 
 @torch.library.custom_op("gadm::pack_match_outputs", mutates_args=("out",), device_types="cuda")

@@ -42,7 +42,7 @@ def test_error_codes_and_no_gpu_behaviour():
         assert len(lib.gadm_strerror(code)) > 3
     assert lib.gadm_operand_k(128, 0) == 128 and lib.gadm_operand_k(128, 1) == 384
     assert lib.gadm_operand_k(128, 9) == -2 and lib.gadm_operand_k(0, 0) == -1
-    assert lib.gadm_aux_floats(8, 8192) == 8 * 8192 * 15 and lib.gadm_aux_floats(1, 520) == 520 * 7 + 8 * 576
+    assert lib.gadm_aux_floats(8, 8192) == 8 * 8192 * 7 and lib.gadm_aux_floats(1, 520) == 520 * 7
     if not torch.cuda.is_available():
         # without a device gadm_init fails (CUDA error) and every compute entry point refuses: no CPU fallback
         assert lib.gadm_init(0) in (-5, -6)

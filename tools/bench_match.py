@@ -24,7 +24,6 @@ PEAK = 1658.8
 
 # (label, mode, bf16n operands, config switches)
 CASES = [("argmax", "argmax", False, {}), ("soft", "soft", False, {}),
-         ("soft_pair(fa=0)", "soft", False, {"match.fa": 0}),
          ("argmax_bf16n", "argmax_bf16n", True, {}), ("argmax_unit", "argmax_unit", True, {})]
 if os.environ.get("CASES"):
     CASES = [c for c in CASES if c[0] in os.environ["CASES"].split(",")]
