@@ -10,6 +10,10 @@ import torch
 LM_K = np.array([[572.4114, 0.0, 325.2611], [0.0, 573.57043, 242.04899], [0.0, 0.0, 1.0]])
 # LM-O object diameters in metres (reference: config/lmo_cfg.py:6-22, mm there)
 LMO_DIAMETERS = [0.10210, 0.24750, 0.16736, 0.17249, 0.20141, 0.15455, 0.12426, 0.26148]
+# config/ycbv_cfg.py:2-24 (mm -> m), objects 1..21
+YCBV_DIAMETERS = [0.172063, 0.269573, 0.198377, 0.120543, 0.196463, 0.089797, 0.142543, 0.114053, 0.129540, 0.197796,
+                  0.259534, 0.259566, 0.161922, 0.124990, 0.226170, 0.237299, 0.203973, 0.121365, 0.174746, 0.217094,
+                  0.102903]
 
 
 def bf16_round(t):

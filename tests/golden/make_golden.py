@@ -10,6 +10,9 @@
                      gather_neighbour, EXECUTED from the reference source text
   circle_golden.npz  the training-side matching loss: CircleLoss imported from models/loss.py, GeoMatch.matching_loss /
                      pointwise_feature_matching and pdist EXECUTED from the reference source text
+  pointops_golden.npz  lib/pointops/functions/pointops.py: KNNQueryNaive.forward (:396-426, pure torch, the reference's
+                     own oracle for its CUDA knnquery) and QueryAndGroup.forward (:548-585) EXECUTED from the reference
+                     source text (its `grouping` CUDA call replaced by the gather its docstring :151-155 specifies)
 Nothing from the reference is copied into the repo: only inputs and numeric outputs are stored."""
 import os
 import sys
@@ -218,6 +221,48 @@ def make_circle():
     print("circle golden: total", float(total), "per sample", per_sample)
 
 
+def make_pointops():
+    """lib/pointops ships no CUDA sources and nothing imports it, but KNNQueryNaive.forward (:396-426) is pure torch:
+    it is EXECUTED from the reference text.  QueryAndGroup.forward (:548-585) is executed too, with knnquery_heap bound
+    to that naive query and `grouping` to the gather its docstring (:151-155) specifies
+    (out[b, c, m, s] = features[b, c, idx[b, m, s]])."""
+    from typing import Tuple
+    ns = {"torch": torch, "Tuple": Tuple}
+    exec(ref_lines("lib/pointops/functions/pointops.py", 396, 426), ns)          # @staticmethod def forward(ctx, ...)
+    knn_naive = ns["forward"]
+
+    def grouping(features, idx):
+        b, c, n = features.shape
+        _, m, k = idx.shape
+        return torch.gather(features, 2, idx.long().view(b, 1, m * k).expand(b, c, m * k)).view(b, c, m, k)
+    ns2 = {"torch": torch, "grouping": grouping, "knnquery_heap": lambda k, xyz, new: knn_naive(None, k, xyz, new),
+           "ballquery": None}
+    exec(ref_lines("lib/pointops/functions/pointops.py", 548, 585), ns2)         # def forward(self, xyz, new_xyz, ...)
+
+    class _QG:
+        radius, nsample, use_xyz, return_idx = None, 16, True, True
+    g = torch.Generator().manual_seed(77)
+    b, n, m, c, k = 2, 300, 90, 5, 16
+    xyz = torch.rand((b, n, 3), generator=g)
+    new_xyz = torch.rand((b, m, 3), generator=g)
+    feats = torch.randn((b, c, n), generator=g)
+    out = {"xyz": xyz.numpy(), "new_xyz": new_xyz.numpy(), "features": feats.numpy(), "k": np.int64(k)}
+    out["knn_idx"] = knn_naive(None, k, xyz, new_xyz).numpy()
+    out["knn_self_idx"] = knn_naive(None, k, xyz, None).numpy()
+    nf, gxyz, idx = ns2["forward"](_QG(), xyz, new_xyz, feats)
+    out["qg_new_features"], out["qg_grouped_xyz"], out["qg_idx"] = nf.numpy(), gxyz.numpy(), idx.numpy()
+    _QG.use_xyz = False
+    out["qg_features_only"] = ns2["forward"](_QG(), xyz, new_xyz, feats)[0].numpy()
+    _QG.use_xyz = True
+    out["qg_xyz_only"] = ns2["forward"](_QG(), xyz, new_xyz, None)[0].numpy()
+    # the same distances in the order the naive query computes them (for the tie-free check of the fixture)
+    dist = (new_xyz[:, :, None, :] - xyz[:, None, :, :]).pow(2).sum(dim=3)
+    srt = torch.sort(dist, dim=2)[0]
+    out["knn_gap"] = (srt[:, :, 1:k + 1] - srt[:, :, :k]).min().numpy()          # > 0: no ties among the first k + 1
+    np.savez_compressed(os.path.join(HERE, "pointops_golden.npz"), **out)
+    print("pointops golden: min gap among the first k + 1 distances", float(out["knn_gap"]))
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "needs the reference tree"
     assert ko.have_reference()
@@ -225,7 +270,9 @@ if __name__ == "__main__":
         make_randla()
     elif len(sys.argv) > 1 and sys.argv[1] == "circle":
         make_circle()
+    elif len(sys.argv) > 1 and sys.argv[1] == "pointops":
+        make_pointops()
     else:
-        make_knn(); make_match(); make_dgcnn(); make_randla(); make_circle()
+        make_knn(); make_match(); make_dgcnn(); make_randla(); make_circle(); make_pointops()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -119,3 +119,42 @@ def test_config5_dgcnn_full_size(cuda):
     for b in (0, 63):
         ref = do.get_graph_feature(x[b:b + 1], k=k, idx=idx[b:b + 1].cpu())
         assert torch.equal(out[b:b + 1].cpu(), ref)
+
+
+def test_frame_stream_host_buffers_match_direct_calls(cuda):
+    """The end-to-end front end (pipeline.FrameStream: ONE packed pinned H2D with bf16 descriptors, ONE packed D2H of
+    {int32 idx, max_sim, weight, xyz} records + kNN indices, three batches in flight) returns, bit for bit, what the
+    direct calls return on the same inputs -- and bf16 host descriptors lose nothing (the matcher's operands are bf16)."""
+    from gadm_b200 import matching, ops, synth
+    from gadm_b200.knn import KnnPyramid
+    from gadm_b200.pipeline import FrameStream
+    B, N, M, d, in_size = 2, 4096, 1024, 128, 32
+    xyz = synth.model_bank_xyz(2, M).to(cuda)
+    bank = None
+    pyr = KnnPyramid(N, {s: (in_size // s) ** 2 for s in (2, 4, 8)}, B)
+    obj = torch.tensor([1, 0], dtype=torch.int32, device=cuda)
+    fs, batches, inputs = None, [], []
+    for i in range(4):                                         # more batches than slots: every slot is reused
+        rgbd, mesh, _ = synth.descriptors(B, N, M, d, n_obj=2, regime="planted", seed=40 + i)
+        if bank is None:
+            bank = matching.ModelBank(mesh.to(cuda), xyz)
+            fs = FrameStream(bank, pyr, B, d, N, obj_id=obj, gamma=16.0, mode="soft", depth=3)
+        cld, sr = synth.frame_batch(B, in_size, N, seed=40 + i)
+        inputs.append((rgbd, cld, sr))
+        batches.append(fs.host_batch().fill(rgbd, cld, sr))
+    assert fs.h2d_bytes == B * d * N * 2 + B * pyr.P * 12
+    tickets = [fs.submit(hb) for hb in batches[:3]]
+    got = [{k: v.clone() for k, v in fs.result(t).items()} for t in tickets]
+    got.append({k: v.clone() for k, v in fs.result(fs.submit(batches[3])).items()})
+    with pytest.raises(ValueError):
+        fs.result(0)                                           # its buffers were reused by ticket 3
+    for (rgbd, cld, sr), out in zip(inputs, got):
+        idx, sim, w, sx = matching.match(rgbd.to(cuda), bank, obj_id=obj, gamma=16.0, mode="soft")
+        assert torch.equal(out["idx"].long(), idx.cpu()) and torch.equal(out["max_sim"], sim.cpu())
+        assert torch.equal(out["weight"], w.cpu()) and torch.equal(out["soft_xyz"], sx.cpu())
+        knn = pyr.run_packed(pyr.pack(cld.to(cuda), {s: v.to(cuda) for s, v in sr.items()}))
+        assert torch.equal(out["knn"], knn.cpu())
+    # fp32 device descriptors and their bf16 copies prepare identical operands
+    rows32 = ops.prep_rows(inputs[0][0].to(cuda), 0, 1)
+    rows16 = ops.prep_rows(inputs[0][0].to(cuda).to(torch.bfloat16), 0, 1)
+    assert all(torch.equal(a, b) for a, b in zip(rows32, rows16))
