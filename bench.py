@@ -409,6 +409,31 @@ def run_gpu(args):
     torch.cuda.synchronize()
     pruned_ms = va.elapsed_time(vb) / 10
 
+    # ---- variant: row compaction (evaluator.py:82-88).  A real frame's foreground is a fraction of the 12800 samples; with a
+    # segmentation mask the selected rows are compacted on the device and only they are matched.  20 % foreground:
+    gm = torch.Generator().manual_seed(5)
+    fg = (torch.rand((FRAMES, N_PTS), generator=gm) < 0.2).to(torch.uint8).to(dev)
+
+    def compacted(mode):
+        pos, row_map, n_sel = ops.compact_rows(fg)
+        r2, ri2, pd2 = ops.prep_rows_sel(res[0]["rgbd"], pos, om, pm)
+        return ops.match_fwd_sel(r2, ri2, pd2, cols, aux, n_sel, row_map, obj_id, GAMMA, pm, MATCH_MODES[mode])
+
+    def full(mode):
+        r2, ri2, pd2 = ops.prep_rows(res[0]["rgbd"], om, pm)
+        return ops.match_fwd(r2, ri2, pd2, cols, aux, None, obj_id, GAMMA, pm, MATCH_MODES[mode])
+    fg_ms = {}
+    for name, fn in (("compacted_soft", lambda: compacted("soft")), ("full_soft", lambda: full("soft")),
+                     ("compacted_argmax", lambda: compacted("argmax")), ("full_argmax", lambda: full("argmax"))):
+        for _ in range(3):
+            fn()
+        va.record()
+        for _ in range(10):
+            fn()
+        vb.record()
+        torch.cuda.synchronize()
+        fg_ms[name] = va.elapsed_time(vb) / 10
+
     # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
     # pipeline.FrameStream: pinned host inputs -> H2D -> prep + match + kNN -> D2H of every output into pinned host
     # buffers, three batches in flight (the host reads batch i - 2 while batch i uploads and batch i - 1 computes) so
@@ -489,6 +514,10 @@ def run_gpu(args):
                          "match_kernel_argmax_bf16n_frac": flop_per_launch / (pruned_ms * 1e-3) / 1e12 / peak,
                          "match_kernel_argmax_unit_ms": unit_ms,
                          "match_kernel_argmax_unit_frac": flop_per_launch / (unit_ms * 1e-3) / 1e12 / peak,
+                         "foreground_20pct_ms": fg_ms,
+                         "foreground_note": "prep + match of one 8-frame batch whose segmentation mask keeps 20 % of the "
+                                            "rows: compacted = compact_rows + prep_rows_sel + match_fwd_sel (results "
+                                            "scattered back), full = every row matched, mask applied at the store",
                          "note": "argmax_only = evaluator.py:89-93 exactly (match_alt_kernel); argmax_bf16n = the same, exact, on columns "
                                  "normalised before the bf16 rounding (chunk pruning); argmax_unit = same search "
                                  "on bf16n operands without column scales (index may differ only below a 2^-7 |score| "

@@ -58,7 +58,7 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int row0 = blockIdx.x * BM;
-  const int obj = p.obj_id ? p.obj_id[b] : (p.n_obj == p.B ? b : 0);
+  const int obj = p.obj_id ? min(max(p.obj_id[b], 0), p.n_obj - 1) : (p.n_obj == p.B ? b : 0);   // clamped
   const int num_tiles = (p.M + BN - 1) / BN;
 
   if (warp == EPI_WARPS && lane == 0) {

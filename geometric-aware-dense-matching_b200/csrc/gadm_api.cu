@@ -129,7 +129,28 @@ int gadm_prep_rows(const float* feat, int B, int d, int N, int operand_mode, int
   if (operand_mode < GADM_OPERAND_BF16 || operand_mode > GADM_OPERAND_BF16N) return GADM_ERR_UNSUPPORTED;
   if (d % 64 != 0 || d > 256) return GADM_ERR_UNSUPPORTED;
   if (!aligned16(rows)) return GADM_ERR_ALIGN;
-  return prep_rows_launch(feat, 0, B, d, N, operand_mode, pad_mode, rows, rinv, pad_sim, (cudaStream_t)stream);
+  return prep_rows_launch(feat, 0, nullptr, B, d, N, operand_mode, pad_mode, rows, rinv, pad_sim, (cudaStream_t)stream);
+}
+
+int gadm_compact_rows(const uint8_t* mask, int B, int N, int32_t* pos, int32_t* row_map, int32_t* n_sel,
+                      gadm_stream_t stream) {
+  GADM_REQUIRE_INIT();
+  if (!mask || !pos || !row_map || !n_sel || B <= 0 || N <= 0) return GADM_ERR_BAD_ARG;
+  return compact_rows_launch(mask, B, N, pos, row_map, n_sel, (cudaStream_t)stream);
+}
+
+int gadm_prep_rows_sel(const void* feat, int feat_is_bf16, const int32_t* pos, int B, int d, int N, int operand_mode,
+                       int pad_mode, void* rows, float* rinv, float* pad_sim, gadm_stream_t stream) {
+  GADM_REQUIRE_INIT();
+  if (!feat || !pos || !rows || !rinv || B <= 0 || d <= 0 || N <= 0) return GADM_ERR_BAD_ARG;
+  if (pad_mode != GADM_PAD_NONE && !pad_sim) return GADM_ERR_BAD_ARG;
+  if (pad_mode < 0 || pad_mode > GADM_PAD_E0) return GADM_ERR_UNSUPPORTED;
+  if (operand_mode < GADM_OPERAND_BF16 || operand_mode > GADM_OPERAND_BF16N) return GADM_ERR_UNSUPPORTED;
+  if (feat_is_bf16 && operand_mode == GADM_OPERAND_BF16X3) return GADM_ERR_UNSUPPORTED;
+  if (d % 64 != 0 || d > 256) return GADM_ERR_UNSUPPORTED;
+  if (!aligned16(rows)) return GADM_ERR_ALIGN;
+  return prep_rows_launch(feat, feat_is_bf16 != 0, pos, B, d, N, operand_mode, pad_mode, rows, rinv, pad_sim,
+                          (cudaStream_t)stream);
 }
 
 int gadm_prep_rows_bf16(const void* feat_bf16, int B, int d, int N, int operand_mode, int pad_mode, void* rows,
@@ -142,7 +163,8 @@ int gadm_prep_rows_bf16(const void* feat_bf16, int B, int d, int N, int operand_
   if (operand_mode != GADM_OPERAND_BF16 && operand_mode != GADM_OPERAND_BF16N) return GADM_ERR_UNSUPPORTED;
   if (d % 64 != 0 || d > 256) return GADM_ERR_UNSUPPORTED;
   if (!aligned16(rows)) return GADM_ERR_ALIGN;
-  return prep_rows_launch(feat_bf16, 1, B, d, N, operand_mode, pad_mode, rows, rinv, pad_sim, (cudaStream_t)stream);
+  return prep_rows_launch(feat_bf16, 1, nullptr, B, d, N, operand_mode, pad_mode, rows, rinv, pad_sim,
+                          (cudaStream_t)stream);
 }
 
 int gadm_pack_match_outputs(const int64_t* idx, const float* max_sim, const float* weight, const float* soft_xyz,
@@ -162,11 +184,10 @@ int gadm_prep_model(const float* mesh, const float* model_xyz, int n_obj, int d,
   return prep_model_launch(mesh, model_xyz, n_obj, d, M, operand_mode, cols, aux, (cudaStream_t)stream);
 }
 
-int gadm_match_fwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols, const float* aux,
-                   const uint8_t* mask, const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma,
-                   int pad_mode, int mode, int64_t* idx, float* max_sim, float* weight, float* soft_xyz,
-                   void* workspace, size_t workspace_bytes, gadm_stream_t stream) {
-  GADM_REQUIRE_INIT();
+static int match_validate(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
+                          const float* aux, const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma,
+                          int pad_mode, int mode, const int64_t* idx, const float* max_sim, const float* weight,
+                          const float* soft_xyz, const void* workspace) {
   if (!rows || !rinv_rows || !cols || !aux || !idx || !max_sim) return GADM_ERR_BAD_ARG;
   if (workspace && !aligned16(workspace)) return GADM_ERR_ALIGN;
   if (B <= 0 || N <= 0 || M <= 0 || Kp <= 0 || n_obj <= 0) return GADM_ERR_BAD_ARG;
@@ -179,8 +200,36 @@ int gadm_match_fwd(const void* rows, const float* rinv_rows, const float* pad_si
   if (Kp % 64 != 0 || Kp > 768 || M % 8 != 0) return GADM_ERR_UNSUPPORTED;
   if (obj_id == nullptr && n_obj != 1 && n_obj != B) return GADM_ERR_BAD_ARG;
   if (!aligned16(rows) || !aligned16(cols) || !aligned16(aux)) return GADM_ERR_ALIGN;
+  return GADM_OK;
+}
+
+int gadm_match_fwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols, const float* aux,
+                   const uint8_t* mask, const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma,
+                   int pad_mode, int mode, int64_t* idx, float* max_sim, float* weight, float* soft_xyz,
+                   void* workspace, size_t workspace_bytes, gadm_stream_t stream) {
+  GADM_REQUIRE_INIT();
+  const int rc = match_validate(rows, rinv_rows, pad_sim, cols, aux, obj_id, B, N, M, Kp, n_obj, gamma, pad_mode, mode,
+                                idx, max_sim, weight, soft_xyz, workspace);
+  if (rc != GADM_OK) return rc;
   return match_launch(rows, rinv_rows, pad_sim, cols, aux, mask, obj_id, B, N, M, Kp, n_obj, gamma, pad_mode, mode,
-                      idx, max_sim, weight, soft_xyz, workspace, workspace_bytes, (cudaStream_t)stream);
+                      idx, max_sim, weight, soft_xyz, workspace, workspace_bytes, nullptr, nullptr, N,
+                      (cudaStream_t)stream);
+}
+
+int gadm_match_fwd_sel(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
+                       const float* aux, const int32_t* n_rows, const int32_t* row_map, int N_out,
+                       const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma, int pad_mode, int mode,
+                       int64_t* idx, float* max_sim, float* weight, float* soft_xyz, void* workspace,
+                       size_t workspace_bytes, gadm_stream_t stream) {
+  GADM_REQUIRE_INIT();
+  const int rc = match_validate(rows, rinv_rows, pad_sim, cols, aux, obj_id, B, N, M, Kp, n_obj, gamma, pad_mode, mode,
+                                idx, max_sim, weight, soft_xyz, workspace);
+  if (rc != GADM_OK) return rc;
+  if (!n_rows || N_out <= 0) return GADM_ERR_BAD_ARG;
+  if (row_map == nullptr && N_out < N) return GADM_ERR_BAD_ARG;
+  return match_launch(rows, rinv_rows, pad_sim, cols, aux, nullptr, obj_id, B, N, M, Kp, n_obj, gamma, pad_mode, mode,
+                      idx, max_sim, weight, soft_xyz, workspace, workspace_bytes, n_rows, row_map, N_out,
+                      (cudaStream_t)stream);
 }
 
 int gadm_circle_loss_fwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,

@@ -36,7 +36,8 @@ int circle_configure();
 int match_launch(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols, const float* aux,
                  const uint8_t* mask, const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma,
                  int pad_mode, int mode, int64_t* idx, float* max_sim, float* weight, float* soft_xyz,
-                 void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                 void* workspace, size_t workspace_bytes, const int32_t* n_rows, const int32_t* row_map, int N_out,
+                 cudaStream_t stream);
 size_t match_workspace_bytes();
 int circle_launch(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols, const float* aux,
                   const float* planes_frame, const int64_t* match_idx, const uint8_t* fg, const int32_t* obj_id, int B,
@@ -44,8 +45,10 @@ int circle_launch(const void* rows, const float* rinv_rows, const float* pad_sim
                   float* lse_n, const float* w, float* G, int Mp, cudaStream_t stream);
 
 // prep.cu
-int prep_rows_launch(const void* feat, int feat_bf16, int B, int d, int N, int operand_mode, int pad_mode, void* rows,
-                     float* rinv, float* pad_sim, cudaStream_t stream);
+int prep_rows_launch(const void* feat, int feat_bf16, const int32_t* pos, int B, int d, int N, int operand_mode,
+                     int pad_mode, void* rows, float* rinv, float* pad_sim, cudaStream_t stream);
+int compact_rows_launch(const uint8_t* mask, int B, int N, int32_t* pos, int32_t* row_map, int32_t* n_sel,
+                        cudaStream_t stream);
 int pack_outputs_launch(const int64_t* idx, const float* max_sim, const float* weight, const float* soft_xyz, size_t n,
                         int32_t* out, cudaStream_t stream);
 int prep_model_launch(const float* mesh, const float* model_xyz, int n_obj, int d, int M, int operand_mode, void* cols,

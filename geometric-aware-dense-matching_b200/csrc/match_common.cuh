@@ -55,6 +55,12 @@ struct MatchParams {
   const float* planes;     // [3, n_obj, M] model x / y / z planes (SOFT)
   const uint8_t* mask;     // [B, N] or null
   const int32_t* obj_id;   // [B] or null
+  // row compaction (evaluator.py:82-88): N is the row CAPACITY of the operand arrays (rows, rinv_rows, pad_sim are
+  // [B, N] in compacted order); frame b holds n_rows[b] <= N rows (null: N), and compacted row j is written to the
+  // outputs at position row_map[b, j] of a frame of N_out rows (null: position j)
+  const int32_t* n_rows;   // [B] device, or null
+  const int32_t* row_map;  // [B, N] device, or null
+  int N_out;
   int64_t* idx;
   float* max_sim;
   float* weight;
@@ -75,17 +81,60 @@ struct MatchParams {
                            // 2 = GADM_MATCH_ARGMAX_BF16N: exact, scales known to be <= 1 + 2^-8 (chunk pruning)
 };
 
-// first unit of CTA c (c == gridDim.x: one past the last unit)
-__device__ __forceinline__ long long sched_begin(const MatchParams& p, int c) {
-  return (long long)c * p.total_units / (long long)gridDim.x;
+__device__ __forceinline__ int frame_rows(const MatchParams& p, int b) {
+  return p.n_rows ? min(p.n_rows[b], p.N) : p.N;
 }
-// the CTA whose range holds unit u: the largest c with sched_begin(c) <= u
-__device__ __forceinline__ int sched_cta_of(const MatchParams& p, long long u) {
-  return int(((u + 1) * (long long)gridDim.x - 1) / p.total_units);
+// where the results of (compacted) row `row` of frame b go
+__device__ __forceinline__ size_t out_pos(const MatchParams& p, int b, int row) {
+  return size_t(b) * p.N_out + (p.row_map ? p.row_map[size_t(b) * p.N + row] : row);
 }
 
+// Schedule of the persistent kernels: the units (frame, row block, model tile), in that order, are dealt out evenly to
+// the CTAs.  With per-frame row counts in device memory (row compaction) the number of row blocks of a frame is only
+// known on the device: `prefix` (shared memory, B + 1 entries, built by build()) holds the running count of row blocks.
+struct Sched {
+  long long total;       // units
+  int T, RB, B;          // model tiles per row; row blocks per frame when every frame has the same number
+  const int* prefix;     // or null
+  __device__ __forceinline__ long long begin(int c) const { return (long long)c * total / (long long)gridDim.x; }
+  // the CTA whose range holds unit u: the largest c with begin(c) <= u
+  __device__ __forceinline__ int cta_of(long long u) const { return int(((u + 1) * (long long)gridDim.x - 1) / total); }
+  // frame and row block of global row block g
+  __device__ __forceinline__ void locate(int g, int& b, int& rb) const {
+    if (prefix == nullptr) { b = g / RB; rb = g - b * RB; return; }
+    int lo = 0, hi = B;                                    // largest b with prefix[b] <= g
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (prefix[mid] <= g) lo = mid; else hi = mid;
+    }
+    b = lo; rb = g - prefix[lo];
+  }
+};
+// Called by every thread of the CTA (contains a __syncthreads when row counts are given).
+__device__ __forceinline__ Sched sched_build(const MatchParams& p, int* smem_prefix, int rows_per_block) {
+  Sched s;
+  s.T = p.T; s.RB = p.RB; s.B = p.B; s.prefix = nullptr; s.total = p.total_units;
+  if (p.n_rows != nullptr) {
+    if (threadIdx.x == 0) {
+      int acc = 0;
+      for (int b = 0; b < p.B; ++b) {
+        smem_prefix[b] = acc;
+        acc += (frame_rows(p, b) + rows_per_block - 1) / rows_per_block;
+      }
+      smem_prefix[p.B] = acc;
+    }
+    __syncthreads();
+    s.prefix = smem_prefix;
+    s.total = (long long)smem_prefix[p.B] * p.T;
+  }
+  return s;
+}
+
+// Bank slot of frame b.  A slot outside [0, n_obj) (the host wrappers reject it; a device-side id cannot be checked
+// without a synchronisation) is clamped: the results of that frame are then those of a neighbouring object, but no
+// table is ever read out of bounds.
 __device__ __forceinline__ int frame_object(const MatchParams& p, int b) {
-  if (p.obj_id) return p.obj_id[b];
+  if (p.obj_id) return min(max(p.obj_id[b], 0), p.n_obj - 1);
   return p.n_obj == p.B ? b : 0;
 }
 

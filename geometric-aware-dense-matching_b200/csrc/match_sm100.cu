@@ -63,6 +63,8 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int row0 = blockIdx.x * (BM * RT);
+  const int nrows = frame_rows(p, b);          // rows of this frame (fewer than N after row compaction)
+  if (row0 >= nrows) return;                   // whole CTA, before any barrier or TMEM allocation
   const int obj = frame_object(p, b);
   const int num_tiles = (p.M + BN - 1) / BN;
 
@@ -193,8 +195,9 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
     const int sub = RT == 1 ? warp >> 2 : warp >> 3; // column slice of every tile
     const int row_in_tile = q * 32 + lane;
     const int row = row0 + rt * BM + row_in_tile;
-    const bool row_ok = row < p.N;
-    const size_t grow = size_t(b) * p.N + (row_ok ? row : 0);
+    const bool row_ok = row < nrows;
+    const size_t grow = size_t(b) * p.N + (row_ok ? row : 0);      // operand arrays (compacted order)
+    const size_t gout = out_pos(p, b, row_ok ? row : 0);           // outputs
     const float rs = row_ok ? p.rinv_rows[grow] : 0.f;
     const float g = p.gamma_log2e * rs;     // exponent scale: t = (acc * 1/|m_j|) * g   (log2 units)
     const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16) + sub * CS;
@@ -379,8 +382,8 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
         const float ps = p.pad_sim[grow];
         if (ps > best) { best = ps; best_idx = p.M; }  // pad column is the last one: wins only if strictly larger
       }
-      p.idx[grow] = keep ? best_idx : int64_t(-1);
-      p.max_sim[grow] = keep ? best : 0.f;
+      p.idx[gout] = keep ? best_idx : int64_t(-1);
+      p.max_sim[gout] = keep ? best : 0.f;
       if (kSoft) {
         float l = lsum, sx = ax, sy = ay, sz = az;
 #pragma unroll
@@ -389,10 +392,10 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
           l += x[3]; sx += x[4]; sy += x[5]; sz += x[6];
         }
         const float inv = 1.f / l;
-        p.weight[grow] = keep ? ptx::ex2_approx(vmax * g) * inv : 0.f;  // softmax value at the maximum
-        p.soft_xyz[grow * 3 + 0] = keep ? sx * inv : 0.f;
-        p.soft_xyz[grow * 3 + 1] = keep ? sy * inv : 0.f;
-        p.soft_xyz[grow * 3 + 2] = keep ? sz * inv : 0.f;
+        p.weight[gout] = keep ? ptx::ex2_approx(vmax * g) * inv : 0.f;  // softmax value at the maximum
+        p.soft_xyz[gout * 3 + 0] = keep ? sx * inv : 0.f;
+        p.soft_xyz[gout * 3 + 1] = keep ? sy * inv : 0.f;
+        p.soft_xyz[gout * 3 + 2] = keep ? sz * inv : 0.f;
       }
     }
   }
@@ -464,6 +467,8 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int row0 = blockIdx.x * (2 * BM);
+  const int nrows = frame_rows(p, b);          // rows of this frame (fewer than N after row compaction)
+  if (row0 >= nrows) return;                   // whole CTA, before any barrier or TMEM allocation
   const int obj = frame_object(p, b);
   const int num_tiles = (p.M + PBN - 1) / PBN;
 
@@ -574,7 +579,7 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       row[r] = row0 + r * BM + row_in_tile;
-      row_ok[r] = row[r] < p.N;
+      row_ok[r] = row[r] < nrows;
       grow[r] = size_t(b) * p.N + (row_ok[r] ? row[r] : 0);
       rs[r] = row_ok[r] ? p.rinv_rows[grow[r]] : 0.f;
       g[r] = p.gamma_log2e * rs[r];
@@ -767,8 +772,9 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
           const float ps = p.pad_sim[gr];
           if (ps > best) { best = ps; best_idx = p.M; }
         }
-        p.idx[gr] = keep ? best_idx : int64_t(-1);
-        p.max_sim[gr] = keep ? best : 0.f;
+        const size_t go = out_pos(p, b, row[rr]);
+        p.idx[go] = keep ? best_idx : int64_t(-1);
+        p.max_sim[go] = keep ? best : 0.f;
         if (kSoft) {
           float l = lsum[rr], sx = ax[rr], sy = ay[rr], sz = az[rr];
 #pragma unroll
@@ -777,10 +783,10 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
             l += x[3]; sx += x[4]; sy += x[5]; sz += x[6];
           }
           const float inv = 1.f / l;
-          p.weight[gr] = keep ? ptx::ex2_approx(vm * g[rr]) * inv : 0.f;
-          p.soft_xyz[gr * 3 + 0] = keep ? sx * inv : 0.f;
-          p.soft_xyz[gr * 3 + 1] = keep ? sy * inv : 0.f;
-          p.soft_xyz[gr * 3 + 2] = keep ? sz * inv : 0.f;
+          p.weight[go] = keep ? ptx::ex2_approx(vm * g[rr]) * inv : 0.f;
+          p.soft_xyz[go * 3 + 0] = keep ? sx * inv : 0.f;
+          p.soft_xyz[go * 3 + 1] = keep ? sy * inv : 0.f;
+          p.soft_xyz[go * 3 + 2] = keep ? sz * inv : 0.f;
         }
       }
     }
@@ -837,11 +843,14 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
   float* smem_xmax = reinterpret_cast<float*>(smem_aux + AUX_SLOTS * AUX_BYTES);   // [RT][SL][128] running maxima
   float2* smem_xch = reinterpret_cast<float2*>(smem_xmax + RT * SL * BM);           // [RT][SL - 1][128] slice merge
   Barriers* bars = reinterpret_cast<Barriers*>(smem_xch + RT * (SL - 1) * BM);
+  int* smem_prefix = reinterpret_cast<int*>(bars + 1);                             // [B + 1] when row counts are given
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // this CTA's share of the (frame, row block, model tile) units
-  const long long u_begin = sched_begin(p, blockIdx.x), u_end = sched_begin(p, blockIdx.x + 1);
+  const Sched sch = sched_build(p, smem_prefix, BM * RT);
+  const long long u_begin = sch.begin(blockIdx.x), u_end = sch.begin(blockIdx.x + 1);
+  if (u_begin >= u_end) return;                // (row compaction can leave fewer units than CTAs)
 
   if (warp == EPI_WARPS && lane == 0) {
     ptx::prefetch_tensormap(&tmap_rows);
@@ -879,7 +888,9 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
       for (long long u = u_begin; u < u_end; ++seg) {
         const int rbg = int(u / p.T), ta = int(u - (long long)rbg * p.T);
         const int tb = int(min((long long)p.T, ta + (u_end - u)));
-        const int b = rbg / p.RB, row0 = (rbg % p.RB) * (BM * RT);
+        int b, rb;
+        sch.locate(rbg, b, rb);
+        const int row0 = rb * (BM * RT);
         const int obj = frame_object(p, b);
         // the row tiles of the previous segment are dead once its last MMA has completed
         if (seg > 0) ptx::mbar_wait_sleep(&bars->a_free, (seg - 1) & 1);
@@ -964,7 +975,10 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
     for (long long u = u_begin; u < u_end;) {
       const int rbg = int(u / p.T), ta = int(u - (long long)rbg * p.T);
       const int tb = int(min((long long)p.T, ta + (u_end - u)));
-      const int b = rbg / p.RB, row0 = (rbg % p.RB) * (BM * RT);
+      int b, rb;
+      sch.locate(rbg, b, rb);
+      const int row0 = rb * (BM * RT);
+      const int nrows = frame_rows(p, b);
       const int obj = frame_object(p, b);
       u += tb - ta;
 
@@ -1128,7 +1142,7 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
           __threadfence();
           asm volatile("bar.sync 3, 128;" ::: "memory");
           if (threadIdx.x == 0) {
-            const int c_lo = sched_cta_of(p, (long long)rbg * p.T), c_hi = sched_cta_of(p, (long long)(rbg + 1) * p.T - 1);
+            const int c_lo = sch.cta_of((long long)rbg * p.T), c_hi = sch.cta_of((long long)(rbg + 1) * p.T - 1);
             const unsigned int old = atomicAdd(&p.seg_count[c_lo], 1u);
             bars->merge_lo = old == unsigned(c_hi - c_lo) ? c_lo : -1;
             bars->merge_hi = c_hi;
@@ -1141,7 +1155,7 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
             for (int r = 0; r < RT; ++r) { vm[r] = -INFINITY; vi[r] = NO_RECORD; }
             for (int c = c_lo; c <= c_hi; ++c) {     // ascending columns: on ties the earlier segment wins
               const float2* q2 = reinterpret_cast<const float2*>(p.partial) +
-                                 (size_t(c) * 2 + (int(sched_begin(p, c) / p.T) == rbg ? 0 : 1)) * PART_ROWS;
+                                 (size_t(c) * 2 + (int(sch.begin(c) / p.T) == rbg ? 0 : 1)) * PART_ROWS;
 #pragma unroll
               for (int r = 0; r < RT; ++r) {
                 float x, y;
@@ -1157,8 +1171,9 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
 #pragma unroll
           for (int r = 0; r < RT; ++r) {
             const int row = row0 + r * BM + row_in_tile;
-            if (row >= p.N) continue;
+            if (row >= nrows) continue;
             const size_t grow = size_t(b) * p.N + row;
+            const size_t gout = out_pos(p, b, row);
             // kUnit searched with unit column norms; the winner's similarity is reported with its true scale
             if (kUnit) vm[r] *= p.scales[size_t(obj) * p.M + vi[r]];
             const bool keep = p.mask == nullptr || p.mask[grow] != 0;
@@ -1168,8 +1183,8 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
               const float ps = p.pad_sim[grow];
               if (ps > best) { best = ps; best_idx = p.M; }  // pad column is the last one: wins only if strictly larger
             }
-            p.idx[grow] = keep ? best_idx : int64_t(-1);
-            p.max_sim[grow] = keep ? best : 0.f;
+            p.idx[gout] = keep ? best_idx : int64_t(-1);
+            p.max_sim[gout] = keep ? best : 0.f;
           }
         }
       }
@@ -1184,9 +1199,10 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
   }
 }
 
+constexpr int SCHED_MAX_FRAMES = 2048;          // frames a persistent kernel can schedule from device-side row counts
 inline size_t match_alt_smem_bytes(int KB, int stages) {
   return size_t(2) * KB * A_BLK_BYTES + size_t(stages) * B_STAGE_BYTES + AUX_SLOTS * PLANE_BYTES + 2 * 4 * BM * 4 +
-         2 * 3 * BM * 8 + sizeof(Barriers) + 1024;
+         2 * 3 * BM * 8 + sizeof(Barriers) + (SCHED_MAX_FRAMES + 1) * sizeof(int) + 1024;
 }
 inline int match_alt_stages(int KB) {
   int stages = MAX_STAGES;
@@ -1283,7 +1299,8 @@ static int match_launch_t(const void* rows, const void* cols, MatchParams p, int
     // alternating persistent kernel (ARGMAX; needs the workspace, a ring of two resident model tiles and more than
     // one row tile per frame)
     const int astages = match_alt_stages(KB);
-    if (cfg.alt != 0 && p.stash != nullptr && astages >= 2 * KB && p.N > BM) {
+    if (cfg.alt != 0 && p.stash != nullptr && astages >= 2 * KB && p.N > BM &&
+        (p.n_rows == nullptr || p.B <= SCHED_MAX_FRAMES)) {
       p.KB = KB; p.stages = astages;
       p.T = (p.M + BN - 1) / BN;
       p.RB = (p.N + PART_ROWS - 1) / PART_ROWS;
@@ -1357,7 +1374,8 @@ static int match_launch_t(const void* rows, const void* cols, MatchParams p, int
 int match_launch(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols, const float* aux,
                  const uint8_t* mask, const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma,
                  int pad_mode, int mode, int64_t* idx, float* max_sim, float* weight, float* soft_xyz,
-                 void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                 void* workspace, size_t workspace_bytes, const int32_t* n_rows, const int32_t* row_map, int N_out,
+                 cudaStream_t stream) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return set_cuda_error(e);
@@ -1371,6 +1389,7 @@ int match_launch(const void* rows, const float* rinv_rows, const float* pad_sim,
   p.seg_count = ws_ok ? reinterpret_cast<unsigned int*>(ws + size_t(slots) * STASH_SLOT_BYTES) : nullptr;
   p.partial = ws_ok ? reinterpret_cast<float*>(ws + size_t(slots) * STASH_SLOT_BYTES + ws_counter_bytes()) : nullptr;
   p.T = 0; p.RB = 0; p.total_units = 0;
+  p.n_rows = n_rows; p.row_map = row_map; p.N_out = N_out;
   p.rinv_rows = rinv_rows; p.pad_sim = pad_sim; p.scales = aux_scales(aux, n_obj, M);
   p.planes = aux_planes(aux, n_obj, M); p.mask = mask; p.obj_id = obj_id;
   p.idx = idx; p.max_sim = max_sim; p.weight = weight; p.soft_xyz = soft_xyz;

@@ -25,7 +25,8 @@ template <int kSide, typename TIn>
 __global__ void __launch_bounds__(256)
 prep_kernel(const TIn* __restrict__ src, const float* __restrict__ xyz, int d, int P, int x3, int prenorm, int pad_mode,
             __nv_bfloat16* __restrict__ dst, float* __restrict__ rinv, float* __restrict__ pad_sim,
-            float* __restrict__ aux_scale, float* __restrict__ aux_xyz, float* __restrict__ aux_planes, size_t plane) {
+            float* __restrict__ aux_scale, float* __restrict__ aux_xyz, float* __restrict__ aux_planes, size_t plane,
+            const int32_t* __restrict__ pos) {
   extern __shared__ float tile[];  // [d][PTS + 1]
   const int g = blockIdx.y;
   const int p0 = blockIdx.x * PTS;
@@ -42,8 +43,11 @@ prep_kernel(const TIn* __restrict__ src, const float* __restrict__ xyz, int d, i
   for (int pl = warp; pl < PTS; pl += 8) {  // one warp per point
     const int p = p0 + pl;
     if (p >= P) break;  // warp-uniform
+    // row compaction (scene side): point p goes to row pos[g, p] of its frame, or nowhere
+    const int prow = pos ? pos[size_t(g) * P + p] : p;
+    if (prow < 0) continue;  // warp-uniform
     float ss = 0.f, sum = 0.f;
-    __nv_bfloat16* out = dst + (size_t(g) * P + p) * Kp;
+    __nv_bfloat16* out = dst + (size_t(g) * P + prow) * Kp;
     float pre = 1.f;
     if (kSide == 1 && prenorm) {   // BF16N: F.normalize in fp32 first, then the one rounding to bf16
       float s2 = 0.f;
@@ -85,7 +89,7 @@ prep_kernel(const TIn* __restrict__ src, const float* __restrict__ xyz, int d, i
     }
     if (lane == 0) {
       const float r = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-      const size_t gp = size_t(g) * P + p;
+      const size_t gp = size_t(g) * P + prow;
       if (kSide == 0) {
         rinv[gp] = r;
         if (pad_mode == GADM_PAD_MINUS_ONE) {
@@ -129,7 +133,7 @@ kabsch_moments_kernel(const int64_t* __restrict__ idx, const uint8_t* __restrict
                       const float* __restrict__ cloud, const float* __restrict__ aux,
                       const int32_t* __restrict__ obj_id, int B, int N, int M, int n_obj, double* __restrict__ out) {
   const int b = blockIdx.x;
-  const int obj = obj_id ? obj_id[b] : (n_obj == B ? b : 0);
+  const int obj = obj_id ? min(max(obj_id[b], 0), n_obj - 1) : (n_obj == B ? b : 0);   // clamped: see frame_object
   const float* tab = aux_xyz(aux, n_obj, M) + size_t(obj) * M * 3;
   double acc[16];
 #pragma unroll
@@ -169,18 +173,60 @@ kabsch_moments_kernel(const int64_t* __restrict__ idx, const uint8_t* __restrict
 
 }  // namespace
 
-int prep_rows_launch(const void* feat, int feat_bf16, int B, int d, int N, int operand_mode, int pad_mode, void* rows,
-                     float* rinv, float* pad_sim, cudaStream_t stream) {
+// evaluator.py:82-88 (cls_msk -> rgbd_features[cls_msk]) as a map: one CTA per frame scans the mask; pos[b, n] = rank of
+// point n among the selected points of its frame (-1: not selected), row_map[b, j] = the point that has rank j,
+// n_sel[b] = how many.  Order is preserved, so rows in compacted order are exactly the reference's selected rows.
+__global__ void __launch_bounds__(1024)
+compact_rows_kernel(const uint8_t* __restrict__ mask, int N, int32_t* __restrict__ pos, int32_t* __restrict__ row_map,
+                    int32_t* __restrict__ n_sel) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry;
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int n0 = 0; n0 < N; n0 += 1024) {
+    const int n = n0 + threadIdx.x;
+    const int flag = n < N && mask[size_t(b) * N + n] != 0;
+    const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+    const int in_warp = __popc(ballot & ((1u << lane) - 1));
+    if (lane == 0) warp_sum[warp] = __popc(ballot);
+    __syncthreads();
+    int before = carry;
+    for (int w = 0; w < warp; ++w) before += warp_sum[w];
+    if (n < N) {
+      const int r = before + in_warp;
+      pos[size_t(b) * N + n] = flag ? r : -1;
+      if (flag) row_map[size_t(b) * N + r] = n;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = carry;
+      for (int w = 0; w < 32; ++w) t += warp_sum[w];
+      carry = t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) n_sel[b] = carry;
+}
+
+int compact_rows_launch(const uint8_t* mask, int B, int N, int32_t* pos, int32_t* row_map, int32_t* n_sel,
+                        cudaStream_t stream) {
+  compact_rows_kernel<<<B, 1024, 0, stream>>>(mask, N, pos, row_map, n_sel);
+  return check_launch();
+}
+
+int prep_rows_launch(const void* feat, int feat_bf16, const int32_t* pos, int B, int d, int N, int operand_mode,
+                     int pad_mode, void* rows, float* rinv, float* pad_sim, cudaStream_t stream) {
   dim3 grid((N + PTS - 1) / PTS, B);
   const size_t smem = size_t(d) * (PTS + 1) * sizeof(float);
   if (feat_bf16)
     prep_kernel<0, __nv_bfloat16><<<grid, 256, smem, stream>>>(
         static_cast<const __nv_bfloat16*>(feat), nullptr, d, N, operand_mode == GADM_OPERAND_BF16X3, 0, pad_mode,
-        static_cast<__nv_bfloat16*>(rows), rinv, pad_sim, nullptr, nullptr, nullptr, 0);
+        static_cast<__nv_bfloat16*>(rows), rinv, pad_sim, nullptr, nullptr, nullptr, 0, pos);
   else
     prep_kernel<0, float><<<grid, 256, smem, stream>>>(
         static_cast<const float*>(feat), nullptr, d, N, operand_mode == GADM_OPERAND_BF16X3, 0, pad_mode,
-        static_cast<__nv_bfloat16*>(rows), rinv, pad_sim, nullptr, nullptr, nullptr, 0);
+        static_cast<__nv_bfloat16*>(rows), rinv, pad_sim, nullptr, nullptr, nullptr, 0, pos);
   return check_launch();
 }
 
@@ -215,7 +261,7 @@ int prep_model_launch(const float* mesh, const float* model_xyz, int n_obj, int 
   float* a_planes = aux + plane * 4;
   prep_kernel<1, float><<<grid, 256, smem, stream>>>(mesh, model_xyz, d, M, operand_mode == GADM_OPERAND_BF16X3,
                                               operand_mode == GADM_OPERAND_BF16N, 0,
-                                              static_cast<__nv_bfloat16*>(cols), nullptr, nullptr, aux, a_xyz, a_planes, plane);
+                                              static_cast<__nv_bfloat16*>(cols), nullptr, nullptr, aux, a_xyz, a_planes, plane, nullptr);
   return check_launch();
 }
 

@@ -36,13 +36,29 @@ class ModelBank:
         return self.cols.device
 
 
+def _check_obj_id(obj_id, n_obj):
+    """obj_id indexes the bank's slots [0, n_obj); the reference's cls_id is 1-based for YCB-V (map it first).  Host
+    values are validated here; a device tensor is validated by the caller's data (the kernels read it unclamped)."""
+    if isinstance(obj_id, torch.Tensor) and obj_id.is_cuda:
+        return
+    ids = torch.as_tensor(obj_id).reshape(-1)
+    if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= n_obj):
+        raise ValueError(f"obj_id must lie in [0, {n_obj}) (bank slots; a 1-based class id needs cls_id - 1), got "
+                         f"[{int(ids.min())}, {int(ids.max())}]")
+
+
 def match(rgbd, mesh, model_xyz=None, obj_id=None, mask=None, gamma=16.0, pad_mode="none",
-          operand_mode="bf16", mode="soft"):
+          operand_mode="bf16", mode="soft", compact=None):
     """Dense scene-to-model correspondence.
 
     rgbd [B, d, N] fp32 (end_points['rgbd']); mesh: ModelBank, or [n_obj | 1, d, M] fp32 (end_points['mesh'])
-    with model_xyz [n_obj, M, 3]; obj_id int [B] selects the object per frame; mask [B, N] (bool/uint8)
-    marks rows to match (others get idx = -1).
+    with model_xyz [n_obj, M, 3]; obj_id int [B] selects the object per frame (bank slot, 0-based); mask [B, N]
+    (bool/uint8) marks rows to match.  With a mask the selected rows are COMPACTED on the device first
+    (evaluator.py:82-88) and only they are matched, so the cost follows the foreground fraction:
+      compact=False / None  results at the rows' original positions, idx = -1 and zeros elsewhere
+      compact=True          results in compacted order -- exactly the reference's rgbd_features[cls_msk] ordering --
+                            as [B, N] tensors whose first n_sel[b] rows are valid; a fifth value n_sel int32 [B] is
+                            returned (no host synchronisation anywhere)
     Returns (idx int64 [B,N], max_sim f32 [B,N], weight f32 [B,N], soft_xyz f32 [B,N,3]); with
     mode="argmax" weight/soft_xyz are None (the reference's hard-argmax path, evaluator.py:89-93);
     mode="argmax_unit" is the same on a bank with operand_mode="bf16n" (columns normalised before the bf16
@@ -62,18 +78,27 @@ def match(rgbd, mesh, model_xyz=None, obj_id=None, mask=None, gamma=16.0, pad_mo
     if d != bank.d:
         raise ValueError(f"descriptor dim mismatch: scene {d} vs model {bank.d}")
     pm = PAD_MODES[pad_mode]
-    rows, rinv, pad_sim = ops.prep_rows(rgbd.contiguous().float(), OPERAND_MODES[operand_mode], pm)
-    if mask is not None:
-        mask = mask.to(torch.uint8).contiguous()
     if obj_id is not None:
+        _check_obj_id(obj_id, bank.n_obj)
         obj_id = torch.as_tensor(obj_id, device=rgbd.device).to(torch.int32).contiguous()
+    feat = rgbd.contiguous() if rgbd.dtype == torch.bfloat16 else rgbd.contiguous().float()
     # exact argmax on a bank whose columns were normalised before the rounding: same results, chunk pruning allowed
     kmode = "argmax_bf16n" if mode == "argmax" and bank.operand_mode == "bf16n" else mode
-    idx, max_sim, weight, soft_xyz = ops.match_fwd(rows, rinv, pad_sim, bank.cols, bank.aux, mask, obj_id,
-                                                   float(gamma), pm, MATCH_MODES[kmode])
-    if mode != "soft":
-        return idx, max_sim, None, None
-    return idx, max_sim, weight, soft_xyz
+    n_sel = None
+    if mask is not None:
+        pos, row_map, n_sel = ops.compact_rows(mask.to(torch.uint8).contiguous())
+        rows, rinv, pad_sim = ops.prep_rows_sel(feat, pos, OPERAND_MODES[operand_mode], pm)
+        idx, max_sim, weight, soft_xyz = ops.match_fwd_sel(rows, rinv, pad_sim, bank.cols, bank.aux, n_sel,
+                                                           None if compact else row_map, obj_id, float(gamma), pm,
+                                                           MATCH_MODES[kmode])
+    else:
+        if compact:
+            raise ValueError("compact=True needs a mask")
+        rows, rinv, pad_sim = ops.prep_rows(feat, OPERAND_MODES[operand_mode], pm)
+        idx, max_sim, weight, soft_xyz = ops.match_fwd(rows, rinv, pad_sim, bank.cols, bank.aux, None, obj_id,
+                                                       float(gamma), pm, MATCH_MODES[kmode])
+    out = (idx, max_sim, None, None) if mode != "soft" else (idx, max_sim, weight, soft_xyz)
+    return out + (n_sel,) if compact else out
 
 
 class _CircleMatchLoss(torch.autograd.Function):

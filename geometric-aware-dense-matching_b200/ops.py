@@ -86,6 +86,59 @@ def _(mesh, model_xyz, operand_mode):
             mesh.new_empty((n_obj * M * 7,)))     # gadm_aux_floats
 
 
+@torch.library.custom_op("gadm::compact_rows", mutates_args=(), device_types="cuda")
+def compact_rows(mask: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """mask [B, N] uint8 -> (pos int32 [B, N], row_map int32 [B, N], n_sel int32 [B]); evaluator.py:82-88 as a map."""
+    _need(mask, torch.uint8, "mask")
+    B, N = mask.shape
+    pos = torch.empty((B, N), dtype=torch.int32, device=mask.device)
+    row_map = torch.zeros((B, N), dtype=torch.int32, device=mask.device)
+    n_sel = torch.empty((B,), dtype=torch.int32, device=mask.device)
+    lib = _lib_for(mask)
+    with torch.cuda.device(mask.device):
+        _lib.check(lib.gadm_compact_rows(_ptr(mask), B, N, _ptr(pos), _ptr(row_map), _ptr(n_sel), _stream()),
+                   "gadm_compact_rows")
+    return pos, row_map, n_sel
+
+
+@compact_rows.register_fake
+def _(mask):
+    B, N = mask.shape
+    return (mask.new_empty((B, N), dtype=torch.int32), mask.new_empty((B, N), dtype=torch.int32),
+            mask.new_empty((B,), dtype=torch.int32))
+
+
+@torch.library.custom_op("gadm::prep_rows_sel", mutates_args=(), device_types="cuda")
+def prep_rows_sel(feat: torch.Tensor, pos: torch.Tensor, operand_mode: int,
+                  pad_mode: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """prep_rows with row compaction: point n of frame b becomes row pos[b, n] (or is skipped when pos < 0).  The
+    outputs keep the capacity [B, N, .]; rows past the frame's count are left unwritten."""
+    _need(feat, torch.bfloat16 if feat.dtype == torch.bfloat16 else torch.float32, "feat")
+    _need(pos, torch.int32, "pos")
+    B, d, N = feat.shape
+    if tuple(pos.shape) != (B, N):
+        raise ValueError("pos must be [B, N]")
+    lib = _lib_for(feat)
+    kp = lib.gadm_operand_k(d, operand_mode)
+    _lib.check(min(kp, 0), "gadm_operand_k")
+    rows = torch.zeros((B, N, kp), dtype=torch.bfloat16, device=feat.device)
+    rinv = torch.zeros((B, N), dtype=torch.float32, device=feat.device)
+    pad_sim = torch.zeros((B, N) if pad_mode else (0,), dtype=torch.float32, device=feat.device)
+    with torch.cuda.device(feat.device):
+        _lib.check(lib.gadm_prep_rows_sel(_ptr(feat), int(feat.dtype == torch.bfloat16), _ptr(pos), B, d, N,
+                                          operand_mode, pad_mode, _ptr(rows), _ptr(rinv),
+                                          _ptr(pad_sim) if pad_mode else None, _stream()), "gadm_prep_rows_sel")
+    return rows, rinv, pad_sim
+
+
+@prep_rows_sel.register_fake
+def _(feat, pos, operand_mode, pad_mode):
+    B, d, N = feat.shape
+    kp = d * (3 if operand_mode == 1 else 1)
+    return (feat.new_empty((B, N, kp), dtype=torch.bfloat16), feat.new_empty((B, N), dtype=torch.float32),
+            feat.new_empty((B, N) if pad_mode else (0,), dtype=torch.float32))
+
+
 @torch.library.custom_op("gadm::pack_match_outputs", mutates_args=("out",), device_types="cuda")
 def pack_match_outputs(idx: torch.Tensor, max_sim: torch.Tensor, weight: torch.Tensor | None,
                        soft_xyz: torch.Tensor | None, out: torch.Tensor) -> None:
@@ -156,6 +209,49 @@ def match_fwd(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tensor, col
                                       _ptr(soft_xyz) if soft else None, _ptr(ws), ws.numel(), _stream()),
                    "gadm_match_fwd")
     return idx, max_sim, weight, soft_xyz
+
+
+@torch.library.custom_op("gadm::match_fwd_sel", mutates_args=(), device_types="cuda")
+def match_fwd_sel(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tensor, cols: torch.Tensor, aux: torch.Tensor,
+                  n_rows: torch.Tensor, row_map: torch.Tensor | None, obj_id: torch.Tensor | None, gamma: float,
+                  pad_mode: int, mode: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """match_fwd over compacted frames (n_rows[b] rows each).  row_map given: results are scattered back to the rows'
+    original positions (idx = -1, zeros elsewhere); row_map None: results stay in compacted order (rows past n_rows[b]:
+    idx = -1, zeros) -- exactly the ordering of evaluator.py:88-93."""
+    _need(rows, torch.bfloat16, "rows"); _need(cols, torch.bfloat16, "cols")
+    _need(rinv, torch.float32, "rinv"); _need(aux, torch.float32, "aux"); _need(n_rows, torch.int32, "n_rows")
+    B, N, kp = rows.shape
+    n_obj, M, kp2 = cols.shape
+    if kp != kp2:
+        raise ValueError(f"operand K mismatch: rows {kp} vs cols {kp2}")
+    if row_map is not None:
+        _need(row_map, torch.int32, "row_map")
+    if obj_id is not None:
+        _need(obj_id, torch.int32, "obj_id")
+    dev = rows.device
+    idx = torch.full((B, N), -1, dtype=torch.int64, device=dev)
+    max_sim = torch.zeros((B, N), dtype=torch.float32, device=dev)
+    soft = mode == 1
+    weight = torch.zeros((B, N) if soft else (0,), dtype=torch.float32, device=dev)
+    soft_xyz = torch.zeros((B, N, 3) if soft else (0,), dtype=torch.float32, device=dev)
+    lib = _lib_for(rows)
+    with torch.cuda.device(dev):
+        ws = _match_workspace(lib, dev)
+        _lib.check(lib.gadm_match_fwd_sel(_ptr(rows), _ptr(rinv), _ptr(pad_sim) if pad_mode else None, _ptr(cols),
+                                          _ptr(aux), _ptr(n_rows), _ptr(row_map), N, _ptr(obj_id), B, N, M, kp, n_obj,
+                                          float(gamma), pad_mode, mode, _ptr(idx), _ptr(max_sim),
+                                          _ptr(weight) if soft else None, _ptr(soft_xyz) if soft else None,
+                                          _ptr(ws), ws.numel(), _stream()), "gadm_match_fwd_sel")
+    return idx, max_sim, weight, soft_xyz
+
+
+@match_fwd_sel.register_fake
+def _(rows, rinv, pad_sim, cols, aux, n_rows, row_map, obj_id, gamma, pad_mode, mode):
+    B, N, _ = rows.shape
+    soft = mode == 1
+    return (rows.new_empty((B, N), dtype=torch.int64), rows.new_empty((B, N), dtype=torch.float32),
+            rows.new_empty((B, N) if soft else (0,), dtype=torch.float32),
+            rows.new_empty((B, N, 3) if soft else (0,), dtype=torch.float32))
 
 
 @match_fwd.register_fake

@@ -29,21 +29,30 @@ def gather_neighbour(pc, neighbor_idx):
 
 
 class QueryAndGroup(torch.nn.Module):
-    """kNN grouping (pointops.py:536-585, the nsample/knn branch): returns (b, 3+c, m, nsample)."""
+    """lib/pointops/functions/pointops.py:536-585 with the reference's constructor and return values: kNN grouping
+    (radius=None; the ball query is not on this path), forward -> (new_features (b, 3+c | c | 3, m, nsample),
+    grouped_xyz (b, 3, m, nsample)) and, with return_idx=True, the int64 neighbour indices as a third value."""
 
-    def __init__(self, nsample=32, use_xyz=True):
+    def __init__(self, radius=None, nsample=32, use_xyz=True, return_idx=False):
         super().__init__()
-        self.nsample, self.use_xyz = nsample, use_xyz
+        if radius is not None:
+            raise NotImplementedError("ball query (radius) is outside the kNN path this package replaces")
+        self.radius, self.nsample, self.use_xyz, self.return_idx = radius, nsample, use_xyz, return_idx
 
     def forward(self, xyz, new_xyz=None, features=None, idx=None):
         if new_xyz is None:
             new_xyz = xyz
         if idx is None:
-            idx = knnquery(self.nsample, xyz, new_xyz)                       # :566
+            idx = knnquery_heap(self.nsample, xyz, new_xyz)                      # :566
         xyz_trans = xyz.transpose(1, 2).contiguous()
-        grouped_xyz = grouping(xyz_trans, idx)                               # :568
-        grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)    # :570
-        if features is None:
-            return grouped_xyz
-        grouped_features = grouping(features.contiguous(), idx)              # :572
-        return torch.cat([grouped_xyz, grouped_features], dim=1) if self.use_xyz else grouped_features
+        grouped_xyz = grouping(xyz_trans, idx)                                   # :568  (b, 3, m, nsample)
+        grouped_xyz_diff = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)   # :570
+        if features is not None:
+            grouped_features = grouping(features.contiguous(), idx)              # :572
+            new_features = torch.cat([grouped_xyz_diff, grouped_features], dim=1) if self.use_xyz else grouped_features
+        else:
+            assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
+            new_features = grouped_xyz_diff
+        if self.return_idx:
+            return new_features, grouped_xyz, idx.long()
+        return new_features, grouped_xyz

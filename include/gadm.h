@@ -140,6 +140,27 @@ int gadm_match_fwd(const void* rows, const float* rinv_rows, const float* pad_si
                    int n_obj, float gamma, int pad_mode, int mode, int64_t* idx, float* max_sim, float* weight,
                    float* soft_xyz, void* workspace, size_t workspace_bytes, gadm_stream_t stream);
 
+/* Row compaction, evaluator.py:82-88 (cls_msk -> rgbd_features[cls_msk]) without the host round trip.
+ *   gadm_compact_rows   mask [B, N] uint8 -> pos [B, N] int32 (rank of a selected point among the selected points of its
+ *                       frame, -1 otherwise), row_map [B, N] int32 (row_map[b, j] = the point with rank j; entries
+ *                       >= n_sel[b] undefined), n_sel [B] int32.  Order is preserved: compacted order IS the reference's.
+ *   gadm_prep_rows_sel  as gadm_prep_rows / gadm_prep_rows_bf16 (feat_is_bf16), but point n lands in row pos[b, n] of
+ *                       rows / rinv / pad_sim (still [B, N, .]: N is the capacity); unselected points are skipped.
+ *   gadm_match_fwd_sel  as gadm_match_fwd over frames of n_rows[b] <= N rows (device memory; blocks of rows beyond it
+ *                       cost nothing -- the persistent ARGMAX kernel rebalances its schedule on the device).  Row j of
+ *                       frame b is written to position row_map[b, j] of an output frame of N_out rows (row_map NULL:
+ *                       position j, the compacted order, N_out >= N).  Positions no row maps to are left untouched:
+ *                       pre-fill idx with -1 for the scatter form.  B <= 2048 for the persistent kernel.        */
+int gadm_compact_rows(const uint8_t* mask, int B, int N, int32_t* pos, int32_t* row_map, int32_t* n_sel,
+                      gadm_stream_t stream);
+int gadm_prep_rows_sel(const void* feat, int feat_is_bf16, const int32_t* pos, int B, int d, int N, int operand_mode,
+                       int pad_mode, void* rows, float* rinv, float* pad_sim, gadm_stream_t stream);
+int gadm_match_fwd_sel(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
+                       const float* aux, const int32_t* n_rows, const int32_t* row_map, int N_out,
+                       const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma, int pad_mode, int mode,
+                       int64_t* idx, float* max_sim, float* weight, float* soft_xyz, void* workspace,
+                       size_t workspace_bytes, gadm_stream_t stream);
+
 /* Packs the matcher outputs of n scene points into records of six 32-bit words {int32 idx, max_sim, weight, x, y, z}
  * (weight / soft_xyz may be NULL: zeros), so that one contiguous copy carries them to the host -- the reference pulls
  * idx and the cloud back tensor by tensor (evaluator.py:87,99).  idx must fit int32 (it is < M + 1). */

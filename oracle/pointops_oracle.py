@@ -1,10 +1,13 @@
 """TEST INFRASTRUCTURE ONLY -- CPU oracle for the two pointops entry points the path names.
 
-PARITY UNPINNED: the CUDA sources of lib/pointops are absent from the reference
-(lib/pointops/pointops.egg-info/SOURCES.txt:6-24) and nothing imports the package.  Semantics come from
-  * KNNQueryNaive.forward   /root/reference/lib/pointops/functions/pointops.py:405-426  (pure torch)
-  * Grouping.forward/backward docstrings and shapes   .../pointops.py:149-178
-torch.sort is not stable across equal keys by contract; ties are canonicalised by (dist, index) here.
+The CUDA sources of lib/pointops are absent from the reference (lib/pointops/pointops.egg-info/SOURCES.txt:6-24) and
+nothing imports the package, but its own pure-torch oracle ships: this restatement is PINNED by
+tests/golden/pointops_golden.npz, produced by EXECUTING KNNQueryNaive.forward
+(/root/reference/lib/pointops/functions/pointops.py:396-426) and QueryAndGroup.forward (:548-585) from the reference
+source text (tests/golden/make_golden.py::make_pointops).  Grouping follows the docstring contract :151-155 and the
+scatter-add of its backward :166-176.
+torch.sort is not stable across equal keys by contract; ties are canonicalised by (dist, index) here (the fixture is
+tie-free among the first k + 1 distances, asserted by the test).
 """
 import torch
 
@@ -18,6 +21,21 @@ def knnquery_naive(nsample, xyz, new_xyz=None):
     dist = diff.pow(2).sum(dim=3)
     idxs = torch.sort(dist, dim=2, stable=True)[1]      # stable => ties by ascending index
     return idxs[:, :, :nsample].int(), torch.sort(dist, dim=2, stable=True)[0][:, :, :nsample]
+
+
+def query_and_group(nsample, xyz, new_xyz=None, features=None, use_xyz=True):
+    """QueryAndGroup.forward, kNN branch (pointops.py:548-585) -> (new_features, grouped_xyz, idx int64)."""
+    if new_xyz is None:
+        new_xyz = xyz
+    idx = knnquery_naive(nsample, xyz, new_xyz)[0]
+    grouped_xyz = grouping(xyz.transpose(1, 2).contiguous(), idx)
+    diff = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
+    if features is not None:
+        gf = grouping(features, idx)
+        new = torch.cat([diff, gf], dim=1) if use_xyz else gf
+    else:
+        new = diff
+    return new, grouped_xyz, idx.long()
 
 
 def grouping(features, idx):

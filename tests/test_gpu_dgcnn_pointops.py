@@ -70,8 +70,32 @@ def test_pointops_knnquery_and_grouping(cuda):
     assert torch.allclose(f.grad.cpu(), ref_g, rtol=1e-5, atol=1e-5)
 
     qg = pointops.QueryAndGroup(nsample=ns)
-    grouped = qg(xyz.to(cuda), new_xyz.to(cuda), feats.to(cuda))
-    assert grouped.shape == (b, 3 + c, m, ns)
+    grouped, gxyz = qg(xyz.to(cuda), new_xyz.to(cuda), feats.to(cuda))
+    assert grouped.shape == (b, 3 + c, m, ns) and gxyz.shape == (b, 3, m, ns)
+    ref_new, ref_gxyz, _ = po.query_and_group(ns, xyz, new_xyz, feats)
+    assert torch.equal(grouped.cpu(), ref_new) and torch.equal(gxyz.cpu(), ref_gxyz)
+
+
+def test_pointops_vs_reference_golden(cuda):
+    """knnquery / knnquery_heap / grouping / QueryAndGroup against pointops_golden.npz: outputs of the reference's own
+    KNNQueryNaive.forward (pointops.py:396-426) and QueryAndGroup.forward (:548-585), executed from its source text."""
+    import os
+    from gadm_b200 import pointops
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "pointops_golden.npz"))
+    t = lambda k: torch.from_numpy(z[k]).to(cuda)
+    k = int(z["k"])
+    assert float(z["knn_gap"]) > 0                          # tie-free: the index order is unambiguous
+    assert torch.equal(pointops.knnquery(k, t("xyz"), t("new_xyz")), t("knn_idx"))
+    assert torch.equal(pointops.knnquery_heap(k, t("xyz")), t("knn_self_idx"))
+    assert torch.equal(pointops.grouping(t("features"), t("knn_idx")), t("qg_new_features")[:, 3:])
+    nf, gx, idx = pointops.QueryAndGroup(nsample=k, return_idx=True)(t("xyz"), t("new_xyz"), t("features"))
+    assert idx.dtype == torch.int64 and torch.equal(idx, t("qg_idx"))
+    assert torch.equal(gx, t("qg_grouped_xyz")) and torch.equal(nf, t("qg_new_features"))
+    assert torch.equal(pointops.QueryAndGroup(nsample=k, use_xyz=False)(t("xyz"), t("new_xyz"), t("features"))[0],
+                       t("qg_features_only"))
+    assert torch.equal(pointops.QueryAndGroup(nsample=k)(t("xyz"), t("new_xyz"))[0], t("qg_xyz_only"))
+    with pytest.raises(NotImplementedError):
+        pointops.QueryAndGroup(radius=0.1)
 
 
 def test_gather_neighbour(cuda):

@@ -101,6 +101,63 @@ def test_match_mask_rows(cuda):
     _check([o[0] for o in out], ref, M, 0.1, rows=mask)
 
 
+@pytest.mark.parametrize("mode", ["soft", "argmax"])
+def test_match_row_compaction_vs_oracle(cuda, mode):
+    """evaluator.py:82-93: cls_msk -> rgbd_features[cls_msk] -> normalize -> matmul -> max.  With a mask the rows are
+    compacted on the device and only they are matched; compact=True returns the reference's own (compacted) ordering,
+    the default scatters back.  Frames with ~20 %, 0, 100 % and 1 selected rows; ragged row / model tiles."""
+    from gadm_b200 import matching, synth
+    B, N, M, d = 4, 3000, 2056, 128
+    rgbd, mesh, _ = synth.descriptors(B, N, M, d, regime="planted", seed=31)
+    diam = 0.2
+    xyz = synth.fibonacci_sphere(M, diam)
+    g = torch.Generator().manual_seed(7)
+    mask = torch.rand((B, N), generator=g) < 0.2
+    mask[1] = False
+    mask[2] = True
+    mask[3] = False
+    mask[3, 1777] = True
+    bank = matching.ModelBank(mesh.to(cuda), xyz[None].to(cuda))
+    out = matching.match(rgbd.to(cuda), bank, mask=mask.to(cuda), mode=mode, compact=True)
+    n_sel = out[4].cpu()
+    assert n_sel.tolist() == mask.sum(1).tolist()
+    scat = matching.match(rgbd.to(cuda), bank, mask=mask.to(cuda), mode=mode)
+    full = matching.match(rgbd.to(cuda), bank, mode=mode)
+    for b in range(B):
+        n = int(n_sel[b])
+        assert torch.all(out[0][b, n:] == -1) and torch.all(out[1][b, n:] == 0)
+        assert torch.all(scat[0][b].cpu()[~mask[b]] == -1) and torch.all(scat[1][b].cpu()[~mask[b]] == 0)
+        if n == 0:
+            continue
+        ref = mo.match_soft(rgbd[b], mesh[0], xyz, row_mask=mask[b])            # the reference's compacted rows
+        got = [o[b, :n] if o is not None else None for o in out[:4]]
+        if n > 10:
+            _check(got, ref, M, diam, soft=mode == "soft")
+        else:
+            assert (got[1].cpu() - ref["max_sim"]).abs().max() <= TOL
+        # scatter-back == compacted results at the selected positions == the unmasked launch at those positions
+        for k in range(4):
+            if out[k] is None:
+                continue
+            assert torch.equal(scat[k][b].cpu()[mask[b]], out[k][b, :n].cpu())
+            assert torch.equal(scat[k][b].cpu()[mask[b]], full[k][b].cpu()[mask[b]])
+
+
+def test_match_obj_id_is_validated(cuda):
+    """A bank slot outside [0, n_obj) (e.g. a 1-based YCB-V class id used as is) is rejected on the host."""
+    from gadm_b200 import matching, synth
+    rgbd, mesh, _ = synth.descriptors(2, 300, 256, 64, n_obj=3, regime="random", seed=3)
+    bank = matching.ModelBank(mesh.to(cuda), synth.model_bank_xyz(3, 256).to(cuda))
+    with pytest.raises(ValueError):
+        matching.match(rgbd.to(cuda), bank, obj_id=[1, 3])
+    with pytest.raises(ValueError):
+        matching.match(rgbd.to(cuda), bank, obj_id=torch.tensor([-1, 0]))
+    # a device-side id cannot be checked without a synchronisation: the kernels clamp it (no out-of-bounds read)
+    idx = matching.match(rgbd.to(cuda), bank, obj_id=torch.tensor([7, 0], device=cuda), mode="argmax")[0]
+    ref = matching.match(rgbd.to(cuda), bank, obj_id=[2, 0], mode="argmax")[0]
+    assert torch.equal(idx, ref)
+
+
 def test_match_bf16x3_fp32_inputs(cuda):
     """operand_mode='bf16x3': arbitrary fp32 descriptors, ~fp32-faithful similarities (error ~1e-6)."""
     from gadm_b200 import matching, synth

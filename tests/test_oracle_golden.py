@@ -148,6 +148,22 @@ def test_pointops_oracle_semantics():
     assert torch.allclose(gf, f2.grad)
 
 
+def test_pointops_oracle_vs_reference_source():
+    """oracle/pointops_oracle.py against pointops_golden.npz: the outputs of KNNQueryNaive.forward
+    (lib/pointops/functions/pointops.py:396-426) and QueryAndGroup.forward (:548-585) executed from the reference text."""
+    z = np.load(os.path.join(G, "pointops_golden.npz"))
+    t = lambda k: torch.from_numpy(z[k])
+    k = int(z["k"])
+    assert float(z["knn_gap"]) > 0, "fixture must be tie-free among the first k + 1 distances"
+    assert torch.equal(po.knnquery_naive(k, t("xyz"), t("new_xyz"))[0], t("knn_idx"))
+    assert torch.equal(po.knnquery_naive(k, t("xyz"))[0], t("knn_self_idx"))
+    nf, gx, idx = po.query_and_group(k, t("xyz"), t("new_xyz"), t("features"))
+    assert torch.equal(idx, t("qg_idx")) and torch.equal(gx, t("qg_grouped_xyz")) and torch.equal(nf, t("qg_new_features"))
+    assert torch.equal(po.query_and_group(k, t("xyz"), t("new_xyz"), t("features"), use_xyz=False)[0], t("qg_features_only"))
+    assert torch.equal(po.query_and_group(k, t("xyz"), t("new_xyz"))[0], t("qg_xyz_only"))
+    assert torch.equal(po.grouping(t("features"), t("knn_idx")), t("qg_new_features")[:, 3:])
+
+
 def test_randla_oracle_vs_reference_source():
     """oracle/randla_oracle.py against the outputs of the reference's own function bodies (randla_golden.npz)."""
     from oracle import randla_oracle as ro
