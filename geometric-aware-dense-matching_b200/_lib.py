@@ -52,6 +52,9 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "gadm_kabsch_moments": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                     c_void_p, c_void_p]),
+    "gadm_kabsch_moments_w": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                      c_int, c_void_p, c_void_p]),
+    "gadm_kabsch_poses": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "gadm_knn3d_workspace_bytes": (c_size_t, [ctypes.POINTER(KnnJob), c_int, c_int]),
     "gadm_knn3d": (c_int, [c_void_p, c_void_p, ctypes.POINTER(KnnJob), c_int, c_int, c_void_p, c_void_p,
                            c_void_p, c_size_t, c_void_p]),

@@ -281,7 +281,23 @@ int gadm_kabsch_moments(const int64_t* idx, const uint8_t* mask, const float* cl
   GADM_REQUIRE_INIT();
   if (!idx || !cloud || !aux || !out || B <= 0 || N <= 0 || M <= 0 || n_obj <= 0) return GADM_ERR_BAD_ARG;
   if (obj_id == nullptr && n_obj != 1 && n_obj != B) return GADM_ERR_BAD_ARG;
-  return kabsch_moments_launch(idx, mask, cloud, aux, obj_id, B, N, M, n_obj, out, (cudaStream_t)stream);
+  return kabsch_moments_launch(idx, mask, nullptr, cloud, aux, obj_id, B, N, M, n_obj, out, (cudaStream_t)stream);
+}
+
+int gadm_kabsch_moments_w(const int64_t* idx, const uint8_t* mask, const float* weight, const float* cloud,
+                          const float* aux, const int32_t* obj_id, int B, int N, int M, int n_obj, double* out,
+                          gadm_stream_t stream) {
+  GADM_REQUIRE_INIT();
+  if (!idx || !weight || !cloud || !aux || !out || B <= 0 || N <= 0 || M <= 0 || n_obj <= 0) return GADM_ERR_BAD_ARG;
+  if (obj_id == nullptr && n_obj != 1 && n_obj != B) return GADM_ERR_BAD_ARG;
+  return kabsch_moments_launch(idx, mask, weight, cloud, aux, obj_id, B, N, M, n_obj, out, (cudaStream_t)stream);
+}
+
+int gadm_kabsch_poses(const double* moments, const double* count_moments, const uint8_t* det, int B, int min_pts,
+                      float* poses, gadm_stream_t stream) {
+  GADM_REQUIRE_INIT();
+  if (!moments || !poses || B <= 0) return GADM_ERR_BAD_ARG;
+  return kabsch_pose_launch(moments, count_moments, det, B, min_pts, poses, (cudaStream_t)stream);
 }
 
 static int validate_jobs(const gadm_knn_job* jobs, int n_jobs) {

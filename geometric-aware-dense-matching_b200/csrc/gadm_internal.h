@@ -54,8 +54,11 @@ int pack_outputs_launch(const int64_t* idx, const float* max_sim, const float* w
 int prep_model_launch(const float* mesh, const float* model_xyz, int n_obj, int d, int M, int operand_mode, void* cols,
                       float* aux, cudaStream_t stream);
 int seg_mask_launch(const float* seg, int B, int N, uint8_t* mask, cudaStream_t stream);
-int kabsch_moments_launch(const int64_t* idx, const uint8_t* mask, const float* cloud, const float* aux,
-                          const int32_t* obj_id, int B, int N, int M, int n_obj, double* out, cudaStream_t stream);
+int kabsch_moments_launch(const int64_t* idx, const uint8_t* mask, const float* weight, const float* cloud,
+                          const float* aux, const int32_t* obj_id, int B, int N, int M, int n_obj, double* out,
+                          cudaStream_t stream);
+int kabsch_pose_launch(const double* mom, const double* count, const uint8_t* det, int B, int min_pts, float* poses,
+                       cudaStream_t stream);
 
 // knn3d.cu
 int knn3d_configure();

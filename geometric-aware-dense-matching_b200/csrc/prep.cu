@@ -130,7 +130,7 @@ seg_mask_kernel(const float* __restrict__ seg, int N, uint8_t* __restrict__ mask
 // One CTA per frame: fp64 accumulation of n, sum A, sum B, sum A B^T over matched rows.
 __global__ void __launch_bounds__(256)
 kabsch_moments_kernel(const int64_t* __restrict__ idx, const uint8_t* __restrict__ mask,
-                      const float* __restrict__ cloud, const float* __restrict__ aux,
+                      const float* __restrict__ weight, const float* __restrict__ cloud, const float* __restrict__ aux,
                       const int32_t* __restrict__ obj_id, int B, int N, int M, int n_obj, double* __restrict__ out) {
   const int b = blockIdx.x;
   const int obj = obj_id ? min(max(obj_id[b], 0), n_obj - 1) : (n_obj == B ? b : 0);   // clamped: see frame_object
@@ -147,12 +147,15 @@ kabsch_moments_kernel(const int64_t* __restrict__ idx, const uint8_t* __restrict
     float4 a;
     a.x = e[0]; a.y = e[1]; a.z = e[2];
     const float bx = cloud[gn * 3 + 0], by = cloud[gn * 3 + 1], bz = cloud[gn * 3 + 2];
-    acc[0] += 1.0;
-    acc[1] += a.x; acc[2] += a.y; acc[3] += a.z;
-    acc[4] += bx; acc[5] += by; acc[6] += bz;
-    acc[7] += double(a.x) * bx;  acc[8] += double(a.x) * by;  acc[9] += double(a.x) * bz;
-    acc[10] += double(a.y) * bx; acc[11] += double(a.y) * by; acc[12] += double(a.y) * bz;
-    acc[13] += double(a.z) * bx; acc[14] += double(a.z) * by; acc[15] += double(a.z) * bz;
+    // weighted Procrustes: every pair counts with its weight (the matcher's softmax weight); unweighted: w = 1
+    const double w = weight ? double(weight[gn]) : 1.0;
+    const double wx = w * a.x, wy = w * a.y, wz = w * a.z;
+    acc[0] += w;
+    acc[1] += wx; acc[2] += wy; acc[3] += wz;
+    acc[4] += w * bx; acc[5] += w * by; acc[6] += w * bz;
+    acc[7] += wx * bx;  acc[8] += wx * by;  acc[9] += wx * bz;
+    acc[10] += wy * bx; acc[11] += wy * by; acc[12] += wy * bz;
+    acc[13] += wz * bx; acc[14] += wz * by; acc[15] += wz * bz;
   }
   __shared__ double red[8][16];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -271,9 +274,104 @@ int seg_mask_launch(const float* seg, int B, int N, uint8_t* mask, cudaStream_t 
   return check_launch();
 }
 
-int kabsch_moments_launch(const int64_t* idx, const uint8_t* mask, const float* cloud, const float* aux,
-                          const int32_t* obj_id, int B, int N, int M, int n_obj, double* out, cudaStream_t stream) {
-  kabsch_moments_kernel<<<B, 256, 0, stream>>>(idx, mask, cloud, aux, obj_id, B, N, M, n_obj, out);
+int kabsch_moments_launch(const int64_t* idx, const uint8_t* mask, const float* weight, const float* cloud,
+                          const float* aux, const int32_t* obj_id, int B, int N, int M, int n_obj, double* out,
+                          cudaStream_t stream) {
+  kabsch_moments_kernel<<<B, 256, 0, stream>>>(idx, mask, weight, cloud, aux, obj_id, B, N, M, n_obj, out);
+  return check_launch();
+}
+
+// best_fit_transform (utils/pvn3d_eval_utils_kpls.py:43-76; torch twin utils/basic_utils.py:848-880) from the moments
+// of the matched pairs, one thread per frame, fp64:
+//   H = sum(w A B^T) - W cA cB^T,   H = U S V^T (one-sided Jacobi, singular values sorted descending),
+//   R = V U^T, reflection fix (:67-69): det R < 0 -> last column of V negated,   t = cB - R cA.
+// Frames the reference answers with its sentinel (evaluator.py:69-72, :83, :96: not detected, <= 1 or fewer than
+// min_pts matched rows) get identity and t_z = -1000.  `count` = number of pairs (moments of an unweighted pass; null:
+// the weight sum is taken as the count).
+__global__ void __launch_bounds__(128)
+kabsch_pose_kernel(const double* __restrict__ mom, const double* __restrict__ count, const uint8_t* __restrict__ det,
+                   int B, int min_pts, float* __restrict__ poses) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double* m = mom + size_t(b) * 16;
+  float* T = poses + size_t(b) * 12;
+  const double W = m[0];
+  const double npairs = count ? count[size_t(b) * 16] : W;
+  if ((det && !det[b]) || npairs <= 1.0 || npairs < double(min_pts) || !(W > 0.0)) {
+    for (int i = 0; i < 12; ++i) T[i] = 0.f;
+    T[0] = T[5] = T[10] = 1.f;
+    T[11] = -1000.f;
+    return;
+  }
+  double ca[3], cb[3], G[3][3], V[3][3];
+  for (int i = 0; i < 3; ++i) { ca[i] = m[1 + i] / W; cb[i] = m[4 + i] / W; }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) { G[i][j] = m[7 + 3 * i + j] - W * ca[i] * cb[j]; V[i][j] = i == j ? 1.0 : 0.0; }
+  // one-sided Jacobi: rotate column pairs of G (and V) until the columns of G are orthogonal: G = U S, H = U S V^T
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double al = 0, be = 0, ga = 0;
+        for (int i = 0; i < 3; ++i) { al += G[i][p] * G[i][p]; be += G[i][q] * G[i][q]; ga += G[i][p] * G[i][q]; }
+        off = fmax(off, fabs(ga) / fmax(sqrt(al * be), 1e-300));
+        if (fabs(ga) <= 1e-300 || fabs(ga) <= 1e-17 * sqrt(al * be)) continue;
+        const double zeta = (be - al) / (2.0 * ga);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        for (int i = 0; i < 3; ++i) {
+          const double gp = G[i][p], gq = G[i][q];
+          G[i][p] = c * gp - s * gq; G[i][q] = s * gp + c * gq;
+          const double vp = V[i][p], vq = V[i][q];
+          V[i][p] = c * vp - s * vq; V[i][q] = s * vp + c * vq;
+        }
+      }
+    if (off < 1e-15) break;
+  }
+  double sig[3];
+  int ord[3] = {0, 1, 2};
+  for (int j = 0; j < 3; ++j) sig[j] = sqrt(G[0][j] * G[0][j] + G[1][j] * G[1][j] + G[2][j] * G[2][j]);
+  for (int a = 0; a < 2; ++a)                         // descending, like numpy's SVD (the fix below flips the SMALLEST)
+    for (int c2 = a + 1; c2 < 3; ++c2)
+      if (sig[ord[c2]] > sig[ord[a]]) { const int tmp = ord[a]; ord[a] = ord[c2]; ord[c2] = tmp; }
+  double U[3][3], Vs[3][3];
+  for (int j = 0; j < 3; ++j)
+    for (int i = 0; i < 3; ++i) { Vs[i][j] = V[i][ord[j]]; U[i][j] = sig[ord[j]] > 0 ? G[i][ord[j]] / sig[ord[j]] : 0.0; }
+  // rank-deficient H: complete U to a rotation-or-reflection basis (the fix below settles the sign)
+  if (!(sig[ord[1]] > 1e-12 * sig[ord[0]])) {
+    const int k = fabs(U[0][0]) < 0.9 ? 0 : 1;        // any vector not parallel to u0
+    double e[3] = {0, 0, 0}; e[k] = 1.0;
+    const double d0 = U[k][0];
+    double nn = 0;
+    for (int i = 0; i < 3; ++i) { U[i][1] = e[i] - d0 * U[i][0]; nn += U[i][1] * U[i][1]; }
+    for (int i = 0; i < 3; ++i) U[i][1] /= sqrt(nn);
+  }
+  if (!(sig[ord[2]] > 1e-12 * sig[ord[0]])) {
+    U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
+    U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
+    U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
+  }
+  double R[3][3];
+  auto compose = [&]() {
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) R[i][j] = Vs[i][0] * U[j][0] + Vs[i][1] * U[j][1] + Vs[i][2] * U[j][2];
+  };
+  compose();
+  const double detR = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
+                      R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
+  if (detR < 0) {
+    for (int i = 0; i < 3; ++i) Vs[i][2] = -Vs[i][2];
+    compose();
+  }
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) T[i * 4 + j] = float(R[i][j]);
+    T[i * 4 + 3] = float(cb[i] - (R[i][0] * ca[0] + R[i][1] * ca[1] + R[i][2] * ca[2]));
+  }
+}
+
+int kabsch_pose_launch(const double* mom, const double* count, const uint8_t* det, int B, int min_pts, float* poses,
+                       cudaStream_t stream) {
+  kabsch_pose_kernel<<<(B + 127) / 128, 128, 0, stream>>>(mom, count, det, B, min_pts, poses);
   return check_launch();
 }
 

@@ -239,24 +239,30 @@ def sentinel_pose():
     return rt[:3, :]
 
 
-def frame_poses(cld, seg, rgbd, bank, obj_id=None, det=None, min_pts=5):
-    """Batched evaluator.cal_frame_poses: cld [B,>=3,N], seg [B,2,N], rgbd [B,d,N] -> list of [3,4] poses.
-    One matcher launch + one moment launch + ONE device->host copy for the whole batch (the reference
-    syncs per frame at evaluator.py:83, :87, :99)."""
-    B, _, N = rgbd.shape
+def frame_poses_device(cld, seg, rgbd, bank, obj_id=None, det=None, min_pts=5, weighted=False, gamma=16.0):
+    """Batched evaluator.cal_frame_poses entirely on the device: cld [B,>=3,N], seg [B,2,N], rgbd [B,d,N] ->
+    poses float32 [B, 3, 4] (CUDA tensor; no host synchronisation -- the reference syncs per frame at evaluator.py:83,
+    :87, :99).  seg argmax -> row compaction -> fused matcher -> moments -> batched 3x3 SVD (gadm_kabsch_poses).
+    weighted=True fits a weighted Procrustes with the matcher's softmax weights (the soft-correspondence extension);
+    the sentinel rule still counts matched rows."""
     mask = ops.seg_mask(seg.contiguous().float())                            # evaluator.py:78,82 (uint8 [B, N])
-    idx, _, _, _ = match(rgbd, bank, obj_id=obj_id, mask=mask, mode="argmax", operand_mode=bank.operand_mode)
+    out = match(rgbd, bank, obj_id=obj_id, mask=mask, mode="soft" if weighted else "argmax", gamma=gamma,
+                operand_mode=bank.operand_mode)
     cloud = cld[:, :3, :].transpose(1, 2).contiguous().float()               # evaluator.py:85
     oid = None if obj_id is None else torch.as_tensor(obj_id, device=rgbd.device).to(torch.int32)
-    mom = ops.kabsch_moments(idx, mask, cloud, bank.aux, oid, bank.M, bank.n_obj).cpu().numpy()
-    poses = []
-    for b in range(B):
-        n_sel = mom[b, 0]
-        if (det is not None and not bool(det[b])) or n_sel <= 1 or n_sel < min_pts:  # :72, :83, :96
-            poses.append(sentinel_pose())
-        else:
-            poses.append(rt_from_moments(mom[b]).astype(np.float32))
-    return poses
+    mom = ops.kabsch_moments(out[0], mask, cloud, bank.aux, oid, bank.M, bank.n_obj)
+    d8 = None if det is None else torch.as_tensor(det, device=rgbd.device).to(torch.uint8).contiguous()
+    if weighted:
+        momw = ops.kabsch_moments_w(out[0], mask, out[2].contiguous(), cloud, bank.aux, oid, bank.M, bank.n_obj)
+        return ops.kabsch_poses(momw, mom, d8, min_pts)
+    return ops.kabsch_poses(mom, None, d8, min_pts)
+
+
+def frame_poses(cld, seg, rgbd, bank, obj_id=None, det=None, min_pts=5, weighted=False):
+    """Batched evaluator.cal_frame_poses: -> list of numpy [3,4] poses (what the reference's callers consume).
+    Everything runs on the device (frame_poses_device); ONE device->host copy of B x 12 floats ends the batch."""
+    poses = frame_poses_device(cld, seg, rgbd, bank, obj_id=obj_id, det=det, min_pts=min_pts, weighted=weighted)
+    return list(poses.cpu().numpy())
 
 
 def cal_frame_poses(item, bank):

@@ -358,6 +358,51 @@ def _(idx, mask, cloud, aux, obj_id, M, n_obj):
     return idx.new_empty((idx.shape[0], 16), dtype=torch.float64)
 
 
+@torch.library.custom_op("gadm::kabsch_moments_w", mutates_args=(), device_types="cuda")
+def kabsch_moments_w(idx: torch.Tensor, mask: torch.Tensor | None, weight: torch.Tensor, cloud: torch.Tensor,
+                     aux: torch.Tensor, obj_id: torch.Tensor | None, M: int, n_obj: int) -> torch.Tensor:
+    """Weighted moments {sum w, sum w A, sum w B, sum w A B^T} (weighted Procrustes with the matcher's weights)."""
+    _need(idx, torch.int64, "idx"); _need(cloud, torch.float32, "cloud"); _need(aux, torch.float32, "aux")
+    _need(weight, torch.float32, "weight")
+    B, N = idx.shape
+    if tuple(cloud.shape) != (B, N, 3) or tuple(weight.shape) != (B, N):
+        raise ValueError("cloud must be [B, N, 3] and weight [B, N]")
+    out = torch.empty((B, 16), dtype=torch.float64, device=idx.device)
+    lib = _lib_for(idx)
+    with torch.cuda.device(idx.device):
+        _lib.check(lib.gadm_kabsch_moments_w(_ptr(idx), _ptr(mask), _ptr(weight), _ptr(cloud), _ptr(aux), _ptr(obj_id),
+                                             B, N, M, n_obj, _ptr(out), _stream()), "gadm_kabsch_moments_w")
+    return out
+
+
+@kabsch_moments_w.register_fake
+def _(idx, mask, weight, cloud, aux, obj_id, M, n_obj):
+    return idx.new_empty((idx.shape[0], 16), dtype=torch.float64)
+
+
+@torch.library.custom_op("gadm::kabsch_poses", mutates_args=(), device_types="cuda")
+def kabsch_poses(moments: torch.Tensor, count_moments: torch.Tensor | None, det: torch.Tensor | None,
+                 min_pts: int) -> torch.Tensor:
+    """moments [B, 16] fp64 -> poses [B, 3, 4] fp32 on the device (best_fit_transform + the evaluator's sentinel)."""
+    _need(moments, torch.float64, "moments")
+    if count_moments is not None:
+        _need(count_moments, torch.float64, "count_moments")
+    if det is not None:
+        _need(det, torch.uint8, "det")
+    B = moments.shape[0]
+    poses = torch.empty((B, 3, 4), dtype=torch.float32, device=moments.device)
+    lib = _lib_for(moments)
+    with torch.cuda.device(moments.device):
+        _lib.check(lib.gadm_kabsch_poses(_ptr(moments), _ptr(count_moments), _ptr(det), B, int(min_pts), _ptr(poses),
+                                         _stream()), "gadm_kabsch_poses")
+    return poses
+
+
+@kabsch_poses.register_fake
+def _(moments, count_moments, det, min_pts):
+    return moments.new_empty((moments.shape[0], 3, 4), dtype=torch.float32)
+
+
 # --------------------------------------------------------------------------------------------- kNN 3-D
 def make_jobs(job_list):
     """[(support_off, query_off, out_off, s_bstride, q_bstride, o_bstride, n_support, n_query, k, batch)]."""

@@ -211,6 +211,19 @@ int gadm_seg_mask(const float* seg, int B, int N, uint8_t* mask, gadm_stream_t s
 int gadm_kabsch_moments(const int64_t* idx, const uint8_t* mask, const float* cloud, const float* aux,
                         const int32_t* obj_id, int B, int N, int M, int n_obj, double* out,
                         gadm_stream_t stream);
+/* The same with a weight per scene point (weight [B, N] fp32, e.g. the matcher's softmax weight): out[b] =
+ * {sum w, sum w A, sum w B, sum w A B^T} -- weighted Procrustes. */
+int gadm_kabsch_moments_w(const int64_t* idx, const uint8_t* mask, const float* weight, const float* cloud,
+                          const float* aux, const int32_t* obj_id, int B, int N, int M, int n_obj, double* out,
+                          gadm_stream_t stream);
+/* best_fit_transform (utils/pvn3d_eval_utils_kpls.py:43-76, torch twin utils/basic_utils.py:848-880) ON THE DEVICE, one
+ * frame per thread, fp64: moments [B, 16] -> poses [B, 3, 4] fp32 = [R | t] with B ~ R A + t, 3x3 SVD by one-sided
+ * Jacobi, reflection fix on the smallest singular direction (:67-69).  Frames the reference answers with its sentinel
+ * (evaluator.py:69-72, :83, :96: det[b] == 0, <= 1 or fewer than min_pts matched rows) get [I | (0, 0, -1000)].
+ * count_moments (NULL: the weight sum counts): moments of an UNWEIGHTED pass whose [b, 0] is the number of pairs, for
+ * weighted fits.  det [B] uint8 or NULL. */
+int gadm_kabsch_poses(const double* moments, const double* count_moments, const uint8_t* det, int B, int min_pts,
+                      float* poses, gadm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Exact 3-D kNN (RandLA nearest_neighbors / pointops knnquery)

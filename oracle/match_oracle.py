@@ -91,3 +91,19 @@ def best_fit_transform(A, B):
         R = Vt.T @ U.T
     t = cb - R @ ca                                    # :71
     return torch.cat([R, t[:, None]], dim=1)
+
+
+def best_fit_transform_weighted(A, B, w):
+    """Extension (weights = the soft-correspondence weights): weighted Procrustes, same steps as best_fit_transform with
+    weighted centroids and H = sum w (A - ca)(B - cb)^T."""
+    A = A.double(); B = B.double(); w = w.double()
+    W = w.sum()
+    ca, cb = (w[:, None] * A).sum(0) / W, (w[:, None] * B).sum(0) / W
+    H = ((A - ca) * w[:, None]).T @ (B - cb)
+    U, S, Vt = torch.linalg.svd(H)
+    R = Vt.T @ U.T
+    if torch.linalg.det(R) < 0:
+        Vt = Vt.clone(); Vt[2, :] *= -1
+        R = Vt.T @ U.T
+    t = cb - R @ ca
+    return torch.cat([R, t[:, None]], dim=1)

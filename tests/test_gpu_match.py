@@ -231,6 +231,69 @@ def test_frame_poses_recovers_pose(cuda):
     assert RT0[2, 3] == -1000
 
 
+def test_device_pose_fit_vs_best_fit_transform(cuda):
+    """gadm_kabsch_moments(_w) + gadm_kabsch_poses (batched 3x3 Jacobi SVD, reflection fix, sentinel) on
+    the device against the restated best_fit_transform (utils/pvn3d_eval_utils_kpls.py:43-76) at 1e-5: clean rigid
+    motions, heavy noise (reflection fix exercised), planar and collinear point sets (rank-deficient H), too few
+    pairs / not detected (evaluator.py:69-72, :83, :96), and the weighted fit."""
+    from gadm_b200 import matching, ops, synth
+    g = torch.Generator().manual_seed(11)
+    B, N, M = 12, 400, 512
+    xyz = synth.fibonacci_sphere(M, 0.2)
+    bank = matching.ModelBank(synth.bf16_round(torch.randn((1, 64, M), generator=g)).to(cuda), xyz[None].to(cuda))
+    idx = torch.randint(0, M, (B, N), generator=g)
+    A = xyz[idx]                                                  # [B, N, 3] model points of the matches
+    cloud = torch.empty((B, N, 3))
+    for b in range(B):
+        q, _ = torch.linalg.qr(torch.randn((3, 3), generator=g))
+        if torch.linalg.det(q) < 0:
+            q[:, 0] = -q[:, 0]
+        noise = [0.0, 1e-3, 0.05, 0.3][b % 4]                     # 0.3 >> the model radius: the fit is near-degenerate
+        cloud[b] = A[b] @ q.T + torch.randn(3, generator=g) + noise * torch.randn((N, 3), generator=g)
+    cloud[8] = torch.randn((N, 3), generator=g) * torch.tensor([1.0, 1.0, 0.0])          # planar camera points
+    idx[9] = idx[9, 0]                                                                    # one model vertex only
+    A = xyz[idx]
+    mask = (torch.rand((B, N), generator=g) < 0.7)
+    mask[10] = False; mask[10, :3] = True                                                 # 3 pairs < min_pts
+    det = torch.ones(B, dtype=torch.uint8); det[11] = 0
+    w = torch.rand((B, N), generator=g) + 0.01
+    mom = ops.kabsch_moments(idx.to(cuda), mask.to(torch.uint8).to(cuda), cloud.to(cuda), bank.aux, None, M, 1)
+    poses = ops.kabsch_poses(mom, None, det.to(cuda), 5).cpu()
+    momw = ops.kabsch_moments_w(idx.to(cuda), mask.to(torch.uint8).to(cuda), w.to(cuda), cloud.to(cuda), bank.aux, None, M, 1)
+    posesw = ops.kabsch_poses(momw, mom, det.to(cuda), 5).cpu()
+    flips = 0
+    for b in range(B):
+        sel = mask[b]
+        if b in (10, 11):
+            for P in (poses[b], posesw[b]):
+                assert torch.equal(P[:, :3], torch.eye(3)) and P[2, 3] == -1000 and P[0, 3] == 0 and P[1, 3] == 0
+            continue
+        ref = mo.best_fit_transform(A[b][sel], cloud[b][sel])
+        refw = mo.best_fit_transform_weighted(A[b][sel], cloud[b][sel], w[b][sel])
+        H = (A[b][sel].double() - A[b][sel].double().mean(0)).T @ (cloud[b][sel].double() - cloud[b][sel].double().mean(0))
+        U, S, Vt = torch.linalg.svd(H)
+        flips += int(torch.linalg.det(Vt.T @ U.T) < 0)
+        if S[2] > 1e-9 * S[0] and b != 9:                          # unique optimum: compare the matrices
+            assert (poses[b].double() - ref).abs().max() < 1e-5, (b, (poses[b].double() - ref).abs().max())
+            assert (posesw[b].double() - refw).abs().max() < 1e-5
+        # in every case: a proper rotation that attains the optimum's residual
+        R = poses[b][:, :3].double()
+        assert (R @ R.T - torch.eye(3, dtype=torch.float64)).abs().max() < 1e-6 and abs(float(torch.linalg.det(R)) - 1) < 1e-6
+        res = lambda T: ((A[b][sel].double() @ T[:, :3].T + T[:, 3]) - cloud[b][sel].double()).pow(2).sum()
+        assert res(poses[b].double()) <= res(ref) * (1 + 1e-6) + 1e-9
+    assert flips >= 1, "the reflection fix must be exercised"
+    # the whole path on the device: frame_poses_device == the host list of frame_poses
+    rgbd, mesh, corr = synth.descriptors(2, 1024, M, 64, regime="planted", seed=5, sigma=0.3)
+    bank2 = matching.ModelBank(mesh.to(cuda), xyz[None].to(cuda))
+    cld = torch.stack([(xyz[corr[b]] @ torch.eye(3) + torch.tensor([0.0, 0.1 * b, 0.7])).T for b in range(2)])
+    seg = torch.stack([torch.zeros((2, 1024)), torch.ones((2, 1024))], dim=1)
+    pd = matching.frame_poses_device(cld.to(cuda), seg.to(cuda), rgbd.to(cuda), bank2)
+    assert pd.is_cuda and pd.shape == (2, 3, 4)
+    assert (pd.cpu()[:, :, :3] - torch.eye(3)).abs().max() < 1e-3 and (pd.cpu()[1, :, 3] - torch.tensor([0.0, 0.1, 0.7])).abs().max() < 1e-3
+    pw = matching.frame_poses_device(cld.to(cuda), seg.to(cuda), rgbd.to(cuda), bank2, weighted=True)
+    assert (pw.cpu() - pd.cpu()).abs().max() < 1e-3
+
+
 def test_seg_mask_matches_torch_argmax(cuda):
     """the foreground mask of evaluator.py:78,82 in one kernel (ties -> background, as torch.argmax
     returns the first maximal index)."""
