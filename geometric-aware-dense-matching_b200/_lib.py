@@ -45,10 +45,10 @@ SIGNATURES = {
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gadm_match_workspace_bytes": (c_size_t, []),
     "gadm_circle_loss_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
+                                     c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
     "gadm_circle_loss_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     c_int, c_int, c_int, c_int, c_int, c_float, c_float,
+                                     c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "gadm_kabsch_moments": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                     c_void_p, c_void_p]),

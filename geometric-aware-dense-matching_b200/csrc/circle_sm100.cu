@@ -26,6 +26,9 @@ struct CircleParams {
   const float* planes;      // [4, B, M] per-FRAME x / y / z planes (invisible vertices at 1e18) + squared positive radius
   const float* xyz;         // [n_obj, M, 3] model coordinates (ground-truth vertex lookup)
   const int64_t* match_idx; // [B, N], M = not on the model
+  const int64_t* match_idx2;// [B, N] or null.  Non-null selects the EXACT-COLUMN positive set of matching_loss_sys
+                            // (models/geoMatch.py:86-100): the positives of a row are the columns match_idx and
+                            // match_idx2 themselves (M = the pad column), no radius test
   const uint8_t* fg;        // [B, N] rows that take part (labels == 1)
   const int32_t* obj_id;
   float* loss;              // [B, N] softplus(LSE_p + LSE_n), 0 for rows outside fg
@@ -156,7 +159,11 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
     const size_t grow = size_t(b) * p.N + (row_ok ? row : 0);
     const float rs = row_ok ? p.rinv_rows[grow] : 0.f;
     const int64_t mi = row_ok ? p.match_idx[grow] : int64_t(p.M);
-    const bool in_mesh = mi >= 0 && mi < p.M;
+    const bool exact = p.match_idx2 != nullptr;
+    const int c1 = int(mi), c2 = exact && row_ok ? int(p.match_idx2[grow]) : -1;
+    // the pad column is a negative exactly for the rows that have a positive on the model (geoMatch.py:78); with the
+    // exact-column set it is a positive iff one of the two columns IS the pad column
+    const bool in_mesh = exact ? !(c1 == p.M || c2 == p.M) : (mi >= 0 && mi < p.M);
     // ground-truth vertex of the row; rows off the model sit at -1e18: no model vertex is ever within the radius
     float gx = -1e18f, gy = -1e18f, gz = -1e18f;
     if (in_mesh) {
@@ -203,7 +210,9 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
             // (A - B).pow(2).sum(-1) as the reference evaluates it: no FMA, left to right (basic_utils.py:88)
             const float dx = __fsub_rn(gx, xs[e]), dy = __fsub_rn(gy, ys[e]), dz = __fsub_rn(gz, zs[e]);
             const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            const bool pos = __fadd_rn(d2, 1e-7f) < r2s[e];                            // sqrt(D2 + 1e-7) < positive_r[j]
+            const int col = t * BN + sub * CS + c * 16 + j4 * 4 + e;
+            const bool pos = exact ? (col == c1 || col == c2)
+                                   : __fadd_rn(d2, 1e-7f) < r2s[e];                  // sqrt(D2 + 1e-7) < positive_r[j]
             const float ap = fmaxf(one_p - s, 0.f), an = fmaxf(s + m, 0.f);             // loss.py:479-480
             const float lp = -ap * (s - one_m) * gl, ln = an * (s - m) * gl;            // loss.py:488-489 (log2 units)
             const bool valid = c * 16 + j4 * 4 + e < ncols;
@@ -294,13 +303,14 @@ int circle_configure() {
 }
 
 int circle_launch(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols, const float* aux,
-                  const float* planes_frame, const int64_t* match_idx, const uint8_t* fg, const int32_t* obj_id, int B,
+                  const float* planes_frame, const int64_t* match_idx, const int64_t* match_idx2, const uint8_t* fg,
+                  const int32_t* obj_id, int B,
                   int N, int M, int Kp, int n_obj, float gamma, float margin, float* loss, float* lse_p,
                   float* lse_n, const float* w, float* G, int Mp, cudaStream_t stream) {
   CircleParams p;
   p.w = w; p.G = G; p.Mp = Mp;
   p.rinv_rows = rinv_rows; p.pad_sim = pad_sim; p.scales = aux_scales(aux, n_obj, M); p.planes = planes_frame;
-  p.xyz = aux_xyz(aux, n_obj, M); p.match_idx = match_idx; p.fg = fg; p.obj_id = obj_id;
+  p.xyz = aux_xyz(aux, n_obj, M); p.match_idx = match_idx; p.match_idx2 = match_idx2; p.fg = fg; p.obj_id = obj_id;
   p.loss = loss; p.lse_p = lse_p; p.lse_n = lse_n;
   p.B = B; p.N = N; p.M = M; p.n_obj = n_obj;
   p.gamma_log2e = gamma * 1.4426950408889634f; p.margin = margin;

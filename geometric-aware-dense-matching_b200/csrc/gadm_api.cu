@@ -233,7 +233,8 @@ int gadm_match_fwd_sel(const void* rows, const float* rinv_rows, const float* pa
 }
 
 int gadm_circle_loss_fwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
-                         const float* aux, const float* planes_frame, const int64_t* match_idx, const uint8_t* fg,
+                         const float* aux, const float* planes_frame, const int64_t* match_idx, const int64_t* match_idx2,
+                         const uint8_t* fg,
                          const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma, float margin,
                          float* loss, float* lse_p, float* lse_n, gadm_stream_t stream) {
   GADM_REQUIRE_INIT();
@@ -246,12 +247,12 @@ int gadm_circle_loss_fwd(const void* rows, const float* rinv_rows, const float* 
   // 2^logit is summed without a running maximum: |logit| <= gamma (2 + m)(2 - m) must stay inside the fp32 range
   if (gamma * (2.f + margin) * (2.f - margin) * 1.4426950408889634f > 120.f) return GADM_ERR_UNSUPPORTED;
   if (!aligned16(rows) || !aligned16(cols) || !aligned16(aux) || !aligned16(planes_frame)) return GADM_ERR_ALIGN;
-  return circle_launch(rows, rinv_rows, pad_sim, cols, aux, planes_frame, match_idx, fg, obj_id, B, N, M, Kp, n_obj,
-                       gamma, margin, loss, lse_p, lse_n, nullptr, nullptr, 0, (cudaStream_t)stream);
+  return circle_launch(rows, rinv_rows, pad_sim, cols, aux, planes_frame, match_idx, match_idx2, fg, obj_id, B, N, M, Kp,
+                       n_obj, gamma, margin, loss, lse_p, lse_n, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
 
 int gadm_circle_loss_bwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
-                         const float* aux, const float* planes_frame, const int64_t* match_idx,
+                         const float* aux, const float* planes_frame, const int64_t* match_idx, const int64_t* match_idx2,
                          const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma, float margin,
                          const float* lse_p, const float* lse_n, const float* w, float* G, int Mp,
                          gadm_stream_t stream) {
@@ -266,8 +267,8 @@ int gadm_circle_loss_bwd(const void* rows, const float* rinv_rows, const float* 
   if (gamma * (2.f + margin) * (2.f - margin) * 1.4426950408889634f > 120.f) return GADM_ERR_UNSUPPORTED;
   if (!aligned16(rows) || !aligned16(cols) || !aligned16(aux) || !aligned16(planes_frame) || !aligned16(G))
     return GADM_ERR_ALIGN;
-  return circle_launch(rows, rinv_rows, pad_sim, cols, aux, planes_frame, match_idx, nullptr, obj_id, B, N, M, Kp, n_obj,
-                       gamma, margin, nullptr, const_cast<float*>(lse_p), const_cast<float*>(lse_n), w, G, Mp,
+  return circle_launch(rows, rinv_rows, pad_sim, cols, aux, planes_frame, match_idx, match_idx2, nullptr, obj_id, B, N, M,
+                       Kp, n_obj, gamma, margin, nullptr, const_cast<float*>(lse_p), const_cast<float*>(lse_n), w, G, Mp,
                        (cudaStream_t)stream);
 }
 

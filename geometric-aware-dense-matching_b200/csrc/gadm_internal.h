@@ -40,7 +40,8 @@ int match_launch(const void* rows, const float* rinv_rows, const float* pad_sim,
                  cudaStream_t stream);
 size_t match_workspace_bytes();
 int circle_launch(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols, const float* aux,
-                  const float* planes_frame, const int64_t* match_idx, const uint8_t* fg, const int32_t* obj_id, int B,
+                  const float* planes_frame, const int64_t* match_idx, const int64_t* match_idx2, const uint8_t* fg,
+                  const int32_t* obj_id, int B,
                   int N, int M, int Kp, int n_obj, float gamma, float margin, float* loss, float* lse_p,
                   float* lse_n, const float* w, float* G, int Mp, cudaStream_t stream);
 

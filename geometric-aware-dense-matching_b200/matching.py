@@ -12,6 +12,7 @@
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import ops
 from ._lib import MATCH_MODES, OPERAND_MODES, PAD_MODES
@@ -108,7 +109,7 @@ class _CircleMatchLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, rgbd, mesh, model_xyz, labels, match_idx, visible_flag, sel, oid, radius, gamma, margin, pad_mode,
-                grad_gemm):
+                grad_gemm, match_idx2):
         B, d, N = rgbd.shape
         dev = rgbd.device
         rows, rinv, pad_sim = ops.prep_rows(rgbd.contiguous().float(), OPERAND_MODES["bf16"], PAD_MODES[pad_mode])
@@ -120,13 +121,15 @@ class _CircleMatchLoss(torch.autograd.Function):
         planes[3] = radius * radius                                                  # [B, M] squared positive radius
         fg = (labels.to(dev) == 1).to(torch.uint8).contiguous()
         mi = match_idx.to(dev).long().contiguous()
-        loss, lse_p, lse_n = ops.circle_loss_fwd(rows, rinv, pad_sim, cols, aux, planes, mi, fg, oid, gamma, margin)
+        mi2 = None if match_idx2 is None else match_idx2.to(dev).long().contiguous()
+        loss, lse_p, lse_n = ops.circle_loss_fwd(rows, rinv, pad_sim, cols, aux, planes, mi, fg, oid, gamma, margin, mi2)
         cnt = fg.sum(dim=1)
         use = cnt >= 3                                                               # geoMatch.py:128-129
         n_use = use.sum().clamp(min=1)
         row_w = (fg * use[:, None]).float() / (cnt.clamp(min=1)[:, None] * n_use)    # d total / d loss_row
         total = (loss * row_w).sum()
         ctx.save_for_backward(rows, rinv, pad_sim, cols, aux, planes, mi, sel, lse_p, lse_n, row_w)
+        ctx.mi2 = mi2
         ctx.oid, ctx.cfg, ctx.n_obj, ctx.grad_gemm = oid, (gamma, margin, pad_mode), mesh.shape[0], grad_gemm
         ctx.mark_non_differentiable(loss, lse_p, lse_n)
         return total, loss, lse_p, lse_n
@@ -139,7 +142,7 @@ class _CircleMatchLoss(torch.autograd.Function):
         n_obj, M, _ = cols.shape
         w = (torch.sigmoid(lse_p + lse_n) * row_w * g_total).contiguous()            # softplus' = sigmoid
         G = ops.circle_loss_bwd(rows, rinv, pad_sim, cols, aux, planes, mi, ctx.oid, gamma, margin, lse_p, lse_n,
-                                w)                                                   # [B, N, M + 8]
+                                w, ctx.mi2)                                          # [B, N, M + 8]
         f_hat = rows.float() * rinv[..., None]                                       # [B, N, d]
         scale = aux[: n_obj * M].view(n_obj, M, 1)
         m_hat = torch.zeros((n_obj, M + 8, d), dtype=torch.float32, device=rows.device)
@@ -161,7 +164,7 @@ class _CircleMatchLoss(torch.autograd.Function):
         mh = m_hat[:, :M]
         d_m = (d_mhat - (d_mhat * mh).sum(-1, keepdim=True) * mh) * scale
         return (d_f.transpose(1, 2).contiguous(), d_m.transpose(1, 2).contiguous(), None, None, None, None, None, None,
-                None, None, None, None, None)
+                None, None, None, None, None, None)
 
 
 def dgcnn_positive_radius(model_xyz, RT, positive_r):
@@ -172,7 +175,7 @@ def dgcnn_positive_radius(model_xyz, RT, positive_r):
 
 
 def circle_match_loss(rgbd, mesh, labels, match_idx, visible_flag, positive_r, model_xyz=None, obj_id=None,
-                      gamma=16.0, margin=0.2, return_rows=False, pad_mode="minus_one", grad_gemm="fp32"):
+                      gamma=16.0, margin=0.2, return_rows=False, pad_mode="minus_one", grad_gemm="fp32", sys_idx=None):
     """The matching loss of GeoMatch.pointwise_feature_matching (models/geoMatch.py:102-157 + :55-83 +
     CircleLoss.forward, models/loss.py:475-490) for a whole batch in one fused launch, differentiable with respect
     to rgbd and mesh.
@@ -184,6 +187,9 @@ def circle_match_loss(rgbd, mesh, labels, match_idx, visible_flag, positive_r, m
     (dgcnn_positive_radius: the DGCNN variant, which also uses pad_mode="e0" and labels = x['origin_labels']).
     grad_gemm: "fp32" (default) or "tf32" for the two cuBLAS gradient GEMMs of the backward pass (tf32: ~3x faster
     backward, gradient error ~5e-4 of the largest entry instead of ~1e-6).
+    sys_idx (int [>= N], or None): the symmetry-aware variant GeoMatch.matching_loss_sys (models/geoMatch.py:86-100, used
+    when model_emb.sys_corr_idx is set, :138-141): the positives of scene point n are exactly the two columns
+    match_idx[n] and match_idx[sys_idx[n]] -- no radius, no visibility (positive_r / visible_flag are ignored).
     Returns the scalar the reference returns: the mean over samples with >= 3 foreground rows of the mean row loss
     (0 if there is none); return_rows=True adds the per-row (loss, lse_p, lse_n) tensors."""
     if isinstance(mesh, ModelBank):
@@ -207,11 +213,19 @@ def circle_match_loss(rgbd, mesh, labels, match_idx, visible_flag, positive_r, m
     sel = oid.long() if oid is not None else (torch.arange(B, device=dev) if n_obj == B
                                               else torch.zeros(B, dtype=torch.long, device=dev))
     M = mesh.shape[-1]
+    mi2 = None
+    if sys_idx is not None:                                                   # geoMatch.py:92: match_idx[sys_cor[idxs]]
+        N = rgbd.shape[2]
+        sidx = torch.as_tensor(sys_idx, device=dev).long()[:N]
+        mi2 = match_idx.to(dev).long()[:, sidx]
+        positive_r = 0.0 if positive_r is None else positive_r
+        if visible_flag is None:
+            visible_flag = torch.ones((B, M), dtype=torch.uint8, device=dev)
     radius = (positive_r.to(dev).float() if torch.is_tensor(positive_r) else
               torch.full((1, 1), float(positive_r), device=dev)).expand(B, M)
     total, loss, lse_p, lse_n = _CircleMatchLoss.apply(rgbd, mesh, model_xyz.contiguous().float().to(dev), labels,
                                                        match_idx, visible_flag, sel, oid, radius, float(gamma),
-                                                       float(margin), pad_mode, grad_gemm)
+                                                       float(margin), pad_mode, grad_gemm, mi2)
     return (total, loss, lse_p, lse_n) if return_rows else total
 
 
@@ -265,18 +279,59 @@ def frame_poses(cld, seg, rgbd, bank, obj_id=None, det=None, min_pts=5, weighted
     return list(poses.cpu().numpy())
 
 
-def cal_frame_poses(item, bank):
+class ModelContainer:
+    """The evaluator's module-level model store (evaluator.py:28-58): model point sets per object id, in metres
+    (np.load(...)[:MODEL_PT_NUM, :3] / 1000 there), plus the optional symmetric correspondence indices.  The
+    reference builds it from its dataset config at import time (`model3ds = ModelContainer(ycbv_cfg)`); here the
+    caller hands over the arrays (mesh files are outside this package): set_model_container(ModelContainer({...}))."""
+
+    def __init__(self, models_3d, sys_corr_idx=None, feat_dim=None):
+        self.models_3d = {int(k): np.asarray(v, dtype=np.float32)[:, :3] for k, v in models_3d.items()}
+        self.sys_corr_idx = {} if sys_corr_idx is None else {str(k): v for k, v in sys_corr_idx.items()}
+        self.feat_dim = feat_dim
+        self._dev = {}
+
+    def xyz(self, cls_id, device):
+        key = (int(cls_id), str(device))
+        if key not in self._dev:
+            self._dev[key] = torch.from_numpy(self.models_3d[int(cls_id)]).to(device)
+        return self._dev[key]
+
+
+model3ds = None          # evaluator.py:58
+
+
+def set_model_container(container):
+    global model3ds
+    model3ds = container
+
+
+def cal_frame_poses(item, bank=None):
     """Drop-in for evaluator.cal_frame_poses(item) (evaluator.py:60-102); item =
-    (cld [>=3,N], seg_features [2,N], mesh_features (unused: the bank holds them), rgbd_features [d,N],
-     cls_id, det).  `bank` is indexed by obj_id = cls_id when it holds more than one object."""
-    cld, seg_features, _mesh, rgbd_features, cls_id, det = item
+    (cld [>=3,N], seg_features [2,N], mesh_features [d,M], rgbd_features [d,N], cls_id, det) -> numpy [3,4].
+
+    With ONE argument it behaves as the reference does: the model points come from the module-level container
+    (`model3ds.models_3d[cls_id]`, evaluator.py:99; install it with set_model_container) and the model descriptors are
+    the item's own mesh_features.  With a prepared ModelBank (second argument) the item's mesh_features are ignored and
+    cls_id selects the bank slot when the bank holds more than one object."""
+    cld, seg_features, mesh_features, rgbd_features, cls_id, det = item
     if not det:
         return sentinel_pose()
-    oid = None if bank.n_obj == 1 else [int(cls_id)]
+    cid = int(cls_id.item()) if torch.is_tensor(cls_id) else int(cls_id)
+    if bank is None:
+        if model3ds is None:
+            raise RuntimeError("cal_frame_poses(item) needs the module-level model container "
+                               "(matching.set_model_container(ModelContainer({cls_id: xyz})), evaluator.py:28-58)")
+        xyz = model3ds.xyz(cid, rgbd_features.device)
+        M = xyz.shape[0]
+        bank = ModelBank(mesh_features[:, :M].contiguous(), xyz)          # evaluator.py:90 normalises mesh_features
+        oid = None
+    else:
+        oid = None if bank.n_obj == 1 else [cid]
     return frame_poses(cld[None], seg_features[None], rgbd_features[None], bank, obj_id=oid, det=[det])[0]
 
 
-class GeoMatch(nn.Module):
+class GeoMatchHead(nn.Module):
     """The reference's GeoMatch forward contract (models/geoMatch.py:159-200, geoMatch_DGCNN.py:138-183) around
     pluggable embedding networks (the FFB6D / SplineCNN / DGCNN backbones are out of scope).
 
@@ -334,3 +389,179 @@ class GeoMatch(nn.Module):
                                       gamma=self.gamma, operand_mode=self.operand_mode)
             end_points.update(match_idx=idx, match_sim=sim, match_weight=w, match_xyz=sxyz)
         return end_points
+
+
+# ------------------------------------------------------------------------------------------------ reference constructors
+class _BN1d(nn.Sequential):
+    """models/pytorch_utils.py:42-54 (BatchNorm1d wrapper: child 'bn', weight 1, bias 0)."""
+
+    def __init__(self, n):
+        super().__init__()
+        self.add_module("bn", nn.BatchNorm1d(n))
+        nn.init.constant_(self[0].weight, 1.0)
+        nn.init.constant_(self[0].bias, 0)
+
+
+def _conv1d(in_size, out_size, bn=False, activation=True, bias=True):
+    """models/pytorch_utils.py:70-160 (Conv1d = _ConvBase): children 'conv' [, 'normlayer'] [, 'activation'], kernel 1,
+    kaiming-normal weight, zero bias, no bias next to a batch norm -- the same module names, so the reference's
+    checkpoints load into it."""
+    m = nn.Sequential()
+    conv = nn.Conv1d(in_size, out_size, kernel_size=1, bias=bias and not bn)
+    nn.init.kaiming_normal_(conv.weight)
+    if conv.bias is not None:
+        nn.init.constant_(conv.bias, 0)
+    m.add_module("conv", conv)
+    if bn:
+        m.add_module("normlayer", _BN1d(out_size))
+    if activation:
+        m.add_module("activation", nn.ReLU(inplace=True))
+    return m
+
+
+def _seq(in_channels, layers):
+    """models/pytorch_utils.py:272-316 (Seq(...).conv1d(...)...): children '0', '1', ..."""
+    m, c = nn.Sequential(), in_channels
+    for i, (out, kw) in enumerate(layers):
+        m.add_module(str(i), _conv1d(c, out, **kw))
+        c = out
+    return m
+
+
+class FocalLoss(nn.Module):
+    """models/loss.py:15-46 with alpha=None, size_average=True (the reference uses FocalLoss(gamma=2),
+    geoMatch.py:29): mean of -(1 - p_t)^gamma log p_t with p_t detached."""
+
+    def __init__(self, gamma=0):
+        super().__init__()
+        self.gamma = gamma
+
+    def forward(self, input, target):
+        logp = F.log_softmax(input.transpose(1, 2).reshape(-1, input.size(1)), dim=-1)
+        logpt = logp.gather(1, target.reshape(-1, 1).long()).view(-1)
+        pt = logpt.detach().exp()
+        return (-1 * (1 - pt) ** self.gamma * logpt).mean()
+
+
+class AutomaticWeightedLoss(nn.Module):
+    """models/loss.py:496-516: sum_i 0.5 / p_i^2 * loss_i + log(1 + p_i^2) with learnable p (ones)."""
+
+    def __init__(self, num=2):
+        super().__init__()
+        self.params = nn.Parameter(torch.ones(num))
+
+    def forward(self, *x):
+        return sum(0.5 / (self.params[i] ** 2) * loss + torch.log(1 + self.params[i] ** 2) for i, loss in enumerate(x))
+
+
+class GeoMatch(GeoMatchHead):
+    """GeoMatch(cfg, cls_id) -- the reference's constructor (models/geoMatch.py:13-52) and forward contract
+    (:159-200).  cfg['feat_dim'], cfg['neighbor_dis_th'], cfg['model_d'][cls_id] are read as there; the heads
+    (seg_layer, feature_encoding_layer, normalize_feature_layer) are built with the reference's layer stack and module
+    names, so its state_dict keys match.  The two backbones are outside this package: pass them as
+    pcd_emb= / model_emb= (or cfg['pcd_emb'] / cfg['model_emb']); model_emb() -> [d, M], with the model points in
+    model_emb._buffers['xyz'] and, for symmetric objects, model_emb.sys_corr_idx / model_emb.sys_idx as in the reference
+    (the symmetry-aware loss of :138-141 is then used)."""
+
+    def __init__(self, cfg, cls_id, pcd_emb=None, model_emb=None, match_in_forward=False, gamma=16.0,
+                 operand_mode="bf16"):
+        feat_dim = cfg["feat_dim"]
+        positive_r = cfg["neighbor_dis_th"] * cfg["model_d"][cls_id] / 1000.0            # geoMatch.py:24
+        pcd_emb = pcd_emb if pcd_emb is not None else cfg.get("pcd_emb")
+        model_emb = model_emb if model_emb is not None else cfg.get("model_emb")
+        if pcd_emb is None or model_emb is None:
+            raise NotImplementedError("the FFB6D / SplineCNN embedding networks are outside this package: pass "
+                                      "pcd_emb= and model_emb= (or cfg['pcd_emb'] / cfg['model_emb'])")
+        bn = dict(bn=True)
+        seg_layer = _seq(feat_dim, [(128, bn), (128, bn), (128, bn), (2, dict(activation=False))])          # :33-39
+        feature_encoding_layer = _seq(self._enc_in(feat_dim), [(128, bn), (128, bn), (128, bn),
+                                                               (feat_dim, dict(activation=False, bias=False))])   # :40-46
+        normalize_feature_layer = _conv1d(feat_dim, feat_dim, bn=True)                                      # :48-51
+        xyz = getattr(model_emb, "_buffers", {}).get("xyz")
+        super().__init__(pcd_emb, model_emb, feature_encoding_layer, seg_layer, normalize_feature_layer,
+                         model_xyz=None, match_in_forward=match_in_forward, gamma=gamma, operand_mode=operand_mode,
+                         positive_r=positive_r, seg_loss_func=FocalLoss(gamma=2), awl=AutomaticWeightedLoss(2))
+        self.feat_dim, self.cls_id = feat_dim, cls_id
+        self._xyz_from_emb = xyz is not None
+
+    @staticmethod
+    def _enc_in(feat_dim):
+        return 128                                                                      # pt_utils.Seq(128), :41
+
+    def _model_xyz(self):
+        return self.model_emb._buffers["xyz"].contiguous() if self._xyz_from_emb else self.xyz       # :148
+
+    def _pcd(self, inputs):
+        return self.pcd_emb(inputs)                                                     # :178
+
+    def _mesh_out(self, mesh_features):
+        return mesh_features.unsqueeze(0)                                               # :184  'mesh' [1, d, M]
+
+    def _match_loss(self, rgbd_features, mesh_features, inputs):
+        sys_idx = self.model_emb.sys_idx if getattr(self.model_emb, "sys_corr_idx", None) is not None else None
+        return circle_match_loss(rgbd_features, mesh_features.reshape(1, *mesh_features.shape[-2:]), inputs['labels'],
+                                 inputs['match_idx'], inputs.get('visible_flag'), self.positive_r,
+                                 model_xyz=self._model_xyz(), gamma=16.0, margin=0.2, sys_idx=sys_idx)   # :27, :81, :98
+
+    def forward(self, inputs, end_points=None):
+        if not end_points:
+            end_points = {}
+        rgbd_emb = self._pcd(inputs)
+        mesh_features = self.model_emb()                                                # :179
+        rgbd_features = self.feature_encoding_layer(rgbd_emb)                           # :180
+        rgbd_emb = rgbd_emb + self.normalize_feature_layer(rgbd_features)               # :181-182
+        seg_features = self.seg_layer(rgbd_emb)                                         # :183
+        mesh_features = self._mesh_out(mesh_features)
+        if self.training:                                                               # :188-195
+            match_loss = self._match_loss(rgbd_features, mesh_features, inputs)
+            seg_loss = self.seg_loss_func(seg_features, inputs[self._label_key])
+            end_points['loss'] = self.awl(seg_loss, match_loss)
+            end_points['seg_loss'] = seg_loss
+            end_points['match_loss'] = match_loss
+        end_points['seg'] = seg_features
+        end_points['mesh'] = mesh_features
+        end_points['rgbd'] = rgbd_features
+        if self.match_in_forward and not self.training:
+            mask = ops.seg_mask(seg_features.detach().contiguous().float())
+            idx, sim, w, sxyz = match(rgbd_features.detach(), mesh_features.detach().reshape(1, *mesh_features.shape[-2:]),
+                                      self._model_xyz(), mask=mask, gamma=self.gamma, operand_mode=self.operand_mode)
+            end_points.update(match_idx=idx, match_sim=sim, match_weight=w, match_xyz=sxyz)
+        return end_points
+
+    _label_key = 'labels'
+
+
+class GeoMatchDGCNN(GeoMatch):
+    """models/geoMatch_DGCNN.py:11-183: the same head on DGCNN embeddings.  Differences kept: positive_r = 3 (a
+    per-vertex radius positive_r / 1000 * camera depth, :22, :64-65), feature_encoding_layer starts from feat_dim
+    (:38), the point embedding takes inputs['cld_rgb_nrm'] (:157-159), the model points are channels 0..2 of
+    model_emb._buffers['mesh'] (:111), the pad column is e0 (:95-98), rows are picked by x['origin_labels'] (:107),
+    and 'mesh' is returned as model_emb() gives it -- NOT unsqueezed (:160, :180)."""
+
+    def __init__(self, cfg, cls_id, pcd_emb=None, model_emb=None, match_in_forward=False, gamma=16.0,
+                 operand_mode="bf16"):
+        cfg = dict(cfg, neighbor_dis_th=0.0, model_d={cls_id: 0.0})
+        super().__init__(cfg, cls_id, pcd_emb, model_emb, match_in_forward, gamma, operand_mode)
+        self.positive_r = 3                                                             # :22
+
+    @staticmethod
+    def _enc_in(feat_dim):
+        return feat_dim                                                                 # pt_utils.Seq(self.feat_dim), :38
+
+    def _model_xyz(self):
+        return self.model_emb._buffers['mesh'][0, :3].t().contiguous()                  # :111
+
+    def _pcd(self, inputs):
+        return self.pcd_emb(inputs['cld_rgb_nrm'])                                      # :157-159
+
+    def _mesh_out(self, mesh_features):
+        return mesh_features                                                            # :160, :180
+
+    def _match_loss(self, rgbd_features, mesh_features, inputs):
+        xyz = self._model_xyz()
+        radius = dgcnn_positive_radius(xyz, inputs['RT'].to(xyz.device).float(), self.positive_r)    # :64-65
+        return circle_match_loss(rgbd_features, mesh_features.reshape(1, *mesh_features.shape[-2:]),
+                                 inputs['origin_labels'], inputs['match_idx'], inputs['visible_flag'], radius,
+                                 model_xyz=xyz, gamma=16.0, margin=0.2, pad_mode="e0")
+
+    _label_key = 'labels'

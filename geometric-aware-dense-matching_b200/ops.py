@@ -267,7 +267,7 @@ def _(rows, rinv, pad_sim, cols, aux, mask, obj_id, gamma, pad_mode, mode):
 def circle_loss_fwd(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tensor, cols: torch.Tensor,
                     aux: torch.Tensor, planes_frame: torch.Tensor, match_idx: torch.Tensor,
                     fg: torch.Tensor | None, obj_id: torch.Tensor | None, gamma: float,
-                    margin: float) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                    margin: float, match_idx2: torch.Tensor | None = None) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Per-row CircleLoss of the similarity with the padded model (gadm_circle_loss_fwd): (loss, lse_p, lse_n).
     planes_frame [4, B, M]: x / y / z of the vertices (invisible ones at 1e18) and their squared positive radius."""
     _need(rows, torch.bfloat16, "rows"); _need(cols, torch.bfloat16, "cols")
@@ -287,6 +287,10 @@ def circle_loss_fwd(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tenso
             raise ValueError("fg must be [B, N]")
     if obj_id is not None:
         _need(obj_id, torch.int32, "obj_id")
+    if match_idx2 is not None:                     # exact-column positives (matching_loss_sys, geoMatch.py:86-100)
+        _need(match_idx2, torch.int64, "match_idx2")
+        if tuple(match_idx2.shape) != (B, N):
+            raise ValueError("match_idx2 must be [B, N]")
     dev = rows.device
     loss = torch.empty((B, N), dtype=torch.float32, device=dev)
     lse_p = torch.empty((B, N), dtype=torch.float32, device=dev)
@@ -294,14 +298,14 @@ def circle_loss_fwd(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tenso
     lib = _lib_for(rows)
     with torch.cuda.device(dev):
         _lib.check(lib.gadm_circle_loss_fwd(_ptr(rows), _ptr(rinv), _ptr(pad_sim), _ptr(cols), _ptr(aux),
-                                            _ptr(planes_frame), _ptr(match_idx), _ptr(fg), _ptr(obj_id), B, N, M, kp,
-                                            n_obj, float(gamma), float(margin), _ptr(loss), _ptr(lse_p),
+                                            _ptr(planes_frame), _ptr(match_idx), _ptr(match_idx2), _ptr(fg), _ptr(obj_id),
+                                            B, N, M, kp, n_obj, float(gamma), float(margin), _ptr(loss), _ptr(lse_p),
                                             _ptr(lse_n), _stream()), "gadm_circle_loss_fwd")
     return loss, lse_p, lse_n
 
 
 @circle_loss_fwd.register_fake
-def _(rows, rinv, pad_sim, cols, aux, planes_frame, match_idx, fg, obj_id, gamma, margin):
+def _(rows, rinv, pad_sim, cols, aux, planes_frame, match_idx, fg, obj_id, gamma, margin, match_idx2=None):
     B, N, _ = rows.shape
     return (rows.new_empty((B, N), dtype=torch.float32), rows.new_empty((B, N), dtype=torch.float32),
             rows.new_empty((B, N), dtype=torch.float32))
@@ -311,7 +315,7 @@ def _(rows, rinv, pad_sim, cols, aux, planes_frame, match_idx, fg, obj_id, gamma
 def circle_loss_bwd(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tensor, cols: torch.Tensor,
                     aux: torch.Tensor, planes_frame: torch.Tensor, match_idx: torch.Tensor,
                     obj_id: torch.Tensor | None, gamma: float, margin: float, lse_p: torch.Tensor,
-                    lse_n: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+                    lse_n: torch.Tensor, w: torch.Tensor, match_idx2: torch.Tensor | None = None) -> torch.Tensor:
     """dL/dsim [B, N, M + 8] (column M = pad column, the rest of the padding 0) for per-row upstream gradients w
     (gadm_circle_loss_bwd)."""
     _need(rows, torch.bfloat16, "rows"); _need(cols, torch.bfloat16, "cols")
@@ -326,14 +330,15 @@ def circle_loss_bwd(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tenso
     lib = _lib_for(rows)
     with torch.cuda.device(rows.device):
         _lib.check(lib.gadm_circle_loss_bwd(_ptr(rows), _ptr(rinv), _ptr(pad_sim), _ptr(cols), _ptr(aux),
-                                            _ptr(planes_frame), _ptr(match_idx), _ptr(obj_id), B, N, M, kp, n_obj,
-                                            float(gamma), float(margin), _ptr(lse_p), _ptr(lse_n),
+                                            _ptr(planes_frame), _ptr(match_idx), _ptr(match_idx2), _ptr(obj_id), B, N, M,
+                                            kp, n_obj, float(gamma), float(margin), _ptr(lse_p), _ptr(lse_n),
                                             _ptr(w), _ptr(G), Mp, _stream()), "gadm_circle_loss_bwd")
     return G
 
 
 @circle_loss_bwd.register_fake
-def _(rows, rinv, pad_sim, cols, aux, planes_frame, match_idx, obj_id, gamma, margin, lse_p, lse_n, w):
+def _(rows, rinv, pad_sim, cols, aux, planes_frame, match_idx, obj_id, gamma, margin, lse_p, lse_n, w,
+      match_idx2=None):
     B, N, _ = rows.shape
     return rows.new_empty((B, N, cols.shape[1] + 8), dtype=torch.float32)
 

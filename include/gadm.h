@@ -179,11 +179,15 @@ int gadm_pack_match_outputs(const int64_t* idx, const float* max_sim, const floa
  *   match_idx [B, N] int64: ground-truth vertex of every row, M = off the model (pad column is its only positive)
  *   fg [B, N] uint8 or NULL: rows that take part (labels == 1); the others get 0
  *   positive j for row i: |xyz[match_idx[i]] - planes_frame[0:3, b, j]|^2 + 1e-7 < planes_frame[3, b, j]   (basic_utils.py:86-89)
+ *   match_idx2 [B, N] int64 or NULL.  Non-NULL selects the symmetry-aware positives of GeoMatch.matching_loss_sys
+ *                (models/geoMatch.py:86-100): the positives of row i are exactly the columns match_idx[i] and
+ *                match_idx2[i] (M = the pad column); planes_frame is not consulted for them
  *   loss [B, N] = softplus(LSE_p + LSE_n) per row; lse_p / lse_n [B, N]: the two natural-log LSEs (what a backward
  *   pass needs).  The mean over rows / samples (geoMatch.py:150-156) is left to the caller.
  * gamma (2 + margin)(2 - margin) log2(e) must be <= 120 (gamma = 16, margin = 0.2: 91).                          */
 int gadm_circle_loss_fwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
-                         const float* aux, const float* planes_frame, const int64_t* match_idx, const uint8_t* fg,
+                         const float* aux, const float* planes_frame, const int64_t* match_idx, const int64_t* match_idx2,
+                         const uint8_t* fg,
                          const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma, float margin,
                          float* loss, float* lse_p, float* lse_n, gadm_stream_t stream);
 
@@ -195,7 +199,7 @@ int gadm_circle_loss_fwd(const void* rows, const float* rinv_rows, const float* 
  *   pad column, columns M + 1 .. Mp - 1 = 0.  ap / an are constants as in the reference (detach, loss.py:479-480).
  * The two gradient GEMMs that follow (G M^ and G^T F^) are plain library GEMMs on the caller's side.                */
 int gadm_circle_loss_bwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
-                         const float* aux, const float* planes_frame, const int64_t* match_idx,
+                         const float* aux, const float* planes_frame, const int64_t* match_idx, const int64_t* match_idx2,
                          const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma, float margin,
                          const float* lse_p, const float* lse_n, const float* w, float* G, int Mp,
                          gadm_stream_t stream);

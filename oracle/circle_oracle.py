@@ -89,3 +89,32 @@ def batch_loss(rgbd, mesh_feature, labels, match_idx, mesh_xyz, vis_flags, posit
                                     pad)
         per.append(rows.mean())
     return torch.stack(per).mean() if per else torch.tensor(0.0)                 # :151-156
+
+
+def sys_positive_mask(match_idx, idxs, sys_idx, M):
+    """GeoMatch.matching_loss_sys (models/geoMatch.py:86-100): for the selected rows idxs, the positives are the columns
+    match_idx[idxs] and match_idx[sys_idx[idxs]] of the [len(idxs), M + 1] similarity."""
+    n = len(idxs)
+    rows = torch.arange(n)
+    rows = torch.cat((rows, rows), dim=0)                                        # :91-92
+    cols = torch.cat((match_idx[idxs], match_idx[sys_idx[idxs]]), dim=0).long()  # :93
+    mask = torch.zeros((n, M + 1), dtype=torch.bool)
+    mask.index_put_((rows, cols), torch.tensor(True))                            # :95-96
+    return mask
+
+
+def batch_loss_sys(rgbd, mesh_feature, labels, match_idx, sys_idx, m=0.2, gamma=16.0):
+    """pointwise_feature_matching (models/geoMatch.py:102-157) on the sys_corr_idx branch (:138-141)."""
+    import torch.nn.functional as F
+    d, M = mesh_feature.shape[-2:]
+    mesh = mesh_feature.reshape(d, M)
+    padded = F.normalize(torch.cat([mesh, -torch.ones((d, 1))], dim=1), p=2, dim=0)   # :117-119
+    losses = []
+    for b in range(rgbd.shape[0]):
+        idxs = torch.where(labels[b] == 1)[0]                                    # :127
+        if len(idxs) < 3:
+            continue
+        sim = F.normalize(rgbd[b].t()[idxs], p=2, dim=1) @ padded                # :131-136
+        mask = sys_positive_mask(match_idx[b].long(), idxs, sys_idx.long(), M)
+        losses.append(circle_rows(sim, mask, m, gamma)[0].mean())
+    return torch.stack(losses).mean() if losses else torch.tensor(0.0)

@@ -13,6 +13,7 @@
   pointops_golden.npz  lib/pointops/functions/pointops.py: KNNQueryNaive.forward (:396-426, pure torch, the reference's
                      own oracle for its CUDA knnquery) and QueryAndGroup.forward (:548-585) EXECUTED from the reference
                      source text (its `grouping` CUDA call replaced by the gather its docstring :151-155 specifies)
+  heads_golden.json  state_dict keys / shapes of the GeoMatch head stacks built with the reference's models/pytorch_utils.py
 Nothing from the reference is copied into the repo: only inputs and numeric outputs are stored."""
 import os
 import sys
@@ -216,9 +217,55 @@ def make_circle():
     finally:
         torch.Tensor.cuda = real_cuda
     out.update(RT=RT.numpy(), dgcnn_positive_r=np.float32(pos_r_dgcnn), dgcnn_ref_total=np.float32(float(total2)))
+
+    # the symmetry-aware branch (models/geoMatch.py:138-141 -> matching_loss_sys :86-100): model_emb.sys_corr_idx set,
+    # model_emb.sys_idx indexed by the selected scene-point ids exactly as the reference does
+    exec(ref_lines("models/geoMatch.py", 86, 100), ns)
+    sys_idx = torch.randint(0, N, (N,), generator=g)
+
+    class _Emb3:
+        sys_corr_idx = True
+        _buffers = {"xyz": xyz}
+    _Emb3.sys_idx = sys_idx
+    stub3 = types.SimpleNamespace(feat_dim=d, positive_r=positive_r, circle_loss=ref_loss.CircleLoss(16), model_emb=_Emb3())
+    stub3.matching_loss_sys = types.MethodType(ns["matching_loss_sys"], stub3)
+    real_tensor = torch.tensor
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        total3 = ns["pointwise_feature_matching"](stub3, rgbd.clone(), mesh.clone(), x)
+    finally:
+        torch.Tensor.cuda = real_cuda
+    out.update(sys_idx=sys_idx.numpy(), sys_ref_total=np.float32(float(total3)))
+    print("circle golden (matching_loss_sys): total", float(total3))
     print("circle golden (DGCNN variant): total", float(total2))
     np.savez_compressed(os.path.join(HERE, "circle_golden.npz"), **out)
     print("circle golden: total", float(total), "per sample", per_sample)
+
+
+def make_heads():
+    """The head stacks of GeoMatch.__init__ (models/geoMatch.py:33-51, geoMatch_DGCNN.py:30-48) built with the reference's
+    own models/pytorch_utils.py: state_dict keys and shapes -> heads_golden.json (what a checkpoint of the reference
+    holds for the heads)."""
+    import importlib.util, json
+    spec = importlib.util.spec_from_file_location("ref_pt_utils", os.path.join(REF, "models/pytorch_utils.py"))
+    pt_utils = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pt_utils)
+    out = {}
+    for variant, enc_in in (("geoMatch", 128), ("geoMatch_DGCNN", 128)):
+        feat_dim = 128
+        seg = (pt_utils.Seq(feat_dim).conv1d(128, bn=True).conv1d(128, bn=True).conv1d(128, bn=True)
+               .conv1d(2, activation=None))
+        enc = (pt_utils.Seq(enc_in).conv1d(128, bn=True).conv1d(128, bn=True).conv1d(128, bn=True)
+               .conv1d(feat_dim, activation=None, bias=False))
+        nrm = pt_utils.Conv1d(feat_dim, feat_dim, bn=True)
+        keys = {}
+        for name, mod in (("seg_layer", seg), ("feature_encoding_layer", enc), ("normalize_feature_layer", nrm)):
+            for k, v in mod.state_dict().items():
+                keys[name + "." + k] = list(v.shape)
+        out[variant] = keys
+    with open(os.path.join(HERE, "heads_golden.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print("heads golden:", len(out["geoMatch"]), "state_dict entries per variant")
 
 
 def make_pointops():
@@ -272,7 +319,9 @@ if __name__ == "__main__":
         make_circle()
     elif len(sys.argv) > 1 and sys.argv[1] == "pointops":
         make_pointops()
+    elif len(sys.argv) > 1 and sys.argv[1] == "heads":
+        make_heads()
     else:
-        make_knn(); make_match(); make_dgcnn(); make_randla(); make_circle(); make_pointops()
+        make_knn(); make_match(); make_dgcnn(); make_randla(); make_circle(); make_pointops(); make_heads()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

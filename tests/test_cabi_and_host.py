@@ -212,3 +212,27 @@ def test_bf16n_column_scales_stay_below_the_pruning_bound():
             mt = F.normalize(m.float(), p=2, dim=0).to(torch.bfloat16).float()
             scale = 1.0 / mt.norm(dim=0).clamp_min(1e-12)
             assert float(scale.max()) <= bound, (d, float(scale.max()))
+
+
+def test_geomatch_cfg_constructor_heads_match_reference_state_dict():
+    """GeoMatch(cfg, cls_id) / GeoMatchDGCNN(cfg, cls_id) build heads whose state_dict keys and shapes are those of the
+    reference's own pt_utils stacks (tests/golden/heads_golden.json, generated from models/pytorch_utils.py)."""
+    import json
+    import torch.nn as nn
+    from gadm_b200 import matching
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "heads_golden.json")))
+
+    class Emb(nn.Module):
+        def forward(self, *a):
+            raise AssertionError("not called")
+    cfg = {"feat_dim": 128, "neighbor_dis_th": 0.03, "model_d": {5: 200.0}}
+    for cls, key in ((matching.GeoMatch, "geoMatch"), (matching.GeoMatchDGCNN, "geoMatch_DGCNN")):
+        net = cls(cfg, 5, pcd_emb=Emb(), model_emb=Emb())
+        sd = {k: list(v.shape) for k, v in net.state_dict().items()
+              if k.split(".")[0] in ("seg_layer", "feature_encoding_layer", "normalize_feature_layer")}
+        assert sd == gold[key]
+        assert "awl.params" in net.state_dict()                       # AutomaticWeightedLoss(2), loss.py:507-510
+    assert abs(matching.GeoMatch(cfg, 5, Emb(), Emb()).positive_r - 0.03 * 200.0 / 1000.0) < 1e-12   # geoMatch.py:24
+    assert matching.GeoMatchDGCNN(cfg, 5, Emb(), Emb()).positive_r == 3                               # geoMatch_DGCNN.py:22
+    with pytest.raises(NotImplementedError):
+        matching.GeoMatch(cfg, 5)                                      # the backbones are outside the package

@@ -71,6 +71,25 @@ def test_circle_loss_dgcnn_variant_golden(cuda):
         assert torch.all((rows[b].cpu()[idxs] - want).abs() <= TOL * want.abs() + TOL)
 
 
+def test_circle_loss_sys_variant_golden(cuda):
+    """GeoMatch.matching_loss_sys (models/geoMatch.py:86-100, the sys_corr_idx branch :138-141): the positives of a row
+    are exactly the columns match_idx[n] and match_idx[sys_idx[n]].  Forward against the reference's own number, gradients
+    against torch autograd through the oracle."""
+    from gadm_b200 import matching
+    g = np.load(os.path.join(GOLD, "circle_golden.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    rgbd = t("rgbd").to(cuda).requires_grad_(True)
+    mesh = t("mesh").to(cuda).requires_grad_(True)
+    total = matching.circle_match_loss(rgbd, mesh, t("labels").to(cuda), t("match_idx").to(cuda), None, None,
+                                       model_xyz=t("xyz")[None].to(cuda), sys_idx=t("sys_idx").to(cuda))
+    assert abs(float(total.detach()) - float(g["sys_ref_total"])) <= TOL * float(g["sys_ref_total"])
+    total.backward()
+    r2, m2 = t("rgbd").clone().requires_grad_(True), t("mesh").clone().requires_grad_(True)
+    co.batch_loss_sys(r2, m2, t("labels"), t("match_idx"), t("sys_idx")).backward()
+    for got, want in ((rgbd.grad.cpu(), r2.grad), (mesh.grad.cpu(), m2.grad)):
+        assert (got - want).abs().max() <= 2e-3 * want.abs().max() + 1e-6
+
+
 def test_circle_loss_ragged_bank(cuda):
     """Ragged rows / model tiles (1500 rows, 2056 vertices), a 2-object bank with per-frame obj_id, planted matches,
     per-frame visibility, 15 % of the rows off the model."""
@@ -172,7 +191,7 @@ def test_geomatch_module_forward_contract(cuda):
             return self.f
 
     xyz = synth.fibonacci_sphere(M, 0.2)
-    net = matching.GeoMatch(Pcd(), Mesh(), nn.Conv1d(C, d, 1), nn.Conv1d(C, 2, 1), nn.Conv1d(d, C, 1), model_xyz=xyz,
+    net = matching.GeoMatchHead(Pcd(), Mesh(), nn.Conv1d(C, d, 1), nn.Conv1d(C, 2, 1), nn.Conv1d(d, C, 1), model_xyz=xyz,
                             match_in_forward=True, positive_r=0.03,
                             seg_loss_func=lambda seg, lab: nn.functional.cross_entropy(seg, lab)).to(cuda)
     g = torch.Generator().manual_seed(1)
@@ -202,3 +221,97 @@ def test_geomatch_module_forward_contract(cuda):
         if name.startswith("normalize_feature_layer"):           # feeds the segmentation branch only
             continue
         assert prm.grad is not None and torch.isfinite(prm.grad).all() and prm.grad.abs().max() > 0, name
+
+
+def test_geomatch_cfg_constructors_forward(cuda):
+    """GeoMatch(cfg, cls_id) (models/geoMatch.py:13-52, :159-200) and the DGCNN variant (geoMatch_DGCNN.py:11-183) with stub
+    backbones: end_points keys and shapes ('mesh' [1, d, M] vs [d, M]), training losses equal to the fused loss computed
+    directly (incl. the symmetry-aware branch when model_emb.sys_corr_idx is set), eval-mode matching."""
+    import torch.nn as nn
+    from gadm_b200 import matching, synth
+    B, N, M, d = 2, 600, 256, 128
+    g = torch.Generator().manual_seed(3)
+    xyz = synth.fibonacci_sphere(M, 0.2)
+
+    class Pcd(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = nn.Conv1d(9, 128, 1)
+
+        def forward(self, x):
+            return self.lin(x['cld_rgb_nrm'] if isinstance(x, dict) else x)
+
+    class Mesh(nn.Module):
+        sys_corr_idx = None
+
+        def __init__(self):
+            super().__init__()
+            self.f = nn.Parameter(torch.randn((d, M), generator=g))
+            self.register_buffer('xyz', xyz)
+            self.register_buffer('mesh', torch.cat([xyz.t(), torch.zeros((3, M))], 0)[None])
+
+        def forward(self):
+            return self.f
+    cfg = {"feat_dim": d, "neighbor_dis_th": 0.15, "model_d": {1: 200.0}}
+    vis = (torch.rand((B, M), generator=g) < 0.7).to(torch.uint8)
+    labels = (torch.rand((B, N), generator=g) < 0.5).long()
+    match_idx = torch.randint(0, M + 1, (B, N), generator=g).int()
+    RT = torch.eye(3, 4)[None].repeat(B, 1, 1)
+    RT[:, 2, 3] = 0.9
+    inputs = {'cld_rgb_nrm': torch.randn((B, 9, N), generator=g).to(cuda), 'labels': labels.to(cuda),
+              'origin_labels': labels.to(cuda), 'match_idx': match_idx.to(cuda), 'visible_flag': vis.to(cuda),
+              'RT': RT.to(cuda)}
+    for cls, mesh_shape in ((matching.GeoMatch, (1, d, M)), (matching.GeoMatchDGCNN, (d, M))):
+        net = cls(cfg, 1, pcd_emb=Pcd(), model_emb=Mesh(), match_in_forward=True).to(cuda)
+        net.train()
+        ep = net(inputs)
+        assert tuple(ep['seg'].shape) == (B, 2, N) and tuple(ep['rgbd'].shape) == (B, d, N)
+        assert tuple(ep['mesh'].shape) == mesh_shape
+        assert set(('loss', 'seg_loss', 'match_loss')) <= set(ep)
+        if cls is matching.GeoMatch:
+            want = matching.circle_match_loss(ep['rgbd'], ep['mesh'], inputs['labels'], inputs['match_idx'], inputs['visible_flag'],
+                                              net.positive_r, model_xyz=xyz.to(cuda))
+        else:
+            rad = matching.dgcnn_positive_radius(xyz.to(cuda), inputs['RT'], 3)
+            want = matching.circle_match_loss(ep['rgbd'], ep['mesh'][None], inputs['origin_labels'], inputs['match_idx'],
+                                              inputs['visible_flag'], rad, model_xyz=xyz.to(cuda), pad_mode="e0")
+        assert torch.allclose(ep['match_loss'], want, rtol=1e-6)
+        assert torch.allclose(ep['loss'], net.awl(ep['seg_loss'], ep['match_loss']))
+        ep['loss'].backward()
+        assert net.model_emb.f.grad is not None and net.pcd_emb.lin.weight.grad is not None
+        net.eval()
+        with torch.no_grad():
+            ep = net(inputs)
+        assert 'loss' not in ep and tuple(ep['match_idx'].shape) == (B, N) and tuple(ep['match_xyz'].shape) == (B, N, 3)
+    # symmetric object: model_emb.sys_corr_idx set -> matching_loss_sys (geoMatch.py:138-141)
+    net = matching.GeoMatch(cfg, 1, pcd_emb=Pcd(), model_emb=Mesh()).to(cuda)
+    net.model_emb.sys_corr_idx = True
+    net.model_emb.sys_idx = torch.randint(0, N, (N,), generator=g).to(cuda)
+    net.train()
+    ep = net(inputs)
+    want = matching.circle_match_loss(ep['rgbd'], ep['mesh'], inputs['labels'], inputs['match_idx'], None, None,
+                                      model_xyz=xyz.to(cuda), sys_idx=net.model_emb.sys_idx)
+    assert torch.allclose(ep['match_loss'], want, rtol=1e-6)
+
+
+def test_cal_frame_poses_single_argument(cuda):
+    """evaluator.cal_frame_poses(item) with the module-level model container (evaluator.py:28-58, :60-102): the item's own
+    mesh_features are used and the model points come from model3ds.models_3d[cls_id]."""
+    from gadm_b200 import matching, synth
+    N, M, d = 1536, 512, 128
+    rgbd, mesh, corr = synth.descriptors(1, N, M, d, regime="planted", seed=8, sigma=0.3)
+    xyz = synth.fibonacci_sphere(M, 0.2)
+    t = torch.tensor([0.05, 0.02, 0.9])
+    cld = (xyz[corr[0]] + t).T.contiguous()
+    seg = torch.stack([torch.zeros(N), torch.ones(N)])
+    item = (cld.to(cuda), seg.to(cuda), mesh[0].to(cuda), rgbd[0].to(cuda), torch.tensor(7), True)
+    matching.set_model_container(None)
+    with pytest.raises(RuntimeError):
+        matching.cal_frame_poses(item)
+    matching.set_model_container(matching.ModelContainer({7: xyz.numpy(), 9: xyz.numpy() * 2}))
+    RT = matching.cal_frame_poses(item)
+    assert RT.shape == (3, 4) and np.abs(RT[:, :3] - np.eye(3)).max() < 1e-3 and np.abs(RT[:, 3] - t.numpy()).max() < 1e-3
+    bank = matching.ModelBank(mesh.to(cuda), xyz[None].to(cuda))
+    assert np.array_equal(RT, matching.cal_frame_poses(item, bank))
+    assert matching.cal_frame_poses(item[:5] + (False,))[2, 3] == -1000
+    matching.set_model_container(None)

@@ -194,6 +194,9 @@ def test_circle_oracle_reproduces_reference_loss():
     rad = torch.stack([co.dgcnn_radius(t("xyz"), t("RT")[b], float(g["dgcnn_positive_r"])) for b in range(3)])
     tot2 = co.batch_loss(t("rgbd"), t("mesh")[0], t("labels"), t("match_idx"), t("xyz"), t("vis"), rad, pad="e0")
     assert abs(float(tot2) - float(g["dgcnn_ref_total"])) <= 1e-6 * abs(float(g["dgcnn_ref_total"]))
+    # the symmetry-aware branch (geoMatch.py:138-141 -> matching_loss_sys :86-100)
+    tot3 = co.batch_loss_sys(t("rgbd"), t("mesh"), t("labels"), t("match_idx"), t("sys_idx"))
+    assert abs(float(tot3) - float(g["sys_ref_total"])) <= 1e-6 * abs(float(g["sys_ref_total"]))
     # the mask the loss sees: every on-model row has its own (visible) ground-truth vertex as a positive, an
     # off-model row has the pad column only
     mi = t("match_idx")[0].long()
