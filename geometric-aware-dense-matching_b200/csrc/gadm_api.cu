@@ -385,6 +385,28 @@ int gadm_relative_pos_encoding(const float* xyz, const int64_t* idx, int B, int 
   return relative_pos_encoding_launch(xyz, idx, B, N, K, out, static_cast<cudaStream_t>(stream));
 }
 
+int gadm_graph_feature_bwd(const float* grad_out, const int64_t* idx, int B, int C, int N, int k, float* grad_x,
+                           gadm_stream_t stream) {
+  GADM_REQUIRE_INIT();
+  if (!grad_out || !idx || !grad_x || B <= 0 || C <= 0 || N <= 0 || k <= 0) return GADM_ERR_BAD_ARG;
+  return graph_feature_bwd_launch(grad_out, idx, B, C, N, k, grad_x, static_cast<cudaStream_t>(stream));
+}
+
+int gadm_gather_neighbour_bwd(const float* grad_out, const int64_t* idx, int B, int N, int C, int M, int K,
+                              float* grad_pc, gadm_stream_t stream) {
+  GADM_REQUIRE_INIT();
+  if (!grad_out || !idx || !grad_pc || B <= 0 || N <= 0 || C <= 0 || M <= 0 || K <= 0) return GADM_ERR_BAD_ARG;
+  return gather_neighbour_bwd_launch(grad_out, idx, B, N, C, M, K, grad_pc, static_cast<cudaStream_t>(stream));
+}
+
+int gadm_gather_max_bwd(const float* feature, const int64_t* idx, const float* grad_out, int B, int C, int N, int M, int K,
+                        float* grad_feature, gadm_stream_t stream) {
+  GADM_REQUIRE_INIT();
+  if (!feature || !idx || !grad_out || !grad_feature || B <= 0 || C <= 0 || N <= 0 || M <= 0 || K <= 0)
+    return GADM_ERR_BAD_ARG;
+  return gather_max_bwd_launch(feature, idx, grad_out, B, C, N, M, K, grad_feature, static_cast<cudaStream_t>(stream));
+}
+
 int gadm_seg_mask(const float* seg, int B, int N, uint8_t* mask, gadm_stream_t stream) {
   GADM_REQUIRE_INIT();
   if (!seg || !mask || B <= 0 || N <= 0) return GADM_ERR_BAD_ARG;

@@ -82,6 +82,12 @@ int gather_neighbour_launch(const float* pc, const int64_t* idx, int B, int N, i
                             cudaStream_t stream);
 int gather_max_launch(const float* feature, const int64_t* idx, int B, int C, int N, int M, int K, float* out,
                       cudaStream_t stream);
+int graph_feature_bwd_launch(const float* grad_out, const int64_t* idx, int B, int C, int N, int k, float* grad_x,
+                             cudaStream_t stream);
+int gather_neighbour_bwd_launch(const float* grad_out, const int64_t* idx, int B, int N, int C, int M, int K,
+                                float* grad_pc, cudaStream_t stream);
+int gather_max_bwd_launch(const float* feature, const int64_t* idx, const float* grad_out, int B, int C, int N, int M,
+                          int K, float* grad_feature, cudaStream_t stream);
 int relative_pos_encoding_launch(const float* xyz, const int64_t* idx, int B, int N, int K, float* out,
                                  cudaStream_t stream);
 

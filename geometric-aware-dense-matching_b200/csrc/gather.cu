@@ -167,7 +167,99 @@ relative_pos_encoding_kernel(const float* __restrict__ xyz, const int64_t* __res
   __stcs(o + 4, make_float2(qy, qz));
 }
 
+// ---- backward passes of the gathers (the reference's torch.gather / max / cat are differentiable in the features:
+// models/dgcnn.py:41-54, models/RandLA/RandLANet.py:90-120, :729-738).  All three are scatter-adds with fp32 atomics.
+
+// graph_feature: out[:, :C] = x[idx] - x, out[:, C:] = x.  thread = one (n, j) pair of one batch item, loops over channels:
+//   gx[c, idx[n, j]] += g1[c, n, j];  gx[c, n] += g2[c, n, j] - g1[c, n, j]
+__global__ void __launch_bounds__(256)
+graph_feature_bwd_kernel(const float* __restrict__ go, const int64_t* __restrict__ idx, int C, int N, int k,
+                         float* __restrict__ gx) {
+  const int b = blockIdx.y;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // n * k + j
+  const long long nk = (long long)N * k;
+  if (e >= nk) return;
+  const int n = int(e / k);
+  const int q = int(idx[(size_t)b * nk + e]);
+  const float* g1 = go + (size_t)b * 2 * C * nk + e;
+  const float* g2 = g1 + (size_t)C * nk;
+  float* gb = gx + (size_t)b * C * N;
+  for (int c = 0; c < C; ++c) {
+    const float a = g1[(size_t)c * nk], d = g2[(size_t)c * nk];
+    atomicAdd(gb + (size_t)c * N + q, a);
+    atomicAdd(gb + (size_t)c * N + n, d - a);
+  }
+}
+
+// gather_neighbour: out[b, m, k, :] = pc[b, idx[b, m, k], :].  warp = one (b, m, k) row of C floats.
+__global__ void __launch_bounds__(256)
+gather_neighbour_bwd_kernel(const float* __restrict__ go, const int64_t* __restrict__ idx, int N, int C, long long rows,
+                            long long rows_per_b, float* __restrict__ gpc) {
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const long long b = r / rows_per_b;
+  float* dst = gpc + ((size_t)b * N + (size_t)idx[r]) * C;
+  const float* src = go + (size_t)r * C;
+  for (int c = lane; c < C; c += 32) atomicAdd(dst + c, src[c]);
+}
+
+// gather_max: out[b, c, m] = max_j f[b, c, idx[b, m, j]]: the gradient goes to the FIRST neighbour that attains the
+// maximum (what torch.max(dim) differentiates to on the CPU).  thread = one (m) of one (b, channel block).
+__global__ void __launch_bounds__(256)
+gather_max_bwd_kernel(const float* __restrict__ f, const int64_t* __restrict__ idx, const float* __restrict__ go, int C,
+                      int N, int M, int K, int c_per_block, float* __restrict__ gf) {
+  const int b = blockIdx.z;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int64_t* ip = idx + ((size_t)b * M + m) * K;
+  const int c0 = blockIdx.y * c_per_block;
+  const int c1 = min(C, c0 + c_per_block);
+  for (int c = c0; c < c1; ++c) {
+    const float* row = f + ((size_t)b * C + c) * N;
+    int best = int(ip[0]);
+    float v = row[best];
+    for (int j = 1; j < K; ++j) {
+      const int q = int(ip[j]);
+      const float w = row[q];
+      if (w > v) { v = w; best = q; }
+    }
+    atomicAdd(gf + ((size_t)b * C + c) * N + best, go[((size_t)b * C + c) * M + m]);
+  }
+}
+
 }  // namespace
+
+int graph_feature_bwd_launch(const float* grad_out, const int64_t* idx, int B, int C, int N, int k, float* grad_x,
+                             cudaStream_t stream) {
+  if (B > 65535) return GADM_ERR_UNSUPPORTED;
+  cudaError_t e = cudaMemsetAsync(grad_x, 0, size_t(B) * C * N * sizeof(float), stream);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  const long long nk = (long long)N * k;
+  graph_feature_bwd_kernel<<<dim3(unsigned((nk + 255) / 256), B), 256, 0, stream>>>(grad_out, idx, C, N, k, grad_x);
+  return check_launch();
+}
+
+int gather_neighbour_bwd_launch(const float* grad_out, const int64_t* idx, int B, int N, int C, int M, int K,
+                                float* grad_pc, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(grad_pc, 0, size_t(B) * N * C * sizeof(float), stream);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  const long long rows = (long long)B * M * K;
+  gather_neighbour_bwd_kernel<<<unsigned((rows + 7) / 8), 256, 0, stream>>>(grad_out, idx, N, C, rows, (long long)M * K,
+                                                                         grad_pc);
+  return check_launch();
+}
+
+int gather_max_bwd_launch(const float* feature, const int64_t* idx, const float* grad_out, int B, int C, int N, int M,
+                          int K, float* grad_feature, cudaStream_t stream) {
+  if (B > 65535) return GADM_ERR_UNSUPPORTED;
+  cudaError_t e = cudaMemsetAsync(grad_feature, 0, size_t(B) * C * N * sizeof(float), stream);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  const int c_per_block = 8;
+  gather_max_bwd_kernel<<<dim3((M + 255) / 256, (C + c_per_block - 1) / c_per_block, B), 256, 0, stream>>>(
+      feature, idx, grad_out, C, N, M, K, c_per_block, grad_feature);
+  return check_launch();
+}
 
 int gather_max_launch(const float* feature, const int64_t* idx, int B, int C, int N, int M, int K, float* out,
                       cudaStream_t stream) {

@@ -1,4 +1,5 @@
-"""Drop-ins for models/dgcnn.py:21-56 (knn, get_graph_feature) on the fused CUDA kernels."""
+"""Drop-ins for models/dgcnn.py:21-56 (knn, get_graph_feature) on the fused CUDA kernels.  get_graph_feature is
+differentiable in x (as the reference's gather / cat), the neighbour indices carry no gradient."""
 from . import ops
 
 

@@ -491,6 +491,37 @@ def _(x, idx):
     return x.new_empty((B, 2 * C, N, idx.shape[2]))
 
 
+@torch.library.custom_op("gadm::graph_feature_bwd", mutates_args=(), device_types="cuda")
+def graph_feature_bwd(grad_out: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """grad_out [B, 2C, N, k] -> grad_x [B, C, N] (models/dgcnn.py:49-54 differentiated)."""
+    _need(grad_out, torch.float32, "grad_out"); _need(idx, torch.int64, "idx")
+    B, C2, N, k = grad_out.shape
+    gx = torch.empty((B, C2 // 2, N), dtype=torch.float32, device=grad_out.device)
+    lib = _lib_for(grad_out)
+    with torch.cuda.device(grad_out.device):
+        _lib.check(lib.gadm_graph_feature_bwd(_ptr(grad_out), _ptr(idx), B, C2 // 2, N, k, _ptr(gx), _stream()),
+                   "gadm_graph_feature_bwd")
+    return gx
+
+
+@graph_feature_bwd.register_fake
+def _(grad_out, idx):
+    B, C2, N, k = grad_out.shape
+    return grad_out.new_empty((B, C2 // 2, N))
+
+
+def _gf_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[1])
+
+
+def _gf_backward(ctx, grad):
+    (idx,) = ctx.saved_tensors
+    return graph_feature_bwd(grad.contiguous(), idx), None
+
+
+graph_feature.register_autograd(_gf_backward, setup_context=_gf_setup)
+
+
 # --------------------------------------------------------------------------------------------- grouping
 @torch.library.custom_op("gadm::group_fwd", mutates_args=(), device_types="cuda")
 def group_fwd(features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
@@ -559,6 +590,37 @@ def _(pc, idx):
     return pc.new_empty((pc.shape[0], idx.shape[1], idx.shape[2], pc.shape[2]))
 
 
+@torch.library.custom_op("gadm::gather_neighbour_bwd", mutates_args=(), device_types="cuda")
+def gather_neighbour_bwd(grad_out: torch.Tensor, idx: torch.Tensor, n: int) -> torch.Tensor:
+    """grad_out [B, M, K, C] -> grad_pc [B, N, C] (RandLANet.py:729-738 differentiated)."""
+    _need(grad_out, torch.float32, "grad_out"); _need(idx, torch.int64, "idx")
+    B, M, K, C = grad_out.shape
+    g = torch.empty((B, n, C), dtype=torch.float32, device=grad_out.device)
+    lib = _lib_for(grad_out)
+    with torch.cuda.device(grad_out.device):
+        _lib.check(lib.gadm_gather_neighbour_bwd(_ptr(grad_out), _ptr(idx), B, n, C, M, K, _ptr(g), _stream()),
+                   "gadm_gather_neighbour_bwd")
+    return g
+
+
+@gather_neighbour_bwd.register_fake
+def _(grad_out, idx, n):
+    return grad_out.new_empty((grad_out.shape[0], n, grad_out.shape[3]))
+
+
+def _gn_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[1])
+    ctx.n = inputs[0].shape[1]
+
+
+def _gn_backward(ctx, grad):
+    (idx,) = ctx.saved_tensors
+    return gather_neighbour_bwd(grad.contiguous(), idx, ctx.n), None
+
+
+gather_neighbour.register_autograd(_gn_backward, setup_context=_gn_setup)
+
+
 # --------------------------------------------------------------------------------------------- RandLA consumers
 @torch.library.custom_op("gadm::gather_max", mutates_args=(), device_types="cuda")
 def gather_max(feature: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
@@ -579,6 +641,54 @@ def _(feature, idx):
     return feature.new_empty((feature.shape[0], feature.shape[1], idx.shape[1]))
 
 
+@torch.library.custom_op("gadm::gather_max_bwd", mutates_args=(), device_types="cuda")
+def gather_max_bwd(feature: torch.Tensor, idx: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
+    """grad_out [B, C, M] -> grad_feature [B, C, N]: to the first neighbour attaining each maximum
+    (RandLANet.py:90-120 differentiated)."""
+    _need(feature, torch.float32, "feature"); _need(idx, torch.int64, "idx"); _need(grad_out, torch.float32, "grad_out")
+    B, C, N = feature.shape
+    _, M, K = idx.shape
+    g = torch.empty((B, C, N), dtype=torch.float32, device=feature.device)
+    lib = _lib_for(feature)
+    with torch.cuda.device(feature.device):
+        _lib.check(lib.gadm_gather_max_bwd(_ptr(feature), _ptr(idx), _ptr(grad_out), B, C, N, M, K, _ptr(g), _stream()),
+                   "gadm_gather_max_bwd")
+    return g
+
+
+@gather_max_bwd.register_fake
+def _(feature, idx, grad_out):
+    return feature.new_empty(feature.shape)
+
+
+def _gm_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1])
+
+
+def _gm_backward(ctx, grad):
+    feature, idx = ctx.saved_tensors
+    return gather_max_bwd(feature, idx, grad.contiguous()), None
+
+
+gather_max.register_autograd(_gm_backward, setup_context=_gm_setup)
+
+
+def _rpe_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1])
+
+
+def _rpe_backward(ctx, grad):
+    """[dis, rel, tile, nbr] with rel = tile - nbr, dis = |rel| (RandLANet.py:720-727): the gradient reaches xyz through
+    the tiled centre (summed over K) and through the gathered neighbour (scatter-add, gather_neighbour_bwd)."""
+    xyz, idx = ctx.saved_tensors
+    enc = relative_pos_encoding(xyz, idx)
+    dis, rel = enc[..., 0:1], enc[..., 1:4]
+    g_rel = grad[..., 1:4] + grad[..., 0:1] * rel / dis.clamp_min(1e-30)
+    g_tile = grad[..., 4:7] + g_rel
+    g_nbr = grad[..., 7:10] - g_rel
+    return g_tile.sum(dim=2) + gather_neighbour_bwd(g_nbr.contiguous(), idx, xyz.shape[1]), None
+
+
 @torch.library.custom_op("gadm::relative_pos_encoding", mutates_args=(), device_types="cuda")
 def relative_pos_encoding(xyz: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     """xyz [B, N, 3] fp32, idx [B, N, K] int64 -> [B, N, K, 10] = [|p-q|, p-q, p, q]."""
@@ -596,6 +706,9 @@ def relative_pos_encoding(xyz: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 @relative_pos_encoding.register_fake
 def _(xyz, idx):
     return xyz.new_empty((xyz.shape[0], xyz.shape[1], idx.shape[2], 10))
+
+
+relative_pos_encoding.register_autograd(_rpe_backward, setup_context=_rpe_setup)
 
 
 @torch.library.custom_op("gadm::seg_mask", mutates_args=(), device_types="cuda")

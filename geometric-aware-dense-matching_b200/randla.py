@@ -6,7 +6,8 @@ instead of a materialised torch.gather + a second pass:
   relative_pos_encoding(xyz, neigh_idx)     models/RandLA/RandLANet.py:720-727   [|p-q|, p-q, p, q] per (point, nbr)
   gather_neighbour(pc, neighbor_idx)        models/RandLA/RandLANet.py:729-738
 
-Forward only (the index tensors are not differentiable; feature gradients are a round-2 item)."""
+Differentiable in the features / coordinates like the reference's torch.gather compositions (scatter-add backward
+kernels, registered as autograd formulas of the custom ops); the index tensors carry no gradient."""
 from . import ops
 from .pointops import gather_neighbour  # noqa: F401
 

@@ -204,6 +204,20 @@ int gadm_circle_loss_bwd(const void* rows, const float* rinv_rows, const float* 
                          const float* lse_p, const float* lse_n, const float* w, float* G, int Mp,
                          gadm_stream_t stream);
 
+/* Backward passes of the gathers: the reference's torch.gather / max / cat are differentiable in the features
+ * (models/dgcnn.py:41-54, models/RandLA/RandLANet.py:90-120, :729-738) and sit inside the trained networks.  Each zeroes
+ * its output and scatter-adds with fp32 atomics (the summation order, hence the last bits, may vary from run to run).
+ *   graph_feature_bwd     grad_out [B, 2C, N, k] -> grad_x [B, C, N]
+ *   gather_neighbour_bwd  grad_out [B, M, K, C]  -> grad_pc [B, N, C]
+ *   gather_max_bwd        grad_out [B, C, M]     -> grad_feature [B, C, N]; the gradient of a maximum goes to the FIRST
+ *                         neighbour that attains it (feature / idx as in the forward call)                             */
+int gadm_graph_feature_bwd(const float* grad_out, const int64_t* idx, int B, int C, int N, int k, float* grad_x,
+                           gadm_stream_t stream);
+int gadm_gather_neighbour_bwd(const float* grad_out, const int64_t* idx, int B, int N, int C, int M, int K,
+                              float* grad_pc, gadm_stream_t stream);
+int gadm_gather_max_bwd(const float* feature, const int64_t* idx, const float* grad_out, int B, int C, int N, int M, int K,
+                        float* grad_feature, gadm_stream_t stream);
+
 /* Foreground mask of the matcher (evaluator.py:78,82: `seg_res = argmax(seg_features, dim=0); cls_msk = seg_res == 1`)
  * without the argmax tensor: seg [B, 2, N] fp32 -> mask [B, N] uint8 = seg[b,1,n] > seg[b,0,n]  (torch.argmax returns
  * the first maximal index, so a tie is background). */
