@@ -59,7 +59,7 @@ const char* gadm_strerror(int status) {
   switch (status) {
     case GADM_OK: return "ok";
     case GADM_ERR_BAD_ARG: return "bad argument (null pointer, non-positive size or inconsistent shapes)";
-    case GADM_ERR_UNSUPPORTED: return "unsupported configuration (d %% 64, M %% 8, k > 32, mode ...)";
+    case GADM_ERR_UNSUPPORTED: return "unsupported configuration (d % 64, M % 8, k > 32, mode ...)";
     case GADM_ERR_ALIGN: return "pointer not 16-byte aligned";
     case GADM_ERR_WORKSPACE: return "workspace too small";
     case GADM_ERR_CUDA: return "CUDA error (see gadm_last_cuda_error)";

@@ -269,7 +269,7 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
           const float gm = ptx::fmax3(a0, a1, fmaxf(f[6], f[7]));
           // strict: an equal value in a later group never displaces the first maximal index
           const bool up = gm > vmax;
-          ptx::sts_stash8(up, stash_addr, v[h * 4 + 0], v[h * 4 + 1], v[h * 4 + 2], v[h * 4 + 3]);
+          ptx::sts_stash8(up, stash_addr, f);
           vgrp = up ? col_base + col0 + h * GRP : vgrp;
           vmax = up ? gm : vmax;
         }
@@ -434,6 +434,7 @@ int match_stages(int RT, int KB) {
 constexpr int PBN = 128;                       // model vertices per tile
 constexpr int PB_STAGE_BYTES = PBN * BK * 2;   // 16 KB
 constexpr int P_MAX_STAGES = 8;
+constexpr int P_MAX_KB = 4;                    // K blocks of a model tile (the issue loop is unrolled over them)
 constexpr int P_PLANE_BYTES = PBN * 4;
 constexpr int P_CS = PBN / 4;                  // 32 columns per warp slice
 constexpr int P_STASH_BYTES = 2 * STASH_BYTES; // two rows per thread
@@ -450,16 +451,21 @@ struct PairBarriers {
   uint32_t pad;
 };
 
-template <bool kSoft>
+template <bool kSoft, bool kCta2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
                   const MatchParams p) {
   constexpr int AUX_BYTES = kSoft ? 4 * P_PLANE_BYTES : P_PLANE_BYTES;
+  // kCta2: the CTA is one half of a pair (cluster of two, cta_group::2 MMAs with M = 256).  It holds its own 256 rows
+  // and HALF of every model tile (64 of the 128 vertices): the MMA reads 6 KB instead of 8 KB of operands per 64
+  // cycles from this SM's shared memory and TMA writes half as much into it -- the data pipe the epilogue shares.
+  constexpr int STAGE_BYTES = kCta2 ? PB_STAGE_BYTES / 2 : PB_STAGE_BYTES;
+  constexpr int STAGE_ROWS = kCta2 ? PBN / 2 : PBN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                    // [2][KB] blocks of 128 rows x 64 k
   uint8_t* smem_b = smem_a + 2 * p.KB * A_BLK_BYTES;
-  uint8_t* smem_aux = smem_b + p.stages * PB_STAGE_BYTES;  // per slot: [1/|m| x128 | x | y | z]
+  uint8_t* smem_aux = smem_b + p.stages * STAGE_BYTES;  // per slot: [1/|m| x128 | x | y | z]
   uint8_t* smem_stash = smem_aux + AUX_SLOTS * AUX_BYTES;
   PairBarriers* bars = reinterpret_cast<PairBarriers*>(smem_stash + P_STASH_BYTES);
 
@@ -468,7 +474,10 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
   const int b = blockIdx.y;
   const int row0 = blockIdx.x * (2 * BM);
   const int nrows = frame_rows(p, b);          // rows of this frame (fewer than N after row compaction)
-  if (row0 >= nrows) return;                   // whole CTA, before any barrier or TMEM allocation
+  const uint32_t rank = kCta2 ? ptx::cluster_ctarank() : 0;   // == blockIdx.x & 1
+  // whole CTA (kCta2: whole pair -- a peer without rows still supplies its half of the model tiles), before any
+  // barrier or TMEM allocation
+  if ((kCta2 ? (blockIdx.x & ~1u) * (2 * BM) : row0) >= nrows) return;
   const int obj = frame_object(p, b);
   const int num_tiles = (p.M + PBN - 1) / PBN;
 
@@ -482,7 +491,7 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
     ptx::mbar_init(&bars->a_full, 1);
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&bars->s_full[a], 1);
-      ptx::mbar_init(&bars->s_free[a], EPI_WARPS);
+      ptx::mbar_init(&bars->s_free[a], kCta2 ? 2 * EPI_WARPS : EPI_WARPS);   // the leader hears both CTAs
     }
     for (int a = 0; a < AUX_SLOTS; ++a) {
       ptx::mbar_init(&bars->aux_full[a], 1);
@@ -491,22 +500,29 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
     ptx::fence_mbar_init();
   }
   if (warp == EPI_WARPS + 1) {
-    ptx::tmem_alloc(&bars->tmem_base, TMEM_COLS);
-    ptx::tmem_relinquish();
+    if (kCta2) { ptx::tmem_alloc_pair(&bars->tmem_base, TMEM_COLS); ptx::tmem_relinquish_pair(); }
+    else       { ptx::tmem_alloc(&bars->tmem_base, TMEM_COLS); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kCta2) ptx::cluster_sync(); else __syncthreads();   // the peer's barriers are initialised too
   ptx::tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  // barriers of the MMA issuer (the leader's), as cluster addresses
+  const uint32_t a_full_ldr = kCta2 ? ptx::mapa(ptx::smem_u32(&bars->a_full), 0) : 0;
 
   if (warp == EPI_WARPS) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(&bars->a_full, 2 * p.KB * A_BLK_BYTES);
+      if (rank == 0) ptx::mbar_arrive_expect_tx(&bars->a_full, (kCta2 ? 4 : 2) * p.KB * A_BLK_BYTES);
       for (int r = 0; r < 2; ++r)
-        for (int kb = 0; kb < p.KB; ++kb)
-          ptx::tma_load_3d(smem_a + (r * p.KB + kb) * A_BLK_BYTES, &tmap_rows, &bars->a_full, kb * BK,
-                           row0 + r * BM, b);   // rows >= N are zero-filled by TMA
+        for (int kb = 0; kb < p.KB; ++kb) {    // rows >= N are zero-filled by TMA
+          if (kCta2)
+            ptx::tma_load_3d_pair(smem_a + (r * p.KB + kb) * A_BLK_BYTES, &tmap_rows, a_full_ldr, kb * BK,
+                                  row0 + r * BM, b);
+          else
+            ptx::tma_load_3d(smem_a + (r * p.KB + kb) * A_BLK_BYTES, &tmap_rows, &bars->a_full, kb * BK,
+                             row0 + r * BM, b);
+        }
       int stage = 0;
       uint32_t phase = 0;
       const size_t plane = size_t(p.n_obj) * p.M;
@@ -528,8 +544,15 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
         }
         for (int kb = 0; kb < p.KB; ++kb) {
           ptx::mbar_wait_sleep(&bars->empty[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&bars->full[stage], PB_STAGE_BYTES);
-          ptx::tma_load_3d(smem_b + stage * PB_STAGE_BYTES, &tmap_cols, &bars->full[stage], kb * BK, t * PBN, obj);
+          // (kCta2: both halves complete on the leader's barrier; the peer's bytes may land before the leader's
+          // expect_tx of the same phase -- the phase cannot end before the leader's arrive)
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&bars->full[stage], PB_STAGE_BYTES);
+          if (kCta2)
+            ptx::tma_load_3d_pair(smem_b + stage * STAGE_BYTES, &tmap_cols,
+                                  ptx::mapa(ptx::smem_u32(&bars->full[stage]), 0), kb * BK,
+                                  t * PBN + int(rank) * STAGE_ROWS, obj);
+          else
+            ptx::tma_load_3d(smem_b + stage * STAGE_BYTES, &tmap_cols, &bars->full[stage], kb * BK, t * PBN, obj);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -539,8 +562,23 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
     // (one lane issues.  Issuing from the whole warp with an elected lane keeps the operands in uniform registers and
     // shortens the scalar code between MMAs, but 32 polling lanes cost the epilogue warps of the same scheduler more
     // than that saves: 0.403 ms against 0.381 ms at the BASELINE shape)
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(BM, PBN);
+    if (lane == 0 && rank == 0) {
+      // The issue loop is the tensor pipe's clock: a 128x128x16 MMA executes in 64 cycles, so everything between two
+      // tcgen05.mma of this one thread has to stay well below that.  Descriptors are therefore kept as 32-bit low
+      // words (start address >> 4 | LBO; every shared-memory address >> 4 fits the 14-bit field, so + 2 steps k
+      // without a mask) next to one constant high word, and the accumulator address is a compile-time function of
+      // (buf, r): the CTA owns all 512 columns, so its allocation starts at column 0 (checked below).  With the
+      // address read back from shared memory the compiler emits an ELECT / R2UR.BROADCAST waterfall per MMA and the
+      // loop issues one MMA per ~130 cycles (0.215 ms for the bare TMA -> MMA pipeline at the BASELINE shape).
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(kCta2 ? 2 * BM : BM, PBN);
+      constexpr uint64_t DESC_HI = uint64_t((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;   // SBO | version | SW128
+      if (tmem_base != 0) __trap();
+      const uint32_t a_lo0 = ((ptx::smem_u32(smem_a) & 0x3FFFF) >> 4) | 0x10000u;
+      const uint32_t b_lo0 = ((ptx::smem_u32(smem_b) & 0x3FFFF) >> 4) | 0x10000u;
+      auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+        if (kCta2) ptx::umma_bf16_ss_pair(d, DESC_HI | a_lo, DESC_HI | b_lo, idesc, acc);
+        else ptx::umma_bf16_ss(d, DESC_HI | a_lo, DESC_HI | b_lo, idesc, acc);
+      };
       ptx::mbar_wait(&bars->a_full, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -548,23 +586,26 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
         const int buf = t & 1;
         ptx::mbar_wait_sleep(&bars->s_free[buf], ((uint32_t(t) >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
-        for (int kb = 0; kb < p.KB; ++kb) {
+#pragma unroll
+        for (int kb = 0; kb < P_MAX_KB; ++kb) {
+          if (kb >= p.KB) break;
           ptx::mbar_wait_sleep(&bars->full[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t b_addr = ptx::smem_u32(smem_b + stage * PB_STAGE_BYTES);
+          const uint32_t b_lo = b_lo0 + uint32_t(stage) * (STAGE_BYTES >> 4);
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
-            const uint32_t a_addr = ptx::smem_u32(smem_a + (r * p.KB + kb) * A_BLK_BYTES);
-            const uint32_t d_tmem = tmem_base + (buf * 2 + r) * PBN;
+            const uint32_t a_lo = a_lo0 + uint32_t(r * p.KB + kb) * (A_BLK_BYTES >> 4);
+            const uint32_t d_tmem = uint32_t(buf * 2 + r) * PBN;
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              ptx::umma_bf16_ss(d_tmem, ptx::umma_desc_sw128_kmajor(a_addr + k * UMMA_K * 2),
-                                ptx::umma_desc_sw128_kmajor(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0);
+              mma(d_tmem, a_lo + k * (UMMA_K * 2 >> 4), b_lo + k * (UMMA_K * 2 >> 4), (kb | k) != 0);
           }
-          ptx::umma_commit(&bars->empty[stage]);
+          if (kCta2) ptx::umma_commit_pair(&bars->empty[stage]);   // frees the stage in both CTAs
+          else ptx::umma_commit(&bars->empty[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&bars->s_full[buf]);
+        if (kCta2) ptx::umma_commit_pair(&bars->s_full[buf]);
+        else ptx::umma_commit(&bars->s_full[buf]);
       }
     }
   } else {
@@ -586,6 +627,7 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
     }
     const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16) + sub * P_CS;
     const uint32_t stash_addr = ptx::smem_u32(smem_stash) + threadIdx.x * 16;   // row r: + r * 2 * STASH_PLANE
+    const uint32_t s_free_ldr = kCta2 ? ptx::mapa(ptx::smem_u32(&bars->s_free[0]), 0) : 0;
 
     float vmax[2] = {-INFINITY, -INFINITY};
     int vgrp[2] = {0, 0};
@@ -633,6 +675,7 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
               v[rr][j] = ptx::pack2f(lo, hi);
             }
         }
+#ifndef GADM_DBG_NOMAX   // (GADM_DBG_*: timing-only ablation builds, tools/ablate_soft.sh; results are wrong)
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
 #pragma unroll
@@ -643,35 +686,49 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
             const float a0 = ptx::fmax3(f[0], f[1], f[2]), a1 = ptx::fmax3(f[3], f[4], f[5]);
             const float gm = ptx::fmax3(a0, a1, fmaxf(f[6], f[7]));
             const bool up = gm > vmax[rr];
-            ptx::sts_stash8(up, stash_addr + rr * 2 * STASH_PLANE, v[rr][h * 4 + 0], v[rr][h * 4 + 1],
-                            v[rr][h * 4 + 2], v[rr][h * 4 + 3]);
+#ifndef GADM_DBG_NOSTASH
+            ptx::sts_stash8(up, stash_addr + rr * 2 * STASH_PLANE, f);
+#endif
             vgrp[rr] = up ? col_base + col0 + h * GRP : vgrp[rr];
             vmax[rr] = up ? gm : vmax[rr];
           }
         }
+#endif
         if (kSoft) {
           // p = 2^(v*g), no reference exponent (see match_kernel)
           const uint64_t g20 = ptx::pack2f(g[0], g[0]), g21 = ptx::pack2f(g[1], g[1]);
 #pragma unroll
           for (int j4 = 0; j4 < W / 4; ++j4) {
+#ifdef GADM_DBG_NOXYZ
+            const float4 X = make_float4(1.f, 2.f, 3.f, 4.f), Y = X, Z = X;
+#else
             const float4 X = ptx::lds128(sc + P_PLANE_BYTES + j4 * 16);
             const float4 Y = ptx::lds128(sc + 2 * P_PLANE_BYTES + j4 * 16);
             const float4 Z = ptx::lds128(sc + 3 * P_PLANE_BYTES + j4 * 16);
+#endif
             const uint64_t X01 = ptx::pack2f(X.x, X.y), X23 = ptx::pack2f(X.z, X.w);
             const uint64_t Y01 = ptx::pack2f(Y.x, Y.y), Y23 = ptx::pack2f(Y.z, Y.w);
             const uint64_t Z01 = ptx::pack2f(Z.x, Z.y), Z23 = ptx::pack2f(Z.z, Z.w);
-            const uint64_t pa0 = ptx::ex2_2(ptx::fmul2(v[0][j4 * 2 + 0], g20));
-            const uint64_t pb0 = ptx::ex2_2(ptx::fmul2(v[0][j4 * 2 + 1], g20));
-            const uint64_t pa1 = ptx::ex2_2(ptx::fmul2(v[1][j4 * 2 + 0], g21));
-            const uint64_t pb1 = ptx::ex2_2(ptx::fmul2(v[1][j4 * 2 + 1], g21));
+#ifdef GADM_DBG_NOEXP
+#define GADM_EX2(x) (x)
+#else
+#define GADM_EX2(x) ptx::ex2_2(x)
+#endif
+            const uint64_t pa0 = GADM_EX2(ptx::fmul2(v[0][j4 * 2 + 0], g20));
+            const uint64_t pb0 = GADM_EX2(ptx::fmul2(v[0][j4 * 2 + 1], g20));
+            const uint64_t pa1 = GADM_EX2(ptx::fmul2(v[1][j4 * 2 + 0], g21));
+            const uint64_t pb1 = GADM_EX2(ptx::fmul2(v[1][j4 * 2 + 1], g21));
+#undef GADM_EX2
             l2[0] = ptx::fadd2(l2[0], ptx::fadd2(pa0, pb0));
             l2[1] = ptx::fadd2(l2[1], ptx::fadd2(pa1, pb1));
+#ifndef GADM_DBG_NOSUMS
             ax2[0] = ptx::ffma2(pb0, X23, ptx::ffma2(pa0, X01, ax2[0]));
             ax2[1] = ptx::ffma2(pb1, X23, ptx::ffma2(pa1, X01, ax2[1]));
             ay2[0] = ptx::ffma2(pb0, Y23, ptx::ffma2(pa0, Y01, ay2[0]));
             ay2[1] = ptx::ffma2(pb1, Y23, ptx::ffma2(pa1, Y01, ay2[1]));
             az2[0] = ptx::ffma2(pb0, Z23, ptx::ffma2(pa0, Z01, az2[0]));
             az2[1] = ptx::ffma2(pb1, Z23, ptx::ffma2(pa1, Z01, az2[1]));
+#endif
           }
         }
       };
@@ -690,22 +747,35 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
           if (ncols >= P_CS) process(ra, rb, 0, guard_off{});
           else process(ra, rb, 0, guard_on{});
         } else {
+          // (the ragged last tile has its own loop: with both variants in one unrolled body the accumulators are
+          // shuffled between their register assignments after every half tile, ~20 MOVs per 32 scores)
+          if (ncols >= P_CS) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (ncols - h * 16 <= 0) break;
-            uint32_t ra[16], rb[16];
-            ptx::tmem_ld_32x16(s_tmem0 + h * 16, ra);
-            ptx::tmem_ld_32x16(s_tmem1 + h * 16, rb);
-            ptx::tmem_ld_wait();
-            if (ncols - h * 16 >= 16) process(ra, rb, h * 16, guard_off{});
-            else process(ra, rb, h * 16, guard_on{});
+            for (int h = 0; h < 2; ++h) {
+              uint32_t ra[16], rb[16];
+              ptx::tmem_ld_32x16(s_tmem0 + h * 16, ra);
+              ptx::tmem_ld_32x16(s_tmem1 + h * 16, rb);
+              ptx::tmem_ld_wait();
+              process(ra, rb, h * 16, guard_off{});
+            }
+          } else {
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+              if (ncols - h * 16 <= 0) break;
+              uint32_t ra[16], rb[16];
+              ptx::tmem_ld_32x16(s_tmem0 + h * 16, ra);
+              ptx::tmem_ld_32x16(s_tmem1 + h * 16, rb);
+              ptx::tmem_ld_wait();
+              process(ra, rb, h * 16, guard_on{});
+            }
           }
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        ptx::mbar_arrive(&bars->s_free[buf]);
+        if (kCta2) ptx::mbar_arrive_cluster(s_free_ldr + buf * 8);
+        else ptx::mbar_arrive(&bars->s_free[buf]);
         ptx::mbar_arrive(&bars->aux_empty[slot]);
       }
     }
@@ -793,22 +863,23 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kCta2) ptx::cluster_sync(); else __syncthreads();   // the pair's MMAs read both CTAs' shared memory
   if (warp == EPI_WARPS + 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    if (kCta2) ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
 template <bool kSoft>
-size_t match_pair_smem_bytes(int KB, int stages) {
-  return size_t(2) * KB * A_BLK_BYTES + size_t(stages) * PB_STAGE_BYTES + AUX_SLOTS * (kSoft ? 4 : 1) * P_PLANE_BYTES +
-         P_STASH_BYTES + sizeof(PairBarriers) + 1024;
+size_t match_pair_smem_bytes(int KB, int stages, bool cta2 = false) {
+  return size_t(2) * KB * A_BLK_BYTES + size_t(stages) * (cta2 ? PB_STAGE_BYTES / 2 : PB_STAGE_BYTES) +
+         AUX_SLOTS * (kSoft ? 4 : 1) * P_PLANE_BYTES + P_STASH_BYTES + sizeof(PairBarriers) + 1024;
 }
 template <bool kSoft>
-int match_pair_stages(int KB) {
+int match_pair_stages(int KB, bool cta2 = false) {
   int stages = P_MAX_STAGES;
-  while (stages > 0 && match_pair_smem_bytes<kSoft>(KB, stages) > 227 * 1024) --stages;
+  while (stages > 0 && match_pair_smem_bytes<kSoft>(KB, stages, cta2) > 227 * 1024) --stages;
   return stages;
 }
 
@@ -923,6 +994,12 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
     // ============================== UMMA issuer ==============================
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(BM, BN);
+      // descriptors as 32-bit low words + one constant high word, accumulator address a function of r alone (the CTA
+      // owns all 512 columns: its allocation starts at column 0) -- see match_pair_kernel
+      constexpr uint64_t DESC_HI = uint64_t((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+      if (tmem_base != 0) __trap();
+      const uint32_t a_lo0 = ((ptx::smem_u32(smem_a) & 0x3FFFF) >> 4) | 0x10000u;
+      const uint32_t b_lo0 = ((ptx::smem_u32(smem_b) & 0x3FFFF) >> 4) | 0x10000u;
       int stage0 = 0;            // ring position of the tile's first K block
       uint32_t phase0 = 0, n = 0, seg = 0;
       for (long long u = u_begin; u < u_end; ++seg) {
@@ -934,7 +1011,7 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
           for (int r = 0; r < RT; ++r) {
             ptx::mbar_wait_sleep(&bars->s_free[r], (n & 1) ^ 1);
             ptx::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + r * BN;
+            const uint32_t d_tmem = r * BN;
             int stage = stage0;
             uint32_t phase = phase0;
             for (int kb = 0; kb < p.KB; ++kb) {
@@ -942,12 +1019,12 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
                 ptx::mbar_wait_sleep(&bars->full[stage], phase);
                 ptx::tc_fence_after();
               }
-              const uint32_t a_addr = ptx::smem_u32(smem_a + (r * p.KB + kb) * A_BLK_BYTES);
-              const uint32_t b_addr = ptx::smem_u32(smem_b + stage * B_STAGE_BYTES);
+              const uint32_t a_lo = a_lo0 + uint32_t(r * p.KB + kb) * (A_BLK_BYTES >> 4);
+              const uint32_t b_lo = b_lo0 + uint32_t(stage) * (B_STAGE_BYTES >> 4);
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) {
-                ptx::umma_bf16_ss(d_tmem, ptx::umma_desc_sw128_kmajor(a_addr + k * UMMA_K * 2),
-                                  ptx::umma_desc_sw128_kmajor(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0);
+                ptx::umma_bf16_ss(d_tmem, DESC_HI | (a_lo + k * (UMMA_K * 2 >> 4)),
+                                  DESC_HI | (b_lo + k * (UMMA_K * 2 >> 4)), idesc, (kb | k) != 0);
               }
               if (r == RT - 1) ptx::umma_commit(&bars->empty[stage]);  // frees the stage once these MMAs have read it
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -1233,6 +1310,7 @@ struct MatchConfig {
   int pair = -1;        // match.pair  1 / 0: force / forbid the paired-row kernel
   int rt = -1;          // match.rt    1 / 2: row tiles per CTA of match_kernel
   int ctas = -1;        // match.ctas  grid of the persistent kernels (default: one CTA per SM)
+  int cta2 = -1;        // match.cta2  1 / 0: allow / forbid CTA pairs (cta_group::2) in the paired-row kernel
 };
 MatchConfig g_cfg;
 
@@ -1252,6 +1330,7 @@ int match_config_set(const char* key, int value) {
   if (!strcmp(key, "match.pair")) { g_cfg.pair = value; return GADM_OK; }
   if (!strcmp(key, "match.rt")) { g_cfg.rt = value; return GADM_OK; }
   if (!strcmp(key, "match.ctas")) { g_cfg.ctas = value; return GADM_OK; }
+  if (!strcmp(key, "match.cta2")) { g_cfg.cta2 = value; return GADM_OK; }
   return GADM_ERR_BAD_ARG;
 }
 
@@ -1262,8 +1341,10 @@ int match_configure(int device) {
   if ((rc = set_smem_limit(match_kernel<true, 1>)) != GADM_OK) return rc;
   if ((rc = set_smem_limit(match_kernel<false, 2>)) != GADM_OK) return rc;
   if ((rc = set_smem_limit(match_kernel<true, 2>)) != GADM_OK) return rc;
-  if ((rc = set_smem_limit(match_pair_kernel<false>)) != GADM_OK) return rc;
-  if ((rc = set_smem_limit(match_pair_kernel<true>)) != GADM_OK) return rc;
+  if ((rc = set_smem_limit(match_pair_kernel<false, false>)) != GADM_OK) return rc;
+  if ((rc = set_smem_limit(match_pair_kernel<true, false>)) != GADM_OK) return rc;
+  if ((rc = set_smem_limit(match_pair_kernel<false, true>)) != GADM_OK) return rc;
+  if ((rc = set_smem_limit(match_pair_kernel<true, true>)) != GADM_OK) return rc;
   if ((rc = set_smem_limit(match_alt_kernel<false, false>)) != GADM_OK) return rc;
   if ((rc = set_smem_limit(match_alt_kernel<true, false>)) != GADM_OK) return rc;
   if ((rc = set_smem_limit(match_alt_kernel<false, true>)) != GADM_OK) return rc;
@@ -1330,7 +1411,7 @@ static int match_launch_t(const void* rows, const void* cols, MatchParams p, int
     // SOFT 0.384 ms against 0.400 ms (RT = 1), ARGMAX 0.241 ms against 0.211 ms (RT = 2) => default for SOFT only.
     const bool pair = cfg.pair < 0 ? kSoft : cfg.pair != 0;
     const int pstages = match_pair_stages<kSoft>(KB);
-    if (pair && pstages >= 2 * KB && p.N > BM) {
+    if (pair && pstages >= 2 * KB && KB <= P_MAX_KB && p.N > BM) {
       p.KB = KB; p.stages = pstages;
       CUtensorMap tmap_rows, tmap_cols;
       int rc = make_tmap_2b_3d(&tmap_rows, rows, uint64_t(Kp), uint64_t(p.N), uint64_t(p.B), BK, BM, 0);
@@ -1338,7 +1419,26 @@ static int match_launch_t(const void* rows, const void* cols, MatchParams p, int
       rc = make_tmap_2b_3d(&tmap_cols, cols, uint64_t(Kp), uint64_t(p.M), uint64_t(p.n_obj), BK, PBN, 0);
       if (rc != GADM_OK) return rc;
       dim3 grid((p.N + 2 * BM - 1) / (2 * BM), p.B);
-      match_pair_kernel<kSoft><<<grid, NUM_THREADS, match_pair_smem_bytes<kSoft>(KB, pstages), stream>>>(
+      if (cfg.cta2 != 0) {
+        // CTA pairs: clusters of two row blocks of a frame share every model tile (half each)
+        const int cstages = match_pair_stages<kSoft>(KB, true);
+        p.stages = cstages;
+        rc = make_tmap_2b_3d(&tmap_cols, cols, uint64_t(Kp), uint64_t(p.M), uint64_t(p.n_obj), BK, PBN / 2, 0);
+        if (rc != GADM_OK) return rc;
+        grid.x = (grid.x + 1) & ~1u;
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = grid; lc.blockDim = dim3(NUM_THREADS);
+        lc.dynamicSmemBytes = match_pair_smem_bytes<kSoft>(KB, cstages, true);
+        lc.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&lc, match_pair_kernel<kSoft, true>, tmap_rows, tmap_cols, p);
+        if (e != cudaSuccess) return set_cuda_error(e);
+        return check_launch();
+      }
+      match_pair_kernel<kSoft, false><<<grid, NUM_THREADS, match_pair_smem_bytes<kSoft>(KB, pstages), stream>>>(
           tmap_rows, tmap_cols, p);
       return check_launch();
     }

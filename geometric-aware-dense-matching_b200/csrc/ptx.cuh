@@ -106,6 +106,69 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
       : "memory");
 }
 
+// ----------------------------------------------------------------------------- CTA pairs (cta_group::2)
+// Two CTAs of a cluster on the two SMs of a TPC execute one tcgen05.mma together: M = 256 (each CTA's TMEM receives its
+// own 128 rows), each CTA supplies its 128 rows of A and HALF of the B tile (N/2 columns) from the same shared-memory
+// offsets.  Only the leader (cluster rank 0) issues; the barriers the issuer waits on live in the leader's shared
+// memory and the peer reaches them through the cluster window.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// (default semantics, release at CTA scope: what the arrival orders here is tcgen05.ld traffic, fenced separately;
+// .release.cluster compiles to MEMBAR.ALL.GPU in front of every arrival)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 3-D tiled load into THIS CTA's shared memory; the bytes complete on a barrier given by its cluster address
+// (the leader's, for operands of a paired MMA)
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                 int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 x 16: 128 rows from each CTA] * B[N x 16: N/2 columns from each CTA]^T
+__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs once the pair's MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(uint16_t(3))
+      : "memory");
+}
+
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
@@ -369,16 +432,18 @@ __device__ __forceinline__ uint64_t ex2_2(uint64_t t) {
 __device__ __forceinline__ void sts32(uint32_t saddr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
 }
-// predicated (branch-free) store of four packed pairs = 8 floats: float4 k goes to saddr + k * 8192
-// (the stash of the matcher epilogue: plane-major so that a full warp stores without bank conflicts)
-__device__ __forceinline__ void sts_stash8(bool pred, uint32_t saddr, uint64_t v0, uint64_t v1, uint64_t v2,
-                                           uint64_t v3) {
+// predicated (branch-free) store of 8 floats: float4 k goes to saddr + k * 8192 (the stash of the matcher epilogue:
+// plane-major so that a full warp stores without bank conflicts).  The operands are the UNPACKED scores the max tree
+// reads anyway: handing the store the packed f32x2 pairs makes ptxas copy every stored register (the pair is
+// overwritten in place by the exponent multiply): 229 -> 201 instructions per 32 scores of the SOFT epilogue.
+__device__ __forceinline__ void sts_stash8(bool pred, uint32_t saddr, const float (&f)[8]) {
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
       "setp.ne.b32 P, %0, 0;\n\t"
-      "@P st.shared.v2.b64 [%1], {%2, %3};\n\t"
-      "@P st.shared.v2.b64 [%1 + 8192], {%4, %5};\n\t}\n"
-      ::"r"(uint32_t(pred)), "r"(saddr), "l"(v0), "l"(v1), "l"(v2), "l"(v3)
+      "@P st.shared.v4.f32 [%1], {%2, %3, %4, %5};\n\t"
+      "@P st.shared.v4.f32 [%1 + 8192], {%6, %7, %8, %9};\n\t}\n"
+      ::"r"(uint32_t(pred)), "r"(saddr), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]),
+        "f"(f[7])
       : "memory");
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }  // -> FMNMX3

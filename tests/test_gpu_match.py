@@ -323,10 +323,11 @@ def cfg():
 
 @pytest.mark.parametrize("env", [{"match.alt": 0, "match.pair": 0, "match.rt": 1},
                                  {"match.alt": 0, "match.pair": 0, "match.rt": 2},
-                                 {"match.alt": 0, "match.pair": 1},
+                                 {"match.alt": 0, "match.pair": 1}, {"match.alt": 0, "match.pair": 1, "match.cta2": 0},
                                  {"match.alt": 1}, {"match.ctas": 5}, {"match.ctas": 37}, {"match.ctas": 1}])
 def test_match_kernel_variants_agree(cuda, cfg, env):
-    """The kernels of the matcher (one row tile per CTA, two row tiles per CTA, paired rows per thread, the
+    """The kernels of the matcher (one row tile per CTA, two row tiles per CTA, paired rows per thread with and
+    without CTA pairs -- cta_group::2 MMAs over a cluster of two row blocks --, the
     persistent kernels with their units dealt out to 148 / 37 / 5 / 1 CTAs -- row blocks split over two or more
     CTAs and merged by the last to arrive) are selected per launch; every one of them must meet the same gates on a
     ragged shape, in both modes."""
@@ -391,6 +392,7 @@ def test_match_bf16n_operands_and_unit_argmax(cuda):
 
 
 @pytest.mark.parametrize("env", [{}, {"match.alt": 0}, {"match.alt": 0, "match.rt": 1},
+                                 {"match.alt": 0, "match.pair": 1}, {"match.alt": 0, "match.pair": 1, "match.cta2": 0},
                                  {"match.ctas": 3}, {"match.ctas": 11}, {"match.ctas": 50}])
 def test_match_exact_ties_first_index_wins(cuda, cfg, env):
     """torch.max returns the FIRST maximal index of the scores it is given (evaluator.py:93).  Model vertices duplicated bit for bit across
