@@ -745,9 +745,9 @@ def run_ycbv(args):
 
 def pyr_launches(pyr):
     """Kernel launches of one gadm_knn3d call (knn3d.cu): 4 grid-build kernels when any job uses the grid
-    (AUTO: n_support >= 512), then one query kernel per algorithm present."""
-    any_grid = any(j.n_support >= 512 for j in pyr.jobs)
-    any_brute = any(j.n_support < 512 for j in pyr.jobs)
+    (AUTO: n_support >= 128, g_grid_min_support), then one query kernel per algorithm present."""
+    any_grid = any(j.n_support >= 128 for j in pyr.jobs)
+    any_brute = any(j.n_support < 128 for j in pyr.jobs)
     return (4 + 1 if any_grid else 0) + (1 if any_brute else 0)
 
 

@@ -434,6 +434,14 @@ int match_stages(int RT, int KB) {
 constexpr int PBN = 128;                       // model vertices per tile
 constexpr int PB_STAGE_BYTES = PBN * BK * 2;   // 16 KB
 constexpr int P_MAX_STAGES = 8;
+// Pairs (of the 4 per 4 columns x 2 rows) whose 2^x runs on the FMA pipe (ptx::ex2_2_poly) instead of MUFU.EX2.
+// Measured at the BASELINE shape: 0 -> 0.353 ms, 1 -> 0.377 ms, 2 -> 0.424 ms, 3 -> 0.473 ms: every exponential moved
+// off the XU pipe makes the kernel slower, i.e. MUFU (59 % busy) is not what bounds the epilogue -- its 16 warps are
+// latency-bound on their own instruction streams (5.9 cycles per instruction and warp), so instructions are what
+// counts.  Kept at 0; the switch stays for the record and for other shapes.
+#ifndef GADM_SOFT_POLY
+#define GADM_SOFT_POLY 0
+#endif
 constexpr int P_MAX_KB = 4;                    // K blocks of a model tile (the issue loop is unrolled over them)
 constexpr int P_PLANE_BYTES = PBN * 4;
 constexpr int P_CS = PBN / 4;                  // 32 columns per warp slice
@@ -714,10 +722,15 @@ match_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
 #else
 #define GADM_EX2(x) ptx::ex2_2(x)
 #endif
+            // GADM_SOFT_POLY of the 4 pairs take the FMA-pipe polynomial instead of MUFU.EX2 (never in the ragged
+            // tile, whose masked columns are -inf)
             const uint64_t pa0 = GADM_EX2(ptx::fmul2(v[0][j4 * 2 + 0], g20));
-            const uint64_t pb0 = GADM_EX2(ptx::fmul2(v[0][j4 * 2 + 1], g20));
-            const uint64_t pa1 = GADM_EX2(ptx::fmul2(v[1][j4 * 2 + 0], g21));
-            const uint64_t pb1 = GADM_EX2(ptx::fmul2(v[1][j4 * 2 + 1], g21));
+            const uint64_t pb0 = (!kGuard && GADM_SOFT_POLY >= 1) ? ptx::ex2_2_poly(v[0][j4 * 2 + 1], g20)
+                                                                  : GADM_EX2(ptx::fmul2(v[0][j4 * 2 + 1], g20));
+            const uint64_t pa1 = (!kGuard && GADM_SOFT_POLY >= 3) ? ptx::ex2_2_poly(v[1][j4 * 2 + 0], g21)
+                                                                  : GADM_EX2(ptx::fmul2(v[1][j4 * 2 + 0], g21));
+            const uint64_t pb1 = (!kGuard && GADM_SOFT_POLY >= 2) ? ptx::ex2_2_poly(v[1][j4 * 2 + 1], g21)
+                                                                  : GADM_EX2(ptx::fmul2(v[1][j4 * 2 + 1], g21));
 #undef GADM_EX2
             l2[0] = ptx::fadd2(l2[0], ptx::fadd2(pa0, pb0));
             l2[1] = ptx::fadd2(l2[1], ptx::fadd2(pa1, pb1));
@@ -1310,7 +1323,7 @@ struct MatchConfig {
   int pair = -1;        // match.pair  1 / 0: force / forbid the paired-row kernel
   int rt = -1;          // match.rt    1 / 2: row tiles per CTA of match_kernel
   int ctas = -1;        // match.ctas  grid of the persistent kernels (default: one CTA per SM)
-  int cta2 = -1;        // match.cta2  1 / 0: allow / forbid CTA pairs (cta_group::2) in the paired-row kernel
+  int cta2 = -1;        // match.cta2  1: CTA pairs (cta_group::2) in the paired-row kernel (default: single CTAs)
 };
 MatchConfig g_cfg;
 
@@ -1419,8 +1432,10 @@ static int match_launch_t(const void* rows, const void* cols, MatchParams p, int
       rc = make_tmap_2b_3d(&tmap_cols, cols, uint64_t(Kp), uint64_t(p.M), uint64_t(p.n_obj), BK, PBN, 0);
       if (rc != GADM_OK) return rc;
       dim3 grid((p.N + 2 * BM - 1) / (2 * BM), p.B);
-      if (cfg.cta2 != 0) {
-        // CTA pairs: clusters of two row blocks of a frame share every model tile (half each)
+      if (cfg.cta2 == 1) {
+        // CTA pairs (opt-in): clusters of two row blocks of a frame share every model tile (half each).  Measured at
+        // the BASELINE shape: shared-memory operand wavefronts -25 %, L2 -> SM traffic -35 %, time unchanged (0.357
+        // against 0.353 ms) -- the epilogue's instruction streams bound this kernel, not its operand traffic.
         const int cstages = match_pair_stages<kSoft>(KB, true);
         p.stages = cstages;
         rc = make_tmap_2b_3d(&tmap_cols, cols, uint64_t(Kp), uint64_t(p.M), uint64_t(p.n_obj), BK, PBN / 2, 0);

@@ -429,6 +429,26 @@ __device__ __forceinline__ uint64_t ex2_2(uint64_t t) {
       : "=l"(d) : "l"(t));
   return d;
 }
+// 2^(v * g) on both halves WITHOUT the MUFU: round-to-nearest split through the 1.5 * 2^23 constant, degree-4 minimax
+// polynomial of 2^f on [-0.5, 0.5] (relative error 2.7e-6), exponent added as an integer.  Seven packed FMA-pipe
+// instructions and two IMAD per pair of scores, against one FMUL2 and two MUFU.EX2 (8 cycles of the XU pipe each): the
+// SOFT epilogue computes part of its exponentials this way because MUFU, not the FMA pipe, is what it saturates.
+// Needs |v * g| < 2^21 and finite (the epilogue guarantees |v * g| <= 58; columns masked to -inf take the MUFU path).
+__device__ __forceinline__ uint64_t ex2_2_poly(uint64_t v, uint64_t g2) {
+  const uint64_t magic = pack2f(12582912.f, 12582912.f), minus1 = pack2f(-1.f, -1.f);
+  const uint64_t t = ffma2(v, g2, magic);          // low mantissa bits = n = round(v * g)
+  const uint64_t nn = ffma2(t, minus1, magic);     // -n as a float (exact)
+  const uint64_t f = ffma2(v, g2, nn);             // v * g - n in [-0.5, 0.5], one rounding
+  uint64_t q = ffma2(pack2f(0.009570077061653137f, 0.009570077061653137f), f,
+                     pack2f(0.055917829275131226f, 0.055917829275131226f));
+  q = ffma2(q, f, pack2f(0.240247443318367f, 0.240247443318367f));
+  q = ffma2(q, f, pack2f(0.6931217908859253f, 0.6931217908859253f));
+  q = ffma2(q, f, pack2f(0.9999992847442627f, 0.9999992847442627f));
+  uint32_t tl, th, ql, qh;
+  unpack2(t, tl, th);
+  unpack2(q, ql, qh);
+  return pack2(ql + (tl << 23), qh + (th << 23));  // 2^n: the shift drops everything but n mod 512
+}
 __device__ __forceinline__ void sts32(uint32_t saddr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
 }

@@ -323,7 +323,7 @@ def cfg():
 
 @pytest.mark.parametrize("env", [{"match.alt": 0, "match.pair": 0, "match.rt": 1},
                                  {"match.alt": 0, "match.pair": 0, "match.rt": 2},
-                                 {"match.alt": 0, "match.pair": 1}, {"match.alt": 0, "match.pair": 1, "match.cta2": 0},
+                                 {"match.alt": 0, "match.pair": 1}, {"match.alt": 0, "match.pair": 1, "match.cta2": 1},
                                  {"match.alt": 1}, {"match.ctas": 5}, {"match.ctas": 37}, {"match.ctas": 1}])
 def test_match_kernel_variants_agree(cuda, cfg, env):
     """The kernels of the matcher (one row tile per CTA, two row tiles per CTA, paired rows per thread with and
@@ -392,7 +392,7 @@ def test_match_bf16n_operands_and_unit_argmax(cuda):
 
 
 @pytest.mark.parametrize("env", [{}, {"match.alt": 0}, {"match.alt": 0, "match.rt": 1},
-                                 {"match.alt": 0, "match.pair": 1}, {"match.alt": 0, "match.pair": 1, "match.cta2": 0},
+                                 {"match.alt": 0, "match.pair": 1}, {"match.alt": 0, "match.pair": 1, "match.cta2": 1},
                                  {"match.ctas": 3}, {"match.ctas": 11}, {"match.ctas": 50}])
 def test_match_exact_ties_first_index_wins(cuda, cfg, env):
     """torch.max returns the FIRST maximal index of the scores it is given (evaluator.py:93).  Model vertices duplicated bit for bit across

@@ -23,7 +23,7 @@ flop = 2.0 * N * M * D * B
 PEAK = 1658.8
 
 # (label, mode, bf16n operands, config switches)
-CASES = [("argmax", "argmax", False, {}), ("soft", "soft", False, {}), ("soft_cta1", "soft", False, {"match.cta2": 0}),
+CASES = [("argmax", "argmax", False, {}), ("soft", "soft", False, {}), ("soft_cta2", "soft", False, {"match.cta2": 1}),
          ("argmax_bf16n", "argmax_bf16n", True, {}), ("argmax_unit", "argmax_unit", True, {})]
 if os.environ.get("CASES"):
     CASES = [c for c in CASES if c[0] in os.environ["CASES"].split(",")]

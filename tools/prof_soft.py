@@ -1,5 +1,5 @@
 """Profiling driver (for ncu; not a benchmark): the SOFT matcher at the BASELINE shape, once per kernel variant --
-CTA pairs (cta_group::2, the default) and single CTAs (match.cta2 = 0)."""
+single CTAs (the default) and CTA pairs (cta_group::2, match.cta2 = 1)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
