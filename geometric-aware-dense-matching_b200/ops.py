@@ -56,8 +56,8 @@ def prep_rows(feat: torch.Tensor, operand_mode: int, pad_mode: int) -> tuple[tor
 def _(feat, operand_mode, pad_mode):
     B, d, N = feat.shape
     kp = d * (3 if operand_mode == 1 else 1)
-    return (feat.new_empty((B, N, kp), dtype=torch.bfloat16), feat.new_empty((B, N)),
-            feat.new_empty((B, N) if pad_mode else (0,)))
+    return (feat.new_empty((B, N, kp), dtype=torch.bfloat16), feat.new_empty((B, N), dtype=torch.float32),
+            feat.new_empty((B, N) if pad_mode else (0,), dtype=torch.float32))
 
 
 @torch.library.custom_op("gadm::prep_model", mutates_args=(), device_types="cuda")
