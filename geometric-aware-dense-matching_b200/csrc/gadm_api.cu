@@ -73,6 +73,7 @@ int gadm_abi_version(void) { return 3; }
 
 int gadm_config_set(const char* key, int value) {
   if (!key) return GADM_ERR_BAD_ARG;
+  if (!strncmp(key, "knn.", 4)) return knn3d_config_set(key, value);
   return match_config_set(key, value);
 }
 

@@ -63,6 +63,7 @@ int kabsch_pose_launch(const double* mom, const double* count, const uint8_t* de
 
 // knn3d.cu
 int knn3d_configure();
+int knn3d_config_set(const char* key, int value);
 size_t knn3d_workspace_bytes(const gadm_knn_job* jobs, int n_jobs, int algo);
 int knn3d_launch(const float* support, const float* query, const gadm_knn_job* jobs, int n_jobs, int algo,
                  int32_t* idx, float* dist2, void* workspace, size_t workspace_bytes, cudaStream_t stream);

@@ -18,6 +18,7 @@
 //          the whole cloud.  Selection is the same lexicographic insertion, so results are identical to BRUTE.
 #include <float.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "gadm_internal.h"
 
@@ -655,11 +656,23 @@ bool same_cloud(const gadm_knn_job& a, const gadm_knn_job& b) {
 
 }  // namespace
 
-int knn3d_configure() {
-  // tuning knobs for experiments (results are identical for every setting)
-  if (const char* s = getenv("GADM_KNN_PPC")) { const float v = float(atof(s)); if (v >= 1.f && v <= 64.f) g_ppc = v; }
-  if (const char* s = getenv("GADM_KNN_GRID_MIN")) { const int v = atoi(s); if (v >= 1) g_grid_min_support = v; }
-  return GADM_OK;
+int knn3d_configure() { return GADM_OK; }
+
+// tuning knobs for experiments (gadm_config_set; results are identical for every setting; -1 restores the default)
+int knn3d_config_set(const char* key, int value) {
+  if (!strcmp(key, "knn.ppc")) {            // target points per occupied cell column
+    if (value < 0) { g_ppc = 16.f; return GADM_OK; }
+    if (value < 1 || value > 64) return GADM_ERR_BAD_ARG;
+    g_ppc = float(value);
+    return GADM_OK;
+  }
+  if (!strcmp(key, "knn.grid_min")) {       // AUTO: clouds with fewer points are scanned by BRUTE
+    if (value < 0) { g_grid_min_support = 128; return GADM_OK; }
+    if (value < 1) return GADM_ERR_BAD_ARG;
+    g_grid_min_support = value;
+    return GADM_OK;
+  }
+  return GADM_ERR_BAD_ARG;
 }
 
 size_t knn3d_workspace_bytes(const gadm_knn_job* jobs, int n_jobs, int algo) {

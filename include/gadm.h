@@ -70,7 +70,11 @@ int gadm_init(int device);
 /* Kernel-selection switches for profiling and tests; -1 restores the automatic choice.  Keys:
  *   "match.alt"   0 forbids the alternating persistent ARGMAX kernel        "match.pair"  1 / 0 forces / forbids the paired-row kernel
  *   "match.rt"    1 / 2 row tiles per CTA of the generic kernel             "match.ctas"  grid of the persistent kernels (<= SM count)
- * Results do not depend on any of them.  GADM_ERR_BAD_ARG for an unknown key. */
+ *   "match.cta2"  1: CTA pairs (clusters of two, tcgen05.mma.cta_group::2) in the paired-row kernel
+ *   "knn.ppc"     target points per occupied grid cell column (1..64, default 16)
+ *   "knn.grid_min" GADM_KNN_AUTO scans clouds with fewer points than this (default 128)
+ * Results do not depend on any of them.  GADM_ERR_BAD_ARG for an unknown key.  The library reads no environment
+ * variable. */
 int gadm_config_set(const char* key, int value);
 /* cudaGetLastError text of the most recent GADM_ERR_CUDA on this thread ("" if none). */
 const char* gadm_last_cuda_error(void);

@@ -128,3 +128,22 @@ def test_knn3d_errors(cuda):
         ops.knn3d(s, s, 16, 2)          # k > n_support: the reference leaves stale ids, we refuse
     with pytest.raises(_lib.GadmError):
         ops.knn3d(torch.rand(1, 100, 3, device=cuda), s, 33, 2)   # k > 32 unsupported
+
+
+@pytest.mark.parametrize("switches", [{"knn.ppc": 4}, {"knn.ppc": 40}, {"knn.grid_min": 1}, {"knn.grid_min": 100000}])
+def test_knn3d_tuning_switches_do_not_change_results(cuda, switches):
+    """gadm_config_set('knn.*'): cell size of the grid and the cloud size below which AUTO scans -- performance knobs
+    only (the library reads no environment variable); the output stays bit-identical to the oracle."""
+    from gadm_b200 import _lib
+    s, q = _clouds(99, 2, 3000, 1500, "surface")
+    ref_idx, ref_d2 = ko.knn_port(s, q, 16, return_dist=True)
+    try:
+        for k_, v in switches.items():
+            _lib.config_set(k_, v)
+        idx, d2 = _run(cuda, s, q, 16, "auto")
+    finally:
+        for k_ in switches:
+            _lib.config_set(k_, -1)
+    assert np.array_equal(d2, ref_d2) and np.array_equal(idx.astype(np.int64), ref_idx)
+    with pytest.raises(_lib.GadmError):
+        _lib.config_set("knn.ppc", 1000)

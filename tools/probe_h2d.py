@@ -7,6 +7,8 @@ Every rank copies the end-to-end leg's own transfer sizes (bench.py: 30.1 MB in,
 large 256 MB buffer between pinned host memory and its GPU, first alone (ranks take turns), then all ranks together
 after a barrier.  The ratio together / alone is what the host's memory system and PCIe topology leave of one GPU's
 copy bandwidth when N ranks stream at once: the ceiling of the e2e scaling efficiency that `bench.py --gpus N` can reach.
+Last, the step's own copy pattern: 27.96 MB in and 16.38 MB out concurrently on two streams, every rank at once -- the time
+of that pair is the floor of an end-to-end step on this box whatever the kernels do ("e2e_copy_floor").
 One JSON line on rank 0."""
 import json
 import os
@@ -72,6 +74,47 @@ def main():
                      "d2h_together_gbs_per_rank": [round(v, 1) for v in m[:, 3].tolist()],
                      "h2d_together_over_alone": round(float(m[:, 2].sum() / m[:, 0].sum()), 3),
                      "d2h_together_over_alone": round(float(m[:, 3].sum() / m[:, 1].sum()), 3)}
+    # the end-to-end step's own copies, both directions at once, every rank at once
+    n_in, n_out = 27_959_296, 16_384_256
+    h_in = torch.empty((n_in,), dtype=torch.uint8).pin_memory()
+    d_in = torch.empty((n_in,), dtype=torch.uint8, device=dev)
+    h_out = torch.empty((n_out,), dtype=torch.uint8).pin_memory()
+    d_out = torch.empty((n_out,), dtype=torch.uint8, device=dev)
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    floors = {}
+    for mode in ("alone", "together"):
+        ms = 0.0
+        for turn in range(world if mode == "alone" else 1):
+            if world > 1:
+                dist.barrier()
+            if mode == "together" or turn == rank:
+                reps = 40
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                a.record()
+                s_in.wait_event(a); s_out.wait_event(a)
+                for _ in range(reps):
+                    with torch.cuda.stream(s_in):
+                        d_in.copy_(h_in, non_blocking=True)
+                    with torch.cuda.stream(s_out):
+                        h_out.copy_(d_out, non_blocking=True)
+                e1, e2 = torch.cuda.Event(), torch.cuda.Event()
+                e1.record(s_in); e2.record(s_out)
+                torch.cuda.current_stream().wait_event(e1); torch.cuda.current_stream().wait_event(e2)
+                b.record()
+                b.synchronize()
+                ms = a.elapsed_time(b) / reps
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            allt = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+        else:
+            allt = [t]
+        floors[mode] = [round(float(x.item()), 3) for x in allt]
+    worst = max(floors["together"])
+    res["e2e_copy_floor"] = {"ms_per_step_alone_per_rank": floors["alone"], "ms_per_step_together_per_rank": floors["together"],
+                             "frames_per_s_ceiling": round(8 * world / worst * 1e3, 1),
+                             "note": "8 frames per rank and step; ceiling = 8 * ranks / slowest rank's copy time"}
     if rank == 0:
         print(json.dumps({"probe": "pinned host <-> device copies, all ranks at once", "n_gpus": world,
                           "host_cores": os.cpu_count(), "results": res}))
