@@ -4,7 +4,7 @@ The reference moves every sample host -> device -> host synchronously (train_lm.
 dict tensor by tensor, evaluator.py:87,99 pulls indices and clouds back per frame).  FrameStream keeps `depth`
 batches in flight,
 
-    pinned host batch --ONE H2D (copy stream)--> prep_rows + match_fwd + kNN pyramid (compute stream)
+    pinned host batch --ONE H2D (copy stream)--> prep_rows + match_fwd (compute stream) | kNN pyramid (its own stream)
                       --ONE D2H (second copy stream)--> pinned host results
 
 so the PCIe copies of batch i+1 / i-1 overlap the kernels of batch i.  Every byte still crosses the bus every batch;
@@ -64,6 +64,7 @@ class FrameStream:
         self.dev = dev
         self.h2d = torch.cuda.Stream(device=dev)
         self.d2h = torch.cuda.Stream(device=dev)
+        self.knn = torch.cuda.Stream(device=dev)        # the pyramid has no data dependence on the matcher
         self.world = dist.get_world_size() if (gather and dist.is_available() and dist.is_initialized()) else 1
         self.coll = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self.rgbd_bytes = B * d * N * 2
@@ -85,6 +86,7 @@ class FrameStream:
             s.gathered = (torch.empty((self.world, self.rec_elems), dtype=torch.int32, device=dev)
                           if self.world > 1 else None)
             s.h2d_done = torch.cuda.Event()
+            s.knn_done = torch.cuda.Event()
             s.compute_done = torch.cuda.Event()
             s.d2h_done = torch.cuda.Event()
             s.coll_done = torch.cuda.Event()
@@ -110,8 +112,10 @@ class FrameStream:
             s.dev_in.copy_(batch.flat, non_blocking=True)
             s.h2d_done.record(self.h2d)
         compute.wait_event(s.h2d_done)
+        self.knn.wait_event(s.h2d_done)
         if s.used:
             compute.wait_event(s.d2h_done)              # the copy (and the collective) that read this slot's outputs
+            self.knn.wait_event(s.d2h_done)
             if self.coll is not None:
                 compute.wait_event(s.coll_done)
         om, pm = OPERAND_MODES[self.bank.operand_mode], PAD_MODES["none"]
@@ -120,7 +124,10 @@ class FrameStream:
                              MATCH_MODES[self.mode])
         rec = s.dev_out[: self.rec_elems]
         ops.pack_match_outputs(outs[0], outs[1], outs[2], outs[3], rec)
-        self.pyr.run_packed(s.pts, out=s.dev_out[self.rec_elems:])
+        with torch.cuda.stream(self.knn):
+            self.pyr.run_packed(s.pts, out=s.dev_out[self.rec_elems:])
+            s.knn_done.record(self.knn)
+        compute.wait_event(s.knn_done)
         s.compute_done.record(compute)
         with torch.cuda.stream(self.d2h):
             self.d2h.wait_event(s.compute_done)
