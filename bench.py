@@ -494,7 +494,7 @@ def run_gpu(args):
                             "collective": ("all_gather of the matcher records on a side stream, in the device-resident "
                                            "and in the end-to-end loop") if world > 1 else "none",
                             "e2e_host_buffers": "one packed pinned buffer per batch: bf16 descriptors + fp32 points in, "
-                                                "int32/fp32 records + kNN indices out",
+                                                "int32/fp32 records + uint16 kNN indices out",
                             "host_threads_per_rank": torch.get_num_threads(), "numa_node": numa},
             "breakdown_ms": {"match_kernel": match_ms, "knn_pyramid": knn_ms,
                              "note": ("serial: prep, match, kNN" if args.no_overlap else

@@ -39,6 +39,7 @@ SIGNATURES = {
                                    c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gadm_pack_match_outputs": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p]),
+    "gadm_pack_indices_u16": (c_int, [c_void_p, ctypes.c_int64, c_void_p, c_void_p]),
     "gadm_prep_model": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "gadm_match_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,

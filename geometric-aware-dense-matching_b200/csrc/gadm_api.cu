@@ -175,6 +175,13 @@ int gadm_pack_match_outputs(const int64_t* idx, const float* max_sim, const floa
   return pack_outputs_launch(idx, max_sim, weight, soft_xyz, size_t(n), out, (cudaStream_t)stream);
 }
 
+int gadm_pack_indices_u16(const int32_t* idx, int64_t n, uint16_t* out, gadm_stream_t stream) {
+  GADM_REQUIRE_INIT();
+  if (!idx || !out || n <= 0) return GADM_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(idx) & 7) || (reinterpret_cast<uintptr_t>(out) & 3)) return GADM_ERR_ALIGN;
+  return pack_u16_launch(idx, size_t(n), out, (cudaStream_t)stream);
+}
+
 int gadm_prep_model(const float* mesh, const float* model_xyz, int n_obj, int d, int M, int operand_mode, void* cols,
                     float* aux, gadm_stream_t stream) {
   GADM_REQUIRE_INIT();

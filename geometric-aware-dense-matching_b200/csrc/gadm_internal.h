@@ -52,6 +52,7 @@ int compact_rows_launch(const uint8_t* mask, int B, int N, int32_t* pos, int32_t
                         cudaStream_t stream);
 int pack_outputs_launch(const int64_t* idx, const float* max_sim, const float* weight, const float* soft_xyz, size_t n,
                         int32_t* out, cudaStream_t stream);
+int pack_u16_launch(const int32_t* idx, size_t n, uint16_t* out, cudaStream_t stream);
 int prep_model_launch(const float* mesh, const float* model_xyz, int n_obj, int d, int M, int operand_mode, void* cols,
                       float* aux, cudaStream_t stream);
 int seg_mask_launch(const float* seg, int B, int N, uint8_t* mask, cudaStream_t stream);

@@ -255,6 +255,24 @@ int pack_outputs_launch(const int64_t* idx, const float* max_sim, const float* w
   return check_launch();
 }
 
+// int32 indices -> uint16 (two per thread, one 32-bit store): halves the device-to-host bytes of the kNN pyramid when
+// every support cloud has fewer than 65536 points
+__global__ void __launch_bounds__(256)
+pack_u16_kernel(const int32_t* __restrict__ idx, size_t n, uint16_t* __restrict__ out) {
+  const size_t i = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
+  if (i + 1 < n) {
+    const int2 v = *reinterpret_cast<const int2*>(idx + i);
+    *reinterpret_cast<uint32_t*>(out + i) = (uint32_t(v.x) & 0xFFFFu) | (uint32_t(v.y) << 16);
+  } else if (i < n) {
+    out[i] = uint16_t(idx[i]);
+  }
+}
+
+int pack_u16_launch(const int32_t* idx, size_t n, uint16_t* out, cudaStream_t stream) {
+  pack_u16_kernel<<<unsigned((n / 2 + 256) / 256), 256, 0, stream>>>(idx, n, out);
+  return check_launch();
+}
+
 int prep_model_launch(const float* mesh, const float* model_xyz, int n_obj, int d, int M, int operand_mode, void* cols,
                       float* aux, cudaStream_t stream) {
   dim3 grid((M + PTS - 1) / PTS, n_obj);

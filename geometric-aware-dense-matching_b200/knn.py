@@ -98,6 +98,10 @@ class KnnPyramid:
         return self.unpack(flat)
 
     def unpack(self, flat):
+        """flat index buffer (int32, or the uint16 transport form of pipeline.FrameStream) -> the reference's dict of
+        int32 [B, nq, k] arrays (datasets/lm/linemod_pbr.py:534-569 keys)."""
+        if flat.dtype != torch.int32:
+            flat = flat.to(torch.int32)
         out = {}
         for name, off, nq, k in self.names:
             out[name] = flat[off: off + self.B * nq * k].view(self.B, nq, k)

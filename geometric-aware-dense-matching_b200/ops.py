@@ -157,6 +157,17 @@ def pack_match_outputs(idx: torch.Tensor, max_sim: torch.Tensor, weight: torch.T
                                                _stream()), "gadm_pack_match_outputs")
 
 
+@torch.library.custom_op("gadm::pack_indices_u16", mutates_args=("out",), device_types="cuda")
+def pack_indices_u16(idx: torch.Tensor, out: torch.Tensor) -> None:
+    """int32 neighbour indices -> uint16 (every support cloud < 65536 points): half the bytes on the bus."""
+    _need(idx, torch.int32, "idx"); _need(out, torch.uint16, "out")
+    if out.numel() != idx.numel():
+        raise ValueError("pack_indices_u16: out must hold one uint16 per index")
+    lib = _lib_for(idx)
+    with torch.cuda.device(idx.device):
+        _lib.check(lib.gadm_pack_indices_u16(_ptr(idx), idx.numel(), _ptr(out), _stream()), "gadm_pack_indices_u16")
+
+
 _MATCH_WS = {}
 
 

@@ -13,7 +13,9 @@ nothing is cached between batches.  What crosses it is packed and as small as th
   in   [ descriptors bf16 [B, d, N] | points fp32 [B, P, 3] ]  -- the matcher consumes bf16-representable descriptors
        (DESIGN.md "precision contract"), so a bf16 host buffer carries exactly the operand values at half the bytes; the
        points are laid out as KnnPyramid's flat buffer (cloud, then the 1/2, 1/4, 1/8 image grids of every frame)
-  out  [ records int32 [B, N, 6] = {idx, max_sim, weight, x, y, z} | kNN indices int32 [out_elems] ]
+  out  [ records int32 [B, N, 6] = {idx, max_sim, weight, x, y, z} | kNN indices uint16 [out_elems] ]
+       (uint16 while every support cloud of the pyramid has fewer than 65536 points -- the indices are narrowed on the
+       device, gadm_pack_indices_u16 -- else int32; KnnPyramid.unpack() accepts either)
 
 With several ranks (torch.distributed initialised) the matcher records of every batch are also all-gathered on a
 side stream, so that each rank holds the whole job's correspondences on its device (evaluator.py:240-249 gathers on
@@ -55,7 +57,8 @@ class FrameStream:
 
     submit(batch: HostBatch) returns a ticket; result(ticket) blocks until that batch's outputs are in host memory and
     returns {'idx' int32, 'max_sim', 'weight', 'soft_xyz', 'knn'} as views of ONE pinned host buffer ('knn' is the
-    flat int32 buffer KnnPyramid.unpack() understands).  The buffers of a ticket are reused `depth` submits later."""
+    flat index buffer KnnPyramid.unpack() understands: uint16, or int32 for clouds of 65536 points and more).  The
+    buffers of a ticket are reused `depth` submits later."""
 
     def __init__(self, bank, pyramid, B, d, N, obj_id=None, gamma=16.0, mode="soft", depth=3, gather=True):
         self.bank, self.pyr, self.B, self.d, self.N = bank, pyramid, B, d, N
@@ -70,7 +73,9 @@ class FrameStream:
         self.rgbd_bytes = B * d * N * 2
         self.in_bytes = self.rgbd_bytes + B * pyramid.P * 3 * 4
         self.rec_elems = B * N * 6
-        self.out_elems = self.rec_elems + pyramid.out_elems
+        self.knn_u16 = max(j.n_support for j in pyramid.jobs) < 65536
+        knn_words = (pyramid.out_elems + 1) // 2 if self.knn_u16 else pyramid.out_elems     # int32 words on the bus
+        self.out_elems = self.rec_elems + knn_words
         self.slots = []
         for _ in range(depth):
             s = _Slot()
@@ -80,9 +85,14 @@ class FrameStream:
             s.dev_out = torch.empty((self.out_elems,), dtype=torch.int32, device=dev)
             s.host_out = torch.empty((self.out_elems,), dtype=torch.int32).pin_memory()
             rec = s.host_out[: self.rec_elems].view(B, N, 6)
+            knn_host = s.host_out[self.rec_elems:]
+            if self.knn_u16:
+                knn_host = knn_host.view(torch.uint16)[: pyramid.out_elems]
+                s.knn32 = torch.empty((pyramid.out_elems,), dtype=torch.int32, device=dev)
+                s.knn16 = s.dev_out[self.rec_elems:].view(torch.uint16)[: pyramid.out_elems]
             s.out = {"idx": rec[..., 0], "max_sim": rec[..., 1].view(torch.float32),
                      "weight": rec[..., 2].view(torch.float32), "soft_xyz": rec[..., 3:6].view(torch.float32),
-                     "knn": s.host_out[self.rec_elems:]}
+                     "knn": knn_host}
             s.gathered = (torch.empty((self.world, self.rec_elems), dtype=torch.int32, device=dev)
                           if self.world > 1 else None)
             s.h2d_done = torch.cuda.Event()
@@ -125,7 +135,11 @@ class FrameStream:
         rec = s.dev_out[: self.rec_elems]
         ops.pack_match_outputs(outs[0], outs[1], outs[2], outs[3], rec)
         with torch.cuda.stream(self.knn):
-            self.pyr.run_packed(s.pts, out=s.dev_out[self.rec_elems:])
+            if self.knn_u16:
+                self.pyr.run_packed(s.pts, out=s.knn32)
+                ops.pack_indices_u16(s.knn32, s.knn16)
+            else:
+                self.pyr.run_packed(s.pts, out=s.dev_out[self.rec_elems:])
             s.knn_done.record(self.knn)
         compute.wait_event(s.knn_done)
         s.compute_done.record(compute)

@@ -171,6 +171,12 @@ int gadm_match_fwd_sel(const void* rows, const float* rinv_rows, const float* pa
 int gadm_pack_match_outputs(const int64_t* idx, const float* max_sim, const float* weight, const float* soft_xyz,
                             int64_t n, int32_t* out, gadm_stream_t stream);
 
+/* Narrows n int32 neighbour indices (gadm_knn3d output) to uint16 for transport: the caller guarantees that every
+ * support cloud has fewer than 65536 points (indices are truncated otherwise).  The reference ships the 22 index
+ * arrays of a sample as int32 numpy arrays (datasets/lm/linemod_pbr.py:534-569); here they cross the bus once, at half
+ * the bytes.  idx 8-byte aligned, out 4-byte aligned (GADM_ERR_ALIGN). */
+int gadm_pack_indices_u16(const int32_t* idx, int64_t n, uint16_t* out, gadm_stream_t stream);
+
 /* Flash-style CircleLoss forward, the training-side twin of the matcher.  Replaces, per batch,
  * models/geoMatch.py:102-157 (similarity of the foreground rows with the -1-padded, normalised model), :55-83
  * (positive mask) and models/loss.py:475-490 (CircleLoss.forward) without materialising sim [n_fg, M + 1]:

@@ -57,6 +57,8 @@ def _cases(dev):
         ("match_fwd_sel", (rows, rinv, pad, cols, aux, n_sel, None, obj, 16.0, 0, 0), BASIC),
         ("pack_match_outputs", (idx, max_sim, weight, soft_xyz,
                                 torch.empty((B, N, 6), dtype=torch.int32, device=dev)), BASIC),
+        ("pack_indices_u16", (torch.randint(0, 60000, (1001,), generator=g).to(torch.int32).to(dev),
+                              torch.empty((1001,), dtype=torch.uint16, device=dev)), BASIC),
         ("kabsch_moments", (idx, mask, cloud, aux, obj, M, n_obj), BASIC),
         ("kabsch_moments_w", (idx, None, weight, cloud, aux, obj, M, n_obj), BASIC),
         ("kabsch_poses", (mom, mom, det, 4), BASIC),

@@ -1,6 +1,8 @@
 """Secondary measurement (BASELINE.json configs[4]): the geoMatch_DGCNN graph path --
 feature-space kNN k=20 on 4096 pts, batch 64, 1 x (C=3 via dim9) + 3 x (C=64) layers, + get_graph_feature.
-Prints one JSON line with per-kernel times and roofline fractions (CUDA events, 3 warm-ups, inputs > L2)."""
+Prints one JSON line with per-kernel times and roofline fractions (CUDA events, 3 warm-ups, inputs > L2), next to the
+reference's own formulation on the same GPU: torch `matmul` + `topk` (models/dgcnn.py:21-27, materialises the
+[B, N, N] distance matrix: 4.3 GB at this shape) and the gather / cat / permute of get_graph_feature (:30-56)."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -49,6 +51,29 @@ def gf():
 
 
 t_gf, out = timed(gf, reps=20)
+
+
+def torch_knn(x_, k_):                 # models/dgcnn.py:21-27, restated line by line
+    inner = -2 * torch.matmul(x_.transpose(2, 1), x_)
+    xx = torch.sum(x_ ** 2, dim=1, keepdim=True)
+    pairwise_distance = -xx - inner - xx.transpose(2, 1)
+    return pairwise_distance.topk(k=k_, dim=-1)[1]
+
+
+def torch_graph_feature(x_, idx_):     # models/dgcnn.py:30-56 (dim9=False), restated
+    batch_size, num_dims, num_points = x_.shape
+    idx_base = torch.arange(0, batch_size, device=x_.device).view(-1, 1, 1) * num_points
+    idx_ = (idx_ + idx_base).view(-1)
+    xt = x_.transpose(2, 1).contiguous()
+    feature = xt.view(batch_size * num_points, -1)[idx_, :].view(batch_size, num_points, k, num_dims)
+    xt = xt.view(batch_size, num_points, 1, num_dims).repeat(1, 1, k, 1)
+    return torch.cat((feature - xt, xt), dim=3).permute(0, 3, 1, 2).contiguous()
+
+
+torch.backends.cuda.matmul.allow_tf32 = False
+t_torch_knn, idx_t = timed(lambda: torch_knn(x, k), reps=3)
+t_torch_gf, _ = timed(lambda: torch_graph_feature(x, idx), reps=3)
+agree = float((idx_t == idx).float().mean())
 t_gf_alloc, _ = timed(lambda: ops.graph_feature(x, idx))
 gf_bytes = 4 * B * C * N + 8 * B * N * k + 4 * B * 2 * C * N * k
 line = {
@@ -58,5 +83,9 @@ line = {
     "graph_feature_ms": t_gf, "graph_feature_with_output_allocation_ms": t_gf_alloc, "graph_feature_gbs": gf_bytes / (t_gf * 1e-3) / 1e9,
     "graph_feature_frac_of_hbm_peak": gf_bytes / (t_gf * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0),
     "layer_stack_ms (1x dim9 + 3x C=64 knn+graph)": t_knn3 + 3 * t_knn64 + 4 * t_gf,
+    "torch_gpu_arm": {"knn_c64_ms (matmul fp32 + topk, models/dgcnn.py:21-27)": t_torch_knn,
+                      "graph_feature_ms (gather + cat + permute, :30-56)": t_torch_gf,
+                      "knn_speedup": t_torch_knn / t_knn64, "graph_feature_speedup": t_torch_gf / t_gf,
+                      "knn_index_agreement": agree},
 }
 print(json.dumps(line))
