@@ -7,23 +7,27 @@
 // models/loss.py:475-490 (circle_kernel).  The softmax weight and soft coordinates are the extension defined in
 // oracle/match_oracle.py.
 //
-// Kernels (what runs when: match_launch_t; measurements and bounds: DESIGN.md 3.1, profiles/SUMMARY_r1.md)
+// Kernels (what runs when: match_launch_t; measurements and bounds: DESIGN.md 3.1, profiles/SUMMARY_r2.md)
 //   match_kernel<soft|argmax, RT>   thread = row; RT row tiles of 128 scene points per CTA.  RT = 1: the two TMEM
 //                                   accumulators alternate between model tiles; RT = 2: accumulator r = row tile r with
 //                                   8 fixed epilogue warps.  The no-workspace ARGMAX path and SOFT for K' > 128.
-//   match_pair_kernel<soft|argmax>  256 rows per CTA, 128-vertex model tiles, every epilogue thread owns the same lane
-//                                   of both row tiles (a per-column constant serves two scores).  Default for SOFT.
-//   match_alt_kernel<exact|unit>    ARGMAX default: two row tiles per CTA, ALL 16 epilogue warps drain one accumulator
-//                                   while the tensor core fills the other; stash in the per-SM workspace slot; running
-//                                   maxima shared across the column slices of a row.  unit: no per-column constant.
-//   match_ta_kernel, match_frag_kernel   opt-in experiments kept parity-green (A operand in tensor memory;
-//                                   tcgen05.ld.16x256b fragment layout): both measured slower, see DESIGN.md.
-//   circle_kernel<fwd|grad>         CircleLoss: masked exponential sums / dL/dsim in the epilogue.
+//   match_pair_kernel<soft|argmax, cta2>  256 rows per CTA, 128-vertex model tiles, every epilogue thread owns the same
+//                                   lane of both row tiles (a per-column constant serves two scores).  Default for
+//                                   SOFT.  cta2: the same on CTA pairs (cluster of two, tcgen05.mma.cta_group::2).
+//   match_alt_kernel<unit, prune>   ARGMAX default, PERSISTENT: the (frame, row block, model tile) units of a launch are
+//                                   dealt out evenly to one CTA per SM (match_common.cuh: Sched); per segment all 16
+//                                   epilogue warps drain one accumulator while the tensor core fills the other; stash in
+//                                   the per-SM workspace slot; running maxima shared across the column slices of a row;
+//                                   row blocks split over CTAs are merged by the last CTA to arrive.  unit: no
+//                                   per-column constant; prune: chunks that cannot win are skipped (BF16N operands).
+//   (circle_sm100.cu)               CircleLoss: masked exponential sums / dL/dsim in the epilogue of the same skeleton.
 //
 // Common skeleton
-//     warp 16     TMA producer: the row tile(s) once, then model tiles (256 vertices x 64 k, 32 KB) through an S-stage
+//     warp 16     TMA producer: the row tile(s), then model tiles (256 or 128 vertices x 64 k) through an S-stage
 //                 mbarrier ring, plus per tile the column scales 1/|m_j| and (SOFT / circle) the coordinate planes
-//     warp 17     UMMA issuer: 128x256x16 tcgen05.mma into two 256-column TMEM accumulators, tcgen05.commit
+//     warp 17     UMMA issuer: tcgen05.mma into TMEM accumulators, tcgen05.commit.  The loop between two MMAs is a
+//                 handful of uniform-datapath instructions: descriptors are 32-bit low words + one constant high word,
+//                 the accumulator address a compile-time function of (buffer, row tile)
 //     warps 0..15 epilogue.  Per 32-column chunk: tcgen05.ld, score = acc * 1/|m_j| (packed f32x2), 3-input max tree
 //                 per 8 columns.  The position of the maximum inside its 8-column group is NOT searched in the loop (a
 //                 search is ~70 warp-divergent instructions and some lane of a warp needs one in most chunks): a
@@ -32,9 +36,9 @@
 //                 is looked up there once, after the last tile.  SOFT adds p = 2^(score * g) (no reference exponent:
 //                 |gamma| <= 40 keeps the sums inside the fp32 range) and fp32 sums of p and p * xyz.  The column
 //                 slices of a row merge through shared memory at the end.
-//   What bounds them: with two row tiles per CTA the UMMA operand reads + TMA writes alone fill the SM's shared-memory
-//   data pipe (1024 wavefronts per 1024-cycle tile), so every epilogue LDS / store wavefront lengthens the tile;
-//   SOFT is additionally capped by MUFU.EX2 (16/clk/SM: 2048 cycles per 128x256 tile).
+//   What bounds them (measured): ARGMAX -- the SM's shared-memory data pipe (UMMA operand reads + TMA
+//   writes fill it with two row tiles per CTA, every epilogue LDS / store wavefront lengthens the tile), then the
+//   power cap when sustained; SOFT -- the latency of its 16 epilogue instruction streams (no pipe above 61 %).
 #include "match_common.cuh"
 
 namespace gadm {
