@@ -60,6 +60,8 @@ SIGNATURES = {
     "gadm_knn3d": (c_int, [c_void_p, c_void_p, ctypes.POINTER(KnnJob), c_int, c_int, c_void_p, c_void_p,
                            c_void_p, c_size_t, c_void_p]),
     "gadm_knn_feat": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "gadm_knn_feat_tc_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "gadm_knn_feat_tc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gadm_graph_feature_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "gadm_graph_feature": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
                                    c_void_p]),

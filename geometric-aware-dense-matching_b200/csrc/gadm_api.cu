@@ -103,6 +103,8 @@ int gadm_init(int device) {
   if (rc != GADM_OK) return rc;
   rc = knn3d_configure();
   if (rc != GADM_OK) return rc;
+  rc = knn_feat_tc_configure();
+  if (rc != GADM_OK) return rc;
   rc = knn_feat_configure();
   if (rc != GADM_OK) return rc;
   g_init = true;
@@ -343,6 +345,19 @@ int gadm_knn_feat(const float* x, int B, int C, int N, int kdim, int k, int64_t*
   if (k > 32) return GADM_ERR_UNSUPPORTED;
   if (k > N) return GADM_ERR_BAD_ARG;
   return knn_feat_launch(x, B, C, N, kdim, k, idx, (cudaStream_t)stream);
+}
+
+size_t gadm_knn_feat_tc_workspace_bytes(int B, int C, int N, int kdim, int k) {
+  if (B <= 0 || C <= 0 || N <= 0 || !knn_feat_tc_supported(C, N, kdim, k)) return 0;
+  return knn_feat_tc_workspace_bytes(B, C, N);
+}
+
+int gadm_knn_feat_tc(const float* x, int B, int C, int N, int k, int64_t* idx, void* workspace, size_t workspace_bytes,
+                     gadm_stream_t stream) {
+  GADM_REQUIRE_INIT();
+  if (!x || !idx || B <= 0 || C <= 0 || N <= 0 || k <= 0) return GADM_ERR_BAD_ARG;
+  if (k > N) return GADM_ERR_BAD_ARG;
+  return knn_feat_tc_launch(x, B, C, N, k, idx, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 size_t gadm_graph_feature_workspace_bytes(int B, int C, int N) {

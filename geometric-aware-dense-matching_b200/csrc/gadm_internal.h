@@ -72,6 +72,12 @@ int knn3d_launch(const float* support, const float* query, const gadm_knn_job* j
 // knn_feat.cu
 int knn_feat_configure();
 int knn_feat_launch(const float* x, int B, int C, int N, int kdim, int k, int64_t* idx, cudaStream_t stream);
+// tensor-core path (knn_feat_tc.cu): C % 64 == 0, k <= 20, N % 4 == 0, N >= 256
+int knn_feat_tc_configure();
+bool knn_feat_tc_supported(int C, int N, int kdim, int k);
+size_t knn_feat_tc_workspace_bytes(int B, int C, int N);
+int knn_feat_tc_launch(const float* x, int B, int C, int N, int k, int64_t* idx, void* workspace, size_t workspace_bytes,
+                       cudaStream_t stream);
 
 // gather.cu
 int graph_feature_launch(const float* x, const int64_t* idx, int B, int C, int N, int k, float* out,

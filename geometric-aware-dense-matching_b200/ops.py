@@ -465,14 +465,25 @@ def _(support, query, k, algo):
 
 
 # --------------------------------------------------------------------------------------------- DGCNN
+_KNN_FEAT_TC = True     # tests switch the tensor-core path off to compare it with the fp32 SIMT kernel
+
+
 @torch.library.custom_op("gadm::knn_feat", mutates_args=(), device_types="cuda")
 def knn_feat(x: torch.Tensor, k: int, kdim: int) -> torch.Tensor:
+    """models/dgcnn.py:21-27.  Shapes the tensor-core kernel takes (kdim == C, C % 64 == 0, k <= 20, N % 4 == 0,
+    N >= 256) run there (bf16x3 split dot products, fp32 accumulate); everything else on the fp32 SIMT kernel."""
     _need(x, torch.float32, "x")
     B, C, N = x.shape
     idx = torch.empty((B, N, k), dtype=torch.int64, device=x.device)
     lib = _lib_for(x)
+    ws_bytes = lib.gadm_knn_feat_tc_workspace_bytes(B, C, N, kdim, k) if _KNN_FEAT_TC else 0
     with torch.cuda.device(x.device):
-        _lib.check(lib.gadm_knn_feat(_ptr(x), B, C, N, kdim, k, _ptr(idx), _stream()), "gadm_knn_feat")
+        if ws_bytes:
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
+            _lib.check(lib.gadm_knn_feat_tc(_ptr(x), B, C, N, k, _ptr(idx), _ptr(ws), ws_bytes, _stream()),
+                       "gadm_knn_feat_tc")
+        else:
+            _lib.check(lib.gadm_knn_feat(_ptr(x), B, C, N, kdim, k, _ptr(idx), _stream()), "gadm_knn_feat")
     return idx
 
 

@@ -284,6 +284,15 @@ int gadm_knn3d(const float* support, const float* query, const gadm_knn_job* job
  * for dim9=True, models/dgcnn.py:38); idx int64 [B, N, k], nearest first, ties by ascending index. k <= 32 */
 int gadm_knn_feat(const float* x, int B, int C, int N, int kdim, int k, int64_t* idx, gadm_stream_t stream);
 
+/* The same ranking on the tensor cores (bf16x3 split dot products, fp32 |x|^2, fp32 accumulate), for
+ * kdim == C, C % 64 == 0, C <= 256, k <= 20, N % 4 == 0, N >= 256.  gadm_knn_feat_tc_workspace_bytes returns 0 when
+ * the shape is not supported (use gadm_knn_feat), else the bytes of device scratch (256-byte aligned) the call needs
+ * for the split operands: 4 C + 4 bytes per point.  Scores differ from gadm_knn_feat's by ~2^-16 |xi||xj|: neighbours
+ * whose distances are closer than that may swap ranks (torch's own GEMM reorders sums on the same scale). */
+size_t gadm_knn_feat_tc_workspace_bytes(int B, int C, int N, int kdim, int k);
+int gadm_knn_feat_tc(const float* x, int B, int C, int N, int k, int64_t* idx, void* workspace, size_t workspace_bytes,
+                     gadm_stream_t stream);
+
 /* out [B, 2C, N, k] fp32: out[b, c, n, j] = x[b, c, idx[b,n,j]] - x[b, c, n];  out[b, C+c, n, j] = x[b, c, n]
  * workspace (optional, 16-byte aligned, gadm_graph_feature_workspace_bytes): a point-major copy of x that makes
  * the neighbour gathers sector-efficient; without it a slower direct-gather kernel runs (same result).      */

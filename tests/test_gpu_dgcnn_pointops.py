@@ -9,9 +9,11 @@ from oracle import pointops_oracle as po
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("tc", [True, False])
 @pytest.mark.parametrize("B,C,N,k,dim9", [(2, 64, 1024, 20, False), (1, 9, 777, 16, True), (2, 3, 500, 20, False),
-                                          (1, 128, 300, 32, False)])
-def test_knn_feat_vs_oracle(cuda, B, C, N, k, dim9):
+                                          (1, 128, 300, 32, False), (2, 128, 1000, 16, False), (1, 64, 4096, 20, False),
+                                          (1, 256, 520, 5, False)])
+def test_knn_feat_vs_oracle(cuda, B, C, N, k, dim9, tc):
     """Exact where the minimum adjacent-rank gap (ranks 1..k+1) exceeds the fp32 noise of the distance form
     (SURVEY.md 7.3-5): gap > 2e-4 * max(1, |pd|max / 79)."""
     from gadm_b200 import dgcnn
@@ -20,7 +22,17 @@ def test_knn_feat_vs_oracle(cuda, B, C, N, k, dim9):
     xs = x[:, :3] if dim9 else x
     ref_idx, gaps, vals = do.knn_with_gaps(xs, k)
     from gadm_b200 import ops
-    idx = ops.knn_feat(x.to(cuda).contiguous(), k, 3 if dim9 else C).cpu()
+    # tc: shapes the tensor-core kernel supports (C % 64 == 0, k <= 20, N % 4 == 0, N >= 256) run there, the others
+    # -- and everything when it is switched off -- on the fp32 SIMT kernel; same gates for both
+    lib = ops._lib.load()
+    on_tc = tc and lib.gadm_knn_feat_tc_workspace_bytes(B, C, N, 3 if dim9 else C, k) > 0
+    if tc and not on_tc and C % 64 == 0 and k <= 20 and N >= 256 and N % 4 == 0:
+        pytest.fail("the tensor-core path should have taken this shape")
+    ops._KNN_FEAT_TC = tc
+    try:
+        idx = ops.knn_feat(x.to(cuda).contiguous(), k, 3 if dim9 else C).cpu()
+    finally:
+        ops._KNN_FEAT_TC = True
     thresh = 2e-4 * max(1.0, float(vals.abs().max()) / 79.0)
     ok = gaps > thresh
     assert ok.float().mean() > 0.5      # low-dimensional inputs have many near-ties; they are excluded, not failed
