@@ -15,8 +15,9 @@
 // value --, a bit mask of the columns that do, and ONE loop in which every lane inserts its next marked column (a
 // 5-level select tree picks the value; the insertion is a 20-step bubble on the value alone: a thread sees its
 // columns in ascending order, so a later equal value never displaces an earlier one and ties resolve to the smaller
-// index without comparing indices).  One insertion site keeps the loop inside the instruction cache.  The four slices
-// of a row merge through shared memory at the end (value descending, index ascending).
+// index without comparing indices).  One insertion site keeps the loop inside the instruction cache.  The four sorted
+// lists of a row go through shared memory at the end and the row's k best come out of a 4-way merge of their heads
+// (value descending, index ascending).
 #include <cuda_bf16.h>
 
 #include "match_common.cuh"
@@ -88,18 +89,6 @@ struct KfList {
     v[0] = sw[0] ? nv : v[0];
     i[0] = sw[0] ? ni : i[0];
   }
-  // the same with the index as tie-break (merge of the slices: their columns interleave)
-  __device__ __forceinline__ void insert_tie(float nv, int ni) {
-#pragma unroll
-    for (int s = 0; s < KF_K; ++s) {
-      const bool sw = nv > v[s] || (nv == v[s] && ni < i[s]);
-      const float tv = sw ? v[s] : nv;
-      const int ti = sw ? i[s] : ni;
-      v[s] = sw ? nv : v[s];
-      i[s] = sw ? ni : i[s];
-      nv = tv; ni = ti;
-    }
-  }
 };
 
 __device__ __forceinline__ float sel32(const float (&a)[32], int j) {
@@ -122,7 +111,8 @@ knn_feat_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint8_t* smem_a = smem;                                        // [2 CB] blocks of 128 rows x 64 k: hi.., lo..
   uint8_t* smem_b = smem_a + 2 * p.CB * A_BLK_BYTES;             // ring of 256 x 64 k blocks
   uint8_t* smem_aux = smem_b + p.stages * B_STAGE_BYTES;         // per slot: |x_j|^2 x 256
-  Barriers* bars = reinterpret_cast<Barriers*>(smem_aux + AUX_SLOTS * PLANE_BYTES);
+  volatile float* smem_thr = reinterpret_cast<volatile float*>(smem_aux + AUX_SLOTS * PLANE_BYTES);   // [KF_SL][BM]
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_aux + AUX_SLOTS * PLANE_BYTES + KF_SL * BM * 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -152,6 +142,7 @@ knn_feat_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     ptx::tmem_alloc(&bars->tmem_base, TMEM_COLS);
     ptx::tmem_relinquish();
   }
+  if (threadIdx.x < KF_SL * BM) smem_thr[threadIdx.x] = -INFINITY;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -267,11 +258,20 @@ knn_feat_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         m[10] = fmaxf(pd[30], pd[31]);
         const float mm = ptx::fmax3(ptx::fmax3(m[0], m[1], m[2]), ptx::fmax3(m[3], m[4], m[5]),
                                     ptx::fmax3(ptx::fmax3(m[6], m[7], m[8]), m[9], m[10]));
+        // A value enters this slice's list if it beats the slice's own 20th value (strictly: the thread sees its
+        // columns in ascending order) AND is not below the ROW bound: every slice publishes its 5th best value, and
+        // the smallest of the four is a value that at least 4 x 5 = 20 candidates of the row reach, so nothing below
+        // it can be in the row's final list.  The four slices hold statistically equal shares of the row, so this
+        // bound sits close to the row's true 20th value -- the slices together then do about the insertions of ONE
+        // list over the whole row instead of four.  Published and read without synchronisation: the values only
+        // grow, a stale one is only a weaker bound.
         const float kth = L.v[KF_K - 1];
-        if (!__any_sync(0xffffffffu, mm > kth)) continue;
+        const float rowb = fminf(fminf(smem_thr[row_in_tile], smem_thr[BM + row_in_tile]),
+                                 fminf(smem_thr[2 * BM + row_in_tile], smem_thr[3 * BM + row_in_tile]));
+        if (!__any_sync(0xffffffffu, mm > kth && mm >= rowb)) continue;
         uint32_t mask = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mask |= pd[j] > kth ? (1u << j) : 0u;
+        for (int j = 0; j < 32; ++j) mask |= (pd[j] > kth && pd[j] >= rowb) ? (1u << j) : 0u;
 #pragma unroll 1
         while (__any_sync(0xffffffffu, mask != 0)) {
           const int j = mask ? __ffs(mask) - 1 : 0;
@@ -279,6 +279,7 @@ knn_feat_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           mask &= mask - 1;
           L.insert(v, col_base + c2 * 32 + j);
         }
+        smem_thr[sub * BM + row_in_tile] = L.v[KF_K / KF_SL - 1];
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -288,28 +289,40 @@ knn_feat_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     }
 
-    // ---- merge the four slices of every row (exchange buffer: the B ring; every MMA has completed)
-    float2* xch = reinterpret_cast<float2*>(smem_b);     // [KF_SL - 1][BM][KF_K]
-    if (sub > 0) {
+    // ---- merge the four slices of every row: every slice's list is sorted, so the row's k best come out of a 4-way
+    // merge of the list heads (exchange buffer: the operand tiles -- every MMA has completed -- [KF_SL][KF_K][BM])
+    float2* xch = reinterpret_cast<float2*>(smem_a);
 #pragma unroll
-      for (int s = 0; s < KF_K; ++s)
-        xch[((sub - 1) * BM + row_in_tile) * KF_K + s] = make_float2(L.v[s], __int_as_float(L.i[s]));
-    }
+    for (int s = 0; s < KF_K; ++s)
+      xch[(sub * KF_K + s) * BM + row_in_tile] = make_float2(L.v[s], __int_as_float(L.i[s]));
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-    if (sub == 0) {
-#pragma unroll 1
-      for (int e = 0; e < (KF_SL - 1) * KF_K; ++e) {
-        const int s2 = e / KF_K, s = e - s2 * KF_K;
-        const float2 c = xch[(s2 * BM + row_in_tile) * KF_K + s];
-        // (a slice's list is descending: once an entry cannot enter, the rest of that slice cannot either; the
-        // warp-uniform loop just runs on)
-        L.insert_tie(c.x, __float_as_int(c.y));
-      }
-      if (row_ok) {
-        int64_t* o = p.idx + (size_t(b) * p.N + row) * p.k;
+    if (sub == 0 && row_ok) {
+      int64_t* o = p.idx + (size_t(b) * p.N + row) * p.k;
+      int h[KF_SL] = {0, 0, 0, 0};
+      float2 head[KF_SL];
 #pragma unroll
-        for (int s = 0; s < KF_K; ++s)
-          if (s < p.k) o[s] = L.i[s];
+      for (int q2 = 0; q2 < KF_SL; ++q2) head[q2] = xch[(q2 * KF_K) * BM + row_in_tile];
+      for (int r = 0; r < p.k; ++r) {
+        // pick the best head: value descending, index ascending
+        float bv = head[0].x;
+        int bi = __float_as_int(head[0].y);
+        int best = 0;
+#pragma unroll
+        for (int q2 = 1; q2 < KF_SL; ++q2) {
+          const float cv = head[q2].x;
+          const int ci = __float_as_int(head[q2].y);
+          const bool w = cv > bv || (cv == bv && ci < bi);
+          bv = w ? cv : bv; bi = w ? ci : bi; best = w ? q2 : best;
+        }
+        o[r] = bi;
+        // advance the winner's list (an exhausted list shows -inf)
+#pragma unroll
+        for (int q2 = 0; q2 < KF_SL; ++q2) {
+          if (q2 == best) {
+            ++h[q2];
+            head[q2] = h[q2] < KF_K ? xch[(q2 * KF_K + h[q2]) * BM + row_in_tile] : make_float2(-INFINITY, __int_as_float(0x7fffffff));
+          }
+        }
       }
     }
   }
@@ -323,7 +336,8 @@ knn_feat_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 }
 
 size_t kf_smem_bytes(int CB, int stages) {
-  return size_t(2) * CB * A_BLK_BYTES + size_t(stages) * B_STAGE_BYTES + AUX_SLOTS * PLANE_BYTES + sizeof(Barriers) + 1024;
+  return size_t(2) * CB * A_BLK_BYTES + size_t(stages) * B_STAGE_BYTES + AUX_SLOTS * PLANE_BYTES + KF_SL * BM * 4 +
+         sizeof(Barriers) + 1024;
 }
 int kf_stages(int CB) {
   int stages = MAX_STAGES;
@@ -343,8 +357,8 @@ int knn_feat_tc_configure() {
 bool knn_feat_tc_supported(int C, int N, int kdim, int k) {
   if (C % 64 != 0 || C > 64 * KF_MAX_CB || kdim != C || k > KF_K || N % 4 != 0 || N < BN) return false;
   const int CB = C / 64, stages = kf_stages(CB);
-  // the exchange buffer of the final merge lives in the B ring
-  return stages >= 2 && size_t(stages) * B_STAGE_BYTES >= size_t(KF_SL - 1) * BM * KF_K * 8;
+  // the exchange buffer of the final merge lives in the operand tiles (row tile + ring)
+  return stages >= 2 && size_t(2) * CB * A_BLK_BYTES + size_t(stages) * B_STAGE_BYTES >= size_t(KF_SL) * BM * KF_K * 8;
 }
 
 size_t knn_feat_tc_workspace_bytes(int B, int C, int N) {
