@@ -60,6 +60,24 @@ def test_get_graph_feature_vs_oracle(cuda):
     assert torch.equal(out9[:, 9:, :, 0], x9)
 
 
+@pytest.mark.parametrize("B,N,k", [(2, 4096, 20), (1, 777, 16), (3, 300, 5)])
+def test_dim9_knn_runs_the_3d_search_and_meets_the_feature_gates(cuda, B, N, k):
+    """get_graph_feature(dim9=True) ranks by the first three channels (models/dgcnn.py:38): that search runs on the
+    exact 3-D grid kNN.  Same gates as the feature-space kernel against the reference's fp32 distance form."""
+    from gadm_b200 import dgcnn
+    g = torch.Generator().manual_seed(900 + N)
+    x = torch.randn((B, 9, N), generator=g)
+    ref_idx, gaps, vals = do.knn_with_gaps(x[:, :3], k)
+    idx = dgcnn.knn_xyz(x.to(cuda), k).cpu()
+    assert idx.dtype == torch.int64 and idx.shape == (B, N, k)
+    ok = gaps > 2e-4 * max(1.0, float(vals.abs().max()) / 79.0)
+    assert ok.float().mean() > 0.5
+    assert torch.equal(idx[ok], ref_idx[ok])
+    assert torch.all(idx[..., 0] == torch.arange(N)[None]), "self is always rank 0"
+    same_set = (torch.sort(idx, -1).values == torch.sort(ref_idx, -1).values).all(-1)
+    assert same_set.float().mean() > 0.95
+
+
 def test_pointops_knnquery_and_grouping(cuda):
     from gadm_b200 import pointops
     g = torch.Generator().manual_seed(2)

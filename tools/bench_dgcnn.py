@@ -34,7 +34,9 @@ def timed(fn, reps=5):
 
 
 t_knn64, idx = timed(lambda: ops.knn_feat(x, k, C))
-t_knn3, idx3 = timed(lambda: ops.knn_feat(x9, k, 3))
+from gadm_b200 import dgcnn
+t_knn3_feat, _ = timed(lambda: ops.knn_feat(x9, k, 3))          # the feature-space kernel on three channels
+t_knn3, idx3 = timed(lambda: dgcnn.knn_xyz(x9, k))              # what get_graph_feature(dim9=True) runs: the 3-D grid search
 # graph_feature through the C ABI with a preallocated output and workspace (ops.graph_feature allocates 2.7 GB per call,
 # which is what an earlier version of this script was really timing)
 lib = ops._lib.load()
@@ -79,7 +81,7 @@ gf_bytes = 4 * B * C * N + 8 * B * N * k + 4 * B * 2 * C * N * k
 line = {
     "workload": "dgcnn_graph: B=64, N=4096, k=20; knn C=64, knn C=3 (dim9), get_graph_feature C=64",
     "knn_feat_c64_ms": t_knn64, "knn_feat_c64_tflops_fp32": 2.0 * B * N * N * C / (t_knn64 * 1e-3) / 1e12,
-    "knn_feat_c3_ms": t_knn3,
+    "knn_feat_c3_ms": t_knn3, "knn_feat_c3_feature_space_kernel_ms": t_knn3_feat,
     "graph_feature_ms": t_gf, "graph_feature_with_output_allocation_ms": t_gf_alloc, "graph_feature_gbs": gf_bytes / (t_gf * 1e-3) / 1e9,
     "graph_feature_frac_of_hbm_peak": gf_bytes / (t_gf * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0),
     "layer_stack_ms (1x dim9 + 3x C=64 knn+graph)": t_knn3 + 3 * t_knn64 + 4 * t_gf,
