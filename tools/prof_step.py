@@ -20,7 +20,10 @@ rows, rinv, pad = ops.prep_rows(rgbd.to(dev), 0, 0)
 cld, sr = synth.frame_batch(B, 128, N, seed=2000)
 pyr = KnnPyramid(N, {s: (128 // s) ** 2 for s in (2, 4, 8)}, B)
 pts = pyr.pack(cld.to(dev), {s: v.to(dev) for s, v in sr.items()})
+xf = torch.randn((16, 64, 4096), generator=torch.Generator().manual_seed(5000)).to(dev)   # a quarter of config 5
 for _ in range(reps):
+    if what in ("all", "dgcnn"):
+        ops.knn_feat(xf, 20, 64)          # tensor-core feature-space kNN (knn_feat_tc_kernel)
     if what in ("all", "match"):
         ops.match_fwd(rows, rinv, pad, cols, aux, None, obj, 16.0, 0, MATCH_MODES["argmax"])
         ops.match_fwd(rows, rinv, pad, cols, aux, None, obj, 16.0, 0, MATCH_MODES["soft"])
