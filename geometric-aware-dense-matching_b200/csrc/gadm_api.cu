@@ -69,7 +69,7 @@ const char* gadm_strerror(int status) {
   }
 }
 
-int gadm_abi_version(void) { return 3; }
+int gadm_abi_version(void) { return GADM_ABI_VERSION; }
 
 int gadm_config_set(const char* key, int value) {
   if (!key) return GADM_ERR_BAD_ARG;

@@ -63,6 +63,7 @@ typedef enum {
 } gadm_status;
 
 const char* gadm_strerror(int status);
+#define GADM_ABI_VERSION 3   /* bumped whenever an existing entry point changes its signature */
 int gadm_abi_version(void);
 /* Checks the device (cc 10.x), resolves cuTensorMapEncodeTiled, raises the kernels' shared-memory limits and records
  * the device's SM count (per device).  Makes `device` current. */

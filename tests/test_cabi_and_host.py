@@ -31,6 +31,7 @@ def test_library_exports_every_header_symbol():
         assert hasattr(lib, s), f"{s} declared in include/gadm.h but not exported by libgadm.so"
     assert set(syms) == set(_lib.SIGNATURES), "ctypes signature table must cover the header exactly"
     assert lib.gadm_abi_version() == 3
+    assert "#define GADM_ABI_VERSION 3" in open(os.path.join(ROOT, "include", "gadm.h")).read()
     assert ctypes.sizeof(_lib.KnnJob) == 64
 
 
@@ -236,3 +237,11 @@ def test_geomatch_cfg_constructor_heads_match_reference_state_dict():
     assert matching.GeoMatchDGCNN(cfg, 5, Emb(), Emb()).positive_r == 3                               # geoMatch_DGCNN.py:22
     with pytest.raises(NotImplementedError):
         matching.GeoMatch(cfg, 5)                                      # the backbones are outside the package
+
+
+def test_graft_entry_build_check_passes():
+    """__graft_entry__.build() is the driver's "does it build" gate: it must succeed on a CPU-only host (nvcc
+    cross-compiles) and its own consistency check (library ABI version == include/gadm.h) must hold."""
+    import importlib
+    ge = importlib.import_module("__graft_entry__")
+    ge.build()
