@@ -3,11 +3,11 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
         tools/probe_h2d.py
 
-Every rank copies the end-to-end leg's own transfer sizes (bench.py: 30.1 MB in, 16.9 MB out per 8-frame batch) and a
+Every rank copies the end-to-end leg's own transfer sizes (bench.py: 28.0 MB in, 9.4 MB out per 8-frame batch) and a
 large 256 MB buffer between pinned host memory and its GPU, first alone (ranks take turns), then all ranks together
 after a barrier.  The ratio together / alone is what the host's memory system and PCIe topology leave of one GPU's
 copy bandwidth when N ranks stream at once: the ceiling of the e2e scaling efficiency that `bench.py --gpus N` can reach.
-Last, the step's own copy pattern: 27.96 MB in and 16.38 MB out concurrently on two streams, every rank at once -- the time
+Last, the step's own copy pattern: 27.96 MB in and 9.42 MB out concurrently on two streams, every rank at once -- the time
 of that pair is the floor of an end-to-end step on this box whatever the kernels do ("e2e_copy_floor").
 One JSON line on rank 0."""
 import json
@@ -41,7 +41,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    sizes = {"in_30MB": 30_105_600, "out_17MB": 16_933_968, "big_256MB": 256 << 20}
+    sizes = {"in_28MB": 27_959_296, "out_9MB": 9_420_928, "big_256MB": 256 << 20}
     stream = torch.cuda.Stream(device=dev)
     res = {}
     for name, nbytes in sizes.items():
@@ -75,7 +75,7 @@ def main():
                      "h2d_together_over_alone": round(float(m[:, 2].sum() / m[:, 0].sum()), 3),
                      "d2h_together_over_alone": round(float(m[:, 3].sum() / m[:, 1].sum()), 3)}
     # the end-to-end step's own copies, both directions at once, every rank at once
-    n_in, n_out = 27_959_296, 16_384_256
+    n_in, n_out = 27_959_296, 9_420_928
     h_in = torch.empty((n_in,), dtype=torch.uint8).pin_memory()
     d_in = torch.empty((n_in,), dtype=torch.uint8, device=dev)
     h_out = torch.empty((n_out,), dtype=torch.uint8).pin_memory()
@@ -113,8 +113,12 @@ def main():
         floors[mode] = [round(float(x.item()), 3) for x in allt]
     worst = max(floors["together"])
     res["e2e_copy_floor"] = {"ms_per_step_alone_per_rank": floors["alone"], "ms_per_step_together_per_rank": floors["together"],
-                             "frames_per_s_ceiling": round(8 * world / worst * 1e3, 1),
-                             "note": "8 frames per rank and step; ceiling = 8 * ranks / slowest rank's copy time"}
+                             "frames_per_s_lockstep": round(8 * world / worst * 1e3, 1),
+                             "frames_per_s_aggregate": round(sum(8 / t * 1e3 for t in floors["together"]), 1),
+                             "note": "8 frames per rank and step, copies only.  lockstep = 8 * ranks / slowest rank's copy "
+                                     "time (every rank waits for the slowest each step); aggregate = sum of the ranks' own "
+                                     "rates (ranks that finish early leave their bandwidth to the others): a run with equal "
+                                     "steps per rank, timed to the last rank, lands between the two"}
     if rank == 0:
         print(json.dumps({"probe": "pinned host <-> device copies, all ranks at once", "n_gpus": world,
                           "host_cores": os.cpu_count(), "results": res}))
