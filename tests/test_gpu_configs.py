@@ -162,3 +162,55 @@ def test_frame_stream_host_buffers_match_direct_calls(cuda):
     rows32 = ops.prep_rows(inputs[0][0].to(cuda), 0, 1)
     rows16 = ops.prep_rows(inputs[0][0].to(cuda).to(torch.bfloat16), 0, 1)
     assert all(torch.equal(a, b) for a, b in zip(rows32, rows16))
+
+
+def test_step_is_cuda_graph_capturable(cuda):
+    """The C ABI never allocates, synchronises or reads device memory on the host: one whole step (prep_rows, the SOFT
+    matcher with its workspace memset, pack, the kNN pyramid with its grid build) is captured into a CUDA graph and
+    replayed on new input values in the same buffers; every replay equals the eager result bit for bit."""
+    from gadm_b200 import ops, synth, matching
+    from gadm_b200._lib import MATCH_MODES
+    from gadm_b200.knn import KnnPyramid
+    B, N, M, d = 2, 1024, 1024, 128
+    xyz = synth.model_bank_xyz(B, M).to(cuda)
+    pyr = KnnPyramid(N, {s: (32 // s) ** 2 for s in (2, 4, 8)}, B)
+    ws = ops._lib.load().gadm_knn3d_workspace_bytes(pyr.jobs, len(pyr.jobs), ops.KNN_ALGOS["auto"])
+    pyr.workspace = torch.empty((max(ws, 16),), dtype=torch.uint8, device=cuda)
+    obj = torch.arange(B, dtype=torch.int32, device=cuda)
+    rgbd_buf = torch.empty((B, d, N), device=cuda)
+    pts_buf = torch.empty((B * pyr.P, 3), device=cuda)
+    rec = torch.empty((B, N, 6), dtype=torch.int32, device=cuda)
+    knn_out = torch.empty((pyr.out_elems,), dtype=torch.int32, device=cuda)
+
+    def make_inputs(seed):
+        rgbd, mesh, _ = synth.descriptors(B, N, M, d, n_obj=B, regime="planted", seed=seed)
+        cld, sr = synth.frame_batch(B, 32, N, seed=seed)
+        return rgbd.to(cuda), mesh.to(cuda), pyr.pack(cld.to(cuda), {s: v.to(cuda) for s, v in sr.items()})
+
+    rgbd0, mesh0, pts0 = make_inputs(1)
+    cols, aux = ops.prep_model(mesh0, xyz, 0)
+
+    def step():
+        rows, rinv, pad = ops.prep_rows(rgbd_buf, 0, 0)
+        o = ops.match_fwd(rows, rinv, pad, cols, aux, None, obj, 16.0, 0, MATCH_MODES["soft"])
+        ops.pack_match_outputs(o[0], o[1], o[2], o[3], rec)
+        pyr.run_packed(pts_buf, out=knn_out)
+
+    rgbd_buf.copy_(rgbd0); pts_buf.copy_(pts0)
+    side = torch.cuda.Stream(device=cuda)
+    side.wait_stream(torch.cuda.current_stream(cuda))
+    with torch.cuda.stream(side):
+        step()                                   # warm-up outside the capture (workspace cache, lazy init)
+    torch.cuda.current_stream(cuda).wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    for seed in (1, 2, 3):
+        rgbd_s, _, pts_s = make_inputs(seed)
+        rgbd_buf.copy_(rgbd_s); pts_buf.copy_(pts_s)
+        graph.replay()
+        torch.cuda.synchronize()
+        got_rec, got_knn = rec.clone(), knn_out.clone()
+        step()
+        torch.cuda.synchronize()
+        assert torch.equal(got_rec, rec) and torch.equal(got_knn, knn_out), f"replay differs from eager (seed {seed})"
