@@ -502,7 +502,12 @@ def run_gpu(args):
                                       "its duration is measured on that stream and overlaps match_kernel")},
             "roofline": {"kernel": "match_pair_kernel<soft> (tcgen05 fused similarity + softmax + argmax + soft coordinates)", "bound": "tensor",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         # the burst figure: the timed region is 20 steps (16 ms) at full clocks (see "clocks"); against
+                         # the 4-second sustained figure of the same file the fraction would be higher
                          "peak_kind": f"{pk_kind} bf16 burst", "flop_per_launch": flop_per_launch,
+                         "peak_sustained": pk.get("bf16_tflops_sustained"),
+                         "frac_of_sustained_peak": (achieved / pk["bf16_tflops_sustained"]
+                                                    if pk.get("bf16_tflops_sustained") else None),
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch of THIS kernel, read from the
                          # committed ncu capture by kernel name (null if the capture does not hold it); the
                          # algorithmic bytes are 45 MB of operands + outputs
