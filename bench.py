@@ -658,13 +658,27 @@ def run_ycbv(args):
                     pyr.run_packed(pts)
             join = torch.cuda.Event(); join.record(knn_stream)
         main.wait_event(coll_done)                     # the previous step's all_gather has read `rec`
-        for c0, n, p0 in chunks():
+        work = list(chunks())
+        if from_host:                                  # chunk i + 1 crosses the bus while chunk i is matched
+            def upload(i):
+                _, n_, p0_ = work[i]
+                buf = slots["rgbd"][i & 1]
+                with torch.cuda.stream(slots["h2d"]):
+                    slots["h2d"].wait_event(slots["free"][i & 1])
+                    buf[:n_].copy_(host_pool[p0_:p0_ + n_], non_blocking=True)
+                    slots["ready"][i & 1].record(slots["h2d"])
+            upload(0)
+        for i, (c0, n, p0) in enumerate(work):
             if from_host:
-                src = slots["rgbd"][:n]
-                src.copy_(host_pool[p0:p0 + n], non_blocking=True)
+                if i + 1 < len(work):
+                    upload(i + 1)
+                main.wait_event(slots["ready"][i & 1])
+                src = slots["rgbd"][i & 1][:n]
             else:
                 src = pool[p0:p0 + n]
             rows, rinv, pad = ops.prep_rows(src, om, pm)
+            if from_host:
+                slots["free"][i & 1].record(main)      # prep_rows has consumed the staging buffer
             out = ops.match_fwd(rows, rinv, pad, cols, aux, None, obj_all[c0:c0 + n], GAMMA, pm, mm)
             ops.pack_match_outputs(out[0], out[1], out[2], out[3], rec[c0:c0 + n])
         if from_host:
@@ -705,7 +719,9 @@ def run_ycbv(args):
     clocks = sampler.stop() if rank == 0 else None
     # end to end: every instance's descriptors and every frame's points come from pinned host memory, every result goes
     # back to pinned host memory, inside the timed region
-    slots = {"rgbd": torch.empty((CH, D, N_PTS), dtype=torch.bfloat16, device=dev), "pts": torch.empty_like(pts),
+    slots = {"rgbd": [torch.empty((CH, D, N_PTS), dtype=torch.bfloat16, device=dev) for _ in range(2)],
+             "h2d": torch.cuda.Stream(device=dev), "ready": [torch.cuda.Event(), torch.cuda.Event()],
+             "free": [torch.cuda.Event(), torch.cuda.Event()], "pts": torch.empty_like(pts),
              "knn": torch.empty((pyr.out_elems,), dtype=torch.int32, device=dev),
              "knn_host": torch.empty((pyr.out_elems,), dtype=torch.int32).pin_memory(),
              "rec_host": torch.empty((cap, N_PTS, 6), dtype=torch.int32).pin_memory()}
