@@ -126,6 +126,12 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
     // ============================== UMMA issuer ==============================
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(BM, BN);
+      // descriptors as 32-bit low words + one constant high word, accumulator address a function of acc alone (the
+      // CTA owns all 512 TMEM columns: its allocation starts at column 0) -- see match_pair_kernel
+      constexpr uint64_t DESC_HI = uint64_t((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+      if (tmem_base != 0) __trap();
+      const uint32_t a_lo0 = ((ptx::smem_u32(smem_a) & 0x3FFFF) >> 4) | 0x10000u;
+      const uint32_t b_lo0 = ((ptx::smem_u32(smem_b) & 0x3FFFF) >> 4) | 0x10000u;
       ptx::mbar_wait(&bars->a_full, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -133,16 +139,16 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
         const int acc = t & 1;
         ptx::mbar_wait_sleep(&bars->s_free[acc], ((uint32_t(t) >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = uint32_t(acc) * BN;
         for (int kb = 0; kb < p.KB; ++kb) {
           ptx::mbar_wait_sleep(&bars->full[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(smem_a + kb * A_BLK_BYTES);
-          const uint32_t b_addr = ptx::smem_u32(smem_b + stage * B_STAGE_BYTES);
+          const uint32_t a_lo = a_lo0 + uint32_t(kb) * (A_BLK_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + uint32_t(stage) * (B_STAGE_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
-            ptx::umma_bf16_ss(d_tmem, ptx::umma_desc_sw128_kmajor(a_addr + k * UMMA_K * 2),
-                              ptx::umma_desc_sw128_kmajor(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0);
+            ptx::umma_bf16_ss(d_tmem, DESC_HI | (a_lo + k * (UMMA_K * 2 >> 4)), DESC_HI | (b_lo + k * (UMMA_K * 2 >> 4)),
+                              idesc, (kb | k) != 0);
           ptx::umma_commit(&bars->empty[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }

@@ -139,6 +139,12 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
     // (waits with a suspend-time hint: a busy poll competes for the MIO pipe the epilogue warps depend on)
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(BM, BN);
+      // descriptors as 32-bit low words + one constant high word, accumulator address without the shared-memory round
+      // trip (the CTA owns all 512 columns: its allocation starts at column 0) -- see match_pair_kernel
+      constexpr uint64_t DESC_HI = uint64_t((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+      if (tmem_base != 0) __trap();
+      const uint32_t a_lo0 = ((ptx::smem_u32(smem_a) & 0x3FFFF) >> 4) | 0x10000u;
+      const uint32_t b_lo0 = ((ptx::smem_u32(smem_b) & 0x3FFFF) >> 4) | 0x10000u;
       ptx::mbar_wait(&bars->a_full, 0);
       int stage0 = 0;            // ring position of the tile's first K block
       uint32_t phase0 = 0;
@@ -158,7 +164,7 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
           tr_free += clock64() - c0;
 #endif
           ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * BN;
+          const uint32_t d_tmem = uint32_t(acc) * BN;
           int stage = stage0;
           uint32_t phase = phase0;
           for (int kb = 0; kb < p.KB; ++kb) {
@@ -172,12 +178,12 @@ match_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constan
 #endif
               ptx::tc_fence_after();
             }
-            const uint32_t a_addr = ptx::smem_u32(smem_a + (r * p.KB + kb) * A_BLK_BYTES);
-            const uint32_t b_addr = ptx::smem_u32(smem_b + stage * B_STAGE_BYTES);
+            const uint32_t a_lo = a_lo0 + uint32_t(r * p.KB + kb) * (A_BLK_BYTES >> 4);
+            const uint32_t b_lo = b_lo0 + uint32_t(stage) * (B_STAGE_BYTES >> 4);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              ptx::umma_bf16_ss(d_tmem, ptx::umma_desc_sw128_kmajor(a_addr + k * UMMA_K * 2),
-                                ptx::umma_desc_sw128_kmajor(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0);
+              ptx::umma_bf16_ss(d_tmem, DESC_HI | (a_lo + k * (UMMA_K * 2 >> 4)), DESC_HI | (b_lo + k * (UMMA_K * 2 >> 4)),
+                                idesc, (kb | k) != 0);
             }
             if (r == RT - 1) ptx::umma_commit(&bars->empty[stage]);  // frees the stage once these MMAs have read it
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
