@@ -43,6 +43,35 @@ def test_knn_feat_vs_oracle(cuda, B, C, N, k, dim9, tc):
     assert same_set.float().mean() > 0.95
 
 
+@pytest.mark.parametrize("tc", [True, False])
+def test_knn_feat_exact_ties_go_to_the_smaller_index(cuda, tc):
+    """Every point twice (bit-identical copies at scattered positions): a copy scores exactly like its original in
+    every row, so the two must come out next to each other, smaller index first -- in the per-thread lists, across the
+    column slices of a row and across tiles (tensor-core kernel), and in the warp lists of the SIMT kernel."""
+    from gadm_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    B, C, N, k = 2, 64, 1024, 20
+    half = torch.randn((B, C, N // 2), generator=g)
+    perm = torch.randperm(N, generator=g)
+    x = torch.empty((B, C, N))
+    x[:, :, perm[: N // 2]] = half
+    x[:, :, perm[N // 2:]] = half                       # point perm[i] == point perm[i + N/2]
+    twin = torch.empty(N, dtype=torch.long)
+    twin[perm[: N // 2]] = perm[N // 2:]
+    twin[perm[N // 2:]] = perm[: N // 2]
+    ops._KNN_FEAT_TC = tc
+    try:
+        idx = ops.knn_feat(x.to(cuda).contiguous(), k, C).cpu()
+    finally:
+        ops._KNN_FEAT_TC = True
+    # ranks come in (original, copy) pairs: 0/1, 2/3, ... hold twins, smaller index first
+    a, b = idx[..., 0::2], idx[..., 1::2]
+    assert torch.equal(twin[a], b), "a copy must follow its original"
+    assert torch.all(a < b), "ties resolve to the smaller index"
+    n = torch.arange(N)[None]
+    assert torch.equal(idx[..., 0], torch.minimum(n, twin[n]).expand(B, N))   # the row's own pair leads
+
+
 def test_get_graph_feature_vs_oracle(cuda):
     from gadm_b200 import dgcnn
     g = torch.Generator().manual_seed(1)
