@@ -218,10 +218,111 @@ int compact_rows_launch(const uint8_t* mask, int B, int N, int32_t* pos, int32_t
   return check_launch();
 }
 
+// The common case of prep_kernel -- one bf16 operand copy (BF16: no split, no pre-normalisation), d % 64 == 0,
+// P % 4 == 0 -- with a quarter of its instructions (it was bound by instruction issue, not by HBM): 16-byte loads
+// along the points (four points of one channel), and in the point phase EIGHT threads per point, each converting and
+// storing 8 consecutive channels with one 16-byte store per pass and reducing the norm over its own channels before
+// three shuffles.  Same outputs as prep_kernel; the norm is summed in a different order (last-bit differences in rinv).
+template <int kSide, typename TIn>
+__global__ void __launch_bounds__(256)
+prep_fast_kernel(const TIn* __restrict__ src, const float* __restrict__ xyz, int d, int P, int pad_mode,
+                 __nv_bfloat16* __restrict__ dst, float* __restrict__ rinv, float* __restrict__ pad_sim,
+                 float* __restrict__ aux_scale, float* __restrict__ aux_xyz, float* __restrict__ aux_planes, size_t plane,
+                 const int32_t* __restrict__ pos) {
+  extern __shared__ float tile[];  // [d][PTS + 1]
+  const int g = blockIdx.y;
+  const int p0 = blockIdx.x * PTS;
+  const TIn* s = src + size_t(g) * d * P;
+  // ---- load: thread -> (channel, group of 4 points); PTS / 4 = 8 groups per channel row
+  for (int e = threadIdx.x; e < d * (PTS / 4); e += 256) {
+    const int c = e >> 3, q = e & 7, p = p0 + q * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p < P) {            // P % 4 == 0: the four points are valid or invalid together
+      if (sizeof(TIn) == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(s + size_t(c) * P + p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+        const uint2 t = *reinterpret_cast<const uint2*>(s + size_t(c) * P + p);
+        v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+        v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+      }
+    }
+    float* row = tile + c * (PTS + 1) + q * 4;
+    row[0] = v[0]; row[1] = v[1]; row[2] = v[2]; row[3] = v[3];
+  }
+  __syncthreads();
+
+  // ---- points: thread -> (point, sub); sub handles the channel groups sub, sub + 8, ... of 8 channels each
+  const int pl = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  const int p = p0 + pl;
+  const bool live = p < P;
+  const int prow = live ? (pos ? pos[size_t(g) * P + p] : p) : -1;   // row compaction: the row this point becomes
+  float ss = 0.f, sum = 0.f;
+  if (prow >= 0) {
+    __nv_bfloat16* out = dst + (size_t(g) * P + prow) * d;
+    for (int cg = sub; cg < d / 8; cg += 8) {
+      float f[8];
+      uint32_t w[4];
+#pragma unroll
+      for (int u = 0; u < 8; u += 2) {
+        const float v0 = tile[(cg * 8 + u) * (PTS + 1) + pl], v1 = tile[(cg * 8 + u + 1) * (PTS + 1) + pl];
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+        w[u >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+        f[u] = __uint_as_float(w[u >> 1] << 16);
+        f[u + 1] = __uint_as_float(w[u >> 1] & 0xffff0000u);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { ss = fmaf(f[u], f[u], ss); sum += f[u]; }
+      *reinterpret_cast<uint4*>(out + cg * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  }
+  if (sub == 0 && prow >= 0) {
+    const float r = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    const size_t gp = size_t(g) * P + prow;
+    if (kSide == 0) {
+      rinv[gp] = r;
+      if (pad_mode == GADM_PAD_MINUS_ONE) pad_sim[gp] = -sum * r * rsqrtf(float(d));
+      else if (pad_mode == GADM_PAD_E0) pad_sim[gp] = __bfloat162float(__float2bfloat16_rn(tile[pl])) * r;
+    } else {
+      aux_scale[gp] = r;
+    }
+  }
+  if (kSide == 1) {
+    for (int e = threadIdx.x; e < 3 * PTS; e += blockDim.x) {
+      const int pl2 = e / 3, c = e - 3 * pl2, p2 = p0 + pl2;
+      if (p2 >= P) continue;
+      const float v = xyz ? xyz[(size_t(g) * P + p0) * 3 + e] : 0.f;
+      aux_xyz[(size_t(g) * P + p0) * 3 + e] = v;
+      aux_planes[c * plane + size_t(g) * P + p2] = v;
+    }
+  }
+}
+
+static bool prep_fast_ok(const void* src, const void* dst, int d, int P, int elem_bytes) {
+  return d % 64 == 0 && P % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (size_t(P) * elem_bytes) % 16 == 0;
+}
+
 int prep_rows_launch(const void* feat, int feat_bf16, const int32_t* pos, int B, int d, int N, int operand_mode,
                      int pad_mode, void* rows, float* rinv, float* pad_sim, cudaStream_t stream) {
   dim3 grid((N + PTS - 1) / PTS, B);
   const size_t smem = size_t(d) * (PTS + 1) * sizeof(float);
+  if (operand_mode != GADM_OPERAND_BF16X3 && prep_fast_ok(feat, rows, d, N, feat_bf16 ? 2 : 4)) {
+    if (feat_bf16)
+      prep_fast_kernel<0, __nv_bfloat16><<<grid, 256, smem, stream>>>(
+          static_cast<const __nv_bfloat16*>(feat), nullptr, d, N, pad_mode, static_cast<__nv_bfloat16*>(rows), rinv,
+          pad_sim, nullptr, nullptr, nullptr, 0, pos);
+    else
+      prep_fast_kernel<0, float><<<grid, 256, smem, stream>>>(
+          static_cast<const float*>(feat), nullptr, d, N, pad_mode, static_cast<__nv_bfloat16*>(rows), rinv, pad_sim,
+          nullptr, nullptr, nullptr, 0, pos);
+    return check_launch();
+  }
   if (feat_bf16)
     prep_kernel<0, __nv_bfloat16><<<grid, 256, smem, stream>>>(
         static_cast<const __nv_bfloat16*>(feat), nullptr, d, N, operand_mode == GADM_OPERAND_BF16X3, 0, pad_mode,
@@ -280,6 +381,11 @@ int prep_model_launch(const float* mesh, const float* model_xyz, int n_obj, int 
   const size_t plane = size_t(n_obj) * M;
   float* a_xyz = aux + plane;
   float* a_planes = aux + plane * 4;
+  if (operand_mode == GADM_OPERAND_BF16 && prep_fast_ok(mesh, cols, d, M, 4)) {
+    prep_fast_kernel<1, float><<<grid, 256, smem, stream>>>(mesh, model_xyz, d, M, 0, static_cast<__nv_bfloat16*>(cols),
+                                                            nullptr, nullptr, aux, a_xyz, a_planes, plane, nullptr);
+    return check_launch();
+  }
   prep_kernel<1, float><<<grid, 256, smem, stream>>>(mesh, model_xyz, d, M, operand_mode == GADM_OPERAND_BF16X3,
                                               operand_mode == GADM_OPERAND_BF16N, 0,
                                               static_cast<__nv_bfloat16*>(cols), nullptr, nullptr, aux, a_xyz, a_planes, plane, nullptr);
