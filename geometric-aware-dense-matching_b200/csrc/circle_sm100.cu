@@ -44,7 +44,7 @@ struct CircleParams {
 // kGrad: the same pass, but instead of the two sums every score's gradient is written,
 //   dL/dsim_ij = w_i * (j positive ? softmax_p(j) * (-ap_ij gamma) : softmax_n(j) * (an_ij gamma)),
 // with ap / an constants (the reference detaches them, loss.py:479-480) and the row's two LSEs from the forward pass.
-template <bool kGrad>
+template <bool kGrad, bool kExact>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
               const CircleParams p) {
@@ -165,7 +165,7 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
     const size_t grow = size_t(b) * p.N + (row_ok ? row : 0);
     const float rs = row_ok ? p.rinv_rows[grow] : 0.f;
     const int64_t mi = row_ok ? p.match_idx[grow] : int64_t(p.M);
-    const bool exact = p.match_idx2 != nullptr;
+    constexpr bool exact = kExact;      // exact-column positives (matching_loss_sys): p.match_idx2 is given
     const int c1 = int(mi), c2 = exact && row_ok ? int(p.match_idx2[grow]) : -1;
     // the pad column is a negative exactly for the rows that have a positive on the model (geoMatch.py:78); with the
     // exact-column set it is a positive iff one of the two columns IS the pad column
@@ -195,9 +195,11 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
       const int ncols = min(BN, p.M - t * BN) - sub * CS;   // valid columns of this slice (may be <= 0)
       const uint32_t s_tmem = lane_base + acc * BN;
       const uint32_t sc_addr = ptx::smem_u32(smem_aux + slot * AUX_BYTES) + sub * CS * 4;
-#pragma unroll 1
-      for (int c = 0; c < CS / 16; ++c) {
-        if (ncols - c * 16 <= 0) break;
+      // 16 columns of the slice.  kGuard (ragged last tile only) masks the columns >= ncols.  Only the branch of the
+      // logit that the score's set needs is evaluated (the other one was computed and thrown away: 56 -> ~30
+      // instructions per score); the operation order inside the branch is the reference's (loss.py:479-489).
+      auto chunk = [&](int c, auto guard_tag) {
+        constexpr bool kGuard = decltype(guard_tag)::value;
         uint32_t d[16];
         ptx::tmem_ld_32x16(s_tmem + c * 16, d);
         ptx::tmem_ld_wait();
@@ -206,29 +208,41 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
         for (int j4 = 0; j4 < 4; ++j4) {
           const uint32_t a = sc_addr + (c * 16 + j4 * 4) * 4;
           const float4 cm = ptx::lds128(a);
-          const float4 X = ptx::lds128(a + PLANE_BYTES), Y = ptx::lds128(a + 2 * PLANE_BYTES),
-                       Z = ptx::lds128(a + 3 * PLANE_BYTES), R = ptx::lds128(a + 4 * PLANE_BYTES);
-          const float cs[4] = {cm.x, cm.y, cm.z, cm.w}, xs[4] = {X.x, X.y, X.z, X.w};
-          const float ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w}, r2s[4] = {R.x, R.y, R.z, R.w};
+          float xs[4], ys[4], zs[4], r2s[4];
+          if (!exact) {
+            const float4 X = ptx::lds128(a + PLANE_BYTES), Y = ptx::lds128(a + 2 * PLANE_BYTES),
+                         Z = ptx::lds128(a + 3 * PLANE_BYTES), R = ptx::lds128(a + 4 * PLANE_BYTES);
+            xs[0] = X.x; xs[1] = X.y; xs[2] = X.z; xs[3] = X.w;
+            ys[0] = Y.x; ys[1] = Y.y; ys[2] = Y.z; ys[3] = Y.w;
+            zs[0] = Z.x; zs[1] = Z.y; zs[2] = Z.z; zs[3] = Z.w;
+            r2s[0] = R.x; r2s[1] = R.y; r2s[2] = R.z; r2s[3] = R.w;
+          }
+          const float cs[4] = {cm.x, cm.y, cm.z, cm.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float s = (__uint_as_float(d[j4 * 4 + e]) * cs[e]) * rs;             // cosine similarity
-            // (A - B).pow(2).sum(-1) as the reference evaluates it: no FMA, left to right (basic_utils.py:88)
-            const float dx = __fsub_rn(gx, xs[e]), dy = __fsub_rn(gy, ys[e]), dz = __fsub_rn(gz, zs[e]);
-            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            const int col = t * BN + sub * CS + c * 16 + j4 * 4 + e;
-            const bool pos = exact ? (col == c1 || col == c2)
-                                   : __fadd_rn(d2, 1e-7f) < r2s[e];                  // sqrt(D2 + 1e-7) < positive_r[j]
-            const float ap = fmaxf(one_p - s, 0.f), an = fmaxf(s + m, 0.f);             // loss.py:479-480
-            const float lp = -ap * (s - one_m) * gl, ln = an * (s - m) * gl;            // loss.py:488-489 (log2 units)
-            const bool valid = c * 16 + j4 * 4 + e < ncols;
-            if (kGrad) {
-              const float sm = ptx::ex2_approx(pos ? lp - Lp : ln - Ln);                // softmax weight inside its set
-              gout[j4 * 4 + e] = wg * sm * (pos ? -ap : an);
+            bool pos;
+            if (exact) {
+              const int col = t * BN + sub * CS + c * 16 + j4 * 4 + e;
+              pos = col == c1 || col == c2;
             } else {
-              const float ex = ptx::ex2_approx(pos ? lp : ln);
-              sum_p += (valid && pos) ? ex : 0.f;
-              sum_n += (valid && !pos) ? ex : 0.f;
+              // (A - B).pow(2).sum(-1) as the reference evaluates it: no FMA, left to right (basic_utils.py:88)
+              const float dx = __fsub_rn(gx, xs[e]), dy = __fsub_rn(gy, ys[e]), dz = __fsub_rn(gz, zs[e]);
+              const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+              pos = __fadd_rn(d2, 1e-7f) < r2s[e];                                     // sqrt(D2 + 1e-7) < positive_r[j]
+            }
+            // positive: ap = max(1 + m - s, 0), logit = (-ap (s - (1 - m))) gamma;  negative: an = max(s + m, 0),
+            // logit = (an (s - m)) gamma   (loss.py:479-480, 488-489; log2 units)
+            const float a_ = fmaxf(pos ? one_p - s : s + m, 0.f);
+            const float lg = (a_ * (s - (pos ? one_m : m))) * (pos ? -gl : gl);
+            const bool valid = !kGuard || c * 16 + j4 * 4 + e < ncols;
+            if (kGrad) {
+              const float sm = ptx::ex2_approx(lg - (pos ? Lp : Ln));                   // softmax weight inside its set
+              gout[j4 * 4 + e] = wg * sm * (pos ? -a_ : a_);
+            } else {
+              const float ex = ptx::ex2_approx(lg);
+              if (valid && pos) sum_p += ex;
+              if (valid && !pos) sum_n += ex;
             }
           }
         }
@@ -236,9 +250,19 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
           float* dst = grow_g + t * BN + sub * CS + c * 16;
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4)
-            if (c * 16 + j4 * 4 < ncols)           // M % 8 == 0 and 16-byte groups: a float4 is valid or invalid as a whole
+            if (!kGuard || c * 16 + j4 * 4 < ncols)   // M % 8 == 0 and 16-byte groups: a float4 is valid or invalid as a whole
               *reinterpret_cast<float4*>(dst + j4 * 4) =
                   make_float4(gout[j4 * 4], gout[j4 * 4 + 1], gout[j4 * 4 + 2], gout[j4 * 4 + 3]);
+        }
+      };
+      if (ncols >= CS) {
+#pragma unroll 1
+        for (int c = 0; c < CS / 16; ++c) chunk(c, std::integral_constant<bool, false>{});
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < CS / 16; ++c) {
+          if (ncols - c * 16 <= 0) break;
+          chunk(c, std::integral_constant<bool, true>{});
         }
       }
       ptx::tc_fence_before();
@@ -301,9 +325,13 @@ inline size_t circle_smem_bytes(int KB, int stages) {
 }  // namespace
 
 int circle_configure() {
-  cudaError_t e = cudaFuncSetAttribute(circle_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(circle_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
-  e = cudaFuncSetAttribute(circle_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(circle_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(circle_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(circle_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
   return GADM_OK;
 }
@@ -331,10 +359,15 @@ int circle_launch(const void* rows, const float* rinv_rows, const float* pad_sim
   rc = make_tmap_2b_3d(&tmap_cols, cols, uint64_t(Kp), uint64_t(M), uint64_t(n_obj), BK, BN, 0);
   if (rc != GADM_OK) return rc;
   dim3 grid((N + BM - 1) / BM, B);
-  if (G != nullptr)
-    circle_kernel<true><<<grid, NUM_THREADS, circle_smem_bytes(KB, stages), stream>>>(tmap_rows, tmap_cols, p);
-  else
-    circle_kernel<false><<<grid, NUM_THREADS, circle_smem_bytes(KB, stages), stream>>>(tmap_rows, tmap_cols, p);
+  const size_t smem = circle_smem_bytes(KB, stages);
+  const bool exact = match_idx2 != nullptr;
+  if (G != nullptr) {
+    if (exact) circle_kernel<true, true><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+    else circle_kernel<true, false><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+  } else {
+    if (exact) circle_kernel<false, true><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+    else circle_kernel<false, false><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+  }
   return check_launch();
 }
 
