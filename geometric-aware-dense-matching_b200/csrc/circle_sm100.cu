@@ -247,12 +247,14 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
           }
         }
         if (kGrad && row_ok) {
+          // 32-byte stores: a lane writes whole sectors of its row of G (the rows of a warp are 32 KB apart, so a
+          // 16-byte store leaves every sector it touches half written)
           float* dst = grow_g + t * BN + sub * CS + c * 16;
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4)
-            if (!kGuard || c * 16 + j4 * 4 < ncols)   // M % 8 == 0 and 16-byte groups: a float4 is valid or invalid as a whole
-              *reinterpret_cast<float4*>(dst + j4 * 4) =
-                  make_float4(gout[j4 * 4], gout[j4 * 4 + 1], gout[j4 * 4 + 2], gout[j4 * 4 + 3]);
+          for (int j8 = 0; j8 < 2; ++j8)
+            if (!kGuard || c * 16 + j8 * 8 < ncols)   // M % 8 == 0: a group of 8 columns is valid or invalid as a whole
+              ptx::stg256(dst + j8 * 8, gout[j8 * 8], gout[j8 * 8 + 1], gout[j8 * 8 + 2], gout[j8 * 8 + 3],
+                          gout[j8 * 8 + 4], gout[j8 * 8 + 5], gout[j8 * 8 + 6], gout[j8 * 8 + 7]);
         }
       };
       if (ncols >= CS) {

@@ -271,11 +271,12 @@ int gadm_circle_loss_bwd(const void* rows, const float* rinv_rows, const float* 
     return GADM_ERR_BAD_ARG;
   if (B <= 0 || N <= 0 || M <= 0 || Kp <= 0 || n_obj <= 0) return GADM_ERR_BAD_ARG;
   if (B > 65535 || Kp % 64 != 0 || Kp > 768 || M % 8 != 0) return GADM_ERR_UNSUPPORTED;
-  if (Mp < M + 1 || Mp % 4 != 0) return GADM_ERR_BAD_ARG;
+  if (Mp < M + 1 || Mp % 8 != 0) return GADM_ERR_BAD_ARG;   // rows of G are written with 32-byte stores
   if (obj_id == nullptr && n_obj != 1 && n_obj != B) return GADM_ERR_BAD_ARG;
   if (!(margin >= 0.f && margin < 1.f) || !(gamma > 0.f)) return GADM_ERR_BAD_ARG;
   if (gamma * (2.f + margin) * (2.f - margin) * 1.4426950408889634f > 120.f) return GADM_ERR_UNSUPPORTED;
-  if (!aligned16(rows) || !aligned16(cols) || !aligned16(aux) || !aligned16(planes_frame) || !aligned16(G))
+  if (!aligned16(rows) || !aligned16(cols) || !aligned16(aux) || !aligned16(planes_frame) ||
+      (reinterpret_cast<uintptr_t>(G) & 31) != 0)
     return GADM_ERR_ALIGN;
   return circle_launch(rows, rinv_rows, pad_sim, cols, aux, planes_frame, match_idx, match_idx2, nullptr, obj_id, B, N, M,
                        Kp, n_obj, gamma, margin, nullptr, const_cast<float*>(lse_p), const_cast<float*>(lse_n), w, G, Mp,

@@ -354,6 +354,12 @@ __device__ __forceinline__ void stg_pred32(bool pred, void* gaddr, uint64_t v0, 
       ::"r"(uint32_t(pred)), "l"(gaddr), "l"(v0), "l"(v1), "l"(v2), "l"(v3)
       : "memory");
 }
+// 32-byte global store (sm_100: STG.256); gaddr 32-byte aligned
+__device__ __forceinline__ void stg256(float* gaddr, float a, float b, float c, float d, float e, float f, float g,
+                                       float h) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(gaddr), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f), "f"(g), "f"(h) : "memory");
+}
 __device__ __forceinline__ void stg_pred8(bool pred, void* gaddr, uint64_t v) {
   asm volatile(
       "{\n\t.reg .pred P;\n\t"

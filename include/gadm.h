@@ -206,7 +206,7 @@ int gadm_circle_loss_fwd(const void* rows, const float* rinv_rows, const float* 
  * pass keeps 8 bytes per row, not the similarity matrix).
  *   lse_p / lse_n [B, N] from gadm_circle_loss_fwd;  w [B, N] = dL/d(LSE_p + LSE_n) of every row, i.e.
  *   sigmoid(LSE_p + LSE_n) * dL/dloss_row (0 for rows that take no part)
- *   G [B, N, Mp] fp32 (16-byte aligned, Mp >= M + 1, Mp % 4 == 0): G[b, i, j] = dL/dsim_ij for j < M, column M = the
+ *   G [B, N, Mp] fp32 (32-byte aligned, Mp >= M + 1, Mp % 8 == 0): G[b, i, j] = dL/dsim_ij for j < M, column M = the
  *   pad column, columns M + 1 .. Mp - 1 = 0.  ap / an are constants as in the reference (detach, loss.py:479-480).
  * The two gradient GEMMs that follow (G M^ and G^T F^) are plain library GEMMs on the caller's side.                */
 int gadm_circle_loss_bwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
