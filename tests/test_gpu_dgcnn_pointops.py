@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("tc", [True, False])
 @pytest.mark.parametrize("B,C,N,k,dim9", [(2, 64, 1024, 20, False), (1, 9, 777, 16, True), (2, 3, 500, 20, False),
                                           (1, 128, 300, 32, False), (2, 128, 1000, 16, False), (1, 64, 4096, 20, False),
-                                          (1, 256, 520, 5, False)])
+                                          (1, 256, 520, 5, False), (1, 64, 260, 1, False), (3, 192, 300, 20, False),
+                                          (1, 64, 256, 20, False)])
 def test_knn_feat_vs_oracle(cuda, B, C, N, k, dim9, tc):
     """Exact where the minimum adjacent-rank gap (ranks 1..k+1) exceeds the fp32 noise of the distance form
     (SURVEY.md 7.3-5): gap > 2e-4 * max(1, |pd|max / 79)."""
