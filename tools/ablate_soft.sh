@@ -15,7 +15,7 @@ build() {  # name flags...
   name=$1; shift
   $NV "$@" -c match_sm100.cu -o /tmp/abl/match_$name.o
   nvcc -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -shared -o ../../tools/_stats/libgadm_$name.so \
-    build/gadm_api.o /tmp/abl/match_$name.o build/circle_sm100.o build/prep.o build/knn3d.o build/knn_feat.o build/gather.o -cudart static
+    build/gadm_api.o /tmp/abl/match_$name.o build/circle_sm100.o build/prep.o build/knn3d.o build/knn_feat.o build/knn_feat_tc.o build/gather.o -cudart static
   echo built $name
 }
 if [ $# -gt 0 ]; then
