@@ -512,7 +512,10 @@ def run_gpu(args):
                          # committed ncu capture by kernel name (null if the capture does not hold it); the
                          # algorithmic bytes are 45 MB of operands + outputs
                          "traffic": (match_prof or {}).get("dram_bytes"),
-                         "traffic_source": (match_prof or {}).get("source")},
+                         "traffic_source": (match_prof or {}).get("source"),
+                         # the pipe that caps a SOFT kernel below the tensor peak: one fp32 MUFU.EX2 per score,
+                         # 16.3 results / clk / SM measured (profiles/r2c_probe_pipe_mix.txt), at the SM clock of this run
+                         "xu_pipe": xu_ceiling(match_ms, clocks, flop_per_launch, peak)},
             "variants": {"match_kernel_argmax_only_ms": argmax_ms,
                          "match_kernel_argmax_only_frac": flop_per_launch / (argmax_ms * 1e-3) / 1e12 / peak,
                          "match_kernel_argmax_bf16n_ms": pruned_ms,
@@ -763,6 +766,21 @@ def run_ycbv(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+MUFU_PER_CLK_PER_SM = 16.3   # MUFU.EX2 results, tools/probes/pipe_mix_probe.cu on B200 (profiles/r2c_probe_pipe_mix.txt)
+
+
+def xu_ceiling(match_ms, clocks, flop_per_launch, peak_tflops):
+    """What the XU pipe alone needs for the SOFT kernel's exponentials (one per score) at this run's SM clock."""
+    mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz")
+    if not mhz:
+        return None
+    scores = float(N_PTS) * M_VERTS * FRAMES
+    floor_ms = scores / (MUFU_PER_CLK_PER_SM * 148 * mhz * 1e6) * 1e3
+    return {"exp2_per_launch": scores, "results_per_clk_per_sm": MUFU_PER_CLK_PER_SM, "sm_mhz": mhz,
+            "floor_ms": floor_ms, "frac_of_xu_peak": floor_ms / match_ms,
+            "tensor_frac_if_xu_bound": flop_per_launch / (floor_ms * 1e-3) / 1e12 / peak_tflops}
+
 
 def pyr_launches(pyr):
     """Kernel launches of one gadm_knn3d call (knn3d.cu): 4 grid-build kernels when any job uses the grid
