@@ -36,6 +36,8 @@ struct CircleParams {
   float* lse_n;
   const float* w;           // kGrad: [B, N] dL/dz of every row (0 for rows that take no part)
   float* G;                 // kGrad: [B, N, Mp] dL/dsim, column M = pad column, columns M+1.. = 0
+                            // kGrad == 2: the same bytes hold bf16 pairs, see gadm_circle_loss_bwd_split
+  float* g_pad;             // kGrad == 2: [B, N] dL/dsim of the pad column (fp32, unscaled)
   int Mp;
   int B, N, M, KB, n_obj, stages;
   float gamma_log2e, margin;
@@ -44,7 +46,11 @@ struct CircleParams {
 // kGrad: the same pass, but instead of the two sums every score's gradient is written,
 //   dL/dsim_ij = w_i * (j positive ? softmax_p(j) * (-ap_ij gamma) : softmax_n(j) * (an_ij gamma)),
 // with ap / an constants (the reference detaches them, loss.py:479-480) and the row's two LSEs from the forward pass.
-template <bool kGrad, bool kExact>
+// kGrad == 2 (split): G''_ij = G_ij * (1/|f_i|) * (1/|m_j|) as an unevaluated sum of two bf16 (hi + lo, 16 mantissa
+// bits), every group of 8 columns stored as 8 hi then 8 lo -- the same 32 bytes the fp32 group takes.  With the norms
+// folded into G'' both gradient GEMMs run on the EXACT bf16 operands the forward pass used, on the tensor cores, with
+// K interleaved the same way (see gadm.h).
+template <int kGrad, bool kExact>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
               const CircleParams p) {
@@ -182,7 +188,9 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
     // kGrad: row constants (log2 units) and the row of G
     const float Lp = kGrad && row_ok ? p.lse_p[grow] * 1.4426950408889634f : 0.f;
     const float Ln = kGrad && row_ok ? p.lse_n[grow] * 1.4426950408889634f : 0.f;
+    constexpr bool kSplit = kGrad == 2;
     const float wg = kGrad && row_ok ? p.w[grow] * (gl * 0.6931471805599453f) : 0.f;     // w_i * gamma
+    const float wgs = wg * rs;                                                            // kSplit: the row norm folded in
     float* grow_g = kGrad ? p.G + grow * size_t(p.Mp) : nullptr;
 
     for (int t = 0; t < num_tiles; ++t) {
@@ -238,7 +246,7 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
             const bool valid = !kGuard || c * 16 + j4 * 4 + e < ncols;
             if (kGrad) {
               const float sm = ptx::ex2_approx(lg - (pos ? Lp : Ln));                   // softmax weight inside its set
-              gout[j4 * 4 + e] = wg * sm * (pos ? -a_ : a_);
+              gout[j4 * 4 + e] = kSplit ? ((wgs * sm) * (pos ? -a_ : a_)) * cs[e] : wg * sm * (pos ? -a_ : a_);
             } else {
               const float ex = ptx::ex2_approx(lg);
               if (valid && pos) sum_p += ex;
@@ -252,9 +260,23 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
           float* dst = grow_g + t * BN + sub * CS + c * 16;
 #pragma unroll
           for (int j8 = 0; j8 < 2; ++j8)
-            if (!kGuard || c * 16 + j8 * 8 < ncols)   // M % 8 == 0: a group of 8 columns is valid or invalid as a whole
-              ptx::stg256(dst + j8 * 8, gout[j8 * 8], gout[j8 * 8 + 1], gout[j8 * 8 + 2], gout[j8 * 8 + 3],
-                          gout[j8 * 8 + 4], gout[j8 * 8 + 5], gout[j8 * 8 + 6], gout[j8 * 8 + 7]);
+            if (!kGuard || c * 16 + j8 * 8 < ncols) {  // M % 8 == 0: a group of 8 columns is valid or invalid as a whole
+              if (kSplit) {
+                float hw[4], lw[4];                    // 4 words of bf16 pairs each: hi parts, lo parts
+#pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2) {
+                  const float v0 = gout[j8 * 8 + e2 * 2], v1 = gout[j8 * 8 + e2 * 2 + 1];
+                  const uint32_t h = ptx::cvt_bf16x2(v1, v0);                       // {hi16: bf16(v1), lo16: bf16(v0)}
+                  const float r0 = v0 - __uint_as_float(h << 16), r1 = v1 - __uint_as_float(h & 0xffff0000u);
+                  hw[e2] = __uint_as_float(h);
+                  lw[e2] = __uint_as_float(ptx::cvt_bf16x2(r1, r0));
+                }
+                ptx::stg256(dst + j8 * 8, hw[0], hw[1], hw[2], hw[3], lw[0], lw[1], lw[2], lw[3]);
+              } else {
+                ptx::stg256(dst + j8 * 8, gout[j8 * 8], gout[j8 * 8 + 1], gout[j8 * 8 + 2], gout[j8 * 8 + 3],
+                            gout[j8 * 8 + 4], gout[j8 * 8 + 5], gout[j8 * 8 + 6], gout[j8 * 8 + 7]);
+              }
+            }
         }
       };
       if (ncols >= CS) {
@@ -283,7 +305,12 @@ circle_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_consta
         const float ap = fmaxf(one_p - s, 0.f), an = fmaxf(s + m, 0.f);
         const float gp = in_mesh ? wg * ptx::ex2_approx(an * (s - m) * gl - Ln) * an
                                  : wg * ptx::ex2_approx(-ap * (s - one_m) * gl - Lp) * -ap;
-        for (int j = p.M; j < p.Mp; ++j) grow_g[j] = j == p.M ? gp : 0.f;
+        if (kGrad == 2) {
+          p.g_pad[grow] = gp;
+          for (int j = p.M; j < p.Mp; ++j) grow_g[j] = 0.f;     // (bf16 zeros too)
+        } else {
+          for (int j = p.M; j < p.Mp; ++j) grow_g[j] = j == p.M ? gp : 0.f;
+        }
       }
     }
     float* xch = reinterpret_cast<float*>(smem_a);      // 3 * 128 * 8 B
@@ -327,13 +354,17 @@ inline size_t circle_smem_bytes(int KB, int stages) {
 }  // namespace
 
 int circle_configure() {
-  cudaError_t e = cudaFuncSetAttribute(circle_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(circle_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
-  e = cudaFuncSetAttribute(circle_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(circle_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
-  e = cudaFuncSetAttribute(circle_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(circle_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
-  e = cudaFuncSetAttribute(circle_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(circle_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(circle_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(circle_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
   return GADM_OK;
 }
@@ -342,9 +373,9 @@ int circle_launch(const void* rows, const float* rinv_rows, const float* pad_sim
                   const float* planes_frame, const int64_t* match_idx, const int64_t* match_idx2, const uint8_t* fg,
                   const int32_t* obj_id, int B,
                   int N, int M, int Kp, int n_obj, float gamma, float margin, float* loss, float* lse_p,
-                  float* lse_n, const float* w, float* G, int Mp, cudaStream_t stream) {
+                  float* lse_n, const float* w, float* G, int Mp, float* g_pad, cudaStream_t stream) {
   CircleParams p;
-  p.w = w; p.G = G; p.Mp = Mp;
+  p.w = w; p.G = G; p.Mp = Mp; p.g_pad = g_pad;
   p.rinv_rows = rinv_rows; p.pad_sim = pad_sim; p.scales = aux_scales(aux, n_obj, M); p.planes = planes_frame;
   p.xyz = aux_xyz(aux, n_obj, M); p.match_idx = match_idx; p.match_idx2 = match_idx2; p.fg = fg; p.obj_id = obj_id;
   p.loss = loss; p.lse_p = lse_p; p.lse_n = lse_n;
@@ -363,12 +394,15 @@ int circle_launch(const void* rows, const float* rinv_rows, const float* pad_sim
   dim3 grid((N + BM - 1) / BM, B);
   const size_t smem = circle_smem_bytes(KB, stages);
   const bool exact = match_idx2 != nullptr;
-  if (G != nullptr) {
-    if (exact) circle_kernel<true, true><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
-    else circle_kernel<true, false><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+  if (G != nullptr && g_pad != nullptr) {
+    if (exact) circle_kernel<2, true><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+    else circle_kernel<2, false><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+  } else if (G != nullptr) {
+    if (exact) circle_kernel<1, true><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+    else circle_kernel<1, false><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
   } else {
-    if (exact) circle_kernel<false, true><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
-    else circle_kernel<false, false><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+    if (exact) circle_kernel<0, true><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+    else circle_kernel<0, false><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
   }
   return check_launch();
 }

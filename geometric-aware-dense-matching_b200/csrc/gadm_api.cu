@@ -258,14 +258,14 @@ int gadm_circle_loss_fwd(const void* rows, const float* rinv_rows, const float* 
   if (gamma * (2.f + margin) * (2.f - margin) * 1.4426950408889634f > 120.f) return GADM_ERR_UNSUPPORTED;
   if (!aligned16(rows) || !aligned16(cols) || !aligned16(aux) || !aligned16(planes_frame)) return GADM_ERR_ALIGN;
   return circle_launch(rows, rinv_rows, pad_sim, cols, aux, planes_frame, match_idx, match_idx2, fg, obj_id, B, N, M, Kp,
-                       n_obj, gamma, margin, loss, lse_p, lse_n, nullptr, nullptr, 0, (cudaStream_t)stream);
+                       n_obj, gamma, margin, loss, lse_p, lse_n, nullptr, nullptr, 0, nullptr, (cudaStream_t)stream);
 }
 
-int gadm_circle_loss_bwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
-                         const float* aux, const float* planes_frame, const int64_t* match_idx, const int64_t* match_idx2,
-                         const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma, float margin,
-                         const float* lse_p, const float* lse_n, const float* w, float* G, int Mp,
-                         gadm_stream_t stream) {
+static int circle_bwd_checked(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
+                              const float* aux, const float* planes_frame, const int64_t* match_idx,
+                              const int64_t* match_idx2, const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj,
+                              float gamma, float margin, const float* lse_p, const float* lse_n, const float* w, void* G,
+                              int Mp, float* g_pad, gadm_stream_t stream) {
   GADM_REQUIRE_INIT();
   if (!rows || !rinv_rows || !pad_sim || !cols || !aux || !planes_frame || !match_idx || !lse_p || !lse_n || !w || !G)
     return GADM_ERR_BAD_ARG;
@@ -279,8 +279,27 @@ int gadm_circle_loss_bwd(const void* rows, const float* rinv_rows, const float* 
       (reinterpret_cast<uintptr_t>(G) & 31) != 0)
     return GADM_ERR_ALIGN;
   return circle_launch(rows, rinv_rows, pad_sim, cols, aux, planes_frame, match_idx, match_idx2, nullptr, obj_id, B, N, M,
-                       Kp, n_obj, gamma, margin, nullptr, const_cast<float*>(lse_p), const_cast<float*>(lse_n), w, G, Mp,
-                       (cudaStream_t)stream);
+                       Kp, n_obj, gamma, margin, nullptr, const_cast<float*>(lse_p), const_cast<float*>(lse_n), w,
+                       static_cast<float*>(G), Mp, g_pad, (cudaStream_t)stream);
+}
+
+int gadm_circle_loss_bwd(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
+                         const float* aux, const float* planes_frame, const int64_t* match_idx, const int64_t* match_idx2,
+                         const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma, float margin,
+                         const float* lse_p, const float* lse_n, const float* w, float* G, int Mp,
+                         gadm_stream_t stream) {
+  return circle_bwd_checked(rows, rinv_rows, pad_sim, cols, aux, planes_frame, match_idx, match_idx2, obj_id, B, N, M, Kp,
+                            n_obj, gamma, margin, lse_p, lse_n, w, G, Mp, nullptr, stream);
+}
+
+int gadm_circle_loss_bwd_split(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
+                               const float* aux, const float* planes_frame, const int64_t* match_idx,
+                               const int64_t* match_idx2, const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj,
+                               float gamma, float margin, const float* lse_p, const float* lse_n, const float* w,
+                               void* G2, int Mp, float* g_pad, gadm_stream_t stream) {
+  if (!g_pad) return GADM_ERR_BAD_ARG;
+  return circle_bwd_checked(rows, rinv_rows, pad_sim, cols, aux, planes_frame, match_idx, match_idx2, obj_id, B, N, M, Kp,
+                            n_obj, gamma, margin, lse_p, lse_n, w, G2, Mp, g_pad, stream);
 }
 
 size_t gadm_match_workspace_bytes(void) {

@@ -43,7 +43,7 @@ int circle_launch(const void* rows, const float* rinv_rows, const float* pad_sim
                   const float* planes_frame, const int64_t* match_idx, const int64_t* match_idx2, const uint8_t* fg,
                   const int32_t* obj_id, int B,
                   int N, int M, int Kp, int n_obj, float gamma, float margin, float* loss, float* lse_p,
-                  float* lse_n, const float* w, float* G, int Mp, cudaStream_t stream);
+                  float* lse_n, const float* w, float* G, int Mp, float* g_pad, cudaStream_t stream);
 
 // prep.cu
 int prep_rows_launch(const void* feat, int feat_bf16, const int32_t* pos, int B, int d, int N, int operand_mode,

@@ -355,6 +355,12 @@ __device__ __forceinline__ void stg_pred32(bool pred, void* gaddr, uint64_t v0, 
       : "memory");
 }
 // 32-byte global store (sm_100: STG.256); gaddr 32-byte aligned
+// {upper 16 bits: bf16(hi), lower 16 bits: bf16(lo)}, round to nearest even
+__device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ void stg256(float* gaddr, float a, float b, float c, float d, float e, float f, float g,
                                        float h) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"

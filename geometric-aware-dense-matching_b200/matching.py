@@ -141,6 +141,8 @@ class _CircleMatchLoss(torch.autograd.Function):
         B, N, d = rows.shape
         n_obj, M, _ = cols.shape
         w = (torch.sigmoid(lse_p + lse_n) * row_w * g_total).contiguous()            # softplus' = sigmoid
+        if ctx.grad_gemm == "bf16x2":
+            return _circle_backward_split(ctx, w)
         G = ops.circle_loss_bwd(rows, rinv, pad_sim, cols, aux, planes, mi, ctx.oid, gamma, margin, lse_p, lse_n,
                                 w, ctx.mi2)                                          # [B, N, M + 8]
         f_hat = rows.float() * rinv[..., None]                                       # [B, N, d]
@@ -167,6 +169,42 @@ class _CircleMatchLoss(torch.autograd.Function):
                 None, None, None, None, None, None)
 
 
+def _circle_backward_split(ctx, w):
+    """grad_gemm = "bf16x2": dL/dsim leaves the kernel with both norms folded in and split into two bf16 parts
+    (gadm_circle_loss_bwd_split), so the two gradient products run as bf16 tensor-core GEMMs with fp32 accumulation
+    on the forward pass's own bf16 operands -- exact products, 16 mantissa bits of G (tf32 keeps 10 of G AND rounds the
+    other operand) -- with the parts interleaved along K; the norms come back as fp32 row scalings of the results."""
+    rows, rinv, pad_sim, cols, aux, planes, mi, sel, lse_p, lse_n, row_w = ctx.saved_tensors
+    gamma, margin, pad_mode = ctx.cfg
+    B, N, d = rows.shape
+    n_obj, M, _ = cols.shape
+    Mp = M + 8
+    dev = rows.device
+    G2, g_pad = ops.circle_loss_bwd_split(rows, rinv, pad_sim, cols, aux, planes, mi, ctx.oid, gamma, margin, lse_p,
+                                          lse_n, w, ctx.mi2)                         # [B, N, 2 Mp] bf16, [B, N]
+    k = torch.arange(2 * Mp, device=dev)
+    col_of_k = (k // 16) * 8 + k % 8                                                 # K2 of gadm.h
+    cols_p = torch.zeros((n_obj, Mp, d), dtype=torch.bfloat16, device=dev)
+    cols_p[:, :M] = cols
+    cols2 = cols_p[:, col_of_k]                                                      # [n_obj, 2 Mp, d]
+    scale = aux[: n_obj * M].view(n_obj, M, 1)
+    m_pad = torch.zeros((d,), dtype=torch.float32, device=dev)
+    if pad_mode == "minus_one":
+        m_pad[:] = -(d ** -0.5)
+    else:
+        m_pad[0] = 1.0
+    d_fhat = torch.bmm(G2, cols2[sel], out_dtype=torch.float32) / rinv[..., None] + g_pad[..., None] * m_pad
+    t = torch.bmm(G2.transpose(1, 2), rows, out_dtype=torch.float32)                 # [B, 2 Mp, d]
+    d_mhat_b = t.view(B, Mp // 8, 2, 8, d).sum(2).reshape(B, Mp, d)[:, :M]           # hi + lo
+    d_mhat = torch.zeros((n_obj, M, d), dtype=torch.float32, device=dev).index_add_(0, sel, d_mhat_b) / scale
+    f_hat = rows.float() * rinv[..., None]
+    mh = cols.float() * scale
+    d_f = (d_fhat - (d_fhat * f_hat).sum(-1, keepdim=True) * f_hat) * rinv[..., None]
+    d_m = (d_mhat - (d_mhat * mh).sum(-1, keepdim=True) * mh) * scale
+    return (d_f.transpose(1, 2).contiguous(), d_m.transpose(1, 2).contiguous(), None, None, None, None, None, None,
+            None, None, None, None, None, None)
+
+
 def dgcnn_positive_radius(model_xyz, RT, positive_r):
     """Per-vertex positive radius of the DGCNN variant (models/geoMatch_DGCNN.py:64-65):
     positive_r / 1000 * the camera-space depth of every model vertex.  model_xyz [M, 3], RT [B, 3, 4] -> [B, M]."""
@@ -185,13 +223,18 @@ def circle_match_loss(rgbd, mesh, labels, match_idx, visible_flag, positive_r, m
     x['labels']); match_idx [B, N] int (ground-truth vertex, M = off the model, x['match_idx']); visible_flag [B, M]
     (x['visible_flag']); positive_r: metres (geoMatch.py:24), a scalar, or a [B, M] tensor of per-vertex radii
     (dgcnn_positive_radius: the DGCNN variant, which also uses pad_mode="e0" and labels = x['origin_labels']).
-    grad_gemm: "fp32" (default) or "tf32" for the two cuBLAS gradient GEMMs of the backward pass (tf32: ~3x faster
-    backward, gradient error ~5e-4 of the largest entry instead of ~1e-6).
+    grad_gemm: how the two gradient products of the backward pass (G M^ and G^T F^) run.  "fp32" (default): library
+    fp32 GEMMs on the fp32 dL/dsim; "tf32": the same with tf32 allowed (~3x faster backward, gradient error ~5e-4 of
+    the largest entry instead of ~1e-6); "bf16x2": dL/dsim leaves the kernel split into two bf16 parts with both norms
+    folded in and the products run as bf16 tensor-core GEMMs on the forward pass's own bf16 operands (exact products,
+    16 mantissa bits of dL/dsim: more accurate than tf32 and faster than either).
     sys_idx (int [>= N], or None): the symmetry-aware variant GeoMatch.matching_loss_sys (models/geoMatch.py:86-100, used
     when model_emb.sys_corr_idx is set, :138-141): the positives of scene point n are exactly the two columns
     match_idx[n] and match_idx[sys_idx[n]] -- no radius, no visibility (positive_r / visible_flag are ignored).
     Returns the scalar the reference returns: the mean over samples with >= 3 foreground rows of the mean row loss
     (0 if there is none); return_rows=True adds the per-row (loss, lse_p, lse_n) tensors."""
+    if grad_gemm not in ("fp32", "tf32", "bf16x2"):
+        raise ValueError("grad_gemm must be 'fp32', 'tf32' or 'bf16x2'")
     if isinstance(mesh, ModelBank):
         bank = mesh
         if bank.operand_mode != "bf16":

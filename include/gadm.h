@@ -215,6 +215,22 @@ int gadm_circle_loss_bwd(const void* rows, const float* rinv_rows, const float* 
                          const float* lse_p, const float* lse_n, const float* w, float* G, int Mp,
                          gadm_stream_t stream);
 
+/* The same pass with the gradient written for tensor-core GEMMs on the forward pass's own bf16 operands.
+ *   G2 [B, N, 2 Mp] bf16 (the same bytes as G above): G''[b, i, j] = dL/dsim_ij * (1/|f_i|) * (1/|m_j|) as an unevaluated
+ *   sum hi + lo of two bf16 (16 mantissa bits, relative error <= 2^-17), every group of 8 columns stored as its 8 hi
+ *   parts followed by its 8 lo parts: element [b, i, 16 g + 8 h + e] = part h of column 8 g + e.  Columns >= M are 0.
+ *   g_pad [B, N] fp32: dL/dsim of the pad column (unscaled).
+ * With K2[16 g + 8 h + e] = 8 g + e the two gradient products are plain bf16 GEMMs with fp32 accumulation:
+ *   dL/df^_i = (1/rinv_i) * sum_k G2[i, k] * cols[K2[k]]  + g_pad_i * m^_pad
+ *   dL/dm^_j = (1/scale_j) * sum_{h} (G2^T rows)[16 g + 8 h + e],  j = 8 g + e
+ * where rows / cols are the bf16 operands of the forward pass and rinv / scale their fp32 norms' reciprocals.
+ * Same argument rules as gadm_circle_loss_bwd.                                                                      */
+int gadm_circle_loss_bwd_split(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
+                               const float* aux, const float* planes_frame, const int64_t* match_idx,
+                               const int64_t* match_idx2, const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj,
+                               float gamma, float margin, const float* lse_p, const float* lse_n, const float* w,
+                               void* G2, int Mp, float* g_pad, gadm_stream_t stream);
+
 /* Backward passes of the gathers: the reference's torch.gather / max / cat are differentiable in the features
  * (models/dgcnn.py:41-54, models/RandLA/RandLANet.py:90-120, :729-738) and sit inside the trained networks.  Each zeroes
  * its output and scatter-adds with fp32 atomics (the summation order, hence the last bits, may vary from run to run).

@@ -114,7 +114,42 @@ def test_circle_loss_ragged_bank(cuda):
     assert total > 0
 
 
-@pytest.mark.parametrize("grad_gemm,gate", [("fp32", 1e-3), ("tf32", 3e-3)])
+def test_circle_loss_bwd_split_is_the_fp32_gradient_with_the_norms_folded_in(cuda):
+    """gadm_circle_loss_bwd_split against gadm_circle_loss_bwd on the same inputs: hi + lo of group g, element e =
+    G[.., 8 g + e] * rinv_i * scale_j to 2^-16 relative (two bf16 parts), the pad column's gradient in g_pad, zeros in
+    the padding; ragged N and M (the guard paths of the kernel)."""
+    from gadm_b200 import ops, synth
+    from gadm_b200.ops import OPERAND_MODES, PAD_MODES
+    B, N, M, d = 2, 333, 520, 64
+    g = torch.Generator().manual_seed(7)
+    rgbd, mesh, _ = synth.descriptors(B, N, M, d, seed=11)
+    xyz = synth.fibonacci_sphere(M, 0.2)[None].to(cuda)
+    rows, rinv, pad_sim = ops.prep_rows(rgbd.to(cuda), OPERAND_MODES["bf16"], PAD_MODES["minus_one"])
+    cols, aux = ops.prep_model(mesh[:1].to(cuda), xyz, OPERAND_MODES["bf16"])
+    planes = torch.empty((4, B, M), device=cuda)
+    planes[:3] = xyz[0].t()[:, None, :].expand(3, B, M)
+    planes[3] = 0.05 ** 2
+    mi = torch.randint(0, M + 1, (B, N), generator=g).to(cuda)
+    fg = torch.ones((B, N), dtype=torch.uint8, device=cuda)
+    _, lp, ln = ops.circle_loss_fwd(rows, rinv, pad_sim, cols, aux, planes, mi, fg, None, 16.0, 0.2)
+    w = torch.rand((B, N), generator=g).to(cuda)
+    G = ops.circle_loss_bwd(rows, rinv, pad_sim, cols, aux, planes, mi, None, 16.0, 0.2, lp, ln, w)
+    G2, g_pad = ops.circle_loss_bwd_split(rows, rinv, pad_sim, cols, aux, planes, mi, None, 16.0, 0.2, lp, ln, w)
+    Mp = M + 8
+    assert G2.shape == (B, N, 2 * Mp) and G2.dtype == torch.bfloat16
+    parts = G2.float().view(B, N, Mp // 8, 2, 8)
+    got = (parts[:, :, :, 0] + parts[:, :, :, 1]).reshape(B, N, Mp)
+    scale = aux[:M].view(1, 1, M)
+    want = G[:, :, :M] * rinv[..., None] * scale
+    err = (got[:, :, :M] - want).abs()
+    assert bool((err <= 2.0 ** -15 * want.abs() + 1e-37).all()), float((err / want.abs().clamp(min=1e-30)).max())
+    assert bool((parts[:, :, :, 1].abs() <= 2.0 ** -8 * parts[:, :, :, 0].abs() + 1e-37).all())   # lo is the remainder of hi
+    assert float(got[:, :, M:].abs().max()) == 0.0
+    assert torch.equal(g_pad, G[:, :, M])
+    assert float(G.abs().max()) > 0
+
+
+@pytest.mark.parametrize("grad_gemm,gate", [("fp32", 1e-3), ("tf32", 3e-3), ("bf16x2", 1e-3)])
 def test_circle_loss_gradients_vs_autograd_of_the_reference_math(cuda, grad_gemm, gate):
     """d loss / d rgbd and d loss / d mesh against torch autograd through the oracle (the reference's own formulas,
     ap / an detached as at loss.py:479-480) on the CPU.  Gate: 1e-3 of the largest gradient entry (3e-3 when the two

@@ -78,6 +78,8 @@ def _cases(dev):
         ("circle_loss_fwd", (rows_p, rinv_p, pad_p, cols, aux, planes, mi, None, obj, 16.0, 0.25, mi), BASIC),
         ("circle_loss_bwd", (rows_p, rinv_p, pad_p, cols, aux, planes, mi, obj, 16.0, 0.25, lse_p, lse_n,
                              torch.ones((B, N), device=dev)), BASIC),
+        ("circle_loss_bwd_split", (rows_p, rinv_p, pad_p, cols, aux, planes, mi, obj, 16.0, 0.25, lse_p, lse_n,
+                                   torch.ones((B, N), device=dev)), BASIC),
     ]
 
 
