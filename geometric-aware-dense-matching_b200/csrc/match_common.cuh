@@ -96,9 +96,10 @@ struct Sched {
   long long total;       // units
   int T, RB, B;          // model tiles per row; row blocks per frame when every frame has the same number
   const int* prefix;     // or null
-  __device__ __forceinline__ long long begin(int c) const { return (long long)c * total / (long long)gridDim.x; }
-  // the CTA whose range holds unit u: the largest c with begin(c) <= u
-  __device__ __forceinline__ int cta_of(long long u) const { return int(((u + 1) * (long long)gridDim.x - 1) / total); }
+  int nc;                // scheduling entities: CTAs (gridDim.x), or CTA pairs
+  __device__ __forceinline__ long long begin(int c) const { return (long long)c * total / (long long)nc; }
+  // the CTA (pair) whose range holds unit u: the largest c with begin(c) <= u
+  __device__ __forceinline__ int cta_of(long long u) const { return int(((u + 1) * (long long)nc - 1) / total); }
   // frame and row block of global row block g
   __device__ __forceinline__ void locate(int g, int& b, int& rb) const {
     if (prefix == nullptr) { b = g / RB; rb = g - b * RB; return; }
@@ -111,9 +112,9 @@ struct Sched {
   }
 };
 // Called by every thread of the CTA (contains a __syncthreads when row counts are given).
-__device__ __forceinline__ Sched sched_build(const MatchParams& p, int* smem_prefix, int rows_per_block) {
+__device__ __forceinline__ Sched sched_build(const MatchParams& p, int* smem_prefix, int rows_per_block, int nc) {
   Sched s;
-  s.T = p.T; s.RB = p.RB; s.B = p.B; s.prefix = nullptr; s.total = p.total_units;
+  s.T = p.T; s.RB = p.RB; s.B = p.B; s.prefix = nullptr; s.total = p.total_units; s.nc = nc;
   if (p.n_rows != nullptr) {
     if (threadIdx.x == 0) {
       int acc = 0;
@@ -127,6 +128,10 @@ __device__ __forceinline__ Sched sched_build(const MatchParams& p, int* smem_pre
     s.prefix = smem_prefix;
     s.total = (long long)smem_prefix[p.B] * p.T;
   }
+  // Never more scheduling entities than units: begin() would leave CTAs with empty ranges BETWEEN the CTAs of a row
+  // block, and the merge of that block counts one arrival per CTA of [c_lo, c_hi].  (Only the device knows the unit
+  // count when rows were compacted.)  CTAs with index >= nc have nothing to do.
+  if ((long long)s.nc > s.total) s.nc = int(s.total);
   return s;
 }
 

@@ -920,12 +920,19 @@ int match_pair_stages(int KB, bool cta2 = false) {
 // kPrune (GADM_MATCH_ARGMAX_BF16N, same operands): exact scores, but a 32-column chunk is skipped -- no scale LDS, no
 // multiply, no stash -- when max(raw, 0) * (1 + 2^-8) cannot beat the running maximum of any row of the warp: every
 // column scale of BF16N operands is <= 1 / (1 - 2^-9), products round monotonically, so nothing is ever missed.
-template <bool kUnit, bool kPrune>
+// kCta2 (match.alt_cta2): the CTAs run as pairs (clusters of two, cta_group::2 MMAs with M = 256).  A pair shares its
+// units -- (pair of row blocks, model tile) --, each CTA keeps its own row block, row tiles and accumulators but only
+// HALF of every model tile (128 of the 256 vertices) in shared memory: a third fewer operand wavefronts and half the TMA
+// writes on the shared-memory data pipe that bounds this kernel.  The leader issues every MMA and hears both CTAs'
+// epilogues on its s_free barriers; commits are multicast to both CTAs.
+template <bool kUnit, bool kPrune, bool kCta2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
                  const MatchParams p) {
   constexpr int RT = 2;
   constexpr int AUX_BYTES = PLANE_BYTES;
+  constexpr int STAGE_BYTES = kCta2 ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
+  constexpr int STAGE_ROWS = kCta2 ? BN / 2 : BN;
   constexpr int SL = 4;                      // column slices per row
   constexpr int CS = BN / SL;                // 64 columns per slice
 
@@ -933,7 +940,7 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                    // [RT][KB] blocks of 128 rows x 64 k
   uint8_t* smem_b = smem_a + RT * p.KB * A_BLK_BYTES;
-  uint8_t* smem_aux = smem_b + p.stages * B_STAGE_BYTES;   // per slot: 1/|m| x256
+  uint8_t* smem_aux = smem_b + p.stages * STAGE_BYTES;   // per slot: 1/|m| x256
   float* smem_xmax = reinterpret_cast<float*>(smem_aux + AUX_SLOTS * AUX_BYTES);   // [RT][SL][128] running maxima
   float2* smem_xch = reinterpret_cast<float2*>(smem_xmax + RT * SL * BM);           // [RT][SL - 1][128] slice merge
   Barriers* bars = reinterpret_cast<Barriers*>(smem_xch + RT * (SL - 1) * BM);
@@ -941,10 +948,14 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // this CTA's share of the (frame, row block, model tile) units
-  const Sched sch = sched_build(p, smem_prefix, BM * RT);
-  const long long u_begin = sch.begin(blockIdx.x), u_end = sch.begin(blockIdx.x + 1);
-  if (u_begin >= u_end) return;                // (row compaction can leave fewer units than CTAs)
+  // this CTA's (pair's) share of the (frame, row block, model tile) units; a pair's row block is 512 rows, rank r of
+  // the pair owns rows [256 r, 256 r + 256) of it
+  const uint32_t rank = kCta2 ? ptx::cluster_ctarank() : 0;     // == blockIdx.x & 1
+  const int cidx = kCta2 ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  constexpr int BLOCK_ROWS = BM * RT * (kCta2 ? 2 : 1);
+  const Sched sch = sched_build(p, smem_prefix, BLOCK_ROWS, kCta2 ? int(gridDim.x >> 1) : int(gridDim.x));
+  if (cidx >= sch.nc) return;                  // (row compaction can leave fewer units than CTAs; pair-uniform)
+  const long long u_begin = sch.begin(cidx), u_end = sch.begin(cidx + 1);
 
   if (warp == EPI_WARPS && lane == 0) {
     ptx::prefetch_tensormap(&tmap_rows);
@@ -957,8 +968,8 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
     ptx::mbar_init(&bars->a_free, 1);
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&bars->s_full[a], 1);
-      ptx::mbar_init(&bars->s_free[a], EPI_WARPS);   // every epilogue warp drains every accumulator
-    }
+      ptx::mbar_init(&bars->s_free[a], kCta2 ? 2 * EPI_WARPS : EPI_WARPS);   // every epilogue warp (of both CTAs)
+    }                                                                          // drains every accumulator
     for (int a = 0; a < AUX_SLOTS; ++a) {
       ptx::mbar_init(&bars->aux_full[a], 1);
       ptx::mbar_init(&bars->aux_empty[a], EPI_WARPS);
@@ -966,17 +977,18 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
     ptx::fence_mbar_init();
   }
   if (warp == EPI_WARPS + 1) {
-    ptx::tmem_alloc(&bars->tmem_base, TMEM_COLS);
-    ptx::tmem_relinquish();
+    if (kCta2) { ptx::tmem_alloc_pair(&bars->tmem_base, TMEM_COLS); ptx::tmem_relinquish_pair(); }
+    else       { ptx::tmem_alloc(&bars->tmem_base, TMEM_COLS); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kCta2) ptx::cluster_sync(); else __syncthreads();   // the peer's barriers are initialised too
   ptx::tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == EPI_WARPS) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
+      const uint32_t a_full_ldr = kCta2 ? ptx::mapa(ptx::smem_u32(&bars->a_full), 0) : 0;
       int stage = 0;
       uint32_t phase = 0, n = 0, seg = 0;      // n: model tiles this CTA has started so far (all segments)
       for (long long u = u_begin; u < u_end; ++seg) {
@@ -984,15 +996,20 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
         const int tb = int(min((long long)p.T, ta + (u_end - u)));
         int b, rb;
         sch.locate(rbg, b, rb);
-        const int row0 = rb * (BM * RT);
+        const int row0 = rb * BLOCK_ROWS + int(rank) * (BM * RT);
         const int obj = frame_object(p, b);
         // the row tiles of the previous segment are dead once its last MMA has completed
         if (seg > 0) ptx::mbar_wait_sleep(&bars->a_free, (seg - 1) & 1);
-        ptx::mbar_arrive_expect_tx(&bars->a_full, RT * p.KB * A_BLK_BYTES);
+        if (rank == 0) ptx::mbar_arrive_expect_tx(&bars->a_full, (kCta2 ? 2 : 1) * RT * p.KB * A_BLK_BYTES);
         for (int r = 0; r < RT; ++r)
-          for (int kb = 0; kb < p.KB; ++kb)
-            ptx::tma_load_3d(smem_a + (r * p.KB + kb) * A_BLK_BYTES, &tmap_rows, &bars->a_full, kb * BK,
-                             row0 + r * BM, b);   // rows >= N are zero-filled by TMA
+          for (int kb = 0; kb < p.KB; ++kb) {    // rows >= N are zero-filled by TMA
+            if (kCta2)
+              ptx::tma_load_3d_pair(smem_a + (r * p.KB + kb) * A_BLK_BYTES, &tmap_rows, a_full_ldr, kb * BK,
+                                    row0 + r * BM, b);
+            else
+              ptx::tma_load_3d(smem_a + (r * p.KB + kb) * A_BLK_BYTES, &tmap_rows, &bars->a_full, kb * BK,
+                               row0 + r * BM, b);
+          }
         const float* sc_tab = p.scales + size_t(obj) * p.M;
         for (int t = ta; t < tb; ++t, ++n) {
           const int slot = n % AUX_SLOTS;
@@ -1005,8 +1022,14 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
           }
           for (int kb = 0; kb < p.KB; ++kb) {
             ptx::mbar_wait_sleep(&bars->empty[stage], phase ^ 1);
-            ptx::mbar_arrive_expect_tx(&bars->full[stage], B_STAGE_BYTES);
-            ptx::tma_load_3d(smem_b + stage * B_STAGE_BYTES, &tmap_cols, &bars->full[stage], kb * BK, t * BN, obj);
+            // (kCta2: both halves complete on the leader's barrier, see match_pair_kernel)
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&bars->full[stage], B_STAGE_BYTES);
+            if (kCta2)
+              ptx::tma_load_3d_pair(smem_b + stage * STAGE_BYTES, &tmap_cols,
+                                    ptx::mapa(ptx::smem_u32(&bars->full[stage]), 0), kb * BK,
+                                    t * BN + int(rank) * STAGE_ROWS, obj);
+            else
+              ptx::tma_load_3d(smem_b + stage * STAGE_BYTES, &tmap_cols, &bars->full[stage], kb * BK, t * BN, obj);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -1015,8 +1038,8 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
     }
   } else if (warp == EPI_WARPS + 1) {
     // ============================== UMMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(BM, BN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(kCta2 ? 2 * BM : BM, BN);
       // descriptors as 32-bit low words + one constant high word, accumulator address a function of r alone (the CTA
       // owns all 512 columns: its allocation starts at column 0) -- see match_pair_kernel
       constexpr uint64_t DESC_HI = uint64_t((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
@@ -1043,20 +1066,26 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
                 ptx::tc_fence_after();
               }
               const uint32_t a_lo = a_lo0 + uint32_t(r * p.KB + kb) * (A_BLK_BYTES >> 4);
-              const uint32_t b_lo = b_lo0 + uint32_t(stage) * (B_STAGE_BYTES >> 4);
+              const uint32_t b_lo = b_lo0 + uint32_t(stage) * (STAGE_BYTES >> 4);
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) {
-                ptx::umma_bf16_ss(d_tmem, DESC_HI | (a_lo + k * (UMMA_K * 2 >> 4)),
-                                  DESC_HI | (b_lo + k * (UMMA_K * 2 >> 4)), idesc, (kb | k) != 0);
+                if (kCta2)
+                  ptx::umma_bf16_ss_pair(d_tmem, DESC_HI | (a_lo + k * (UMMA_K * 2 >> 4)),
+                                         DESC_HI | (b_lo + k * (UMMA_K * 2 >> 4)), idesc, (kb | k) != 0);
+                else
+                  ptx::umma_bf16_ss(d_tmem, DESC_HI | (a_lo + k * (UMMA_K * 2 >> 4)),
+                                    DESC_HI | (b_lo + k * (UMMA_K * 2 >> 4)), idesc, (kb | k) != 0);
               }
-              if (r == RT - 1) ptx::umma_commit(&bars->empty[stage]);  // frees the stage once these MMAs have read it
+              if (r == RT - 1) {   // frees the stage (in both CTAs) once these MMAs have read it
+                if (kCta2) ptx::umma_commit_pair(&bars->empty[stage]); else ptx::umma_commit(&bars->empty[stage]);
+              }
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
-            ptx::umma_commit(&bars->s_full[r]);     // accumulator tile complete
+            if (kCta2) ptx::umma_commit_pair(&bars->s_full[r]); else ptx::umma_commit(&bars->s_full[r]);   // tile complete
             if (r == RT - 1) { stage0 = stage; phase0 = phase; }
           }
         }
-        ptx::umma_commit(&bars->a_free);            // the row tiles may be overwritten
+        if (kCta2) ptx::umma_commit_pair(&bars->a_free); else ptx::umma_commit(&bars->a_free);   // row tiles are dead
         u += ntiles;
       }
     }
@@ -1070,6 +1099,7 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
     // stash entry of row tile r, float4 k: + (2 r + k) * 8192 (plane-major: coalesced 512-byte warp stores)
     uint8_t* stash = p.stash + size_t(ptx::smid()) * STASH_SLOT_BYTES + threadIdx.x * 16;
     const int rbg_first = int(u_begin / p.T);        // the row block this CTA's first segment belongs to
+    const uint32_t s_free_ldr = kCta2 ? ptx::mapa(ptx::smem_u32(&bars->s_free[0]), 0) : 0;
 
     uint32_t n = 0;
     for (long long u = u_begin; u < u_end;) {
@@ -1077,7 +1107,7 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
       const int tb = int(min((long long)p.T, ta + (u_end - u)));
       int b, rb;
       sch.locate(rbg, b, rb);
-      const int row0 = rb * (BM * RT);
+      const int row0 = rb * BLOCK_ROWS + int(rank) * (BM * RT);
       const int nrows = frame_rows(p, b);
       const int obj = frame_object(p, b);
       u += tb - ta;
@@ -1172,7 +1202,7 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            ptx::mbar_arrive(&bars->s_free[r]);
+            if (kCta2) ptx::mbar_arrive_cluster(s_free_ldr + r * 8); else ptx::mbar_arrive(&bars->s_free[r]);
             if (!kUnit && r == RT - 1) ptx::mbar_arrive(&bars->aux_empty[slot]);
           }
         }
@@ -1242,8 +1272,10 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
           __threadfence();
           asm volatile("bar.sync 3, 128;" ::: "memory");
           if (threadIdx.x == 0) {
+            // (kCta2: c counts pairs; rank r of every pair holds rows [256 r, 256 r + 256) of the row block, so the two
+            // ranks merge independently: own counter, own partial slots)
             const int c_lo = sch.cta_of((long long)rbg * p.T), c_hi = sch.cta_of((long long)(rbg + 1) * p.T - 1);
-            const unsigned int old = atomicAdd(&p.seg_count[c_lo], 1u);
+            const unsigned int old = atomicAdd(&p.seg_count[kCta2 ? c_lo * 2 + int(rank) : c_lo], 1u);
             bars->merge_lo = old == unsigned(c_hi - c_lo) ? c_lo : -1;
             bars->merge_hi = c_hi;
           }
@@ -1255,7 +1287,8 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
             for (int r = 0; r < RT; ++r) { vm[r] = -INFINITY; vi[r] = NO_RECORD; }
             for (int c = c_lo; c <= c_hi; ++c) {     // ascending columns: on ties the earlier segment wins
               const float2* q2 = reinterpret_cast<const float2*>(p.partial) +
-                                 (size_t(c) * 2 + (int(sch.begin(c) / p.T) == rbg ? 0 : 1)) * PART_ROWS;
+                                 (size_t(kCta2 ? c * 2 + int(rank) : c) * 2 + (int(sch.begin(c) / p.T) == rbg ? 0 : 1)) *
+                                     PART_ROWS;
 #pragma unroll
               for (int r = 0; r < RT; ++r) {
                 float x, y;
@@ -1292,21 +1325,22 @@ match_alt_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kCta2) ptx::cluster_sync(); else __syncthreads();   // the pair's MMAs read both CTAs' shared memory
   if (warp == EPI_WARPS + 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    if (kCta2) ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS); else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
 constexpr int SCHED_MAX_FRAMES = 2048;          // frames a persistent kernel can schedule from device-side row counts
-inline size_t match_alt_smem_bytes(int KB, int stages) {
-  return size_t(2) * KB * A_BLK_BYTES + size_t(stages) * B_STAGE_BYTES + AUX_SLOTS * PLANE_BYTES + 2 * 4 * BM * 4 +
-         2 * 3 * BM * 8 + sizeof(Barriers) + (SCHED_MAX_FRAMES + 1) * sizeof(int) + 1024;
+inline size_t match_alt_smem_bytes(int KB, int stages, bool cta2 = false) {
+  return size_t(2) * KB * A_BLK_BYTES + size_t(stages) * (cta2 ? B_STAGE_BYTES / 2 : B_STAGE_BYTES) +
+         AUX_SLOTS * PLANE_BYTES + 2 * 4 * BM * 4 + 2 * 3 * BM * 8 + sizeof(Barriers) +
+         (SCHED_MAX_FRAMES + 1) * sizeof(int) + 1024;
 }
-inline int match_alt_stages(int KB) {
+inline int match_alt_stages(int KB, bool cta2 = false) {
   int stages = MAX_STAGES;
-  while (stages > 0 && match_alt_smem_bytes(KB, stages) > 227 * 1024) --stages;
+  while (stages > 0 && match_alt_smem_bytes(KB, stages, cta2) > 227 * 1024) --stages;
   return stages;
 }
 
@@ -1334,6 +1368,7 @@ struct MatchConfig {
   int rt = -1;          // match.rt    1 / 2: row tiles per CTA of match_kernel
   int ctas = -1;        // match.ctas  grid of the persistent kernels (default: one CTA per SM)
   int cta2 = -1;        // match.cta2  1: CTA pairs (cta_group::2) in the paired-row kernel (default: single CTAs)
+  int alt_cta2 = -1;    // match.alt_cta2  1 / 0: CTA pairs in the alternating ARGMAX kernel
 };
 MatchConfig g_cfg;
 
@@ -1354,6 +1389,7 @@ int match_config_set(const char* key, int value) {
   if (!strcmp(key, "match.rt")) { g_cfg.rt = value; return GADM_OK; }
   if (!strcmp(key, "match.ctas")) { g_cfg.ctas = value; return GADM_OK; }
   if (!strcmp(key, "match.cta2")) { g_cfg.cta2 = value; return GADM_OK; }
+  if (!strcmp(key, "match.alt_cta2")) { g_cfg.alt_cta2 = value; return GADM_OK; }
   return GADM_ERR_BAD_ARG;
 }
 
@@ -1368,9 +1404,12 @@ int match_configure(int device) {
   if ((rc = set_smem_limit(match_pair_kernel<true, false>)) != GADM_OK) return rc;
   if ((rc = set_smem_limit(match_pair_kernel<false, true>)) != GADM_OK) return rc;
   if ((rc = set_smem_limit(match_pair_kernel<true, true>)) != GADM_OK) return rc;
-  if ((rc = set_smem_limit(match_alt_kernel<false, false>)) != GADM_OK) return rc;
-  if ((rc = set_smem_limit(match_alt_kernel<true, false>)) != GADM_OK) return rc;
-  if ((rc = set_smem_limit(match_alt_kernel<false, true>)) != GADM_OK) return rc;
+  if ((rc = set_smem_limit(match_alt_kernel<false, false, false>)) != GADM_OK) return rc;
+  if ((rc = set_smem_limit(match_alt_kernel<true, false, false>)) != GADM_OK) return rc;
+  if ((rc = set_smem_limit(match_alt_kernel<false, true, false>)) != GADM_OK) return rc;
+  if ((rc = set_smem_limit(match_alt_kernel<false, false, true>)) != GADM_OK) return rc;
+  if ((rc = set_smem_limit(match_alt_kernel<true, false, true>)) != GADM_OK) return rc;
+  if ((rc = set_smem_limit(match_alt_kernel<false, true, true>)) != GADM_OK) return rc;
   int sms = 0;
   cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (e != cudaSuccess) return set_cuda_error(e);
@@ -1416,15 +1455,43 @@ static int match_launch_t(const void* rows, const void* cols, MatchParams p, int
       if (rc != GADM_OK) return rc;
       rc = make_tmap_2b_3d(&tmap_cols, cols, uint64_t(Kp), uint64_t(p.M), uint64_t(p.n_obj), BK, BN, 0);
       if (rc != GADM_OK) return rc;
+      const bool cta2 = cfg.alt_cta2 == 1 && grid >= 2 && p.N > PART_ROWS;
+      if (cta2) {
+        // CTA pairs: units are (pair of row blocks, model tile), dealt out to grid / 2 clusters
+        p.stages = match_alt_stages(KB, true);
+        p.RB = (p.N + 2 * PART_ROWS - 1) / (2 * PART_ROWS);
+        p.total_units = (long long)p.B * p.RB * p.T;
+        int pairs = (cfg.ctas > 0 ? min(cfg.ctas, sms) : sms) / 2;
+        if ((long long)pairs > p.total_units) pairs = int(p.total_units);
+        if (pairs < 1) pairs = 1;
+        grid = 2 * pairs;
+        rc = make_tmap_2b_3d(&tmap_cols, cols, uint64_t(Kp), uint64_t(p.M), uint64_t(p.n_obj), BK, BN / 2, 0);
+        if (rc != GADM_OK) return rc;
+      }
       cudaError_t e = cudaMemsetAsync(p.seg_count, 0, size_t(grid) * sizeof(unsigned int), stream);
       if (e != cudaSuccess) return set_cuda_error(e);
+      if (cta2) {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(grid); lc.blockDim = dim3(NUM_THREADS);
+        lc.dynamicSmemBytes = match_alt_smem_bytes(KB, p.stages, true);
+        lc.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        if (p.unit_scales == 1) e = cudaLaunchKernelEx(&lc, match_alt_kernel<true, false, true>, tmap_rows, tmap_cols, p);
+        else if (p.unit_scales == 2) e = cudaLaunchKernelEx(&lc, match_alt_kernel<false, true, true>, tmap_rows, tmap_cols, p);
+        else e = cudaLaunchKernelEx(&lc, match_alt_kernel<false, false, true>, tmap_rows, tmap_cols, p);
+        if (e != cudaSuccess) return set_cuda_error(e);
+        return check_launch();
+      }
       const size_t smem = match_alt_smem_bytes(KB, astages);
       if (p.unit_scales == 1)
-        match_alt_kernel<true, false><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+        match_alt_kernel<true, false, false><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
       else if (p.unit_scales == 2)
-        match_alt_kernel<false, true><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+        match_alt_kernel<false, true, false><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
       else
-        match_alt_kernel<false, false><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+        match_alt_kernel<false, false, false><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
       return check_launch();
     }
   }

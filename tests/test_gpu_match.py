@@ -143,6 +143,31 @@ def test_match_row_compaction_vs_oracle(cuda, mode):
             assert torch.equal(scat[k][b].cpu()[mask[b]], full[k][b].cpu()[mask[b]])
 
 
+@pytest.mark.parametrize("frac", [0.02, 0.1, 0.4])
+@pytest.mark.parametrize("B,N,M", [(3, 1500, 2056), (1, 12800, 8192), (2, 900, 520)])
+def test_match_few_selected_rows_fewer_units_than_sms(cuda, B, N, M, frac):
+    """A mask that keeps so few rows that the persistent ARGMAX kernel has fewer (row block, model tile) units than the
+    GPU has SMs -- one object instance with some hundred foreground points.  (The unit count is only known on the
+    device then; CTAs without units must not sit between the CTAs that share a row block, or its merge never ends and
+    every index stays -1.)  Against the oracle on the compacted rows, both modes."""
+    from gadm_b200 import matching, synth
+    d = 128
+    rgbd, mesh, _ = synth.descriptors(B, N, M, d, n_obj=1, regime="planted", seed=5 + N)
+    xyz = synth.fibonacci_sphere(M, 0.2)
+    g = torch.Generator().manual_seed(N + int(frac * 100))
+    mask = torch.rand((B, N), generator=g) < frac
+    bank = matching.ModelBank(mesh.to(cuda), xyz[None].to(cuda))
+    for mode in ("argmax", "soft"):
+        out = matching.match(rgbd.to(cuda), bank, mask=mask.to(cuda), mode=mode)
+        for b in range(B):
+            ref = mo.match_soft(rgbd[b], mesh[0], xyz, row_mask=mask[b])
+            idx = out[0][b].cpu()
+            assert torch.all(idx[~mask[b]] == -1)
+            ok = ref["margin"] > TOL
+            assert torch.equal(idx[mask[b]][ok], ref["idx"][ok])
+            assert (out[1][b].cpu()[mask[b]] - ref["max_sim"]).abs().max() <= TOL
+
+
 def test_match_obj_id_is_validated(cuda):
     """A bank slot outside [0, n_obj) (e.g. a 1-based YCB-V class id used as is) is rejected on the host."""
     from gadm_b200 import matching, synth
@@ -325,7 +350,9 @@ def cfg():
 @pytest.mark.parametrize("env", [{"match.alt": 0, "match.pair": 0, "match.rt": 1},
                                  {"match.alt": 0, "match.pair": 0, "match.rt": 2},
                                  {"match.alt": 0, "match.pair": 1}, {"match.alt": 0, "match.pair": 1, "match.cta2": 1},
-                                 {"match.alt": 1}, {"match.ctas": 5}, {"match.ctas": 37}, {"match.ctas": 1}])
+                                 {"match.alt": 1}, {"match.ctas": 5}, {"match.ctas": 37}, {"match.ctas": 1},
+                                 {"match.alt_cta2": 1}, {"match.alt_cta2": 1, "match.ctas": 6},
+                                 {"match.alt_cta2": 1, "match.ctas": 38}])
 def test_match_kernel_variants_agree(cuda, cfg, env):
     """The kernels of the matcher (one row tile per CTA, two row tiles per CTA, paired rows per thread with and
     without CTA pairs -- cta_group::2 MMAs over a cluster of two row blocks --, the
@@ -392,9 +419,39 @@ def test_match_bf16n_operands_and_unit_argmax(cuda):
         matching.match(rgbd.to(cuda), matching.ModelBank(mesh.to(cuda), xyz[None].to(cuda)), mode="argmax_unit")
 
 
+@pytest.mark.parametrize("ctas", [0, 2, 14, 74])
+@pytest.mark.parametrize("B,N,M", [(3, 1500, 2056), (1, 257, 520), (2, 3333, 8192), (5, 700, 264)])
+def test_match_argmax_cta_pairs_change_nothing(cuda, cfg, B, N, M, ctas):
+    """match.alt_cta2: the persistent ARGMAX kernel as CTA pairs (cta_group::2 MMAs, half a model tile per CTA, units =
+    pairs of row blocks).  Indices and similarities are bit-identical to the single-CTA kernel: odd numbers of row
+    blocks per frame (the second CTA of the last pair has no rows), ragged model tiles, row blocks split over several
+    pairs and merged, compacted rows (device-side row counts), every ARGMAX flavour."""
+    from gadm_b200 import matching, ops, synth
+    d = 128
+    rgbd, mesh, _ = synth.descriptors(B, N, M, d, n_obj=1, regime="random", seed=31 + N)
+    xyz = synth.fibonacci_sphere(M, 0.2)[None].to(cuda)
+    g = torch.Generator().manual_seed(N)
+    mask = (torch.rand((B, N), generator=g) < 0.4).to(cuda)
+    bank = matching.ModelBank(mesh.to(cuda), xyz)
+    bank_n = matching.ModelBank(mesh.to(cuda), xyz, operand_mode="bf16n")
+
+    def run():
+        outs = [matching.match(rgbd.to(cuda), bank, mode="argmax"),
+                matching.match(rgbd.to(cuda), bank, mode="argmax", mask=mask),
+                matching.match(rgbd.to(cuda), bank_n, mode="argmax", operand_mode="bf16n"),
+                matching.match(rgbd.to(cuda), bank_n, mode="argmax_unit", operand_mode="bf16n")]
+        return [(o[0].clone(), o[1].clone()) for o in outs]
+    want = run()
+    cfg({"match.alt_cta2": 1, **({"match.ctas": ctas} if ctas else {})})
+    got = run()
+    for (wi, ws), (gi, gs) in zip(want, got):
+        assert torch.equal(wi, gi) and torch.equal(ws, gs)
+
+
 @pytest.mark.parametrize("env", [{}, {"match.alt": 0}, {"match.alt": 0, "match.rt": 1},
                                  {"match.alt": 0, "match.pair": 1}, {"match.alt": 0, "match.pair": 1, "match.cta2": 1},
-                                 {"match.ctas": 3}, {"match.ctas": 11}, {"match.ctas": 50}])
+                                 {"match.ctas": 3}, {"match.ctas": 11}, {"match.ctas": 50}, {"match.alt_cta2": 1},
+                                 {"match.alt_cta2": 1, "match.ctas": 10}])
 def test_match_exact_ties_first_index_wins(cuda, cfg, env):
     """torch.max returns the FIRST maximal index of the scores it is given (evaluator.py:93).  Model vertices duplicated bit for bit across
     groups, chunks, column slices, model tiles and (alternating kernel) beyond the tiles after which the slices
