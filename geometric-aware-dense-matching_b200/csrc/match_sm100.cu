@@ -920,7 +920,7 @@ int match_pair_stages(int KB, bool cta2 = false) {
 // kPrune (GADM_MATCH_ARGMAX_BF16N, same operands): exact scores, but a 32-column chunk is skipped -- no scale LDS, no
 // multiply, no stash -- when max(raw, 0) * (1 + 2^-8) cannot beat the running maximum of any row of the warp: every
 // column scale of BF16N operands is <= 1 / (1 - 2^-9), products round monotonically, so nothing is ever missed.
-// kCta2 (match.alt_cta2): the CTAs run as pairs (clusters of two, cta_group::2 MMAs with M = 256).  A pair shares its
+// kCta2 (default; match.alt_cta2 = 0 switches it off): the CTAs run as pairs (clusters of two, cta_group::2 MMAs with M = 256).  A pair shares its
 // units -- (pair of row blocks, model tile) --, each CTA keeps its own row block, row tiles and accumulators but only
 // HALF of every model tile (128 of the 256 vertices) in shared memory: a third fewer operand wavefronts and half the TMA
 // writes on the shared-memory data pipe that bounds this kernel.  The leader issues every MMA and hears both CTAs'
@@ -1368,7 +1368,7 @@ struct MatchConfig {
   int rt = -1;          // match.rt    1 / 2: row tiles per CTA of match_kernel
   int ctas = -1;        // match.ctas  grid of the persistent kernels (default: one CTA per SM)
   int cta2 = -1;        // match.cta2  1: CTA pairs (cta_group::2) in the paired-row kernel (default: single CTAs)
-  int alt_cta2 = -1;    // match.alt_cta2  1 / 0: CTA pairs in the alternating ARGMAX kernel
+  int alt_cta2 = -1;    // match.alt_cta2  0: single CTAs in the alternating ARGMAX kernel (default: CTA pairs)
 };
 MatchConfig g_cfg;
 
@@ -1455,7 +1455,9 @@ static int match_launch_t(const void* rows, const void* cols, MatchParams p, int
       if (rc != GADM_OK) return rc;
       rc = make_tmap_2b_3d(&tmap_cols, cols, uint64_t(Kp), uint64_t(p.M), uint64_t(p.n_obj), BK, BN, 0);
       if (rc != GADM_OK) return rc;
-      const bool cta2 = cfg.alt_cta2 == 1 && grid >= 2 && p.N > PART_ROWS;
+      // CTA pairs by default: bit-identical results, 2-4 % faster at the BASELINE shape in every ARGMAX flavour, alone
+      // and under the kNN pyramid of a second stream (tools/bench_match.py, tools/bench_overlap.py)
+      const bool cta2 = cfg.alt_cta2 != 0 && grid >= 2 && p.N > PART_ROWS;
       if (cta2) {
         // CTA pairs: units are (pair of row blocks, model tile), dealt out to grid / 2 clusters
         p.stages = match_alt_stages(KB, true);

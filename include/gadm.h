@@ -72,6 +72,7 @@ int gadm_init(int device);
  *   "match.alt"   0 forbids the alternating persistent ARGMAX kernel        "match.pair"  1 / 0 forces / forbids the paired-row kernel
  *   "match.rt"    1 / 2 row tiles per CTA of the generic kernel             "match.ctas"  grid of the persistent kernels (<= SM count)
  *   "match.cta2"  1: CTA pairs (clusters of two, tcgen05.mma.cta_group::2) in the paired-row kernel
+ *   "match.alt_cta2"  0: single CTAs instead of CTA pairs in the alternating ARGMAX kernel
  *   "knn.ppc"     target points per occupied grid cell column (1..64, default 16)
  *   "knn.grid_min" GADM_KNN_AUTO scans clouds with fewer points than this (default 128)
  * Results do not depend on any of them.  GADM_ERR_BAD_ARG for an unknown key.  The library reads no environment

@@ -351,8 +351,8 @@ def cfg():
                                  {"match.alt": 0, "match.pair": 0, "match.rt": 2},
                                  {"match.alt": 0, "match.pair": 1}, {"match.alt": 0, "match.pair": 1, "match.cta2": 1},
                                  {"match.alt": 1}, {"match.ctas": 5}, {"match.ctas": 37}, {"match.ctas": 1},
-                                 {"match.alt_cta2": 1}, {"match.alt_cta2": 1, "match.ctas": 6},
-                                 {"match.alt_cta2": 1, "match.ctas": 38}])
+                                 {"match.alt_cta2": 0}, {"match.alt_cta2": 0, "match.ctas": 5},
+                                 {"match.alt_cta2": 0, "match.ctas": 37}, {"match.alt_cta2": 0, "match.ctas": 1}])
 def test_match_kernel_variants_agree(cuda, cfg, env):
     """The kernels of the matcher (one row tile per CTA, two row tiles per CTA, paired rows per thread with and
     without CTA pairs -- cta_group::2 MMAs over a cluster of two row blocks --, the
@@ -422,8 +422,8 @@ def test_match_bf16n_operands_and_unit_argmax(cuda):
 @pytest.mark.parametrize("ctas", [0, 2, 14, 74])
 @pytest.mark.parametrize("B,N,M", [(3, 1500, 2056), (1, 257, 520), (2, 3333, 8192), (5, 700, 264)])
 def test_match_argmax_cta_pairs_change_nothing(cuda, cfg, B, N, M, ctas):
-    """match.alt_cta2: the persistent ARGMAX kernel as CTA pairs (cta_group::2 MMAs, half a model tile per CTA, units =
-    pairs of row blocks).  Indices and similarities are bit-identical to the single-CTA kernel: odd numbers of row
+    """The persistent ARGMAX kernel runs as CTA pairs by default (cta_group::2 MMAs, half a model tile per CTA, units =
+    pairs of row blocks; match.alt_cta2 = 0: single CTAs).  Indices and similarities are bit-identical between the two: odd numbers of row
     blocks per frame (the second CTA of the last pair has no rows), ragged model tiles, row blocks split over several
     pairs and merged, compacted rows (device-side row counts), every ARGMAX flavour."""
     from gadm_b200 import matching, ops, synth
@@ -441,6 +441,7 @@ def test_match_argmax_cta_pairs_change_nothing(cuda, cfg, B, N, M, ctas):
                 matching.match(rgbd.to(cuda), bank_n, mode="argmax", operand_mode="bf16n"),
                 matching.match(rgbd.to(cuda), bank_n, mode="argmax_unit", operand_mode="bf16n")]
         return [(o[0].clone(), o[1].clone()) for o in outs]
+    cfg({"match.alt_cta2": 0})
     want = run()
     cfg({"match.alt_cta2": 1, **({"match.ctas": ctas} if ctas else {})})
     got = run()
@@ -450,8 +451,8 @@ def test_match_argmax_cta_pairs_change_nothing(cuda, cfg, B, N, M, ctas):
 
 @pytest.mark.parametrize("env", [{}, {"match.alt": 0}, {"match.alt": 0, "match.rt": 1},
                                  {"match.alt": 0, "match.pair": 1}, {"match.alt": 0, "match.pair": 1, "match.cta2": 1},
-                                 {"match.ctas": 3}, {"match.ctas": 11}, {"match.ctas": 50}, {"match.alt_cta2": 1},
-                                 {"match.alt_cta2": 1, "match.ctas": 10}])
+                                 {"match.ctas": 3}, {"match.ctas": 11}, {"match.ctas": 50}, {"match.alt_cta2": 0},
+                                 {"match.alt_cta2": 0, "match.ctas": 3}, {"match.alt_cta2": 0, "match.ctas": 11}])
 def test_match_exact_ties_first_index_wins(cuda, cfg, env):
     """torch.max returns the FIRST maximal index of the scores it is given (evaluator.py:93).  Model vertices duplicated bit for bit across
     groups, chunks, column slices, model tiles and (alternating kernel) beyond the tiles after which the slices

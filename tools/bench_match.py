@@ -26,9 +26,9 @@ PEAK = 1658.8
 CASES = [("argmax", "argmax", False, {}), ("argmax_pair", "argmax", False, {"match.alt": 0, "match.pair": 1}),
          ("argmax_pair_cta2", "argmax", False, {"match.alt": 0, "match.pair": 1, "match.cta2": 1}),
          ("argmax_rt2", "argmax", False, {"match.alt": 0, "match.pair": 0, "match.rt": 2}),
-         ("argmax_cta2", "argmax", False, {"match.alt_cta2": 1}), ("soft", "soft", False, {}),
-         ("argmax_bf16n_cta2", "argmax_bf16n", True, {"match.alt_cta2": 1}),
-         ("argmax_unit_cta2", "argmax_unit", True, {"match.alt_cta2": 1}), ("soft_cta2", "soft", False, {"match.cta2": 1}),
+         ("argmax_single", "argmax", False, {"match.alt_cta2": 0}), ("soft", "soft", False, {}),
+         ("argmax_bf16n_single", "argmax_bf16n", True, {"match.alt_cta2": 0}),
+         ("argmax_unit_single", "argmax_unit", True, {"match.alt_cta2": 0}), ("soft_cta2", "soft", False, {"match.cta2": 1}),
          ("argmax_bf16n", "argmax_bf16n", True, {}), ("argmax_unit", "argmax_unit", True, {})]
 if os.environ.get("CASES"):
     CASES = [c for c in CASES if c[0] in os.environ["CASES"].split(",")]

@@ -1,4 +1,4 @@
-"""Experiment: one bench step (prep + SOFT match + kNN pyramid) with the kNN pyramid on a second stream, so that its
+"""Experiment: one bench step (prep + SOFT (MATCH_MODE=argmax: ARGMAX) match + kNN pyramid) with the kNN pyramid on a second stream, so that its
 CTAs (40 registers, no shared memory) share the SMs with the matcher's (1 CTA per SM, shared-memory bound)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,6 +8,10 @@ from gadm_b200 import ops, synth
 from gadm_b200._lib import MATCH_MODES
 from gadm_b200.knn import KnnPyramid
 
+MM = os.environ.get("MATCH_MODE", "soft")          # soft | argmax
+for kv in os.environ.get("CONFIG", "").split(","):  # e.g. CONFIG=match.alt_cta2=0
+    if kv:
+        ops._lib.config_set(kv.split("=")[0], int(kv.split("=")[1]))
 dev = torch.device("cuda", 0)
 B, N, M, D = 8, 12800, 8192, 128
 sets = []
@@ -38,7 +42,7 @@ def step(i, mode):
         cols, aux = ops.prep_model(mesh, xyz, 0)
         rows, rinv, pad = ops.prep_rows(rgbd, 0, 0)
         e0.record()
-        out = ops.match_fwd(rows, rinv, pad, cols, aux, None, obj, 16.0, 0, MATCH_MODES["soft"])
+        out = ops.match_fwd(rows, rinv, pad, cols, aux, None, obj, 16.0, 0, MATCH_MODES[MM])
         e1.record()
         knn = pyr.run_packed(pts[i % 4])
         return out, knn
@@ -47,7 +51,7 @@ def step(i, mode):
     fork = torch.cuda.Event(); fork.record(cur)
     if mode == "match_first":
         e0.record()
-        out = ops.match_fwd(rows, rinv, pad, cols, aux, None, obj, 16.0, 0, MATCH_MODES["soft"])
+        out = ops.match_fwd(rows, rinv, pad, cols, aux, None, obj, 16.0, 0, MATCH_MODES[MM])
         e1.record()
     with torch.cuda.stream(side):
         side.wait_event(fork)
@@ -55,7 +59,7 @@ def step(i, mode):
         join = torch.cuda.Event(); join.record(side)
     if mode == "knn_first":
         e0.record()
-        out = ops.match_fwd(rows, rinv, pad, cols, aux, None, obj, 16.0, 0, MATCH_MODES["soft"])
+        out = ops.match_fwd(rows, rinv, pad, cols, aux, None, obj, 16.0, 0, MATCH_MODES[MM])
         e1.record()
     cur.wait_event(join)
     return out, knn
