@@ -14,12 +14,14 @@
 //   match_pair_kernel<soft|argmax, cta2>  256 rows per CTA, 128-vertex model tiles, every epilogue thread owns the same
 //                                   lane of both row tiles (a per-column constant serves two scores).  Default for
 //                                   SOFT.  cta2: the same on CTA pairs (cluster of two, tcgen05.mma.cta_group::2).
-//   match_alt_kernel<unit, prune>   ARGMAX default, PERSISTENT: the (frame, row block, model tile) units of a launch are
+//   match_alt_kernel<unit, prune, cta2>  ARGMAX default, PERSISTENT: the (frame, row block, model tile) units of a launch are
 //                                   dealt out evenly to one CTA per SM (match_common.cuh: Sched); per segment all 16
 //                                   epilogue warps drain one accumulator while the tensor core fills the other; stash in
 //                                   the per-SM workspace slot; running maxima shared across the column slices of a row;
 //                                   row blocks split over CTAs are merged by the last CTA to arrive.  unit: no
-//                                   per-column constant; prune: chunks that cannot win are skipped (BF16N operands).
+//                                   per-column constant; prune: chunks that cannot win are skipped (BF16N operands);
+//                                   cta2 (default): CTA pairs, units = (pair of row blocks, model tile), half a model
+//                                   tile per CTA, cta_group::2 MMAs.
 //   (circle_sm100.cu)               CircleLoss: masked exponential sums / dL/dsim in the epilogue of the same skeleton.
 //
 // Common skeleton
