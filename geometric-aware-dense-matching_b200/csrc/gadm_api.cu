@@ -101,6 +101,8 @@ int gadm_init(int device) {
   if (rc != GADM_OK) return rc;
   rc = circle_configure();
   if (rc != GADM_OK) return rc;
+  rc = circle_df_configure();
+  if (rc != GADM_OK) return rc;
   rc = knn3d_configure();
   if (rc != GADM_OK) return rc;
   rc = knn_feat_tc_configure();
@@ -300,6 +302,29 @@ int gadm_circle_loss_bwd_split(const void* rows, const float* rinv_rows, const f
   if (!g_pad) return GADM_ERR_BAD_ARG;
   return circle_bwd_checked(rows, rinv_rows, pad_sim, cols, aux, planes_frame, match_idx, match_idx2, obj_id, B, N, M, Kp,
                             n_obj, gamma, margin, lse_p, lse_n, w, G2, Mp, g_pad, stream);
+}
+
+int gadm_circle_loss_bwd_fused(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
+                               const float* aux, const float* planes_frame, const int64_t* match_idx,
+                               const int64_t* match_idx2, const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj,
+                               float gamma, float margin, const float* lse_p, const float* lse_n, const float* w,
+                               void* G2, int Mp, float* g_pad, float* dF, gadm_stream_t stream) {
+  GADM_REQUIRE_INIT();
+  if (!rows || !rinv_rows || !pad_sim || !cols || !aux || !planes_frame || !match_idx || !lse_p || !lse_n || !w || !G2 ||
+      !g_pad || !dF)
+    return GADM_ERR_BAD_ARG;
+  if (B <= 0 || N <= 0 || M <= 0 || Kp <= 0 || n_obj <= 0) return GADM_ERR_BAD_ARG;
+  if (B > 65535 || M % 8 != 0 || !circle_df_supported(Kp)) return GADM_ERR_UNSUPPORTED;
+  if (Mp < M + 1 || Mp % 8 != 0) return GADM_ERR_BAD_ARG;
+  if (obj_id == nullptr && n_obj != 1 && n_obj != B) return GADM_ERR_BAD_ARG;
+  if (!(margin >= 0.f && margin < 1.f) || !(gamma > 0.f)) return GADM_ERR_BAD_ARG;
+  if (gamma * (2.f + margin) * (2.f - margin) * 1.4426950408889634f > 120.f) return GADM_ERR_UNSUPPORTED;
+  if (!aligned16(rows) || !aligned16(cols) || !aligned16(aux) || !aligned16(planes_frame) ||
+      (reinterpret_cast<uintptr_t>(G2) & 31) != 0 || (reinterpret_cast<uintptr_t>(dF) & 31) != 0)
+    return GADM_ERR_ALIGN;
+  return circle_df_launch(rows, rinv_rows, pad_sim, cols, aux, planes_frame, match_idx, match_idx2, obj_id, B, N, M, Kp,
+                          n_obj, gamma, margin, lse_p, lse_n, w, static_cast<float*>(G2), Mp, g_pad, dF,
+                          (cudaStream_t)stream);
 }
 
 size_t gadm_match_workspace_bytes(void) {

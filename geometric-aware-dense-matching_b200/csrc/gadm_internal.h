@@ -33,6 +33,13 @@ int match_configure(int device);
 int match_config_set(const char* key, int value);
 // circle_sm100.cu
 int circle_configure();
+int circle_df_configure();
+bool circle_df_supported(int Kp);
+int circle_df_launch(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols, const float* aux,
+                     const float* planes_frame, const int64_t* match_idx, const int64_t* match_idx2,
+                     const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma, float margin,
+                     const float* lse_p, const float* lse_n, const float* w, float* G, int Mp, float* g_pad, float* dF,
+                     cudaStream_t stream);
 int match_launch(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols, const float* aux,
                  const uint8_t* mask, const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma,
                  int pad_mode, int mode, int64_t* idx, float* max_sim, float* weight, float* soft_xyz,

@@ -355,6 +355,9 @@ __device__ __forceinline__ void stg_pred32(bool pred, void* gaddr, uint64_t v0, 
       : "memory");
 }
 // 32-byte global store (sm_100: STG.256); gaddr 32-byte aligned
+__device__ __forceinline__ void sts128(uint32_t saddr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 // {upper 16 bits: bf16(hi), lower 16 bits: bf16(lo)}, round to nearest even
 __device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) {
   uint32_t r;

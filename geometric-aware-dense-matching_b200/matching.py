@@ -141,8 +141,8 @@ class _CircleMatchLoss(torch.autograd.Function):
         B, N, d = rows.shape
         n_obj, M, _ = cols.shape
         w = (torch.sigmoid(lse_p + lse_n) * row_w * g_total).contiguous()            # softplus' = sigmoid
-        if ctx.grad_gemm == "bf16x2":
-            return _circle_backward_split(ctx, w)
+        if ctx.grad_gemm in ("bf16x2", "fused"):
+            return _circle_backward_split(ctx, w, fused=ctx.grad_gemm == "fused")
         G = ops.circle_loss_bwd(rows, rinv, pad_sim, cols, aux, planes, mi, ctx.oid, gamma, margin, lse_p, lse_n,
                                 w, ctx.mi2)                                          # [B, N, M + 8]
         f_hat = rows.float() * rinv[..., None]                                       # [B, N, d]
@@ -169,7 +169,7 @@ class _CircleMatchLoss(torch.autograd.Function):
                 None, None, None, None, None, None)
 
 
-def _circle_backward_split(ctx, w):
+def _circle_backward_split(ctx, w, fused=False):
     """grad_gemm = "bf16x2": dL/dsim leaves the kernel with both norms folded in and split into two bf16 parts
     (gadm_circle_loss_bwd_split), so the two gradient products run as bf16 tensor-core GEMMs with fp32 accumulation
     on the forward pass's own bf16 operands -- exact products, 16 mantissa bits of G (tf32 keeps 10 of G AND rounds the
@@ -180,8 +180,13 @@ def _circle_backward_split(ctx, w):
     n_obj, M, _ = cols.shape
     Mp = M + 8
     dev = rows.device
-    G2, g_pad = ops.circle_loss_bwd_split(rows, rinv, pad_sim, cols, aux, planes, mi, ctx.oid, gamma, margin, lse_p,
-                                          lse_n, w, ctx.mi2)                         # [B, N, 2 Mp] bf16, [B, N]
+    dF = None
+    if fused and rows.shape[2] <= 128:      # the scene-side product inside the kernel (second MMA per model tile)
+        G2, g_pad, dF = ops.circle_loss_bwd_fused(rows, rinv, pad_sim, cols, aux, planes, mi, ctx.oid, gamma, margin,
+                                                  lse_p, lse_n, w, ctx.mi2)
+    else:
+        G2, g_pad = ops.circle_loss_bwd_split(rows, rinv, pad_sim, cols, aux, planes, mi, ctx.oid, gamma, margin, lse_p,
+                                              lse_n, w, ctx.mi2)                     # [B, N, 2 Mp] bf16, [B, N]
     k = torch.arange(2 * Mp, device=dev)
     col_of_k = (k // 16) * 8 + k % 8                                                 # K2 of gadm.h
     cols_p = torch.zeros((n_obj, Mp, d), dtype=torch.bfloat16, device=dev)
@@ -193,7 +198,9 @@ def _circle_backward_split(ctx, w):
         m_pad[:] = -(d ** -0.5)
     else:
         m_pad[0] = 1.0
-    d_fhat = torch.bmm(G2, cols2[sel], out_dtype=torch.float32) / rinv[..., None] + g_pad[..., None] * m_pad
+    if dF is None:
+        dF = torch.bmm(G2, cols2[sel], out_dtype=torch.float32)
+    d_fhat = dF / rinv[..., None] + g_pad[..., None] * m_pad
     t = torch.bmm(G2.transpose(1, 2), rows, out_dtype=torch.float32)                 # [B, 2 Mp, d]
     d_mhat_b = t.view(B, Mp // 8, 2, 8, d).sum(2).reshape(B, Mp, d)[:, :M]           # hi + lo
     d_mhat = torch.zeros((n_obj, M, d), dtype=torch.float32, device=dev).index_add_(0, sel, d_mhat_b) / scale
@@ -227,14 +234,15 @@ def circle_match_loss(rgbd, mesh, labels, match_idx, visible_flag, positive_r, m
     fp32 GEMMs on the fp32 dL/dsim; "tf32": the same with tf32 allowed (~3x faster backward, gradient error ~5e-4 of
     the largest entry instead of ~1e-6); "bf16x2": dL/dsim leaves the kernel split into two bf16 parts with both norms
     folded in and the products run as bf16 tensor-core GEMMs on the forward pass's own bf16 operands (exact products,
-    16 mantissa bits of dL/dsim: more accurate than tf32 and faster than either).
+    16 mantissa bits of dL/dsim: more accurate than tf32 and faster than fp32); "fused": as "bf16x2", with the
+    scene-side product accumulated inside the kernel by a second MMA per model tile (d <= 128; falls back to "bf16x2").
     sys_idx (int [>= N], or None): the symmetry-aware variant GeoMatch.matching_loss_sys (models/geoMatch.py:86-100, used
     when model_emb.sys_corr_idx is set, :138-141): the positives of scene point n are exactly the two columns
     match_idx[n] and match_idx[sys_idx[n]] -- no radius, no visibility (positive_r / visible_flag are ignored).
     Returns the scalar the reference returns: the mean over samples with >= 3 foreground rows of the mean row loss
     (0 if there is none); return_rows=True adds the per-row (loss, lse_p, lse_n) tensors."""
-    if grad_gemm not in ("fp32", "tf32", "bf16x2"):
-        raise ValueError("grad_gemm must be 'fp32', 'tf32' or 'bf16x2'")
+    if grad_gemm not in ("fp32", "tf32", "bf16x2", "fused"):
+        raise ValueError("grad_gemm must be 'fp32', 'tf32', 'bf16x2' or 'fused'")
     if isinstance(mesh, ModelBank):
         bank = mesh
         if bank.operand_mode != "bf16":

@@ -390,6 +390,43 @@ def _(rows, rinv, pad_sim, cols, aux, planes_frame, match_idx, obj_id, gamma, ma
             rows.new_empty((B, N), dtype=torch.float32))
 
 
+@torch.library.custom_op("gadm::circle_loss_bwd_fused", mutates_args=(), device_types="cuda")
+def circle_loss_bwd_fused(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tensor, cols: torch.Tensor,
+                          aux: torch.Tensor, planes_frame: torch.Tensor, match_idx: torch.Tensor,
+                          obj_id: torch.Tensor | None, gamma: float, margin: float, lse_p: torch.Tensor,
+                          lse_n: torch.Tensor, w: torch.Tensor,
+                          match_idx2: torch.Tensor | None = None) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(G2, g_pad, dF): circle_loss_bwd_split plus dF [B, N, K'] fp32 = sum_j G''_ij cols_j, accumulated in tensor memory
+    by a second MMA inside the kernel (gadm_circle_loss_bwd_fused; K' <= 128)."""
+    _need(rows, torch.bfloat16, "rows"); _need(cols, torch.bfloat16, "cols")
+    for t, n in ((rinv, "rinv"), (pad_sim, "pad_sim"), (aux, "aux"), (planes_frame, "planes_frame"), (lse_p, "lse_p"),
+                 (lse_n, "lse_n"), (w, "w")):
+        _need(t, torch.float32, n)
+    _need(match_idx, torch.int64, "match_idx")
+    B, N, kp = rows.shape
+    n_obj, M, _ = cols.shape
+    Mp = M + 8
+    G2 = torch.empty((B, N, 2 * Mp), dtype=torch.bfloat16, device=rows.device)
+    g_pad = torch.empty((B, N), dtype=torch.float32, device=rows.device)
+    dF = torch.empty((B, N, kp), dtype=torch.float32, device=rows.device)
+    lib = _lib_for(rows)
+    with torch.cuda.device(rows.device):
+        _lib.check(lib.gadm_circle_loss_bwd_fused(_ptr(rows), _ptr(rinv), _ptr(pad_sim), _ptr(cols), _ptr(aux),
+                                                  _ptr(planes_frame), _ptr(match_idx), _ptr(match_idx2), _ptr(obj_id),
+                                                  B, N, M, kp, n_obj, float(gamma), float(margin), _ptr(lse_p),
+                                                  _ptr(lse_n), _ptr(w), _ptr(G2), Mp, _ptr(g_pad), _ptr(dF), _stream()),
+                   "gadm_circle_loss_bwd_fused")
+    return G2, g_pad, dF
+
+
+@circle_loss_bwd_fused.register_fake
+def _(rows, rinv, pad_sim, cols, aux, planes_frame, match_idx, obj_id, gamma, margin, lse_p, lse_n, w,
+      match_idx2=None):
+    B, N, kp = rows.shape
+    return (rows.new_empty((B, N, 2 * (cols.shape[1] + 8)), dtype=torch.bfloat16),
+            rows.new_empty((B, N), dtype=torch.float32), rows.new_empty((B, N, kp), dtype=torch.float32))
+
+
 @torch.library.custom_op("gadm::kabsch_moments", mutates_args=(), device_types="cuda")
 def kabsch_moments(idx: torch.Tensor, mask: torch.Tensor | None, cloud: torch.Tensor, aux: torch.Tensor,
                    obj_id: torch.Tensor | None, M: int, n_obj: int) -> torch.Tensor:

@@ -26,7 +26,7 @@ def test_library_exports_every_header_symbol():
     from gadm_b200 import _lib
     lib = gadm_b200.load_library()
     syms = header_symbols()
-    assert len(syms) == 39
+    assert len(syms) == 40
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/gadm.h but not exported by libgadm.so"
     assert set(syms) == set(_lib.SIGNATURES), "ctypes signature table must cover the header exactly"

@@ -149,7 +149,44 @@ def test_circle_loss_bwd_split_is_the_fp32_gradient_with_the_norms_folded_in(cud
     assert float(G.abs().max()) > 0
 
 
-@pytest.mark.parametrize("grad_gemm,gate", [("fp32", 1e-3), ("tf32", 3e-3), ("bf16x2", 1e-3)])
+@pytest.mark.parametrize("B,N,M,d,sys2", [(2, 333, 520, 64, False), (1, 700, 1000, 128, False), (2, 130, 264, 128, True),
+                                          (1, 1300, 8192, 128, False)])
+def test_circle_loss_bwd_fused_dF_matches_the_library_product(cuda, B, N, M, d, sys2):
+    """gadm_circle_loss_bwd_fused: G2 and g_pad bit-identical to gadm_circle_loss_bwd_split, and dF -- the second MMA of
+    the kernel, G'' from shared memory against the resident model tile read MN-major -- equal to the same product
+    computed from G2 by a library GEMM (fp32 accumulation in both, in different orders over 2 (M + 8) terms: 5e-5 of
+    the largest entry).  Ragged rows / model
+    tiles, both positive rules."""
+    from gadm_b200 import ops, synth
+    from gadm_b200.ops import OPERAND_MODES, PAD_MODES
+    g = torch.Generator().manual_seed(17 + N)
+    rgbd, mesh, _ = synth.descriptors(B, N, M, d, seed=3 + N)
+    xyz = synth.fibonacci_sphere(M, 0.2)[None].to(cuda)
+    rows, rinv, pad_sim = ops.prep_rows(rgbd.to(cuda), OPERAND_MODES["bf16"], PAD_MODES["minus_one"])
+    cols, aux = ops.prep_model(mesh[:1].to(cuda), xyz, OPERAND_MODES["bf16"])
+    planes = torch.empty((4, B, M), device=cuda)
+    planes[:3] = xyz[0].t()[:, None, :].expand(3, B, M)
+    planes[3] = 0.05 ** 2
+    mi = torch.randint(0, M + 1, (B, N), generator=g).to(cuda)
+    mi2 = torch.randint(0, M + 1, (B, N), generator=g).to(cuda) if sys2 else None
+    fg = torch.ones((B, N), dtype=torch.uint8, device=cuda)
+    _, lp, ln = ops.circle_loss_fwd(rows, rinv, pad_sim, cols, aux, planes, mi, fg, None, 16.0, 0.2, mi2)
+    w = torch.rand((B, N), generator=g).to(cuda)
+    G2, g_pad = ops.circle_loss_bwd_split(rows, rinv, pad_sim, cols, aux, planes, mi, None, 16.0, 0.2, lp, ln, w, mi2)
+    G2f, g_padf, dF = ops.circle_loss_bwd_fused(rows, rinv, pad_sim, cols, aux, planes, mi, None, 16.0, 0.2, lp, ln, w, mi2)
+    assert torch.equal(G2.view(torch.int16), G2f.view(torch.int16)) and torch.equal(g_pad, g_padf)
+    Mp = M + 8
+    k = torch.arange(2 * Mp, device=cuda)
+    col_of_k = (k // 16) * 8 + k % 8
+    cols_p = torch.zeros((1, Mp, d), dtype=torch.bfloat16, device=cuda)
+    cols_p[:, :M] = cols
+    want = torch.bmm(G2, cols_p[:, col_of_k].expand(B, -1, -1), out_dtype=torch.float32)
+    err = (dF - want).abs().max()
+    assert float(want.abs().max()) > 0
+    assert err <= 5e-5 * want.abs().max(), f"dF max err {float(err)} vs max {float(want.abs().max())}"
+
+
+@pytest.mark.parametrize("grad_gemm,gate", [("fp32", 1e-3), ("tf32", 3e-3), ("bf16x2", 1e-3), ("fused", 1e-3)])
 def test_circle_loss_gradients_vs_autograd_of_the_reference_math(cuda, grad_gemm, gate):
     """d loss / d rgbd and d loss / d mesh against torch autograd through the oracle (the reference's own formulas,
     ap / an detached as at loss.py:479-480) on the CPU.  Gate: 1e-3 of the largest gradient entry (3e-3 when the two

@@ -103,13 +103,21 @@ def fused_fwd_bwd_split():
 k_split = timed(lambda: ops.circle_loss_bwd_split(rows, rinv, pad_sim, cols, aux, planes, match_idx, None, 16.0, 0.2, lp_, ln_, w))
 print(f"circle_kernel<grad, split>                  {k_split:.3f} ms")
 print(f"fused forward + backward (bf16x2 grad GEMMs) {timed(fused_fwd_bwd_split, 3):.3f} ms")
-# accuracy of the three gradient paths against the fp32 library GEMMs
+def fused_fwd_bwd_fused():
+    rg.grad = me.grad = None
+    matching.circle_match_loss(rg, me, labels, match_idx, vis, r, model_xyz=xyz, grad_gemm="fused").backward()
+
+
+k_fused = timed(lambda: ops.circle_loss_bwd_fused(rows, rinv, pad_sim, cols, aux, planes, match_idx, None, 16.0, 0.2, lp_, ln_, w))
+print(f"circle_df_kernel (grad + fused dF)          {k_fused:.3f} ms")
+print(f"fused forward + backward (fused dF, bf16x2 dM GEMM) {timed(fused_fwd_bwd_fused, 3):.3f} ms")
+# accuracy of the gradient paths against the fp32 library GEMMs
 grads = {}
-for mode in ("fp32", "tf32", "bf16x2"):
+for mode in ("fp32", "tf32", "bf16x2", "fused"):
     rg.grad = me.grad = None
     matching.circle_match_loss(rg, me, labels, match_idx, vis, r, model_xyz=xyz, grad_gemm=mode).backward()
     grads[mode] = (rg.grad.clone(), me.grad.clone())
-for mode in ("tf32", "bf16x2"):
+for mode in ("tf32", "bf16x2", "fused"):
     e = [float((grads[mode][i] - grads["fp32"][i]).abs().max() / grads["fp32"][i].abs().max()) for i in range(2)]
     print(f"max |grad - grad_fp32| / max |grad_fp32|, {mode:7s}: d rgbd {e[0]:.2e}   d mesh {e[1]:.2e}")
 print(f"torch materialised forward                  {timed(lambda: torch_materialised(False), 3):.3f} ms")
