@@ -2,8 +2,9 @@
 //   dL/df^_i = sum_j dL/dsim_ij m^_j
 // is accumulated in tensor memory by a second MMA per model tile, fed from shared memory with the tile of dL/dsim the
 // epilogue has just computed -- the score tile is recomputed (as in circle_kernel<grad>), nothing of size [N, M] is read
-// back for this product.  dL/dsim still leaves the SM once (the split bf16 form of gadm_circle_loss_bwd_split) for
-// the model-side product G^T F^, which stays a library GEMM.
+// back for this product.  Without kDm dL/dsim still leaves the SM once (the split bf16 form of
+// gadm_circle_loss_bwd_split) for the model-side product G^T F^ as a library GEMM; with kDm that product is formed here
+// as well (see the kernel) and dL/dsim never leaves the SM.
 //
 // Per CTA: one row tile (128 scene rows), model tiles of 128 vertices.
 //   S   [128 x 128]  = F (rows, K-major over d)  x  M_t (K-major over d)          two accumulators, alternating
@@ -14,7 +15,8 @@
 //                      64-wide d blocks, SBO = 1024 B between groups of 8 vertex rows)
 // The stage of a model tile is released by the commit of ITS dF MMAs, the G'' buffer by the same commit; the epilogue of
 // tile t + 1 reaches its first G'' store about when the 16 dF MMAs of tile t have drained, so one buffer suffices.
-// TMEM: S 2 x 128 columns, dF d <= 128 columns.  d <= 128 (K' <= 128) only; other shapes use the library path.
+// TMEM: S 2 x 128 columns, dF d <= 128 columns, kDm: the tile's dM 128 more.  d <= 128 (K' <= 128) only; other shapes
+// use the library path.
 #include "match_common.cuh"
 
 namespace gadm {
@@ -36,6 +38,7 @@ struct DfBarriers {
   uint64_t s_full[2], s_free[2];
   uint64_t aux_full[AUX_SLOTS], aux_empty[AUX_SLOTS];
   uint64_t g_full, g_free, df_full;
+  uint64_t dm_full, dm_free;      // kDm: the model-side tile product is complete / has been drained
   uint32_t tmem_base, pad;
 };
 
@@ -54,11 +57,18 @@ struct DfParams {
   float* G;        // [B, N, Mp] words: split bf16 form
   float* g_pad;    // [B, N]
   float* dF;       // [B, N, Kp] fp32: rinv_i * dL/df^_i without the pad column's term
+  float* dM;       // kDm: [B, Mp, Kp] fp32, zeroed by the caller: scale_j * dL/dm^_j of every frame (fp32 reductions)
   int Mp, B, N, M, KB, n_obj;
   float gamma_log2e, margin;
 };
 
-template <bool kExact>
+// kDm: the model-side product too.  After dF += G'' M_t the issuer computes the tile's own
+//   dM_t [128 vertices x d] = G''^T [vertices x rows] x F [rows x d]
+// with BOTH operands MN-major -- the G'' buffer read transposed (M = vertices contiguous, K = rows: LBO = the 16 KB stride
+// between its two 64-vertex blocks), the row tile read with N = d contiguous -- into a fourth 128-column accumulator;
+// the epilogue drains it one tile later with 16-byte fp32 reductions into the frame's dM (every row tile of the frame
+// adds to the same [M, d] array).  dL/dsim then never leaves the SM: G is not written.
+template <bool kExact, bool kDm>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 circle_df_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
                  const DfParams p) {
@@ -97,6 +107,8 @@ circle_df_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
     ptx::mbar_init(&bars->g_full, EPI_WARPS);
     ptx::mbar_init(&bars->g_free, 1);
     ptx::mbar_init(&bars->df_full, 1);
+    ptx::mbar_init(&bars->dm_full, 1);
+    ptx::mbar_init(&bars->dm_free, EPI_WARPS);
     ptx::fence_mbar_init();
   }
   if (warp == EPI_WARPS + 1) {
@@ -149,6 +161,10 @@ circle_df_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
       constexpr uint32_t B_LBO_K = 0x10000u;                                  // K-major: LBO unused (1)
       constexpr uint32_t B_LBO_MN = uint32_t(D_BLK_BYTES >> 4) << 16;          // MN-major: next 64-wide d block
       constexpr uint32_t D_DF = 2 * DBN;                                       // TMEM column of the dF accumulator
+      constexpr uint32_t D_DM = 3 * DBN;                                       // ... of the tile's dM accumulator
+      const uint32_t idesc_dm = idesc_df | (1u << 15);                         // A operand MN-major as well
+      const uint32_t g_lo_mn0 = (ptx::smem_u32(smem_g) & 0x3FFFF) >> 4;
+      const uint32_t a_lo_mn0 = (ptx::smem_u32(smem_a) & 0x3FFFF) >> 4;
       auto issue_df = [&](int u) {
         ptx::mbar_wait_sleep(&bars->g_full, uint32_t(u) & 1);
         ptx::tc_fence_after();
@@ -164,6 +180,20 @@ circle_df_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
               const uint32_t b_lo = (b_tile + uint32_t((vb * 64 + k * UMMA_K) * 128 >> 4)) | B_LBO_MN;
               ptx::umma_bf16_ss(D_DF, DESC_HI | a_lo, DESC_HI | b_lo, idesc_df, (u | part | vb | k) != 0);
             }
+        if (kDm) {
+          if (u >= 1) ptx::mbar_wait_sleep(&bars->dm_free, uint32_t(u - 1) & 1);   // the previous tile's product is drained
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int part = 0; part < 2; ++part)
+#pragma unroll
+            for (int k = 0; k < BM / UMMA_K; ++k) {     // K = the 128 rows of the tile, 16 (2048 bytes) per step
+              const uint32_t a_lo = (g_lo_mn0 + uint32_t(part * 2) * (G_BLK_BYTES >> 4) + uint32_t(k * UMMA_K * 128 >> 4)) |
+                                    (uint32_t(G_BLK_BYTES >> 4) << 16);
+              const uint32_t b_lo = (a_lo_mn0 + uint32_t(k * UMMA_K * 128 >> 4)) | (uint32_t(A_BLK_BYTES >> 4) << 16);
+              ptx::umma_bf16_ss(D_DM, DESC_HI | a_lo, DESC_HI | b_lo, idesc_dm, (part | k) != 0);
+            }
+          ptx::umma_commit(&bars->dm_full);
+        }
         ptx::umma_commit(&bars->g_free);
         ptx::umma_commit(&bars->empty[u % D_STAGES]);
       };
@@ -212,10 +242,33 @@ circle_df_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
     const float Ln = row_ok ? p.lse_n[grow] * 1.4426950408889634f : 0.f;
     const float wg = row_ok ? p.w[grow] * (gl * 0.6931471805599453f) : 0.f;     // w_i * gamma
     const float wgs = wg * rs;
-    float* grow_g = p.G + grow * size_t(p.Mp);
+    float* grow_g = kDm ? nullptr : p.G + grow * size_t(p.Mp);
     // G'' in shared memory: block (part, sub >> 1), row row_in_tile, 16-byte chunk ((sub & 1) * 4 + c * 2 + {0, 1}) ^ (row & 7)
     const uint32_t g_row = ptx::smem_u32(smem_g) + uint32_t(sub >> 1) * G_BLK_BYTES + uint32_t(row_in_tile) * 128;
     const uint32_t sw = uint32_t(row_in_tile & 7);
+
+    // kDm: tile u's model-side product: this thread holds vertex u * 128 + row_in_tile, d columns [sub * dcm, + dcm)
+    const int dcm = p.KB * BK / DSL;
+    auto drain_dm = [&](int u) {
+      ptx::mbar_wait_sleep(&bars->dm_full, uint32_t(u) & 1);
+      ptx::tc_fence_after();
+      const int vtx = u * DBN + row_in_tile;
+      float* dst = p.dM + (size_t(b) * p.Mp + size_t(min(vtx, p.Mp - 1))) * size_t(p.KB * BK) + sub * dcm;
+      for (int c0 = 0; c0 < dcm; c0 += 16) {
+        uint32_t d[16];
+        ptx::tmem_ld_32x16(lane_base + 3 * DBN + sub * dcm + c0, d);
+        ptx::tmem_ld_wait();
+        if (vtx < p.M) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4)
+            ptx::red_add_v4(dst + c0 + j4 * 4, __uint_as_float(d[j4 * 4]), __uint_as_float(d[j4 * 4 + 1]),
+                            __uint_as_float(d[j4 * 4 + 2]), __uint_as_float(d[j4 * 4 + 3]));
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars->dm_free);
+    };
 
     for (int t = 0; t < num_tiles; ++t) {
       const int acc = t & 1;
@@ -280,7 +333,7 @@ circle_df_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
           hw[e2] = __uint_as_float(h);
           lw[e2] = __uint_as_float(ptx::cvt_bf16x2(r1, r0));
         }
-        if (row_ok) {
+        if (!kDm && row_ok) {
           float* dst = grow_g + t * DBN + sub * DCS + c * 16;
 #pragma unroll
           for (int j8 = 0; j8 < 2; ++j8)
@@ -298,6 +351,7 @@ circle_df_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
         }
       }
       ptx::fence_proxy_async();          // the G'' stores must be visible to the tensor core's (async proxy) reads
+      if (kDm && t >= 1) drain_dm(t - 1);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -313,8 +367,9 @@ circle_df_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_con
       const float gp = in_mesh ? wg * ptx::ex2_approx(an * (s - m) * gl - Ln) * an
                                : wg * ptx::ex2_approx(-ap * (s - one_m) * gl - Lp) * -ap;
       p.g_pad[grow] = gp;
-      for (int j = p.M; j < p.Mp; ++j) grow_g[j] = 0.f;
+      if (!kDm) for (int j = p.M; j < p.Mp; ++j) grow_g[j] = 0.f;
     }
+    if (kDm) drain_dm(num_tiles - 1);
     // ---- dF: this thread's row, d columns [sub * (Kp / 4), +Kp / 4)
     ptx::mbar_wait_sleep(&bars->df_full, 0);
     ptx::tc_fence_after();
@@ -351,9 +406,13 @@ inline size_t circle_df_smem_bytes(int KB) {
 }  // namespace
 
 int circle_df_configure() {
-  cudaError_t e = cudaFuncSetAttribute(circle_df_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(circle_df_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
-  e = cudaFuncSetAttribute(circle_df_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(circle_df_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(circle_df_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaFuncSetAttribute(circle_df_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return set_cuda_error(e);
   return GADM_OK;
 }
@@ -364,12 +423,12 @@ int circle_df_launch(const void* rows, const float* rinv_rows, const float* pad_
                      const float* planes_frame, const int64_t* match_idx, const int64_t* match_idx2,
                      const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma, float margin,
                      const float* lse_p, const float* lse_n, const float* w, float* G, int Mp, float* g_pad, float* dF,
-                     cudaStream_t stream) {
+                     float* dM, cudaStream_t stream) {
   if (!circle_df_supported(Kp)) return GADM_ERR_UNSUPPORTED;
   DfParams p;
   p.rinv_rows = rinv_rows; p.pad_sim = pad_sim; p.scales = aux_scales(aux, n_obj, M); p.planes = planes_frame;
   p.xyz = aux_xyz(aux, n_obj, M); p.match_idx = match_idx; p.match_idx2 = match_idx2; p.obj_id = obj_id;
-  p.lse_p = lse_p; p.lse_n = lse_n; p.w = w; p.G = G; p.g_pad = g_pad; p.dF = dF; p.Mp = Mp;
+  p.lse_p = lse_p; p.lse_n = lse_n; p.w = w; p.G = G; p.g_pad = g_pad; p.dF = dF; p.dM = dM; p.Mp = Mp;
   p.B = B; p.N = N; p.M = M; p.KB = Kp / BK; p.n_obj = n_obj;
   p.gamma_log2e = gamma * 1.4426950408889634f; p.margin = margin;
   CUtensorMap tmap_rows, tmap_cols;
@@ -379,8 +438,13 @@ int circle_df_launch(const void* rows, const float* rinv_rows, const float* pad_
   if (rc != GADM_OK) return rc;
   dim3 grid((N + BM - 1) / BM, B);
   const size_t smem = circle_df_smem_bytes(p.KB);
-  if (match_idx2 != nullptr) circle_df_kernel<true><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
-  else circle_df_kernel<false><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+  if (dM != nullptr) {
+    if (match_idx2 != nullptr) circle_df_kernel<true, true><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+    else circle_df_kernel<false, true><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+  } else {
+    if (match_idx2 != nullptr) circle_df_kernel<true, false><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+    else circle_df_kernel<false, false><<<grid, NUM_THREADS, smem, stream>>>(tmap_rows, tmap_cols, p);
+  }
   return check_launch();
 }
 

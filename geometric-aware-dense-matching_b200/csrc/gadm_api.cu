@@ -308,10 +308,10 @@ int gadm_circle_loss_bwd_fused(const void* rows, const float* rinv_rows, const f
                                const float* aux, const float* planes_frame, const int64_t* match_idx,
                                const int64_t* match_idx2, const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj,
                                float gamma, float margin, const float* lse_p, const float* lse_n, const float* w,
-                               void* G2, int Mp, float* g_pad, float* dF, gadm_stream_t stream) {
+                               void* G2, int Mp, float* g_pad, float* dF, float* dM, gadm_stream_t stream) {
   GADM_REQUIRE_INIT();
-  if (!rows || !rinv_rows || !pad_sim || !cols || !aux || !planes_frame || !match_idx || !lse_p || !lse_n || !w || !G2 ||
-      !g_pad || !dF)
+  if (!rows || !rinv_rows || !pad_sim || !cols || !aux || !planes_frame || !match_idx || !lse_p || !lse_n || !w ||
+      (!G2 && !dM) || !g_pad || !dF)
     return GADM_ERR_BAD_ARG;
   if (B <= 0 || N <= 0 || M <= 0 || Kp <= 0 || n_obj <= 0) return GADM_ERR_BAD_ARG;
   if (B > 65535 || M % 8 != 0 || !circle_df_supported(Kp)) return GADM_ERR_UNSUPPORTED;
@@ -320,10 +320,11 @@ int gadm_circle_loss_bwd_fused(const void* rows, const float* rinv_rows, const f
   if (!(margin >= 0.f && margin < 1.f) || !(gamma > 0.f)) return GADM_ERR_BAD_ARG;
   if (gamma * (2.f + margin) * (2.f - margin) * 1.4426950408889634f > 120.f) return GADM_ERR_UNSUPPORTED;
   if (!aligned16(rows) || !aligned16(cols) || !aligned16(aux) || !aligned16(planes_frame) ||
-      (reinterpret_cast<uintptr_t>(G2) & 31) != 0 || (reinterpret_cast<uintptr_t>(dF) & 31) != 0)
+      (reinterpret_cast<uintptr_t>(G2) & 31) != 0 || (reinterpret_cast<uintptr_t>(dF) & 31) != 0 ||
+      (reinterpret_cast<uintptr_t>(dM) & 15) != 0)
     return GADM_ERR_ALIGN;
   return circle_df_launch(rows, rinv_rows, pad_sim, cols, aux, planes_frame, match_idx, match_idx2, obj_id, B, N, M, Kp,
-                          n_obj, gamma, margin, lse_p, lse_n, w, static_cast<float*>(G2), Mp, g_pad, dF,
+                          n_obj, gamma, margin, lse_p, lse_n, w, static_cast<float*>(G2), Mp, g_pad, dF, dM,
                           (cudaStream_t)stream);
 }
 

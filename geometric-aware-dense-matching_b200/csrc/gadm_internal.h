@@ -39,7 +39,7 @@ int circle_df_launch(const void* rows, const float* rinv_rows, const float* pad_
                      const float* planes_frame, const int64_t* match_idx, const int64_t* match_idx2,
                      const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma, float margin,
                      const float* lse_p, const float* lse_n, const float* w, float* G, int Mp, float* g_pad, float* dF,
-                     cudaStream_t stream);
+                     float* dM, cudaStream_t stream);
 int match_launch(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols, const float* aux,
                  const uint8_t* mask, const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj, float gamma,
                  int pad_mode, int mode, int64_t* idx, float* max_sim, float* weight, float* soft_xyz,

@@ -355,6 +355,10 @@ __device__ __forceinline__ void stg_pred32(bool pred, void* gaddr, uint64_t v0, 
       : "memory");
 }
 // 32-byte global store (sm_100: STG.256); gaddr 32-byte aligned
+// fp32 reduction into global memory, 16 bytes at a time (sm_90+), no return value
+__device__ __forceinline__ void red_add_v4(float* gaddr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gaddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void sts128(uint32_t saddr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }

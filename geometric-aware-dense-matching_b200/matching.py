@@ -141,8 +141,8 @@ class _CircleMatchLoss(torch.autograd.Function):
         B, N, d = rows.shape
         n_obj, M, _ = cols.shape
         w = (torch.sigmoid(lse_p + lse_n) * row_w * g_total).contiguous()            # softplus' = sigmoid
-        if ctx.grad_gemm in ("bf16x2", "fused"):
-            return _circle_backward_split(ctx, w, fused=ctx.grad_gemm == "fused")
+        if ctx.grad_gemm in ("bf16x2", "fused", "flash"):
+            return _circle_backward_split(ctx, w, fused={"bf16x2": 0, "fused": 1, "flash": 2}[ctx.grad_gemm])
         G = ops.circle_loss_bwd(rows, rinv, pad_sim, cols, aux, planes, mi, ctx.oid, gamma, margin, lse_p, lse_n,
                                 w, ctx.mi2)                                          # [B, N, M + 8]
         f_hat = rows.float() * rinv[..., None]                                       # [B, N, d]
@@ -169,7 +169,7 @@ class _CircleMatchLoss(torch.autograd.Function):
                 None, None, None, None, None, None)
 
 
-def _circle_backward_split(ctx, w, fused=False):
+def _circle_backward_split(ctx, w, fused=0):
     """grad_gemm = "bf16x2": dL/dsim leaves the kernel with both norms folded in and split into two bf16 parts
     (gadm_circle_loss_bwd_split), so the two gradient products run as bf16 tensor-core GEMMs with fp32 accumulation
     on the forward pass's own bf16 operands -- exact products, 16 mantissa bits of G (tf32 keeps 10 of G AND rounds the
@@ -180,19 +180,23 @@ def _circle_backward_split(ctx, w, fused=False):
     n_obj, M, _ = cols.shape
     Mp = M + 8
     dev = rows.device
-    dF = None
-    if fused and rows.shape[2] <= 128:      # the scene-side product inside the kernel (second MMA per model tile)
-        G2, g_pad, dF = ops.circle_loss_bwd_fused(rows, rinv, pad_sim, cols, aux, planes, mi, ctx.oid, gamma, margin,
-                                                  lse_p, lse_n, w, ctx.mi2)
+    dF = dMb = None
+    if fused == 2 and rows.shape[2] <= 128:   # both gradient products inside the kernel: dL/dsim never leaves the SM
+        _, g_pad, dF, dMb = ops.circle_loss_bwd_fused(rows, rinv, pad_sim, cols, aux, planes, mi, ctx.oid, gamma, margin,
+                                                      lse_p, lse_n, w, ctx.mi2, True)
+    elif fused == 1 and rows.shape[2] <= 128:  # the scene-side product inside the kernel, the model-side one a GEMM
+        G2, g_pad, dF, _ = ops.circle_loss_bwd_fused(rows, rinv, pad_sim, cols, aux, planes, mi, ctx.oid, gamma, margin,
+                                                     lse_p, lse_n, w, ctx.mi2, False)
     else:
         G2, g_pad = ops.circle_loss_bwd_split(rows, rinv, pad_sim, cols, aux, planes, mi, ctx.oid, gamma, margin, lse_p,
                                               lse_n, w, ctx.mi2)                     # [B, N, 2 Mp] bf16, [B, N]
-    k = torch.arange(2 * Mp, device=dev)
-    col_of_k = (k // 16) * 8 + k % 8                                                 # K2 of gadm.h
-    cols_p = torch.zeros((n_obj, Mp, d), dtype=torch.bfloat16, device=dev)
-    cols_p[:, :M] = cols
-    cols2 = cols_p[:, col_of_k]                                                      # [n_obj, 2 Mp, d]
     scale = aux[: n_obj * M].view(n_obj, M, 1)
+    if dF is None:
+        k = torch.arange(2 * Mp, device=dev)
+        col_of_k = (k // 16) * 8 + k % 8                                             # K2 of gadm.h
+        cols_p = torch.zeros((n_obj, Mp, d), dtype=torch.bfloat16, device=dev)
+        cols_p[:, :M] = cols
+        cols2 = cols_p[:, col_of_k]                                                  # [n_obj, 2 Mp, d]
     m_pad = torch.zeros((d,), dtype=torch.float32, device=dev)
     if pad_mode == "minus_one":
         m_pad[:] = -(d ** -0.5)
@@ -201,8 +205,11 @@ def _circle_backward_split(ctx, w, fused=False):
     if dF is None:
         dF = torch.bmm(G2, cols2[sel], out_dtype=torch.float32)
     d_fhat = dF / rinv[..., None] + g_pad[..., None] * m_pad
-    t = torch.bmm(G2.transpose(1, 2), rows, out_dtype=torch.float32)                 # [B, 2 Mp, d]
-    d_mhat_b = t.view(B, Mp // 8, 2, 8, d).sum(2).reshape(B, Mp, d)[:, :M]           # hi + lo
+    if dMb is None:
+        t = torch.bmm(G2.transpose(1, 2), rows, out_dtype=torch.float32)             # [B, 2 Mp, d]
+        d_mhat_b = t.view(B, Mp // 8, 2, 8, d).sum(2).reshape(B, Mp, d)[:, :M]       # hi + lo
+    else:
+        d_mhat_b = dMb[:, :M]
     d_mhat = torch.zeros((n_obj, M, d), dtype=torch.float32, device=dev).index_add_(0, sel, d_mhat_b) / scale
     f_hat = rows.float() * rinv[..., None]
     mh = cols.float() * scale
@@ -235,14 +242,16 @@ def circle_match_loss(rgbd, mesh, labels, match_idx, visible_flag, positive_r, m
     the largest entry instead of ~1e-6); "bf16x2": dL/dsim leaves the kernel split into two bf16 parts with both norms
     folded in and the products run as bf16 tensor-core GEMMs on the forward pass's own bf16 operands (exact products,
     16 mantissa bits of dL/dsim: more accurate than tf32 and faster than fp32); "fused": as "bf16x2", with the
-    scene-side product accumulated inside the kernel by a second MMA per model tile (d <= 128; falls back to "bf16x2").
+    scene-side product accumulated inside the kernel by a second MMA per model tile (fastest accurate path); "flash":
+    the model-side product inside the kernel as well (third MMA per tile, fp32 reductions into global memory): nothing
+    of size [N, M] exists at any time, 10 % slower than "fused".  Both need d <= 128 and fall back to "bf16x2".
     sys_idx (int [>= N], or None): the symmetry-aware variant GeoMatch.matching_loss_sys (models/geoMatch.py:86-100, used
     when model_emb.sys_corr_idx is set, :138-141): the positives of scene point n are exactly the two columns
     match_idx[n] and match_idx[sys_idx[n]] -- no radius, no visibility (positive_r / visible_flag are ignored).
     Returns the scalar the reference returns: the mean over samples with >= 3 foreground rows of the mean row loss
     (0 if there is none); return_rows=True adds the per-row (loss, lse_p, lse_n) tensors."""
-    if grad_gemm not in ("fp32", "tf32", "bf16x2", "fused"):
-        raise ValueError("grad_gemm must be 'fp32', 'tf32', 'bf16x2' or 'fused'")
+    if grad_gemm not in ("fp32", "tf32", "bf16x2", "fused", "flash"):
+        raise ValueError("grad_gemm must be 'fp32', 'tf32', 'bf16x2', 'fused' or 'flash'")
     if isinstance(mesh, ModelBank):
         bank = mesh
         if bank.operand_mode != "bf16":

@@ -394,10 +394,12 @@ def _(rows, rinv, pad_sim, cols, aux, planes_frame, match_idx, obj_id, gamma, ma
 def circle_loss_bwd_fused(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch.Tensor, cols: torch.Tensor,
                           aux: torch.Tensor, planes_frame: torch.Tensor, match_idx: torch.Tensor,
                           obj_id: torch.Tensor | None, gamma: float, margin: float, lse_p: torch.Tensor,
-                          lse_n: torch.Tensor, w: torch.Tensor,
-                          match_idx2: torch.Tensor | None = None) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """(G2, g_pad, dF): circle_loss_bwd_split plus dF [B, N, K'] fp32 = sum_j G''_ij cols_j, accumulated in tensor memory
-    by a second MMA inside the kernel (gadm_circle_loss_bwd_fused; K' <= 128)."""
+                          lse_n: torch.Tensor, w: torch.Tensor, match_idx2: torch.Tensor | None = None,
+                          model_side: bool = False) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(G2, g_pad, dF, dM) of gadm_circle_loss_bwd_fused (K' <= 128): dF [B, N, K'] fp32 = sum_j G''_ij cols_j, accumulated
+    in tensor memory by a second MMA inside the kernel.  model_side=False: G2 as circle_loss_bwd_split, dM empty.
+    model_side=True: dM [B, M + 8, K'] fp32 = sum_i G''_ij rows_i formed in the kernel as well (third MMA per model tile,
+    fp32 reductions into global memory); G2 is not written (empty)."""
     _need(rows, torch.bfloat16, "rows"); _need(cols, torch.bfloat16, "cols")
     for t, n in ((rinv, "rinv"), (pad_sim, "pad_sim"), (aux, "aux"), (planes_frame, "planes_frame"), (lse_p, "lse_p"),
                  (lse_n, "lse_n"), (w, "w")):
@@ -406,25 +408,31 @@ def circle_loss_bwd_fused(rows: torch.Tensor, rinv: torch.Tensor, pad_sim: torch
     B, N, kp = rows.shape
     n_obj, M, _ = cols.shape
     Mp = M + 8
-    G2 = torch.empty((B, N, 2 * Mp), dtype=torch.bfloat16, device=rows.device)
-    g_pad = torch.empty((B, N), dtype=torch.float32, device=rows.device)
-    dF = torch.empty((B, N, kp), dtype=torch.float32, device=rows.device)
+    dev = rows.device
+    G2 = torch.empty((0,) if model_side else (B, N, 2 * Mp), dtype=torch.bfloat16, device=dev)
+    dM = torch.zeros((B, Mp, kp), dtype=torch.float32, device=dev) if model_side else \
+        torch.empty((0,), dtype=torch.float32, device=dev)
+    g_pad = torch.empty((B, N), dtype=torch.float32, device=dev)
+    dF = torch.empty((B, N, kp), dtype=torch.float32, device=dev)
     lib = _lib_for(rows)
-    with torch.cuda.device(rows.device):
+    with torch.cuda.device(dev):
         _lib.check(lib.gadm_circle_loss_bwd_fused(_ptr(rows), _ptr(rinv), _ptr(pad_sim), _ptr(cols), _ptr(aux),
                                                   _ptr(planes_frame), _ptr(match_idx), _ptr(match_idx2), _ptr(obj_id),
                                                   B, N, M, kp, n_obj, float(gamma), float(margin), _ptr(lse_p),
-                                                  _ptr(lse_n), _ptr(w), _ptr(G2), Mp, _ptr(g_pad), _ptr(dF), _stream()),
+                                                  _ptr(lse_n), _ptr(w), None if model_side else _ptr(G2), Mp,
+                                                  _ptr(g_pad), _ptr(dF), _ptr(dM) if model_side else None, _stream()),
                    "gadm_circle_loss_bwd_fused")
-    return G2, g_pad, dF
+    return G2, g_pad, dF, dM
 
 
 @circle_loss_bwd_fused.register_fake
 def _(rows, rinv, pad_sim, cols, aux, planes_frame, match_idx, obj_id, gamma, margin, lse_p, lse_n, w,
-      match_idx2=None):
+      match_idx2=None, model_side=False):
     B, N, kp = rows.shape
-    return (rows.new_empty((B, N, 2 * (cols.shape[1] + 8)), dtype=torch.bfloat16),
-            rows.new_empty((B, N), dtype=torch.float32), rows.new_empty((B, N, kp), dtype=torch.float32))
+    Mp = cols.shape[1] + 8
+    return (rows.new_empty((0,) if model_side else (B, N, 2 * Mp), dtype=torch.bfloat16),
+            rows.new_empty((B, N), dtype=torch.float32), rows.new_empty((B, N, kp), dtype=torch.float32),
+            rows.new_empty((B, Mp, kp) if model_side else (0,), dtype=torch.float32))
 
 
 @torch.library.custom_op("gadm::kabsch_moments", mutates_args=(), device_types="cuda")

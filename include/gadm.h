@@ -236,13 +236,18 @@ int gadm_circle_loss_bwd_split(const void* rows, const float* rinv_rows, const f
  * G'' the epilogue has just formed goes to shared memory as the A operand of a second tcgen05 MMA against the model tile
  * that is already resident (read as an MN-major B operand), accumulated over the model tiles in tensor memory:
  *   dF [B, N, K'] fp32 (32-byte aligned) = sum_j G''[b, i, j] * cols[j]  =  rinv_i * (dL/df^_i - g_pad_i * m^_pad)
- * G2 and g_pad are written as by gadm_circle_loss_bwd_split (the model-side product G''^T rows stays a library GEMM).
+ * dM == NULL: G2 and g_pad are written as by gadm_circle_loss_bwd_split (the model-side product G''^T rows is a library
+ *   GEMM on the caller's side).
+ * dM != NULL ([B, Mp, K'] fp32, 16-byte aligned, ZEROED by the caller): the model-side product is formed in the kernel
+ *   too -- per model tile a third MMA G''^T x rows (both operands read MN-major from the buffers already in shared
+ *   memory), added to dM[b] with fp32 reductions (the order of the additions, hence the last bits, varies from run to
+ *   run): dM[b, j] = scale_j * dL/dm^_j of frame b.  dL/dsim then never leaves the SM: G2 is not written (may be NULL).
  * GADM_ERR_UNSUPPORTED for K' > 128.                                                                                */
 int gadm_circle_loss_bwd_fused(const void* rows, const float* rinv_rows, const float* pad_sim, const void* cols,
                                const float* aux, const float* planes_frame, const int64_t* match_idx,
                                const int64_t* match_idx2, const int32_t* obj_id, int B, int N, int M, int Kp, int n_obj,
                                float gamma, float margin, const float* lse_p, const float* lse_n, const float* w,
-                               void* G2, int Mp, float* g_pad, float* dF, gadm_stream_t stream);
+                               void* G2, int Mp, float* g_pad, float* dF, float* dM, gadm_stream_t stream);
 
 /* Backward passes of the gathers: the reference's torch.gather / max / cat are differentiable in the features
  * (models/dgcnn.py:41-54, models/RandLA/RandLANet.py:90-120, :729-738) and sit inside the trained networks.  Each zeroes

@@ -151,7 +151,7 @@ def test_circle_loss_bwd_split_is_the_fp32_gradient_with_the_norms_folded_in(cud
 
 @pytest.mark.parametrize("B,N,M,d,sys2", [(2, 333, 520, 64, False), (1, 700, 1000, 128, False), (2, 130, 264, 128, True),
                                           (1, 1300, 8192, 128, False)])
-def test_circle_loss_bwd_fused_dF_matches_the_library_product(cuda, B, N, M, d, sys2):
+def test_circle_loss_bwd_fused_products_match_the_library_products(cuda, B, N, M, d, sys2):
     """gadm_circle_loss_bwd_fused: G2 and g_pad bit-identical to gadm_circle_loss_bwd_split, and dF -- the second MMA of
     the kernel, G'' from shared memory against the resident model tile read MN-major -- equal to the same product
     computed from G2 by a library GEMM (fp32 accumulation in both, in different orders over 2 (M + 8) terms: 5e-5 of
@@ -173,7 +173,7 @@ def test_circle_loss_bwd_fused_dF_matches_the_library_product(cuda, B, N, M, d, 
     _, lp, ln = ops.circle_loss_fwd(rows, rinv, pad_sim, cols, aux, planes, mi, fg, None, 16.0, 0.2, mi2)
     w = torch.rand((B, N), generator=g).to(cuda)
     G2, g_pad = ops.circle_loss_bwd_split(rows, rinv, pad_sim, cols, aux, planes, mi, None, 16.0, 0.2, lp, ln, w, mi2)
-    G2f, g_padf, dF = ops.circle_loss_bwd_fused(rows, rinv, pad_sim, cols, aux, planes, mi, None, 16.0, 0.2, lp, ln, w, mi2)
+    G2f, g_padf, dF, _ = ops.circle_loss_bwd_fused(rows, rinv, pad_sim, cols, aux, planes, mi, None, 16.0, 0.2, lp, ln, w, mi2)
     assert torch.equal(G2.view(torch.int16), G2f.view(torch.int16)) and torch.equal(g_pad, g_padf)
     Mp = M + 8
     k = torch.arange(2 * Mp, device=cuda)
@@ -184,9 +184,20 @@ def test_circle_loss_bwd_fused_dF_matches_the_library_product(cuda, B, N, M, d, 
     err = (dF - want).abs().max()
     assert float(want.abs().max()) > 0
     assert err <= 5e-5 * want.abs().max(), f"dF max err {float(err)} vs max {float(want.abs().max())}"
+    # model_side=True: the model-side product in the kernel as well (third MMA, both operands MN-major, fp32 reductions
+    # over the row tiles of a frame); dL/dsim is not written at all
+    G0, g_padm, dFm, dM = ops.circle_loss_bwd_fused(rows, rinv, pad_sim, cols, aux, planes, mi, None, 16.0, 0.2, lp, ln, w,
+                                                    mi2, True)
+    assert G0.numel() == 0 and torch.equal(g_padm, g_pad) and torch.equal(dFm, dF)
+    t = torch.bmm(G2.transpose(1, 2), rows, out_dtype=torch.float32)
+    want_m = t.view(B, Mp // 8, 2, 8, d).sum(2).reshape(B, Mp, d)
+    assert dM.shape == (B, Mp, d) and float(dM[:, M:].abs().max()) == 0.0
+    errm = (dM - want_m).abs().max()
+    assert float(want_m.abs().max()) > 0
+    assert errm <= 5e-5 * want_m.abs().max(), f"dM max err {float(errm)} vs max {float(want_m.abs().max())}"
 
 
-@pytest.mark.parametrize("grad_gemm,gate", [("fp32", 1e-3), ("tf32", 3e-3), ("bf16x2", 1e-3), ("fused", 1e-3)])
+@pytest.mark.parametrize("grad_gemm,gate", [("fp32", 1e-3), ("tf32", 3e-3), ("bf16x2", 1e-3), ("fused", 1e-3), ("flash", 1e-3)])
 def test_circle_loss_gradients_vs_autograd_of_the_reference_math(cuda, grad_gemm, gate):
     """d loss / d rgbd and d loss / d mesh against torch autograd through the oracle (the reference's own formulas,
     ap / an detached as at loss.py:479-480) on the CPU.  Gate: 1e-3 of the largest gradient entry (3e-3 when the two

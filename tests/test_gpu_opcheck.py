@@ -82,6 +82,8 @@ def _cases(dev):
                                    torch.ones((B, N), device=dev)), BASIC),
         ("circle_loss_bwd_fused", (rows_p, rinv_p, pad_p, cols, aux, planes, mi, obj, 16.0, 0.25, lse_p, lse_n,
                                    torch.ones((B, N), device=dev)), BASIC),
+        ("circle_loss_bwd_fused", (rows_p, rinv_p, pad_p, cols, aux, planes, mi, obj, 16.0, 0.25, lse_p, lse_n,
+                                   torch.ones((B, N), device=dev), None, True), BASIC),
     ]
 
 

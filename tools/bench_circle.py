@@ -109,15 +109,25 @@ def fused_fwd_bwd_fused():
 
 
 k_fused = timed(lambda: ops.circle_loss_bwd_fused(rows, rinv, pad_sim, cols, aux, planes, match_idx, None, 16.0, 0.2, lp_, ln_, w))
-print(f"circle_df_kernel (grad + fused dF)          {k_fused:.3f} ms")
-print(f"fused forward + backward (fused dF, bf16x2 dM GEMM) {timed(fused_fwd_bwd_fused, 3):.3f} ms")
+print(f"circle_df_kernel<dF> (G2 written)           {k_fused:.3f} ms")
+k_full = timed(lambda: ops.circle_loss_bwd_fused(rows, rinv, pad_sim, cols, aux, planes, match_idx, None, 16.0, 0.2, lp_, ln_, w, None, True))
+print(f"circle_df_kernel<dF, dM> (no G at all)      {k_full:.3f} ms")
+print(f"fused forward + backward (grad_gemm='fused': dF in the kernel, dM a GEMM) {timed(fused_fwd_bwd_fused, 3):.3f} ms")
+
+
+def fused_fwd_bwd_flash():
+    rg.grad = me.grad = None
+    matching.circle_match_loss(rg, me, labels, match_idx, vis, r, model_xyz=xyz, grad_gemm="flash").backward()
+
+
+print(f"fused forward + backward (grad_gemm='flash': both products in the kernel) {timed(fused_fwd_bwd_flash, 3):.3f} ms")
 # accuracy of the gradient paths against the fp32 library GEMMs
 grads = {}
-for mode in ("fp32", "tf32", "bf16x2", "fused"):
+for mode in ("fp32", "tf32", "bf16x2", "fused", "flash"):
     rg.grad = me.grad = None
     matching.circle_match_loss(rg, me, labels, match_idx, vis, r, model_xyz=xyz, grad_gemm=mode).backward()
     grads[mode] = (rg.grad.clone(), me.grad.clone())
-for mode in ("tf32", "bf16x2", "fused"):
+for mode in ("tf32", "bf16x2", "fused", "flash"):
     e = [float((grads[mode][i] - grads["fp32"][i]).abs().max() / grads["fp32"][i].abs().max()) for i in range(2)]
     print(f"max |grad - grad_fp32| / max |grad_fp32|, {mode:7s}: d rgbd {e[0]:.2e}   d mesh {e[1]:.2e}")
 print(f"torch materialised forward                  {timed(lambda: torch_materialised(False), 3):.3f} ms")
