@@ -30,5 +30,20 @@ for _ in range(reps):
         ops.match_fwd(rows, rinv, pad, cols_n, aux_n, None, obj, 16.0, 0, MATCH_MODES["argmax_unit"])
     if what in ("all", "knn"):
         pyr.run_packed(pts)
+if what == "circle":     # CircleLoss kernels: forward, dL/dsim (fp32 / split bf16), fused dF, fused dF + dM
+    M8 = M
+    planes = torch.empty((4, B, M8), device=dev)
+    planes[:3] = xyz[0].t()[:, None, :].expand(3, B, M8)
+    planes[3] = 0.006 ** 2
+    rows1, rinv1, pad1 = ops.prep_rows(rgbd.to(dev), 0, 1)
+    mi = torch.randint(0, M8, (B, N), generator=torch.Generator().manual_seed(1)).to(dev)
+    fg = torch.ones((B, N), dtype=torch.uint8, device=dev)
+    w = torch.full((B, N), 1.0 / (B * N), device=dev)
+    for _ in range(reps):
+        _, lp_, ln_ = ops.circle_loss_fwd(rows1, rinv1, pad1, cols, aux, planes, mi, fg, obj, 16.0, 0.2)
+        ops.circle_loss_bwd(rows1, rinv1, pad1, cols, aux, planes, mi, obj, 16.0, 0.2, lp_, ln_, w)
+        ops.circle_loss_bwd_split(rows1, rinv1, pad1, cols, aux, planes, mi, obj, 16.0, 0.2, lp_, ln_, w)
+        ops.circle_loss_bwd_fused(rows1, rinv1, pad1, cols, aux, planes, mi, obj, 16.0, 0.2, lp_, ln_, w)
+        ops.circle_loss_bwd_fused(rows1, rinv1, pad1, cols, aux, planes, mi, obj, 16.0, 0.2, lp_, ln_, w, None, True)
 torch.cuda.synchronize()
 print("done")
