@@ -150,7 +150,7 @@ def test_circle_loss_bwd_split_is_the_fp32_gradient_with_the_norms_folded_in(cud
 
 
 @pytest.mark.parametrize("B,N,M,d,sys2", [(2, 333, 520, 64, False), (1, 700, 1000, 128, False), (2, 130, 264, 128, True),
-                                          (1, 1300, 8192, 128, False)])
+                                          (1, 1300, 8192, 128, False), (3, 50, 72, 64, False), (1, 128, 128, 128, True)])
 def test_circle_loss_bwd_fused_products_match_the_library_products(cuda, B, N, M, d, sys2):
     """gadm_circle_loss_bwd_fused: G2 and g_pad bit-identical to gadm_circle_loss_bwd_split, and dF -- the second MMA of
     the kernel, G'' from shared memory against the resident model tile read MN-major -- equal to the same product
