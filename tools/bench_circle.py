@@ -39,7 +39,7 @@ def fused_fwd():
 
 def fused_fwd_bwd():
     rg.grad = me.grad = None
-    matching.circle_match_loss(rg, me, labels, match_idx, vis, r, model_xyz=xyz).backward()
+    matching.circle_match_loss(rg, me, labels, match_idx, vis, r, model_xyz=xyz, grad_gemm="fp32").backward()
 
 
 def torch_materialised(backward):
@@ -84,7 +84,7 @@ flop = 2.0 * N * M * D * B
 print(f"circle_kernel<fwd>  {k_fwd:.3f} ms  ({flop / k_fwd / 1e9:.0f} TFLOP/s of similarity)   "
       f"circle_kernel<grad> {k_bwd:.3f} ms (writes {B * N * (M + 8) * 4 / 1e9:.2f} GB: {B * N * (M + 8) * 4 / k_bwd / 1e6:.0f} GB/s)")
 print(f"fused forward (prep + kernel + reduction)   {timed(fused_fwd):.3f} ms")
-print(f"fused forward + backward                    {timed(fused_fwd_bwd, 3):.3f} ms")
+print(f"fused forward + backward (fp32 grad GEMMs)  {timed(fused_fwd_bwd, 3):.3f} ms")
 
 
 def fused_fwd_bwd_tf32():
