@@ -9,9 +9,10 @@
  *       utils/pvn3d_eval_utils_kpls.py:436-444, models/geoMatch.py:117-119   "-1" pad column variant
  *       models/geoMatch_DGCNN.py:92-99                                       "e0" pad column variant
  *       (+ the soft-correspondence extension: softmax weights and soft model coordinates)
- *   gadm_circle_loss_fwd / gadm_circle_loss_bwd
+ *   gadm_circle_loss_fwd / gadm_circle_loss_bwd / gadm_circle_loss_bwd_split / gadm_circle_loss_bwd_fused
  *       models/geoMatch.py:55-83, 102-157 (geoMatch_DGCNN.py:53-78, 80-136) + models/loss.py:475-490
- *       pointwise_feature_matching + matching_loss + CircleLoss.forward, and dL/dsim for its backward pass
+ *       pointwise_feature_matching + matching_loss + CircleLoss.forward, and its backward pass: dL/dsim as fp32, as two
+ *       bf16 parts for tensor-core gradient products, or with the gradient products formed inside the kernel
  *   gadm_seg_mask
  *       evaluator.py:78,82            seg argmax -> foreground mask
  *   gadm_kabsch_moments
