@@ -235,6 +235,47 @@ def test_circle_loss_gradients_vs_autograd_of_the_reference_math(cuda, grad_gemm
         assert wd.abs().max() > 0
 
 
+@pytest.mark.parametrize("variant", ["e0_per_vertex_radius", "sys", "two_objects"])
+@pytest.mark.parametrize("grad_gemm", ["bf16x2", "fused", "flash"])
+def test_circle_loss_backward_modes_agree_on_every_variant(cuda, variant, grad_gemm):
+    """The tensor-core / in-kernel gradient products against the fp32 library products (grad_gemm="fp32", itself gated
+    against torch autograd above) on the variants that test does not cover: the DGCNN variant (e0 pad column, per-vertex
+    radii), the symmetry-aware positives, a bank of two objects with per-frame object ids.  1e-3 of the largest entry."""
+    from gadm_b200 import matching, synth
+    B, N, M, d = 3, 420, 520, 128
+    g = torch.Generator().manual_seed(77)
+    n_obj = 2 if variant == "two_objects" else 1
+    mesh = synth.bf16_round(torch.randn((n_obj, d, M), generator=g))
+    xyz = torch.stack([synth.fibonacci_sphere(M, 0.2 - 0.03 * o) for o in range(n_obj)])
+    obj = [1, 0, 1] if n_obj == 2 else None
+    vis = torch.rand((B, M), generator=g) < 0.6
+    labels = (torch.rand((B, N), generator=g) < 0.6).long()
+    match_idx = torch.randint(0, M + 1, (B, N), generator=g)
+    rgbd = synth.bf16_round(torch.randn((B, d, N), generator=g))
+    kw = dict(model_xyz=xyz.to(cuda))
+    if obj is not None:
+        kw["obj_id"] = obj
+    if variant == "e0_per_vertex_radius":
+        kw["pad_mode"] = "e0"
+        radius = (0.02 + 0.03 * torch.rand((B, M), generator=g)).to(cuda)
+    else:
+        radius = 0.03
+    if variant == "sys":
+        kw["sys_idx"] = torch.randperm(N, generator=g).to(cuda)
+    grads = {}
+    for mode in ("fp32", grad_gemm):
+        a = rgbd.to(cuda).requires_grad_(True)
+        m = mesh.to(cuda).requires_grad_(True)
+        loss = matching.circle_match_loss(a, m, labels.to(cuda), match_idx.to(cuda), vis.to(cuda), radius, grad_gemm=mode, **kw)
+        loss.backward()
+        grads[mode] = (float(loss.detach()), a.grad.clone(), m.grad.clone())
+    assert grads["fp32"][0] == grads[grad_gemm][0] and grads["fp32"][0] > 0
+    for k in (1, 2):
+        ref, got = grads["fp32"][k], grads[grad_gemm][k]
+        assert float(ref.abs().max()) > 0
+        assert float((got - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
+
+
 def test_circle_loss_errors(cuda):
     from gadm_b200 import matching, synth, _lib
     rgbd, mesh, _ = synth.descriptors(1, 256, 256, 64, seed=3)
